@@ -1,0 +1,285 @@
+/*
+ * nqcb200.h -- C ABI of the B200 ensemble-trajectory engine.
+ *
+ * This is the drop-in boundary for NQCDynamics.jl's ensemble hot path.  The reference has NO
+ * FFI for this path (it is 100 % Julia); the seam these entry points replace is the call
+ *
+ *     SciMLBase.solve(ensemble_problem, algorithm, ensemble_algorithm; trajectories, kwargs...)
+ *                                              reference: src/Ensembles/run_dynamics.jl:91-97
+ *
+ * i.e. "step `trajectories` independent copies of one Simulation for nsteps of dt, evaluate the
+ * outputs at the save points, hand the per-trajectory (or reduced) outputs back".  A Julia
+ * `EnsembleB200 <: SciMLBase.EnsembleAlgorithm` binds these symbols with `@ccall` (stub in
+ * INTEGRATION.md); the Python mirror in `nqcdynamics.jl_b200/` binds them with ctypes.
+ *
+ * Conventions
+ *   - plain C, no torch / CUDA types in any signature; all pointers are HOST pointers unless the
+ *     function name ends in `_device`.
+ *   - the caller owns every host buffer; nothing is retained after a call returns.
+ *   - every function returns NQCB200_OK (0) or a negative error code; the message is available
+ *     from nqcb200_last_error().  No exception, abort or sticky CUDA error crosses the boundary.
+ *   - Host layout is the Julia layout, trajectory-major: for trajectory t
+ *         r, v   : (ndofs, natoms, nbeads) column-major  -> flat [dof + D*bead + D*B*t],  D = ndofs*natoms
+ *         sigma  : (nstates, nstates) column-major, real and imaginary parts separate
+ *                  (reference: SurfaceHoppingVariables.jl:10-25 sigma_real / sigma_imag)
+ *         psi    : (nstates, nelectrons) column-major (IESH; reference: iesh.jl:89-97)
+ *         qmap,pmap : (nstates, nbeads) column-major (NRPMD; reference: nrpmd.jl:47-65)
+ *     The library transposes to SoA ([field][component][trajectory]) on upload.
+ *   - State indices are 1-based on the host side, exactly as the reference stores them
+ *     (u.state as Float64, sim.method.state as Int; fssh.jl:53-63).
+ *   - There is NO CPU fallback: nqcb200_create fails with NQCB200_ERR_NO_DEVICE when no sm_100
+ *     class GPU is visible, and with NQCB200_ERR_UNSUPPORTED for (method, model, size)
+ *     combinations that have no kernel.
+ */
+#ifndef NQCB200_H
+#define NQCB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NQCB200_ABI_VERSION 1
+
+/* ---- error codes ------------------------------------------------------------------------- */
+#define NQCB200_OK               0
+#define NQCB200_ERR_INVALID     -1   /* bad argument / config                                   */
+#define NQCB200_ERR_UNSUPPORTED -2   /* no kernel for this (method, model, n, D, B) combination */
+#define NQCB200_ERR_NO_DEVICE   -3   /* no usable GPU (the library never computes on the CPU)   */
+#define NQCB200_ERR_CUDA        -4   /* CUDA runtime error, message holds cudaGetErrorString    */
+#define NQCB200_ERR_STATE       -5   /* call order violated (e.g. run before set_state)         */
+#define NQCB200_ERR_NOMEM       -6
+
+/* ---- dynamics method: reference type -> enum ---------------------------------------------- */
+/* Simulation{FSSH} + BABwithTsit5          fssh.jl:23-45, bab_electronics.jl:61-91
+ * RingPolymerSimulation{FSSH}+BCBwithTsit5 rpsh.jl:8-10,  bcb_electronics.jl:53-97   (nbeads>1)
+ * Simulation{Ehrenfest}                    ehrenfest.jl:27-41                        (+RP: nbeads>1)
+ * Simulation{AdiabaticIESH}+VerletwithElectronics  iesh.jl:26-87, verlet_with_electronics.jl:42-69
+ * RingPolymerSimulation{Classical}+BCB     classical.jl:40-86, bcb.jl:81-116         (RPMD)
+ *   (nbeads==1: Simulation{Classical} + VelocityVerlet, classical.jl:86)
+ * RingPolymerSimulation{NRPMD}+RingPolymerMInt  nrpmd.jl:34-45, ringpolymer_mint.jl:28-78     */
+enum nqcb200_method {
+    NQCB200_METHOD_FSSH      = 1,
+    NQCB200_METHOD_EHRENFEST = 2,
+    NQCB200_METHOD_IESH      = 3,
+    NQCB200_METHOD_CLASSICAL = 4,
+    NQCB200_METHOD_NRPMD     = 5
+};
+
+/* ---- analytic model Hamiltonians (NQCModels.jl, external to the reference tree) ------------ */
+/* params[] meaning per model (defaults are the NQCModels defaults):
+ *  TULLY_ONE   {a,b,c,d}           V11=sgn(q) a (1-exp(-b|q|)), V22=-V11, V12=c exp(-d q^2)
+ *  TULLY_TWO   {a,b,c,d,e}         V11=0, V22=-a exp(-b q^2)+e, V12=c exp(-d q^2)
+ *  TULLY_THREE {a,b,c}             V11=a, V22=-a, V12= b exp(c q) (q<0) | b (2-exp(-c q)) (q>=0)
+ *  DOUBLE_WELL {mass,omega,gamma,delta}  V11/22 = 1/2 m w^2 q^2 +- sqrt(2) gamma q, V12 = delta/2
+ *  SPIN_BOSON  {epsilon,delta}; bath_a=omega_j[D], bath_b=c_j[D]
+ *              V11/22 = +-(eps + sum c_j r_j) + sum 1/2 w_j^2 r_j^2, V12 = delta
+ *  THREE_STATE_MORSE {d1,d2,d3, alpha1..3, r1..3, c1..3, a12,a13,a23, alpha12,alpha13,alpha23,
+ *                     r12,r13,r23}  V_ii = d_i (1-exp(-alpha_i (q-r_i)))^2 + c_i,
+ *                                   V_ij = a_ij exp(-alpha_ij (q-r_ij)^2)
+ *  HARMONIC    {m,omega,r0}        classical, V = sum_dof 1/2 m w^2 (q-r0)^2
+ *  FREE        {}                  classical, V = 0
+ *  ANDERSON_HOLSTEIN_MIAO_SUBOTNIK {m,omega,g,DeltaG}; bath_a=eps_k[M], bath_b=V_k[M]
+ *              U0 = 1/2 m w^2 q^2 (state independent), h = U1-U0, U1 = 1/2 m w^2 (q-g)^2 + DeltaG
+ *              H[0,0]=h(q), H[k,k]=eps_k, H[0,k]=H[k,0]=V_k ; nstates = M+1   (iesh.md:71-76)      */
+enum nqcb200_model {
+    NQCB200_MODEL_TULLY_ONE         = 1,
+    NQCB200_MODEL_TULLY_TWO         = 2,
+    NQCB200_MODEL_TULLY_THREE       = 3,
+    NQCB200_MODEL_DOUBLE_WELL       = 4,
+    NQCB200_MODEL_SPIN_BOSON        = 5,
+    NQCB200_MODEL_THREE_STATE_MORSE = 6,
+    NQCB200_MODEL_HARMONIC          = 7,
+    NQCB200_MODEL_FREE              = 8,
+    NQCB200_MODEL_ANDERSON_HOLSTEIN_MIAO_SUBOTNIK = 9
+};
+
+/* frustrated-hop policy: surface_hopping.jl:65,79-91 */
+enum nqcb200_rescaling {
+    NQCB200_RESCALE_STANDARD   = 0,
+    NQCB200_RESCALE_VINVERSION = 1,
+    NQCB200_RESCALE_OFF        = 2
+};
+
+/* Random numbers for the hop test (reference: one rand() per trajectory per step,
+ * fssh.jl:112, iesh.jl:393).  PHILOX: counter-based Philox4x32-10 keyed by (seed; global
+ * trajectory id, step) -> results independent of sharding.  INJECTED: draws supplied by
+ * nqcb200_set_draws (parity mode, identical hop sequences in engine and oracle).              */
+enum nqcb200_rng {
+    NQCB200_RNG_PHILOX   = 0,
+    NQCB200_RNG_INJECTED = 1
+};
+
+/* ---- observables evaluated on the device at every save point ------------------------------ */
+/* Each maps to a reference output functor / estimator; `width` doubles per save point.
+ *  ADIABATIC_POP   n        Estimators.adiabatic_population  fssh.jl:144-148, ehrenfest.jl:70-73, iesh.jl:371-375
+ *  DIABATIC_POP    n        Estimators.diabatic_population   fssh.jl:132-142, ehrenfest.jl:75-83, iesh.jl:337-369, nrpmd.jl:111-122
+ *  POPCORR_DIABATIC  n*n    PopulationCorrelationFunction{Diabatic}  TimeCorrelationFunctions.jl:26-40,86-88
+ *                           out[i + n*j] = P_i(0) * P_j(t)
+ *  POPCORR_ADIABATIC n*n    PopulationCorrelationFunction{Adiabatic}
+ *  KINETIC         1        OutputKineticEnergy  DynamicsOutputs.jl:98  (DynamicsUtils.jl:108-135)
+ *  POTENTIAL       1        OutputPotentialEnergy :82 (classical_potential_energy per method)
+ *  TOTAL_ENERGY    1        OutputTotalEnergy :90 (classical_hamiltonian, includes RP spring energy)
+ *  POSITION        D        OutputPosition :39 / OutputCentroidPosition :47 for ring polymers
+ *  VELOCITY        D        OutputVelocity :66 / OutputCentroidVelocity :74
+ *  DISCRETE_STATE  1 (FSSH) / ne (IESH)   OutputDiscreteState :178
+ *  SCATTERING      2n       OutputStateResolvedScattering1D(:adiabatic) :313-338 -- final state only:
+ *                           [reflection(n), transmission(n)], transmission iff r[0] > 0
+ *  SCATTERING_DIABATIC 2n   same with type=:diabatic
+ *  SIGMA           2*n*n    OutputQuantumSubsystem :149 (re then im, column-major)                */
+enum nqcb200_observable {
+    NQCB200_OBS_ADIABATIC_POP       = 0,
+    NQCB200_OBS_DIABATIC_POP        = 1,
+    NQCB200_OBS_POPCORR_DIABATIC    = 2,
+    NQCB200_OBS_POPCORR_ADIABATIC   = 3,
+    NQCB200_OBS_KINETIC             = 4,
+    NQCB200_OBS_POTENTIAL           = 5,
+    NQCB200_OBS_TOTAL_ENERGY        = 6,
+    NQCB200_OBS_POSITION            = 7,
+    NQCB200_OBS_VELOCITY            = 8,
+    NQCB200_OBS_DISCRETE_STATE      = 9,
+    NQCB200_OBS_SCATTERING          = 10,
+    NQCB200_OBS_SCATTERING_DIABATIC = 11,
+    NQCB200_OBS_SIGMA               = 12,
+    NQCB200_OBS_COUNT               = 13
+};
+
+#define NQCB200_MAX_PARAMS 32
+
+/* Flat POD description of one ensemble run.  Mirrors what the reference spreads over
+ * Simulation / RingPolymerSimulation (simulations.jl:12-73), the method constructor kwargs
+ * (fssh.jl:41, iesh.jl:72-74, nrpmd.jl:43) and the run_dynamics kwargs (run_dynamics.jl:42-56). */
+typedef struct nqcb200_config {
+    int32_t  abi_version;       /* must be NQCB200_ABI_VERSION                                   */
+    int32_t  method;            /* enum nqcb200_method                                           */
+    int32_t  model;             /* enum nqcb200_model                                            */
+    int32_t  nstates;           /* n  (1 for classical models)                                   */
+    int32_t  ndofs;             /* D = ndofs*natoms, nuclear degrees of freedom per replica      */
+    int32_t  nbeads;            /* B  (1 = plain Simulation)                                     */
+    int32_t  nelectrons;        /* ne (IESH only)                                                */
+    int32_t  rescaling;         /* enum nqcb200_rescaling                                        */
+    int32_t  estimate_probability; /* IESH pruning, iesh.jl:251-254 (default 1)                  */
+    int32_t  disable_hopping;   /* IESH, iesh.jl:392                                             */
+    int32_t  rng;               /* enum nqcb200_rng                                              */
+    int32_t  device;            /* CUDA device ordinal this handle runs on                       */
+    int32_t  save_every;        /* save point every `save_every` steps (saveat = k*dt); >=1      */
+    int32_t  nsave;             /* capacity: number of save points incl. t0 (steps/save_every+1) */
+    int32_t  per_trajectory;    /* 0: observables summed over trajectories on device
+                                   1: additionally keep every trajectory's values (output stream) */
+    int32_t  diagnostics;       /* 1: keep eigenvalues / NAC / acceleration of the last step     */
+    uint32_t observables;       /* bitmask of (1u << enum nqcb200_observable)                    */
+    uint32_t reserved0;
+    int64_t  ntraj;             /* trajectories owned by this handle                             */
+    int64_t  traj_offset;       /* global index of local trajectory 0 (RNG key, sharding)        */
+    uint64_t seed;
+    double   dt;
+    double   t0;                /* tspan[1]                                                      */
+    double   temperature;       /* ring polymer: omega_n = nbeads*temperature (ring_polymer.jl:18) */
+    double   nrpmd_gamma;       /* nrpmd.jl:43                                                   */
+    double   edc_C;             /* >0: EDC decoherence constant (decoherence_corrections.jl:14)  */
+    double   params[NQCB200_MAX_PARAMS];
+    const double* masses;       /* [D] mass per nuclear degree of freedom                        */
+    const double* bath_a;       /* model array a (see enum nqcb200_model), may be NULL           */
+    const double* bath_b;       /* model array b                                                 */
+    int32_t  nbath;             /* length of bath_a / bath_b                                     */
+    int32_t  reserved1;
+} nqcb200_config;
+
+typedef struct nqcb200_handle nqcb200_handle;
+
+/* Library / ABI version (NQCB200_ABI_VERSION). */
+int nqcb200_version(void);
+
+/* Number of CUDA devices visible to the library (0 when none: every other call then fails). */
+int nqcb200_device_count(void);
+
+/* Create an engine for one shard of trajectories on cfg->device.  Copies everything it needs
+ * out of *cfg (masses, bath arrays).  Replaces: Simulation construction + create_problem +
+ * alg_cache (simulations.jl:28-44, SurfaceHoppingMethods.jl:75-79, bab_electronics.jl:15-46). */
+int nqcb200_create(const nqcb200_config* cfg, nqcb200_handle** out);
+int nqcb200_destroy(nqcb200_handle* h);
+
+/* Message of the last failing call on this handle (h may be NULL: last create error). */
+const char* nqcb200_last_error(const nqcb200_handle* h);
+
+/* Width (doubles per save point per trajectory) of an observable for this handle's config. */
+int nqcb200_observable_width(const nqcb200_handle* h, int obs_id);
+
+/* Upload initial DynamicsVariables for all ntraj trajectories and (re)initialise the integrator
+ * caches: update_cache!(r), acceleration k0, all-zero electronic double buffer (quirk Q1,
+ * electronic_dynamics.jl:118-127), eigenvector gauge reference, step counter = 0, observable
+ * accumulators = 0, save point 0 recorded.
+ *   sig_re/sig_im: density matrix (FSSH/Ehrenfest, n*n per trajectory) or psi (IESH, n*ne);
+ *                  NULL for CLASSICAL/NRPMD.
+ *   state: 1-based active state (FSSH: 1 per trajectory; IESH: ne sorted occupied states);
+ *          NULL for methods without a discrete state.
+ * Replaces: prob_func/sample_distribution output -> integrator init
+ *           (selections.jl:38-101, bab_electronics.jl:48-59).                                   */
+int nqcb200_set_state(nqcb200_handle* h, const double* r, const double* v,
+                      const double* sig_re, const double* sig_im, const int32_t* state);
+
+/* Same, but the electronic state is given in the DIABATIC basis (PureState(i) / MixedState,
+ * the default basis of NQCDistributions): rho is rotated on the device, sigma = Z' rho Z at r0
+ * (density_matrix_dynamics.jl:37-46,64-75).  FSSH: if state == NULL the active state is sampled
+ * with weights Re diag(sigma) (fssh.jl:53-54, StatsBase.sample(Weights)) from state_draw[traj]
+ * (uniform [0,1)) or, when state_draw == NULL, from Philox (purpose 1).                          */
+int nqcb200_set_state_diabatic(nqcb200_handle* h, const double* r, const double* v,
+                               const double* rho_re, const double* rho_im, const int32_t* state,
+                               const double* state_draw);
+
+/* NRPMD mapping variables (nstates, nbeads) per trajectory; call after nqcb200_set_state. */
+int nqcb200_set_mapping(nqcb200_handle* h, const double* qmap, const double* pmap);
+
+/* Optional: eigenvector gauge reference Z_ref (n*n column-major per trajectory [, per bead and
+ * centroid]) replacing the identity default in the column-sign continuity rule of
+ * NQCCalculators (dot(Z_new[:,i], Z_old[:,i]) < 0 -> flip).  Lets the Julia shim hand over
+ * sim.cache.eigen.Z so the engine continues in LAPACK's gauge.  Call before nqcb200_set_state. */
+int nqcb200_set_gauge_reference(nqcb200_handle* h, const double* Z, int64_t count_per_traj);
+
+/* Parity mode (cfg.rng == INJECTED): xi[step*ntraj + traj], uniform [0,1) draws consumed one per
+ * trajectory per step starting at the current step counter.                                    */
+int nqcb200_set_draws(nqcb200_handle* h, const double* xi, int64_t nsteps);
+
+/* Advance every trajectory by nsteps of dt (blocking).  Order inside a step follows the
+ * reference: perform_step! -> hop callback -> save.                              */
+int nqcb200_run(nqcb200_handle* h, int64_t nsteps);
+
+/* Download the current DynamicsVariables (any pointer may be NULL to skip that field). */
+int nqcb200_get_state(nqcb200_handle* h, double* r, double* v,
+                      double* sig_re, double* sig_im, int32_t* state);
+int nqcb200_get_mapping(nqcb200_handle* h, double* qmap, double* pmap);
+
+/* Observable summed over this handle's trajectories: out[isave*width + k], isave < nsave_done.
+ * (SumReduction, reductions.jl:12-31; MeanReduction divides by the global trajectory count.)   */
+int nqcb200_get_observable_sum(nqcb200_handle* h, int obs_id, double* out, int64_t len);
+
+/* Same accumulator as a DEVICE pointer (ntotal doubles, all enabled observables packed in enum
+ * order, each [nsave][width]) so a host can all-reduce it in place with NCCL across shards.    */
+int nqcb200_observable_sum_device(nqcb200_handle* h, double** dev_ptr, int64_t* ntotal);
+int nqcb200_observable_offset(const nqcb200_handle* h, int obs_id, int64_t* offset);
+
+/* Per-trajectory values (cfg.per_trajectory=1): out[(traj*nsave + isave)*width + k]
+ * (SortByTrajectoryReduction, reductions.jl:54-55).                                             */
+int nqcb200_get_observable_per_trajectory(nqcb200_handle* h, int obs_id, double* out, int64_t len);
+
+/* Diagnostics of the most recent step (cfg.diagnostics=1), trajectory-major:
+ *   eig   [traj][n]          adiabatic energies w (centroid for ring polymers)
+ *   nac   [traj][D][n*n]     nonadiabatic coupling d_I, column-major (centroid for ring polymers)
+ *   accel [traj][B][D]       acceleration k used for the next half kick
+ *   Z     [traj][n*n]        eigenvectors in the engine's gauge                                 */
+int nqcb200_get_diagnostics(nqcb200_handle* h, double* eig, double* nac, double* accel, double* Z);
+
+/* Counters summed over this handle's trajectories (SURVEY.md section 5 metrics row). */
+int nqcb200_get_counters(nqcb200_handle* h, int64_t* steps, int64_t* hops, int64_t* frustrated,
+                         int64_t* nonfinite);
+
+/* Number of save points recorded so far, and device time (ms, CUDA events on the launch stream)
+ * spent in step kernels by the last nqcb200_run, with the number of kernel launches it made.   */
+int nqcb200_get_progress(nqcb200_handle* h, int64_t* nsave_done, int64_t* step_count);
+int nqcb200_get_last_run_timing(nqcb200_handle* h, double* kernel_ms, int64_t* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NQCB200_H */

@@ -1,0 +1,314 @@
+"""ctypes mirror of ``include/nqcb200.h`` (the C ABI of the B200 ensemble-trajectory engine).
+
+This module only describes the ABI (config struct, enums, argument types) and wraps an opaque
+handle; it contains no numerics.  ``load_engine_library`` loads the CUDA shared library built
+from ``csrc/`` and raises if it is missing -- there is no CPU fallback anywhere in the package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+ABI_VERSION = 1
+MAX_PARAMS = 32
+
+# enums (include/nqcb200.h)
+METHOD_FSSH, METHOD_EHRENFEST, METHOD_IESH, METHOD_CLASSICAL, METHOD_NRPMD = 1, 2, 3, 4, 5
+(MODEL_TULLY_ONE, MODEL_TULLY_TWO, MODEL_TULLY_THREE, MODEL_DOUBLE_WELL, MODEL_SPIN_BOSON,
+ MODEL_THREE_STATE_MORSE, MODEL_HARMONIC, MODEL_FREE, MODEL_ANDERSON_HOLSTEIN_MIAO_SUBOTNIK) = range(1, 10)
+RESCALE_STANDARD, RESCALE_VINVERSION, RESCALE_OFF = 0, 1, 2
+RNG_PHILOX, RNG_INJECTED = 0, 1
+(OBS_ADIABATIC_POP, OBS_DIABATIC_POP, OBS_POPCORR_DIABATIC, OBS_POPCORR_ADIABATIC, OBS_KINETIC,
+ OBS_POTENTIAL, OBS_TOTAL_ENERGY, OBS_POSITION, OBS_VELOCITY, OBS_DISCRETE_STATE, OBS_SCATTERING,
+ OBS_SCATTERING_DIABATIC, OBS_SIGMA) = range(13)
+OBS_COUNT = 13
+
+ERRORS = {0: "ok", -1: "invalid argument", -2: "unsupported configuration (no kernel, no CPU fallback)",
+          -3: "no CUDA device", -4: "CUDA error", -5: "call order violated", -6: "out of memory"}
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+_lp = C.POINTER(C.c_int64)
+
+
+class Config(C.Structure):
+    """``nqcb200_config`` -- field order and types must match the header exactly."""
+    _fields_ = [
+        ("abi_version", C.c_int32), ("method", C.c_int32), ("model", C.c_int32), ("nstates", C.c_int32),
+        ("ndofs", C.c_int32), ("nbeads", C.c_int32), ("nelectrons", C.c_int32), ("rescaling", C.c_int32),
+        ("estimate_probability", C.c_int32), ("disable_hopping", C.c_int32), ("rng", C.c_int32),
+        ("device", C.c_int32), ("save_every", C.c_int32), ("nsave", C.c_int32), ("per_trajectory", C.c_int32),
+        ("diagnostics", C.c_int32), ("observables", C.c_uint32), ("reserved0", C.c_uint32),
+        ("ntraj", C.c_int64), ("traj_offset", C.c_int64), ("seed", C.c_uint64),
+        ("dt", C.c_double), ("t0", C.c_double), ("temperature", C.c_double), ("nrpmd_gamma", C.c_double),
+        ("edc_C", C.c_double), ("params", C.c_double * MAX_PARAMS),
+        ("masses", _dp), ("bath_a", _dp), ("bath_b", _dp), ("nbath", C.c_int32), ("reserved1", C.c_int32),
+    ]
+
+
+class EngineError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"[{code}: {ERRORS.get(code, '?')}] {message}")
+        self.code = code
+
+
+def _as_f64(a, size: Optional[int] = None) -> np.ndarray:
+    out = np.ascontiguousarray(a, dtype=np.float64).reshape(-1)
+    if size is not None and out.size != size:
+        raise ValueError(f"expected {size} doubles, got {out.size}")
+    return out
+
+
+def _ptr(a: Optional[np.ndarray], typ=_dp):
+    return a.ctypes.data_as(typ) if a is not None else None
+
+
+def bind(lib: C.CDLL, prefix: str) -> None:
+    """Declare argument/return types for every entry point of the header on ``lib``."""
+    H = C.c_void_p
+
+    def f(name, args, res=C.c_int, required=True):
+        try:
+            fn = getattr(lib, prefix + name)
+        except AttributeError:
+            if required:
+                raise
+            return
+        fn.argtypes, fn.restype = args, res
+
+    f("version", [])
+    f("device_count", [], required=False)
+    f("create", [C.POINTER(Config), C.POINTER(H)])
+    f("destroy", [H])
+    f("last_error", [H], C.c_char_p)
+    f("observable_width", [H, C.c_int])
+    f("set_state", [H, _dp, _dp, _dp, _dp, _ip])
+    f("set_state_diabatic", [H, _dp, _dp, _dp, _dp, _ip, _dp])
+    f("set_mapping", [H, _dp, _dp])
+    f("set_gauge_reference", [H, _dp, C.c_int64])
+    f("set_draws", [H, _dp, C.c_int64])
+    f("run", [H, C.c_int64])
+    f("get_state", [H, _dp, _dp, _dp, _dp, _ip])
+    f("get_mapping", [H, _dp, _dp])
+    f("get_observable_sum", [H, C.c_int, _dp, C.c_int64])
+    f("observable_sum_device", [H, C.POINTER(C.c_void_p), _lp], required=False)
+    f("observable_offset", [H, C.c_int, _lp], required=False)
+    f("get_observable_per_trajectory", [H, C.c_int, _dp, C.c_int64])
+    f("get_diagnostics", [H, _dp, _dp, _dp, _dp])
+    f("get_counters", [H, _lp, _lp, _lp, _lp])
+    f("get_progress", [H, _lp, _lp])
+    f("get_last_run_timing", [H, _dp, _lp], required=False)
+
+
+HEADER_SYMBOLS = [
+    "version", "device_count", "create", "destroy", "last_error", "observable_width", "set_state",
+    "set_state_diabatic", "set_mapping", "set_gauge_reference", "set_draws", "run", "get_state", "get_mapping",
+    "get_observable_sum", "observable_sum_device", "observable_offset", "get_observable_per_trajectory",
+    "get_diagnostics", "get_counters", "get_progress", "get_last_run_timing",
+]
+
+_ENGINE_LIB: Optional[C.CDLL] = None
+
+
+def engine_library_path() -> str:
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libnqcb200.so")
+
+
+def load_engine_library() -> C.CDLL:
+    """Load ``csrc/libnqcb200.so`` (built by ``__graft_entry__.build()`` / ``csrc/Makefile``)."""
+    global _ENGINE_LIB
+    if _ENGINE_LIB is None:
+        path = engine_library_path()
+        if not os.path.exists(path):
+            raise ImportError(
+                f"{path} is missing: build the CUDA engine first (python -c 'import __graft_entry__ as g; g.build()' "
+                "or make -C nqcdynamics.jl_b200/csrc).  There is no CPU fallback.")
+        lib = C.CDLL(path)
+        bind(lib, "nqcb200_")
+        _ENGINE_LIB = lib
+    return _ENGINE_LIB
+
+
+class CHandle:
+    """Thin object wrapper over an opaque ``<prefix>handle*``; every method is one C call."""
+
+    def __init__(self, lib: C.CDLL, prefix: str, cfg: Config, keepalive=()):
+        self._lib, self._p = lib, prefix
+        self.cfg = cfg
+        self._keepalive = keepalive
+        self._h = C.c_void_p()
+        rc = getattr(lib, prefix + "create")(C.byref(cfg), C.byref(self._h))
+        if rc != 0:
+            msg = getattr(lib, prefix + "last_error")(None)
+            self._h = C.c_void_p()
+            raise EngineError(rc, (msg or b"").decode())
+        self.n, self.D, self.B, self.ne = cfg.nstates, cfg.ndofs, cfg.nbeads, cfg.nelectrons
+        self.T = int(cfg.ntraj)
+        self.nsig = self.n * (self.ne if cfg.method == METHOD_IESH else self.n)
+        self.nstate = self.ne if cfg.method == METHOD_IESH else 1
+
+    # -- plumbing ------------------------------------------------------------------------------
+    def _call(self, name, *args):
+        rc = getattr(self._lib, self._p + name)(self._h, *args)
+        if rc < 0:
+            msg = getattr(self._lib, self._p + "last_error")(self._h)
+            raise EngineError(rc, (msg or b"").decode())
+        return rc
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            getattr(self._lib, self._p + "destroy")(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- state upload / download ---------------------------------------------------------------
+    def _state_args(self, r, v, sre, sim, state):
+        nrv = self.T * self.B * self.D
+        r_, v_ = _as_f64(r, nrv), _as_f64(v, nrv)
+        sre_ = _as_f64(sre, self.T * self.nsig) if sre is not None else None
+        sim_ = _as_f64(sim, self.T * self.nsig) if sim is not None else None
+        st_ = np.ascontiguousarray(state, dtype=np.int32).reshape(-1) if state is not None else None
+        if st_ is not None and st_.size != self.T * self.nstate:
+            raise ValueError("state has the wrong size")
+        return r_, v_, sre_, sim_, st_
+
+    def set_state(self, r, v, sigma_re=None, sigma_im=None, state=None):
+        r_, v_, sre_, sim_, st_ = self._state_args(r, v, sigma_re, sigma_im, state)
+        self._call("set_state", _ptr(r_), _ptr(v_), _ptr(sre_), _ptr(sim_), _ptr(st_, _ip))
+
+    def set_state_diabatic(self, r, v, rho_re, rho_im=None, state=None, state_draw=None):
+        r_, v_, sre_, sim_, st_ = self._state_args(r, v, rho_re, rho_im, state)
+        dr_ = _as_f64(state_draw, self.T) if state_draw is not None else None
+        self._call("set_state_diabatic", _ptr(r_), _ptr(v_), _ptr(sre_), _ptr(sim_), _ptr(st_, _ip), _ptr(dr_))
+
+    def set_mapping(self, qmap, pmap):
+        q, p = _as_f64(qmap, self.T * self.n * self.B), _as_f64(pmap, self.T * self.n * self.B)
+        self._call("set_mapping", _ptr(q), _ptr(p))
+
+    def set_gauge_reference(self, Z, count_per_traj=1):
+        z = _as_f64(Z, self.T * count_per_traj * self.n * self.n)
+        self._call("set_gauge_reference", _ptr(z), C.c_int64(count_per_traj))
+
+    def set_draws(self, xi):
+        xi_ = np.ascontiguousarray(xi, dtype=np.float64)
+        if xi_.ndim != 2 or xi_.shape[1] != self.T:
+            raise ValueError("draws must have shape (nsteps, ntraj)")
+        self._call("set_draws", _ptr(xi_.reshape(-1)), C.c_int64(xi_.shape[0]))
+
+    def run(self, nsteps: int):
+        self._call("run", C.c_int64(int(nsteps)))
+
+    def get_state(self):
+        T, B, D, n = self.T, self.B, self.D, self.n
+        r = np.empty((T, B, D)); v = np.empty((T, B, D))
+        has_sig = self.cfg.method in (METHOD_FSSH, METHOD_EHRENFEST, METHOD_IESH)
+        has_state = self.cfg.method in (METHOD_FSSH, METHOD_IESH)
+        ncol = self.ne if self.cfg.method == METHOD_IESH else n
+        sre = np.empty((T, ncol, n)) if has_sig else None
+        sim = np.empty((T, ncol, n)) if has_sig else None
+        st = np.empty((T, self.nstate), dtype=np.int32) if has_state else None
+        self._call("get_state", _ptr(r), _ptr(v), _ptr(sre), _ptr(sim), _ptr(st, _ip))
+        out = {"r": r, "v": v}
+        if has_sig:
+            # column-major (n, ncol) per trajectory -> numpy [t, col, row]; expose as [t, row, col]
+            out["sigma"] = (sre + 1j * sim).transpose(0, 2, 1)
+        if has_state:
+            out["state"] = st
+        return out
+
+    def get_mapping(self):
+        q = np.empty((self.T, self.B, self.n)); p = np.empty((self.T, self.B, self.n))
+        self._call("get_mapping", _ptr(q), _ptr(p))
+        return q, p
+
+    # -- outputs -------------------------------------------------------------------------------
+    def observable_width(self, obs_id: int) -> int:
+        return self._call("observable_width", C.c_int(obs_id))
+
+    def observable_sum(self, obs_id: int) -> np.ndarray:
+        w = self.observable_width(obs_id)
+        out = np.empty((self.cfg.nsave, w))
+        self._call("get_observable_sum", C.c_int(obs_id), _ptr(out), C.c_int64(out.size))
+        return out
+
+    def observable_per_trajectory(self, obs_id: int) -> np.ndarray:
+        w = self.observable_width(obs_id)
+        out = np.empty((self.T, self.cfg.nsave, w))
+        self._call("get_observable_per_trajectory", C.c_int(obs_id), _ptr(out), C.c_int64(out.size))
+        return out
+
+    def diagnostics(self):
+        T, n, D, B = self.T, self.n, self.D, self.B
+        eig = np.empty((T, n)); nac = np.empty((T, D, n, n)); acc = np.empty((T, B, D)); Z = np.empty((T, n, n))
+        self._call("get_diagnostics", _ptr(eig), _ptr(nac), _ptr(acc), _ptr(Z))
+        # matrices are column-major: numpy [.., col, row] -> [.., row, col]
+        return {"eig": eig, "nac": nac.transpose(0, 1, 3, 2), "accel": acc, "Z": Z.transpose(0, 2, 1)}
+
+    def counters(self):
+        vals = [C.c_int64() for _ in range(4)]
+        self._call("get_counters", *[C.byref(x) for x in vals])
+        return dict(zip(("steps", "hops", "frustrated", "nonfinite"), (int(x.value) for x in vals)))
+
+    def progress(self):
+        a, b = C.c_int64(), C.c_int64()
+        self._call("get_progress", C.byref(a), C.byref(b))
+        return int(a.value), int(b.value)
+
+    def last_run_timing(self):
+        ms, n = C.c_double(), C.c_int64()
+        self._call("get_last_run_timing", C.byref(ms), C.byref(n))
+        return float(ms.value), int(n.value)
+
+    def observable_sum_device(self):
+        p, n = C.c_void_p(), C.c_int64()
+        self._call("observable_sum_device", C.byref(p), C.byref(n))
+        return int(p.value or 0), int(n.value)
+
+    def observable_offset(self, obs_id: int) -> int:
+        o = C.c_int64()
+        self._call("observable_offset", C.c_int(obs_id), C.byref(o))
+        return int(o.value)
+
+
+def make_config(*, method, model, nstates, ndofs, masses, ntraj, dt, nbeads=1, nelectrons=0, params=(),
+                bath_a=None, bath_b=None, rescaling=RESCALE_STANDARD, estimate_probability=1, disable_hopping=0,
+                rng=RNG_PHILOX, device=0, save_every=1, nsave=1, per_trajectory=0, diagnostics=0, observables=0,
+                traj_offset=0, seed=0, t0=0.0, temperature=0.0, nrpmd_gamma=0.5, edc_C=0.0):
+    """Build a :class:`Config`; returns ``(cfg, keepalive)`` -- keep ``keepalive`` referenced until create returns."""
+    cfg = Config()
+    cfg.abi_version = ABI_VERSION
+    cfg.method, cfg.model, cfg.nstates, cfg.ndofs, cfg.nbeads = method, model, nstates, ndofs, nbeads
+    cfg.nelectrons, cfg.rescaling = nelectrons, rescaling
+    cfg.estimate_probability, cfg.disable_hopping, cfg.rng, cfg.device = estimate_probability, disable_hopping, rng, device
+    cfg.save_every, cfg.nsave, cfg.per_trajectory, cfg.diagnostics = save_every, nsave, per_trajectory, diagnostics
+    cfg.observables = observables
+    cfg.ntraj, cfg.traj_offset, cfg.seed = ntraj, traj_offset, seed
+    cfg.dt, cfg.t0, cfg.temperature, cfg.nrpmd_gamma, cfg.edc_C = dt, t0, temperature, nrpmd_gamma, edc_C
+    if len(params) > MAX_PARAMS:
+        raise ValueError("too many model parameters")
+    for i, p in enumerate(params):
+        cfg.params[i] = float(p)
+    m = _as_f64(masses, ndofs)
+    keep = [m]
+    cfg.masses = _ptr(m)
+    if bath_a is not None:
+        a, b = _as_f64(bath_a), _as_f64(bath_b)
+        if a.size != b.size:
+            raise ValueError("bath arrays differ in length")
+        keep += [a, b]
+        cfg.bath_a, cfg.bath_b, cfg.nbath = _ptr(a), _ptr(b), a.size
+    return cfg, keep

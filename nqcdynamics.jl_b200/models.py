@@ -1,0 +1,124 @@
+"""Model table: NQCModels.jl constructors -> (model enum, params[], bath arrays) of the C ABI.
+
+The reference's models live in the external package NQCModels.jl (not under /root/reference); the
+constructor names, keyword names and defaults below follow its documentation in the reference tree
+(docs/src/NQCModels/analyticmodels.md, systembathmodels.md) and SURVEY.md section 8c / A.5.  The numeric
+evaluation of V(r) and dV/dr happens on the device (csrc/models.cuh) -- nothing here is numerics.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _abi
+
+
+@dataclass
+class Model:
+    kind: int
+    nstates: int
+    params: Sequence[float] = ()
+    bath_a: Optional[np.ndarray] = None
+    bath_b: Optional[np.ndarray] = None
+    ndofs: int = 1            # dofs per atom (reference: NQCModels.ndofs)
+    natoms: Optional[int] = None  # fixed by the model (SpinBoson: one atom per bath mode)
+    nelectrons: int = 0
+    name: str = ""
+    classical: bool = False
+    fermi_level: float = 0.0
+
+
+def TullyModelOne(a=0.01, b=1.6, c=0.005, d=1.0) -> Model:
+    return Model(_abi.MODEL_TULLY_ONE, 2, (a, b, c, d), name="TullyModelOne")
+
+
+def TullyModelTwo(a=0.1, b=0.28, c=0.015, d=0.06, e=0.05) -> Model:
+    return Model(_abi.MODEL_TULLY_TWO, 2, (a, b, c, d, e), name="TullyModelTwo")
+
+
+def TullyModelThree(a=6e-4, b=0.1, c=0.9) -> Model:
+    return Model(_abi.MODEL_TULLY_THREE, 2, (a, b, c), name="TullyModelThree")
+
+
+def DoubleWell(mass=1.0, ω=1.0, γ=1.0, Δ=1.0) -> Model:
+    return Model(_abi.MODEL_DOUBLE_WELL, 2, (mass, ω, γ, Δ), name="DoubleWell")
+
+
+@dataclass
+class OhmicSpectralDensity:
+    """J(w) = pi/2 alpha w exp(-w/wc); discretisation docs/src/NQCModels/systembathmodels.md:47-59."""
+    ωᶜ: float
+    α: float
+
+    def discretize(self, N: int):
+        j = np.arange(1, N + 1)
+        ω = -self.ωᶜ * np.log(1.0 - j / (N + 1.0))
+        c = math.sqrt(self.α * self.ωᶜ / (N + 1.0)) * ω
+        return ω, c
+
+
+@dataclass
+class DebyeSpectralDensity:
+    """J(w) = 2 lambda wc w/(wc^2+w^2); discretisation systembathmodels.md:82-94."""
+    ωᶜ: float
+    λ: float
+
+    def discretize(self, N: int):
+        j = np.arange(1, N + 1)
+        ω = self.ωᶜ * np.tan(np.pi / 2.0 * (1.0 - j / (N + 1.0)))
+        c = math.sqrt(2.0 * self.λ / (N + 1.0)) * ω
+        return ω, c
+
+
+def SpinBoson(density, N: int, ϵ: float, Δ: float) -> Model:
+    ω, c = density.discretize(N)
+    return Model(_abi.MODEL_SPIN_BOSON, 2, (ϵ, Δ), bath_a=ω, bath_b=c, natoms=N, name="SpinBoson")
+
+
+def ThreeStateMorse(d=(0.02, 0.02, 0.003), α=(0.4, 0.65, 0.65), r=(4.0, 4.5, 6.0), c=(0.02, 0.0, 0.02),
+                    a=(0.005, 0.005, 0.0), αc=(32.0, 32.0, 0.0), rc=(3.40, 4.97, 0.0)) -> Model:
+    """Coronado/Xing/Miller 2001 three-state Morse model (pairs ordered 12, 13, 23); parameters recalled
+    from NQCModels ('NOT in tree')."""
+    return Model(_abi.MODEL_THREE_STATE_MORSE, 3, (*d, *α, *r, *c, *a, *αc, *rc), name="ThreeStateMorse")
+
+
+def Harmonic(m=1.0, ω=1.0, r0=0.0, dofs=1) -> Model:
+    return Model(_abi.MODEL_HARMONIC, 1, (m, ω, r0), ndofs=dofs, name="Harmonic", classical=True)
+
+
+def Free(dofs=1) -> Model:
+    return Model(_abi.MODEL_FREE, 1, (), ndofs=dofs, name="Free", classical=True)
+
+
+@dataclass
+class TrapezoidalRule:
+    """eps_n = a + (n-1)(b-a)/(M-1), V_n = sqrt((b-a)/(M-1)) V(eps)  (systembathmodels.md:210-215)."""
+    M: int
+    bandmin: float
+    bandmax: float
+
+    def discretize(self, coupling: float):
+        eps = self.bandmin + np.arange(self.M) * (self.bandmax - self.bandmin) / (self.M - 1)
+        V = np.full(self.M, math.sqrt((self.bandmax - self.bandmin) / (self.M - 1)) * coupling)
+        return eps, V
+
+
+@dataclass
+class MiaoSubotnik:
+    """U0 = 1/2 m w^2 x^2, U1 = 1/2 m w^2 (x-g)^2 + DeltaG, coupling sqrt(Gamma/2pi) (recalled)."""
+    Γ: float = 6.4e-3
+    m: float = 2000.0
+    ω: float = 2e-4
+    g: float = 20.6097
+    ΔG: float = -3.8e-3
+
+
+def AndersonHolstein(impurity: MiaoSubotnik, bath: TrapezoidalRule, fermi_level: float = 0.0) -> Model:
+    eps, V = bath.discretize(math.sqrt(impurity.Γ / (2.0 * math.pi)))
+    ne = int(np.count_nonzero(eps <= fermi_level))
+    return Model(_abi.MODEL_ANDERSON_HOLSTEIN_MIAO_SUBOTNIK, bath.M + 1,
+                 (impurity.m, impurity.ω, impurity.g, impurity.ΔG), bath_a=eps, bath_b=V, nelectrons=ne,
+                 name="AndersonHolstein", fermi_level=fermi_level)
