@@ -1,0 +1,87 @@
+// common.cuh -- shared definitions for the sm_100a trajectory kernels.
+#pragma once
+#include <cstdint>
+#include <cmath>
+
+#include "../../include/nqcb200.h"
+
+#if defined(__CUDACC__)
+#define NQ_HD __host__ __device__ __forceinline__
+#define NQ_D __device__ __forceinline__
+#else
+#define NQ_HD inline
+#define NQ_D inline
+#endif
+
+namespace nq {
+
+constexpr int kBlockThreads = 128;
+
+// Packed layout of the enabled observables: each observable occupies [nsave][width] doubles at
+// obs_offset[id] in the per-shard accumulator (and, per trajectory, [nsave][width][ntraj] at the
+// same offset scaled by ntraj in the output stream).
+struct ObsLayout {
+    int32_t width[NQCB200_OBS_COUNT];
+    int64_t offset[NQCB200_OBS_COUNT];  // -1 when disabled
+    int64_t total;                      // doubles in the accumulator
+};
+
+// Kernel parameter block (passed by value as a __grid_constant__).
+struct KParams {
+    // sizes
+    int64_t ntraj;
+    int64_t traj_offset;
+    int32_t n, D, B, ne;
+    // run control
+    int64_t step0;       // global step index of the first step of this launch
+    int32_t nsteps;      // steps in this launch
+    int32_t save_every, nsave;
+    int32_t rescaling, rng, diagnostics, per_trajectory;
+    int32_t estimate_probability, disable_hopping;
+    uint32_t observables;
+    uint64_t seed;
+    double dt, t0, omega_n, nrpmd_gamma, edc_C;
+    double params[NQCB200_MAX_PARAMS];
+    // model / system arrays (device)
+    const double* masses;   // [D]
+    const double* bath_a;   // [nbath]
+    const double* bath_b;
+    // ring polymer: normal-mode tables (lane-fastest, see kernel_ring.cuh) and Cayley 2x2 per mode
+    const double* nm_to;    // [j*B + k] = U[j,k]
+    const double* nm_from;  // [k*B + j] = U[j,k]
+    const double* cayley;   // [4*k + {c11,c12,c21,c22}]
+    // state, SoA: [component][traj]
+    double* r;      // [B*D][T]
+    double* v;      // [B*D][T]
+    double* acc;    // [B*D][T]   acceleration k carried between steps (quirk Q2)
+    double* sig_re; // [n*n or n*ne][T]
+    double* sig_im;
+    int32_t* state; // [1 or ne][T]  0-based on the device
+    double* Zprev;  // [(B (+1 centroid)) * n*n][T] eigenvector gauge reference
+    double* ecur;   // [n + n*n][T]  "current" half of the electronic double buffer: E then v.d
+    double* pop0;   // [2n][T] initial diabatic / adiabatic population (correlation functions)
+    double* qmap;   // [B*n][T]
+    double* pmap;
+    // draws (injected): xi[(step - draws_step0) * T + traj]
+    const double* draws;
+    int64_t draws_step0;
+    // outputs
+    double* obs_sum;    // [layout.total]
+    double* obs_traj;   // [layout.total][T] or nullptr
+    ObsLayout layout;
+    // diagnostics of the last step (optional)
+    double* diag_eig;   // [n][T]
+    double* diag_nac;   // [D*n*n][T]
+    double* diag_Z;     // [n*n][T]
+    // counters: [0]=hops [1]=frustrated
+    unsigned long long* counters;
+};
+
+NQ_HD constexpr int sym_size(int n) { return n * (n + 1) / 2; }
+NQ_HD constexpr int asym_size(int n) { return n * (n - 1) / 2; }
+// packed upper-triangular index for j <= k (row-wise)
+NQ_HD constexpr int sidx(int n, int j, int k) { return j * n - j * (j - 1) / 2 + (k - j); }
+// packed strict upper index for j < k
+NQ_HD constexpr int aidx(int n, int j, int k) { return j * n - j * (j + 1) / 2 + (k - j - 1); }
+
+}  // namespace nq

@@ -1,0 +1,126 @@
+// density.cuh -- electronic density-matrix propagation in registers.
+//
+// Reference: DensityMatrixODEProblem (src/DynamicsMethods/electronic_dynamics.jl:104-130),
+//   dsigma/dt = -i [A(t), sigma],  A(t) = diag(lerp(E_cur, E_next)) - i lerp(vd_cur, vd_next)
+// integrated with OrdinaryDiffEq Tsit5 at fixed dt/5 (bab_electronics.jl:40-43,88-89): 5 sub-steps,
+// 31 RHS evaluations per nuclear step (FSAL reused inside the step).
+//
+// B200 restatement.  sigma is Hermitian and vd = sum_I d_I v_I is real antisymmetric, so with
+// sigma = X + iY (X symmetric, Y antisymmetric, both real) and G = vd, dE_jk = E_j - E_k:
+//     dX/dt =  dE o Y - [G, X]        dY/dt = -dE o X - [G, Y]
+// Only the packed upper triangles (n(n+1)/2 + n(n-1)/2 = n^2 doubles) are carried, every index is a
+// compile-time constant after unrolling, and the whole Tsit5 stage set lives in registers
+// (n = 2: 4 state variables x 6 stages).  This executes ~8x fewer flops than the reference's dense
+// complex commutator (16 n^3 + 10 n^2 per RHS) for the same result up to rounding.
+#pragma once
+#include "common.cuh"
+
+namespace nq {
+
+template <int N>
+struct Herm {
+    double x[sym_size(N)];                     // Re sigma, packed upper
+    double y[asym_size(N) > 0 ? asym_size(N) : 1];  // Im sigma, packed strict upper
+    NQ_HD double X(int j, int k) const { return (j <= k) ? x[sidx(N, j, k)] : x[sidx(N, k, j)]; }
+    NQ_HD double Y(int j, int k) const { return (j == k) ? 0.0 : ((j < k) ? y[aidx(N, j, k)] : -y[aidx(N, k, j)]); }
+};
+
+// One half of the reference's DoubleBuffer (electronic_dynamics.jl:15-36): eigenvalues and the
+// strict upper triangle of the antisymmetric dynamical coupling vd.
+template <int N>
+struct ElecParams {
+    double E[N];
+    double g[asym_size(N) > 0 ? asym_size(N) : 1];
+    NQ_HD double G(int j, int k) const { return (j == k) ? 0.0 : ((j < k) ? g[aidx(N, j, k)] : -g[aidx(N, k, j)]); }
+};
+
+template <int N>
+NQ_HD void density_rhs(const ElecParams<N>& cur, const ElecParams<N>& nxt, double loc, const Herm<N>& u, Herm<N>& du) {
+    ElecParams<N> a;
+#pragma unroll
+    for (int i = 0; i < N; ++i) a.E[i] = cur.E[i] + (nxt.E[i] - cur.E[i]) * loc;
+#pragma unroll
+    for (int i = 0; i < asym_size(N); ++i) a.g[i] = cur.g[i] + (nxt.g[i] - cur.g[i]) * loc;
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+#pragma unroll
+        for (int k = j; k < N; ++k) {
+            // [G,X]_jk = sum_l G_jl X_lk - X_jl G_lk
+            double cx = 0.0;
+#pragma unroll
+            for (int l = 0; l < N; ++l) cx += a.G(j, l) * u.X(l, k) - u.X(j, l) * a.G(l, k);
+            du.x[sidx(N, j, k)] = (a.E[j] - a.E[k]) * u.Y(j, k) - cx;
+            if (k > j) {
+                double cy = 0.0;
+#pragma unroll
+                for (int l = 0; l < N; ++l) cy += a.G(j, l) * u.Y(l, k) - u.Y(j, l) * a.G(l, k);
+                du.y[aidx(N, j, k)] = -(a.E[j] - a.E[k]) * u.X(j, k) - cy;
+            }
+        }
+}
+
+namespace tsit5 {
+constexpr double c1 = 0.161, c2 = 0.327, c3 = 0.9, c4 = 0.9800255409045097;
+constexpr double a21 = 0.161;
+constexpr double a31 = -0.008480655492356989, a32 = 0.335480655492357;
+constexpr double a41 = 2.8971530571054935, a42 = -6.359448489975075, a43 = 4.3622954328695815;
+constexpr double a51 = 5.325864828439257, a52 = -11.748883564062828, a53 = 7.4955393428898365,
+                 a54 = -0.09249506636175525;
+constexpr double a61 = 5.86145544294642, a62 = -12.92096931784711, a63 = 8.159367898576159,
+                 a64 = -0.071584973281401, a65 = -0.028269050394068383;
+constexpr double a71 = 0.09646076681806523, a72 = 0.01, a73 = 0.4798896504144996, a74 = 1.379008574103742,
+                 a75 = -3.290069515436081, a76 = 2.324710524099774;
+}  // namespace tsit5
+
+#define NQ_FOR_HERM(expr)                                              \
+    _Pragma("unroll") for (int i_ = 0; i_ < sym_size(N); ++i_) { auto& o = tmp.x[i_]; const int i = i_; const bool isx = true; expr; } \
+    _Pragma("unroll") for (int i_ = 0; i_ < asym_size(N); ++i_) { auto& o = tmp.y[i_]; const int i = i_; const bool isx = false; expr; }
+
+// sigma(t) -> sigma(t+dt): set_ut! + step!(integrator, dt, true) of the reference.
+// tcur / tnext are the time stamps of the two buffer halves (quirk Q1: tcur = 0 and cur = 0 on the
+// very first step of a trajectory).
+template <int N>
+NQ_HD void propagate_density(const ElecParams<N>& cur, double tcur, const ElecParams<N>& nxt, double tnext,
+                             double t, double dt, Herm<N>& s) {
+    using namespace tsit5;
+    const double h = dt / 5.0;
+    const double inv_span = 1.0 / (tnext - tcur);
+    auto loc_of = [&](double tau) {
+        double l = (tau - tcur) * inv_span;
+        return (l != l) ? 0.0 : l;   // isnan -> 0 (electronic_dynamics.jl:62,75)
+    };
+    Herm<N> k1, k2, k3, k4, k5, k6, tmp;
+    double ts = t;
+    density_rhs<N>(cur, nxt, loc_of(ts), s, k1);
+#pragma unroll 1
+    for (int sub = 0; sub < 5; ++sub) {
+        const double hh = (sub == 4) ? (t + dt) - ts : h;   // tstop snapping of the last sub-step
+#define NQ_STAGE(EXPRX, EXPRY)                                                              \
+        _Pragma("unroll") for (int i = 0; i < sym_size(N); ++i) tmp.x[i] = s.x[i] + hh * (EXPRX);  \
+        _Pragma("unroll") for (int i = 0; i < asym_size(N); ++i) tmp.y[i] = s.y[i] + hh * (EXPRY);
+        NQ_STAGE(a21 * k1.x[i], a21 * k1.y[i])
+        density_rhs<N>(cur, nxt, loc_of(ts + c1 * hh), tmp, k2);
+        NQ_STAGE(a31 * k1.x[i] + a32 * k2.x[i], a31 * k1.y[i] + a32 * k2.y[i])
+        density_rhs<N>(cur, nxt, loc_of(ts + c2 * hh), tmp, k3);
+        NQ_STAGE(a41 * k1.x[i] + a42 * k2.x[i] + a43 * k3.x[i], a41 * k1.y[i] + a42 * k2.y[i] + a43 * k3.y[i])
+        density_rhs<N>(cur, nxt, loc_of(ts + c3 * hh), tmp, k4);
+        NQ_STAGE(a51 * k1.x[i] + a52 * k2.x[i] + a53 * k3.x[i] + a54 * k4.x[i],
+                 a51 * k1.y[i] + a52 * k2.y[i] + a53 * k3.y[i] + a54 * k4.y[i])
+        density_rhs<N>(cur, nxt, loc_of(ts + c4 * hh), tmp, k5);
+        NQ_STAGE(a61 * k1.x[i] + a62 * k2.x[i] + a63 * k3.x[i] + a64 * k4.x[i] + a65 * k5.x[i],
+                 a61 * k1.y[i] + a62 * k2.y[i] + a63 * k3.y[i] + a64 * k4.y[i] + a65 * k5.y[i])
+        density_rhs<N>(cur, nxt, loc_of(ts + hh), tmp, k6);
+#pragma unroll
+        for (int i = 0; i < sym_size(N); ++i)
+            s.x[i] = s.x[i] + hh * (a71 * k1.x[i] + a72 * k2.x[i] + a73 * k3.x[i] + a74 * k4.x[i] + a75 * k5.x[i] + a76 * k6.x[i]);
+#pragma unroll
+        for (int i = 0; i < asym_size(N); ++i)
+            s.y[i] = s.y[i] + hh * (a71 * k1.y[i] + a72 * k2.y[i] + a73 * k3.y[i] + a74 * k4.y[i] + a75 * k5.y[i] + a76 * k6.y[i]);
+#undef NQ_STAGE
+        ts = (sub == 4) ? (t + dt) : ts + hh;
+        if (sub < 4) density_rhs<N>(cur, nxt, loc_of(ts), s, k1);  // FSAL: k7 of this sub-step = k1 of the next
+    }
+}
+#undef NQ_FOR_HERM
+
+}  // namespace nq

@@ -1,0 +1,718 @@
+// engine.cu -- C ABI of include/nqcb200.h on top of the sm_100a trajectory kernels.
+//
+// Host side of the drop-in boundary: owns device memory behind an opaque handle, packs the
+// reference's DynamicsVariables (trajectory-major Julia layout) into SoA device buffers, launches
+// the persistent step kernels on a private stream, and hands observables back.  Pure CUDA runtime:
+// no torch types, no CPU compute path (a missing device is an error, never a fallback).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "kernel_density.cuh"
+#include "kernel_ring.cuh"
+
+using namespace nq;
+
+namespace {
+
+std::string g_create_error;
+
+// ---- kernel table ------------------------------------------------------------------------------
+using StepFn = void (*)(const KParams);
+using InitFn = void (*)(const KParams, int, int, const double*);
+
+struct KernelSet {
+    StepFn step = nullptr;
+    InitFn init = nullptr;
+    int L = 1, DPL = 1;
+    const char* name = "";
+};
+
+template <class M, int DPL, int L, int METHOD>
+KernelSet density_set(const char* name) {
+    KernelSet k;
+    k.step = density_step_kernel<M, DPL, L, METHOD>;
+    k.init = density_init_kernel<M, DPL, L, METHOD>;
+    k.L = L; k.DPL = DPL; k.name = name;
+    return k;
+}
+template <class M, int NB, int METHOD>
+KernelSet ring_set(const char* name) {
+    KernelSet k;
+    k.step = ring_step_kernel<M, NB, METHOD>;
+    k.init = ring_init_kernel<M, NB, METHOD>;
+    k.L = NB; k.DPL = 1; k.name = name;
+    return k;
+}
+
+template <class M>
+bool pick_density_1d(int method, KernelSet& out, const char* name) {
+    if (method == NQCB200_METHOD_FSSH) out = density_set<M, 1, 1, NQCB200_METHOD_FSSH>(name);
+    else if (method == NQCB200_METHOD_EHRENFEST) out = density_set<M, 1, 1, NQCB200_METHOD_EHRENFEST>(name);
+    else return false;
+    return true;
+}
+
+template <int DPL, int L>
+bool pick_spin_boson(int method, KernelSet& out) {
+    using M = ModelT<NQCB200_MODEL_SPIN_BOSON>;
+    if (method == NQCB200_METHOD_FSSH) out = density_set<M, DPL, L, NQCB200_METHOD_FSSH>("spinboson_fssh");
+    else if (method == NQCB200_METHOD_EHRENFEST) out = density_set<M, DPL, L, NQCB200_METHOD_EHRENFEST>("spinboson_ehrenfest");
+    else return false;
+    return true;
+}
+
+template <class M, int NB>
+bool pick_ring(int method, KernelSet& out, const char* name) {
+    if (method == NQCB200_METHOD_FSSH) out = ring_set<M, NB, NQCB200_METHOD_FSSH>(name);
+    else if (method == NQCB200_METHOD_EHRENFEST) out = ring_set<M, NB, NQCB200_METHOD_EHRENFEST>(name);
+    else return false;
+    return true;
+}
+template <class M>
+bool pick_ring_beads(int method, int B, KernelSet& out, const char* name) {
+    switch (B) {
+        case 2: return pick_ring<M, 2>(method, out, name);
+        case 4: return pick_ring<M, 4>(method, out, name);
+        case 8: return pick_ring<M, 8>(method, out, name);
+        case 16: return pick_ring<M, 16>(method, out, name);
+        case 32: return pick_ring<M, 32>(method, out, name);
+    }
+    return false;
+}
+template <class M, int NB>
+KernelSet classical_ring_set(const char* name) {
+    KernelSet k;
+    k.step = classical_ring_step_kernel<M, NB>;
+    k.init = classical_ring_init_kernel<M, NB>;
+    k.L = NB; k.DPL = 1; k.name = name;
+    return k;
+}
+template <class M>
+bool pick_classical(int B, KernelSet& out, const char* name) {
+    switch (B) {
+        case 1: out = classical_ring_set<M, 1>(name); return true;
+        case 2: out = classical_ring_set<M, 2>(name); return true;
+        case 4: out = classical_ring_set<M, 4>(name); return true;
+        case 8: out = classical_ring_set<M, 8>(name); return true;
+        case 16: out = classical_ring_set<M, 16>(name); return true;
+        case 32: out = classical_ring_set<M, 32>(name); return true;
+    }
+    return false;
+}
+
+// Choose a kernel for (method, model, n, D, B); false => NQCB200_ERR_UNSUPPORTED (no fallback).
+bool select_kernels(const nqcb200_config& c, KernelSet& out, std::string& why) {
+    const int m = c.method, D = c.ndofs, B = c.nbeads;
+    const bool density = (m == NQCB200_METHOD_FSSH || m == NQCB200_METHOD_EHRENFEST);
+    if (m == NQCB200_METHOD_CLASSICAL) {
+        if (D != 1) { why = "classical/RPMD kernels are instantiated for ndofs == 1"; return false; }
+        bool ok = false;
+        if (c.model == NQCB200_MODEL_HARMONIC) ok = pick_classical<ModelT<NQCB200_MODEL_HARMONIC>>(B, out, "rpmd_harmonic");
+        else if (c.model == NQCB200_MODEL_FREE) ok = pick_classical<ModelT<NQCB200_MODEL_FREE>>(B, out, "rpmd_free");
+        if (!ok) why = "classical method needs a classical model and nbeads in {1,2,4,8,16,32}";
+        return ok;
+    }
+    if (!density) { why = "method has no kernel yet (IESH / NRPMD are not built in this round)"; return false; }
+    if (B > 1) {
+        if (D != 1) { why = "ring-polymer FSSH/Ehrenfest kernels are instantiated for ndofs == 1"; return false; }
+        bool ok = false;
+        switch (c.model) {
+            case NQCB200_MODEL_TULLY_ONE: ok = pick_ring_beads<ModelT<NQCB200_MODEL_TULLY_ONE>>(m, B, out, "rp_tully1"); break;
+            case NQCB200_MODEL_TULLY_TWO: ok = pick_ring_beads<ModelT<NQCB200_MODEL_TULLY_TWO>>(m, B, out, "rp_tully2"); break;
+            case NQCB200_MODEL_DOUBLE_WELL: ok = pick_ring_beads<ModelT<NQCB200_MODEL_DOUBLE_WELL>>(m, B, out, "rp_doublewell"); break;
+            case NQCB200_MODEL_THREE_STATE_MORSE: ok = pick_ring_beads<ModelT<NQCB200_MODEL_THREE_STATE_MORSE>>(m, B, out, "rp_morse3"); break;
+            default: break;
+        }
+        if (!ok) why = "ring-polymer kernel: unsupported model or nbeads not in {2,4,8,16,32}";
+        return ok;
+    }
+    switch (c.model) {
+        case NQCB200_MODEL_TULLY_ONE: if (D == 1) return pick_density_1d<ModelT<NQCB200_MODEL_TULLY_ONE>>(m, out, "tully1"); break;
+        case NQCB200_MODEL_TULLY_TWO: if (D == 1) return pick_density_1d<ModelT<NQCB200_MODEL_TULLY_TWO>>(m, out, "tully2"); break;
+        case NQCB200_MODEL_TULLY_THREE: if (D == 1) return pick_density_1d<ModelT<NQCB200_MODEL_TULLY_THREE>>(m, out, "tully3"); break;
+        case NQCB200_MODEL_DOUBLE_WELL: if (D == 1) return pick_density_1d<ModelT<NQCB200_MODEL_DOUBLE_WELL>>(m, out, "doublewell"); break;
+        case NQCB200_MODEL_THREE_STATE_MORSE: if (D == 1) return pick_density_1d<ModelT<NQCB200_MODEL_THREE_STATE_MORSE>>(m, out, "morse3"); break;
+        case NQCB200_MODEL_SPIN_BOSON: {
+            if (c.nbath != D) { why = "SpinBoson needs nbath == ndofs"; return false; }
+            int lanes = 0;
+            if (const char* env = getenv("NQCB200_SPINBOSON_LANES")) lanes = atoi(env);
+            if (D <= 4 && (lanes == 0 || lanes == 1)) return pick_spin_boson<4, 1>(m, out);
+            if (D <= 8 && (lanes == 0 || lanes == 1)) return pick_spin_boson<8, 1>(m, out);
+            if (D <= 100 && lanes == 4) return pick_spin_boson<25, 4>(m, out);
+            if (D <= 104 && (lanes == 0 || lanes == 8)) return pick_spin_boson<13, 8>(m, out);
+            if (D <= 112 && lanes == 16) return pick_spin_boson<7, 16>(m, out);
+            if (D <= 128) return pick_spin_boson<4, 32>(m, out);
+            if (D <= 512) return pick_spin_boson<16, 32>(m, out);
+            why = "SpinBoson kernels cover ndofs <= 512";
+            return false;
+        }
+        default: break;
+    }
+    why = "no kernel for this model / ndofs combination";
+    return false;
+}
+
+// ---- small device utilities --------------------------------------------------------------------
+// in: [T][C] (trajectory-major, host layout)  ->  out: [C][T] (SoA)
+template <typename Tin, typename Tout>
+__global__ void aos_to_soa(const Tin* __restrict__ in, Tout* __restrict__ out, int64_t T, int C, Tout add) {
+    __shared__ Tout tile[32][33];
+    const int64_t t0 = (int64_t)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int64_t t = t0 + i; const int c = c0 + threadIdx.x;
+        if (t < T && c < C) tile[i][threadIdx.x] = (Tout)in[t * C + c] + add;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i; const int64_t t = t0 + threadIdx.x;
+        if (t < T && c < C) out[(int64_t)c * T + t] = tile[threadIdx.x][i];
+    }
+}
+template <typename Tin, typename Tout>
+__global__ void soa_to_aos(const Tin* __restrict__ in, Tout* __restrict__ out, int64_t T, int C, Tout add) {
+    __shared__ Tout tile[32][33];
+    const int64_t t0 = (int64_t)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i; const int64_t t = t0 + threadIdx.x;
+        if (t < T && c < C) tile[i][threadIdx.x] = (Tout)in[(int64_t)c * T + t] + add;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int64_t t = t0 + i; const int c = c0 + threadIdx.x;
+        if (t < T && c < C) out[t * C + c] = tile[threadIdx.x][i];
+    }
+}
+__global__ void fold_replicas(const double* __restrict__ rep, double* __restrict__ out, int64_t total, int nrep) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    double s = 0.0;
+    for (int k = 0; k < nrep; ++k) s += rep[(int64_t)k * total + i];
+    out[i] = s;
+}
+__global__ void fill_identity(double* Z, int64_t T, int n, int copies) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= T) return;
+    for (int c = 0; c < copies; ++c)
+        for (int k = 0; k < n; ++k)
+            for (int j = 0; j < n; ++j) Z[((int64_t)c * n * n + j + n * k) * T + i] = (j == k) ? 1.0 : 0.0;
+}
+__global__ void count_nonfinite(const double* r, const double* v, int64_t T, int C, unsigned long long* out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= T) return;
+    bool bad = false;
+    for (int c = 0; c < C; ++c) bad |= !isfinite(r[(int64_t)c * T + i]) || !isfinite(v[(int64_t)c * T + i]);
+    if (bad) atomicAdd(out, 1ull);
+}
+
+int obs_width(const nqcb200_config& c, int id) {
+    const int n = c.nstates, D = c.ndofs;
+    switch (id) {
+        case NQCB200_OBS_ADIABATIC_POP: case NQCB200_OBS_DIABATIC_POP: return n;
+        case NQCB200_OBS_POPCORR_DIABATIC: case NQCB200_OBS_POPCORR_ADIABATIC: return n * n;
+        case NQCB200_OBS_KINETIC: case NQCB200_OBS_POTENTIAL: case NQCB200_OBS_TOTAL_ENERGY: return 1;
+        case NQCB200_OBS_POSITION: case NQCB200_OBS_VELOCITY: return D;
+        case NQCB200_OBS_DISCRETE_STATE: return c.method == NQCB200_METHOD_IESH ? c.nelectrons : 1;
+        case NQCB200_OBS_SCATTERING: case NQCB200_OBS_SCATTERING_DIABATIC: return 2 * n;
+        case NQCB200_OBS_SIGMA: return c.method == NQCB200_METHOD_IESH ? 2 * n * c.nelectrons : 2 * n * n;
+    }
+    return 0;
+}
+
+}  // namespace
+
+struct nqcb200_handle {
+    nqcb200_config cfg;
+    KParams kp;
+    KernelSet ks;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<void*> allocs;
+    double* staging = nullptr;      // trajectory-major staging for uploads / downloads
+    size_t staging_doubles = 0;
+    double* obs_folded = nullptr;
+    double* d_draws = nullptr;
+    int64_t draws_cap = 0;
+    int64_t draws_nsteps = 0;
+    double* d_state_draw = nullptr;
+    bool user_gauge = false;
+    int zcopies = 1;
+    int64_t step_count = 0, nsave_done = 0;
+    bool has_state = false;
+    int nsig = 0, nstate = 0;
+    double last_ms = 0.0;
+    int64_t last_launches = 0;
+    std::string err;
+};
+
+#define NQ_CUDA(h, call)                                                                    \
+    do {                                                                                    \
+        cudaError_t e_ = (call);                                                            \
+        if (e_ != cudaSuccess) {                                                            \
+            (h)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                  \
+            cudaGetLastError();                                                             \
+            return e_ == cudaErrorMemoryAllocation ? NQCB200_ERR_NOMEM : NQCB200_ERR_CUDA;  \
+        }                                                                                   \
+    } while (0)
+
+namespace {
+
+template <typename T>
+int dev_alloc(nqcb200_handle* h, T** ptr, size_t count) {
+    void* p = nullptr;
+    NQ_CUDA(h, cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
+    NQ_CUDA(h, cudaMemsetAsync(p, 0, std::max<size_t>(count, 1) * sizeof(T), h->stream));
+    h->allocs.push_back(p);
+    *ptr = (T*)p;
+    return NQCB200_OK;
+}
+
+int upload_field(nqcb200_handle* h, const double* host, double* dst, int C) {
+    const int64_t T = h->cfg.ntraj;
+    if (T == 0 || C == 0) return NQCB200_OK;
+    NQ_CUDA(h, cudaMemcpyAsync(h->staging, host, sizeof(double) * T * C, cudaMemcpyHostToDevice, h->stream));
+    dim3 grid((unsigned)((T + 31) / 32), (unsigned)((C + 31) / 32)), block(32, 8);
+    aos_to_soa<double, double><<<grid, block, 0, h->stream>>>(h->staging, dst, T, C, 0.0);
+    NQ_CUDA(h, cudaGetLastError());
+    return NQCB200_OK;
+}
+int download_field(nqcb200_handle* h, const double* src, double* host, int C) {
+    const int64_t T = h->cfg.ntraj;
+    if (T == 0 || C == 0) return NQCB200_OK;
+    dim3 grid((unsigned)((T + 31) / 32), (unsigned)((C + 31) / 32)), block(32, 8);
+    soa_to_aos<double, double><<<grid, block, 0, h->stream>>>(src, h->staging, T, C, 0.0);
+    NQ_CUDA(h, cudaGetLastError());
+    NQ_CUDA(h, cudaMemcpyAsync(host, h->staging, sizeof(double) * T * C, cudaMemcpyDeviceToHost, h->stream));
+    NQ_CUDA(h, cudaStreamSynchronize(h->stream));
+    return NQCB200_OK;
+}
+
+unsigned grid_for(const nqcb200_handle* h) {
+    const int64_t threads = h->cfg.ntraj * h->ks.L;
+    return (unsigned)std::max<int64_t>(1, (threads + kBlockThreads - 1) / kBlockThreads);
+}
+
+int fold_observables(nqcb200_handle* h) {
+    const int64_t total = h->kp.layout.total;
+    if (total == 0) return NQCB200_OK;
+    fold_replicas<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(h->kp.obs_sum, h->obs_folded, total, kObsReplicas);
+    NQ_CUDA(h, cudaGetLastError());
+    return NQCB200_OK;
+}
+
+int set_state_impl(nqcb200_handle* h, const double* r, const double* v, const double* sre, const double* sim,
+                   const int32_t* state, int basis, const double* state_draw) {
+    if (!h) return NQCB200_ERR_INVALID;
+    if (!r || !v) { h->err = "r and v are required"; return NQCB200_ERR_INVALID; }
+    const nqcb200_config& c = h->cfg;
+    const int64_t T = c.ntraj;
+    const bool density = (c.method == NQCB200_METHOD_FSSH || c.method == NQCB200_METHOD_EHRENFEST);
+    if (density && !sre) { h->err = "the density matrix is required for FSSH / Ehrenfest"; return NQCB200_ERR_INVALID; }
+    NQ_CUDA(h, cudaSetDevice(c.device));
+    int rc;
+    const int BD = c.nbeads * c.ndofs;
+    if ((rc = upload_field(h, r, h->kp.r, BD)) != 0) return rc;
+    if ((rc = upload_field(h, v, h->kp.v, BD)) != 0) return rc;
+    if (density) {
+        if ((rc = upload_field(h, sre, h->kp.sig_re, h->nsig)) != 0) return rc;
+        if (sim) { if ((rc = upload_field(h, sim, h->kp.sig_im, h->nsig)) != 0) return rc; }
+        else NQ_CUDA(h, cudaMemsetAsync(h->kp.sig_im, 0, sizeof(double) * T * h->nsig, h->stream));
+    }
+    int sample_state = 0;
+    if (c.method == NQCB200_METHOD_FSSH) {
+        if (state) {
+            int32_t* stage_i = (int32_t*)h->staging;
+            NQ_CUDA(h, cudaMemcpyAsync(stage_i, state, sizeof(int32_t) * T, cudaMemcpyHostToDevice, h->stream));
+            dim3 grid((unsigned)((T + 31) / 32), 1), block(32, 8);
+            aos_to_soa<int32_t, int32_t><<<grid, block, 0, h->stream>>>(stage_i, h->kp.state, T, 1, -1);
+            NQ_CUDA(h, cudaGetLastError());
+        } else {
+            sample_state = 1;
+            if (state_draw) NQ_CUDA(h, cudaMemcpyAsync(h->d_state_draw, state_draw, sizeof(double) * T, cudaMemcpyHostToDevice, h->stream));
+        }
+    }
+    if (!h->user_gauge && c.nstates > 1) {
+        fill_identity<<<(unsigned)((T + 255) / 256), 256, 0, h->stream>>>(h->kp.Zprev, T, c.nstates, h->zcopies);
+        NQ_CUDA(h, cudaGetLastError());
+    }
+    NQ_CUDA(h, cudaMemsetAsync(h->kp.obs_sum, 0, sizeof(double) * std::max<int64_t>(1, h->kp.layout.total) * kObsReplicas, h->stream));
+    if (h->kp.obs_traj) NQ_CUDA(h, cudaMemsetAsync(h->kp.obs_traj, 0, sizeof(double) * h->kp.layout.total * T, h->stream));
+    NQ_CUDA(h, cudaMemsetAsync(h->kp.counters, 0, sizeof(unsigned long long) * 4, h->stream));
+    h->step_count = 0;
+    h->kp.step0 = 0;
+    h->kp.nsteps = 0;
+    if (T > 0) {
+        h->ks.init<<<grid_for(h), kBlockThreads, 0, h->stream>>>(h->kp, basis, sample_state,
+                                                                (sample_state && state_draw) ? h->d_state_draw : nullptr);
+        NQ_CUDA(h, cudaGetLastError());
+    }
+    NQ_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->nsave_done = 1;
+    h->has_state = true;
+    h->user_gauge = false;   // a gauge reference applies to the next set_state only
+    return NQCB200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int nqcb200_version(void) { return NQCB200_ABI_VERSION; }
+
+int nqcb200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char* nqcb200_last_error(const nqcb200_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int nqcb200_destroy(nqcb200_handle* h) {
+    if (!h) return NQCB200_OK;
+    cudaSetDevice(h->cfg.device);
+    for (void* p : h->allocs) cudaFree(p);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    cudaGetLastError();
+    delete h;
+    return NQCB200_OK;
+}
+
+int nqcb200_create(const nqcb200_config* cfg, nqcb200_handle** out) {
+    if (!cfg || !out) { g_create_error = "null argument"; return NQCB200_ERR_INVALID; }
+    *out = nullptr;
+    if (cfg->abi_version != NQCB200_ABI_VERSION) { g_create_error = "abi version mismatch"; return NQCB200_ERR_INVALID; }
+    if (cfg->nstates < 1 || cfg->ndofs < 1 || cfg->nbeads < 1 || cfg->ntraj < 0 || cfg->save_every < 1 || cfg->nsave < 1 ||
+        !cfg->masses || !(cfg->dt > 0.0)) { g_create_error = "invalid sizes / dt / masses"; return NQCB200_ERR_INVALID; }
+    KernelSet ks;
+    std::string why;
+    if (!select_kernels(*cfg, ks, why)) { g_create_error = why; return NQCB200_ERR_UNSUPPORTED; }
+    int ndev = nqcb200_device_count();
+    if (ndev <= 0) { g_create_error = "no CUDA device visible (this library has no CPU path)"; return NQCB200_ERR_NO_DEVICE; }
+    if (cfg->device < 0 || cfg->device >= ndev) { g_create_error = "device ordinal out of range"; return NQCB200_ERR_INVALID; }
+
+    nqcb200_handle* h = new nqcb200_handle();
+    h->cfg = *cfg;
+    h->ks = ks;
+    auto fail = [&](int rc) { g_create_error = h->err; nqcb200_destroy(h); return rc; };
+    {
+        cudaError_t e = cudaSetDevice(cfg->device);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreate(&h->ev0);
+        if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
+        if (e != cudaSuccess) { h->err = cudaGetErrorString(e); cudaGetLastError(); return fail(NQCB200_ERR_CUDA); }
+    }
+    const nqcb200_config& c = h->cfg;
+    const int64_t T = c.ntraj;
+    const int n = c.nstates, D = c.ndofs, B = c.nbeads;
+    KParams& kp = h->kp;
+    std::memset(&kp, 0, sizeof(kp));
+    kp.ntraj = T; kp.traj_offset = c.traj_offset; kp.n = n; kp.D = D; kp.B = B; kp.ne = c.nelectrons;
+    kp.save_every = c.save_every; kp.nsave = c.nsave; kp.rescaling = c.rescaling; kp.rng = c.rng;
+    kp.diagnostics = c.diagnostics; kp.per_trajectory = c.per_trajectory;
+    kp.estimate_probability = c.estimate_probability; kp.disable_hopping = c.disable_hopping;
+    kp.observables = c.observables; kp.seed = c.seed; kp.dt = c.dt; kp.t0 = c.t0;
+    kp.omega_n = B * c.temperature; kp.nrpmd_gamma = c.nrpmd_gamma; kp.edc_C = c.edc_C;
+    std::memcpy(kp.params, c.params, sizeof(kp.params));
+    // observable layout
+    int64_t off = 0;
+    for (int id = 0; id < NQCB200_OBS_COUNT; ++id) {
+        kp.layout.width[id] = obs_width(c, id);
+        kp.layout.offset[id] = -1;
+        if (c.observables & (1u << id)) { kp.layout.offset[id] = off; off += (int64_t)c.nsave * kp.layout.width[id]; }
+    }
+    kp.layout.total = off;
+    h->nsig = (c.method == NQCB200_METHOD_FSSH || c.method == NQCB200_METHOD_EHRENFEST) ? n * n : 0;
+    h->nstate = (c.method == NQCB200_METHOD_FSSH) ? 1 : 0;
+    h->zcopies = (B > 1) ? B + 1 : 1;
+
+    int rc;
+    double *masses = nullptr, *ba = nullptr, *bb = nullptr;
+    if ((rc = dev_alloc(h, &masses, D)) != 0) return fail(rc);
+    if (cudaMemcpyAsync(masses, c.masses, sizeof(double) * D, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) { h->err = "masses upload"; return fail(NQCB200_ERR_CUDA); }
+    kp.masses = masses;
+    if (c.nbath > 0 && c.bath_a && c.bath_b) {
+        if ((rc = dev_alloc(h, &ba, c.nbath)) != 0) return fail(rc);
+        if ((rc = dev_alloc(h, &bb, c.nbath)) != 0) return fail(rc);
+        cudaMemcpyAsync(ba, c.bath_a, sizeof(double) * c.nbath, cudaMemcpyHostToDevice, h->stream);
+        cudaMemcpyAsync(bb, c.bath_b, sizeof(double) * c.nbath, cudaMemcpyHostToDevice, h->stream);
+        kp.bath_a = ba; kp.bath_b = bb;
+    }
+    {
+        // normal-mode transformation U[j,k] (RingPolymerArrays.NormalModeTransformation) and Cayley
+        // propagator (ring_polymer.jl:71-82), full step (half=false) as in bcb.jl:40 / bcb_electronics.jl:36
+        const double pi = 3.14159265358979323846;
+        std::vector<double> to((size_t)B * B), from((size_t)B * B), cay((size_t)4 * B);
+        for (int k = 0; k < B; ++k)
+            for (int j = 0; j < B; ++j) {
+                double u;
+                if (k == 0) u = 1.0 / std::sqrt((double)B);
+                else if (2 * k < B) u = std::sqrt(2.0 / B) * std::cos(2.0 * pi * j * k / B);
+                else if (2 * k == B) u = ((j % 2) ? -1.0 : 1.0) / std::sqrt((double)B);
+                else u = std::sqrt(2.0 / B) * std::sin(2.0 * pi * j * k / B);
+                to[(size_t)j * B + k] = u;
+                from[(size_t)k * B + j] = u;
+            }
+        for (int k = 0; k < B; ++k) {
+            const double wk = 2.0 * kp.omega_n * std::sin(k * pi / B);   // ring_polymer.jl:60
+            const double a = 0.5 * wk * c.dt, den = 1.0 + a * a;
+            cay[4 * k + 0] = (1.0 - a * a) / den; cay[4 * k + 1] = c.dt / den;
+            cay[4 * k + 2] = -wk * wk * c.dt / den; cay[4 * k + 3] = (1.0 - a * a) / den;
+        }
+        double *dto = nullptr, *dfrom = nullptr, *dcay = nullptr;
+        if ((rc = dev_alloc(h, &dto, to.size())) != 0) return fail(rc);
+        if ((rc = dev_alloc(h, &dfrom, from.size())) != 0) return fail(rc);
+        if ((rc = dev_alloc(h, &dcay, cay.size())) != 0) return fail(rc);
+        cudaMemcpyAsync(dto, to.data(), sizeof(double) * to.size(), cudaMemcpyHostToDevice, h->stream);
+        cudaMemcpyAsync(dfrom, from.data(), sizeof(double) * from.size(), cudaMemcpyHostToDevice, h->stream);
+        cudaMemcpyAsync(dcay, cay.data(), sizeof(double) * cay.size(), cudaMemcpyHostToDevice, h->stream);
+        if (cudaStreamSynchronize(h->stream) != cudaSuccess) { h->err = "ring-polymer table upload"; cudaGetLastError(); return fail(NQCB200_ERR_CUDA); }
+        kp.nm_to = dto; kp.nm_from = dfrom; kp.cayley = dcay;
+    }
+    const size_t BD = (size_t)B * D;
+    if ((rc = dev_alloc(h, &kp.r, BD * T)) != 0) return fail(rc);
+    if ((rc = dev_alloc(h, &kp.v, BD * T)) != 0) return fail(rc);
+    if ((rc = dev_alloc(h, &kp.acc, BD * T)) != 0) return fail(rc);
+    if (h->nsig) {
+        if ((rc = dev_alloc(h, &kp.sig_re, (size_t)h->nsig * T)) != 0) return fail(rc);
+        if ((rc = dev_alloc(h, &kp.sig_im, (size_t)h->nsig * T)) != 0) return fail(rc);
+        if ((rc = dev_alloc(h, &kp.Zprev, (size_t)h->zcopies * n * n * T)) != 0) return fail(rc);
+        if ((rc = dev_alloc(h, &kp.ecur, (size_t)(n + n * n) * T)) != 0) return fail(rc);
+        if ((rc = dev_alloc(h, &kp.pop0, (size_t)2 * n * T)) != 0) return fail(rc);
+    }
+    if (h->nstate) { if ((rc = dev_alloc(h, &kp.state, (size_t)h->nstate * T)) != 0) return fail(rc); }
+    if ((rc = dev_alloc(h, &kp.obs_sum, (size_t)std::max<int64_t>(1, kp.layout.total) * kObsReplicas)) != 0) return fail(rc);
+    if ((rc = dev_alloc(h, &h->obs_folded, (size_t)std::max<int64_t>(1, kp.layout.total))) != 0) return fail(rc);
+    if (c.per_trajectory && kp.layout.total > 0) { if ((rc = dev_alloc(h, &kp.obs_traj, (size_t)kp.layout.total * T)) != 0) return fail(rc); }
+    if (c.diagnostics && n > 1) {
+        if ((rc = dev_alloc(h, &kp.diag_eig, (size_t)n * T)) != 0) return fail(rc);
+        if ((rc = dev_alloc(h, &kp.diag_nac, (size_t)D * n * n * T)) != 0) return fail(rc);
+        if ((rc = dev_alloc(h, &kp.diag_Z, (size_t)n * n * T)) != 0) return fail(rc);
+    }
+    if ((rc = dev_alloc(h, &kp.counters, 4)) != 0) return fail(rc);
+    if ((rc = dev_alloc(h, &h->d_state_draw, (size_t)T)) != 0) return fail(rc);
+    // staging: large enough for any single field (and the per-trajectory outputs of one observable)
+    size_t stage = std::max<size_t>({BD, (size_t)h->nsig, (size_t)D * n * n, (size_t)h->zcopies * n * n, (size_t)1});
+    if (c.per_trajectory) {
+        for (int id = 0; id < NQCB200_OBS_COUNT; ++id)
+            if (c.observables & (1u << id)) stage = std::max(stage, (size_t)c.nsave * kp.layout.width[id]);
+    }
+    h->staging_doubles = stage * (size_t)std::max<int64_t>(T, 1);
+    if ((rc = dev_alloc(h, &h->staging, h->staging_doubles)) != 0) return fail(rc);
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess) { h->err = "create sync failed"; cudaGetLastError(); return fail(NQCB200_ERR_CUDA); }
+    *out = h;
+    return NQCB200_OK;
+}
+
+int nqcb200_observable_width(const nqcb200_handle* h, int obs_id) {
+    if (!h || obs_id < 0 || obs_id >= NQCB200_OBS_COUNT) return NQCB200_ERR_INVALID;
+    return h->kp.layout.width[obs_id];
+}
+
+int nqcb200_set_gauge_reference(nqcb200_handle* h, const double* Z, int64_t count_per_traj) {
+    if (!h || !Z) return NQCB200_ERR_INVALID;
+    if (count_per_traj != h->zcopies || h->cfg.nstates < 2) { h->err = "gauge reference: expected nbeads(+1 centroid) matrices per trajectory"; return NQCB200_ERR_INVALID; }
+    NQ_CUDA(h, cudaSetDevice(h->cfg.device));
+    int rc = upload_field(h, Z, h->kp.Zprev, h->zcopies * h->cfg.nstates * h->cfg.nstates);
+    if (rc) return rc;
+    NQ_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->user_gauge = true;
+    return NQCB200_OK;
+}
+
+int nqcb200_set_state(nqcb200_handle* h, const double* r, const double* v, const double* sig_re, const double* sig_im,
+                      const int32_t* state) {
+    if (h && h->cfg.method == NQCB200_METHOD_FSSH && !state) { h->err = "FSSH needs the active state (or use set_state_diabatic)"; return NQCB200_ERR_INVALID; }
+    return set_state_impl(h, r, v, sig_re, sig_im, state, 0, nullptr);
+}
+int nqcb200_set_state_diabatic(nqcb200_handle* h, const double* r, const double* v, const double* rho_re,
+                               const double* rho_im, const int32_t* state, const double* state_draw) {
+    return set_state_impl(h, r, v, rho_re, rho_im, state, 1, state_draw);
+}
+
+int nqcb200_set_mapping(nqcb200_handle* h, const double*, const double*) {
+    if (!h) return NQCB200_ERR_INVALID;
+    h->err = "NRPMD is not built in this round";
+    return NQCB200_ERR_UNSUPPORTED;
+}
+int nqcb200_get_mapping(nqcb200_handle* h, double*, double*) {
+    if (!h) return NQCB200_ERR_INVALID;
+    h->err = "NRPMD is not built in this round";
+    return NQCB200_ERR_UNSUPPORTED;
+}
+
+int nqcb200_set_draws(nqcb200_handle* h, const double* xi, int64_t nsteps) {
+    if (!h || !xi || nsteps < 0) return NQCB200_ERR_INVALID;
+    NQ_CUDA(h, cudaSetDevice(h->cfg.device));
+    const int64_t need = nsteps * h->cfg.ntraj;
+    if (need > h->draws_cap) {
+        void* p = nullptr;
+        NQ_CUDA(h, cudaMalloc(&p, sizeof(double) * std::max<int64_t>(need, 1)));
+        h->allocs.push_back(p);   // the previous (smaller) buffer is released with the handle
+        h->d_draws = (double*)p;
+        h->draws_cap = need;
+    }
+    NQ_CUDA(h, cudaMemcpyAsync(h->d_draws, xi, sizeof(double) * need, cudaMemcpyHostToDevice, h->stream));
+    NQ_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->kp.draws = h->d_draws;
+    h->kp.draws_step0 = h->step_count;
+    h->draws_nsteps = nsteps;
+    return NQCB200_OK;
+}
+
+int nqcb200_run(nqcb200_handle* h, int64_t nsteps) {
+    if (!h || nsteps < 0) return NQCB200_ERR_INVALID;
+    if (!h->has_state) { h->err = "run before set_state"; return NQCB200_ERR_STATE; }
+    const nqcb200_config& c = h->cfg;
+    NQ_CUDA(h, cudaSetDevice(c.device));
+    if (c.method == NQCB200_METHOD_FSSH && c.rng == NQCB200_RNG_INJECTED) {
+        if (!h->kp.draws || h->step_count < h->kp.draws_step0 ||
+            h->step_count + nsteps > h->kp.draws_step0 + h->draws_nsteps) {
+            h->err = "not enough injected draws for this run"; return NQCB200_ERR_STATE;
+        }
+    }
+    h->last_launches = 0;
+    h->last_ms = 0.0;
+    if (c.ntraj == 0 || nsteps == 0) { h->step_count += nsteps; return NQCB200_OK; }
+    const int64_t max_per_launch = 1 << 16;
+    NQ_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+    int64_t done = 0;
+    while (done < nsteps) {
+        const int64_t chunk = std::min(nsteps - done, max_per_launch);
+        h->kp.step0 = h->step_count + done;
+        h->kp.nsteps = (int32_t)chunk;
+        h->ks.step<<<grid_for(h), kBlockThreads, 0, h->stream>>>(h->kp);
+        NQ_CUDA(h, cudaGetLastError());
+        h->last_launches++;
+        done += chunk;
+    }
+    NQ_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+    NQ_CUDA(h, cudaStreamSynchronize(h->stream));
+    float ms = 0.f;
+    NQ_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->last_ms = ms;
+    h->step_count += nsteps;
+    h->nsave_done = std::min<int64_t>(c.nsave, h->step_count / c.save_every + 1);
+    return NQCB200_OK;
+}
+
+int nqcb200_get_state(nqcb200_handle* h, double* r, double* v, double* sig_re, double* sig_im, int32_t* state) {
+    if (!h) return NQCB200_ERR_INVALID;
+    if (!h->has_state) { h->err = "no state"; return NQCB200_ERR_STATE; }
+    NQ_CUDA(h, cudaSetDevice(h->cfg.device));
+    const int BD = h->cfg.nbeads * h->cfg.ndofs;
+    int rc;
+    if (r && (rc = download_field(h, h->kp.r, r, BD)) != 0) return rc;
+    if (v && (rc = download_field(h, h->kp.v, v, BD)) != 0) return rc;
+    if (sig_re && h->nsig && (rc = download_field(h, h->kp.sig_re, sig_re, h->nsig)) != 0) return rc;
+    if (sig_im && h->nsig && (rc = download_field(h, h->kp.sig_im, sig_im, h->nsig)) != 0) return rc;
+    if (state && h->nstate) {
+        const int64_t T = h->cfg.ntraj;
+        int32_t* stage_i = (int32_t*)h->staging;
+        dim3 grid((unsigned)((T + 31) / 32), 1), block(32, 8);
+        if (T > 0) {
+            soa_to_aos<int32_t, int32_t><<<grid, block, 0, h->stream>>>(h->kp.state, stage_i, T, h->nstate, 1);
+            NQ_CUDA(h, cudaGetLastError());
+            NQ_CUDA(h, cudaMemcpyAsync(state, stage_i, sizeof(int32_t) * T * h->nstate, cudaMemcpyDeviceToHost, h->stream));
+            NQ_CUDA(h, cudaStreamSynchronize(h->stream));
+        }
+    }
+    return NQCB200_OK;
+}
+
+int nqcb200_get_observable_sum(nqcb200_handle* h, int obs_id, double* out, int64_t len) {
+    if (!h || !out || obs_id < 0 || obs_id >= NQCB200_OBS_COUNT) return NQCB200_ERR_INVALID;
+    if (h->kp.layout.offset[obs_id] < 0) { h->err = "observable not enabled in config.observables"; return NQCB200_ERR_INVALID; }
+    const int64_t need = (int64_t)h->cfg.nsave * h->kp.layout.width[obs_id];
+    if (len < need) { h->err = "output buffer too small"; return NQCB200_ERR_INVALID; }
+    NQ_CUDA(h, cudaSetDevice(h->cfg.device));
+    int rc = fold_observables(h);
+    if (rc) return rc;
+    NQ_CUDA(h, cudaMemcpyAsync(out, h->obs_folded + h->kp.layout.offset[obs_id], sizeof(double) * need, cudaMemcpyDeviceToHost, h->stream));
+    NQ_CUDA(h, cudaStreamSynchronize(h->stream));
+    return NQCB200_OK;
+}
+
+int nqcb200_observable_sum_device(nqcb200_handle* h, double** dev_ptr, int64_t* ntotal) {
+    if (!h || !dev_ptr || !ntotal) return NQCB200_ERR_INVALID;
+    NQ_CUDA(h, cudaSetDevice(h->cfg.device));
+    int rc = fold_observables(h);
+    if (rc) return rc;
+    NQ_CUDA(h, cudaStreamSynchronize(h->stream));
+    *dev_ptr = h->obs_folded;
+    *ntotal = h->kp.layout.total;
+    return NQCB200_OK;
+}
+
+int nqcb200_observable_offset(const nqcb200_handle* h, int obs_id, int64_t* offset) {
+    if (!h || !offset || obs_id < 0 || obs_id >= NQCB200_OBS_COUNT) return NQCB200_ERR_INVALID;
+    *offset = h->kp.layout.offset[obs_id];
+    return NQCB200_OK;
+}
+
+int nqcb200_get_observable_per_trajectory(nqcb200_handle* h, int obs_id, double* out, int64_t len) {
+    if (!h || !out || obs_id < 0 || obs_id >= NQCB200_OBS_COUNT) return NQCB200_ERR_INVALID;
+    if (!h->kp.obs_traj || h->kp.layout.offset[obs_id] < 0) { h->err = "per-trajectory output not enabled"; return NQCB200_ERR_INVALID; }
+    const int C = h->cfg.nsave * h->kp.layout.width[obs_id];
+    if (len < (int64_t)C * h->cfg.ntraj) { h->err = "output buffer too small"; return NQCB200_ERR_INVALID; }
+    NQ_CUDA(h, cudaSetDevice(h->cfg.device));
+    return download_field(h, h->kp.obs_traj + h->kp.layout.offset[obs_id] * h->cfg.ntraj, out, C);
+}
+
+int nqcb200_get_diagnostics(nqcb200_handle* h, double* eig, double* nac, double* accel, double* Z) {
+    if (!h) return NQCB200_ERR_INVALID;
+    if (!h->cfg.diagnostics || !h->kp.diag_eig) { h->err = "diagnostics not enabled"; return NQCB200_ERR_INVALID; }
+    NQ_CUDA(h, cudaSetDevice(h->cfg.device));
+    const int n = h->cfg.nstates, D = h->cfg.ndofs;
+    int rc;
+    if (eig && (rc = download_field(h, h->kp.diag_eig, eig, n)) != 0) return rc;
+    if (nac && (rc = download_field(h, h->kp.diag_nac, nac, D * n * n)) != 0) return rc;
+    if (accel && (rc = download_field(h, h->kp.acc, accel, h->cfg.nbeads * D)) != 0) return rc;
+    if (Z && (rc = download_field(h, h->kp.diag_Z, Z, n * n)) != 0) return rc;
+    return NQCB200_OK;
+}
+
+int nqcb200_get_counters(nqcb200_handle* h, int64_t* steps, int64_t* hops, int64_t* frustrated, int64_t* nonfinite) {
+    if (!h) return NQCB200_ERR_INVALID;
+    NQ_CUDA(h, cudaSetDevice(h->cfg.device));
+    unsigned long long host[4] = {0, 0, 0, 0};
+    const int64_t T = h->cfg.ntraj;
+    if (nonfinite && T > 0 && h->has_state) {
+        NQ_CUDA(h, cudaMemsetAsync(h->kp.counters + 2, 0, sizeof(unsigned long long), h->stream));
+        count_nonfinite<<<(unsigned)((T + 255) / 256), 256, 0, h->stream>>>(h->kp.r, h->kp.v, T, h->cfg.nbeads * h->cfg.ndofs, h->kp.counters + 2);
+        NQ_CUDA(h, cudaGetLastError());
+    }
+    NQ_CUDA(h, cudaMemcpyAsync(host, h->kp.counters, sizeof(host), cudaMemcpyDeviceToHost, h->stream));
+    NQ_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (steps) *steps = h->step_count * T;
+    if (hops) *hops = (int64_t)host[0];
+    if (frustrated) *frustrated = (int64_t)host[1];
+    if (nonfinite) *nonfinite = (int64_t)host[2];
+    return NQCB200_OK;
+}
+
+int nqcb200_get_progress(nqcb200_handle* h, int64_t* nsave_done, int64_t* step_count) {
+    if (!h) return NQCB200_ERR_INVALID;
+    if (nsave_done) *nsave_done = h->nsave_done;
+    if (step_count) *step_count = h->step_count;
+    return NQCB200_OK;
+}
+
+int nqcb200_get_last_run_timing(nqcb200_handle* h, double* kernel_ms, int64_t* launches) {
+    if (!h) return NQCB200_ERR_INVALID;
+    if (kernel_ms) *kernel_ms = h->last_ms;
+    if (launches) *launches = h->last_launches;
+    return NQCB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,132 @@
+// linalg.cuh -- register-resident symmetric eigensolver for the tiny diabatic matrices (n <= 6).
+//
+// Replaces LAPACK syevr behind NQCCalculators' `eigen(Hermitian(V))` (external; semantics pinned by
+// test/Core/calculators.jl:99-108).  All loops have compile-time bounds so that, after unrolling,
+// every matrix element is a named register: no local memory, no shared memory.
+//   n == 2 : one Jacobi rotation is exact (closed form).
+//   n >= 3 : cyclic Jacobi sweeps until the off-diagonal mass is below 1e-32 of the total.
+// Eigenvalues ascending; the column signs are then fixed by continuity with the previous
+// eigenvectors: dot(Z_new[:,i], Z_old[:,i]) < 0 -> flip   (NQCCalculators correct_phase!).
+#pragma once
+#include "common.cuh"
+
+namespace nq {
+
+template <int N>
+struct Eig {
+    double w[N];
+    double Z[N][N];  // Z[row][col], column i = eigenvector i
+};
+
+template <int N>
+NQ_HD void jacobi_rotate(double (&A)[N][N], double (&Z)[N][N], int p, int q) {
+    const double apq = A[p][q];
+    if (apq == 0.0) return;
+    const double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
+    const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+    const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        if (k != p && k != q) {
+            const double akp = A[k][p], akq = A[k][q];
+            const double np_ = c * akp - s * akq, nq_ = s * akp + c * akq;
+            A[k][p] = np_; A[p][k] = np_;
+            A[k][q] = nq_; A[q][k] = nq_;
+        }
+    }
+    A[p][p] -= t * apq;
+    A[q][q] += t * apq;
+    A[p][q] = 0.0; A[q][p] = 0.0;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        const double zkp = Z[k][p], zkq = Z[k][q];
+        Z[k][p] = c * zkp - s * zkq;
+        Z[k][q] = s * zkp + c * zkq;
+    }
+}
+
+// Vp: packed upper triangle (row-wise) of the symmetric matrix.
+template <int N>
+NQ_HD void sym_eigh(const double (&Vp)[sym_size(N)], Eig<N>& e) {
+    double A[N][N];
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+#pragma unroll
+        for (int k = j; k < N; ++k) { A[j][k] = Vp[sidx(N, j, k)]; A[k][j] = A[j][k]; }
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+#pragma unroll
+        for (int k = 0; k < N; ++k) e.Z[j][k] = (j == k) ? 1.0 : 0.0;
+
+    if (N == 2) {
+        jacobi_rotate<N>(A, e.Z, 0, 1);
+    } else if (N > 2) {
+        for (int sweep = 0; sweep < 30; ++sweep) {
+            double off = 0.0, diag = 0.0;
+#pragma unroll
+            for (int j = 0; j < N; ++j)
+#pragma unroll
+                for (int k = 0; k < N; ++k) {
+                    if (j == k) diag += A[j][k] * A[j][k]; else off += A[j][k] * A[j][k];
+                }
+            if (off <= 1e-32 * (diag + off)) break;
+#pragma unroll
+            for (int p = 0; p < N - 1; ++p)
+#pragma unroll
+                for (int q = p + 1; q < N; ++q) jacobi_rotate<N>(A, e.Z, p, q);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < N; ++j) e.w[j] = A[j][j];
+    // ascending order (stable odd-even transposition network: N passes)
+#pragma unroll
+    for (int pass = 0; pass < N; ++pass)
+#pragma unroll
+        for (int j = 0; j < N - 1; ++j) {
+            if (e.w[j + 1] < e.w[j]) {
+                const double tw = e.w[j]; e.w[j] = e.w[j + 1]; e.w[j + 1] = tw;
+#pragma unroll
+                for (int k = 0; k < N; ++k) { const double tz = e.Z[k][j]; e.Z[k][j] = e.Z[k][j + 1]; e.Z[k][j + 1] = tz; }
+            }
+        }
+}
+
+// Column-sign continuity with the previous eigenvectors; Zref is updated to the new vectors.
+template <int N>
+NQ_HD void fix_gauge(Eig<N>& e, double (&Zref)[N][N]) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        double dot = 0.0;
+#pragma unroll
+        for (int k = 0; k < N; ++k) dot += e.Z[k][i] * Zref[k][i];
+        const double sgn = dot < 0.0 ? -1.0 : 1.0;
+#pragma unroll
+        for (int k = 0; k < N; ++k) { e.Z[k][i] *= sgn; Zref[k][i] = e.Z[k][i]; }
+    }
+}
+
+// A = Z' * S * Z for packed symmetric S; result packed symmetric.
+template <int N>
+NQ_HD void similarity(const double (&Sp)[sym_size(N)], const double (&Z)[N][N], double (&Ap)[sym_size(N)]) {
+    double T[N][N];  // T = S * Z
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < N; ++k) s += Sp[(i <= k) ? sidx(N, i, k) : sidx(N, k, i)] * Z[k][j];
+            T[i][j] = s;
+        }
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = i; j < N; ++j) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < N; ++k) s += Z[k][i] * T[k][j];
+            Ap[sidx(N, i, j)] = s;
+        }
+}
+
+}  // namespace nq

@@ -1,0 +1,242 @@
+"""GPU parity tests: the CUDA engine (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Tolerances (north_star): per-step deterministic quantities within 1e-10 relative in FP64; identical hop
+sequences when the same uniform draws are injected into both implementations.
+"""
+import numpy as np
+import pytest
+
+import nqcdynamics_jl_b200 as nq
+from helpers import A, ALL_POP_OBS, CLASSICAL_OBS, engine_factory, make_pair, model_config, oracle_factory, rel_err
+
+pytestmark = pytest.mark.gpu
+
+STEP_TOL = 1e-10
+
+
+def _pure_state(T, n, i):
+    rho = np.zeros((T, n, n))
+    rho[:, i, i] = 1.0
+    return rho
+
+
+def _compare_state(e, o, tol, what=""):
+    se, so = e.get_state(), o.get_state()
+    for key in ("r", "v"):
+        assert rel_err(se[key], so[key]) < tol, f"{what} {key}"
+    if "sigma" in so:
+        assert np.max(np.abs(se["sigma"] - so["sigma"])) < tol, f"{what} sigma"
+    if "state" in so:
+        assert np.array_equal(se["state"], so["state"]), f"{what} discrete state"
+
+
+def _compare_observables(e, o, obs_mask, tol, T):
+    for oid in range(A.OBS_COUNT):
+        if obs_mask & (1 << oid):
+            a, b = e.observable_sum(oid), o.observable_sum(oid)
+            assert np.max(np.abs(a - b)) <= tol * max(1.0, np.max(np.abs(b))), f"observable {oid}"
+
+
+SCATTER_MODELS = [
+    ("tully1", nq.TullyModelOne(), 2000.0, -5.0, 10.0 / 2000),
+    ("tully2", nq.TullyModelTwo(), 2000.0, -8.0, 16.0 / 2000),
+    ("tully3", nq.TullyModelThree(), 2000.0, -10.0, 10.0 / 2000),
+    ("doublewell", nq.DoubleWell(), 1.0, -0.5, 0.7),
+    ("morse3", nq.ThreeStateMorse(), 20000.0, 2.1, 0.0),
+]
+
+
+@pytest.mark.parametrize("method", [A.METHOD_FSSH, A.METHOD_EHRENFEST])
+@pytest.mark.parametrize("name,model,mass,r0,v0", SCATTER_MODELS)
+def test_per_step_parity(method, name, model, mass, r0, v0):
+    """Step by step: r, v, sigma, state, eigenvalues, NAC, acceleration, eigenvectors within 1e-10."""
+    T, nsteps = 96, 40
+    rng = np.random.default_rng(7)
+    dt = 1.0 if mass > 100 else 0.05
+    kw = model_config(model, method=method, masses=[mass], ntraj=T, dt=dt, rng=A.RNG_INJECTED, diagnostics=1,
+                      save_every=1, nsave=nsteps + 1, observables=ALL_POP_OBS, per_trajectory=1)
+    e, o = make_pair(engine_factory(), oracle_factory(), **kw)
+    r = r0 + 0.3 * rng.standard_normal(T)
+    v = v0 * (1 + 0.1 * rng.standard_normal(T)) + (0.0 if v0 else 1e-4 * rng.standard_normal(T))
+    rho = _pure_state(T, model.nstates, 0)
+    draws = rng.random((nsteps, T))
+    sdraw = rng.random(T)
+    for h in (e, o):
+        h.set_state_diabatic(r, v, rho, None, None, sdraw)
+        h.set_draws(draws)
+    _compare_state(e, o, STEP_TOL, "t0")
+    for step in range(nsteps):
+        e.run(1); o.run(1)
+        _compare_state(e, o, STEP_TOL, f"step {step}")
+        de, do = e.diagnostics(), o.diagnostics()
+        assert rel_err(de["eig"], do["eig"]) < STEP_TOL
+        assert np.max(np.abs(de["Z"] - do["Z"])) < STEP_TOL
+        assert rel_err(de["nac"], do["nac"]) < STEP_TOL
+        assert rel_err(de["accel"], do["accel"]) < STEP_TOL
+    _compare_observables(e, o, ALL_POP_OBS, 1e-9, T)
+    for oid in (A.OBS_DIABATIC_POP, A.OBS_TOTAL_ENERGY):
+        assert np.max(np.abs(e.observable_per_trajectory(oid) - o.observable_per_trajectory(oid))) < 1e-9
+    assert e.counters()["hops"] == o.counters()["hops"]
+    assert e.counters()["frustrated"] == o.counters()["frustrated"]
+
+
+def test_tully_fssh_long_run_identical_hops():
+    """BASELINE config 1 (TullyModelOne FSSH, 1000 trajectories, 3000 steps): same draws -> same hop sequence."""
+    T, nsteps, save_every = 1000, 3000, 10
+    rng = np.random.default_rng(11)
+    model = nq.TullyModelOne()
+    obs = ALL_POP_OBS | (1 << A.OBS_DISCRETE_STATE)
+    kw = model_config(model, method=A.METHOD_FSSH, masses=[2000.0], ntraj=T, dt=1.0, rng=A.RNG_INJECTED,
+                      save_every=save_every, nsave=nsteps // save_every + 1, observables=obs, per_trajectory=1)
+    e, o = make_pair(engine_factory(), oracle_factory(), **kw)
+    r = rng.normal(-8.0, 1.0, T)
+    v = np.full(T, 10.0 / 2000)
+    rho = _pure_state(T, 2, 1)
+    draws = rng.random((nsteps, T))
+    sdraw = rng.random(T)
+    for h in (e, o):
+        h.set_state_diabatic(r, v, rho, None, None, sdraw)
+        h.set_draws(draws)
+        h.run(nsteps)
+    se = e.observable_per_trajectory(A.OBS_DISCRETE_STATE)
+    so = o.observable_per_trajectory(A.OBS_DISCRETE_STATE)
+    assert np.array_equal(se, so), "hop sequences differ"
+    assert e.counters()["hops"] == o.counters()["hops"] > 0
+    _compare_state(e, o, 1e-8, "final")
+    _compare_observables(e, o, obs, 1e-9, T)
+    scat = e.observable_sum(A.OBS_SCATTERING)[-1] / T
+    assert abs(scat.sum() - 1.0) < 1e-12
+
+
+def test_philox_streams_match_oracle():
+    """Production RNG: engine and oracle implement the same Philox4x32-10 keyed by (seed, trajectory, step)."""
+    T, nsteps = 512, 1500
+    model = nq.TullyModelOne()
+    obs = (1 << A.OBS_DISCRETE_STATE) | (1 << A.OBS_ADIABATIC_POP)
+    kw = model_config(model, method=A.METHOD_FSSH, masses=[2000.0], ntraj=T, dt=1.0, rng=A.RNG_PHILOX, seed=20261017,
+                      traj_offset=12345, save_every=25, nsave=nsteps // 25 + 1, observables=obs, per_trajectory=1)
+    e, o = make_pair(engine_factory(), oracle_factory(), **kw)
+    rng = np.random.default_rng(3)
+    r = rng.normal(-6.0, 0.5, T); v = np.full(T, 12.0 / 2000)
+    rho = _pure_state(T, 2, 0)
+    for h in (e, o):
+        h.set_state_diabatic(r, v, rho)
+        h.run(nsteps)
+    assert np.array_equal(e.observable_per_trajectory(A.OBS_DISCRETE_STATE), o.observable_per_trajectory(A.OBS_DISCRETE_STATE))
+    assert e.counters()["hops"] == o.counters()["hops"] > 0
+
+
+def test_sharding_independence():
+    """Philox keyed by the global trajectory id: two shards reproduce the single-shard result exactly."""
+    T, nsteps = 256, 800
+    model = nq.TullyModelOne()
+    obs = (1 << A.OBS_DISCRETE_STATE)
+    rng = np.random.default_rng(5)
+    r = rng.normal(-6.0, 0.5, T); v = np.full(T, 12.0 / 2000)
+    rho = _pure_state(T, 2, 0)
+    mk = engine_factory()
+
+    def run(lo, hi):
+        kw = model_config(model, method=A.METHOD_FSSH, masses=[2000.0], ntraj=hi - lo, dt=1.0, seed=99, traj_offset=lo,
+                          save_every=nsteps, nsave=2, observables=obs, per_trajectory=1)
+        cfg, keep = A.make_config(**kw)
+        h = mk(cfg, keep)
+        h.set_state_diabatic(r[lo:hi], v[lo:hi], rho[lo:hi])
+        h.run(nsteps)
+        return h.get_state()
+
+    full = run(0, T)
+    a, b = run(0, 100), run(100, T)
+    for key in ("r", "v", "state"):
+        assert np.array_equal(np.concatenate([a[key], b[key]]), full[key])
+
+
+@pytest.mark.parametrize("method", [A.METHOD_FSSH, A.METHOD_EHRENFEST])
+@pytest.mark.parametrize("nmodes", [3, 8, 100])
+def test_spin_boson_parity(method, nmodes):
+    """BASELINE config 2: SpinBoson with a Debye bath, lanes-over-modes kernels."""
+    T, nsteps = 48, 60
+    rng = np.random.default_rng(13)
+    model = nq.SpinBoson(nq.DebyeSpectralDensity(0.25, 0.5), nmodes, 0.0, 1.0)
+    obs = ALL_POP_OBS & ~((1 << A.OBS_SCATTERING) | (1 << A.OBS_SCATTERING_DIABATIC))
+    kw = model_config(model, method=method, masses=np.ones(nmodes), ntraj=T, dt=0.1, rng=A.RNG_INJECTED, diagnostics=1,
+                      save_every=5, nsave=nsteps // 5 + 1, observables=obs)
+    e, o = make_pair(engine_factory(), oracle_factory(), **kw)
+    w = model.bath_a
+    beta = 5.0
+    sr = np.sqrt(1.0 / (2 * w * np.tanh(beta * w / 2))); sv = np.sqrt(w / (2 * np.tanh(beta * w / 2)))
+    r = rng.standard_normal((T, nmodes)) * sr
+    v = rng.standard_normal((T, nmodes)) * sv
+    rho = _pure_state(T, 2, 0)
+    draws = rng.random((nsteps, T)); sdraw = rng.random(T)
+    for h in (e, o):
+        h.set_state_diabatic(r, v, rho, None, None, sdraw)
+        h.set_draws(draws)
+    for chunk in range(nsteps // 5):
+        e.run(5); o.run(5)
+        _compare_state(e, o, 1e-9, f"chunk {chunk}")
+        de, do = e.diagnostics(), o.diagnostics()
+        assert rel_err(de["eig"], do["eig"]) < 1e-9
+        assert rel_err(de["nac"], do["nac"]) < 1e-9
+        assert rel_err(de["accel"], do["accel"]) < 1e-9
+    _compare_observables(e, o, obs, 1e-9, T)
+
+
+@pytest.mark.parametrize("method", [A.METHOD_FSSH, A.METHOD_EHRENFEST])
+@pytest.mark.parametrize("nbeads", [4, 16, 32])
+@pytest.mark.parametrize("name,model,mass,r0,v0,temp", [
+    ("tully1", nq.TullyModelOne(), 2000.0, -4.0, 10.0 / 2000, 1e-3),
+    ("morse3", nq.ThreeStateMorse(), 20000.0, 2.1, 0.0, 9.5e-4),
+])
+def test_ring_polymer_parity(method, nbeads, name, model, mass, r0, v0, temp):
+    """RPSH / RP-Ehrenfest (BASELINE config 5): beads-on-lanes kernel vs oracle BCBwithTsit5."""
+    T, nsteps = 40, 50
+    rng = np.random.default_rng(17)
+    kw = model_config(model, method=method, masses=[mass], ntraj=T, dt=1.0, nbeads=nbeads, temperature=temp,
+                      rng=A.RNG_INJECTED, diagnostics=1, save_every=5, nsave=nsteps // 5 + 1, observables=ALL_POP_OBS)
+    e, o = make_pair(engine_factory(), oracle_factory(), **kw)
+    r = r0 + 0.05 * rng.standard_normal((T, nbeads))
+    v = v0 + np.sqrt(temp * nbeads / mass) * rng.standard_normal((T, nbeads))
+    rho = _pure_state(T, model.nstates, 0)
+    draws = rng.random((nsteps, T)); sdraw = rng.random(T)
+    for h in (e, o):
+        h.set_state_diabatic(r, v, rho, None, None, sdraw)
+        h.set_draws(draws)
+    for chunk in range(nsteps // 5):
+        e.run(5); o.run(5)
+        _compare_state(e, o, 1e-9, f"chunk {chunk}")
+        de, do = e.diagnostics(), o.diagnostics()
+        assert rel_err(de["eig"], do["eig"]) < 1e-9
+        assert rel_err(de["nac"], do["nac"]) < 1e-9
+        assert rel_err(de["accel"], do["accel"]) < 1e-9
+    _compare_observables(e, o, ALL_POP_OBS, 1e-9, T)
+
+
+@pytest.mark.parametrize("nbeads", [1, 2, 8, 32])
+def test_rpmd_parity(nbeads):
+    """BASELINE config 3: RPMD on Harmonic, normal-mode Cayley propagation."""
+    T, nsteps = 64, 200
+    rng = np.random.default_rng(19)
+    model = nq.Harmonic(m=1837.0, ω=0.005, r0=0.1)
+    temp = 9.5e-4
+    kw = model_config(model, method=A.METHOD_CLASSICAL, masses=[1837.0], ntraj=T, dt=2.5, nbeads=nbeads, temperature=temp,
+                      save_every=10, nsave=nsteps // 10 + 1, observables=CLASSICAL_OBS, per_trajectory=1)
+    e, o = make_pair(engine_factory(), oracle_factory(), **kw)
+    r = 0.1 + 0.2 * rng.standard_normal((T, nbeads))
+    v = np.sqrt(temp * nbeads / 1837.0) * rng.standard_normal((T, nbeads))
+    for h in (e, o):
+        h.set_state(r, v)
+        h.run(nsteps)
+    _compare_state(e, o, 1e-10, "final")
+    _compare_observables(e, o, CLASSICAL_OBS, 1e-10, T)
+    E = e.observable_per_trajectory(A.OBS_TOTAL_ENERGY)[:, :, 0]
+    assert np.max(np.abs(E - E[:, :1])) < 1e-3 * np.max(np.abs(E))   # symplectic: bounded energy error
+
+
+def test_unsupported_configuration_fails_loudly():
+    """No CPU fallback: a configuration without a kernel is an error, not a silent slow path."""
+    kw = model_config(nq.TullyModelOne(), method=A.METHOD_NRPMD, masses=[2000.0], ntraj=4, dt=1.0)
+    cfg, keep = A.make_config(**kw)
+    with pytest.raises(nq.EngineError) as ei:
+        engine_factory()(cfg, keep)
+    assert ei.value.code == -2
