@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""bench.py -- trajectory-steps/s of the ensemble hot path on N B200s (contract: see the task brief).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--trajectories T] [--impl reference]
+
+A "step" is one whole ensemble job of the named workload: every trajectory advanced over the config's full
+tspan (e.g. 200 nuclear steps of dt = 0.1 for the spin-boson config) with its observables accumulated on the
+device at every save point.  Successive steps continue the same trajectories (work per step is identical).
+
+  value     trajectory-steps/s with the trajectory state resident in HBM (device time, CUDA events on the
+            engine's launch stream, max over ranks).
+  e2e       the same metric through the public C-ABI call sequence with HOST buffers: every step uploads fresh
+            initial conditions from pinned host memory (set_state), runs, and reads the reduced observable back.
+  roofline  FP64: algorithmic flops per trajectory-step x trajectory-steps per launch / kernel
+            time, against the DFMA peak measured in this run (MEASURED_PEAKS.json has no FP64 entry).
+  cpu_baseline  the CPU oracle (a C++ restatement of the reference algorithm, NOT Julia) on the host cores,
+            on a bounded sample of the same workload.
+
+`--impl reference` times that CPU restatement alone (the Julia reference cannot run here: no julia binary).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DEFAULT_WORKLOAD = "spinboson_debye100_fssh"   # BASELINE.json configs[1]
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
+    ap.add_argument("--trajectories", type=int, default=0, help="trajectories PER GPU (default: the config's)")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target duration of the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.proc, self.lines = device, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_model_name():
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def run_cpu_oracle(wl, seconds, seed=1):
+    """Time the CPU restatement (oracle) on a bounded sample of the workload; returns (traj-steps/s, info)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle
+    import nqcdynamics_jl_b200 as nq
+    A = nq._abi
+    cores = oracle.set_num_threads(0)
+    rng = np.random.default_rng(seed)
+
+    def job(T):
+        cfg, keep = A.make_config(**wl.config_kwargs(T, seed=seed))
+        h = oracle.OracleEngine(cfg, keep)
+        ic = wl.sample(rng, T)
+        t0 = time.perf_counter()
+        if wl.method in (A.METHOD_FSSH, A.METHOD_EHRENFEST):
+            h.set_state_diabatic(ic["r"], ic["v"], wl.initial_density(T))
+        else:
+            h.set_state(ic["r"], ic["v"])
+        h.run(wl.nsteps)
+        dt = time.perf_counter() - t0
+        h.close()
+        return dt
+    T = max(cores * 2, 16)
+    dt = job(T)                               # calibration sample
+    rate = T * wl.nsteps / dt
+    T2 = int(max(T, min(rate * seconds / wl.nsteps, 4_000_000)))
+    T2 = max(cores, (T2 // cores) * cores)
+    dt2 = job(T2)
+    value = T2 * wl.nsteps / dt2
+    info = {"value": value, "unit": "trajectory-steps/s", "cores": cores, "kind": "port",
+            "sample": f"{T2} trajectories x {wl.nsteps} steps of {wl.name} ({dt2:.1f} s wall), OpenMP over "
+                      f"trajectories, g++ -O2 -ffp-contract=off, CPU: {cpu_model_name()}; C++ restatement of the "
+                      f"reference algorithm (oracle/), not the Julia reference (no julia binary in this image)"}
+    return value, info, T2, dt2
+
+
+def reference_arm(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    per_step = max(2.0, min(args.cpu_seconds, 120.0 / max(1, args.steps + args.warmup)))
+    times, units = [], []
+    info = None
+    for i in range(args.warmup + args.steps):
+        value, info, T2, dt2 = run_cpu_oracle(wl, per_step, seed=100 + i)
+        if i >= args.warmup:
+            times.append(dt2); units.append(T2 * wl.nsteps)
+    value = sum(units) / sum(times)
+    info["value"] = value
+    line = {"impl": "reference", "metric": "trajectory-steps/sec (FP64)", "value": value, "unit": "trajectory-steps/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl.name, "description": wl.description,
+                       "note": "CPU restatement of the reference algorithm on the host cores; bounded sample per step"},
+            "cpu_baseline": info,
+            "e2e": {"value": value, "unit": "trajectory-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+class _DevArray:
+    """Expose a raw device pointer to torch through __cuda_array_interface__ (for the NCCL all-reduce)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+
+
+def main():
+    args = parse_args()
+    import nqcdynamics_jl_b200 as nq
+    from nqcdynamics_jl_b200 import workloads
+    A = nq._abi
+    wl = workloads.get(args.workload)
+    if args.impl == "reference":
+        reference_arm(args, wl)
+        return
+
+    from nqcdynamics_jl_b200.engine import Engine
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    torch = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = A.load_engine_library()
+    if lib.nqcb200_device_count() <= 0:
+        raise SystemExit("bench.py: no CUDA device visible -- the engine has no CPU path")
+
+    T = args.trajectories or wl.ntraj_default
+    K, W = args.steps, args.warmup
+    density = wl.method in (A.METHOD_FSSH, A.METHOD_EHRENFEST)
+    # one handle, trajectories keep running across the K+W steps; save capacity covers all of them
+    nsave_total = (W + K) * wl.nsteps // wl.save_every + 1
+    kw = wl.config_kwargs(T, seed=20261017, device=local_rank, traj_offset=rank * T)
+    kw["nsave"] = nsave_total
+    cfg, keep = A.make_config(**kw)
+    eng = Engine(cfg, keep)
+    rng = np.random.default_rng(1234 + rank)
+    ic = wl.sample(rng, T)
+    rho = wl.initial_density(T) if density else None
+
+    def upload(h, r, v):
+        if density:
+            h.set_state_diabatic(r, v, rho)
+        else:
+            h.set_state(r, v)
+
+    upload(eng, ic["r"], ic["v"])
+    peak = __import__("ctypes").c_double()
+    lib.nqcb200_measure_fp64_peak(local_rank, __import__("ctypes").byref(peak))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def allreduce_observables(h):
+        if dist is None:
+            return
+        ptr, n = h.observable_sum_device()
+        if n:
+            t = torch.as_tensor(_DevArray(ptr, n), device=f"cuda:{local_rank}")
+            dist.all_reduce(t)
+            torch.cuda.synchronize()
+
+    for _ in range(W):
+        eng.run(wl.nsteps)
+    allreduce_observables(eng)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    kernel_ms, launches = 0.0, 0
+    t0 = time.perf_counter()
+    for _ in range(K):
+        eng.run(wl.nsteps)                      # blocking; device time from CUDA events on the launch stream
+        ms, nl = eng.last_run_timing()
+        kernel_ms += ms; launches += nl
+    allreduce_observables(eng)                  # the job's only exchange: one all-reduce of the accumulators
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    barrier()
+    # device-timed value: max over ranks of the summed kernel time (+ the measured wall for the collective)
+    dev_s = kernel_ms * 1e-3
+    if dist is not None:
+        tt = torch.tensor([dev_s, wall], device=f"cuda:{local_rank}", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dev_s, wall = float(tt[0]), float(tt[1])
+        region_s = wall                          # includes the NCCL all-reduce
+    else:
+        region_s = dev_s
+    units = float(T) * world * wl.nsteps * K
+    value = units / region_s
+    counters = eng.counters()
+    obs_check = float(np.sum(eng.observable_sum(A.OBS_POPCORR_DIABATIC)[0])) if (wl.observables >> A.OBS_POPCORR_DIABATIC) & 1 else None
+
+    # ---- end-to-end through the C ABI with host buffers -------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        try:
+            import torch as _t
+            pin = lambda a: _t.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+        except Exception:
+            pin = np.ascontiguousarray
+        kw2 = wl.config_kwargs(T, seed=7, device=local_rank, traj_offset=rank * T)
+        cfg2, keep2 = A.make_config(**kw2)
+        eng.close()
+        eng2 = Engine(cfg2, keep2)
+        r_h, v_h = pin(ic["r"]), pin(ic["v"])
+        first_obs = next(o for o in range(A.OBS_COUNT) if (wl.observables >> o) & 1)
+        h2d = r_h.nbytes + v_h.nbytes + (rho.nbytes if density else 0)
+        d2h = 0
+        ke = max(1, min(K, 3))
+        upload(eng2, r_h, v_h); eng2.run(wl.nsteps)            # warm-up job
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(ke):
+            upload(eng2, r_h, v_h)
+            eng2.run(wl.nsteps)
+            allreduce_observables(eng2)
+            out = eng2.observable_sum(first_obs)
+            d2h = out.nbytes
+        e2e_s = time.perf_counter() - t0
+        barrier()
+        if dist is not None:
+            tt = torch.tensor([e2e_s], device=f"cuda:{local_rank}", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            e2e_s = float(tt[0])
+        e2e = {"value": float(T) * world * wl.nsteps * ke / e2e_s, "unit": "trajectory-steps/s",
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": ke,
+               "path": "nqcb200_set_state_diabatic (pinned host r, v, rho) -> nqcb200_run -> nqcb200_get_observable_sum"}
+        eng2.close()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        _, cpu, _, _ = run_cpu_oracle(wl, args.cpu_seconds)
+
+    if rank == 0:
+        per_launch_units = float(T) * wl.nsteps            # one run() = one launch (<= 65536 steps)
+        kernel_s_per_launch = (kernel_ms * 1e-3) / max(1, launches)
+        achieved = wl.flops_per_traj_step * per_launch_units / kernel_s_per_launch / 1e12
+        line = {
+            "metric": "trajectory-steps/sec (FP64)", "value": value, "unit": "trajectory-steps/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": 1e3 * region_s / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl.name, "description": wl.description, "trajectories_per_gpu": T,
+                       "nuclear_steps_per_step": wl.nsteps, "save_every": wl.save_every,
+                       "observables_on_device": [o for o in range(A.OBS_COUNT) if (wl.observables >> o) & 1],
+                       "l2": "trajectory state larger than L2" if T * 8 * 3 * len(wl.masses) * wl.nbeads > 126e6
+                             else "state register-resident for the whole launch; no reuse of cached inputs between steps",
+                       "parallelism": f"trajectories sharded over {world} GPU(s), one NCCL all-reduce of observables"},
+            "e2e": e2e,
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "fp64", "achieved": achieved, "peak": float(peak.value), "unit": "TFLOP/s",
+                         "frac": achieved / float(peak.value) if peak.value else None, "traffic": None,
+                         "flops_per_trajectory_step_algorithmic": wl.flops_per_traj_step,
+                         "peak_source": "DFMA microbenchmark measured in this run (nqcb200_measure_fp64_peak); "
+                                        "MEASURED_PEAKS.json has no FP64 entry",
+                         "note": "algorithmic = the reference's dense complex formulation (SURVEY.md 8d); the kernel "
+                                 "executes fewer flops (Hermitian/antisymmetric structure), see DESIGN.md"},
+            "cpu_baseline": cpu,
+            "counters": counters, "kernel_ms_total": kernel_ms, "wall_s_timed_region": wall,
+            "observable_checksum": obs_check,
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -279,6 +279,10 @@ int nqcb200_get_counters(nqcb200_handle* h, int64_t* steps, int64_t* hops, int64
 int nqcb200_get_progress(nqcb200_handle* h, int64_t* nsave_done, int64_t* step_count);
 int nqcb200_get_last_run_timing(nqcb200_handle* h, double* kernel_ms, int64_t* launches);
 
+/* Measured FP64 FMA peak of `device` in TFLOP/s (a DFMA-saturating microbenchmark; the roofline
+ * denominator for this FP64 path -- MEASURED_PEAKS.json only carries HBM and bf16 numbers).      */
+int nqcb200_measure_fp64_peak(int device, double* tflops);
+
 #ifdef __cplusplus
 }
 #endif

@@ -101,13 +101,14 @@ def bind(lib: C.CDLL, prefix: str) -> None:
     f("get_counters", [H, _lp, _lp, _lp, _lp])
     f("get_progress", [H, _lp, _lp])
     f("get_last_run_timing", [H, _dp, _lp], required=False)
+    f("measure_fp64_peak", [C.c_int, _dp], required=False)
 
 
 HEADER_SYMBOLS = [
     "version", "device_count", "create", "destroy", "last_error", "observable_width", "set_state",
     "set_state_diabatic", "set_mapping", "set_gauge_reference", "set_draws", "run", "get_state", "get_mapping",
     "get_observable_sum", "observable_sum_device", "observable_offset", "get_observable_per_trajectory",
-    "get_diagnostics", "get_counters", "get_progress", "get_last_run_timing",
+    "get_diagnostics", "get_counters", "get_progress", "get_last_run_timing", "measure_fp64_peak",
 ]
 
 _ENGINE_LIB: Optional[C.CDLL] = None

@@ -214,6 +214,23 @@ __global__ void count_nonfinite(const double* r, const double* v, int64_t T, int
     if (bad) atomicAdd(out, 1ull);
 }
 
+// FP64 roofline denominator: MEASURED_PEAKS.json carries only HBM and bf16 numbers, so the DFMA
+// peak is measured in-run: 16 independent FMA chains per thread, every SM saturated.
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, double seed) {
+    double a[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = seed + i * 1e-3 + threadIdx.x * 1e-6;
+    const double m = 1.0000001, c = 1e-9;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) a[i] = fma(a[i], m, c);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += a[i];
+    if (s == 123.456) out[0] = s;   // never true: keeps the chains alive
+}
+
 int obs_width(const nqcb200_config& c, int id) {
     const int n = c.nstates, D = c.ndofs;
     switch (id) {
@@ -705,6 +722,33 @@ int nqcb200_get_progress(nqcb200_handle* h, int64_t* nsave_done, int64_t* step_c
     if (!h) return NQCB200_ERR_INVALID;
     if (nsave_done) *nsave_done = h->nsave_done;
     if (step_count) *step_count = h->step_count;
+    return NQCB200_OK;
+}
+
+int nqcb200_measure_fp64_peak(int device, double* tflops) {
+    if (!tflops) return NQCB200_ERR_INVALID;
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return NQCB200_ERR_NO_DEVICE; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { cudaGetLastError(); return NQCB200_ERR_CUDA; }
+    double* d = nullptr;
+    cudaEvent_t e0, e1;
+    if (cudaMalloc(&d, sizeof(double)) != cudaSuccess) { cudaGetLastError(); return NQCB200_ERR_NOMEM; }
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const int iters = 1 << 14, blocks = prop.multiProcessorCount * 8, threads = 256;
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0);
+        dfma_peak_kernel<<<blocks, threads>>>(d, iters, 1.0 + rep);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double flops = 2.0 * 16.0 * iters * (double)blocks * threads;
+        if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    if (cudaGetLastError() != cudaSuccess) return NQCB200_ERR_CUDA;
+    *tflops = best;
     return NQCB200_OK;
 }
 

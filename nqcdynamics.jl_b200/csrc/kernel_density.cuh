@@ -28,10 +28,20 @@ namespace nq {
 
 #if defined(__CUDACC__)
 
+// Sum over the L lanes that share one trajectory.  The shuffle mask names only that lane group, so
+// the reduction is legal inside branches taken by whole groups (the hop / rescale path) while other
+// trajectories of the same warp are elsewhere.
+template <int L>
+NQ_D unsigned group_mask() {
+    if (L >= 32) return 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31u;
+    return ((1u << L) - 1u) << (lane & ~(unsigned)(L - 1));
+}
 template <int L>
 NQ_D double lane_sum(double x) {
+    const unsigned mask = group_mask<L>();
 #pragma unroll
-    for (int o = L / 2; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    for (int o = L / 2; o > 0; o >>= 1) x += __shfl_xor_sync(mask, x, o);
     return x;
 }
 NQ_D double warp_sum(double x) { return lane_sum<32>(x); }

@@ -1,0 +1,163 @@
+"""The BASELINE.json configurations as seeded synthetic workloads.
+
+Each workload fixes the model, method, time step, run length, save grid, observables and a sampler for the
+initial conditions, plus the ALGORITHMIC flop count per trajectory-step from SURVEY.md 8d (the reference's
+dense formulation), which is the numerator of the reported roofline.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Callable, Dict, Optional
+
+import numpy as np
+
+from . import _abi as A
+from . import models
+
+
+def fssh_flops(n: int, D: int, f_model: float, eig: Optional[float] = None) -> float:
+    """F_model + E(n) + (4n^3+3n^2+2n+9) D + 496 n^3 + 730 n^2 + 10 n."""
+    E = 40.0 if n == 2 else 9.0 * n ** 3
+    if eig is not None:
+        E = eig
+    return f_model + E + (4 * n ** 3 + 3 * n ** 2 + 2 * n + 9) * D + 496 * n ** 3 + 730 * n ** 2 + 10 * n
+
+
+def ehrenfest_flops(n: int, D: int, f_model: float) -> float:
+    """FSSH count minus the hop test (2nD + 10n) plus the mean-field force (2 n^2 D instead of D)."""
+    return fssh_flops(n, D, f_model) - (2 * n * D + 10 * n) + (2 * n * n - 1) * D
+
+
+def rpmd_flops(B: int, D: int, f_model: float) -> float:
+    """RP nuclear part (BCB): 8 B^2 D dense normal-mode transforms + 14 B D, plus the model per bead."""
+    return 8 * B * B * D + 14 * B * D + B * f_model
+
+
+def rpsh_flops(n: int, D: int, B: int, f_model: float) -> float:
+    E = 40.0 if n == 2 else 9.0 * n ** 3
+    return (B + 1) * (f_model + E + (4 * n ** 3 + n * n) * D) + 8 * B * B * D + 14 * B * D + 496 * n ** 3 + 730 * n * n
+
+
+@dataclass
+class Workload:
+    name: str
+    description: str
+    model: models.Model
+    method: int
+    masses: np.ndarray
+    dt: float
+    nsteps: int                  # nuclear steps of one job (tspan / dt)
+    save_every: int
+    observables: int
+    ntraj_default: int
+    flops_per_traj_step: float
+    sample: Callable[[np.random.Generator, int], Dict[str, np.ndarray]]
+    nbeads: int = 1
+    temperature: float = 0.0
+    initial_diabatic_state: int = 0      # 0-based PureState index (diabatic basis)
+    rescaling: int = A.RESCALE_STANDARD
+
+    @property
+    def nsave(self) -> int:
+        return self.nsteps // self.save_every + 1
+
+    def config_kwargs(self, ntraj: int, **extra):
+        D = len(self.masses)
+        kw = dict(method=self.method, model=self.model.kind, nstates=self.model.nstates, ndofs=D, masses=self.masses,
+                  ntraj=ntraj, dt=self.dt, nbeads=self.nbeads, params=self.model.params, bath_a=self.model.bath_a,
+                  bath_b=self.model.bath_b, save_every=self.save_every, nsave=self.nsave,
+                  observables=self.observables, temperature=self.temperature, rescaling=self.rescaling,
+                  nelectrons=self.model.nelectrons)
+        kw.update(extra)
+        return kw
+
+    def initial_density(self, ntraj: int) -> np.ndarray:
+        n = self.model.nstates
+        rho = np.zeros((ntraj, n, n))
+        rho[:, self.initial_diabatic_state, self.initial_diabatic_state] = 1.0
+        return rho
+
+
+def _tully1_fssh() -> Workload:
+    # C1: docs/src/ensemble_simulations.md:39-55 -- Atoms(2000), k = 10, r ~ Normal(-8, 1), PureState(2)
+    def sample(rng, T):
+        return {"r": rng.normal(-8.0, 1.0, (T, 1, 1)), "v": np.full((T, 1, 1), 10.0 / 2000.0)}
+    obs = (1 << A.OBS_DIABATIC_POP) | (1 << A.OBS_SCATTERING)
+    return Workload("tully1_fssh", "C1 TullyModelOne FSSH, n=2, D=1, mass 2000, k0=10, dt=1, tspan (0,3000), saveat 10",
+                    models.TullyModelOne(), A.METHOD_FSSH, np.array([2000.0]), 1.0, 3000, 10, obs, 1 << 22,
+                    fssh_flops(2, 1, 30.0), sample, initial_diabatic_state=1)
+
+
+def _spinboson(method: int, name: str) -> Workload:
+    # C2: SpinBoson(DebyeSpectralDensity(0.25, 0.5), 100, 0, 1), beta = 5, dt = 0.1, tspan (0, 20)
+    N = 100
+    model = models.SpinBoson(models.DebyeSpectralDensity(0.25, 0.5), N, 0.0, 1.0)
+    w = model.bath_a
+    beta = 5.0
+    sr = np.sqrt(1.0 / (2.0 * w * np.tanh(beta * w / 2.0)))   # harmonic Wigner, m = 1
+    sv = np.sqrt(w / (2.0 * np.tanh(beta * w / 2.0)))
+
+    def sample(rng, T):
+        return {"r": (rng.standard_normal((T, N)) * sr).reshape(T, 1, N),
+                "v": (rng.standard_normal((T, N)) * sv).reshape(T, 1, N)}
+    obs = (1 << A.OBS_POPCORR_DIABATIC)
+    flops = fssh_flops(2, N, 6.0 * N) if method == A.METHOD_FSSH else ehrenfest_flops(2, N, 6.0 * N)
+    return Workload(name, "C2 SpinBoson (Debye bath, 100 modes), n=2, D=100, beta=5, dt=0.1, tspan (0,20), saveat 0.1",
+                    model, method, np.ones(N), 0.1, 200, 1, obs, 1_000_000, flops, sample)
+
+
+def _rpmd_harmonic() -> Workload:
+    # C3: RingPolymerSimulation{Classical}(Atoms(:H), Harmonic(m, w), 32; T = 300 K), exact thermal sample
+    B, m, w = 32, 1837.4715941070515, 0.005
+    kT = 300.0 * 3.166811563e-6
+    beta_B = 1.0 / (kT * B)
+    omega_n = B * kT
+    wk = 2.0 * omega_n * np.sin(np.arange(B) * np.pi / B)
+    U = np.empty((B, B))
+    for k in range(B):
+        j = np.arange(B)
+        if k == 0: U[:, k] = 1 / np.sqrt(B)
+        elif 2 * k < B: U[:, k] = np.sqrt(2 / B) * np.cos(2 * np.pi * j * k / B)
+        elif 2 * k == B: U[:, k] = (-1.0) ** j / np.sqrt(B)
+        else: U[:, k] = np.sqrt(2 / B) * np.sin(2 * np.pi * j * k / B)
+    sr = np.sqrt(1.0 / (beta_B * m * (wk ** 2 + w ** 2)))
+    sv = np.sqrt(1.0 / (beta_B * m))
+
+    def sample(rng, T):
+        rn = rng.standard_normal((T, B)) * sr
+        vn = rng.standard_normal((T, B)) * sv
+        return {"r": (rn @ U.T).reshape(T, B, 1), "v": (vn @ U.T).reshape(T, B, 1)}
+    obs = (1 << A.OBS_POSITION) | (1 << A.OBS_KINETIC) | (1 << A.OBS_TOTAL_ENERGY)
+    return Workload("rpmd_harmonic32", "C3 RPMD 32 beads, Harmonic(m_H, w=0.005), 300 K thermal sample, dt=2.5, 10^4 steps, saveat 100",
+                    models.Harmonic(m=m, ω=w), A.METHOD_CLASSICAL, np.array([m]), 2.5, 10000, 100, obs, 1 << 20,
+                    rpmd_flops(B, 1, 3.0), sample, nbeads=B, temperature=kT)
+
+
+def _rpsh_morse() -> Workload:
+    # C5: RingPolymerSimulation{FSSH}(Atoms(20000), ThreeStateMorse(), 16; T = 300 K)
+    B, m = 16, 20000.0
+    kT = 300.0 * 3.166811563e-6
+
+    def sample(rng, T):
+        return {"r": rng.normal(2.1, 1.0 / np.sqrt(m * 0.005), (T, B, 1)),
+                "v": rng.standard_normal((T, B, 1)) * np.sqrt(kT * B / m)}
+    obs = (1 << A.OBS_POPCORR_DIABATIC)
+    return Workload("rpsh_morse3_16", "C5 RPSH 16 beads, ThreeStateMorse, mass 20000, 300 K, dt=1, tspan (0,3000), saveat 50",
+                    models.ThreeStateMorse(), A.METHOD_FSSH, np.array([m]), 1.0, 3000, 50, obs, 100_000,
+                    rpsh_flops(3, 1, B, 60.0), sample, nbeads=B, temperature=kT)
+
+
+def get(name: str) -> Workload:
+    table = {
+        "tully1_fssh": _tully1_fssh,
+        "spinboson_debye100_fssh": lambda: _spinboson(A.METHOD_FSSH, "spinboson_debye100_fssh"),
+        "spinboson_debye100_ehrenfest": lambda: _spinboson(A.METHOD_EHRENFEST, "spinboson_debye100_ehrenfest"),
+        "rpmd_harmonic32": _rpmd_harmonic,
+        "rpsh_morse3_16": _rpsh_morse,
+    }
+    if name not in table:
+        raise KeyError(f"unknown workload {name!r}; available: {sorted(table)}")
+    return table[name]()
+
+
+NAMES = ["tully1_fssh", "spinboson_debye100_fssh", "spinboson_debye100_ehrenfest", "rpmd_harmonic32", "rpsh_morse3_16"]
