@@ -1,0 +1,429 @@
+"""Host-side mirror of the reference's user interface for the ensemble hot path.
+
+Same names, argument meaning and return shapes as NQCDynamics.jl (Julia cannot run in this image, so the host
+side above the C ABI is Python; the Julia shim that binds the same ABI is in INTEGRATION.md):
+
+    sim = Simulation[FSSH](Atoms(2000), TullyModelOne())             # Simulation{FSSH}(atoms, model)
+    out = run_dynamics(sim, (0.0, 3000.0), distribution; output=..., trajectories=..., dt=1.0,
+                       ensemble_algorithm=EnsembleB200(ngpus))        # src/Ensembles/run_dynamics.jl:42-136
+
+Every trajectory is stepped on the GPU by ``libnqcb200.so``; there is no CPU path -- unsupported
+(method, model, output) combinations raise.
+"""
+from __future__ import annotations
+
+import threading
+from dataclasses import dataclass, field
+from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+
+from . import _abi as A
+from . import models as _models
+from .engine import Engine, device_count
+
+# ---- atoms -------------------------------------------------------------------------------------
+_AMU = 1822.888486209          # atomic mass unit in electron masses
+_SYMBOL_MASS = {"H": 1.008 * _AMU, "D": 2.014 * _AMU, "C": 12.011 * _AMU, "N": 14.007 * _AMU, "O": 15.999 * _AMU}
+
+
+class Atoms:
+    """``Atoms(2000)`` = one atom of mass 2000 a.u.; ``Atoms([:H, :H])`` -> periodic-table masses
+    (docs/src/atoms.md:16-21)."""
+
+    def __init__(self, spec):
+        if np.isscalar(spec) and not isinstance(spec, str):
+            self.types, self.masses = ["X"], np.array([float(spec)])
+        elif isinstance(spec, str):
+            self.types, self.masses = [spec], np.array([_SYMBOL_MASS[spec]])
+        else:
+            spec = list(spec)
+            if spec and isinstance(spec[0], str):
+                self.types, self.masses = spec, np.array([_SYMBOL_MASS[s] for s in spec])
+            else:
+                self.types, self.masses = ["X"] * len(spec), np.asarray(spec, dtype=np.float64)
+
+    def __len__(self):
+        return len(self.masses)
+
+
+# ---- dynamics methods (reference: DynamicsMethods.Method subtypes) -------------------------------
+@dataclass
+class FSSH:
+    rescaling: str = "standard"          # :standard | :vinversion | :off  (fssh.jl:41)
+    method_id: int = A.METHOD_FSSH
+
+
+@dataclass
+class Ehrenfest:
+    method_id: int = A.METHOD_EHRENFEST
+
+
+@dataclass
+class Classical:
+    method_id: int = A.METHOD_CLASSICAL
+
+
+@dataclass
+class AdiabaticIESH:
+    rescaling: str = "standard"
+    estimate_probability: bool = True
+    disable_hopping: bool = False
+    decoherence_C: float = 0.0           # DecoherenceCorrectionEDC(C) when > 0 (iesh.jl:72-74)
+    method_id: int = A.METHOD_IESH
+
+
+@dataclass
+class NRPMD:
+    γ: float = 0.5                        # nrpmd.jl:43
+    method_id: int = A.METHOD_NRPMD
+
+
+_RESCALE = {"standard": A.RESCALE_STANDARD, "vinversion": A.RESCALE_VINVERSION, "off": A.RESCALE_OFF}
+
+
+class _Parametric(type):
+    """``Simulation[FSSH](atoms, model, **kw)`` mirrors Julia's ``Simulation{FSSH}(atoms, model; kw...)``."""
+
+    def __getitem__(cls, method_type):
+        def construct(atoms, model, *args, **kw):
+            method_kw = {k: kw.pop(k) for k in list(kw) if k in getattr(method_type, "__dataclass_fields__", {})}
+            return cls(atoms, model, method_type(**method_kw), *args, **kw)
+        return construct
+
+
+class Simulation(metaclass=_Parametric):
+    """simulations.jl:12-44.  ``size(sim) = (ndofs, natoms)``."""
+
+    def __init__(self, atoms: Atoms, model: _models.Model, method=None, temperature: float = 0.0):
+        self.atoms, self.model, self.method = atoms, model, method or Classical()
+        self.temperature = float(temperature)
+        if model.natoms is not None and model.natoms != len(atoms):
+            raise ValueError(f"{model.name} expects {model.natoms} atoms, got {len(atoms)}")
+        self.beads = 1
+
+    @property
+    def size(self) -> Tuple[int, ...]:
+        return (self.model.ndofs, len(self.atoms))
+
+    @property
+    def ndofs_total(self) -> int:
+        return self.model.ndofs * len(self.atoms)
+
+    @property
+    def dof_masses(self) -> np.ndarray:
+        return np.repeat(self.atoms.masses, self.model.ndofs)
+
+
+class RingPolymerSimulation(Simulation):
+    """simulations.jl:46-73.  ``size(sim) = (ndofs, natoms, nbeads)``; omega_n = nbeads * temperature."""
+
+    def __init__(self, atoms, model, method=None, n_beads: int = 1, temperature: float = 0.0):
+        super().__init__(atoms, model, method, temperature)
+        self.beads = int(n_beads)
+
+    @property
+    def size(self):
+        return (self.model.ndofs, len(self.atoms), self.beads)
+
+
+# ---- distributions (NQCDistributions.jl, external) ------------------------------------------------
+@dataclass
+class Normal:
+    μ: float = 0.0
+    σ: float = 1.0
+
+    def sample(self, rng, shape):
+        return rng.normal(self.μ, self.σ, shape)
+
+
+@dataclass
+class VelocityBoltzmann:
+    """v ~ Normal(0, sqrt(T/m)) per atom (src/NQCDistributions-convenience.jl:16-42)."""
+    temperature: float
+    masses: Sequence[float]
+    dims: Tuple[int, int]
+
+    def sample(self, rng, shape):
+        sd = np.sqrt(self.temperature / np.repeat(np.asarray(self.masses, dtype=float), self.dims[0]))
+        return rng.standard_normal(shape) * sd
+
+
+class Diabatic:
+    pass
+
+
+class Adiabatic:
+    pass
+
+
+@dataclass
+class PureState:
+    """``PureState(i)`` is diabatic by default; 1-based state index."""
+    state: int
+    statetype: Any = field(default_factory=Diabatic)
+
+    def __mul__(self, other):
+        return ProductDistribution(other, self)
+
+    __rmul__ = __mul__
+
+
+@dataclass
+class DynamicalDistribution:
+    """``DynamicalDistribution(velocity, position, size)``: each entry a number, an array (broadcast over
+    trajectories or indexed by trajectory on the leading axis) or a samplable distribution."""
+    velocity: Any
+    position: Any
+    size: Tuple[int, ...]
+
+    def __mul__(self, electronic):
+        return ProductDistribution(self, electronic)
+
+    __rmul__ = __mul__
+
+    def _to_flat(self, x):
+        """One configuration in the Julia layout (ndofs, natoms[, nbeads]) -> (B, D), D index = dof + ndofs*atom."""
+        x = np.asarray(x, dtype=np.float64)
+        D = int(np.prod(self.size[:2]))
+        B = self.size[2] if len(self.size) > 2 else 1
+        if x.ndim == 3:
+            return x.transpose(2, 1, 0).reshape(B, D)
+        if x.ndim == 2 and x.shape == tuple(self.size[:2]):
+            return np.broadcast_to(x.T.reshape(1, D), (B, D))
+        return np.broadcast_to(x.reshape(-1), (B, D)) if x.size == D else x.reshape(B, D)
+
+    def _draw(self, spec, rng, T, selection):
+        D = int(np.prod(self.size[:2]))
+        B = self.size[2] if len(self.size) > 2 else 1
+        shape = (T, B, D)
+        if hasattr(spec, "sample"):
+            return np.ascontiguousarray(spec.sample(rng, shape))
+        if isinstance(spec, (list, tuple)) and len(spec) and np.ndim(spec[0]) >= 1:
+            # a vector of configurations: OrderedSelection (selection given) or RandomSelection (selections.jl:24-36)
+            idx = [j - 1 for j in selection] if selection is not None else rng.integers(0, len(spec), T)
+            return np.ascontiguousarray(np.stack([self._to_flat(spec[i]) for i in idx]))
+        arr = np.asarray(spec, dtype=np.float64)
+        if arr.ndim == 0:
+            return np.full(shape, float(arr))
+        return np.ascontiguousarray(np.broadcast_to(self._to_flat(arr), shape))
+
+    def sample(self, rng, T, selection=None):
+        return self._draw(self.position, rng, T, selection), self._draw(self.velocity, rng, T, selection)
+
+
+@dataclass
+class ProductDistribution:
+    nuclear: DynamicalDistribution
+    electronic: PureState
+
+
+# ---- outputs (src/DynamicsOutputs.jl, src/TimeCorrelationFunctions.jl) ----------------------------
+@dataclass(frozen=True)
+class _Output:
+    name: str
+    obs: int
+    kind: str = "series"      # series | final | hops | scatter
+
+
+OutputDiabaticPopulation = _Output("OutputDiabaticPopulation", A.OBS_DIABATIC_POP)
+OutputAdiabaticPopulation = _Output("OutputAdiabaticPopulation", A.OBS_ADIABATIC_POP)
+OutputKineticEnergy = _Output("OutputKineticEnergy", A.OBS_KINETIC)
+OutputPotentialEnergy = _Output("OutputPotentialEnergy", A.OBS_POTENTIAL)
+OutputTotalEnergy = _Output("OutputTotalEnergy", A.OBS_TOTAL_ENERGY)
+OutputPosition = _Output("OutputPosition", A.OBS_POSITION)
+OutputVelocity = _Output("OutputVelocity", A.OBS_VELOCITY)
+OutputCentroidPosition = _Output("OutputCentroidPosition", A.OBS_POSITION)
+OutputCentroidVelocity = _Output("OutputCentroidVelocity", A.OBS_VELOCITY)
+OutputDiscreteState = _Output("OutputDiscreteState", A.OBS_DISCRETE_STATE)
+OutputQuantumSubsystem = _Output("OutputQuantumSubsystem", A.OBS_SIGMA)
+OutputSurfaceHops = _Output("OutputSurfaceHops", A.OBS_DISCRETE_STATE, "hops")
+
+
+def OutputStateResolvedScattering1D(sim, type="adiabatic"):      # DynamicsOutputs.jl:313-338
+    if type not in ("adiabatic", "diabatic"):
+        raise ValueError(f"{type} not recognised. Only `:diabatic` or `:adiabatic` accepted.")
+    return _Output("OutputStateResolvedScattering1D",
+                   A.OBS_SCATTERING if type == "adiabatic" else A.OBS_SCATTERING_DIABATIC, "scatter")
+
+
+def PopulationCorrelationFunction(sim, statetype=None):          # TimeCorrelationFunctions.jl:61-88
+    adiabatic = isinstance(statetype, Adiabatic) or statetype is Adiabatic
+    return _Output("PopulationCorrelationFunction", A.OBS_POPCORR_ADIABATIC if adiabatic else A.OBS_POPCORR_DIABATIC)
+
+
+# ---- reductions (src/Ensembles/reductions.jl) ------------------------------------------------------
+class SortByTrajectoryReduction:
+    pass
+
+
+class SortByOutputReduction:
+    pass
+
+
+class SumReduction:
+    pass
+
+
+class MeanReduction:
+    pass
+
+
+@dataclass
+class EnsembleB200:
+    """``ensemble_algorithm=EnsembleB200(ngpus)``: shard trajectories over ``ngpus`` B200s of this node."""
+    ngpus: int = 1
+
+
+# ---- run_dynamics ----------------------------------------------------------------------------------
+def _shape_series(sim, out: _Output, arr: np.ndarray):
+    """arr: (nsave, width) -> the reference's per-frame value shape."""
+    n = sim.model.nstates
+    if out.obs in (A.OBS_POPCORR_DIABATIC, A.OBS_POPCORR_ADIABATIC):
+        return arr.reshape(-1, n, n).transpose(0, 2, 1)          # column-major (i, j) per frame
+    if out.obs == A.OBS_SIGMA:
+        c = arr.reshape(-1, 2, n, n)
+        return (c[:, 0] + 1j * c[:, 1]).transpose(0, 2, 1)
+    if out.obs in (A.OBS_POSITION, A.OBS_VELOCITY):
+        return arr.reshape((-1,) + tuple(reversed(sim.size[:2]))).transpose(0, 2, 1)   # (nsave, ndofs, natoms)
+    if arr.shape[1] == 1:
+        return arr[:, 0]
+    return arr
+
+
+def _finalise(sim, out: _Output, arr: np.ndarray, per_trajectory: bool):
+    """Engine array -> reference output value.  arr: (nsave, width) (reduced) or that per trajectory."""
+    if out.kind == "scatter":
+        last = arr[-1]
+        n = sim.model.nstates
+        return {"reflection": last[:n].copy(), "transmission": last[n:].copy()}
+    if out.kind == "hops":
+        if not per_trajectory:
+            raise ValueError("OutputSurfaceHops needs per-trajectory states (use SortByTrajectoryReduction)")
+        st = np.rint(arr).astype(np.int64)
+        return int(np.count_nonzero(np.any(st[1:] != st[:-1], axis=1)))
+    val = _shape_series(sim, out, arr)
+    if out.obs == A.OBS_DISCRETE_STATE:
+        val = np.rint(val).astype(np.int64)
+    return val
+
+
+def run_dynamics(sim: Simulation, tspan, distribution, *, output, selection: Optional[Sequence[int]] = None,
+                 reduction=None, ensemble_algorithm: Optional[EnsembleB200] = None, trajectories: int = 1,
+                 dt: float = 1.0, saveat: Optional[float] = None, savetime: bool = True, seed: Optional[int] = None,
+                 draws: Optional[np.ndarray] = None, **kwargs):
+    """Run ``trajectories`` trajectories over ``tspan`` sampling ``distribution`` (run_dynamics.jl:42-136).
+
+    Keywords follow the reference; ``saveat`` must be a multiple of ``dt`` (the engine's integrators are
+    fixed-step, like the reference's custom algorithms).  Extra: ``seed`` (Philox key / IC sampling) and
+    ``draws`` (parity mode: uniform hop draws of shape (nsteps, trajectories)).  The reference's
+    ``precompile_dynamics`` pass is skipped (nothing to JIT)."""
+    kwargs.pop("precompile_dynamics", None)
+    if kwargs:
+        raise TypeError(f"unsupported keyword(s) for the B200 ensemble path: {sorted(kwargs)}")
+    reduction = reduction or SortByTrajectoryReduction()
+    alg = ensemble_algorithm or EnsembleB200(1)
+    outputs = output if isinstance(output, (tuple, list)) else (output,)
+    for o in outputs:
+        if not isinstance(o, _Output):
+            raise TypeError("EnsembleB200 evaluates outputs on the device: pass Output* objects of this package "
+                            "(arbitrary f(sol, i) closures are not supported on this path)")
+    T = int(trajectories)
+    t0, t1 = float(tspan[0]), float(tspan[1])
+    nsteps = int(round((t1 - t0) / dt))
+    save_every = 1 if saveat is None else int(round(float(saveat) / dt))
+    if save_every < 1 or (saveat is not None and abs(save_every * dt - float(saveat)) > 1e-9 * max(1.0, abs(float(saveat)))):
+        raise ValueError("saveat must be a positive multiple of dt")
+    nsave = nsteps // save_every + 1
+    per_traj = isinstance(reduction, (SortByTrajectoryReduction, SortByOutputReduction))
+    obs_mask = 0
+    for o in outputs:
+        obs_mask |= 1 << o.obs
+
+    method, model = sim.method, sim.model
+    rng = np.random.default_rng(seed)
+    if isinstance(distribution, ProductDistribution):
+        nuclear, electronic = distribution.nuclear, distribution.electronic
+    else:
+        nuclear, electronic = distribution, None
+    r, v = nuclear.sample(rng, T, selection)
+    density = method.method_id in (A.METHOD_FSSH, A.METHOD_EHRENFEST)
+    if density and electronic is None:
+        raise ValueError("FSSH / Ehrenfest need an electronic distribution: nuclear * PureState(i)")
+
+    ngpus = max(1, int(alg.ngpus))
+    if ngpus > device_count():
+        raise RuntimeError(f"EnsembleB200({ngpus}) but only {device_count()} CUDA device(s) visible")
+    bounds = np.linspace(0, T, ngpus + 1).astype(np.int64)
+    engine_seed = int(rng.integers(0, 2 ** 63 - 1)) if seed is None else int(seed)
+    results: List[Any] = [None] * ngpus
+    errors: List[BaseException] = []
+
+    def shard(g):
+        try:
+            lo, hi = int(bounds[g]), int(bounds[g + 1])
+            Tg = hi - lo
+            cfg, keep = A.make_config(
+                method=method.method_id, model=model.kind, nstates=model.nstates, ndofs=sim.ndofs_total,
+                masses=sim.dof_masses, ntraj=Tg, dt=dt, nbeads=sim.beads, nelectrons=model.nelectrons,
+                params=model.params, bath_a=model.bath_a, bath_b=model.bath_b,
+                rescaling=_RESCALE[getattr(method, "rescaling", "standard")],
+                estimate_probability=int(getattr(method, "estimate_probability", True)),
+                disable_hopping=int(getattr(method, "disable_hopping", False)),
+                rng=A.RNG_INJECTED if draws is not None else A.RNG_PHILOX, device=g, save_every=save_every,
+                nsave=nsave, per_trajectory=int(per_traj), observables=obs_mask, traj_offset=lo, seed=engine_seed,
+                t0=t0, temperature=sim.temperature, nrpmd_gamma=getattr(method, "γ", 0.5),
+                edc_C=getattr(method, "decoherence_C", 0.0))
+            with Engine(cfg, keep) as eng:
+                rg, vg = r[lo:hi], v[lo:hi]
+                if density:
+                    n = model.nstates
+                    rho = np.zeros((Tg, n, n))
+                    rho[:, electronic.state - 1, electronic.state - 1] = 1.0
+                    adiabatic = isinstance(electronic.statetype, Adiabatic) or electronic.statetype is Adiabatic
+                    if adiabatic:
+                        state = np.full(Tg, electronic.state, dtype=np.int32) if method.method_id == A.METHOD_FSSH else None
+                        eng.set_state(rg, vg, rho, None, state)
+                    else:
+                        eng.set_state_diabatic(rg, vg, rho)
+                else:
+                    eng.set_state(rg, vg)
+                if draws is not None:
+                    eng.set_draws(np.ascontiguousarray(draws[:, lo:hi]))
+                eng.run(nsteps)
+                res = {}
+                for o in outputs:
+                    res[o] = eng.observable_per_trajectory(o.obs) if per_traj else eng.observable_sum(o.obs)
+                results[g] = res
+        except BaseException as exc:   # re-raised on the caller's thread
+            errors.append(exc)
+
+    if ngpus == 1:
+        shard(0)
+    else:
+        threads = [threading.Thread(target=shard, args=(g,)) for g in range(ngpus)]
+        for th in threads: th.start()
+        for th in threads: th.join()
+    if errors:
+        raise errors[0]
+
+    time = t0 + dt * save_every * np.arange(nsave)
+    if per_traj:
+        per_out = {o: np.concatenate([res[o] for res in results], axis=0) for o in outputs}    # (T, nsave, w)
+        trajs = []
+        for i in range(T):
+            d: Dict[str, Any] = {"Time": time.copy()} if savetime else {}
+            for o in outputs:
+                d[o.name] = _finalise(sim, o, per_out[o][i], True)
+            trajs.append(d)
+        if isinstance(reduction, SortByOutputReduction):
+            keys = list(trajs[0].keys())
+            return {k: [tr[k] for tr in trajs] for k in keys}
+        return trajs[0] if T == 1 else trajs
+    summed = {o: sum(res[o] for res in results) for o in outputs}
+    scale = 1.0 / T if isinstance(reduction, MeanReduction) else 1.0
+    d = {"Time": time * (T * scale)} if savetime else {}     # `:Time` is reduced too (test/Ensembles/ensembles.jl:21)
+    for o in outputs:
+        val = _finalise(sim, o, summed[o] * scale, False)
+        d[o.name] = val
+    return d

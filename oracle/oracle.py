@@ -43,6 +43,13 @@ def lib():
                                              C.c_double, _dp, _dp]
         L.nqco_philox_uniform.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32]
         L.nqco_philox_uniform.restype = C.c_double
+        L.nqco_select_new_state.argtypes = [C.c_int, _dp, C.c_int, C.c_double]
+        L.nqco_unit_rescale.argtypes = [C.POINTER(_abi.Config), _dp, _dp, C.c_int, C.c_int, _dp]
+        _ip = C.POINTER(C.c_int32)
+        L.nqco_unoccupied.argtypes = [C.c_int, C.c_int, _ip, _ip]
+        L.nqco_edc.argtypes = [C.c_int, _dp, _dp, C.c_int, C.c_double, _dp, C.c_double, C.c_double]
+        _up = C.POINTER(C.c_uint32)
+        L.nqco_philox_raw.argtypes = [_up, _up, _up]
         _LIB = L
     return _LIB
 
@@ -123,3 +130,39 @@ def propagate_density(E0, vd0, t0, E1, vd1, t1, t, dt, sigma):
 
 def philox_uniform(seed, gid, step, purpose=0):
     return lib().nqco_philox_uniform(seed, gid, step, purpose)
+
+
+def select_new_state(cumprob, state, xi):
+    p = np.ascontiguousarray(cumprob, dtype=np.float64)
+    return lib().nqco_select_new_state(len(p), _p(p), int(state), float(xi))
+
+
+def unit_rescale(cfg, r, v, new_state, old_state):
+    r = np.ascontiguousarray(r, dtype=np.float64).reshape(-1)
+    v = np.array(v, dtype=np.float64).reshape(-1)
+    eig = np.empty(cfg.nstates)
+    ok = lib().nqco_unit_rescale(C.byref(cfg), _p(r), _p(v), new_state, old_state, _p(eig))
+    assert ok >= 0
+    return bool(ok), v, eig
+
+
+def unoccupied(n, occ):
+    occ = np.ascontiguousarray(occ, dtype=np.int32)
+    out = np.empty(n - len(occ), dtype=np.int32)
+    ip = C.POINTER(C.c_int32)
+    lib().nqco_unoccupied(n, len(occ), occ.ctypes.data_as(ip), out.ctypes.data_as(ip))
+    return out
+
+
+def edc(psi, occupied, dt, E, Ekin, Cc=0.1):
+    re = np.ascontiguousarray(np.real(psi), dtype=np.float64).copy(); im = np.ascontiguousarray(np.imag(psi), dtype=np.float64).copy()
+    E = np.ascontiguousarray(E, dtype=np.float64)
+    lib().nqco_edc(len(re), _p(re), _p(im), occupied, dt, _p(E), Ekin, Cc)
+    return re + 1j * im
+
+
+def philox_raw(ctr, key):
+    up = C.POINTER(C.c_uint32)
+    c = np.array(ctr, dtype=np.uint32); k = np.array(key, dtype=np.uint32); o = np.empty(4, dtype=np.uint32)
+    lib().nqco_philox_raw(c.ctypes.data_as(up), k.ctypes.data_as(up), o.ctypes.data_as(up))
+    return o

@@ -97,7 +97,7 @@ static void record_save(nqco_handle* h, int64_t isave) {
     const Setup& S = h->S;
     const nqcb200_config& c = S.cfg;
     if (isave >= c.nsave) return;
-    const int n = S.n, D = S.D;
+    const int n = S.n;
     const int64_t T = (int64_t)h->traj.size();
     const bool last = (isave == c.nsave - 1);
     vec local;  // per trajectory values, then summed sequentially (deterministic)
@@ -525,6 +525,58 @@ int nqco_propagate_density(int n, const double* E0, const double* vd0, double t0
     for (int i = 0; i < n * n; ++i) s[i] = cd(sre[i], sim[i]);
     propagate_density(n, cur, nxt, t, dt, s);
     for (int i = 0; i < n * n; ++i) { sre[i] = s[i].real(); sim[i] = s[i].imag(); }
+    return 0;
+}
+// select_new_state (fssh.jl:110-121): cumulative probabilities, 1-based states
+int nqco_select_new_state(int n, const double* cumprob, int state, double xi) {
+    vec p(cumprob, cumprob + n);
+    return fssh_select(p, state - 1, xi) + 1;
+}
+// rescale_velocity! for one configuration: caches evaluated at r, velocities updated in place.
+// returns 1 (accepted) / 0 (frustrated); eig receives the hopping eigenvalues.
+int nqco_unit_rescale(const nqcb200_config* cfg, const double* r, double* v, int new_state, int old_state, double* eig) {
+    nqco_handle* h = nullptr;
+    nqcb200_config c = *cfg;
+    c.ntraj = 1;
+    if (nqco_create(&c, &h) != 0) return -1;
+    Trajectory& tr = h->traj[0];
+    const size_t N = (size_t)h->S.B * h->S.D;
+    tr.r.assign(r, r + N); tr.v.assign(v, v + N);
+    tr.sigma.assign((size_t)h->S.n * h->S.n, cd(0.0));
+    initialise(h->S, tr, nullptr);
+    bool ok = rescale_velocity(h->S, tr, new_state - 1, old_state - 1);
+    std::copy(tr.v.begin(), tr.v.end(), v);
+    if (eig) { const Cache& cc = hop_cache(h->S, tr); std::copy(cc.w.begin(), cc.w.end(), eig); }
+    nqco_destroy(h);
+    return ok ? 1 : 0;
+}
+int nqco_unoccupied(int n, int ne, const int32_t* occ, int32_t* out) {   // 1-based (DynamicsUtils.jl:162-171)
+    std::vector<int> o(ne), un;
+    for (int i = 0; i < ne; ++i) o[i] = occ[i] - 1;
+    iesh_unoccupied(n, o, un);
+    for (size_t i = 0; i < un.size(); ++i) out[i] = un[i] + 1;
+    return (int)un.size();
+}
+// apply_decoherence_correction! (decoherence_corrections.jl:21-38) on one wavefunction column
+int nqco_edc(int n, double* psi_re, double* psi_im, int occupied, double dt, const double* E, double Ekin, double C) {
+    int occ = occupied - 1;
+    double un = 0.0;
+    for (int i = 0; i < n; ++i) {
+        if (i == occ) continue;
+        double tau = (1.0 + C / Ekin) / std::fabs(E[i] - E[occ]);
+        double f = std::exp(-dt / tau);
+        psi_re[i] *= f; psi_im[i] *= f;
+        un += psi_re[i] * psi_re[i] + psi_im[i] * psi_im[i];
+    }
+    double nrm = psi_re[occ] * psi_re[occ] + psi_im[occ] * psi_im[occ];
+    double f = std::sqrt((1.0 - un) / nrm);
+    psi_re[occ] *= f; psi_im[occ] *= f;
+    return 0;
+}
+int nqco_philox_raw(const uint32_t* ctr, const uint32_t* key, uint32_t* out) {
+    uint32_t c[4] = {ctr[0], ctr[1], ctr[2], ctr[3]};
+    philox4x32_10(c, key[0], key[1]);
+    for (int i = 0; i < 4; ++i) out[i] = c[i];
     return 0;
 }
 double nqco_philox_uniform(uint64_t seed, uint64_t gid, uint64_t step, uint32_t purpose) {

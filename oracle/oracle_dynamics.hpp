@@ -225,12 +225,13 @@ inline void step_C(const Setup& S, vec& v, vec& r) {  // steps.jl:10-17
 // ---- FSSH hop ---------------------------------------------------------------------------------
 // evaluate_hopping_probability! / fewest_switches_probability! fssh.jl:86-108 (Q4),
 // select_new_state fssh.jl:110-121, rescale_velocity! surface_hopping.jl:64-99 (+ rpsh.jl:30-50)
-inline void fssh_hop(const Setup& S, Trajectory& T, double xi) {
+// fewest_switches_probability! fssh.jl:96-108: clamped, then cumulative
+inline void fssh_probabilities(const Setup& S, const Trajectory& T, vec& prob) {
     const int n = S.n, D = S.D, s = T.state;
     const Cache& c = hop_cache(S, T);
     vec vh(D);
     hop_velocity(S, T, vh.data());
-    vec prob(n, 0.0);
+    prob.assign(n, 0.0);
     for (int m = 0; m < n; ++m) {
         if (m == s) continue;
         for (int I = 0; I < D; ++I) {
@@ -240,41 +241,53 @@ inline void fssh_hop(const Setup& S, Trajectory& T, double xi) {
     }
     for (int m = 0; m < n; ++m) prob[m] = std::min(1.0, std::max(0.0, prob[m]));
     for (int m = 1; m < n; ++m) prob[m] += prob[m - 1];
-    int new_state = s;
-    for (int m = 0; m < n; ++m)
-        if (m != s && prob[m] > xi) { new_state = m; break; }
-    if (new_state == s) return;
-
-    // execute_hop! surface_hopping.jl:9-16
-    bool accept = true;
-    if (S.cfg.rescaling != NQCB200_RESCALE_OFF) {
-        vec d(D);
-        for (int I = 0; I < D; ++I) d[I] = c.nac[(size_t)I * n * n + new_state + (size_t)n * s];  // d[I][new, old]
-        double a = 0.0, b = 0.0;
-        for (int I = 0; I < D; ++I) { a += d[I] * d[I] / S.masses[I]; b += d[I] * vh[I]; }
-        a /= 2.0;
-        double cc = c.w[new_state] - c.w[s];
-        double disc = b * b - 4.0 * a * cc;
-        if (disc < 0.0) {
-            accept = false;
-            T.cnt.frustrated++;
-            if (S.cfg.rescaling == NQCB200_RESCALE_VINVERSION) {
-                double nrm = 0.0;
-                for (int I = 0; I < D; ++I) nrm += d[I] * d[I];
-                nrm = std::sqrt(nrm);
-                double gam = 0.0;
-                for (int I = 0; I < D; ++I) gam += vh[I] * d[I] / nrm;  // (RP: bead-average velocity)
-                for (int b2 = 0; b2 < S.B; ++b2)
-                    for (int I = 0; I < D; ++I) T.v[I + (size_t)D * b2] -= 2.0 * gam * d[I] / nrm;
-            }
-        } else {
-            double root = std::sqrt(disc);
-            double gam = (b < 0.0) ? (b + root) / (2.0 * a) : (b - root) / (2.0 * a);
+}
+// select_new_state fssh.jl:110-121 (prob is the cumulative vector)
+inline int fssh_select(const vec& prob, int s, double xi) {
+    for (int m = 0; m < (int)prob.size(); ++m)
+        if (m != s && prob[m] > xi) return m;
+    return s;
+}
+// rescale_velocity! surface_hopping.jl:64-99 (+ RP variants rpsh.jl:30-50); true = hop accepted
+inline bool rescale_velocity(const Setup& S, Trajectory& T, int new_state, int old_state) {
+    if (S.cfg.rescaling == NQCB200_RESCALE_OFF) return true;
+    const int n = S.n, D = S.D;
+    const Cache& c = hop_cache(S, T);
+    vec vh(D), d(D);
+    hop_velocity(S, T, vh.data());
+    for (int I = 0; I < D; ++I) d[I] = c.nac[(size_t)I * n * n + new_state + (size_t)n * old_state];  // d[I][new, old]
+    double a = 0.0, b = 0.0;
+    for (int I = 0; I < D; ++I) { a += d[I] * d[I] / S.masses[I]; b += d[I] * vh[I]; }
+    a /= 2.0;
+    double cc = c.w[new_state] - c.w[old_state];
+    double disc = b * b - 4.0 * a * cc;
+    if (disc < 0.0) {
+        if (S.cfg.rescaling == NQCB200_RESCALE_VINVERSION) {
+            double nrm = 0.0;
+            for (int I = 0; I < D; ++I) nrm += d[I] * d[I];
+            nrm = std::sqrt(nrm);
+            double gam = 0.0;
+            for (int I = 0; I < D; ++I) gam += vh[I] * d[I] / nrm;  // (RP: bead-average velocity)
             for (int b2 = 0; b2 < S.B; ++b2)
-                for (int I = 0; I < D; ++I) T.v[I + (size_t)D * b2] -= gam * d[I] / S.masses[I];
+                for (int I = 0; I < D; ++I) T.v[I + (size_t)D * b2] -= 2.0 * gam * d[I] / nrm;
         }
+        return false;
     }
-    if (accept) { T.state = new_state; T.cnt.hops++; }
+    double root = std::sqrt(disc);
+    double gam = (b < 0.0) ? (b + root) / (2.0 * a) : (b - root) / (2.0 * a);
+    for (int b2 = 0; b2 < S.B; ++b2)
+        for (int I = 0; I < D; ++I) T.v[I + (size_t)D * b2] -= gam * d[I] / S.masses[I];
+    return true;
+}
+inline void fssh_hop(const Setup& S, Trajectory& T, double xi) {
+    vec prob;
+    fssh_probabilities(S, T, prob);
+    const int s = T.state;
+    const int new_state = fssh_select(prob, s, xi);
+    if (new_state == s) return;
+    // execute_hop! surface_hopping.jl:9-16
+    if (rescale_velocity(S, T, new_state, s)) { T.state = new_state; T.cnt.hops++; }
+    else T.cnt.frustrated++;
     // Q2: T.k (acceleration) is NOT refreshed; Q3: T.nxt.vd keeps the pre-rescale velocity.
 }
 

@@ -1,0 +1,141 @@
+"""CPU-only checks of the boundary: the C-ABI library loads and exports every symbol the header declares, refuses
+to compute without a GPU, and the host mirror reproduces the reference's layouts / argument handling."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import nqcdynamics_jl_b200 as nq
+from helpers import A, model_config
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    text = open(os.path.join(ROOT, "include", "nqcb200.h")).read()
+    return sorted(set(re.findall(r"\b(nqcb200_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = ctypes.CDLL(A.engine_library_path())
+    names = _header_symbols()
+    assert len(names) >= 20
+    for name in names:
+        assert hasattr(lib, name), f"{name} declared in include/nqcb200.h but not exported"
+    assert sorted("nqcb200_" + s for s in A.HEADER_SYMBOLS) == names, "python binding list out of sync with the header"
+    assert lib.nqcb200_version() == A.ABI_VERSION
+
+
+def test_config_struct_matches_header_layout():
+    """Field order / sizes of the ctypes mirror against the C compiler's view of the header."""
+    import subprocess, tempfile, textwrap
+    fields = [f[0] for f in A.Config._fields_]
+    src = textwrap.dedent("""
+        #include <stdio.h>
+        #include <stddef.h>
+        #include "nqcb200.h"
+        int main(void) {
+        %s
+            printf("sizeof %%zu\\n", sizeof(nqcb200_config));
+            return 0;
+        }""") % "\n".join(f'    printf("{f} %zu\\n", offsetof(nqcb200_config, {f}));' for f in fields)
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "t.c"), "w").write(src)
+        subprocess.check_call(["/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc", "-I", os.path.join(ROOT, "include"),
+                               os.path.join(d, "t.c"), "-o", os.path.join(d, "t")])
+        out = dict(line.split() for line in subprocess.check_output([os.path.join(d, "t")], text=True).splitlines())
+    for f in fields:
+        assert int(out[f]) == getattr(A.Config, f).offset, f
+    assert int(out["sizeof"]) == ctypes.sizeof(A.Config)
+
+
+def test_no_gpu_means_error_not_fallback():
+    lib = A.load_engine_library()
+    if lib.nqcb200_device_count() > 0:
+        pytest.skip("a GPU is visible")
+    cfg, keep = A.make_config(**model_config(nq.TullyModelOne(), method=A.METHOD_FSSH, masses=[2000.0], ntraj=4, dt=1.0))
+    from nqcdynamics_jl_b200.engine import Engine
+    with pytest.raises(nq.EngineError) as ei:
+        Engine(cfg, keep)
+    assert ei.value.code == -3
+    sim = nq.Simulation[nq.FSSH](nq.Atoms(2000), nq.TullyModelOne())
+    dist = nq.DynamicalDistribution(0.005, -5.0, sim.size) * nq.PureState(1)
+    with pytest.raises(RuntimeError):
+        nq.run_dynamics(sim, (0.0, 10.0), dist, output=nq.OutputDiabaticPopulation, trajectories=2)
+
+
+def test_unsupported_and_invalid_configs_are_rejected_before_touching_a_device():
+    from nqcdynamics_jl_b200.engine import Engine
+    cfg, keep = A.make_config(**model_config(nq.TullyModelOne(), method=A.METHOD_FSSH, masses=[2000.0], ntraj=4, dt=1.0))
+    cfg.abi_version = 99
+    with pytest.raises(nq.EngineError) as ei:
+        Engine(cfg, keep)
+    assert ei.value.code == -1
+    cfg, keep = A.make_config(**model_config(nq.Harmonic(), method=A.METHOD_FSSH, masses=[1.0], ntraj=4, dt=1.0))
+    with pytest.raises(nq.EngineError) as ei:
+        Engine(cfg, keep)
+    assert ei.value.code == -2        # no kernel for that combination -> unsupported, never a CPU path
+
+
+def test_model_table_matches_reference_docs():
+    """Bath discretisations: docs/src/NQCModels/systembathmodels.md:47-59 (Ohmic), :82-94 (Debye), :210-215."""
+    N = 10
+    w, c = nq.OhmicSpectralDensity(2.5, 0.1).discretize(N)
+    j = np.arange(1, N + 1)
+    assert np.allclose(w, -2.5 * np.log(1 - j / (N + 1)))
+    assert np.allclose(c, np.sqrt(0.1 * 2.5 / (N + 1)) * w)
+    w, c = nq.DebyeSpectralDensity(0.25, 0.5).discretize(N)
+    assert np.allclose(w, 0.25 * np.tan(np.pi / 2 * (1 - j / (N + 1))))
+    assert np.allclose(c, np.sqrt(2 * 0.5 / (N + 1)) * w)
+    m = nq.AndersonHolstein(nq.MiaoSubotnik(Γ=6.4e-3), nq.TrapezoidalRule(30, -0.0192, 0.0192))
+    assert m.nstates == 31 and m.nelectrons == 15          # test/Dynamics/iesh.jl:19,30,78-79
+    sb = nq.SpinBoson(nq.DebyeSpectralDensity(0.25, 0.5), 100, 0.0, 1.0)
+    sim = nq.Simulation[nq.FSSH](nq.Atoms(np.ones(100)), sb)
+    assert sim.size == (1, 100) and sim.ndofs_total == 100
+
+
+def test_distribution_layouts():
+    """Julia (ndofs, natoms, nbeads) column-major -> engine [traj][bead][dof + ndofs*atom]."""
+    sim = nq.RingPolymerSimulation[nq.FSSH](nq.Atoms([1.0, 2.0]), nq.TullyModelOne(), 3, temperature=1e-3)
+    assert sim.size == (1, 2, 3)
+    x = np.arange(6.0).reshape(1, 2, 3)            # x[dof, atom, bead]
+    d = nq.DynamicalDistribution(x, x * 10, sim.size)
+    r, v = d.sample(np.random.default_rng(0), 4)
+    assert r.shape == (4, 3, 2)
+    for b in range(3):
+        for a in range(2):
+            assert r[1, b, a] == 10 * x[0, a, b] and v[1, b, a] == x[0, a, b]
+    sims = nq.Simulation[nq.FSSH](nq.Atoms(2000), nq.TullyModelOne())
+    d2 = nq.DynamicalDistribution(nq.VelocityBoltzmann(1e-3, [2000.0], (1, 1)), nq.Normal(-8, 1), sims.size)
+    r, v = d2.sample(np.random.default_rng(1), 20000)
+    assert abs(r.mean() + 8) < 0.05 and abs(v.std() - np.sqrt(1e-3 / 2000)) < 2e-5
+    # OrderedSelection: 1-based indices into a vector of configurations (selections.jl:38-42)
+    d3 = nq.DynamicalDistribution([np.array([[0.1]]), np.array([[0.2]]), np.array([[0.3]])],
+                                  [np.array([[1.0]]), np.array([[2.0]]), np.array([[3.0]])], sims.size)
+    r, v = d3.sample(np.random.default_rng(2), 2, selection=[3, 1])
+    assert list(r.ravel()) == [3.0, 1.0] and list(v.ravel()) == [0.3, 0.1]
+
+
+def test_run_dynamics_argument_checks():
+    sim = nq.Simulation[nq.FSSH](nq.Atoms(2000), nq.TullyModelOne(), rescaling="vinversion")
+    assert sim.method.rescaling == "vinversion"
+    dist = nq.DynamicalDistribution(0.005, -5.0, sim.size) * nq.PureState(1)
+    with pytest.raises(TypeError):
+        nq.run_dynamics(sim, (0.0, 10.0), dist, output=lambda sol, i: 0, trajectories=2)
+    with pytest.raises(ValueError):
+        nq.run_dynamics(sim, (0.0, 10.0), dist, output=nq.OutputDiabaticPopulation, trajectories=2, dt=1.0, saveat=2.5)
+    with pytest.raises(ValueError):
+        nq.OutputStateResolvedScattering1D(sim, "blah")
+
+
+def test_shard_bounds_cover_range():
+    from nqcdynamics_jl_b200.distributed import shard_bounds
+    for T in (0, 1, 7, 1000, 1001):
+        for W in (1, 2, 3, 8):
+            blocks = [shard_bounds(T, W, r) for r in range(W)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == T
+            assert all(blocks[i][1] == blocks[i + 1][0] for i in range(W - 1))
+            sizes = [b - a for a, b in blocks]
+            assert max(sizes) - min(sizes) <= 1
