@@ -15,8 +15,7 @@
 #include <vector>
 
 #include "common.cuh"
-#include "kernel_density.cuh"
-#include "kernel_ring.cuh"
+#include "kernels.h"
 
 using namespace nq;
 
@@ -24,142 +23,23 @@ namespace {
 
 std::string g_create_error;
 
-// ---- kernel table ------------------------------------------------------------------------------
-using StepFn = void (*)(const KParams);
-using InitFn = void (*)(const KParams, int, int, const double*);
-
-struct KernelSet {
-    StepFn step = nullptr;
-    InitFn init = nullptr;
-    int L = 1, DPL = 1;
-    const char* name = "";
-};
-
-template <class M, int DPL, int L, int METHOD>
-KernelSet density_set(const char* name) {
-    KernelSet k;
-    k.step = density_step_kernel<M, DPL, L, METHOD>;
-    k.init = density_init_kernel<M, DPL, L, METHOD>;
-    k.L = L; k.DPL = DPL; k.name = name;
-    return k;
-}
-template <class M, int NB, int METHOD>
-KernelSet ring_set(const char* name) {
-    KernelSet k;
-    k.step = ring_step_kernel<M, NB, METHOD>;
-    k.init = ring_init_kernel<M, NB, METHOD>;
-    k.L = NB; k.DPL = 1; k.name = name;
-    return k;
-}
-
-template <class M>
-bool pick_density_1d(int method, KernelSet& out, const char* name) {
-    if (method == NQCB200_METHOD_FSSH) out = density_set<M, 1, 1, NQCB200_METHOD_FSSH>(name);
-    else if (method == NQCB200_METHOD_EHRENFEST) out = density_set<M, 1, 1, NQCB200_METHOD_EHRENFEST>(name);
-    else return false;
-    return true;
-}
-
-template <int DPL, int L>
-bool pick_spin_boson(int method, KernelSet& out) {
-    using M = ModelT<NQCB200_MODEL_SPIN_BOSON>;
-    if (method == NQCB200_METHOD_FSSH) out = density_set<M, DPL, L, NQCB200_METHOD_FSSH>("spinboson_fssh");
-    else if (method == NQCB200_METHOD_EHRENFEST) out = density_set<M, DPL, L, NQCB200_METHOD_EHRENFEST>("spinboson_ehrenfest");
-    else return false;
-    return true;
-}
-
-template <class M, int NB>
-bool pick_ring(int method, KernelSet& out, const char* name) {
-    if (method == NQCB200_METHOD_FSSH) out = ring_set<M, NB, NQCB200_METHOD_FSSH>(name);
-    else if (method == NQCB200_METHOD_EHRENFEST) out = ring_set<M, NB, NQCB200_METHOD_EHRENFEST>(name);
-    else return false;
-    return true;
-}
-template <class M>
-bool pick_ring_beads(int method, int B, KernelSet& out, const char* name) {
-    switch (B) {
-        case 2: return pick_ring<M, 2>(method, out, name);
-        case 4: return pick_ring<M, 4>(method, out, name);
-        case 8: return pick_ring<M, 8>(method, out, name);
-        case 16: return pick_ring<M, 16>(method, out, name);
-        case 32: return pick_ring<M, 32>(method, out, name);
-    }
-    return false;
-}
-template <class M, int NB>
-KernelSet classical_ring_set(const char* name) {
-    KernelSet k;
-    k.step = classical_ring_step_kernel<M, NB>;
-    k.init = classical_ring_init_kernel<M, NB>;
-    k.L = NB; k.DPL = 1; k.name = name;
-    return k;
-}
-template <class M>
-bool pick_classical(int B, KernelSet& out, const char* name) {
-    switch (B) {
-        case 1: out = classical_ring_set<M, 1>(name); return true;
-        case 2: out = classical_ring_set<M, 2>(name); return true;
-        case 4: out = classical_ring_set<M, 4>(name); return true;
-        case 8: out = classical_ring_set<M, 8>(name); return true;
-        case 16: out = classical_ring_set<M, 16>(name); return true;
-        case 32: out = classical_ring_set<M, 32>(name); return true;
-    }
-    return false;
-}
-
 // Choose a kernel for (method, model, n, D, B); false => NQCB200_ERR_UNSUPPORTED (no fallback).
 bool select_kernels(const nqcb200_config& c, KernelSet& out, std::string& why) {
-    const int m = c.method, D = c.ndofs, B = c.nbeads;
-    const bool density = (m == NQCB200_METHOD_FSSH || m == NQCB200_METHOD_EHRENFEST);
-    if (m == NQCB200_METHOD_CLASSICAL) {
-        if (D != 1) { why = "classical/RPMD kernels are instantiated for ndofs == 1"; return false; }
-        bool ok = false;
-        if (c.model == NQCB200_MODEL_HARMONIC) ok = pick_classical<ModelT<NQCB200_MODEL_HARMONIC>>(B, out, "rpmd_harmonic");
-        else if (c.model == NQCB200_MODEL_FREE) ok = pick_classical<ModelT<NQCB200_MODEL_FREE>>(B, out, "rpmd_free");
-        if (!ok) why = "classical method needs a classical model and nbeads in {1,2,4,8,16,32}";
-        return ok;
-    }
-    if (!density) { why = "method has no kernel yet (IESH / NRPMD are not built in this round)"; return false; }
-    if (B > 1) {
-        if (D != 1) { why = "ring-polymer FSSH/Ehrenfest kernels are instantiated for ndofs == 1"; return false; }
-        bool ok = false;
-        switch (c.model) {
-            case NQCB200_MODEL_TULLY_ONE: ok = pick_ring_beads<ModelT<NQCB200_MODEL_TULLY_ONE>>(m, B, out, "rp_tully1"); break;
-            case NQCB200_MODEL_TULLY_TWO: ok = pick_ring_beads<ModelT<NQCB200_MODEL_TULLY_TWO>>(m, B, out, "rp_tully2"); break;
-            case NQCB200_MODEL_DOUBLE_WELL: ok = pick_ring_beads<ModelT<NQCB200_MODEL_DOUBLE_WELL>>(m, B, out, "rp_doublewell"); break;
-            case NQCB200_MODEL_THREE_STATE_MORSE: ok = pick_ring_beads<ModelT<NQCB200_MODEL_THREE_STATE_MORSE>>(m, B, out, "rp_morse3"); break;
-            default: break;
-        }
-        if (!ok) why = "ring-polymer kernel: unsupported model or nbeads not in {2,4,8,16,32}";
-        return ok;
-    }
-    switch (c.model) {
-        case NQCB200_MODEL_TULLY_ONE: if (D == 1) return pick_density_1d<ModelT<NQCB200_MODEL_TULLY_ONE>>(m, out, "tully1"); break;
-        case NQCB200_MODEL_TULLY_TWO: if (D == 1) return pick_density_1d<ModelT<NQCB200_MODEL_TULLY_TWO>>(m, out, "tully2"); break;
-        case NQCB200_MODEL_TULLY_THREE: if (D == 1) return pick_density_1d<ModelT<NQCB200_MODEL_TULLY_THREE>>(m, out, "tully3"); break;
-        case NQCB200_MODEL_DOUBLE_WELL: if (D == 1) return pick_density_1d<ModelT<NQCB200_MODEL_DOUBLE_WELL>>(m, out, "doublewell"); break;
-        case NQCB200_MODEL_THREE_STATE_MORSE: if (D == 1) return pick_density_1d<ModelT<NQCB200_MODEL_THREE_STATE_MORSE>>(m, out, "morse3"); break;
-        case NQCB200_MODEL_SPIN_BOSON: {
-            if (c.nbath != D) { why = "SpinBoson needs nbath == ndofs"; return false; }
-            int lanes = 0;
-            if (const char* env = getenv("NQCB200_SPINBOSON_LANES")) lanes = atoi(env);
-            if (D <= 4 && (lanes == 0 || lanes == 1)) return pick_spin_boson<4, 1>(m, out);
-            if (D <= 8 && (lanes == 0 || lanes == 1)) return pick_spin_boson<8, 1>(m, out);
-            if (D <= 100 && lanes == 4) return pick_spin_boson<25, 4>(m, out);
-            if (D <= 104 && (lanes == 0 || lanes == 8)) return pick_spin_boson<13, 8>(m, out);
-            if (D <= 112 && lanes == 16) return pick_spin_boson<7, 16>(m, out);
-            if (D <= 128) return pick_spin_boson<4, 32>(m, out);
-            if (D <= 512) return pick_spin_boson<16, 32>(m, out);
-            why = "SpinBoson kernels cover ndofs <= 512";
-            return false;
-        }
+    switch (c.method) {
+        case NQCB200_METHOD_CLASSICAL: return select_classical(c, out, why);
+        case NQCB200_METHOD_NRPMD: return select_nrpmd(c, out, why);
+        case NQCB200_METHOD_FSSH:
+        case NQCB200_METHOD_EHRENFEST:
+            if (c.nbeads > 1) return select_ring_density(c, out, why);
+            if (c.model == NQCB200_MODEL_SPIN_BOSON) return select_density_spinboson(c, out, why);
+            return select_density_1d(c, out, why);
         default: break;
     }
-    why = "no kernel for this model / ndofs combination";
+    why = "method has no kernel yet (AdiabaticIESH is not built in this round)";
     return false;
 }
 
+// kernel selection lives in the tu_*.cu translation units (compiled in parallel), see kernels.h
 // ---- small device utilities --------------------------------------------------------------------
 // in: [T][C] (trajectory-major, host layout)  ->  out: [C][T] (SoA)
 template <typename Tin, typename Tout>
@@ -264,7 +144,7 @@ struct nqcb200_handle {
     bool user_gauge = false;
     int zcopies = 1;
     int64_t step_count = 0, nsave_done = 0;
-    bool has_state = false;
+    bool has_state = false, has_nuclei = false;
     int nsig = 0, nstate = 0;
     double last_ms = 0.0;
     int64_t last_launches = 0;
@@ -367,14 +247,15 @@ int set_state_impl(nqcb200_handle* h, const double* r, const double* v, const do
     h->step_count = 0;
     h->kp.step0 = 0;
     h->kp.nsteps = 0;
-    if (T > 0) {
+    if (T > 0 && c.method != NQCB200_METHOD_NRPMD) {   // NRPMD: save point 0 is recorded by set_mapping
         h->ks.init<<<grid_for(h), kBlockThreads, 0, h->stream>>>(h->kp, basis, sample_state,
                                                                 (sample_state && state_draw) ? h->d_state_draw : nullptr);
         NQ_CUDA(h, cudaGetLastError());
     }
     NQ_CUDA(h, cudaStreamSynchronize(h->stream));
-    h->nsave_done = 1;
-    h->has_state = true;
+    h->nsave_done = (c.method == NQCB200_METHOD_NRPMD) ? 0 : 1;
+    h->has_state = (c.method != NQCB200_METHOD_NRPMD);
+    h->has_nuclei = true;
     h->user_gauge = false;   // a gauge reference applies to the next set_state only
     return NQCB200_OK;
 }
@@ -485,6 +366,13 @@ int nqcb200_create(const nqcb200_config* cfg, nqcb200_handle** out) {
             const double a = 0.5 * wk * c.dt, den = 1.0 + a * a;
             cay[4 * k + 0] = (1.0 - a * a) / den; cay[4 * k + 1] = c.dt / den;
             cay[4 * k + 2] = -wk * wk * c.dt / den; cay[4 * k + 3] = (1.0 - a * a) / den;
+            if (c.method == NQCB200_METHOD_NRPMD) {
+                // RingPolymerMInt uses half = true (ringpolymer_mint.jl:22): principal square root of the
+                // unimodular 2x2, sqrt(M) = (M + I) / sqrt(tr M + 2)
+                const double sq = std::sqrt(cay[4 * k + 0] + cay[4 * k + 3] + 2.0);
+                cay[4 * k + 0] = (cay[4 * k + 0] + 1.0) / sq; cay[4 * k + 3] = (cay[4 * k + 3] + 1.0) / sq;
+                cay[4 * k + 1] /= sq; cay[4 * k + 2] /= sq;
+            }
         }
         double *dto = nullptr, *dfrom = nullptr, *dcay = nullptr;
         if ((rc = dev_alloc(h, &dto, to.size())) != 0) return fail(rc);
@@ -508,6 +396,11 @@ int nqcb200_create(const nqcb200_config* cfg, nqcb200_handle** out) {
         if ((rc = dev_alloc(h, &kp.pop0, (size_t)2 * n * T)) != 0) return fail(rc);
     }
     if (h->nstate) { if ((rc = dev_alloc(h, &kp.state, (size_t)h->nstate * T)) != 0) return fail(rc); }
+    if (c.method == NQCB200_METHOD_NRPMD) {
+        if ((rc = dev_alloc(h, &kp.qmap, (size_t)B * n * T)) != 0) return fail(rc);
+        if ((rc = dev_alloc(h, &kp.pmap, (size_t)B * n * T)) != 0) return fail(rc);
+        if ((rc = dev_alloc(h, &kp.pop0, (size_t)2 * n * T)) != 0) return fail(rc);
+    }
     if ((rc = dev_alloc(h, &kp.obs_sum, (size_t)std::max<int64_t>(1, kp.layout.total) * kObsReplicas)) != 0) return fail(rc);
     if ((rc = dev_alloc(h, &h->obs_folded, (size_t)std::max<int64_t>(1, kp.layout.total))) != 0) return fail(rc);
     if (c.per_trajectory && kp.layout.total > 0) { if ((rc = dev_alloc(h, &kp.obs_traj, (size_t)kp.layout.total * T)) != 0) return fail(rc); }
@@ -519,7 +412,7 @@ int nqcb200_create(const nqcb200_config* cfg, nqcb200_handle** out) {
     if ((rc = dev_alloc(h, &kp.counters, 4)) != 0) return fail(rc);
     if ((rc = dev_alloc(h, &h->d_state_draw, (size_t)T)) != 0) return fail(rc);
     // staging: large enough for any single field (and the per-trajectory outputs of one observable)
-    size_t stage = std::max<size_t>({BD, (size_t)h->nsig, (size_t)D * n * n, (size_t)h->zcopies * n * n, (size_t)1});
+    size_t stage = std::max<size_t>({BD, (size_t)h->nsig, (size_t)D * n * n, (size_t)h->zcopies * n * n, (size_t)B * n, (size_t)1});
     if (c.per_trajectory) {
         for (int id = 0; id < NQCB200_OBS_COUNT; ++id)
             if (c.observables & (1u << id)) stage = std::max(stage, (size_t)c.nsave * kp.layout.width[id]);
@@ -557,15 +450,34 @@ int nqcb200_set_state_diabatic(nqcb200_handle* h, const double* r, const double*
     return set_state_impl(h, r, v, rho_re, rho_im, state, 1, state_draw);
 }
 
-int nqcb200_set_mapping(nqcb200_handle* h, const double*, const double*) {
-    if (!h) return NQCB200_ERR_INVALID;
-    h->err = "NRPMD is not built in this round";
-    return NQCB200_ERR_UNSUPPORTED;
+int nqcb200_set_mapping(nqcb200_handle* h, const double* qmap, const double* pmap) {
+    if (!h || !qmap || !pmap) return NQCB200_ERR_INVALID;
+    if (h->cfg.method != NQCB200_METHOD_NRPMD) { h->err = "mapping variables exist only for NRPMD"; return NQCB200_ERR_INVALID; }
+    if (!h->has_nuclei) { h->err = "set_mapping before set_state"; return NQCB200_ERR_STATE; }
+    NQ_CUDA(h, cudaSetDevice(h->cfg.device));
+    const int C = h->cfg.nbeads * h->cfg.nstates;
+    int rc;
+    if ((rc = upload_field(h, qmap, h->kp.qmap, C)) != 0) return rc;
+    if ((rc = upload_field(h, pmap, h->kp.pmap, C)) != 0) return rc;
+    NQ_CUDA(h, cudaMemsetAsync(h->kp.obs_sum, 0, sizeof(double) * std::max<int64_t>(1, h->kp.layout.total) * kObsReplicas, h->stream));
+    if (h->cfg.ntraj > 0) {
+        h->ks.init<<<grid_for(h), kBlockThreads, 0, h->stream>>>(h->kp, 0, 0, nullptr);
+        NQ_CUDA(h, cudaGetLastError());
+    }
+    NQ_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->nsave_done = 1;
+    h->has_state = true;
+    return NQCB200_OK;
 }
-int nqcb200_get_mapping(nqcb200_handle* h, double*, double*) {
+int nqcb200_get_mapping(nqcb200_handle* h, double* qmap, double* pmap) {
     if (!h) return NQCB200_ERR_INVALID;
-    h->err = "NRPMD is not built in this round";
-    return NQCB200_ERR_UNSUPPORTED;
+    if (h->cfg.method != NQCB200_METHOD_NRPMD || !h->has_state) { h->err = "no mapping variables"; return NQCB200_ERR_STATE; }
+    NQ_CUDA(h, cudaSetDevice(h->cfg.device));
+    const int C = h->cfg.nbeads * h->cfg.nstates;
+    int rc;
+    if (qmap && (rc = download_field(h, h->kp.qmap, qmap, C)) != 0) return rc;
+    if (pmap && (rc = download_field(h, h->kp.pmap, pmap, C)) != 0) return rc;
+    return NQCB200_OK;
 }
 
 int nqcb200_set_draws(nqcb200_handle* h, const double* xi, int64_t nsteps) {

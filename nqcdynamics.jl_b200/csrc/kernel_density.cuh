@@ -23,6 +23,7 @@
 #include "linalg.cuh"
 #include "models.cuh"
 #include "philox.cuh"
+#include "kernels.h"
 
 namespace nq {
 
@@ -46,7 +47,7 @@ NQ_D double lane_sum(double x) {
 }
 NQ_D double warp_sum(double x) { return lane_sum<32>(x); }
 
-constexpr int kObsReplicas = 16;  // accumulator copies, folded after the launch (atomic contention)
+// kObsReplicas: see kernels.h
 
 // Block-wide sum of one observable value into the shard accumulator.  Warp-collective and
 // block-collective: every thread of the block must call it the same number of times.

@@ -1,0 +1,32 @@
+// kernels.h -- host-visible kernel table.  Each tu_*.cu instantiates one kernel family and exports a
+// selector; engine.cu only sees function pointers, so the families compile in parallel.
+#pragma once
+#include <string>
+
+#include "common.cuh"
+
+namespace nq {
+
+using StepFn = void (*)(const KParams);
+using InitFn = void (*)(const KParams, int, int, const double*);
+
+struct KernelSet {
+    StepFn step = nullptr;
+    InitFn init = nullptr;
+    int L = 1;              // lanes (threads) per trajectory
+    int DPL = 1;            // nuclear dofs per lane
+    int block = kBlockThreads;
+    size_t dyn_smem = 0;
+    bool cta_per_trajectory = false;
+    const char* name = "";
+};
+
+constexpr int kObsReplicas = 16;  // accumulator copies, folded after each launch (atomic contention)
+
+bool select_density_1d(const nqcb200_config& c, KernelSet& out, std::string& why);
+bool select_density_spinboson(const nqcb200_config& c, KernelSet& out, std::string& why);
+bool select_ring_density(const nqcb200_config& c, KernelSet& out, std::string& why);
+bool select_classical(const nqcb200_config& c, KernelSet& out, std::string& why);
+bool select_nrpmd(const nqcb200_config& c, KernelSet& out, std::string& why);
+
+}  // namespace nq

@@ -1,0 +1,39 @@
+// tu_density_spinboson.cu -- FSSH / Ehrenfest kernels for SpinBoson: L lanes per trajectory, modes over lanes.
+#include <cstdlib>
+
+#include "kernel_density.cuh"
+
+namespace nq {
+namespace {
+template <int DPL, int L>
+bool pick(int method, KernelSet& out) {
+    using M = ModelT<NQCB200_MODEL_SPIN_BOSON>;
+    if (method == NQCB200_METHOD_FSSH) {
+        out.step = density_step_kernel<M, DPL, L, NQCB200_METHOD_FSSH>;
+        out.init = density_init_kernel<M, DPL, L, NQCB200_METHOD_FSSH>;
+        out.name = "spinboson_fssh";
+    } else if (method == NQCB200_METHOD_EHRENFEST) {
+        out.step = density_step_kernel<M, DPL, L, NQCB200_METHOD_EHRENFEST>;
+        out.init = density_init_kernel<M, DPL, L, NQCB200_METHOD_EHRENFEST>;
+        out.name = "spinboson_ehrenfest";
+    } else return false;
+    out.L = L; out.DPL = DPL;
+    return true;
+}
+}  // namespace
+
+bool select_density_spinboson(const nqcb200_config& c, KernelSet& out, std::string& why) {
+    const int D = c.ndofs, m = c.method;
+    if (c.nbath != D) { why = "SpinBoson needs nbath == ndofs"; return false; }
+    int lanes = 0;
+    if (const char* env = getenv("NQCB200_SPINBOSON_LANES")) lanes = atoi(env);
+    if (D <= 4 && (lanes == 0 || lanes == 1)) return pick<4, 1>(m, out);
+    if (D <= 8 && (lanes == 0 || lanes == 1)) return pick<8, 1>(m, out);
+    if (D <= 104 && (lanes == 0 || lanes == 8)) return pick<13, 8>(m, out);
+    if (D <= 112 && lanes == 16) return pick<7, 16>(m, out);
+    if (D <= 128) return pick<4, 32>(m, out);
+    if (D <= 512) return pick<16, 32>(m, out);
+    why = "SpinBoson kernels cover ndofs <= 512";
+    return false;
+}
+}  // namespace nq

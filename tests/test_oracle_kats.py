@@ -323,6 +323,34 @@ def test_spin_boson_ehrenfest_vs_gao_saller_curve():
     assert np.max(np.abs(result - ref)) < 0.2
 
 
+def test_nrpmd_energy_conservation_second_order():
+    """test/Dynamics/nrpmd.jl:40-83: RingPolymerMInt is symplectic and of order 2 -- the error of the NRPMD
+    Hamiltonian (spring + kinetic + mapping potential, nrpmd.jl:124-139) quarters when dt halves; the total
+    mapping population sum_j [(q_j^2 + p_j^2)/2 - gamma] stays 1."""
+    B, T, g = 4, 3, 0.5
+    rng = np.random.default_rng(0)
+    r0 = 0.3 * rng.standard_normal((T, B, 1)); v0 = 0.5 * rng.standard_normal((T, B, 1))
+    th = rng.random((T, B, 2)) * 2 * np.pi
+    R = np.array([np.sqrt(2 + 2 * g), np.sqrt(2 * g)])          # nrpmd.jl:47-65, PureState(1)
+    q0, p0 = np.cos(th) * R, np.sin(th) * R
+    errs = []
+    for dt in (0.02, 0.01, 0.005):
+        n = int(round(2.0 / dt))
+        kw = model_config(nq.DoubleWell(), method=A.METHOD_NRPMD, masses=[1.0], ntraj=T, dt=dt, nbeads=B, temperature=0.7,
+                          save_every=n, nsave=2, observables=(1 << A.OBS_TOTAL_ENERGY) | (1 << A.OBS_DIABATIC_POP),
+                          per_trajectory=1, nrpmd_gamma=g)
+        cfg, keep = A.make_config(**kw)
+        h = oracle.OracleEngine(cfg, keep)
+        h.set_state(r0, v0); h.set_mapping(q0, p0)
+        h.run(n)
+        E = h.observable_per_trajectory(A.OBS_TOTAL_ENERGY)[:, :, 0]
+        errs.append(np.max(np.abs(E[:, 1] - E[:, 0])))
+        pop = h.observable_per_trajectory(A.OBS_DIABATIC_POP)
+        assert np.allclose(pop[:, 0], [1.0, 0.0], atol=1e-12) and np.allclose(pop.sum(axis=2), 1.0, atol=1e-10)
+    orders = np.log2(np.array(errs[:-1]) / np.array(errs[1:]))
+    assert np.all(np.abs(orders - 2.0) < 0.1), orders
+
+
 # ---- IESH pieces -----------------------------------------------------------------------------------
 def test_set_unoccupied_states():
     """test/Dynamics/iesh.jl:66-73."""

@@ -233,9 +233,43 @@ def test_rpmd_parity(nbeads):
     assert np.max(np.abs(E - E[:, :1])) < 1e-3 * np.max(np.abs(E))   # symplectic: bounded energy error
 
 
+@pytest.mark.parametrize("nbeads", [1, 4, 16])
+@pytest.mark.parametrize("name,model,mass,r0,temp", [
+    ("doublewell", nq.DoubleWell(), 1.0, 0.2, 0.7),
+    ("morse3", nq.ThreeStateMorse(), 20000.0, 2.6, 9.5e-4),
+])
+def test_nrpmd_parity(nbeads, name, model, mass, r0, temp):
+    """BASELINE config 5 (NRPMD): RingPolymerMInt with mapping variables in the adiabatic basis vs the oracle's
+    dense C/D/E/F matrices (ringpolymer_mint.jl:28-130)."""
+    T, nsteps = 48, 120
+    n = model.nstates
+    rng = np.random.default_rng(23)
+    obs = ((1 << A.OBS_DIABATIC_POP) | (1 << A.OBS_POPCORR_DIABATIC) | (1 << A.OBS_KINETIC) | (1 << A.OBS_POTENTIAL) |
+           (1 << A.OBS_TOTAL_ENERGY) | (1 << A.OBS_POSITION) | (1 << A.OBS_VELOCITY))
+    dt = 0.01 if mass < 100 else 1.0
+    kw = model_config(model, method=A.METHOD_NRPMD, masses=[mass], ntraj=T, dt=dt, nbeads=nbeads, temperature=temp,
+                      save_every=10, nsave=nsteps // 10 + 1, observables=obs, per_trajectory=1, nrpmd_gamma=0.5)
+    e, o = make_pair(engine_factory(), oracle_factory(), **kw)
+    r = r0 + 0.1 * rng.standard_normal((T, nbeads, 1))
+    v = np.sqrt(temp * nbeads / mass) * rng.standard_normal((T, nbeads, 1))
+    th = rng.random((T, nbeads, n)) * 2 * np.pi
+    R = np.full(n, np.sqrt(2 * 0.5)); R[0] = np.sqrt(2 + 2 * 0.5)
+    q, p = np.cos(th) * R, np.sin(th) * R
+    for h in (e, o):
+        h.set_state(r, v)
+        h.set_mapping(q, p)
+    for chunk in range(nsteps // 10):
+        e.run(10); o.run(10)
+        _compare_state(e, o, 1e-10, f"chunk {chunk}")
+        qe, pe = e.get_mapping(); qo, po = o.get_mapping()
+        assert np.max(np.abs(qe - qo)) < 1e-10 and np.max(np.abs(pe - po)) < 1e-10
+    _compare_observables(e, o, obs, 1e-9, T)
+    assert np.max(np.abs(e.observable_per_trajectory(A.OBS_TOTAL_ENERGY) - o.observable_per_trajectory(A.OBS_TOTAL_ENERGY))) < 1e-9
+
+
 def test_unsupported_configuration_fails_loudly():
     """No CPU fallback: a configuration without a kernel is an error, not a silent slow path."""
-    kw = model_config(nq.TullyModelOne(), method=A.METHOD_NRPMD, masses=[2000.0], ntraj=4, dt=1.0)
+    kw = model_config(nq.TullyModelOne(), method=A.METHOD_IESH, masses=[2000.0], ntraj=4, dt=1.0, nelectrons=1)
     cfg, keep = A.make_config(**kw)
     with pytest.raises(nq.EngineError) as ei:
         engine_factory()(cfg, keep)
