@@ -237,7 +237,7 @@ int set_state_impl(nqcb200_handle* h, const double* r, const double* v, const do
             if (state_draw) NQ_CUDA(h, cudaMemcpyAsync(h->d_state_draw, state_draw, sizeof(double) * T, cudaMemcpyHostToDevice, h->stream));
         }
     }
-    if (!h->user_gauge && c.nstates > 1) {
+    if (!h->user_gauge && c.nstates > 1 && h->kp.Zprev) {
         fill_identity<<<(unsigned)((T + 255) / 256), 256, 0, h->stream>>>(h->kp.Zprev, T, c.nstates, h->zcopies);
         NQ_CUDA(h, cudaGetLastError());
     }

@@ -129,7 +129,7 @@ def _rpmd_harmonic() -> Workload:
         return {"r": (rn @ U.T).reshape(T, B, 1), "v": (vn @ U.T).reshape(T, B, 1)}
     obs = (1 << A.OBS_POSITION) | (1 << A.OBS_KINETIC) | (1 << A.OBS_TOTAL_ENERGY)
     return Workload("rpmd_harmonic32", "C3 RPMD 32 beads, Harmonic(m_H, w=0.005), 300 K thermal sample, dt=2.5, 10^4 steps, saveat 100",
-                    models.Harmonic(m=m, ω=w), A.METHOD_CLASSICAL, np.array([m]), 2.5, 10000, 100, obs, 1 << 20,
+                    models.Harmonic(m=m, ω=w), A.METHOD_CLASSICAL, np.array([m]), 2.5, 10000, 100, obs, 1 << 18,
                     rpmd_flops(B, 1, 3.0), sample, nbeads=B, temperature=kT)
 
 
