@@ -26,6 +26,26 @@ struct ObsLayout {
     int64_t total;                      // doubles in the accumulator
 };
 
+// AdiabaticIESH (CTA per trajectory, kernel_iesh.cuh): tile / shared-memory plan computed on the host.
+struct IeshLayout {
+    int32_t threads;    // block size
+    int32_t nrt;        // row tiles of 8 states
+    int32_t ldg;        // 8*nrt: leading dimension of G (column-major) and rows of the psi chunk
+    int32_t nct;        // column tiles (4 doubles = 2 electrons, re/im interleaved) per psi chunk
+    int32_t ldb;        // 4*nct: row length of the psi chunk
+    int32_t nchunks;    // psi chunks per trajectory
+    int32_t resident;   // 1: G lives in shared memory; 0: streamed from global in slabs of kb columns
+    int32_t kb;
+    int32_t nslab;
+    int32_t lds;        // leading dimension of the overlap matrix S in the hop phase
+    int32_t lr;         // lanes per secular-equation root (power of two)
+    int32_t off_b;      // psi-chunk offset (doubles) inside the work region
+    int32_t off_hop;    // hop-phase offset inside the work region
+    int32_t work_doubles;
+    int32_t smem_bytes;
+    int32_t reserved;
+};
+
 // Kernel parameter block (passed by value as a __grid_constant__).
 struct KParams {
     // sizes
@@ -62,6 +82,11 @@ struct KParams {
     double* pop0;   // [2n][T] initial diabatic / adiabatic population (correlation functions)
     double* qmap;   // [B*n][T]
     double* pmap;
+    // AdiabaticIESH: psi / occupations are TRAJECTORY-major ([T][n*ne], [T][ne]); see kernel_iesh.cuh
+    IeshLayout iesh;
+    double* iesh_lam;   // [T][n]   adiabatic energies of the last step (warm start of the root finder)
+    double* iesh_sgn;   // [T][n]   eigenvector column signs (gauge), constant along a trajectory
+    double* iesh_G;     // [grid][ldg*kb*nslab] v.d scratch when it does not fit in shared memory
     // draws (injected): xi[(step - draws_step0) * T + traj]
     const double* draws;
     int64_t draws_step0;

@@ -33,9 +33,10 @@ bool select_kernels(const nqcb200_config& c, KernelSet& out, std::string& why) {
             if (c.nbeads > 1) return select_ring_density(c, out, why);
             if (c.model == NQCB200_MODEL_SPIN_BOSON) return select_density_spinboson(c, out, why);
             return select_density_1d(c, out, why);
+        case NQCB200_METHOD_IESH: return select_iesh(c, out, why);
         default: break;
     }
-    why = "method has no kernel yet (AdiabaticIESH is not built in this round)";
+    why = "unknown dynamics method";
     return false;
 }
 
@@ -71,6 +72,10 @@ __global__ void soa_to_aos(const Tin* __restrict__ in, Tout* __restrict__ out, i
         const int64_t t = t0 + i; const int c = c0 + threadIdx.x;
         if (t < T && c < C) out[t * C + c] = tile[threadIdx.x][i];
     }
+}
+__global__ void add_offset_i32(const int32_t* __restrict__ in, int32_t* __restrict__ out, int64_t count, int32_t add) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) out[i] = in[i] + add;
 }
 __global__ void fold_replicas(const double* __restrict__ rep, double* __restrict__ out, int64_t total, int nrep) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -148,6 +153,8 @@ struct nqcb200_handle {
     int nsig = 0, nstate = 0;
     double last_ms = 0.0;
     int64_t last_launches = 0;
+    int64_t persistent_ctas = 1;   // CTA-per-trajectory kernels: resident CTAs (one per SM)
+    bool traj_major = false;       // AdiabaticIESH: psi / occupations / diagnostics stay trajectory-major on the device
     std::string err;
 };
 
@@ -194,6 +201,7 @@ int download_field(nqcb200_handle* h, const double* src, double* host, int C) {
 }
 
 unsigned grid_for(const nqcb200_handle* h) {
+    if (h->ks.cta_per_trajectory) return (unsigned)std::max<int64_t>(1, std::min<int64_t>(h->cfg.ntraj, h->persistent_ctas));
     const int64_t threads = h->cfg.ntraj * h->ks.L;
     return (unsigned)std::max<int64_t>(1, (threads + kBlockThreads - 1) / kBlockThreads);
 }
@@ -206,6 +214,12 @@ int fold_observables(nqcb200_handle* h) {
     return NQCB200_OK;
 }
 
+int launch_init(nqcb200_handle* h, int basis, int sample_state, const double* state_draw) {
+    h->ks.init<<<grid_for(h), h->ks.block, h->ks.dyn_smem, h->stream>>>(h->kp, basis, sample_state, state_draw);
+    NQ_CUDA(h, cudaGetLastError());
+    return NQCB200_OK;
+}
+
 int set_state_impl(nqcb200_handle* h, const double* r, const double* v, const double* sre, const double* sim,
                    const int32_t* state, int basis, const double* state_draw) {
     if (!h) return NQCB200_ERR_INVALID;
@@ -213,7 +227,10 @@ int set_state_impl(nqcb200_handle* h, const double* r, const double* v, const do
     const nqcb200_config& c = h->cfg;
     const int64_t T = c.ntraj;
     const bool density = (c.method == NQCB200_METHOD_FSSH || c.method == NQCB200_METHOD_EHRENFEST);
+    const bool iesh = (c.method == NQCB200_METHOD_IESH);
     if (density && !sre) { h->err = "the density matrix is required for FSSH / Ehrenfest"; return NQCB200_ERR_INVALID; }
+    if (iesh && (!sre || !state)) { h->err = "AdiabaticIESH needs psi (n x ne) and the occupied states"; return NQCB200_ERR_INVALID; }
+    if (iesh && basis != 0) { h->err = "AdiabaticIESH: only adiabatic initial wavefunctions are supported"; return NQCB200_ERR_UNSUPPORTED; }
     NQ_CUDA(h, cudaSetDevice(c.device));
     int rc;
     const int BD = c.nbeads * c.ndofs;
@@ -223,6 +240,18 @@ int set_state_impl(nqcb200_handle* h, const double* r, const double* v, const do
         if ((rc = upload_field(h, sre, h->kp.sig_re, h->nsig)) != 0) return rc;
         if (sim) { if ((rc = upload_field(h, sim, h->kp.sig_im, h->nsig)) != 0) return rc; }
         else NQ_CUDA(h, cudaMemsetAsync(h->kp.sig_im, 0, sizeof(double) * T * h->nsig, h->stream));
+    }
+    if (iesh && T > 0) {
+        // psi and the occupation vectors stay trajectory-major: one CTA owns one trajectory (kernel_iesh.cuh)
+        const size_t bytes = sizeof(double) * (size_t)T * h->nsig;
+        NQ_CUDA(h, cudaMemcpyAsync(h->kp.sig_re, sre, bytes, cudaMemcpyHostToDevice, h->stream));
+        if (sim) NQ_CUDA(h, cudaMemcpyAsync(h->kp.sig_im, sim, bytes, cudaMemcpyHostToDevice, h->stream));
+        else NQ_CUDA(h, cudaMemsetAsync(h->kp.sig_im, 0, bytes, h->stream));
+        const int64_t cnt = T * h->nstate;
+        int32_t* stage_i = (int32_t*)h->staging;
+        NQ_CUDA(h, cudaMemcpyAsync(stage_i, state, sizeof(int32_t) * cnt, cudaMemcpyHostToDevice, h->stream));
+        add_offset_i32<<<(unsigned)((cnt + 255) / 256), 256, 0, h->stream>>>(stage_i, h->kp.state, cnt, -1);
+        NQ_CUDA(h, cudaGetLastError());
     }
     int sample_state = 0;
     if (c.method == NQCB200_METHOD_FSSH) {
@@ -237,7 +266,7 @@ int set_state_impl(nqcb200_handle* h, const double* r, const double* v, const do
             if (state_draw) NQ_CUDA(h, cudaMemcpyAsync(h->d_state_draw, state_draw, sizeof(double) * T, cudaMemcpyHostToDevice, h->stream));
         }
     }
-    if (!h->user_gauge && c.nstates > 1 && h->kp.Zprev) {
+    if (!iesh && !h->user_gauge && c.nstates > 1 && h->kp.Zprev) {
         fill_identity<<<(unsigned)((T + 255) / 256), 256, 0, h->stream>>>(h->kp.Zprev, T, c.nstates, h->zcopies);
         NQ_CUDA(h, cudaGetLastError());
     }
@@ -248,9 +277,9 @@ int set_state_impl(nqcb200_handle* h, const double* r, const double* v, const do
     h->kp.step0 = 0;
     h->kp.nsteps = 0;
     if (T > 0 && c.method != NQCB200_METHOD_NRPMD) {   // NRPMD: save point 0 is recorded by set_mapping
-        h->ks.init<<<grid_for(h), kBlockThreads, 0, h->stream>>>(h->kp, basis, sample_state,
-                                                                (sample_state && state_draw) ? h->d_state_draw : nullptr);
-        NQ_CUDA(h, cudaGetLastError());
+        if (iesh) rc = launch_init(h, h->user_gauge ? 1 : 0, 0, nullptr);
+        else rc = launch_init(h, basis, sample_state, (sample_state && state_draw) ? h->d_state_draw : nullptr);
+        if (rc) return rc;
     }
     NQ_CUDA(h, cudaStreamSynchronize(h->stream));
     h->nsave_done = (c.method == NQCB200_METHOD_NRPMD) ? 0 : 1;
@@ -295,6 +324,10 @@ int nqcb200_create(const nqcb200_config* cfg, nqcb200_handle** out) {
     KernelSet ks;
     std::string why;
     if (!select_kernels(*cfg, ks, why)) { g_create_error = why; return NQCB200_ERR_UNSUPPORTED; }
+    if (cfg->method == NQCB200_METHOD_IESH &&
+        (cfg->observables & ((1u << NQCB200_OBS_POPCORR_DIABATIC) | (1u << NQCB200_OBS_POPCORR_ADIABATIC)))) {
+        g_create_error = "PopulationCorrelationFunction is not available for AdiabaticIESH"; return NQCB200_ERR_UNSUPPORTED;
+    }
     int ndev = nqcb200_device_count();
     if (ndev <= 0) { g_create_error = "no CUDA device visible (this library has no CPU path)"; return NQCB200_ERR_NO_DEVICE; }
     if (cfg->device < 0 || cfg->device >= ndev) { g_create_error = "device ordinal out of range"; return NQCB200_ERR_INVALID; }
@@ -330,9 +363,22 @@ int nqcb200_create(const nqcb200_config* cfg, nqcb200_handle** out) {
         if (c.observables & (1u << id)) { kp.layout.offset[id] = off; off += (int64_t)c.nsave * kp.layout.width[id]; }
     }
     kp.layout.total = off;
-    h->nsig = (c.method == NQCB200_METHOD_FSSH || c.method == NQCB200_METHOD_EHRENFEST) ? n * n : 0;
-    h->nstate = (c.method == NQCB200_METHOD_FSSH) ? 1 : 0;
+    const bool iesh = (c.method == NQCB200_METHOD_IESH);
+    h->nsig = (c.method == NQCB200_METHOD_FSSH || c.method == NQCB200_METHOD_EHRENFEST) ? n * n : (iesh ? n * c.nelectrons : 0);
+    h->nstate = (c.method == NQCB200_METHOD_FSSH) ? 1 : (iesh ? c.nelectrons : 0);
     h->zcopies = (B > 1) ? B + 1 : 1;
+    h->traj_major = iesh;
+    if (ks.cta_per_trajectory) {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) { h->err = "cudaGetDeviceProperties"; cudaGetLastError(); return fail(NQCB200_ERR_CUDA); }
+        h->persistent_ctas = prop.multiProcessorCount;
+        if (ks.dyn_smem > (size_t)prop.sharedMemPerBlockOptin) { h->err = "kernel needs more shared memory than the device offers"; return fail(NQCB200_ERR_UNSUPPORTED); }
+        if (cudaFuncSetAttribute((const void*)ks.step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ks.dyn_smem) != cudaSuccess ||
+            cudaFuncSetAttribute((const void*)ks.init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ks.dyn_smem) != cudaSuccess) {
+            h->err = "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)"; cudaGetLastError(); return fail(NQCB200_ERR_CUDA);
+        }
+        kp.iesh = ks.iesh;
+    }
 
     int rc;
     double *masses = nullptr, *ba = nullptr, *bb = nullptr;
@@ -391,9 +437,19 @@ int nqcb200_create(const nqcb200_config* cfg, nqcb200_handle** out) {
     if (h->nsig) {
         if ((rc = dev_alloc(h, &kp.sig_re, (size_t)h->nsig * T)) != 0) return fail(rc);
         if ((rc = dev_alloc(h, &kp.sig_im, (size_t)h->nsig * T)) != 0) return fail(rc);
+    }
+    if (h->nsig && !iesh) {
         if ((rc = dev_alloc(h, &kp.Zprev, (size_t)h->zcopies * n * n * T)) != 0) return fail(rc);
         if ((rc = dev_alloc(h, &kp.ecur, (size_t)(n + n * n) * T)) != 0) return fail(rc);
         if ((rc = dev_alloc(h, &kp.pop0, (size_t)2 * n * T)) != 0) return fail(rc);
+    }
+    if (iesh) {
+        if ((rc = dev_alloc(h, &kp.iesh_lam, (size_t)n * T)) != 0) return fail(rc);
+        if ((rc = dev_alloc(h, &kp.iesh_sgn, (size_t)n * T)) != 0) return fail(rc);
+        if (!kp.iesh.resident) {
+            const size_t per_cta = (size_t)kp.iesh.ldg * kp.iesh.kb * kp.iesh.nslab;
+            if ((rc = dev_alloc(h, &kp.iesh_G, per_cta * (size_t)h->persistent_ctas)) != 0) return fail(rc);
+        }
     }
     if (h->nstate) { if ((rc = dev_alloc(h, &kp.state, (size_t)h->nstate * T)) != 0) return fail(rc); }
     if (c.method == NQCB200_METHOD_NRPMD) {
@@ -412,7 +468,8 @@ int nqcb200_create(const nqcb200_config* cfg, nqcb200_handle** out) {
     if ((rc = dev_alloc(h, &kp.counters, 4)) != 0) return fail(rc);
     if ((rc = dev_alloc(h, &h->d_state_draw, (size_t)T)) != 0) return fail(rc);
     // staging: large enough for any single field (and the per-trajectory outputs of one observable)
-    size_t stage = std::max<size_t>({BD, (size_t)h->nsig, (size_t)D * n * n, (size_t)h->zcopies * n * n, (size_t)B * n, (size_t)1});
+    size_t stage = iesh ? std::max<size_t>(BD, (size_t)(h->nstate + 1) / 2 + 1)
+                        : std::max<size_t>({BD, (size_t)h->nsig, (size_t)D * n * n, (size_t)h->zcopies * n * n, (size_t)B * n, (size_t)1});
     if (c.per_trajectory) {
         for (int id = 0; id < NQCB200_OBS_COUNT; ++id)
             if (c.observables & (1u << id)) stage = std::max(stage, (size_t)c.nsave * kp.layout.width[id]);
@@ -433,7 +490,13 @@ int nqcb200_set_gauge_reference(nqcb200_handle* h, const double* Z, int64_t coun
     if (!h || !Z) return NQCB200_ERR_INVALID;
     if (count_per_traj != h->zcopies || h->cfg.nstates < 2) { h->err = "gauge reference: expected nbeads(+1 centroid) matrices per trajectory"; return NQCB200_ERR_INVALID; }
     NQ_CUDA(h, cudaSetDevice(h->cfg.device));
-    int rc = upload_field(h, Z, h->kp.Zprev, h->zcopies * h->cfg.nstates * h->cfg.nstates);
+    int rc;
+    if (h->traj_major) {
+        const size_t cnt = (size_t)h->cfg.nstates * h->cfg.nstates * (size_t)h->cfg.ntraj;
+        if (!h->kp.Zprev && (rc = dev_alloc(h, &h->kp.Zprev, cnt)) != 0) return rc;
+        NQ_CUDA(h, cudaMemcpyAsync(h->kp.Zprev, Z, sizeof(double) * cnt, cudaMemcpyHostToDevice, h->stream));
+        rc = NQCB200_OK;
+    } else rc = upload_field(h, Z, h->kp.Zprev, h->zcopies * h->cfg.nstates * h->cfg.nstates);
     if (rc) return rc;
     NQ_CUDA(h, cudaStreamSynchronize(h->stream));
     h->user_gauge = true;
@@ -461,8 +524,8 @@ int nqcb200_set_mapping(nqcb200_handle* h, const double* qmap, const double* pma
     if ((rc = upload_field(h, pmap, h->kp.pmap, C)) != 0) return rc;
     NQ_CUDA(h, cudaMemsetAsync(h->kp.obs_sum, 0, sizeof(double) * std::max<int64_t>(1, h->kp.layout.total) * kObsReplicas, h->stream));
     if (h->cfg.ntraj > 0) {
-        h->ks.init<<<grid_for(h), kBlockThreads, 0, h->stream>>>(h->kp, 0, 0, nullptr);
-        NQ_CUDA(h, cudaGetLastError());
+        int rc2 = launch_init(h, 0, 0, nullptr);
+        if (rc2) return rc2;
     }
     NQ_CUDA(h, cudaStreamSynchronize(h->stream));
     h->nsave_done = 1;
@@ -504,7 +567,7 @@ int nqcb200_run(nqcb200_handle* h, int64_t nsteps) {
     if (!h->has_state) { h->err = "run before set_state"; return NQCB200_ERR_STATE; }
     const nqcb200_config& c = h->cfg;
     NQ_CUDA(h, cudaSetDevice(c.device));
-    if (c.method == NQCB200_METHOD_FSSH && c.rng == NQCB200_RNG_INJECTED) {
+    if ((c.method == NQCB200_METHOD_FSSH || (c.method == NQCB200_METHOD_IESH && !c.disable_hopping)) && c.rng == NQCB200_RNG_INJECTED) {
         if (!h->kp.draws || h->step_count < h->kp.draws_step0 ||
             h->step_count + nsteps > h->kp.draws_step0 + h->draws_nsteps) {
             h->err = "not enough injected draws for this run"; return NQCB200_ERR_STATE;
@@ -520,7 +583,7 @@ int nqcb200_run(nqcb200_handle* h, int64_t nsteps) {
         const int64_t chunk = std::min(nsteps - done, max_per_launch);
         h->kp.step0 = h->step_count + done;
         h->kp.nsteps = (int32_t)chunk;
-        h->ks.step<<<grid_for(h), kBlockThreads, 0, h->stream>>>(h->kp);
+        h->ks.step<<<grid_for(h), h->ks.block, h->ks.dyn_smem, h->stream>>>(h->kp);
         NQ_CUDA(h, cudaGetLastError());
         h->last_launches++;
         done += chunk;
@@ -543,6 +606,23 @@ int nqcb200_get_state(nqcb200_handle* h, double* r, double* v, double* sig_re, d
     int rc;
     if (r && (rc = download_field(h, h->kp.r, r, BD)) != 0) return rc;
     if (v && (rc = download_field(h, h->kp.v, v, BD)) != 0) return rc;
+    if (h->traj_major) {
+        const int64_t T = h->cfg.ntraj;
+        if (T > 0) {
+            const size_t bytes = sizeof(double) * (size_t)T * h->nsig;
+            if (sig_re) NQ_CUDA(h, cudaMemcpyAsync(sig_re, h->kp.sig_re, bytes, cudaMemcpyDeviceToHost, h->stream));
+            if (sig_im) NQ_CUDA(h, cudaMemcpyAsync(sig_im, h->kp.sig_im, bytes, cudaMemcpyDeviceToHost, h->stream));
+            if (state) {
+                const int64_t cnt = T * h->nstate;
+                int32_t* stage_i = (int32_t*)h->staging;
+                add_offset_i32<<<(unsigned)((cnt + 255) / 256), 256, 0, h->stream>>>(h->kp.state, stage_i, cnt, 1);
+                NQ_CUDA(h, cudaGetLastError());
+                NQ_CUDA(h, cudaMemcpyAsync(state, stage_i, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, h->stream));
+            }
+            NQ_CUDA(h, cudaStreamSynchronize(h->stream));
+        }
+        return NQCB200_OK;
+    }
     if (sig_re && h->nsig && (rc = download_field(h, h->kp.sig_re, sig_re, h->nsig)) != 0) return rc;
     if (sig_im && h->nsig && (rc = download_field(h, h->kp.sig_im, sig_im, h->nsig)) != 0) return rc;
     if (state && h->nstate) {
@@ -604,6 +684,15 @@ int nqcb200_get_diagnostics(nqcb200_handle* h, double* eig, double* nac, double*
     NQ_CUDA(h, cudaSetDevice(h->cfg.device));
     const int n = h->cfg.nstates, D = h->cfg.ndofs;
     int rc;
+    if (h->traj_major) {
+        const size_t T = (size_t)h->cfg.ntraj;
+        if (eig) NQ_CUDA(h, cudaMemcpyAsync(eig, h->kp.diag_eig, sizeof(double) * T * n, cudaMemcpyDeviceToHost, h->stream));
+        if (nac) NQ_CUDA(h, cudaMemcpyAsync(nac, h->kp.diag_nac, sizeof(double) * T * n * n, cudaMemcpyDeviceToHost, h->stream));
+        if (accel) NQ_CUDA(h, cudaMemcpyAsync(accel, h->kp.acc, sizeof(double) * T, cudaMemcpyDeviceToHost, h->stream));
+        if (Z) NQ_CUDA(h, cudaMemcpyAsync(Z, h->kp.diag_Z, sizeof(double) * T * n * n, cudaMemcpyDeviceToHost, h->stream));
+        NQ_CUDA(h, cudaStreamSynchronize(h->stream));
+        return NQCB200_OK;
+    }
     if (eig && (rc = download_field(h, h->kp.diag_eig, eig, n)) != 0) return rc;
     if (nac && (rc = download_field(h, h->kp.diag_nac, nac, D * n * n)) != 0) return rc;
     if (accel && (rc = download_field(h, h->kp.acc, accel, h->cfg.nbeads * D)) != 0) return rc;

@@ -18,6 +18,7 @@ struct KernelSet {
     int block = kBlockThreads;
     size_t dyn_smem = 0;
     bool cta_per_trajectory = false;
+    IeshLayout iesh = {};   // AdiabaticIESH tile / shared-memory plan (kernel_iesh.cuh)
     const char* name = "";
 };
 
@@ -28,5 +29,6 @@ bool select_density_spinboson(const nqcb200_config& c, KernelSet& out, std::stri
 bool select_ring_density(const nqcb200_config& c, KernelSet& out, std::string& why);
 bool select_classical(const nqcb200_config& c, KernelSet& out, std::string& why);
 bool select_nrpmd(const nqcb200_config& c, KernelSet& out, std::string& why);
+bool select_iesh(const nqcb200_config& c, KernelSet& out, std::string& why);
 
 }  // namespace nq

@@ -274,3 +274,152 @@ def test_unsupported_configuration_fails_loudly():
     with pytest.raises(nq.EngineError) as ei:
         engine_factory()(cfg, keep)
     assert ei.value.code == -2
+
+
+# ---- AdiabaticIESH on the Newns-Anderson model (BASELINE config 4) ---------------------------------------
+IESH_OBS = ((1 << A.OBS_ADIABATIC_POP) | (1 << A.OBS_DIABATIC_POP) | (1 << A.OBS_KINETIC) | (1 << A.OBS_POTENTIAL) |
+            (1 << A.OBS_TOTAL_ENERGY) | (1 << A.OBS_POSITION) | (1 << A.OBS_VELOCITY) | (1 << A.OBS_DISCRETE_STATE) |
+            (1 << A.OBS_SIGMA))
+
+
+def _iesh_model(M, width=0.0192):
+    return nq.AndersonHolstein(nq.MiaoSubotnik(Γ=6.4e-3), nq.TrapezoidalRule(M, -width, width))
+
+
+def _iesh_ground_state(T, n, ne):
+    psi = np.zeros((T, ne, n))
+    psi[:, np.arange(ne), np.arange(ne)] = 1.0            # DynamicsVariables(sim, v, r): iesh.jl:89-97
+    state = np.tile(np.arange(1, ne + 1, dtype=np.int32), (T, 1))
+    return psi, state
+
+
+def _iesh_random_state(rng, T, n, ne):
+    """Orthonormal complex orbitals near (but not at) the adiabatic ground state, so that det S is not tiny."""
+    re = np.empty((T, ne, n)); im = np.empty((T, ne, n))
+    for t in range(T):
+        q, _ = np.linalg.qr(rng.standard_normal((n, ne)) + 1j * rng.standard_normal((n, ne)))
+        q, _ = np.linalg.qr(np.eye(n, ne) + 0.3 * q)
+        re[t], im[t] = q.T.real, q.T.imag
+    state = np.tile(np.arange(1, ne + 1, dtype=np.int32), (T, 1))
+    return re, im, state
+
+
+def _iesh_pair(M, T, dt, nsave, save_every=1, **extra):
+    model = _iesh_model(M)
+    kw = model_config(model, method=A.METHOD_IESH, masses=[2000.0], ntraj=T, dt=dt, rng=A.RNG_INJECTED, diagnostics=1,
+                      save_every=save_every, nsave=nsave, observables=IESH_OBS, per_trajectory=1)
+    kw.update(extra)
+    return model, make_pair(engine_factory(), oracle_factory(), **kw)
+
+
+def _iesh_compare(e, o, tol, what):
+    se, so = e.get_state(), o.get_state()
+    for key in ("r", "v"):
+        assert rel_err(se[key], so[key]) < tol, f"{what} {key}"
+    assert np.max(np.abs(se["sigma"] - so["sigma"])) < tol, f"{what} psi"
+    assert np.array_equal(se["state"], so["state"]), f"{what} occupations"
+    de, do = e.diagnostics(), o.diagnostics()
+    assert rel_err(de["eig"], do["eig"]) < tol, f"{what} eigenvalues"
+    assert rel_err(de["accel"], do["accel"]) < tol, f"{what} acceleration"
+    assert np.max(np.abs(de["Z"] - do["Z"])) < tol, f"{what} eigenvectors"
+    assert np.max(np.abs(de["nac"] - do["nac"])) < tol * max(1.0, np.max(np.abs(do["nac"]))), f"{what} NAC"
+
+
+@pytest.mark.parametrize("start", ["ground", "random"])
+def test_iesh_per_step_parity(start):
+    """n = 31, ne = 15 (test/Dynamics/iesh.jl:19,30): r, v, psi, occupations, w, Z, NAC, force, every estimator."""
+    M, T, nsteps = 30, 6, 12
+    rng = np.random.default_rng(21)
+    model, (e, o) = _iesh_pair(M, T, 1.0, nsteps + 1)
+    n, ne = model.nstates, model.nelectrons
+    r = 21.0 * rng.random(T)            # both wells and the crossing region
+    v = rng.standard_normal(T) * np.sqrt(9.5e-4 / 2000.0) * 5
+    if start == "ground":
+        re, state = _iesh_ground_state(T, n, ne); im = None
+    else:
+        re, im, state = _iesh_random_state(rng, T, n, ne)
+    xi = rng.random((nsteps, T))
+    for h in (e, o):
+        h.set_state(r, v, re, im, state)
+        h.set_draws(xi)
+    _iesh_compare(e, o, STEP_TOL, "t0")
+    for chunk in range(nsteps // 4):
+        e.run(4); o.run(4)
+        _iesh_compare(e, o, STEP_TOL, f"chunk {chunk}")
+    _compare_observables(e, o, IESH_OBS, 1e-9, T)
+    for oid in (A.OBS_DIABATIC_POP, A.OBS_TOTAL_ENERGY, A.OBS_SIGMA):
+        assert np.max(np.abs(e.observable_per_trajectory(oid) - o.observable_per_trajectory(oid))) < 1e-9
+    psi = e.get_state()["sigma"]        # sanity: the orbitals stay normalised
+    assert np.allclose(np.einsum("tie,tie->te", psi.conj(), psi).real, 1.0, atol=1e-12)
+
+
+@pytest.mark.parametrize("rescaling", [A.RESCALE_STANDARD, A.RESCALE_VINVERSION])
+def test_iesh_identical_hop_sequences(rescaling):
+    """Same injected draws -> same hops, frustrated hops and occupations (small draws force the unpruned branch)."""
+    M, T, nsteps = 30, 8, 30
+    rng = np.random.default_rng(22)
+    model, (e, o) = _iesh_pair(M, T, 5.0, nsteps + 1, rescaling=rescaling)
+    n, ne = model.nstates, model.nelectrons
+    r = 5.0 + 12.0 * rng.random(T)
+    v = -np.abs(rng.standard_normal(T)) * 6e-3
+    v[::2] *= 0.05                      # slow trajectories: frustrated hops
+    re, im, state = _iesh_random_state(rng, T, n, ne)
+    xi = rng.random((nsteps, T)) * 5e-4
+    for h in (e, o):
+        h.set_state(r, v, re, im, state)
+        h.set_draws(xi)
+    e.run(nsteps); o.run(nsteps)
+    ce, co = e.counters(), o.counters()
+    assert ce["hops"] == co["hops"] and ce["frustrated"] == co["frustrated"], (ce, co)
+    assert ce["hops"] > 0 and ce["frustrated"] > 0, ce
+    de, do = e.observable_per_trajectory(A.OBS_DISCRETE_STATE), o.observable_per_trajectory(A.OBS_DISCRETE_STATE)
+    assert np.array_equal(de, do)
+    _iesh_compare(e, o, 1e-9, "after hops")
+
+
+@pytest.mark.parametrize("M,T,nsteps,dt", [(100, 2, 3, 1.0), (200, 1, 2, 1.0), (100, 1, 2, 10.0)])
+def test_iesh_large_bath_parity(M, T, nsteps, dt):
+    """BASELINE config 4 sizes: n = 101 (G resident in shared memory) and n = 201 (G streamed in slabs)."""
+    rng = np.random.default_rng(23)
+    model, (e, o) = _iesh_pair(M, T, dt, nsteps + 1)
+    n, ne = model.nstates, model.nelectrons
+    r = 8.0 + 10.0 * rng.random(T)
+    v = -np.abs(rng.standard_normal(T)) * 2e-3
+    re, state = _iesh_ground_state(T, n, ne)
+    xi = rng.random((nsteps, T)) * 0.05
+    for h in (e, o):
+        h.set_state(r, v, re, None, state)
+        h.set_draws(xi)
+    e.run(nsteps); o.run(nsteps)
+    _iesh_compare(e, o, STEP_TOL, f"n={n}")
+    _compare_observables(e, o, IESH_OBS, 1e-9, T)
+
+
+def test_iesh_edc_and_philox_sharding():
+    """EDC decoherence matches the oracle; Philox draws keyed by the global trajectory id are shard independent."""
+    M, T, nsteps = 30, 6, 10
+    rng = np.random.default_rng(24)
+    model, (e, o) = _iesh_pair(M, T, 10.0, nsteps + 1, edc_C=0.1)
+    n, ne = model.nstates, model.nelectrons
+    r = 5.0 + 10.0 * rng.random(T); v = -np.abs(rng.standard_normal(T)) * 2e-3
+    re, im, state = _iesh_random_state(rng, T, n, ne)
+    xi = rng.random((nsteps, T))
+    for h in (e, o):
+        h.set_state(r, v, re, im, state); h.set_draws(xi)
+    e.run(nsteps); o.run(nsteps)
+    _iesh_compare(e, o, 1e-9, "edc")
+    # sharding: the same six trajectories as one handle or as two handles with traj_offset
+    kw = model_config(model, method=A.METHOD_IESH, masses=[2000.0], dt=5.0, rng=A.RNG_PHILOX, seed=99, save_every=1,
+                      nsave=nsteps + 1, observables=(1 << A.OBS_DISCRETE_STATE), per_trajectory=1)
+    outs = []
+    for parts in ([(0, T)], [(0, 2), (2, T)]):
+        acc = []
+        for lo, hi in parts:
+            cfg, keep = A.make_config(ntraj=hi - lo, traj_offset=lo, **kw)
+            h = engine_factory()(cfg, keep)
+            h.set_state(r[lo:hi], 3 * v[lo:hi], re[lo:hi], im[lo:hi], state[lo:hi])
+            h.run(nsteps)
+            acc.append((h.get_state(), h.observable_per_trajectory(A.OBS_DISCRETE_STATE)))
+            h.close()
+        outs.append((np.concatenate([a[0]["sigma"] for a in acc]), np.concatenate([a[1] for a in acc])))
+    assert np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][0], outs[1][0])
