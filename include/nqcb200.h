@@ -274,6 +274,11 @@ int nqcb200_get_diagnostics(nqcb200_handle* h, double* eig, double* nac, double*
 int nqcb200_get_counters(nqcb200_handle* h, int64_t* steps, int64_t* hops, int64_t* frustrated,
                          int64_t* nonfinite);
 
+/* AdiabaticIESH: number of trajectory-steps on which the pruning estimate (iesh.jl:251-254) did NOT
+ * rule out a hop, i.e. on which all ne*(n-ne) hopping probabilities were evaluated (iesh.jl:256-266).
+ * Zero for the other methods.                                                                    */
+int nqcb200_get_hop_search_count(nqcb200_handle* h, int64_t* searches);
+
 /* Number of save points recorded so far, and device time (ms, CUDA events on the launch stream)
  * spent in step kernels by the last nqcb200_run, with the number of kernel launches it made.   */
 int nqcb200_get_progress(nqcb200_handle* h, int64_t* nsave_done, int64_t* step_count);

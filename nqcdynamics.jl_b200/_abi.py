@@ -99,6 +99,7 @@ def bind(lib: C.CDLL, prefix: str) -> None:
     f("get_observable_per_trajectory", [H, C.c_int, _dp, C.c_int64])
     f("get_diagnostics", [H, _dp, _dp, _dp, _dp])
     f("get_counters", [H, _lp, _lp, _lp, _lp])
+    f("get_hop_search_count", [H, _lp])
     f("get_progress", [H, _lp, _lp])
     f("get_last_run_timing", [H, _dp, _lp], required=False)
     f("measure_fp64_peak", [C.c_int, _dp], required=False)
@@ -108,7 +109,7 @@ HEADER_SYMBOLS = [
     "version", "device_count", "create", "destroy", "last_error", "observable_width", "set_state",
     "set_state_diabatic", "set_mapping", "set_gauge_reference", "set_draws", "run", "get_state", "get_mapping",
     "get_observable_sum", "observable_sum_device", "observable_offset", "get_observable_per_trajectory",
-    "get_diagnostics", "get_counters", "get_progress", "get_last_run_timing", "measure_fp64_peak",
+    "get_diagnostics", "get_counters", "get_hop_search_count", "get_progress", "get_last_run_timing", "measure_fp64_peak",
 ]
 
 _ENGINE_LIB: Optional[C.CDLL] = None
@@ -263,6 +264,11 @@ class CHandle:
         vals = [C.c_int64() for _ in range(4)]
         self._call("get_counters", *[C.byref(x) for x in vals])
         return dict(zip(("steps", "hops", "frustrated", "nonfinite"), (int(x.value) for x in vals)))
+
+    def hop_search_count(self) -> int:
+        x = C.c_int64()
+        self._call("get_hop_search_count", C.byref(x))
+        return int(x.value)
 
     def progress(self):
         a, b = C.c_int64(), C.c_int64()

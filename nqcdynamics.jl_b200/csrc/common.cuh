@@ -28,11 +28,11 @@ struct ObsLayout {
 
 // AdiabaticIESH (CTA per trajectory, kernel_iesh.cuh): tile / shared-memory plan computed on the host.
 struct IeshLayout {
-    int32_t threads;    // block size
+    int32_t threads;    // block size (13 warps)
     int32_t nrt;        // row tiles of 8 states
-    int32_t ldg;        // 8*nrt: leading dimension of G (column-major) and rows of the psi chunk
-    int32_t nct;        // column tiles (4 doubles = 2 electrons, re/im interleaved) per psi chunk
-    int32_t ldb;        // 4*nct: row length of the psi chunk
+    int32_t ldg;        // leading dimension of G (column-major), >= 8*nrt and = 4 (mod 16): conflict-free DMMA fragments
+    int32_t nct;        // column tiles (8 doubles = 4 electrons, re/im interleaved) per psi chunk
+    int32_t ldb;        // row length of the psi chunk, >= 8*nct and = 4 (mod 16)
     int32_t nchunks;    // psi chunks per trajectory
     int32_t resident;   // 1: G lives in shared memory; 0: streamed from global in slabs of kb columns
     int32_t kb;
@@ -43,7 +43,7 @@ struct IeshLayout {
     int32_t off_hop;    // hop-phase offset inside the work region
     int32_t work_doubles;
     int32_t smem_bytes;
-    int32_t reserved;
+    int32_t rounds;     // row tiles per warp (1 or 2)
 };
 
 // Kernel parameter block (passed by value as a __grid_constant__).

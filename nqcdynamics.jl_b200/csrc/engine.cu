@@ -719,6 +719,16 @@ int nqcb200_get_counters(nqcb200_handle* h, int64_t* steps, int64_t* hops, int64
     return NQCB200_OK;
 }
 
+int nqcb200_get_hop_search_count(nqcb200_handle* h, int64_t* searches) {
+    if (!h || !searches) return NQCB200_ERR_INVALID;
+    NQ_CUDA(h, cudaSetDevice(h->cfg.device));
+    unsigned long long host = 0;
+    NQ_CUDA(h, cudaMemcpyAsync(&host, h->kp.counters + 3, sizeof(host), cudaMemcpyDeviceToHost, h->stream));
+    NQ_CUDA(h, cudaStreamSynchronize(h->stream));
+    *searches = (int64_t)host;
+    return NQCB200_OK;
+}
+
 int nqcb200_get_progress(nqcb200_handle* h, int64_t* nsave_done, int64_t* step_count) {
     if (!h) return NQCB200_ERR_INVALID;
     if (nsave_done) *nsave_done = h->nsave_done;

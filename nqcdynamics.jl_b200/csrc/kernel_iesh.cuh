@@ -24,12 +24,14 @@
 //    eigenvectors is 1 + sum_k V_k^2/((l-eps_k)(l'-eps_k)) > 0 -- the sign fixed at t0 never changes.
 //  * exp(-i (W - i G) dt) psi  (G = v.d real antisymmetric) is applied as a Taylor series in the shifted
 //    generator A = -i dt (W - s) - dt G acting on the n x 2ne real matrix [Re psi | Im psi]: one real
-//    GEMM  G * [X|Y]  per term (8x4 register tiles, G in shared memory or streamed from L2 in slabs).
+//    GEMM  G * [X|Y]  per Horner stage on the FP64 tensor cores (DMMA m8n8k4; G in shared memory or streamed from
+//    L2 in slabs).
 //    The truncation order is chosen per step from rho = dt (max|w - s| + ||G||_F) so that the remainder
 //    is below 1e-17; eigensolver-independent, agrees with V exp(-i lambda dt) V' psi to rounding.
-//  * Hop probabilities: one in-place Gauss-Jordan inversion of the overlap S (ne x ne complex) gives det S
-//    and, through the matrix-determinant lemma, every det S_{e->m} / det S = (psi_m . S^-1)_e -- instead of
-//    ne (n - ne) separate LU factorisations.  The reference's pruning estimate and single draw are kept.
+//  * Hop test: det S (ne x ne complex overlap) from an LU factorisation held in registers across the CTA; the
+//    reference's pruning estimate and single draw are kept.  Only when the estimate does not rule a hop out, one
+//    in-place Gauss-Jordan inversion of S gives, through the matrix-determinant lemma, every
+//    det S_{e->m} / det S = (psi_m . S^-1)_e -- instead of ne (n - ne) separate LU factorisations.
 #pragma once
 #include "common.cuh"
 #include "philox.cuh"
@@ -93,31 +95,43 @@ NQ_HD int iesh_small_doubles(int n) {
 }
 
 // Secular function at offset mu from pole p: f = (h - eps_p) - mu - sum_k V_k^2 / ((eps_k - eps_p) - mu),
-// fp = -f' = 1 + sum_k V_k^2 / (...)^2.  The lr lanes of a group split the sum (bit-identical result on all).
+// fp = -f' = 1 + sum_k V_k^2 / (...)^2, s3 = sum_k V_k^2 / (...)^3 (so d fp / d mu = 2 s3).
+// The lr lanes of a group split the sum (xor butterfly: bit-identical result on all of them).
 NQ_D void iesh_secular(const double* eps, const double* V2, int M, int p, double hp, double mu, int sub, int lr,
-                       unsigned mask, double& f, double& fp) {
+                       unsigned mask, double& f, double& fp, double& s3) {
     const double ep = eps[p];
-    double s1 = 0.0, s2 = 0.0;
+    double s1 = 0.0, s2 = 0.0, s3l = 0.0;
+#pragma unroll 4
     for (int k = sub; k < M; k += lr) {
         const double d = (eps[k] - ep) - mu;
         const double inv = 1.0 / d;
         const double t = V2[k] * inv;
+        const double u = t * inv;
         s1 += t;
-        s2 = fma(t, inv, s2);
+        s2 += u;
+        s3l = fma(u, inv, s3l);
     }
     for (int o = lr >> 1; o > 0; o >>= 1) {
         s1 += __shfl_xor_sync(mask, s1, o);
         s2 += __shfl_xor_sync(mask, s2, o);
+        s3l += __shfl_xor_sync(mask, s3l, o);
     }
     f = (hp - mu) - s1;
     fp = 1.0 + s2;
+    s3 = s3l;
 }
 
 // Root i of the secular equation (i = 0..M, ascending): pole index p, offset mu = lambda - eps_p, fp = -f'(lambda).
+// Roots interlace the poles: root i lies in (eps[i-1], eps[i]) (eps[-1] = -inf, eps[M] = +inf).  The offset is taken
+// from the pole nearest to the warm start lam_prev (the previous step's eigenvalue; NaN = cold start: the pole
+// is then chosen by the sign of f at the interval midpoint).  Safeguarded Newton on phi(mu) = mu f(mu), which
+// removes the pole at mu = 0 and converges quadratically; the last step is accepted when it is below 3e-8 |mu|
+// (error after it ~ 1e-15 |mu|) and fp is corrected to first order with s3.
 NQ_D void iesh_root(const double* eps, const double* V2, int M, int i, double h, double vnorm, double lam_prev,
                     int sub, int lr, unsigned mask, int& p_out, double& mu_out, double& fp_out) {
     int p;
     double lo, hi;
+    const bool cold = !(lam_prev == lam_prev);
     if (i == 0) {
         p = 0; hi = 0.0;
         lo = (fmin(h, eps[0]) - vnorm) - eps[0];
@@ -127,28 +141,37 @@ NQ_D void iesh_root(const double* eps, const double* V2, int M, int i, double h,
         hi = (fmax(h, eps[M - 1]) + vnorm) - eps[M - 1];
         hi += 1e-6 * fabs(hi) + 1e-300;
     } else {
-        const double half = 0.5 * (eps[i] - eps[i - 1]);
-        double f, fp;
-        iesh_secular(eps, V2, M, i - 1, h - eps[i - 1], half, sub, lr, mask, f, fp);
-        if (f > 0.0) { p = i; lo = -half; hi = 0.0; }       // f decreases: root right of the midpoint
-        else { p = i - 1; lo = 0.0; hi = half * (1.0 + 4e-16); }
+        const double gap = eps[i] - eps[i - 1];
+        bool right;
+        if (cold) {
+            double f, fp, s3;
+            iesh_secular(eps, V2, M, i - 1, h - eps[i - 1], 0.5 * gap, sub, lr, mask, f, fp, s3);
+            right = f > 0.0;                                  // f decreases: root right of the midpoint
+        } else right = (eps[i] - lam_prev) < (lam_prev - eps[i - 1]);
+        if (right) { p = i; lo = -gap; hi = 0.0; }
+        else { p = i - 1; lo = 0.0; hi = gap; }
     }
     const double hp = h - eps[p];
     double mu = lam_prev - eps[p];
-    if (!(mu > lo && mu < hi)) mu = 0.5 * (lo + hi);
+    if (!(mu > lo && mu < hi)) {
+        if (i == 0 || i == M) mu = 0.5 * (lo + hi);
+        else mu = (p == i) ? 0.25 * lo : 0.25 * hi;          // a quarter of the gap away from the chosen pole
+    }
     double fpv = 1.0;
-    for (int it = 0; it < 80; ++it) {
-        double f, fp;
-        iesh_secular(eps, V2, M, p, hp, mu, sub, lr, mask, f, fp);
+    for (int it = 0; it < 100; ++it) {
+        double f, fp, s3;
+        iesh_secular(eps, V2, M, p, hp, mu, sub, lr, mask, f, fp, s3);
         fpv = fp;
         if (f == 0.0) break;
         if (f > 0.0) lo = mu; else hi = mu;
-        // Newton on phi(mu) = mu f(mu) (removes the pole at mu = 0): phi' = f + mu f' = f - mu fp
+        // Newton on phi(mu) = mu f(mu): phi' = f + mu f' = f - mu fp
         double munew = mu - mu * f / (f - mu * fp);
-        if (!(munew > lo && munew < hi)) munew = 0.5 * (lo + hi);
-        const double dm = fabs(munew - mu);
+        const bool newton = (munew > lo && munew < hi);
+        if (!newton) munew = 0.5 * (lo + hi);
+        const double step = munew - mu;
         mu = munew;
-        if (dm <= 4.5e-16 * fabs(munew)) break;
+        if (newton && fabs(step) <= 3e-8 * fabs(munew)) { fpv = fma(2.0 * s3, step, fp); break; }
+        if (hi - lo <= 4.5e-16 * fmax(fabs(lo), fabs(hi))) break;
     }
     p_out = p; mu_out = mu; fp_out = fpv;
 }
@@ -197,6 +220,7 @@ NQ_D void iesh_eigen(const KParams& p, IeshSmem& S, double h, double vnorm, bool
         int pp; double mu, fp;
         const double guess = cold ? nan("") : S.lam[root];
         iesh_root(S.eps, S.V2, M, root, h, vnorm, guess, sub, lr, mask, pp, mu, fp);
+        __syncwarp(mask);   // every lane of the group has read its warm start S.lam[root]
         if (sub == 0) {
             S.pole[root] = pp; S.mu[root] = mu; S.lam[root] = S.eps[pp] + mu;
             S.z0[root] = S.sgn[root] / sqrt(fp);
@@ -291,26 +315,328 @@ NQ_D void iesh_record_save(const KParams& p, IeshSmem& S, int64_t traj, int isav
     __syncthreads();
 }
 
+// rows-done bit mask helpers (static register indexing)
+NQ_D bool iesh_bit(const unsigned (&m)[4], int i) {
+    unsigned w = 0u;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) w = ((i >> 5) == q) ? m[q] : w;
+    return (w >> (i & 31)) & 1u;
+}
+NQ_D void iesh_set_bit(unsigned (&m)[4], int i) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) if ((i >> 5) == q) m[q] |= 1u << (i & 31);
+}
+
+// ---- FP64 tensor-core tile product -------------------------------------------------------------------
+// D(8x8) += A(8x4) B(4x8), fragments per lane T: a = A[T/4][T%4], b = B[T%4][T/4], c = C[T/4][2(T%4) + {0,1}].
+NQ_D void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// psi' = exp(-i (W - i G) dt) psi  (wavefunction_dynamics.jl:15-58) for every chunk of electrons:
+// Horner form of the Taylor polynomial of the shifted generator A = -i dts (W - sigma) - dts G,
+//     y_K+1 = psi0 ;  y_j = psi0 + (A y_j+1) / j  (j = K..1) ;  psi' = y_1 ,  psi0 = e^{-i sigma dts} psi,
+// acting on the real matrix [X | Y] (columns 2e, 2e+1 = Re, Im of electron e).  Stages j > Kg drop the G part
+// (its contribution to psi' is below 1e-18) and are purely diagonal.  One warp owns R row tiles of 8 states x NT
+// column tiles of 8 (= 4 electrons); G y is accumulated with DMMA m8n8k4, A fragments from G (column-major, leading
+// dimension = 4 mod 16: conflict-free), B fragments from the y chunk (row-major, same rule).
+template <int R, int NT>
+__device__ __noinline__ void iesh_propagate(const KParams& p, const IeshSmem& S, double* __restrict__ psi_re, double* __restrict__ psi_im,
+                         double* Gs, double* Bs, const double* Gglob, double sigma, double dts, int nsub, int K, int Kg) {
+    const IeshLayout& L = p.iesh;
+    const int n = p.n, ne = p.ne, tid = threadIdx.x, nt = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+    const int lq = lane >> 2, lr4 = lane & 3;
+    const int n4 = (n + 3) & ~3;
+    const int ecap = 4 * L.nct;                       // electrons per chunk (nct column tiles of 8 doubles)
+    const double cph = cos(sigma * dts), sph = sin(sigma * dts);
+    int mt[R];
+    bool mok[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) { mt[r] = warp + r * nwarps; mok[r] = mt[r] < L.nrt; }
+
+    for (int sub_i = 0; sub_i < nsub; ++sub_i) {
+        for (int ch = 0; ch < L.nchunks; ++ch) {
+            const int e0 = ch * ecap, e1 = min(ne, e0 + ecap);
+            const int nt_act = (e1 - e0 + 3) / 4;
+            // chunk load: psi0 = e^{-i sigma dts} psi -> global (read back at every stage) and y = psi0 -> Bs
+            for (int idx = tid; idx < ecap * n4; idx += nt) {
+                const int i = idx % n4, el = idx / n4, e = e0 + el;
+                double x = 0.0, y = 0.0;
+                if (i < n && e < e1) {
+                    const double a = psi_re[i + (int64_t)n * e], b = psi_im[i + (int64_t)n * e];
+                    x = a * cph + b * sph; y = b * cph - a * sph;
+                    psi_re[i + (int64_t)n * e] = x; psi_im[i + (int64_t)n * e] = y;
+                }
+                Bs[i * L.ldb + 2 * el] = x; Bs[i * L.ldb + 2 * el + 1] = y;
+            }
+            __syncthreads();
+            // diagonal-only stages (own elements only: no barrier between them)
+            for (int j = K; j > Kg; --j) {
+                const double ck = dts / j;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int i = 8 * mt[r] + lq;
+                    if (!mok[r] || i >= n) continue;
+                    const double wsi = S.ws[i];
+#pragma unroll
+                    for (int t = 0; t < NT; ++t) {
+                        const int e = e0 + 4 * t + lr4;
+                        if (t < nt_act && e < e1) {
+                            double2* bp = reinterpret_cast<double2*>(Bs + i * L.ldb + 8 * t + 2 * lr4);
+                            const double2 old = *bp;
+                            const double x0 = psi_re[i + (int64_t)n * e], y0 = psi_im[i + (int64_t)n * e];
+                            *bp = make_double2(fma(ck, wsi * old.y, x0), fma(ck, -wsi * old.x, y0));
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            for (int j = Kg; j >= 1; --j) {
+                const double ck = dts / j;
+                double c[R][NT][2];
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+#pragma unroll
+                    for (int t = 0; t < NT; ++t) { c[r][t][0] = 0.0; c[r][t][1] = 0.0; }
+                // ---- G y on the tensor cores ----------------------------------------------------------
+                if (L.resident) {
+                    const double* gp[R];
+#pragma unroll
+                    for (int r = 0; r < R; ++r) gp[r] = Gs + (8 * (mok[r] ? mt[r] : 0) + lq) + L.ldg * lr4;
+                    const double* bp = Bs + lr4 * L.ldb + lq;
+                    if (mok[0]) {
+#pragma unroll 2
+                        for (int k = 0; k < n4; k += 4) {
+                            double a[R];
+#pragma unroll
+                            for (int r = 0; r < R; ++r) a[r] = gp[r][(int64_t)k * L.ldg];
+#pragma unroll
+                            for (int t = 0; t < NT; ++t) {
+                                if (t < nt_act) {
+                                    const double b = bp[k * L.ldb + 8 * t];
+#pragma unroll
+                                    for (int r = 0; r < R; ++r) dmma884(c[r][t][0], c[r][t][1], a[r], b);
+                                }
+                            }
+                        }
+                    }
+                    __syncthreads();
+                } else {
+                    const int pieces = L.ldg * L.kb / 2;   // 16-byte pieces per slab
+                    for (int cc = tid; cc < pieces; cc += nt) cp_async16(Gs + 2 * cc, Gglob + 2 * cc);
+                    cp_async_commit();
+                    for (int s = 0; s < L.nslab; ++s) {
+                        if (s + 1 < L.nslab) {
+                            const double* src = Gglob + (int64_t)(s + 1) * L.ldg * L.kb;
+                            double* dst = Gs + ((s + 1) & 1) * L.ldg * L.kb;
+                            for (int cc = tid; cc < pieces; cc += nt) cp_async16(dst + 2 * cc, src + 2 * cc);
+                        }
+                        cp_async_commit();
+                        cp_async_wait<1>();
+                        __syncthreads();
+                        if (mok[0]) {
+                            const int k0 = s * L.kb, k1 = min(n4, k0 + L.kb);
+                            const double* gbase = Gs + (s & 1) * L.ldg * L.kb;
+                            const double* gp[R];
+#pragma unroll
+                            for (int r = 0; r < R; ++r) gp[r] = gbase + (8 * (mok[r] ? mt[r] : 0) + lq) + L.ldg * lr4;
+                            const double* bp = Bs + lr4 * L.ldb + lq;
+                            for (int k = k0; k < k1; k += 4) {
+                                double a[R];
+#pragma unroll
+                                for (int r = 0; r < R; ++r) a[r] = gp[r][(k - k0) * L.ldg];
+#pragma unroll
+                                for (int t = 0; t < NT; ++t) {
+                                    if (t < nt_act) {
+                                        const double b = bp[k * L.ldb + 8 * t];
+#pragma unroll
+                                        for (int r = 0; r < R; ++r) dmma884(c[r][t][0], c[r][t][1], a[r], b);
+                                    }
+                                }
+                            }
+                        }
+                        __syncthreads();
+                    }
+                }
+                // ---- y_j = psi0 + ck ( (ws Y - G X) + i (-ws X - G Y) ), in place ---------------------------
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int i = 8 * mt[r] + lq;
+                    if (!mok[r] || i >= n) continue;
+                    const double wsi = S.ws[i];
+#pragma unroll
+                    for (int t = 0; t < NT; ++t) {
+                        const int e = e0 + 4 * t + lr4;
+                        if (t < nt_act && e < e1) {
+                            double2* bp2 = reinterpret_cast<double2*>(Bs + i * L.ldb + 8 * t + 2 * lr4);
+                            const double2 old = *bp2;
+                            const double x0 = psi_re[i + (int64_t)n * e], y0 = psi_im[i + (int64_t)n * e];
+                            *bp2 = make_double2(fma(ck, wsi * old.y - c[r][t][0], x0), fma(ck, -wsi * old.x - c[r][t][1], y0));
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+            // y_1 = psi' of this chunk: every thread stores the elements it owns
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int i = 8 * mt[r] + lq;
+                if (!mok[r] || i >= n) continue;
+#pragma unroll
+                for (int t = 0; t < NT; ++t) {
+                    const int e = e0 + 4 * t + lr4;
+                    if (t < nt_act && e < e1) {
+                        const double2 y = *reinterpret_cast<const double2*>(Bs + i * L.ldb + 8 * t + 2 * lr4);
+                        psi_re[i + (int64_t)n * e] = y.x; psi_im[i + (int64_t)n * e] = y.y;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// det S for S[j][i] = psi[occ_j, i] (iesh.jl:309-316; FastDeterminant.det!, FastDeterminant.jl:20-22): LU with
+// partial (row) pivoting on a 16 x (threads/16) thread grid with cyclic distribution.  Each thread owns RL x CL
+// elements, held in REGISTERS (REG = true, ne <= 52) or in its own shared-memory slots (REG = false); the pivot
+// column and pivot row travel through shared memory (double buffered: two barriers per column).  Rows are never
+// swapped (implicit pivoting); the permutation sign is accumulated from the rank of each pivot among the
+// remaining rows.   buf: 8 * roundup(ne, 4) doubles ; store (REG = false): 2 * RL * CL * blockDim doubles.
+template <int RL, int CL, bool REG>
+__device__ __noinline__ void iesh_det_lu(const KParams& p, const IeshSmem& S, const double* __restrict__ psi_re,
+                      const double* __restrict__ psi_im, double* buf, double* store, double& det_re, double& det_im) {
+    const int n = p.n, ne = p.ne, tid = threadIdx.x, nt = blockDim.x;
+    const int PC = nt >> 4;
+    const int tr = tid & 15, tc = tid >> 4, lane = tid & 31;
+    double are[REG ? RL : 1][REG ? CL : 1], aim[REG ? RL : 1][REG ? CL : 1];
+    double* sre = store + tid;
+    double* sim = store + (int64_t)RL * CL * nt + tid;
+    auto slot = [&](int a, int b) { return (a * CL + b) * nt; };
+#pragma unroll
+    for (int a = 0; a < RL; ++a)
+#pragma unroll
+        for (int b = 0; b < CL; ++b) {
+            const int i = tr + 16 * a, j = tc + PC * b;
+            const bool ok = (i < ne && j < ne);
+            const double vr = ok ? psi_re[S.occ[i] + (int64_t)n * j] : 0.0;
+            const double vi = ok ? psi_im[S.occ[i] + (int64_t)n * j] : 0.0;
+            if (REG) { are[a][b] = vr; aim[a][b] = vi; } else { sre[slot(a, b)] = vr; sim[slot(a, b)] = vi; }
+        }
+    const int nep = (ne + 3) & ~3;
+    double* cb_re = buf; double* cb_im = buf + 2 * nep; double* rb_re = buf + 4 * nep; double* rb_im = buf + 6 * nep;
+    unsigned done[4] = {0u, 0u, 0u, 0u};
+    double dr = 1.0, di = 0.0;
+    for (int k = 0; k < ne; ++k) {
+        const int par = (k & 1) * nep;
+        if (tc == k % PC) {
+            const int bk = k / PC;
+#pragma unroll
+            for (int a = 0; a < RL; ++a) {
+                const int i = tr + 16 * a;
+                if (i < ne) {
+                    double vr = 0.0, vi = 0.0;
+                    if (REG) {
+#pragma unroll
+                        for (int b = 0; b < CL; ++b) if (b == bk) { vr = are[a][b]; vi = aim[a][b]; }
+                    } else { vr = sre[slot(a, bk)]; vi = sim[slot(a, bk)]; }
+                    cb_re[par + i] = vr; cb_im[par + i] = vi;
+                }
+            }
+        }
+        __syncthreads();
+        // pivot: largest |S[i][k]| among the rows not used yet (ties: smallest i), found redundantly by every warp
+        double best = -1.0; int bi = 0;
+        for (int i = lane; i < ne; i += 32) {
+            const bool dn = iesh_bit(done, i);
+            const double m2 = cb_re[par + i] * cb_re[par + i] + cb_im[par + i] * cb_im[par + i];
+            if (!dn && m2 > best) { best = m2; bi = i; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        const int pr = bi;
+        if (tr == (pr & 15)) {
+            const int ap = pr >> 4;
+#pragma unroll
+            for (int b = 0; b < CL; ++b) {
+                const int j = tc + PC * b;
+                if (j < ne) {
+                    double vr = 0.0, vi = 0.0;
+                    if (REG) {
+#pragma unroll
+                        for (int a = 0; a < RL; ++a) if (a == ap) { vr = are[a][b]; vi = aim[a][b]; }
+                    } else { vr = sre[slot(ap, b)]; vi = sim[slot(ap, b)]; }
+                    rb_re[par + j] = vr; rb_im[par + j] = vi;
+                }
+            }
+        }
+        __syncthreads();
+        const double pre = cb_re[par + pr], pim = cb_im[par + pr];
+        const double pm2 = pre * pre + pim * pim;
+        const double ire = pre / pm2, iim = -pim / pm2;
+        int rank = 0;   // rank of pr among the remaining rows -> sign of the permutation
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const unsigned remaining = ~done[w];
+            if (32 * w + 31 < pr) rank += __popc(remaining);
+            else if (32 * w <= pr) rank += __popc(remaining & ((1u << (pr & 31)) - 1u));
+        }
+        {
+            const double nr = dr * pre - di * pim, ni = dr * pim + di * pre;
+            dr = (rank & 1) ? -nr : nr; di = (rank & 1) ? -ni : ni;
+        }
+        iesh_set_bit(done, pr);
+#pragma unroll
+        for (int a = 0; a < RL; ++a) {
+            const int i = tr + 16 * a;
+            const bool dn = iesh_bit(done, i);     // includes pr itself
+            if (i < ne && !dn) {
+                const double cr = cb_re[par + i], ci = cb_im[par + i];
+                const double lre = cr * ire - ci * iim, lim = cr * iim + ci * ire;
+#pragma unroll
+                for (int b = 0; b < CL; ++b) {
+                    const int j = tc + PC * b;
+                    if (j > k && j < ne) {
+                        const double ur = rb_re[par + j], ui = rb_im[par + j];
+                        if (REG) {
+                            are[a][b] -= lre * ur - lim * ui;
+                            aim[a][b] -= lre * ui + lim * ur;
+                        } else {
+                            sre[slot(a, b)] -= lre * ur - lim * ui;
+                            sim[slot(a, b)] -= lre * ui + lim * ur;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    det_re = dr; det_im = di;
+}
+
 // ---- the step kernel -----------------------------------------------------------------------------
-__global__ void __launch_bounds__(384, 1) iesh_step_kernel(const __grid_constant__ KParams p) {
+__global__ void __launch_bounds__(416, 1) iesh_step_kernel(const __grid_constant__ KParams p) {
     extern __shared__ __align__(16) double iesh_sm[];
     IeshSmem S;
     S.carve(iesh_sm, p.n);
     const IeshLayout& L = p.iesh;
-    const int n = p.n, ne = p.ne, M = n - 1, tid = threadIdx.x, nt = blockDim.x;
+    const int n = p.n, ne = p.ne, tid = threadIdx.x, nt = blockDim.x;
     const int nun = n - ne;
     const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+    const int n4 = (n + 3) & ~3;
     const double dt = p.dt, hdt = 0.5 * p.dt;
     const IeshModel mdl{p.params[0] * p.params[1] * p.params[1], p.params[2], p.params[3], p.masses[0]};
     const double vnorm = iesh_load_bath(p, S);
 
-    // work-region pointers
-    double* Gs = S.work;                                   // resident: ldg*ldg ; streaming: 2 slabs of ldg*kb
-    double* Bs = S.work + L.off_b;                         // psi chunk, row-major [ldg][ldb]
+    double* Gs = S.work;                                   // resident: ldg x n4 ; streaming: 2 slabs of ldg x kb
+    double* Bs = S.work + L.off_b;                         // y chunk, row-major [n4][ldb]
     double* Hs = S.work + L.off_hop;                       // hop phase
     double* Gglob = L.resident ? nullptr : p.iesh_G + (int64_t)blockIdx.x * L.ldg * L.kb * L.nslab;
-    // GEMM tile of this thread
-    const int ti = tid % L.nrt, tj = tid / L.nrt;
+    if (L.resident) for (int idx = tid; idx < L.ldg * n4; idx += nt) Gs[idx] = 0.0;
     unsigned long long nhops = 0, nfrus = 0, nunpruned = 0;
 
     for (int64_t traj = blockIdx.x; traj < p.ntraj; traj += gridDim.x) {
@@ -321,7 +647,6 @@ __global__ void __launch_bounds__(384, 1) iesh_step_kernel(const __grid_constant
         for (int e = tid; e < ne; e += nt) S.occ[e] = p.state[traj * ne + e];
         iesh_refresh_unoccupied(p, S);
         double r = p.r[traj], v = p.v[traj], acc = p.acc[traj];
-        bool have_eigen = false;   // z0 / pole / mu valid for the current r
 
 #pragma unroll 1
         for (int is = 0; is < p.nsteps; ++is) {
@@ -332,7 +657,6 @@ __global__ void __launch_bounds__(384, 1) iesh_step_kernel(const __grid_constant
             double h, dh, u0, du0;
             mdl.eval(r, h, dh, u0, du0);
             iesh_eigen(p, S, h, vnorm, false);
-            have_eigen = true;
             {
                 double part = 0.0;
                 for (int e = tid; e < ne; e += nt) { const double z = S.z0[S.occ[e]]; part += z * z; }
@@ -349,143 +673,41 @@ __global__ void __launch_bounds__(384, 1) iesh_step_kernel(const __grid_constant
             double g2 = 0.0, sabs = 0.0;
             {
                 double* Gdst = L.resident ? Gs : Gglob;
-                for (int idx = tid; idx < n * n; idx += nt) {
-                    const int i = idx % n, j = idx / n;
-                    double g = 0.0;
-                    if (i != j) {
-                        g = gpref * S.z0[i] * S.z0[j] / iesh_wdiff(S, i, j);
-                        if (S.flag[i] < 0 && S.flag[j] >= 0) sabs += fabs(g);    // |v_dot_d[m, e]|, iesh.jl:285-298
+                // thread -> (row i fastest); one division per element, w_i - w_j from pole offsets
+                for (int j = warp; j < n; j += nwarps) {
+                    const double zj = S.z0[j] * gpref, ej = S.eps[S.pole[j]], mj = S.mu[j];
+                    const bool occ_j = S.flag[j] >= 0;
+                    for (int i = lane; i < n; i += 32) {
+                        double g = 0.0;
+                        if (i != j) {
+                            g = zj * S.z0[i] / ((S.eps[S.pole[i]] - ej) + (S.mu[i] - mj));
+                            if (occ_j && S.flag[i] < 0) sabs += fabs(g);         // |v_dot_d[m, e]|, iesh.jl:285-298
+                        }
+                        g2 = fma(g, g, g2);
+                        Gdst[i + (int64_t)L.ldg * j] = g;
                     }
-                    g2 = fma(g, g, g2);
-                    Gdst[i + (int64_t)L.ldg * j] = g;
                 }
             }
             const double gnorm = sqrt(iesh_block_sum(g2, S.red));
             sabs = iesh_block_sum(sabs, S.red);
             const double wspan = 0.5 * (wmax - wmin);
-            // Taylor plan: nsub sub-steps of dt/nsub, K terms each, remainder < 1e-17
+            // Taylor plan: nsub sub-steps of dt/nsub; K stages (remainder < 1e-17), the first Kg of them with G
             const double rho_full = dt * (wspan + gnorm);
             const int nsub = max(1, (int)ceil(rho_full / 4.0));
-            const double dts = dt / nsub, rho = rho_full / nsub;
-            int K = 1;
+            const double dts = dt / nsub, rho = rho_full / nsub, rho_g = dts * gnorm;
+            int K = 1, Kg = (rho_g >= 1e-18) ? 1 : 0;
             {
-                double term = rho;
-                while (term > 1e-17 && K < 80) { ++K; term *= rho / K; }
-            }
-            if (!L.resident) { __threadfence_block(); }
-            __syncthreads();
-
-            // ---- psi' = exp(-i (W - i G) dt) psi  (wavefunction_dynamics.jl:15-58) -----------------
-            const double cph = cos(sigma * dts), sph = sin(sigma * dts);
-            const int ecap = 2 * L.nct;
-            for (int sub_i = 0; sub_i < nsub; ++sub_i) {
-                for (int ch = 0; ch < L.nchunks; ++ch) {
-                    const int e0 = ch * ecap, e1 = min(ne, e0 + ecap);
-                    const int nct_act = (e1 - e0 + 1) / 2;
-                    // load chunk: B[i][2 el] = Re, B[i][2 el + 1] = Im of e^{-i sigma dts} psi ; term 0 of the sum
-                    for (int idx = tid; idx < ecap * L.ldg; idx += nt) {
-                        const int i = idx % L.ldg, el = idx / L.ldg, e = e0 + el;
-                        double x = 0.0, y = 0.0;
-                        if (i < n && e < e1) {
-                            const double a = psi_re[i + (int64_t)n * e], b = psi_im[i + (int64_t)n * e];
-                            x = a * cph + b * sph; y = b * cph - a * sph;
-                            psi_re[i + (int64_t)n * e] = x; psi_im[i + (int64_t)n * e] = y;
-                        }
-                        Bs[i * L.ldb + 2 * el] = x; Bs[i * L.ldb + 2 * el + 1] = y;
-                    }
-                    __syncthreads();
-                    const bool active = (tj < nct_act);
-                    for (int term = 1; term <= K; ++term) {
-                        const double ck = dts / term;
-                        double a[8][4];
-#pragma unroll
-                        for (int q = 0; q < 8; ++q)
-#pragma unroll
-                            for (int c = 0; c < 4; ++c) a[q][c] = 0.0;
-                        if (L.resident) {
-                            if (active) {
-                                const double2* gp = reinterpret_cast<const double2*>(Gs) + ti;
-                                const double2* bp = reinterpret_cast<const double2*>(Bs) + 2 * tj;
-                                const int gstride = L.ldg / 2, bstride = L.ldb / 2, nrt = L.nrt;
-#pragma unroll 2
-                                for (int k = 0; k < n; ++k) {
-                                    const double2 g0 = gp[0], g1 = gp[nrt], g2v = gp[2 * nrt], g3 = gp[3 * nrt];
-                                    const double2 b0 = bp[0], b1 = bp[1];
-                                    const double gv[8] = {g0.x, g0.y, g1.x, g1.y, g2v.x, g2v.y, g3.x, g3.y};
-                                    const double bv[4] = {b0.x, b0.y, b1.x, b1.y};
-#pragma unroll
-                                    for (int q = 0; q < 8; ++q)
-#pragma unroll
-                                        for (int c = 0; c < 4; ++c) a[q][c] = fma(gv[q], bv[c], a[q][c]);
-                                    gp += gstride; bp += bstride;
-                                }
-                            }
-                            __syncthreads();
-                        } else {
-                            const int chunks16 = L.ldg * L.kb / 2;   // 16-byte pieces per slab
-                            {
-                                const double* src = Gglob;
-                                for (int c = tid; c < chunks16; c += nt) cp_async16(Gs + 2 * c, src + 2 * c);
-                                cp_async_commit();
-                            }
-                            for (int s = 0; s < L.nslab; ++s) {
-                                if (s + 1 < L.nslab) {
-                                    const double* src = Gglob + (int64_t)(s + 1) * L.ldg * L.kb;
-                                    double* dst = Gs + ((s + 1) & 1) * L.ldg * L.kb;
-                                    for (int c = tid; c < chunks16; c += nt) cp_async16(dst + 2 * c, src + 2 * c);
-                                }
-                                cp_async_commit();
-                                cp_async_wait<1>();
-                                __syncthreads();
-                                if (active) {
-                                    const int k0 = s * L.kb, k1 = min(n, k0 + L.kb);
-                                    const double2* gp = reinterpret_cast<const double2*>(Gs + (s & 1) * L.ldg * L.kb) + ti;
-                                    const double2* bp = reinterpret_cast<const double2*>(Bs + (int64_t)k0 * L.ldb) + 2 * tj;
-                                    const int gstride = L.ldg / 2, bstride = L.ldb / 2, nrt = L.nrt;
-#pragma unroll 2
-                                    for (int k = k0; k < k1; ++k) {
-                                        const double2 g0 = gp[0], g1 = gp[nrt], g2v = gp[2 * nrt], g3 = gp[3 * nrt];
-                                        const double2 b0 = bp[0], b1 = bp[1];
-                                        const double gv[8] = {g0.x, g0.y, g1.x, g1.y, g2v.x, g2v.y, g3.x, g3.y};
-                                        const double bv[4] = {b0.x, b0.y, b1.x, b1.y};
-#pragma unroll
-                                        for (int q = 0; q < 8; ++q)
-#pragma unroll
-                                            for (int c = 0; c < 4; ++c) a[q][c] = fma(gv[q], bv[c], a[q][c]);
-                                        gp += gstride; bp += bstride;
-                                    }
-                                }
-                                __syncthreads();
-                            }
-                        }
-                        // epilogue: T_{k+1} = ck ( (ws Y - G X) + i (-ws X - G Y) ), in place, and psi += T_{k+1}
-                        if (active) {
-#pragma unroll
-                            for (int q = 0; q < 8; ++q) {
-                                const int i = (q >> 1) * (2 * L.nrt) + 2 * ti + (q & 1);
-                                if (i < n) {
-                                    const double wsi = S.ws[i];
-                                    double2* brow = reinterpret_cast<double2*>(Bs + i * L.ldb + 4 * tj);
-#pragma unroll
-                                    for (int pp = 0; pp < 2; ++pp) {
-                                        const double2 old = brow[pp];
-                                        const double xn = ck * (wsi * old.y - a[q][2 * pp]);
-                                        const double yn = ck * (-wsi * old.x - a[q][2 * pp + 1]);
-                                        brow[pp] = make_double2(xn, yn);
-                                        const int e = e0 + 2 * tj + pp;
-                                        if (e < e1) {
-                                            psi_re[i + (int64_t)n * e] += xn;
-                                            psi_im[i + (int64_t)n * e] += yn;
-                                        }
-                                    }
-                                }
-                            }
-                        }
-                        __syncthreads();
-                    }
+                double term = rho;                       // rho^K / K!
+                while (term > 1e-17 && K < 90) {
+                    ++K;
+                    if (rho_g * term / K >= 1e-18) Kg = K;   // stage K contributes rho_g rho^(K-1) / K!
+                    term *= rho / K;
                 }
             }
-            __threadfence_block();
+            __syncthreads();
+
+            if (L.rounds == 1) iesh_propagate<1, 16>(p, S, psi_re, psi_im, Gs, Bs, Gglob, sigma, dts, nsub, K, Kg);
+            else iesh_propagate<2, 8>(p, S, psi_re, psi_im, Gs, Bs, Gglob, sigma, dts, nsub, K, Kg);
             __syncthreads();
 
             // ---- IESHCallback: hop test (iesh.jl:231-335,390-407) ----------------------------------
@@ -493,71 +715,10 @@ __global__ void __launch_bounds__(384, 1) iesh_step_kernel(const __grid_constant
                 const double xi = (p.rng == NQCB200_RNG_INJECTED)
                                       ? p.draws[(step - p.draws_step0) * p.ntraj + traj]
                                       : philox_uniform(p.seed, (uint64_t)(p.traj_offset + traj), (uint64_t)step, 0u);
-                const int lds = L.lds;
-                double* Sre = Hs; double* Sim = Sre + ne * lds;
-                double* rk_re = Sim + ne * lds; double* rk_im = rk_re + ne;
-                double* ro_re = rk_im + ne; double* ro_im = ro_re + ne;
-                double* ck_re = ro_im + ne; double* ck_im = ck_re + ne;
-                double* sum_e = ck_im + ne; double* probs = sum_e + ne;
-                int* perm = (int*)(probs + n); int* srcc = perm + ne;
-                // overlap S[j][i] = psi[occ_j, i]   (iesh.jl:309-316)
-                for (int idx = tid; idx < ne * ne; idx += nt) {
-                    const int j = idx % ne, i = idx / ne;
-                    Sre[j * lds + i] = psi_re[S.occ[j] + (int64_t)n * i];
-                    Sim[j * lds + i] = psi_im[S.occ[j] + (int64_t)n * i];
-                }
-                __syncthreads();
-                // in-place Gauss-Jordan inversion with row pivoting; det = product of pivots
-                double det_re = 1.0, det_im = 0.0;
-                for (int k = 0; k < ne; ++k) {
-                    if (warp == 0) {
-                        double best = -1.0; int bi = k;
-                        for (int i = k + lane; i < ne; i += 32) {
-                            const double m2 = Sre[i * lds + k] * Sre[i * lds + k] + Sim[i * lds + k] * Sim[i * lds + k];
-                            if (m2 > best) { best = m2; bi = i; }
-                        }
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) {
-                            const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-                            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-                        }
-                        if (lane == 0) S.ctl[0] = bi;
-                    }
-                    __syncthreads();
-                    const int pr = S.ctl[0];
-                    const double pre = Sre[pr * lds + k], pim = Sim[pr * lds + k];
-                    const double pm2 = pre * pre + pim * pim;
-                    const double ire = pre / pm2, iim = -pim / pm2;              // 1 / pivot
-                    for (int j = tid; j < ne; j += nt) {
-                        const double xr = Sre[pr * lds + j], xi_ = Sim[pr * lds + j];
-                        rk_re[j] = (j == k) ? ire : xr * ire - xi_ * iim;
-                        rk_im[j] = (j == k) ? iim : xr * iim + xi_ * ire;
-                        ro_re[j] = Sre[k * lds + j]; ro_im[j] = Sim[k * lds + j];
-                        ck_re[j] = Sre[j * lds + k]; ck_im[j] = Sim[j * lds + k];
-                    }
-                    __syncthreads();
-                    for (int idx = tid; idx < ne * ne; idx += nt) {
-                        const int i = idx / ne, j = idx % ne;
-                        double nr, ni;
-                        if (i == k) { nr = rk_re[j]; ni = rk_im[j]; }
-                        else {
-                            const bool sw = (i == pr);
-                            const double cr = sw ? ro_re[k] : ck_re[i], ci = sw ? ro_im[k] : ck_im[i];
-                            double br = sw ? ro_re[j] : Sre[i * lds + j], bi_ = sw ? ro_im[j] : Sim[i * lds + j];
-                            if (j == k) { br = 0.0; bi_ = 0.0; }
-                            nr = br - (cr * rk_re[j] - ci * rk_im[j]);
-                            ni = bi_ - (cr * rk_im[j] + ci * rk_re[j]);
-                        }
-                        Sre[i * lds + j] = nr; Sim[i * lds + j] = ni;
-                    }
-                    if (tid == 0) perm[k] = pr;
-                    {
-                        const double dr = det_re * pre - det_im * pim, di = det_re * pim + det_im * pre;
-                        det_re = (pr != k) ? -dr : dr; det_im = (pr != k) ? -di : di;
-                    }
-                    __syncthreads();
-                }
+                double det_re, det_im;
+                const int nep8 = 8 * ((ne + 3) & ~3);
+                if (ne <= 16 * 4 && ne <= (nt >> 4) * 2) iesh_det_lu<4, 2, true>(p, S, psi_re, psi_im, Hs, Hs + nep8, det_re, det_im);
+                else iesh_det_lu<7, 4, false>(p, S, psi_re, psi_im, Hs, Hs + nep8, det_re, det_im);
                 const double Akk = det_re * det_re + det_im * det_im;
                 const double prefactor = 2.0 * dt / Akk;
                 bool pruned = false;
@@ -565,8 +726,70 @@ __global__ void __launch_bounds__(384, 1) iesh_step_kernel(const __grid_constant
                     const double estimate = prefactor * sabs * (fabs(det_re) + fabs(det_im));
                     pruned = estimate < xi;
                 }
+                __syncthreads();
                 if (!pruned) {
                     nunpruned += (tid == 0);
+                    // rare path: all ne (n - ne) probabilities from S^-1 (matrix-determinant lemma):
+                    //   det S_{e->m} / det S = (psi_m . S^-1)_e ;  g = 2 dt Re(.) v_dot_d[m, e]
+                    const int lds = L.lds;
+                    double* Sre = Hs; double* Sim = Sre + ne * lds;
+                    double* rk_re = Sim + ne * lds; double* rk_im = rk_re + ne;
+                    double* ro_re = rk_im + ne; double* ro_im = ro_re + ne;
+                    double* ck_re = ro_im + ne; double* ck_im = ck_re + ne;
+                    double* sum_e = ck_im + ne; double* probs = sum_e + ne;
+                    int* perm = (int*)(probs + n); int* srcc = perm + ne;
+                    for (int idx = tid; idx < ne * ne; idx += nt) {
+                        const int j = idx % ne, i = idx / ne;
+                        Sre[j * lds + i] = psi_re[S.occ[j] + (int64_t)n * i];
+                        Sim[j * lds + i] = psi_im[S.occ[j] + (int64_t)n * i];
+                    }
+                    __syncthreads();
+                    // in-place Gauss-Jordan inversion with row pivoting
+                    for (int k = 0; k < ne; ++k) {
+                        if (warp == 0) {
+                            double best = -1.0; int bi = k;
+                            for (int i = k + lane; i < ne; i += 32) {
+                                const double m2 = Sre[i * lds + k] * Sre[i * lds + k] + Sim[i * lds + k] * Sim[i * lds + k];
+                                if (m2 > best) { best = m2; bi = i; }
+                            }
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1) {
+                                const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+                                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                                if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+                            }
+                            if (lane == 0) S.ctl[0] = bi;
+                        }
+                        __syncthreads();
+                        const int pr = S.ctl[0];
+                        const double pre = Sre[pr * lds + k], pim = Sim[pr * lds + k];
+                        const double pm2 = pre * pre + pim * pim;
+                        const double ire = pre / pm2, iim = -pim / pm2;          // 1 / pivot
+                        for (int j = tid; j < ne; j += nt) {
+                            const double xr = Sre[pr * lds + j], xi_ = Sim[pr * lds + j];
+                            rk_re[j] = (j == k) ? ire : xr * ire - xi_ * iim;
+                            rk_im[j] = (j == k) ? iim : xr * iim + xi_ * ire;
+                            ro_re[j] = Sre[k * lds + j]; ro_im[j] = Sim[k * lds + j];
+                            ck_re[j] = Sre[j * lds + k]; ck_im[j] = Sim[j * lds + k];
+                        }
+                        __syncthreads();
+                        for (int idx = tid; idx < ne * ne; idx += nt) {
+                            const int i = idx / ne, j = idx % ne;
+                            double nr, ni;
+                            if (i == k) { nr = rk_re[j]; ni = rk_im[j]; }
+                            else {
+                                const bool sw = (i == pr);
+                                const double cr = sw ? ro_re[k] : ck_re[i], ci = sw ? ro_im[k] : ck_im[i];
+                                double br = sw ? ro_re[j] : Sre[i * lds + j], bi_ = sw ? ro_im[j] : Sim[i * lds + j];
+                                if (j == k) { br = 0.0; bi_ = 0.0; }
+                                nr = br - (cr * rk_re[j] - ci * rk_im[j]);
+                                ni = bi_ - (cr * rk_im[j] + ci * rk_re[j]);
+                            }
+                            Sre[i * lds + j] = nr; Sim[i * lds + j] = ni;
+                        }
+                        if (tid == 0) perm[k] = pr;
+                        __syncthreads();
+                    }
                     if (tid == 0) {
                         for (int j = 0; j < ne; ++j) srcc[j] = j;
                         for (int k = ne - 1; k >= 0; --k) { const int t = srcc[k]; srcc[k] = srcc[perm[k]]; srcc[perm[k]] = t; }
@@ -574,7 +797,6 @@ __global__ void __launch_bounds__(384, 1) iesh_step_kernel(const __grid_constant
                     }
                     __syncthreads();
                     const double* Gsrc = L.resident ? Gs : Gglob;
-                    // g[m,e] = clamp(2 dt Re((psi_m . S^-1)_e) * (-G[m, occ_e]), 0, 1)
                     auto prob_of = [&](int m, int e) -> double {
                         const int ce = srcc[e];
                         double rr = 0.0;
@@ -597,7 +819,6 @@ __global__ void __launch_bounds__(384, 1) iesh_step_kernel(const __grid_constant
                     double cum = 0.0;
                     int e_scan = 0;
                     while (true) {
-                        // first electron whose block can contain the crossing (uniform: sum_e is in shared memory)
                         while (e_scan < ne && !(xi < cum + sum_e[e_scan] * (1.0 + 1e-12) + 1e-300)) { cum += sum_e[e_scan]; ++e_scan; }
                         if (e_scan >= ne) break;
                         for (int u = tid; u < nun; u += nt) probs[u] = prob_of(S.un[u], e_scan);
@@ -674,7 +895,6 @@ __global__ void __launch_bounds__(384, 1) iesh_step_kernel(const __grid_constant
                         psi_re[oc + (int64_t)n * e] = a * sc; psi_im[oc + (int64_t)n * e] = b * sc;
                     }
                 }
-                __threadfence_block();
                 __syncthreads();
             }
 
@@ -684,7 +904,6 @@ __global__ void __launch_bounds__(384, 1) iesh_step_kernel(const __grid_constant
                 if (isave < p.nsave) iesh_record_save(p, S, traj, (int)isave, r, v, mdl, psi_re, psi_im);
             }
         }
-        (void)have_eigen;
         __syncthreads();
         for (int i = tid; i < n; i += nt) p.iesh_lam[traj * n + i] = S.lam[i];
         for (int e = tid; e < ne; e += nt) p.state[traj * ne + e] = S.occ[e];
@@ -711,7 +930,7 @@ __global__ void __launch_bounds__(384, 1) iesh_step_kernel(const __grid_constant
 // Initialisation: update_cache!(r0) with a cold root search, gauge signs against the identity
 // (or a user reference Z through p.Zprev, [T][n*n] trajectory-major), initial acceleration
 // (verlet_with_electronics.jl:30-40), save point 0.
-__global__ void __launch_bounds__(384, 1) iesh_init_kernel(const __grid_constant__ KParams p, int user_gauge, int,
+__global__ void __launch_bounds__(416, 1) iesh_init_kernel(const __grid_constant__ KParams p, int user_gauge, int,
                                                           const double*) {
     extern __shared__ __align__(16) double iesh_sm[];
     IeshSmem S;

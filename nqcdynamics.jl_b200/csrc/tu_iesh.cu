@@ -5,46 +5,56 @@ namespace nq {
 namespace {
 
 // Tile / shared-memory plan for (n states, ne electrons); false when nothing fits.
+int pad16_4(int x) { int y = x; while (y % 16 != 4) ++y; return y; }
+
 bool iesh_plan(int n, int ne, size_t smem_max, IeshLayout& L) {
     L = IeshLayout{};
-    L.threads = 384;
+    L.threads = 416;
+    const int nwarps = L.threads / 32;
     L.nrt = (n + 7) / 8;
-    L.ldg = 8 * L.nrt;
-    if (L.nrt > L.threads) return false;
-    const int nct_need = (ne + 1) / 2;
-    const int nct_cap = L.threads / L.nrt;
+    L.rounds = (L.nrt + nwarps - 1) / nwarps;
+    if (L.rounds > 2) return false;
+    L.ldg = pad16_4(8 * L.nrt);
+    const int n4 = (n + 3) & ~3;
+    const int nt_need = (ne + 3) / 4;                 // column tiles for all electrons
+    const int nt_max = (L.rounds == 1) ? 16 : 8;     // accumulator tiles per warp (register budget)
     L.lds = ne | 1;
+    const int nep = (ne + 3) & ~3;
     const long small = iesh_small_doubles(n);
-    const long hop = 2L * ne * L.lds + 7L * ne + n + (2 * ne + 1) / 2 + 4;
+    // hop phase: Gauss-Jordan fallback (S, S^-1 work vectors) or the LU buffers (+ per-thread element slots when ne > 52)
+    const long lu = 8L * nep + (ne > 52 ? 2L * 7 * 4 * L.threads : 0L);
+    const long hop = std::max(2L * ne * L.lds + 7L * ne + n + (2 * ne + 1) / 2 + 4, lu);
     int lr = 1;
     while (lr < 32 && (long)n * lr * 2 <= L.threads) lr *= 2;
     L.lr = lr;
     // (a) G resident in shared memory
     {
-        const int nct = std::min(nct_need, nct_cap);
-        const long B = (long)L.ldg * 4 * nct;
-        const long work = (long)L.ldg * L.ldg + std::max(B, hop);
+        const int nct = std::min(nt_need, nt_max);
+        const int ldb = pad16_4(8 * nct);
+        const long work = (long)L.ldg * n4 + std::max((long)n4 * ldb, hop);
         if ((size_t)(small + work) * 8 <= smem_max) {
-            L.resident = 1; L.nct = nct; L.ldb = 4 * nct; L.kb = L.ldg; L.nslab = 1;
-            L.off_b = L.ldg * L.ldg; L.off_hop = L.off_b; L.work_doubles = (int)work;
+            L.resident = 1; L.nct = nct; L.ldb = ldb; L.kb = n4; L.nslab = 1;
+            L.off_b = L.ldg * n4; L.off_hop = L.off_b; L.work_doubles = (int)work;
         }
     }
     // (b) G streamed from global memory (L2) in slabs of kb columns, double buffered
     if (!L.resident) {
         L.kb = 16;
-        L.nslab = (n + L.kb - 1) / L.kb;
+        L.nslab = (n4 + L.kb - 1) / L.kb;
         const long slabs = 2L * L.ldg * L.kb;
-        int nct = std::min(nct_need, nct_cap);
+        int nct = std::min(nt_need, nt_max);
         while (nct >= 1) {
-            const long work = std::max(slabs + (long)L.ldg * 4 * nct, hop);
+            const long work = std::max(slabs + (long)n4 * pad16_4(8 * nct), hop);
             if ((size_t)(small + work) * 8 <= smem_max) break;
             --nct;
         }
         if (nct < 1) return false;
-        L.nct = nct; L.ldb = 4 * nct; L.off_b = (int)slabs; L.off_hop = 0;
-        L.work_doubles = (int)std::max(slabs + (long)L.ldg * 4 * nct, hop);
+        L.nct = nct; L.ldb = pad16_4(8 * nct); L.off_b = (int)slabs; L.off_hop = 0;
+        L.work_doubles = (int)std::max(slabs + (long)n4 * L.ldb, hop);
     }
-    L.nchunks = (nct_need + L.nct - 1) / L.nct;
+    L.nchunks = (nt_need + L.nct - 1) / L.nct;
+    L.nct = (nt_need + L.nchunks - 1) / L.nchunks;      // balance the chunks
+    L.ldb = pad16_4(8 * L.nct);
     L.smem_bytes = (int)((small + L.work_doubles) * 8);
     return true;
 }
@@ -57,6 +67,7 @@ bool select_iesh(const nqcb200_config& c, KernelSet& out, std::string& why) {
     }
     if (c.ndofs != 1 || c.nbeads != 1) { why = "AdiabaticIESH kernel: ndofs == 1 and nbeads == 1"; return false; }
     const int n = c.nstates, ne = c.nelectrons;
+    if (ne > 104) { why = "AdiabaticIESH kernel: at most 104 electrons"; return false; }
     if (n < 3 || ne < 1 || ne >= n) { why = "AdiabaticIESH needs nstates >= 3 and 1 <= nelectrons < nstates"; return false; }
     if (c.nbath != n - 1 || !c.bath_a || !c.bath_b) { why = "AndersonHolstein needs nstates-1 bath energies and couplings"; return false; }
     for (int k = 0; k < n - 1; ++k) {

@@ -38,6 +38,19 @@ def rpsh_flops(n: int, D: int, B: int, f_model: float) -> float:
     return (B + 1) * (f_model + E + (4 * n ** 3 + n * n) * D) + 8 * B * B * D + 14 * B * D + 496 * n ** 3 + 730 * n * n
 
 
+def iesh_flops(n: int, ne: int, D: int = 1) -> float:
+    """SURVEY.md 8d, IESH base step (no unpruned hop search): F_model + 9n^3 + 4n^3 D + n^2 D + [36n^3 + 8n^3 + 6n^2]
+    + 8 n^2 ne + (8/3) ne^3 + 2 ne (n - ne) D -- the reference's dense formulation (real symmetric eigen, two
+    similarity products, complex Hermitian eigen of H_eff, U = V e^{-i lambda dt} V', psi' = U psi, one complex LU)."""
+    return 4.0 * n + 9.0 * n ** 3 + 4.0 * n ** 3 * D + n * n * D + 44.0 * n ** 3 + 6.0 * n * n + 8.0 * n * n * ne \
+        + (8.0 / 3.0) * ne ** 3 + 2.0 * ne * (n - ne) * D
+
+
+def iesh_hop_search_flops(n: int, ne: int) -> float:
+    """Extra flops of a step whose hop search is not pruned: ne (n - ne) complex LUs of size ne (iesh.jl:256-266)."""
+    return ne * (n - ne) * (8.0 / 3.0) * ne ** 3
+
+
 @dataclass
 class Workload:
     name: str
@@ -70,6 +83,29 @@ class Workload:
                   nelectrons=self.model.nelectrons)
         kw.update(extra)
         return kw
+
+    def upload(self, h, ic, rho=None) -> int:
+        """Hand one batch of initial DynamicsVariables to an engine / oracle handle; returns the bytes uploaded."""
+        T = ic["r"].shape[0]
+        if self.method in (A.METHOD_FSSH, A.METHOD_EHRENFEST):
+            rho = self.initial_density(T) if rho is None else rho
+            h.set_state_diabatic(ic["r"], ic["v"], rho)
+            return ic["r"].nbytes + ic["v"].nbytes + rho.nbytes
+        if self.method == A.METHOD_IESH:
+            psi, state = ic.get("psi"), ic.get("state")
+            if psi is None:
+                psi, state = self.iesh_ground_state(T)
+            h.set_state(ic["r"], ic["v"], psi, None, state)
+            return ic["r"].nbytes + ic["v"].nbytes + psi.nbytes + state.nbytes
+        h.set_state(ic["r"], ic["v"])
+        return ic["r"].nbytes + ic["v"].nbytes
+
+    def iesh_ground_state(self, ntraj: int):
+        """DynamicsVariables(sim, v, r) for AdiabaticIESH (iesh.jl:89-97): the ne lowest adiabatic orbitals."""
+        n, ne = self.model.nstates, self.model.nelectrons
+        psi = np.zeros((ntraj, ne, n))
+        psi[:, np.arange(ne), np.arange(ne)] = 1.0
+        return psi, np.tile(np.arange(1, ne + 1, dtype=np.int32), (ntraj, 1))
 
     def initial_density(self, ntraj: int) -> np.ndarray:
         n = self.model.nstates
@@ -147,8 +183,30 @@ def _rpsh_morse() -> Workload:
                     rpsh_flops(3, 1, B, 60.0), sample, nbeads=B, temperature=kT)
 
 
+def _iesh(M: int, nsteps: int, ntraj: int) -> Workload:
+    # C4: Simulation{AdiabaticIESH}(Atoms(2000), AndersonHolstein(MiaoSubotnik(G = 6.4e-3), TrapezoidalRule(M, -W, W))),
+    # W = 6G/2 (test/Dynamics/iesh.jl:17-25), kT = 9.5e-4, dt = 1 (iesh.jl:158); thermal sample in the U1 well.
+    imp = models.MiaoSubotnik(Γ=6.4e-3)
+    W = 3.0 * imp.Γ
+    model = models.AndersonHolstein(imp, models.TrapezoidalRule(M, -W, W))
+    kT, m = 9.5e-4, 2000.0
+    sr, sv = np.sqrt(kT / (m * imp.ω ** 2)), np.sqrt(kT / m)
+
+    def sample(rng, T):
+        return {"r": rng.normal(imp.g, sr, (T, 1, 1)), "v": rng.normal(0.0, sv, (T, 1, 1))}
+    obs = (1 << A.OBS_ADIABATIC_POP) | (1 << A.OBS_DIABATIC_POP) | (1 << A.OBS_KINETIC)
+    n, ne = model.nstates, model.nelectrons
+    return Workload(f"iesh_anderson_holstein_m{M}",
+                    f"C4 AdiabaticIESH, AndersonHolstein(MiaoSubotnik, TrapezoidalRule({M}, -3G, 3G)), n={n}, ne={ne}, mass 2000, "
+                    f"kT=9.5e-4 thermal sample around x=g, ground-state orbitals, dt=1, tspan (0,{nsteps}), saveat 10",
+                    model, A.METHOD_IESH, np.array([m]), 1.0, nsteps, 10, obs, ntraj, iesh_flops(n, ne), sample)
+
+
 def get(name: str) -> Workload:
     table = {
+        "iesh_anderson_holstein_m100": lambda: _iesh(100, 1000, 10_000),
+        "iesh_anderson_holstein_m200": lambda: _iesh(200, 200, 10_000),
+        "iesh_anderson_holstein_m30": lambda: _iesh(30, 1000, 10_000),
         "tully1_fssh": _tully1_fssh,
         "spinboson_debye100_fssh": lambda: _spinboson(A.METHOD_FSSH, "spinboson_debye100_fssh"),
         "spinboson_debye100_ehrenfest": lambda: _spinboson(A.METHOD_EHRENFEST, "spinboson_debye100_ehrenfest"),
@@ -160,4 +218,5 @@ def get(name: str) -> Workload:
     return table[name]()
 
 
-NAMES = ["tully1_fssh", "spinboson_debye100_fssh", "spinboson_debye100_ehrenfest", "rpmd_harmonic32", "rpsh_morse3_16"]
+NAMES = ["tully1_fssh", "spinboson_debye100_fssh", "spinboson_debye100_ehrenfest", "rpmd_harmonic32", "rpsh_morse3_16",
+         "iesh_anderson_holstein_m100", "iesh_anderson_holstein_m200", "iesh_anderson_holstein_m30"]

@@ -461,6 +461,14 @@ int nqco_get_counters(nqco_handle* h, int64_t* steps, int64_t* hops, int64_t* fr
     return NQCB200_OK;
 }
 
+int nqco_get_hop_search_count(nqco_handle* h, int64_t* searches) {
+    if (!h || !searches) return NQCB200_ERR_INVALID;
+    int64_t s = 0;
+    for (const Trajectory& tr : h->traj) s += tr.cnt.hop_searches;
+    *searches = s;
+    return NQCB200_OK;
+}
+
 int nqco_get_progress(nqco_handle* h, int64_t* nsave_done, int64_t* step_count) {
     if (!h) return NQCB200_ERR_INVALID;
     if (nsave_done) *nsave_done = h->nsave_done;

@@ -38,7 +38,7 @@ struct ElectronicParameters {
 };
 
 struct Counters {
-    int64_t steps = 0, hops = 0, frustrated = 0, nonfinite = 0;
+    int64_t steps = 0, hops = 0, frustrated = 0, nonfinite = 0, hop_searches = 0;
 };
 
 struct Setup {
@@ -523,6 +523,7 @@ inline void iesh_hop(const Setup& S, Trajectory& T, double xi) {
         if (estimate < xi) pruned = true;
     }
     if (!pruned) {
+        T.cnt.hop_searches++;
         std::vector<int> prop(ne);
         for (int e = 0; e < ne; ++e)
             for (int m : un) {

@@ -372,6 +372,7 @@ def test_iesh_identical_hop_sequences(rescaling):
     ce, co = e.counters(), o.counters()
     assert ce["hops"] == co["hops"] and ce["frustrated"] == co["frustrated"], (ce, co)
     assert ce["hops"] > 0 and ce["frustrated"] > 0, ce
+    assert e.hop_search_count() == o.hop_search_count() > 0
     de, do = e.observable_per_trajectory(A.OBS_DISCRETE_STATE), o.observable_per_trajectory(A.OBS_DISCRETE_STATE)
     assert np.array_equal(de, do)
     _iesh_compare(e, o, 1e-9, "after hops")

@@ -15,10 +15,7 @@ kw = wl.config_kwargs(T, seed=1, nsave=launches * nsteps // wl.save_every + 1)
 cfg, keep = A.make_config(**kw)
 e = Engine(cfg, keep)
 ic = wl.sample(np.random.default_rng(0), T)
-if wl.method in (A.METHOD_FSSH, A.METHOD_EHRENFEST):
-    e.set_state_diabatic(ic["r"], ic["v"], wl.initial_density(T))
-else:
-    e.set_state(ic["r"], ic["v"])
+wl.upload(e, ic)
 for i in range(launches):
     e.run(nsteps)
     ms, nl = e.last_run_timing()
