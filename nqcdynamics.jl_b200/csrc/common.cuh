@@ -28,7 +28,7 @@ struct ObsLayout {
 
 // AdiabaticIESH (CTA per trajectory, kernel_iesh.cuh): tile / shared-memory plan computed on the host.
 struct IeshLayout {
-    int32_t threads;    // block size (13 warps)
+    int32_t threads;    // block size (12 warps: 3 per SM sub-partition)
     int32_t nrt;        // row tiles of 8 states
     int32_t ldg;        // leading dimension of G (column-major), >= 8*nrt and = 4 (mod 16): conflict-free DMMA fragments
     int32_t nct;        // column tiles (8 doubles = 4 electrons, re/im interleaved) per psi chunk
@@ -43,7 +43,7 @@ struct IeshLayout {
     int32_t off_hop;    // hop-phase offset inside the work region
     int32_t work_doubles;
     int32_t smem_bytes;
-    int32_t rounds;     // row tiles per warp (1 or 2)
+    int32_t rounds;     // full rows of 8 states per warp (0, 1 or 2); the other rows are dealt out tile by tile
 };
 
 // Kernel parameter block (passed by value as a __grid_constant__).
@@ -86,6 +86,7 @@ struct KParams {
     IeshLayout iesh;
     double* iesh_lam;   // [T][n]   adiabatic energies of the last step (warm start of the root finder)
     double* iesh_sgn;   // [T][n]   eigenvector column signs (gauge), constant along a trajectory
+    double* iesh_orth;  // [T]      1.0 when the initial orbitals are orthonormal (determinant-free pruning bound)
     double* iesh_G;     // [grid][ldg*kb*nslab] v.d scratch when it does not fit in shared memory
     // draws (injected): xi[(step - draws_step0) * T + traj]
     const double* draws;

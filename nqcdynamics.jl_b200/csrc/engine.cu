@@ -446,6 +446,7 @@ int nqcb200_create(const nqcb200_config* cfg, nqcb200_handle** out) {
     if (iesh) {
         if ((rc = dev_alloc(h, &kp.iesh_lam, (size_t)n * T)) != 0) return fail(rc);
         if ((rc = dev_alloc(h, &kp.iesh_sgn, (size_t)n * T)) != 0) return fail(rc);
+        if ((rc = dev_alloc(h, &kp.iesh_orth, (size_t)T)) != 0) return fail(rc);
         if (!kp.iesh.resident) {
             const size_t per_cta = (size_t)kp.iesh.ldg * kp.iesh.kb * kp.iesh.nslab;
             if ((rc = dev_alloc(h, &kp.iesh_G, per_cta * (size_t)h->persistent_ctas)) != 0) return fail(rc);

@@ -338,12 +338,16 @@ NQ_D void dmma884(double& c0, double& c1, double a, double b) {
 // Horner form of the Taylor polynomial of the shifted generator A = -i dts (W - sigma) - dts G,
 //     y_K+1 = psi0 ;  y_j = psi0 + (A y_j+1) / j  (j = K..1) ;  psi' = y_1 ,  psi0 = e^{-i sigma dts} psi,
 // acting on the real matrix [X | Y] (columns 2e, 2e+1 = Re, Im of electron e).  Stages j > Kg drop the G part
-// (its contribution to psi' is below 1e-18) and are purely diagonal.  One warp owns R row tiles of 8 states x NT
-// column tiles of 8 (= 4 electrons); G y is accumulated with DMMA m8n8k4, A fragments from G (column-major, leading
-// dimension = 4 mod 16: conflict-free), B fragments from the y chunk (row-major, same rule).
-template <int R, int NT>
-__device__ __noinline__ void iesh_propagate(const KParams& p, const IeshSmem& S, double* __restrict__ psi_re, double* __restrict__ psi_im,
-                         double* Gs, double* Bs, const double* Gglob, double sigma, double dts, int nsub, int K, int Kg) {
+// (its contribution to psi' is below 1e-18) and are purely diagonal.  G y is accumulated with DMMA m8n8k4:
+// A fragments from G (column-major, leading dimension = 4 mod 16: conflict-free), B fragments from the y chunk
+// (row-major, same rule).  Tile ownership (12 warps = 3 per SM sub-partition, so the tensor pipes stay balanced):
+// warp w owns the R full rows of 8 states {w, w+12, ..} x all NT column tiles of the chunk, and the tiles of the
+// remaining rows are dealt out one by one as "extra" tiles (at most NX per warp).
+// Returns (to every thread) the leakage  sum_{m unoccupied, e} |psi'_me|^2.
+template <int R, int NT, int NX>
+__device__ __noinline__ double iesh_propagate(const KParams& p, const IeshSmem& S, double* __restrict__ psi_re,
+                                              double* __restrict__ psi_im, double* Gs, double* Bs, const double* Gglob,
+                                              double sigma, double dts, int nsub, int K, int Kg) {
     const IeshLayout& L = p.iesh;
     const int n = p.n, ne = p.ne, tid = threadIdx.x, nt = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
@@ -351,15 +355,24 @@ __device__ __noinline__ void iesh_propagate(const KParams& p, const IeshSmem& S,
     const int n4 = (n + 3) & ~3;
     const int ecap = 4 * L.nct;                       // electrons per chunk (nct column tiles of 8 doubles)
     const double cph = cos(sigma * dts), sph = sin(sigma * dts);
-    int mt[R];
-    bool mok[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) { mt[r] = warp + r * nwarps; mok[r] = mt[r] < L.nrt; }
+    const int rem_rows = L.nrt - R * nwarps;          // rows of 8 states dealt out tile by tile
+    double leak = 0.0;
 
     for (int sub_i = 0; sub_i < nsub; ++sub_i) {
+        const bool last_sub = (sub_i == nsub - 1);
         for (int ch = 0; ch < L.nchunks; ++ch) {
             const int e0 = ch * ecap, e1 = min(ne, e0 + ecap);
             const int nt_act = (e1 - e0 + 3) / 4;
+            // extra tiles of this warp in this chunk
+            int xrow[NX], xcol[NX];
+            bool xok[NX];
+#pragma unroll
+            for (int x = 0; x < NX; ++x) {
+                const int g = warp + nwarps * x;
+                xok[x] = g < rem_rows * nt_act;
+                xrow[x] = xok[x] ? R * nwarps + g / nt_act : 0;
+                xcol[x] = xok[x] ? g % nt_act : 0;
+            }
             // chunk load: psi0 = e^{-i sigma dts} psi -> global (read back at every stage) and y = psi0 -> Bs
             for (int idx = tid; idx < ecap * n4; idx += nt) {
                 const int i = idx % n4, el = idx / n4, e = e0 + el;
@@ -372,56 +385,65 @@ __device__ __noinline__ void iesh_propagate(const KParams& p, const IeshSmem& S,
                 Bs[i * L.ldb + 2 * el] = x; Bs[i * L.ldb + 2 * el + 1] = y;
             }
             __syncthreads();
+            // one owned element pair (row i, electron e0 + 4 t + lr4): y <- psi0 + ck ((ws Y - gx) + i (-ws X - gy))
+            auto update = [&](int mtile, int t, double ck, double gx, double gy) {
+                const int i = 8 * mtile + lq, e = e0 + 4 * t + lr4;
+                if (i < n && e < e1) {
+                    const double wsi = S.ws[i];
+                    double2* bp2 = reinterpret_cast<double2*>(Bs + i * L.ldb + 8 * t + 2 * lr4);
+                    const double2 old = *bp2;
+                    const double x0 = psi_re[i + (int64_t)n * e], y0 = psi_im[i + (int64_t)n * e];
+                    *bp2 = make_double2(fma(ck, wsi * old.y - gx, x0), fma(ck, -wsi * old.x - gy, y0));
+                }
+            };
             // diagonal-only stages (own elements only: no barrier between them)
             for (int j = K; j > Kg; --j) {
                 const double ck = dts / j;
 #pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    const int i = 8 * mt[r] + lq;
-                    if (!mok[r] || i >= n) continue;
-                    const double wsi = S.ws[i];
+                for (int r = 0; r < R; ++r)
 #pragma unroll
-                    for (int t = 0; t < NT; ++t) {
-                        const int e = e0 + 4 * t + lr4;
-                        if (t < nt_act && e < e1) {
-                            double2* bp = reinterpret_cast<double2*>(Bs + i * L.ldb + 8 * t + 2 * lr4);
-                            const double2 old = *bp;
-                            const double x0 = psi_re[i + (int64_t)n * e], y0 = psi_im[i + (int64_t)n * e];
-                            *bp = make_double2(fma(ck, wsi * old.y, x0), fma(ck, -wsi * old.x, y0));
-                        }
-                    }
-                }
+                    for (int t = 0; t < NT; ++t)
+                        if (t < nt_act) update(warp + r * nwarps, t, ck, 0.0, 0.0);
+#pragma unroll
+                for (int x = 0; x < NX; ++x)
+                    if (xok[x]) update(xrow[x], xcol[x], ck, 0.0, 0.0);
             }
             __syncthreads();
             for (int j = Kg; j >= 1; --j) {
                 const double ck = dts / j;
-                double c[R][NT][2];
+                double c[R > 0 ? R : 1][NT][2], cx[NX][2];
 #pragma unroll
                 for (int r = 0; r < R; ++r)
 #pragma unroll
                     for (int t = 0; t < NT; ++t) { c[r][t][0] = 0.0; c[r][t][1] = 0.0; }
-                // ---- G y on the tensor cores ----------------------------------------------------------
-                if (L.resident) {
-                    const double* gp[R];
 #pragma unroll
-                    for (int r = 0; r < R; ++r) gp[r] = Gs + (8 * (mok[r] ? mt[r] : 0) + lq) + L.ldg * lr4;
+                for (int x = 0; x < NX; ++x) { cx[x][0] = 0.0; cx[x][1] = 0.0; }
+                // one k-slab [k0, k1) of the product, G columns read from gbase (column k0 at offset 0)
+                auto slab = [&](const double* gbase, int k0, int k1) {
+                    const double* gp = gbase + lq + L.ldg * lr4;
                     const double* bp = Bs + lr4 * L.ldb + lq;
-                    if (mok[0]) {
 #pragma unroll 2
-                        for (int k = 0; k < n4; k += 4) {
-                            double a[R];
+                    for (int k = k0; k < k1; k += 4) {
+                        const double* gk = gp + (k - k0) * L.ldg;
+                        const double* bk = bp + k * L.ldb;
+                        double a[R > 0 ? R : 1];
 #pragma unroll
-                            for (int r = 0; r < R; ++r) a[r] = gp[r][(int64_t)k * L.ldg];
+                        for (int r = 0; r < R; ++r) a[r] = gk[8 * (warp + r * nwarps)];
 #pragma unroll
-                            for (int t = 0; t < NT; ++t) {
-                                if (t < nt_act) {
-                                    const double b = bp[k * L.ldb + 8 * t];
+                        for (int t = 0; t < NT; ++t) {
+                            if (R > 0 && t < nt_act) {
+                                const double b = bk[8 * t];
 #pragma unroll
-                                    for (int r = 0; r < R; ++r) dmma884(c[r][t][0], c[r][t][1], a[r], b);
-                                }
+                                for (int r = 0; r < R; ++r) dmma884(c[r][t][0], c[r][t][1], a[r], b);
                             }
                         }
+#pragma unroll
+                        for (int x = 0; x < NX; ++x)
+                            if (xok[x]) dmma884(cx[x][0], cx[x][1], gk[8 * xrow[x]], bk[8 * xcol[x]]);
                     }
+                };
+                if (L.resident) {
+                    slab(Gs, 0, n4);
                     __syncthreads();
                 } else {
                     const int pieces = L.ldg * L.kb / 2;   // 16-byte pieces per slab
@@ -436,66 +458,41 @@ __device__ __noinline__ void iesh_propagate(const KParams& p, const IeshSmem& S,
                         cp_async_commit();
                         cp_async_wait<1>();
                         __syncthreads();
-                        if (mok[0]) {
-                            const int k0 = s * L.kb, k1 = min(n4, k0 + L.kb);
-                            const double* gbase = Gs + (s & 1) * L.ldg * L.kb;
-                            const double* gp[R];
-#pragma unroll
-                            for (int r = 0; r < R; ++r) gp[r] = gbase + (8 * (mok[r] ? mt[r] : 0) + lq) + L.ldg * lr4;
-                            const double* bp = Bs + lr4 * L.ldb + lq;
-                            for (int k = k0; k < k1; k += 4) {
-                                double a[R];
-#pragma unroll
-                                for (int r = 0; r < R; ++r) a[r] = gp[r][(k - k0) * L.ldg];
-#pragma unroll
-                                for (int t = 0; t < NT; ++t) {
-                                    if (t < nt_act) {
-                                        const double b = bp[k * L.ldb + 8 * t];
-#pragma unroll
-                                        for (int r = 0; r < R; ++r) dmma884(c[r][t][0], c[r][t][1], a[r], b);
-                                    }
-                                }
-                            }
-                        }
+                        slab(Gs + (s & 1) * L.ldg * L.kb, s * L.kb, min(n4, (s + 1) * L.kb));
                         __syncthreads();
                     }
                 }
-                // ---- y_j = psi0 + ck ( (ws Y - G X) + i (-ws X - G Y) ), in place ---------------------------
 #pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    const int i = 8 * mt[r] + lq;
-                    if (!mok[r] || i >= n) continue;
-                    const double wsi = S.ws[i];
+                for (int r = 0; r < R; ++r)
 #pragma unroll
-                    for (int t = 0; t < NT; ++t) {
-                        const int e = e0 + 4 * t + lr4;
-                        if (t < nt_act && e < e1) {
-                            double2* bp2 = reinterpret_cast<double2*>(Bs + i * L.ldb + 8 * t + 2 * lr4);
-                            const double2 old = *bp2;
-                            const double x0 = psi_re[i + (int64_t)n * e], y0 = psi_im[i + (int64_t)n * e];
-                            *bp2 = make_double2(fma(ck, wsi * old.y - c[r][t][0], x0), fma(ck, -wsi * old.x - c[r][t][1], y0));
-                        }
-                    }
-                }
+                    for (int t = 0; t < NT; ++t)
+                        if (t < nt_act) update(warp + r * nwarps, t, ck, c[r][t][0], c[r][t][1]);
+#pragma unroll
+                for (int x = 0; x < NX; ++x)
+                    if (xok[x]) update(xrow[x], xcol[x], ck, cx[x][0], cx[x][1]);
                 __syncthreads();
             }
-            // y_1 = psi' of this chunk: every thread stores the elements it owns
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const int i = 8 * mt[r] + lq;
-                if (!mok[r] || i >= n) continue;
-#pragma unroll
-                for (int t = 0; t < NT; ++t) {
-                    const int e = e0 + 4 * t + lr4;
-                    if (t < nt_act && e < e1) {
-                        const double2 y = *reinterpret_cast<const double2*>(Bs + i * L.ldb + 8 * t + 2 * lr4);
-                        psi_re[i + (int64_t)n * e] = y.x; psi_im[i + (int64_t)n * e] = y.y;
-                    }
+            // y_1 = psi' of this chunk: every thread stores the elements it owns (+ leakage out of the occupied orbitals)
+            auto store = [&](int mtile, int t) {
+                const int i = 8 * mtile + lq, e = e0 + 4 * t + lr4;
+                if (i < n && e < e1) {
+                    const double2 y = *reinterpret_cast<const double2*>(Bs + i * L.ldb + 8 * t + 2 * lr4);
+                    psi_re[i + (int64_t)n * e] = y.x; psi_im[i + (int64_t)n * e] = y.y;
+                    if (last_sub && S.flag[i] < 0) leak += y.x * y.x + y.y * y.y;
                 }
-            }
+            };
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int t = 0; t < NT; ++t)
+                    if (t < nt_act) store(warp + r * nwarps, t);
+#pragma unroll
+            for (int x = 0; x < NX; ++x)
+                if (xok[x]) store(xrow[x], xcol[x]);
             __syncthreads();
         }
     }
+    return iesh_block_sum(leak, S.red);
 }
 
 // det S for S[j][i] = psi[occ_j, i] (iesh.jl:309-316; FastDeterminant.det!, FastDeterminant.jl:20-22): LU with
@@ -503,7 +500,7 @@ __device__ __noinline__ void iesh_propagate(const KParams& p, const IeshSmem& S,
 // elements, held in REGISTERS (REG = true, ne <= 52) or in its own shared-memory slots (REG = false); the pivot
 // column and pivot row travel through shared memory (double buffered: two barriers per column).  Rows are never
 // swapped (implicit pivoting); the permutation sign is accumulated from the rank of each pivot among the
-// remaining rows.   buf: 8 * roundup(ne, 4) doubles ; store (REG = false): 2 * RL * CL * blockDim doubles.
+// remaining rows.   buf: 8 * roundup(ne, 4) doubles ; store (REG = false): 2 * ne * lds doubles.
 template <int RL, int CL, bool REG>
 __device__ __noinline__ void iesh_det_lu(const KParams& p, const IeshSmem& S, const double* __restrict__ psi_re,
                       const double* __restrict__ psi_im, double* buf, double* store, double& det_re, double& det_im) {
@@ -511,9 +508,10 @@ __device__ __noinline__ void iesh_det_lu(const KParams& p, const IeshSmem& S, co
     const int PC = nt >> 4;
     const int tr = tid & 15, tc = tid >> 4, lane = tid & 31;
     double are[REG ? RL : 1][REG ? CL : 1], aim[REG ? RL : 1][REG ? CL : 1];
-    double* sre = store + tid;
-    double* sim = store + (int64_t)RL * CL * nt + tid;
-    auto slot = [&](int a, int b) { return (a * CL + b) * nt; };
+    const int lds = p.iesh.lds;                       // REG = false: S in the standard [ne][lds] layout
+    double* sre = store;
+    double* sim = store + ne * lds;
+    auto slot = [&](int a, int b) { return (tr + 16 * a) * lds + tc + PC * b; };
 #pragma unroll
     for (int a = 0; a < RL; ++a)
 #pragma unroll
@@ -522,7 +520,7 @@ __device__ __noinline__ void iesh_det_lu(const KParams& p, const IeshSmem& S, co
             const bool ok = (i < ne && j < ne);
             const double vr = ok ? psi_re[S.occ[i] + (int64_t)n * j] : 0.0;
             const double vi = ok ? psi_im[S.occ[i] + (int64_t)n * j] : 0.0;
-            if (REG) { are[a][b] = vr; aim[a][b] = vi; } else { sre[slot(a, b)] = vr; sim[slot(a, b)] = vi; }
+            if (REG) { are[a][b] = vr; aim[a][b] = vi; } else if (ok) { sre[slot(a, b)] = vr; sim[slot(a, b)] = vi; }
         }
     const int nep = (ne + 3) & ~3;
     double* cb_re = buf; double* cb_im = buf + 2 * nep; double* rb_re = buf + 4 * nep; double* rb_im = buf + 6 * nep;
@@ -619,7 +617,7 @@ __device__ __noinline__ void iesh_det_lu(const KParams& p, const IeshSmem& S, co
 }
 
 // ---- the step kernel -----------------------------------------------------------------------------
-__global__ void __launch_bounds__(416, 1) iesh_step_kernel(const __grid_constant__ KParams p) {
+__global__ void __launch_bounds__(384, 1) iesh_step_kernel(const __grid_constant__ KParams p) {
     extern __shared__ __align__(16) double iesh_sm[];
     IeshSmem S;
     S.carve(iesh_sm, p.n);
@@ -647,6 +645,7 @@ __global__ void __launch_bounds__(416, 1) iesh_step_kernel(const __grid_constant
         for (int e = tid; e < ne; e += nt) S.occ[e] = p.state[traj * ne + e];
         iesh_refresh_unoccupied(p, S);
         double r = p.r[traj], v = p.v[traj], acc = p.acc[traj];
+        const bool orth_ok = p.iesh_orth[traj] != 0.0;
 
 #pragma unroll 1
         for (int is = 0; is < p.nsteps; ++is) {
@@ -706,8 +705,10 @@ __global__ void __launch_bounds__(416, 1) iesh_step_kernel(const __grid_constant
             }
             __syncthreads();
 
-            if (L.rounds == 1) iesh_propagate<1, 16>(p, S, psi_re, psi_im, Gs, Bs, Gglob, sigma, dts, nsub, K, Kg);
-            else iesh_propagate<2, 8>(p, S, psi_re, psi_im, Gs, Bs, Gglob, sigma, dts, nsub, K, Kg);
+            double leak;
+            if (L.rounds == 0) leak = iesh_propagate<0, 1, 4>(p, S, psi_re, psi_im, Gs, Bs, Gglob, sigma, dts, nsub, K, Kg);
+            else if (L.rounds == 1) leak = iesh_propagate<1, 16, 4>(p, S, psi_re, psi_im, Gs, Bs, Gglob, sigma, dts, nsub, K, Kg);
+            else leak = iesh_propagate<2, 8, 4>(p, S, psi_re, psi_im, Gs, Bs, Gglob, sigma, dts, nsub, K, Kg);
             __syncthreads();
 
             // ---- IESHCallback: hop test (iesh.jl:231-335,390-407) ----------------------------------
@@ -715,10 +716,20 @@ __global__ void __launch_bounds__(416, 1) iesh_step_kernel(const __grid_constant
                 const double xi = (p.rng == NQCB200_RNG_INJECTED)
                                       ? p.draws[(step - p.draws_step0) * p.ntraj + traj]
                                       : philox_uniform(p.seed, (uint64_t)(p.traj_offset + traj), (uint64_t)step, 0u);
+                // Pruning without the determinant: for orthonormal orbitals |det S|^2 = det(I - U'U) >= 1 - tr U'U = 1 - leak
+                // (U = unoccupied rows of psi), and |Re det| + |Im det| <= sqrt(2) |det|, hence
+                //   estimate <= 2 sqrt(2) dt sum|v.d| / sqrt(1 - leak);  if even this bound is below xi the reference's
+                // test (iesh.jl:251-254) prunes the step and det S is not needed at all.
+                bool certainly_pruned = false;
+                if (p.estimate_probability && orth_ok && p.edc_C <= 0.0) {
+                    const double d2lo = (1.0 - leak) * (1.0 - 1e-9) - 1e-9;
+                    if (d2lo > 0.0) certainly_pruned = 2.8284271247461903 * dt * sabs / sqrt(d2lo) * (1.0 + 1e-9) < xi;
+                }
+                if (!certainly_pruned) {
                 double det_re, det_im;
                 const int nep8 = 8 * ((ne + 3) & ~3);
-                if (ne <= 16 * 4 && ne <= (nt >> 4) * 2) iesh_det_lu<4, 2, true>(p, S, psi_re, psi_im, Hs, Hs + nep8, det_re, det_im);
-                else iesh_det_lu<7, 4, false>(p, S, psi_re, psi_im, Hs, Hs + nep8, det_re, det_im);
+                if (ne <= 64) iesh_det_lu<4, 3, true>(p, S, psi_re, psi_im, Hs, Hs + nep8, det_re, det_im);      // 16 x 24 threads
+                else iesh_det_lu<7, 5, false>(p, S, psi_re, psi_im, Hs, Hs + nep8, det_re, det_im);
                 const double Akk = det_re * det_re + det_im * det_im;
                 const double prefactor = 2.0 * dt / Akk;
                 bool pruned = false;
@@ -869,6 +880,7 @@ __global__ void __launch_bounds__(416, 1) iesh_step_kernel(const __grid_constant
                         }
                     }
                 }
+                }
                 __syncthreads();
             }
 
@@ -930,7 +942,7 @@ __global__ void __launch_bounds__(416, 1) iesh_step_kernel(const __grid_constant
 // Initialisation: update_cache!(r0) with a cold root search, gauge signs against the identity
 // (or a user reference Z through p.Zprev, [T][n*n] trajectory-major), initial acceleration
 // (verlet_with_electronics.jl:30-40), save point 0.
-__global__ void __launch_bounds__(416, 1) iesh_init_kernel(const __grid_constant__ KParams p, int user_gauge, int,
+__global__ void __launch_bounds__(384, 1) iesh_init_kernel(const __grid_constant__ KParams p, int user_gauge, int,
                                                           const double*) {
     extern __shared__ __align__(16) double iesh_sm[];
     IeshSmem S;
@@ -966,6 +978,23 @@ __global__ void __launch_bounds__(416, 1) iesh_init_kernel(const __grid_constant
         const double occsum = iesh_block_sum(part, S.red);
         if (tid == 0) p.acc[traj] = (-du0 - dh * occsum) / mdl.mass;
         iesh_record_save(p, S, traj, 0, r, v, mdl, psi_re, psi_im);
+        {
+            // are the orbitals orthonormal?  (enables the determinant-free pruning bound of the step kernel)
+            double dev = 0.0;
+            for (int idx = tid; idx < ne * ne; idx += nt) {
+                const int e1 = idx % ne, e2 = idx / ne;
+                if (e1 > e2) continue;
+                double sr = 0.0, si = 0.0;
+                for (int i = 0; i < n; ++i) {
+                    const double ar = psi_re[i + (int64_t)n * e1], ai = psi_im[i + (int64_t)n * e1];
+                    const double br = psi_re[i + (int64_t)n * e2], bi = psi_im[i + (int64_t)n * e2];
+                    sr += ar * br + ai * bi; si += ar * bi - ai * br;
+                }
+                dev = fmax(dev, fmax(fabs(sr - (e1 == e2 ? 1.0 : 0.0)), fabs(si)));
+            }
+            dev = iesh_block_max(dev, S.red);
+            if (tid == 0) p.iesh_orth[traj] = (dev < 1e-11) ? 1.0 : 0.0;
+        }
         if (p.diagnostics && p.diag_eig) {
             for (int i = tid; i < n; i += nt) p.diag_eig[traj * n + i] = S.lam[i];
             for (int idx = tid; idx < n * n; idx += nt) {

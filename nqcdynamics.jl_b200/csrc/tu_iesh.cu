@@ -9,20 +9,23 @@ int pad16_4(int x) { int y = x; while (y % 16 != 4) ++y; return y; }
 
 bool iesh_plan(int n, int ne, size_t smem_max, IeshLayout& L) {
     L = IeshLayout{};
-    L.threads = 416;
+    L.threads = 384;
     const int nwarps = L.threads / 32;
     L.nrt = (n + 7) / 8;
-    L.rounds = (L.nrt + nwarps - 1) / nwarps;
+    L.rounds = L.nrt / nwarps;                        // full rows per warp; the remaining rows are dealt out tile by tile
     if (L.rounds > 2) return false;
+    const int rem_rows = L.nrt - L.rounds * nwarps;
     L.ldg = pad16_4(8 * L.nrt);
     const int n4 = (n + 3) & ~3;
     const int nt_need = (ne + 3) / 4;                 // column tiles for all electrons
-    const int nt_max = (L.rounds == 1) ? 16 : 8;     // accumulator tiles per warp (register budget)
+    int nt_max = (L.rounds <= 1) ? 16 : 8;            // accumulator tiles per warp (register budget)
+    if (rem_rows > 0) nt_max = std::min(nt_max, (4 * nwarps) / rem_rows);   // at most 4 extra tiles per warp
+    if (nt_max < 1) return false;
     L.lds = ne | 1;
     const int nep = (ne + 3) & ~3;
     const long small = iesh_small_doubles(n);
-    // hop phase: Gauss-Jordan fallback (S, S^-1 work vectors) or the LU buffers (+ per-thread element slots when ne > 52)
-    const long lu = 8L * nep + (ne > 52 ? 2L * 7 * 4 * L.threads : 0L);
+    // hop phase: Gauss-Jordan fallback (S, S^-1 work vectors) or the LU buffers (+ S itself when ne > 64)
+    const long lu = 8L * nep + (ne > 64 ? 2L * ne * L.lds : 0L);
     const long hop = std::max(2L * ne * L.lds + 7L * ne + n + (2 * ne + 1) / 2 + 4, lu);
     int lr = 1;
     while (lr < 32 && (long)n * lr * 2 <= L.threads) lr *= 2;
@@ -67,7 +70,7 @@ bool select_iesh(const nqcb200_config& c, KernelSet& out, std::string& why) {
     }
     if (c.ndofs != 1 || c.nbeads != 1) { why = "AdiabaticIESH kernel: ndofs == 1 and nbeads == 1"; return false; }
     const int n = c.nstates, ne = c.nelectrons;
-    if (ne > 104) { why = "AdiabaticIESH kernel: at most 104 electrons"; return false; }
+    if (ne > 112) { why = "AdiabaticIESH kernel: at most 112 electrons"; return false; }
     if (n < 3 || ne < 1 || ne >= n) { why = "AdiabaticIESH needs nstates >= 3 and 1 <= nelectrons < nstates"; return false; }
     if (c.nbath != n - 1 || !c.bath_a || !c.bath_b) { why = "AndersonHolstein needs nstates-1 bath energies and couplings"; return false; }
     for (int k = 0; k < n - 1; ++k) {

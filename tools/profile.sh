@@ -16,6 +16,7 @@ smsp__sass_thread_inst_executed_op_dfma_pred_on.sum,smsp__sass_thread_inst_execu
 $NCU -i gpurun_out/prof_$TAG.ncu-rep --page raw --csv > gpurun_out/prof_${TAG}_raw.csv 2>/dev/null
 $NCU -i gpurun_out/prof_$TAG.ncu-rep --page details --csv > gpurun_out/prof_${TAG}_details.csv 2>/dev/null
 $NCU -i gpurun_out/prof_$TAG.ncu-rep --page source --csv 2>/dev/null | gzip -9 > gpurun_out/prof_${TAG}_source.csv.gz
+$NCU -i gpurun_out/prof_$TAG.ncu-rep --page source --print-source cuda,sass --csv 2>/dev/null | gzip -9 > gpurun_out/prof_${TAG}_cudasass.csv.gz
 rm -f gpurun_out/prof_$TAG.ncu-rep
 tail -2 gpurun_out/launches_$TAG.log
 ls -la gpurun_out | head -20

@@ -1,0 +1,24 @@
+"""Aggregate an `ncu --page source --print-source cuda,sass --csv` export per CUDA source line.
+usage: src_hotspots.py FILE.csv.gz [TOP]"""
+import csv, gzip, sys, collections
+rows = list(csv.reader(gzip.open(sys.argv[1], 'rt')))
+top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
+line = None; src = {}
+samples = collections.Counter(); insts = collections.Counter()
+fn = ''
+for r in rows:
+    if not r: continue
+    if r[0] == 'Function Name': fn = r[1][:40]; continue
+    if r[0] in ('File Path', 'Line No'): continue
+    if r[0].isdigit():
+        line = (fn, int(r[0])); src[line] = r[1][:90]
+        continue
+    if r[0] == '' and len(r) >= 8 and r[2].startswith('0x') and line is not None:
+        try:
+            samples[line] += int(r[6]); insts[line] += int(r[7])
+        except ValueError:
+            pass
+tot = sum(samples.values())
+print("total samples", tot)
+for ln, s in samples.most_common(top):
+    print(f"{100*s/tot:5.1f}%  {insts[ln]/1e6:9.1f}M  {ln[0][:28]:28s} L{ln[1]:4d}  {src[ln]}")
