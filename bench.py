@@ -266,7 +266,7 @@ def main():
     flops_step = wl.flops_per_traj_step
     flops_note = ""
     if wl.method == A.METHOD_IESH:
-        counters["hop_searches"] = eng.hop_search_count()
+        counters.update(eng.iesh_stats())
         frac = counters["hop_searches"] / max(1, counters["steps"])
         extra = workloads.iesh_hop_search_flops(wl.model.nstates, wl.model.nelectrons)
         flops_step = wl.flops_per_traj_step + frac * extra

@@ -274,10 +274,15 @@ int nqcb200_get_diagnostics(nqcb200_handle* h, double* eig, double* nac, double*
 int nqcb200_get_counters(nqcb200_handle* h, int64_t* steps, int64_t* hops, int64_t* frustrated,
                          int64_t* nonfinite);
 
-/* AdiabaticIESH: number of trajectory-steps on which the pruning estimate (iesh.jl:251-254) did NOT
- * rule out a hop, i.e. on which all ne*(n-ne) hopping probabilities were evaluated (iesh.jl:256-266).
- * Zero for the other methods.                                                                    */
-int nqcb200_get_hop_search_count(nqcb200_handle* h, int64_t* searches);
+/* AdiabaticIESH work counters, summed over this handle's trajectories since set_state (any pointer may be NULL):
+ *   hop_searches   trajectory-steps on which the pruning estimate (iesh.jl:251-254) did NOT rule out a hop, i.e. on
+ *                  which all ne*(n-ne) hopping probabilities were evaluated (iesh.jl:256-266)
+ *   determinants   trajectory-steps on which det S was evaluated (the others were pruned by a rigorous bound)
+ *   taylor_stages  polynomial stages spent on propagate_wavefunction! (wavefunction_dynamics.jl:15-58)
+ *   gemm_stages    of which stages that needed the dense v.d product
+ * All zero for the other methods.                                                                  */
+int nqcb200_get_iesh_stats(nqcb200_handle* h, int64_t* hop_searches, int64_t* determinants,
+                           int64_t* taylor_stages, int64_t* gemm_stages);
 
 /* Number of save points recorded so far, and device time (ms, CUDA events on the launch stream)
  * spent in step kernels by the last nqcb200_run, with the number of kernel launches it made.   */

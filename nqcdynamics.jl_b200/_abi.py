@@ -99,7 +99,7 @@ def bind(lib: C.CDLL, prefix: str) -> None:
     f("get_observable_per_trajectory", [H, C.c_int, _dp, C.c_int64])
     f("get_diagnostics", [H, _dp, _dp, _dp, _dp])
     f("get_counters", [H, _lp, _lp, _lp, _lp])
-    f("get_hop_search_count", [H, _lp])
+    f("get_iesh_stats", [H, _lp, _lp, _lp, _lp])
     f("get_progress", [H, _lp, _lp])
     f("get_last_run_timing", [H, _dp, _lp], required=False)
     f("measure_fp64_peak", [C.c_int, _dp], required=False)
@@ -109,7 +109,7 @@ HEADER_SYMBOLS = [
     "version", "device_count", "create", "destroy", "last_error", "observable_width", "set_state",
     "set_state_diabatic", "set_mapping", "set_gauge_reference", "set_draws", "run", "get_state", "get_mapping",
     "get_observable_sum", "observable_sum_device", "observable_offset", "get_observable_per_trajectory",
-    "get_diagnostics", "get_counters", "get_hop_search_count", "get_progress", "get_last_run_timing", "measure_fp64_peak",
+    "get_diagnostics", "get_counters", "get_iesh_stats", "get_progress", "get_last_run_timing", "measure_fp64_peak",
 ]
 
 _ENGINE_LIB: Optional[C.CDLL] = None
@@ -265,10 +265,13 @@ class CHandle:
         self._call("get_counters", *[C.byref(x) for x in vals])
         return dict(zip(("steps", "hops", "frustrated", "nonfinite"), (int(x.value) for x in vals)))
 
+    def iesh_stats(self) -> dict:
+        vals = [C.c_int64() for _ in range(4)]
+        self._call("get_iesh_stats", *[C.byref(x) for x in vals])
+        return dict(zip(("hop_searches", "determinants", "taylor_stages", "gemm_stages"), (int(x.value) for x in vals)))
+
     def hop_search_count(self) -> int:
-        x = C.c_int64()
-        self._call("get_hop_search_count", C.byref(x))
-        return int(x.value)
+        return self.iesh_stats()["hop_searches"]
 
     def progress(self):
         a, b = C.c_int64(), C.c_int64()

@@ -272,7 +272,7 @@ int set_state_impl(nqcb200_handle* h, const double* r, const double* v, const do
     }
     NQ_CUDA(h, cudaMemsetAsync(h->kp.obs_sum, 0, sizeof(double) * std::max<int64_t>(1, h->kp.layout.total) * kObsReplicas, h->stream));
     if (h->kp.obs_traj) NQ_CUDA(h, cudaMemsetAsync(h->kp.obs_traj, 0, sizeof(double) * h->kp.layout.total * T, h->stream));
-    NQ_CUDA(h, cudaMemsetAsync(h->kp.counters, 0, sizeof(unsigned long long) * 4, h->stream));
+    NQ_CUDA(h, cudaMemsetAsync(h->kp.counters, 0, sizeof(unsigned long long) * 8, h->stream));
     h->step_count = 0;
     h->kp.step0 = 0;
     h->kp.nsteps = 0;
@@ -466,7 +466,7 @@ int nqcb200_create(const nqcb200_config* cfg, nqcb200_handle** out) {
         if ((rc = dev_alloc(h, &kp.diag_nac, (size_t)D * n * n * T)) != 0) return fail(rc);
         if ((rc = dev_alloc(h, &kp.diag_Z, (size_t)n * n * T)) != 0) return fail(rc);
     }
-    if ((rc = dev_alloc(h, &kp.counters, 4)) != 0) return fail(rc);
+    if ((rc = dev_alloc(h, &kp.counters, 8)) != 0) return fail(rc);
     if ((rc = dev_alloc(h, &h->d_state_draw, (size_t)T)) != 0) return fail(rc);
     // staging: large enough for any single field (and the per-trajectory outputs of one observable)
     size_t stage = iesh ? std::max<size_t>(BD, (size_t)(h->nstate + 1) / 2 + 1)
@@ -720,13 +720,17 @@ int nqcb200_get_counters(nqcb200_handle* h, int64_t* steps, int64_t* hops, int64
     return NQCB200_OK;
 }
 
-int nqcb200_get_hop_search_count(nqcb200_handle* h, int64_t* searches) {
-    if (!h || !searches) return NQCB200_ERR_INVALID;
+int nqcb200_get_iesh_stats(nqcb200_handle* h, int64_t* hop_searches, int64_t* determinants, int64_t* taylor_stages,
+                           int64_t* gemm_stages) {
+    if (!h) return NQCB200_ERR_INVALID;
     NQ_CUDA(h, cudaSetDevice(h->cfg.device));
-    unsigned long long host = 0;
-    NQ_CUDA(h, cudaMemcpyAsync(&host, h->kp.counters + 3, sizeof(host), cudaMemcpyDeviceToHost, h->stream));
+    unsigned long long host[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    NQ_CUDA(h, cudaMemcpyAsync(host, h->kp.counters, sizeof(host), cudaMemcpyDeviceToHost, h->stream));
     NQ_CUDA(h, cudaStreamSynchronize(h->stream));
-    *searches = (int64_t)host;
+    if (hop_searches) *hop_searches = (int64_t)host[3];
+    if (determinants) *determinants = (int64_t)host[4];
+    if (taylor_stages) *taylor_stages = (int64_t)host[5];
+    if (gemm_stages) *gemm_stages = (int64_t)host[6];
     return NQCB200_OK;
 }
 

@@ -249,8 +249,9 @@ NQ_D void iesh_emit(const KParams& p, int64_t traj, int isave, int obs_id, int k
 }
 
 // Estimators at a save point (iesh.jl:337-388).  Every thread of the CTA must call it.
+// zt: 16 * n doubles of scratch shared memory (the psi-chunk region is free at a save point)
 NQ_D void iesh_record_save(const KParams& p, IeshSmem& S, int64_t traj, int isave, double r, double v,
-                           const IeshModel& mdl, const double* psi_re, const double* psi_im) {
+                           const IeshModel& mdl, const double* psi_re, const double* psi_im, double* zt) {
     const uint32_t obs = p.observables;
     const int n = p.n, ne = p.ne, tid = threadIdx.x, nt = blockDim.x;
     const bool last = (isave == p.nsave - 1);
@@ -267,19 +268,31 @@ NQ_D void iesh_record_save(const KParams& p, IeshSmem& S, int64_t traj, int isav
     }
     if (obs & ((1u << NQCB200_OBS_DIABATIC_POP) | (1u << NQCB200_OBS_SCATTERING_DIABATIC))) {
         // pop_i = sum_e [ (sum_a Z_ia x_ae)^2 - sum_a Z_ia^2 x_ae^2 + Z_{i,occ_e}^2 ],  x = Re psi  (iesh.jl:337-369)
+        // 16 diabatic rows of Z at a time are staged in shared memory (one division per Z entry per save point).
+        constexpr int TI = 16;
         __syncthreads();
         for (int i = tid; i < n; i += nt) S.pop[i] = 0.0;
-        __syncthreads();
-        for (int idx = tid; idx < n * ne; idx += nt) {
-            const int i = idx % n, e = idx / n;
-            double y = 0.0, q = 0.0;
-            for (int a = 0; a < n; ++a) {
-                const double z = iesh_Z(S, i, a), x = psi_re[a + (int64_t)n * e];
-                const double zx = z * x;
-                y += zx; q = fma(zx, zx, q);
+        for (int i0 = 0; i0 < n; i0 += TI) {
+            __syncthreads();
+            for (int idx = tid; idx < TI * n; idx += nt) {
+                const int ii = idx / n, a = idx % n;
+                zt[idx] = (i0 + ii < n) ? iesh_Z(S, i0 + ii, a) : 0.0;
             }
-            const double zo = iesh_Z(S, i, S.occ[e]);
-            atomicAdd(&S.pop[i], y * y - q + zo * zo);
+            __syncthreads();
+            for (int idx = tid; idx < TI * ne; idx += nt) {
+                const int ii = idx % TI, e = idx / TI;
+                if (i0 + ii >= n) continue;
+                const double* zr = zt + ii * n;
+                const double* x = psi_re + (int64_t)n * e;
+                double y = 0.0, q = 0.0;
+#pragma unroll 4
+                for (int a = 0; a < n; ++a) {
+                    const double zx = zr[a] * x[a];
+                    y += zx; q = fma(zx, zx, q);
+                }
+                const double zo = zr[S.occ[e]];
+                atomicAdd(&S.pop[i0 + ii], y * y - q + zo * zo);
+            }
         }
         __syncthreads();
         for (int i = tid; i < n; i += nt) {
@@ -338,11 +351,13 @@ NQ_D void dmma884(double& c0, double& c1, double a, double b) {
 // Horner form of the Taylor polynomial of the shifted generator A = -i dts (W - sigma) - dts G,
 //     y_K+1 = psi0 ;  y_j = psi0 + (A y_j+1) / j  (j = K..1) ;  psi' = y_1 ,  psi0 = e^{-i sigma dts} psi,
 // acting on the real matrix [X | Y] (columns 2e, 2e+1 = Re, Im of electron e).  Stages j > Kg drop the G part
-// (its contribution to psi' is below 1e-18) and are purely diagonal.  G y is accumulated with DMMA m8n8k4:
-// A fragments from G (column-major, leading dimension = 4 mod 16: conflict-free), B fragments from the y chunk
-// (row-major, same rule).  Tile ownership (12 warps = 3 per SM sub-partition, so the tensor pipes stay balanced):
-// warp w owns the R full rows of 8 states {w, w+12, ..} x all NT column tiles of the chunk, and the tiles of the
-// remaining rows are dealt out one by one as "extra" tiles (at most NX per warp).
+// (its contribution to psi' is below 1e-18) and are purely diagonal.  Every thread keeps the y elements it owns in
+// the DMMA accumulators for the whole polynomial: before stage j the accumulators are set to
+// psi0 + (D y_j+1)/j (D = diagonal part) and shared memory holds u = -(dts/j) y_j+1, so that the tensor-core product
+// c += G u leaves y_j in the accumulators.  A fragments come from G (column-major, leading dimension = 4 mod 16:
+// conflict-free), B fragments from the u chunk (row-major, same rule).  Tile ownership (12 warps = 3 per SM
+// sub-partition, so the tensor pipes stay balanced): warp w owns the R full rows of 8 states {w, w+12, ..} x all NT
+// column tiles of the chunk; the tiles of the remaining rows are dealt out one by one ("extra" tiles, <= NX per warp).
 // Returns (to every thread) the leakage  sum_{m unoccupied, e} |psi'_me|^2.
 template <int R, int NT, int NX>
 __device__ __noinline__ double iesh_propagate(const KParams& p, const IeshSmem& S, double* __restrict__ psi_re,
@@ -363,7 +378,6 @@ __device__ __noinline__ double iesh_propagate(const KParams& p, const IeshSmem& 
         for (int ch = 0; ch < L.nchunks; ++ch) {
             const int e0 = ch * ecap, e1 = min(ne, e0 + ecap);
             const int nt_act = (e1 - e0 + 3) / 4;
-            // extra tiles of this warp in this chunk
             int xrow[NX], xcol[NX];
             bool xok[NX];
 #pragma unroll
@@ -373,122 +387,103 @@ __device__ __noinline__ double iesh_propagate(const KParams& p, const IeshSmem& 
                 xrow[x] = xok[x] ? R * nwarps + g / nt_act : 0;
                 xcol[x] = xok[x] ? g % nt_act : 0;
             }
-            // chunk load: psi0 = e^{-i sigma dts} psi -> global (read back at every stage) and y = psi0 -> Bs
-            for (int idx = tid; idx < ecap * n4; idx += nt) {
-                const int i = idx % n4, el = idx / n4, e = e0 + el;
-                double x = 0.0, y = 0.0;
-                if (i < n && e < e1) {
-                    const double a = psi_re[i + (int64_t)n * e], b = psi_im[i + (int64_t)n * e];
-                    x = a * cph + b * sph; y = b * cph - a * sph;
-                    psi_re[i + (int64_t)n * e] = x; psi_im[i + (int64_t)n * e] = y;
+            double c[R > 0 ? R : 1][NT][2], cx[NX][2];
+            // f(row i, electron e, column tile t, y.re, y.im) on every element pair this thread owns
+            auto for_own = [&](auto&& f) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int i = 8 * (warp + r * nwarps) + lq;
+#pragma unroll
+                    for (int t = 0; t < NT; ++t) {
+                        const int e = e0 + 4 * t + lr4;
+                        if (t < nt_act && i < n && e < e1) f(i, e, t, c[r][t][0], c[r][t][1]);
+                    }
                 }
-                Bs[i * L.ldb + 2 * el] = x; Bs[i * L.ldb + 2 * el + 1] = y;
-            }
-            __syncthreads();
-            // one owned element pair (row i, electron e0 + 4 t + lr4): y <- psi0 + ck ((ws Y - gx) + i (-ws X - gy))
-            auto update = [&](int mtile, int t, double ck, double gx, double gy) {
-                const int i = 8 * mtile + lq, e = e0 + 4 * t + lr4;
-                if (i < n && e < e1) {
-                    const double wsi = S.ws[i];
-                    double2* bp2 = reinterpret_cast<double2*>(Bs + i * L.ldb + 8 * t + 2 * lr4);
-                    const double2 old = *bp2;
-                    const double x0 = psi_re[i + (int64_t)n * e], y0 = psi_im[i + (int64_t)n * e];
-                    *bp2 = make_double2(fma(ck, wsi * old.y - gx, x0), fma(ck, -wsi * old.x - gy, y0));
+#pragma unroll
+                for (int x = 0; x < NX; ++x) {
+                    const int i = 8 * xrow[x] + lq, e = e0 + 4 * xcol[x] + lr4;
+                    if (xok[x] && i < n && e < e1) f(i, e, xcol[x], cx[x][0], cx[x][1]);
                 }
             };
-            // diagonal-only stages (own elements only: no barrier between them)
-            for (int j = K; j > Kg; --j) {
-                const double ck = dts / j;
-#pragma unroll
-                for (int r = 0; r < R; ++r)
-#pragma unroll
-                    for (int t = 0; t < NT; ++t)
-                        if (t < nt_act) update(warp + r * nwarps, t, ck, 0.0, 0.0);
-#pragma unroll
-                for (int x = 0; x < NX; ++x)
-                    if (xok[x]) update(xrow[x], xcol[x], ck, 0.0, 0.0);
-            }
-            __syncthreads();
-            for (int j = Kg; j >= 1; --j) {
-                const double ck = dts / j;
-                double c[R > 0 ? R : 1][NT][2], cx[NX][2];
-#pragma unroll
-                for (int r = 0; r < R; ++r)
-#pragma unroll
-                    for (int t = 0; t < NT; ++t) { c[r][t][0] = 0.0; c[r][t][1] = 0.0; }
-#pragma unroll
-                for (int x = 0; x < NX; ++x) { cx[x][0] = 0.0; cx[x][1] = 0.0; }
-                // one k-slab [k0, k1) of the product, G columns read from gbase (column k0 at offset 0)
-                auto slab = [&](const double* gbase, int k0, int k1) {
-                    const double* gp = gbase + lq + L.ldg * lr4;
-                    const double* bp = Bs + lr4 * L.ldb + lq;
-#pragma unroll 2
-                    for (int k = k0; k < k1; k += 4) {
-                        const double* gk = gp + (k - k0) * L.ldg;
-                        const double* bk = bp + k * L.ldb;
-                        double a[R > 0 ? R : 1];
-#pragma unroll
-                        for (int r = 0; r < R; ++r) a[r] = gk[8 * (warp + r * nwarps)];
-#pragma unroll
-                        for (int t = 0; t < NT; ++t) {
-                            if (R > 0 && t < nt_act) {
-                                const double b = bk[8 * t];
-#pragma unroll
-                                for (int r = 0; r < R; ++r) dmma884(c[r][t][0], c[r][t][1], a[r], b);
-                            }
-                        }
-#pragma unroll
-                        for (int x = 0; x < NX; ++x)
-                            if (xok[x]) dmma884(cx[x][0], cx[x][1], gk[8 * xrow[x]], bk[8 * xcol[x]]);
-                    }
-                };
-                if (L.resident) {
-                    slab(Gs, 0, n4);
-                    __syncthreads();
-                } else {
-                    const int pieces = L.ldg * L.kb / 2;   // 16-byte pieces per slab
-                    for (int cc = tid; cc < pieces; cc += nt) cp_async16(Gs + 2 * cc, Gglob + 2 * cc);
-                    cp_async_commit();
-                    for (int s = 0; s < L.nslab; ++s) {
-                        if (s + 1 < L.nslab) {
-                            const double* src = Gglob + (int64_t)(s + 1) * L.ldg * L.kb;
-                            double* dst = Gs + ((s + 1) & 1) * L.ldg * L.kb;
-                            for (int cc = tid; cc < pieces; cc += nt) cp_async16(dst + 2 * cc, src + 2 * cc);
-                        }
-                        cp_async_commit();
-                        cp_async_wait<1>();
-                        __syncthreads();
-                        slab(Gs + (s & 1) * L.ldg * L.kb, s * L.kb, min(n4, (s + 1) * L.kb));
-                        __syncthreads();
-                    }
-                }
-#pragma unroll
-                for (int r = 0; r < R; ++r)
-#pragma unroll
-                    for (int t = 0; t < NT; ++t)
-                        if (t < nt_act) update(warp + r * nwarps, t, ck, c[r][t][0], c[r][t][1]);
-#pragma unroll
-                for (int x = 0; x < NX; ++x)
-                    if (xok[x]) update(xrow[x], xcol[x], ck, cx[x][0], cx[x][1]);
-                __syncthreads();
-            }
-            // y_1 = psi' of this chunk: every thread stores the elements it owns (+ leakage out of the occupied orbitals)
-            auto store = [&](int mtile, int t) {
-                const int i = 8 * mtile + lq, e = e0 + 4 * t + lr4;
-                if (i < n && e < e1) {
-                    const double2 y = *reinterpret_cast<const double2*>(Bs + i * L.ldb + 8 * t + 2 * lr4);
-                    psi_re[i + (int64_t)n * e] = y.x; psi_im[i + (int64_t)n * e] = y.y;
-                    if (last_sub && S.flag[i] < 0) leak += y.x * y.x + y.y * y.y;
-                }
+            // accumulators <- psi0 + (dts / j) (ws Y, -ws X) of the current y ; psi0 re-derived from global psi
+            auto diag_stage = [&](double ck) {
+                for_own([&](int i, int e, int, double& yr, double& yi) {
+                    const double a = psi_re[i + (int64_t)n * e], b = psi_im[i + (int64_t)n * e];
+                    const double w = ck * S.ws[i];
+                    const double nr = fma(w, yi, a * cph + b * sph), ni = fma(-w, yr, b * cph - a * sph);
+                    yr = nr; yi = ni;
+                });
             };
 #pragma unroll
             for (int r = 0; r < R; ++r)
 #pragma unroll
-                for (int t = 0; t < NT; ++t)
-                    if (t < nt_act) store(warp + r * nwarps, t);
+                for (int t = 0; t < NT; ++t) { c[r][t][0] = 0.0; c[r][t][1] = 0.0; }
 #pragma unroll
-            for (int x = 0; x < NX; ++x)
-                if (xok[x]) store(xrow[x], xcol[x]);
+            for (int x = 0; x < NX; ++x) { cx[x][0] = 0.0; cx[x][1] = 0.0; }
+            diag_stage(0.0);                                       // y_K+1 = psi0
+            for (int j = K; j > Kg; --j) diag_stage(dts / j);      // diagonal-only stages
+            if (Kg >= 1) {
+                for (int idx = tid; idx < n4 * L.ldb; idx += nt) Bs[idx] = 0.0;      // padding rows / columns stay zero
+                __syncthreads();
+                for (int j = Kg; j >= 1; --j) {
+                    // u = -(dts/j) y_j+1 -> shared ; accumulators = psi0 + (D y_j+1) / j
+                    const double sj = -dts / j;
+                    for_own([&](int i, int, int t, double& yr, double& yi) {
+                        *reinterpret_cast<double2*>(Bs + i * L.ldb + 8 * t + 2 * lr4) = make_double2(sj * yr, sj * yi);
+                    });
+                    diag_stage(dts / j);
+                    __syncthreads();
+                    // one k-slab [k0, k1) of c += G u, G columns read from gbase (column k0 at offset 0)
+                    auto slab = [&](const double* gbase, int k0, int k1) {
+                        const double* gp = gbase + lq + L.ldg * lr4;
+                        const double* bp = Bs + lr4 * L.ldb + lq;
+#pragma unroll 1
+                        for (int k = k0; k < k1; k += 4) {
+                            const double* gk = gp + (k - k0) * L.ldg;
+                            const double* bk = bp + k * L.ldb;
+                            double a[R > 0 ? R : 1];
+#pragma unroll
+                            for (int r = 0; r < R; ++r) a[r] = gk[8 * (warp + r * nwarps)];
+#pragma unroll
+                            for (int t = 0; t < NT; ++t) {
+                                if (R > 0 && t < nt_act) {
+                                    const double b = bk[8 * t];
+#pragma unroll
+                                    for (int r = 0; r < R; ++r) dmma884(c[r][t][0], c[r][t][1], a[r], b);
+                                }
+                            }
+#pragma unroll
+                            for (int x = 0; x < NX; ++x)
+                                if (xok[x]) dmma884(cx[x][0], cx[x][1], gk[8 * xrow[x]], bk[8 * xcol[x]]);
+                        }
+                    };
+                    if (L.resident) {
+                        slab(Gs, 0, n4);
+                        __syncthreads();
+                    } else {
+                        const int pieces = L.ldg * L.kb / 2;   // 16-byte pieces per slab
+                        for (int cc = tid; cc < pieces; cc += nt) cp_async16(Gs + 2 * cc, Gglob + 2 * cc);
+                        cp_async_commit();
+                        for (int s = 0; s < L.nslab; ++s) {
+                            if (s + 1 < L.nslab) {
+                                const double* src = Gglob + (int64_t)(s + 1) * L.ldg * L.kb;
+                                double* dst = Gs + ((s + 1) & 1) * L.ldg * L.kb;
+                                for (int cc = tid; cc < pieces; cc += nt) cp_async16(dst + 2 * cc, src + 2 * cc);
+                            }
+                            cp_async_commit();
+                            cp_async_wait<1>();
+                            __syncthreads();
+                            slab(Gs + (s & 1) * L.ldg * L.kb, s * L.kb, min(n4, (s + 1) * L.kb));
+                            __syncthreads();
+                        }
+                    }
+                }
+            }
+            // y_1 = psi' of this chunk: every thread stores the elements it owns (+ leakage out of the occupied orbitals)
+            for_own([&](int i, int e, int, double& yr, double& yi) {
+                psi_re[i + (int64_t)n * e] = yr; psi_im[i + (int64_t)n * e] = yi;
+                if (last_sub && S.flag[i] < 0) leak += yr * yr + yi * yi;
+            });
             __syncthreads();
         }
     }
@@ -635,7 +630,7 @@ __global__ void __launch_bounds__(384, 1) iesh_step_kernel(const __grid_constant
     double* Hs = S.work + L.off_hop;                       // hop phase
     double* Gglob = L.resident ? nullptr : p.iesh_G + (int64_t)blockIdx.x * L.ldg * L.kb * L.nslab;
     if (L.resident) for (int idx = tid; idx < L.ldg * n4; idx += nt) Gs[idx] = 0.0;
-    unsigned long long nhops = 0, nfrus = 0, nunpruned = 0;
+    unsigned long long nhops = 0, nfrus = 0, nunpruned = 0, ndet = 0, nstages = 0, ngemm = 0;
 
     for (int64_t traj = blockIdx.x; traj < p.ntraj; traj += gridDim.x) {
         double* psi_re = p.sig_re + traj * (int64_t)n * ne;
@@ -703,12 +698,14 @@ __global__ void __launch_bounds__(384, 1) iesh_step_kernel(const __grid_constant
                     term *= rho / K;
                 }
             }
+            nstages += (tid == 0) ? (unsigned long long)K * nsub : 0ull;
+            ngemm += (tid == 0) ? (unsigned long long)Kg * nsub : 0ull;
             __syncthreads();
 
             double leak;
-            if (L.rounds == 0) leak = iesh_propagate<0, 1, 4>(p, S, psi_re, psi_im, Gs, Bs, Gglob, sigma, dts, nsub, K, Kg);
-            else if (L.rounds == 1) leak = iesh_propagate<1, 16, 4>(p, S, psi_re, psi_im, Gs, Bs, Gglob, sigma, dts, nsub, K, Kg);
-            else leak = iesh_propagate<2, 8, 4>(p, S, psi_re, psi_im, Gs, Bs, Gglob, sigma, dts, nsub, K, Kg);
+            if (L.rounds == 0) leak = iesh_propagate<0, 1, 2>(p, S, psi_re, psi_im, Gs, Bs, Gglob, sigma, dts, nsub, K, Kg);
+            else if (L.rounds == 1) leak = iesh_propagate<1, 16, 2>(p, S, psi_re, psi_im, Gs, Bs, Gglob, sigma, dts, nsub, K, Kg);
+            else leak = iesh_propagate<2, 8, 2>(p, S, psi_re, psi_im, Gs, Bs, Gglob, sigma, dts, nsub, K, Kg);
             __syncthreads();
 
             // ---- IESHCallback: hop test (iesh.jl:231-335,390-407) ----------------------------------
@@ -726,6 +723,7 @@ __global__ void __launch_bounds__(384, 1) iesh_step_kernel(const __grid_constant
                     if (d2lo > 0.0) certainly_pruned = 2.8284271247461903 * dt * sabs / sqrt(d2lo) * (1.0 + 1e-9) < xi;
                 }
                 if (!certainly_pruned) {
+                ndet += (tid == 0);
                 double det_re, det_im;
                 const int nep8 = 8 * ((ne + 3) & ~3);
                 if (ne <= 64) iesh_det_lu<4, 3, true>(p, S, psi_re, psi_im, Hs, Hs + nep8, det_re, det_im);      // 16 x 24 threads
@@ -913,7 +911,7 @@ __global__ void __launch_bounds__(384, 1) iesh_step_kernel(const __grid_constant
             // ---- save (after the callback) ---------------------------------------------
             if ((step + 1) % p.save_every == 0) {
                 const int64_t isave = (step + 1) / p.save_every;
-                if (isave < p.nsave) iesh_record_save(p, S, traj, (int)isave, r, v, mdl, psi_re, psi_im);
+                if (isave < p.nsave) iesh_record_save(p, S, traj, (int)isave, r, v, mdl, psi_re, psi_im, Bs);
             }
         }
         __syncthreads();
@@ -936,6 +934,9 @@ __global__ void __launch_bounds__(384, 1) iesh_step_kernel(const __grid_constant
         if (nhops) atomicAdd(&p.counters[0], nhops);
         if (nfrus) atomicAdd(&p.counters[1], nfrus);
         if (nunpruned) atomicAdd(&p.counters[3], nunpruned);
+        atomicAdd(&p.counters[4], ndet);
+        atomicAdd(&p.counters[5], nstages);
+        atomicAdd(&p.counters[6], ngemm);
     }
 }
 
@@ -977,7 +978,7 @@ __global__ void __launch_bounds__(384, 1) iesh_init_kernel(const __grid_constant
         for (int e = tid; e < ne; e += nt) { const double z = S.z0[S.occ[e]]; part += z * z; }
         const double occsum = iesh_block_sum(part, S.red);
         if (tid == 0) p.acc[traj] = (-du0 - dh * occsum) / mdl.mass;
-        iesh_record_save(p, S, traj, 0, r, v, mdl, psi_re, psi_im);
+        iesh_record_save(p, S, traj, 0, r, v, mdl, psi_re, psi_im, S.work + p.iesh.off_b);
         {
             // are the orbitals orthonormal?  (enables the determinant-free pruning bound of the step kernel)
             double dev = 0.0;

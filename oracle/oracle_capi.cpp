@@ -461,11 +461,15 @@ int nqco_get_counters(nqco_handle* h, int64_t* steps, int64_t* hops, int64_t* fr
     return NQCB200_OK;
 }
 
-int nqco_get_hop_search_count(nqco_handle* h, int64_t* searches) {
-    if (!h || !searches) return NQCB200_ERR_INVALID;
-    int64_t s = 0;
-    for (const Trajectory& tr : h->traj) s += tr.cnt.hop_searches;
-    *searches = s;
+int nqco_get_iesh_stats(nqco_handle* h, int64_t* hop_searches, int64_t* determinants, int64_t* taylor_stages,
+                        int64_t* gemm_stages) {
+    if (!h) return NQCB200_ERR_INVALID;
+    int64_t s = 0, st = 0;
+    for (const Trajectory& tr : h->traj) { s += tr.cnt.hop_searches; st += tr.cnt.steps; }
+    if (hop_searches) *hop_searches = s;
+    if (determinants) *determinants = (h->S.cfg.method == NQCB200_METHOD_IESH && !h->S.cfg.disable_hopping) ? st : 0;
+    if (taylor_stages) *taylor_stages = 0;   // the oracle follows the reference: dense Hermitian eigendecomposition
+    if (gemm_stages) *gemm_stages = 0;
     return NQCB200_OK;
 }
 

@@ -20,3 +20,5 @@ for i in range(launches):
     e.run(nsteps)
     ms, nl = e.last_run_timing()
     print(f"launch {i}: {ms:.3f} ms, {T * nsteps / ms * 1e3:.4g} traj-steps/s")
+if wl.method == A.METHOD_IESH:
+    print(e.iesh_stats(), e.counters())
