@@ -387,8 +387,10 @@ __device__ __noinline__ double iesh_propagate(const KParams& p, const IeshSmem& 
                 xrow[x] = xok[x] ? R * nwarps + g / nt_act : 0;
                 xcol[x] = xok[x] ? g % nt_act : 0;
             }
-            double c[R > 0 ? R : 1][NT][2], cx[NX][2];
-            // f(row i, electron e, column tile t, y.re, y.im) on every element pair this thread owns
+            double c[R > 0 ? R : 1][NT][2], cx[NX][2];       // y (DMMA accumulators)
+            double q[R > 0 ? R : 1][NT][2], qx[NX][2];       // psi0 = e^{-i sigma dts} psi of the same elements
+            double wr[R > 0 ? R : 1], wx[NX];                // w_i - sigma of the owned rows
+            // f(row i, electron e, column tile t, y.re, y.im, psi0.re, psi0.im, ws) on every element pair this thread owns
             auto for_own = [&](auto&& f) {
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
@@ -396,39 +398,51 @@ __device__ __noinline__ double iesh_propagate(const KParams& p, const IeshSmem& 
 #pragma unroll
                     for (int t = 0; t < NT; ++t) {
                         const int e = e0 + 4 * t + lr4;
-                        if (t < nt_act && i < n && e < e1) f(i, e, t, c[r][t][0], c[r][t][1]);
+                        if (t < nt_act && i < n && e < e1) f(i, e, t, c[r][t][0], c[r][t][1], q[r][t][0], q[r][t][1], wr[r]);
                     }
                 }
 #pragma unroll
                 for (int x = 0; x < NX; ++x) {
                     const int i = 8 * xrow[x] + lq, e = e0 + 4 * xcol[x] + lr4;
-                    if (xok[x] && i < n && e < e1) f(i, e, xcol[x], cx[x][0], cx[x][1]);
+                    if (xok[x] && i < n && e < e1) f(i, e, xcol[x], cx[x][0], cx[x][1], qx[x][0], qx[x][1], wx[x]);
                 }
             };
-            // accumulators <- psi0 + (dts / j) (ws Y, -ws X) of the current y ; psi0 re-derived from global psi
+            // accumulators <- psi0 + ck (ws Y, -ws X) of the current y
             auto diag_stage = [&](double ck) {
-                for_own([&](int i, int e, int, double& yr, double& yi) {
-                    const double a = psi_re[i + (int64_t)n * e], b = psi_im[i + (int64_t)n * e];
-                    const double w = ck * S.ws[i];
-                    const double nr = fma(w, yi, a * cph + b * sph), ni = fma(-w, yr, b * cph - a * sph);
+                for_own([&](int, int, int, double& yr, double& yi, double& pr, double& pi, double& w) {
+                    const double nr = fma(ck * w, yi, pr), ni = fma(-ck * w, yr, pi);
                     yr = nr; yi = ni;
                 });
             };
 #pragma unroll
-            for (int r = 0; r < R; ++r)
+            for (int r = 0; r < R; ++r) {
+                const int i = 8 * (warp + r * nwarps) + lq;
+                wr[r] = (i < n) ? S.ws[i] : 0.0;
 #pragma unroll
-                for (int t = 0; t < NT; ++t) { c[r][t][0] = 0.0; c[r][t][1] = 0.0; }
+                for (int t = 0; t < NT; ++t) { c[r][t][0] = 0.0; c[r][t][1] = 0.0; q[r][t][0] = 0.0; q[r][t][1] = 0.0; }
+            }
 #pragma unroll
-            for (int x = 0; x < NX; ++x) { cx[x][0] = 0.0; cx[x][1] = 0.0; }
-            diag_stage(0.0);                                       // y_K+1 = psi0
+            for (int x = 0; x < NX; ++x) {
+                const int i = 8 * xrow[x] + lq;
+                wx[x] = (i < n) ? S.ws[i] : 0.0;
+                cx[x][0] = 0.0; cx[x][1] = 0.0; qx[x][0] = 0.0; qx[x][1] = 0.0;
+            }
+            for_own([&](int i, int e, int, double& yr, double& yi, double& pr, double& pi, double&) {
+                const double a = psi_re[i + (int64_t)n * e], b = psi_im[i + (int64_t)n * e];
+                pr = a * cph + b * sph; pi = b * cph - a * sph;
+                yr = pr; yi = pi;                                  // y_K+1 = psi0
+            });
             for (int j = K; j > Kg; --j) diag_stage(dts / j);      // diagonal-only stages
             if (Kg >= 1) {
-                for (int idx = tid; idx < n4 * L.ldb; idx += nt) Bs[idx] = 0.0;      // padding rows / columns stay zero
+                // rows / columns of the u chunk that nobody owns must be zero: the k padding rows and the electron padding
+                for (int idx = tid; idx < (n4 - n) * L.ldb; idx += nt) Bs[n * L.ldb + idx] = 0.0;
+                if (e1 - e0 < 4 * nt_act)
+                    for (int idx = tid; idx < n * 8; idx += nt) Bs[(idx >> 3) * L.ldb + 8 * (nt_act - 1) + (idx & 7)] = 0.0;
                 __syncthreads();
                 for (int j = Kg; j >= 1; --j) {
                     // u = -(dts/j) y_j+1 -> shared ; accumulators = psi0 + (D y_j+1) / j
                     const double sj = -dts / j;
-                    for_own([&](int i, int, int t, double& yr, double& yi) {
+                    for_own([&](int i, int, int t, double& yr, double& yi, double&, double&, double&) {
                         *reinterpret_cast<double2*>(Bs + i * L.ldb + 8 * t + 2 * lr4) = make_double2(sj * yr, sj * yi);
                     });
                     diag_stage(dts / j);
@@ -437,7 +451,7 @@ __device__ __noinline__ double iesh_propagate(const KParams& p, const IeshSmem& 
                     auto slab = [&](const double* gbase, int k0, int k1) {
                         const double* gp = gbase + lq + L.ldg * lr4;
                         const double* bp = Bs + lr4 * L.ldb + lq;
-#pragma unroll 1
+#pragma unroll 2
                         for (int k = k0; k < k1; k += 4) {
                             const double* gk = gp + (k - k0) * L.ldg;
                             const double* bk = bp + k * L.ldb;
@@ -480,7 +494,7 @@ __device__ __noinline__ double iesh_propagate(const KParams& p, const IeshSmem& 
                 }
             }
             // y_1 = psi' of this chunk: every thread stores the elements it owns (+ leakage out of the occupied orbitals)
-            for_own([&](int i, int e, int, double& yr, double& yi) {
+            for_own([&](int i, int e, int, double& yr, double& yi, double&, double&, double&) {
                 psi_re[i + (int64_t)n * e] = yr; psi_im[i + (int64_t)n * e] = yi;
                 if (last_sub && S.flag[i] < 0) leak += yr * yr + yi * yi;
             });
@@ -704,7 +718,7 @@ __global__ void __launch_bounds__(384, 1) iesh_step_kernel(const __grid_constant
 
             double leak;
             if (L.rounds == 0) leak = iesh_propagate<0, 1, 2>(p, S, psi_re, psi_im, Gs, Bs, Gglob, sigma, dts, nsub, K, Kg);
-            else if (L.rounds == 1) leak = iesh_propagate<1, 16, 2>(p, S, psi_re, psi_im, Gs, Bs, Gglob, sigma, dts, nsub, K, Kg);
+            else if (L.rounds == 1) leak = iesh_propagate<1, 14, 2>(p, S, psi_re, psi_im, Gs, Bs, Gglob, sigma, dts, nsub, K, Kg);
             else leak = iesh_propagate<2, 8, 2>(p, S, psi_re, psi_im, Gs, Bs, Gglob, sigma, dts, nsub, K, Kg);
             __syncthreads();
 

@@ -18,7 +18,7 @@ bool iesh_plan(int n, int ne, size_t smem_max, IeshLayout& L) {
     L.ldg = pad16_4(8 * L.nrt);
     const int n4 = (n + 3) & ~3;
     const int nt_need = (ne + 3) / 4;                 // column tiles for all electrons
-    int nt_max = (L.rounds <= 1) ? 16 : 8;            // accumulator tiles per warp (register budget)
+    int nt_max = (L.rounds <= 1) ? 14 : 8;            // accumulator tiles per warp (register budget)
     if (rem_rows > 0) nt_max = std::min(nt_max, (2 * nwarps) / rem_rows);   // at most 2 extra tiles per warp
     if (nt_max < 1) return false;
     L.lds = ne | 1;

@@ -22,3 +22,11 @@ tot = sum(samples.values())
 print("total samples", tot)
 for ln, s in samples.most_common(top):
     print(f"{100*s/tot:5.1f}%  {insts[ln]/1e6:9.1f}M  {ln[0][:28]:28s} L{ln[1]:4d}  {src[ln]}")
+
+# optional phase table: src_hotspots.py FILE TOP name:lo-hi,name:lo-hi,...
+if len(sys.argv) > 3:
+    print("--- phases")
+    for spec in sys.argv[3].split(','):
+        name, rng = spec.split(':'); lo, hi = map(int, rng.split('-'))
+        s = sum(v for (f, ln), v in samples.items() if lo <= ln <= hi)
+        print(f"{name:14s} {100*s/tot:5.1f}%")
