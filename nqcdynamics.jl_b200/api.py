@@ -12,6 +12,7 @@ Every trajectory is stepped on the GPU by ``libnqcb200.so``; there is no CPU pat
 """
 from __future__ import annotations
 
+import math
 import threading
 from dataclasses import dataclass, field
 from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple, Union
@@ -170,6 +171,41 @@ class PureState:
 
 
 @dataclass
+class FermiDiracState:
+    """``FermiDiracState(fermi_level, temperature)`` in the adiabatic basis (NQCDistributions; used by AdiabaticIESH,
+    iesh.jl:99-128): occupations drawn by the reference's Metropolis walk over orbital swaps
+    (``sample_fermi_dirac_distribution``, DynamicsUtils.jl:194-208, Boltzmann-factor variant)."""
+    fermi_level: float = 0.0
+    temperature: float = 0.0            # k_B T in hartree (atomic units, k_B = 1)
+    statetype: Any = field(default_factory=Adiabatic)
+
+    def __mul__(self, other):
+        return ProductDistribution(other, self)
+
+    __rmul__ = __mul__
+
+    @property
+    def β(self) -> float:
+        return math.inf if self.temperature == 0.0 else 1.0 / self.temperature
+
+    def sample_occupations(self, rng, energies: np.ndarray, nelectrons: int) -> np.ndarray:
+        """1-based sorted occupied adiabatic orbitals for one trajectory."""
+        nstates = len(energies)
+        state = list(range(nelectrons))
+        beta = self.β
+        for _ in range(nstates * nelectrons):
+            k = int(rng.integers(0, nelectrons))
+            i = state[k]
+            free = np.setdiff1d(np.arange(nstates), state, assume_unique=True)
+            j = int(free[rng.integers(0, len(free))])
+            de = energies[j] - energies[i]
+            prob = (1.0 if de <= 0 else 0.0) if math.isinf(beta) else math.exp(min(700.0, -beta * de))
+            if prob > rng.random():
+                state[k] = j
+        return np.sort(np.asarray(state, dtype=np.int32)) + 1
+
+
+@dataclass
 class DynamicalDistribution:
     """``DynamicalDistribution(velocity, position, size)``: each entry a number, an array (broadcast over
     trajectories or indexed by trajectory on the leading axis) or a samplable distribution."""
@@ -215,7 +251,7 @@ class DynamicalDistribution:
 @dataclass
 class ProductDistribution:
     nuclear: DynamicalDistribution
-    electronic: PureState
+    electronic: Any                      # PureState | FermiDiracState
 
 
 # ---- outputs (src/DynamicsOutputs.jl, src/TimeCorrelationFunctions.jl) ----------------------------
@@ -282,7 +318,8 @@ def _shape_series(sim, out: _Output, arr: np.ndarray):
     if out.obs in (A.OBS_POPCORR_DIABATIC, A.OBS_POPCORR_ADIABATIC):
         return arr.reshape(-1, n, n).transpose(0, 2, 1)          # column-major (i, j) per frame
     if out.obs == A.OBS_SIGMA:
-        c = arr.reshape(-1, 2, n, n)
+        ncol = sim.model.nelectrons if sim.method.method_id == A.METHOD_IESH else n      # psi is (n, ne) for IESH
+        c = arr.reshape(-1, 2, ncol, n)
         return (c[:, 0] + 1j * c[:, 1]).transpose(0, 2, 1)
     if out.obs in (A.OBS_POSITION, A.OBS_VELOCITY):
         return arr.reshape((-1,) + tuple(reversed(sim.size[:2]))).transpose(0, 2, 1)   # (nsave, ndofs, natoms)
@@ -301,6 +338,8 @@ def _finalise(sim, out: _Output, arr: np.ndarray, per_trajectory: bool):
         if not per_trajectory:
             raise ValueError("OutputSurfaceHops needs per-trajectory states (use SortByTrajectoryReduction)")
         st = np.rint(arr).astype(np.int64)
+        if sim.method.method_id == A.METHOD_IESH:
+            st = np.sort(st, axis=1)        # the occupation vector is a set (an accepted hop is not re-sorted, iesh.jl:399-407)
         return int(np.count_nonzero(np.any(st[1:] != st[:-1], axis=1)))
     val = _shape_series(sim, out, arr)
     if out.obs == A.OBS_DISCRETE_STATE:
@@ -350,6 +389,24 @@ def run_dynamics(sim: Simulation, tspan, distribution, *, output, selection: Opt
     density = method.method_id in (A.METHOD_FSSH, A.METHOD_EHRENFEST)
     if density and electronic is None:
         raise ValueError("FSSH / Ehrenfest need an electronic distribution: nuclear * PureState(i)")
+    iesh = method.method_id == A.METHOD_IESH
+    psi0 = occ0 = None
+    if iesh:
+        # DynamicsVariables(sim, v, r) -> the ne lowest adiabatic orbitals (iesh.jl:89-97);
+        # DynamicsVariables(sim, v, r, FermiDiracState) -> sampled occupations (iesh.jl:99-128)
+        n, ne = model.nstates, model.nelectrons
+        if electronic is None:
+            occ0 = np.tile(np.arange(1, ne + 1, dtype=np.int32), (T, 1))
+        elif isinstance(electronic, FermiDiracState):
+            if abs(electronic.fermi_level - getattr(model, "fermi_level", 0.0)) > 1e-12:
+                raise ValueError("Fermi level of model and distribution do not match")          # iesh.jl:105-112
+            occ0 = np.empty((T, ne), dtype=np.int32)
+            for t in range(T):
+                occ0[t] = electronic.sample_occupations(rng, model.adiabatic_energies(r[t].reshape(-1)), ne)
+        else:
+            raise TypeError("AdiabaticIESH takes no electronic distribution (ground state) or a FermiDiracState")
+        psi0 = np.zeros((T, ne, n))
+        psi0[np.arange(T)[:, None], np.arange(ne)[None, :], occ0 - 1] = 1.0
 
     ngpus = max(1, int(alg.ngpus))
     if ngpus > device_count():
@@ -386,6 +443,8 @@ def run_dynamics(sim: Simulation, tspan, distribution, *, output, selection: Opt
                         eng.set_state(rg, vg, rho, None, state)
                     else:
                         eng.set_state_diabatic(rg, vg, rho)
+                elif iesh:
+                    eng.set_state(rg, vg, psi0[lo:hi], None, occ0[lo:hi])
                 else:
                     eng.set_state(rg, vg)
                 if draws is not None:

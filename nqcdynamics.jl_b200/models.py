@@ -30,6 +30,20 @@ class Model:
     classical: bool = False
     fermi_level: float = 0.0
 
+    def adiabatic_energies(self, r) -> np.ndarray:
+        """Eigenvalues of the diabatic Hamiltonian at one configuration -- host-side, used ONLY to draw Fermi-Dirac
+        initial occupations (the reference does the same inside sample_distribution, iesh.jl:114-120)."""
+        if self.kind != _abi.MODEL_ANDERSON_HOLSTEIN_MIAO_SUBOTNIK:
+            raise NotImplementedError("adiabatic_energies: only needed for AndersonHolstein initial conditions")
+        m, w, g, dG = self.params
+        q = float(np.asarray(r).reshape(-1)[0])
+        n = self.nstates
+        H = np.zeros((n, n))
+        H[0, 0] = 0.5 * m * w * w * (q - g) ** 2 + dG - 0.5 * m * w * w * q * q
+        H[np.arange(1, n), np.arange(1, n)] = self.bath_a
+        H[0, 1:] = H[1:, 0] = self.bath_b
+        return np.linalg.eigvalsh(H)
+
 
 def TullyModelOne(a=0.01, b=1.6, c=0.005, d=1.0) -> Model:
     return Model(_abi.MODEL_TULLY_ONE, 2, (a, b, c, d), name="TullyModelOne")

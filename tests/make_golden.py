@@ -46,6 +46,13 @@ def cases():
                                  temperature=9.5e-4, save_every=20, nsave=11, observables=ALL_POP_OBS), nsteps=200,
                                  r=rng.normal(2.1, 0.1, (T, 16, 1)), v=np.sqrt(9.5e-4 * 16 / 20000) * rng.standard_normal((T, 16, 1)),
                                  state0=0)
+    # C4 (test-sized, test/Dynamics/iesh.jl:17-30): AdiabaticIESH, 31 states / 15 electrons, ground-state orbitals
+    ah = nq.AndersonHolstein(nq.MiaoSubotnik(Γ=6.4e-3), nq.TrapezoidalRule(30, -0.0192, 0.0192))
+    out["iesh_m30"] = dict(model=ah, kw=dict(method=A.METHOD_IESH, masses=[2000.0], dt=5.0, save_every=5, nsave=9,
+                           observables=(1 << A.OBS_ADIABATIC_POP) | (1 << A.OBS_DIABATIC_POP) | (1 << A.OBS_TOTAL_ENERGY) |
+                                       (1 << A.OBS_DISCRETE_STATE)), nsteps=40,
+                           r=rng.normal(12.0, 4.0, (T, 1, 1)), v=-np.abs(rng.standard_normal((T, 1, 1))) * 8e-3, state0="iesh",
+                           draw_scale=2e-4)
     return out, T, rng
 
 
@@ -55,6 +62,11 @@ def run_case(make, case, T, draws, sdraw):
     h = make(cfg, keep)
     if case["state0"] is None:
         h.set_state(case["r"], case["v"])
+    elif case["state0"] == "iesh":
+        n, ne = case["model"].nstates, case["model"].nelectrons
+        psi = np.zeros((T, ne, n)); psi[:, np.arange(ne), np.arange(ne)] = 1.0
+        h.set_state(case["r"], case["v"], psi, None, np.tile(np.arange(1, ne + 1, dtype=np.int32), (T, 1)))
+        h.set_draws(draws)
     else:
         n = case["model"].nstates
         rho = np.zeros((T, n, n)); rho[:, case["state0"], case["state0"]] = 1.0
@@ -72,8 +84,11 @@ def run_case(make, case, T, draws, sdraw):
 
 if __name__ == "__main__":
     cs, T, rng = cases()
+    only = set(sys.argv[1:])
     for name, case in cs.items():
-        draws = rng.random((case["nsteps"], T)); sdraw = rng.random(T)
+        draws = rng.random((case["nsteps"], T)) * case.get("draw_scale", 1.0); sdraw = rng.random(T)
+        if only and name not in only:
+            continue
         res = run_case(lambda c, k: oracle.OracleEngine(c, k), case, T, draws, sdraw)
         np.savez_compressed(os.path.join(HERE, "golden", f"engine_{name}.npz"), draws=draws, sdraw=sdraw,
                             r0=case["r"], v0=case["v"], **res)

@@ -12,7 +12,8 @@ pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-@pytest.mark.parametrize("name", ["tully1_fssh", "spinboson_fssh", "spinboson_ehrenfest", "rpmd_harmonic32", "rpsh_morse3_16"])
+@pytest.mark.parametrize("name", ["tully1_fssh", "spinboson_fssh", "spinboson_ehrenfest", "rpmd_harmonic32", "rpsh_morse3_16",
+                                  "iesh_m30"])
 def test_engine_reproduces_golden(name):
     cs, T, _ = make_golden.cases()
     g = np.load(os.path.join(GOLDEN, f"engine_{name}.npz"))

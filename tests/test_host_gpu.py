@@ -76,3 +76,30 @@ def test_ehrenfest_and_rpmd_through_host_api():
     E = np.array([t["OutputTotalEnergy"] for t in r2])
     assert np.max(np.abs(E - E[:, :1])) < 1e-3 * np.max(np.abs(E))
     assert r2[0]["OutputCentroidPosition"].shape == (21, 1, 1)
+
+
+def test_run_dynamics_iesh_ground_state_and_fermi_dirac():
+    """Simulation{AdiabaticIESH} through run_dynamics: ground-state DynamicsVariables (iesh.jl:89-97) and
+    FermiDiracState occupations (iesh.jl:99-128); output shapes as in the reference (psi is n x ne)."""
+    model = nq.AndersonHolstein(nq.MiaoSubotnik(Γ=6.4e-3), nq.TrapezoidalRule(30, -0.0192, 0.0192))
+    sim = nq.Simulation[nq.AdiabaticIESH](nq.Atoms(2000), model)
+    n, ne, T = model.nstates, model.nelectrons, 12
+    dist = nq.DynamicalDistribution(nq.Normal(0.0, 7e-4), nq.Normal(21.0, 1.0), (1, 1))
+    out = nq.run_dynamics(sim, (0.0, 50.0), dist, output=(nq.OutputQuantumSubsystem, nq.OutputDiscreteState,
+                                                          nq.OutputTotalEnergy, nq.OutputSurfaceHops),
+                          trajectories=T, dt=5.0, seed=3)
+    assert len(out) == T and out[0]["OutputQuantumSubsystem"].shape == (11, n, ne)
+    assert np.array_equal(out[0]["OutputDiscreteState"][0], np.arange(1, ne + 1))
+    psi = out[3]["OutputQuantumSubsystem"][-1]
+    assert np.allclose(np.sum(np.abs(psi) ** 2, axis=0), 1.0, atol=1e-12)
+    E = np.array([tr["OutputTotalEnergy"] for tr in out])
+    assert np.max(np.abs(E - E[:, :1])) < 1e-5           # no hops accepted without energy conservation
+    hot = nq.run_dynamics(sim, (0.0, 20.0), dist * nq.FermiDiracState(0.0, 9.5e-4), output=nq.OutputDiscreteState,
+                          trajectories=T, dt=5.0, seed=4)
+    occ0 = np.array([tr["OutputDiscreteState"][0] for tr in hot])
+    assert occ0.shape == (T, ne) and np.all(np.diff(occ0, axis=1) > 0) and np.any(occ0 != np.arange(1, ne + 1))
+    mean = nq.run_dynamics(sim, (0.0, 20.0), dist, output=(nq.OutputDiabaticPopulation, nq.OutputAdiabaticPopulation),
+                           reduction=nq.MeanReduction(), trajectories=T, dt=5.0, seed=5)
+    assert mean["OutputAdiabaticPopulation"].shape == (5, n)
+    assert np.allclose(mean["OutputAdiabaticPopulation"].sum(axis=1), ne)
+    assert np.allclose(mean["OutputDiabaticPopulation"].sum(axis=1), ne, atol=1e-9)

@@ -402,3 +402,70 @@ def test_symmetric_eigensolvers_agree_with_numpy():
             assert np.allclose(w, np.linalg.eigvalsh(M), atol=1e-11)
             assert np.allclose(Z.T @ M @ Z, np.diag(w), atol=1e-10)
             assert np.allclose(Z.T @ Z, np.eye(n), atol=1e-12)
+
+
+def _iesh_oracle(M, T, dt, nsteps, **extra):
+    import nqcdynamics_jl_b200 as nq
+    from helpers import A, model_config
+    model = nq.AndersonHolstein(nq.MiaoSubotnik(Γ=6.4e-3), nq.TrapezoidalRule(M, -0.0192, 0.0192))
+    kw = model_config(model, method=A.METHOD_IESH, masses=[2000.0], ntraj=T, dt=dt, rng=A.RNG_INJECTED, save_every=1,
+                      nsave=nsteps + 1, per_trajectory=1, diagnostics=1,
+                      observables=(1 << A.OBS_TOTAL_ENERGY) | (1 << A.OBS_KINETIC) | (1 << A.OBS_POTENTIAL) |
+                                  (1 << A.OBS_DISCRETE_STATE) | (1 << A.OBS_ADIABATIC_POP) | (1 << A.OBS_DIABATIC_POP))
+    kw.update(extra)
+    cfg, keep = A.make_config(**kw)
+    return model, oracle.OracleEngine(cfg, keep)
+
+
+def test_iesh_hop_conserves_energy():
+    """test/Dynamics/iesh.jl:122-152: across an accepted hop dKE = -dE and the Hamiltonian is unchanged."""
+    from helpers import A
+    M, T, nsteps = 30, 6, 60
+    rng = np.random.default_rng(31)
+    model, h = _iesh_oracle(M, T, 0.02, nsteps)
+    n, ne = model.nstates, model.nelectrons
+    psi = np.zeros((T, ne, n), dtype=complex)
+    for t in range(T):
+        q, _ = np.linalg.qr(np.eye(n, ne) + 0.3 * np.linalg.qr(rng.standard_normal((n, ne)) + 1j * rng.standard_normal((n, ne)))[0])
+        psi[t] = q.T
+    state = np.tile(np.arange(1, ne + 1, dtype=np.int32), (T, 1))
+    h.set_state(5.0 + 10.0 * rng.random(T), -np.abs(rng.standard_normal(T)) * 8e-3, psi.real, psi.imag, state)
+    h.set_draws(rng.random((nsteps, T)) * 2e-6)         # tiny draws: a hop is attempted on almost every step
+    h.run(nsteps)
+    c = h.counters()
+    assert c["hops"] > 5, c
+    E = h.observable_per_trajectory(A.OBS_TOTAL_ENERGY)[:, :, 0]
+    KE = h.observable_per_trajectory(A.OBS_KINETIC)[:, :, 0]
+    PE = h.observable_per_trajectory(A.OBS_POTENTIAL)[:, :, 0]
+    occ = np.sort(np.rint(h.observable_per_trajectory(A.OBS_DISCRETE_STATE)).astype(int), axis=2)
+    hopped = np.any(occ[:, 1:] != occ[:, :-1], axis=2)
+    assert hopped.sum() == c["hops"]
+    # dt = 0.02: the integration error (incl. the force that is not refreshed after a hop) is ~1e-8, hop gaps are ~1e-3
+    assert np.max(np.abs(E - E[:, :1])) < 1e-6
+    dKE, dPE = np.diff(KE, axis=1)[hopped], np.diff(PE, axis=1)[hopped]
+    assert np.all(np.abs(dPE) > 1e-5) and np.allclose(dKE, -dPE, rtol=1e-3)
+    # populations: ne electrons in total in either representation; adiabatic occupations are 0/1 (iesh.jl:371-375)
+    adi = h.observable_per_trajectory(A.OBS_ADIABATIC_POP); dia = h.observable_per_trajectory(A.OBS_DIABATIC_POP)
+    assert np.allclose(adi.sum(axis=2), ne) and set(np.unique(adi)) <= {0.0, 1.0}
+    assert np.allclose(dia.sum(axis=2), ne, atol=1e-9)
+
+
+def test_iesh_ground_state_overlap_and_pruning():
+    """test/Dynamics/iesh.jl:87-109: for the ground-state DynamicsVariables the overlap is the identity (det S = 1), so
+    with zero velocity every hopping probability vanishes and a pruned and an unpruned run agree exactly."""
+    from helpers import A
+    M, T, nsteps = 30, 3, 5
+    outs = []
+    for est in (1, 0):
+        model, h = _iesh_oracle(M, T, 1.0, nsteps, estimate_probability=est)
+        n, ne = model.nstates, model.nelectrons
+        psi = np.zeros((T, ne, n)); psi[:, np.arange(ne), np.arange(ne)] = 1.0
+        state = np.tile(np.arange(1, ne + 1, dtype=np.int32), (T, 1))
+        h.set_state(np.array([3.0, 12.0, 21.0]), np.array([1e-4, -2e-4, 3e-4]), psi, None, state)
+        h.set_draws(np.full((nsteps, T), 0.5))
+        h.run(nsteps)
+        outs.append((h.get_state(), h.counters(), h.hop_search_count()))
+    (s1, c1, n1), (s0, c0, n0) = outs
+    assert n1 == 0 and n0 == nsteps * T and c1["hops"] == c0["hops"] == 0
+    assert np.array_equal(s1["sigma"], s0["sigma"]) and np.array_equal(s1["r"], s0["r"])
+    assert np.allclose(np.abs(np.linalg.det(s1["sigma"][:, :ne, :])), 1.0, atol=1e-6)     # still close to adiabatic
