@@ -82,6 +82,7 @@ struct KParams {
     double* pop0;   // [2n][T] initial diabatic / adiabatic population (correlation functions)
     double* qmap;   // [B*n][T]
     double* pmap;
+    double* sb_carry; // [2][T]  SpinBoson thread-per-trajectory kernel: force scalars (A, B) carried between launches
     // AdiabaticIESH: psi / occupations are TRAJECTORY-major ([T][n*ne], [T][ne]); see kernel_iesh.cuh
     IeshLayout iesh;
     double* iesh_lam;   // [T][n]   adiabatic energies of the last step (warm start of the root finder)

@@ -443,6 +443,14 @@ int nqcb200_create(const nqcb200_config* cfg, nqcb200_handle** out) {
         if ((rc = dev_alloc(h, &kp.ecur, (size_t)(n + n * n) * T)) != 0) return fail(rc);
         if ((rc = dev_alloc(h, &kp.pop0, (size_t)2 * n * T)) != 0) return fail(rc);
     }
+    if (ks.needs_sb_carry) {
+        if ((rc = dev_alloc(h, &kp.sb_carry, (size_t)2 * T)) != 0) return fail(rc);
+    }
+    if (ks.step_smem > 48 * 1024) {
+        if (cudaFuncSetAttribute((const void*)ks.step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ks.step_smem) != cudaSuccess) {
+            h->err = "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) for the step kernel"; cudaGetLastError(); return fail(NQCB200_ERR_CUDA);
+        }
+    }
     if (iesh) {
         if ((rc = dev_alloc(h, &kp.iesh_lam, (size_t)n * T)) != 0) return fail(rc);
         if ((rc = dev_alloc(h, &kp.iesh_sgn, (size_t)n * T)) != 0) return fail(rc);
@@ -584,7 +592,11 @@ int nqcb200_run(nqcb200_handle* h, int64_t nsteps) {
         const int64_t chunk = std::min(nsteps - done, max_per_launch);
         h->kp.step0 = h->step_count + done;
         h->kp.nsteps = (int32_t)chunk;
-        h->ks.step<<<grid_for(h), h->ks.block, h->ks.dyn_smem, h->stream>>>(h->kp);
+        if (h->ks.step_block > 0) {
+            const int64_t threads = h->cfg.ntraj * h->ks.step_L;
+            const unsigned grid = (unsigned)std::max<int64_t>(1, (threads + h->ks.step_block - 1) / h->ks.step_block);
+            h->ks.step<<<grid, h->ks.step_block, h->ks.step_smem, h->stream>>>(h->kp);
+        } else h->ks.step<<<grid_for(h), h->ks.block, h->ks.dyn_smem, h->stream>>>(h->kp);
         NQ_CUDA(h, cudaGetLastError());
         h->last_launches++;
         done += chunk;

@@ -1,0 +1,366 @@
+// kernel_spinboson.cuh -- Simulation{FSSH} / Simulation{Ehrenfest} on SpinBoson (linear-coupling harmonic bath):
+// one THREAD per trajectory, the D bath coordinates and velocities of a block's 128 trajectories resident in shared
+// memory ([mode][thread], conflict-free), the 2x2 electronic problem in registers, persistent over the steps of a
+// launch.  Same reference path as kernel_density.cuh (BABwithTsit5, bab_electronics.jl:61-91; HoppingCallback,
+// surface_hopping.jl:2-168; fssh.jl:67-121; ehrenfest.jl:50-68), specialised to the structure of the model
+// (NQCModels SpinBoson, docs/src/NQCModels/systembathmodels.md:20-26):
+//
+//     V = (sum_j w_j^2 r_j^2 / 2) I + (eps + sum_j c_j r_j) sigma_z + Delta sigma_x ,   dV/dr_j = w_j^2 r_j I + c_j sigma_z
+//
+//  * Z' (dV/dr_j) Z = w_j^2 r_j I + c_j S with ONE 2x2 matrix S = Z' sigma_z Z per step, so the force on mode j is
+//    -(w_j^2 r_j A + c_j B) / m_j with two per-trajectory scalars (FSSH: A = 1, B = S_ss; Ehrenfest: A = tr sigma,
+//    B = sum_ab Re sigma_ab S_ab), and d_j[0,1] = -c_j S_01 / (w_0 - w_1): the D similarity transforms of the generic
+//    kernel collapse to a few flops.
+//  * v.d = -S_01/(w_0 - w_1) sum_j c_j v_j,  and the rescaling coefficients a = 1/2 sum d_j^2/m_j, b = sum d_j v_j are
+//    closed forms of sum_j c_j^2/m_j and sum_j c_j v_j: a hop costs O(1).
+//  * Because the force is linear in two scalars, the second half kick of step k and the first half kick of step k+1 use
+//    the same per-mode acceleration; the modes are therefore swept ONCE per step (half kick, half kick, drift) and the
+//    velocity kept in shared memory is the half-kicked one.  sum_j c_j v_j after the full kick follows from sums
+//    accumulated during the sweep.  The velocity change of an accepted hop (v_j -= gamma d_j / m_j) or of a reflected
+//    frustrated hop is applied inside the next sweep through two per-trajectory scalars.
+//  * Quirks Q1-Q4 of the reference are kept: zeroed electronic buffer on the first step, force not refreshed after a
+//    hop (the carried A, B are the pre-hop ones), buffered v.d from the pre-rescale velocity.
+#pragma once
+#include "kernel_density.cuh"
+
+namespace nq {
+
+#if defined(__CUDACC__)
+
+constexpr int kSbThreads = kBlockThreads;   // 128: the Emitter's block reduction is sized for it
+
+struct SbSmem {
+    double* rs;      // [D][TB]
+    double* vs;      // [D][TB]  half-kicked velocity (true velocity before the first step of a launch)
+    double4* cst;    // [D] {w_j^2, c_j, 1/m_j, c_j/m_j}
+    double* red;     // emitter scratch
+    NQ_D void carve(double* base, int D) {
+        rs = base; vs = rs + (size_t)D * kSbThreads;
+        cst = reinterpret_cast<double4*>(vs + (size_t)D * kSbThreads);
+        red = reinterpret_cast<double*>(cst + D);
+    }
+};
+NQ_HD size_t sb_smem_bytes(int D) { return ((size_t)2 * D * kSbThreads + 4 * (size_t)D + 2 * (kSbThreads / 32)) * sizeof(double); }
+
+// S = Z' sigma_z Z (symmetric 2x2): s00, s01, s11
+NQ_D void sb_sz(const Eig<2>& e, double& s00, double& s01, double& s11) {
+    s00 = e.Z[0][0] * e.Z[0][0] - e.Z[1][0] * e.Z[1][0];
+    s01 = e.Z[0][0] * e.Z[0][1] - e.Z[1][0] * e.Z[1][1];
+    s11 = e.Z[0][1] * e.Z[0][1] - e.Z[1][1] * e.Z[1][1];
+}
+// force scalars (A, B): acceleration of mode j = -(w_j^2 r_j A + c_j B) / m_j
+template <int METHOD>
+NQ_D void sb_force_scalars(const Herm<2>& s, int st, double s00, double s01, double s11, double& A, double& B) {
+    if (METHOD == NQCB200_METHOD_FSSH) { A = 1.0; B = st ? s11 : s00; }                       // fssh.jl:67-74
+    else { A = s.x[0] + s.x[2]; B = s.x[0] * s00 + 2.0 * s.x[1] * s01 + s.x[2] * s11; }        // ehrenfest.jl:57-65
+}
+
+struct SbTraj {
+    Herm<2> s;
+    int st;
+    double Zref[2][2];
+    ElecParams<2> cur;
+    double A, B;          // force scalars carried between steps (quirk Q2)
+    double gm, gd;        // pending velocity change: v_j -= c_j (gm / m_j + gd)
+};
+
+// One sweep over the modes.  first: vs holds the true velocity (launch entry) instead of the half-kicked one.
+// kick: perform the drift of a new step (false = only finish the pending kicks, used at save points / launch exit).
+// Accumulates harm = sum w^2 r^2/2, lin = sum c r, cvt = sum c vt, cwr = sum c w^2 r / m (all at the new positions).
+template <bool DRIFT>
+NQ_D void sb_sweep(const SbSmem& M, int D, int tid, bool first, double A, double B, double gm, double gd, double dt,
+                   double hdt, double& harm, double& lin, double& cvt, double& cwr, double& msv2) {
+    harm = 0.0; lin = 0.0; cvt = 0.0; cwr = 0.0; msv2 = 0.0;
+#pragma unroll 4
+    for (int j = 0; j < D; ++j) {
+        const double4 k = M.cst[j];                         // broadcast
+        const double r = M.rs[(size_t)j * kSbThreads + tid];
+        double v = M.vs[(size_t)j * kSbThreads + tid];
+        const double acc = -(k.x * r * A + k.y * B) * k.z;
+        if (!first) v = fma(hdt, acc, v);                   // second half kick of the previous step   steps.jl:3-5
+        v -= k.y * fma(gm, k.z, gd);                        // pending hop rescaling / reflection
+        if (DRIFT) {
+            const double vt = fma(hdt, acc, v);             // first half kick of this step
+            const double rn = fma(dt, vt, r);               // step_A!  steps.jl:6-8
+            M.rs[(size_t)j * kSbThreads + tid] = rn;
+            M.vs[(size_t)j * kSbThreads + tid] = vt;
+            harm = fma(0.5 * k.x * rn, rn, harm);
+            lin = fma(k.y, rn, lin);
+            cvt = fma(k.y, vt, cvt);
+            cwr = fma(k.y * k.x * k.z, rn, cwr);
+        } else {
+            M.vs[(size_t)j * kSbThreads + tid] = v;         // true velocity
+            msv2 = fma(v / k.z, v, msv2);                   // sum m v^2
+            lin = fma(k.y, r, lin);
+        }
+    }
+}
+
+template <int METHOD>
+NQ_D void sb_record_save(const KParams& p, Emitter& em, const SbSmem& M, int tid, const SbTraj& R, const Eig<2>& e,
+                         double msv2) {
+    constexpr int N = 2;
+    const uint32_t obs = p.observables;
+    const int64_t T = p.ntraj;
+    double adi[N], dia[N];
+    adiabatic_population<N, METHOD>(R.s, R.st, adi);
+    const bool need_dia = obs & ((1u << NQCB200_OBS_DIABATIC_POP) | (1u << NQCB200_OBS_POPCORR_DIABATIC) |
+                                 (1u << NQCB200_OBS_SCATTERING_DIABATIC));
+    if (need_dia) diabatic_population<N, METHOD>(R.s, R.st, e, dia);
+    else { dia[0] = 0.0; dia[1] = 0.0; }
+    if (em.isave == 0 && em.active && (obs & ((1u << NQCB200_OBS_POPCORR_DIABATIC) | (1u << NQCB200_OBS_POPCORR_ADIABATIC)))) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) { p.pop0[(int64_t)i * T + em.traj] = dia[i]; p.pop0[(int64_t)(N + i) * T + em.traj] = adi[i]; }
+    }
+    if (obs & (1u << NQCB200_OBS_ADIABATIC_POP)) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) em.emit(NQCB200_OBS_ADIABATIC_POP, i, adi[i]);
+    }
+    if (obs & (1u << NQCB200_OBS_DIABATIC_POP)) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) em.emit(NQCB200_OBS_DIABATIC_POP, i, dia[i]);
+    }
+    if (obs & (1u << NQCB200_OBS_POPCORR_DIABATIC)) {
+        double p0[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) p0[i] = (em.isave == 0) ? dia[i] : p.pop0[(int64_t)i * T + em.traj];
+#pragma unroll
+        for (int j = 0; j < N; ++j)
+#pragma unroll
+            for (int i = 0; i < N; ++i) em.emit(NQCB200_OBS_POPCORR_DIABATIC, i + N * j, p0[i] * dia[j]);
+    }
+    if (obs & (1u << NQCB200_OBS_POPCORR_ADIABATIC)) {
+        double p0[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) p0[i] = (em.isave == 0) ? adi[i] : p.pop0[(int64_t)(N + i) * T + em.traj];
+#pragma unroll
+        for (int j = 0; j < N; ++j)
+#pragma unroll
+            for (int i = 0; i < N; ++i) em.emit(NQCB200_OBS_POPCORR_ADIABATIC, i + N * j, p0[i] * adi[j]);
+    }
+    if (obs & ((1u << NQCB200_OBS_KINETIC) | (1u << NQCB200_OBS_POTENTIAL) | (1u << NQCB200_OBS_TOTAL_ENERGY))) {
+        const double kin = 0.5 * msv2;
+        double pot;
+        if (METHOD == NQCB200_METHOD_FSSH) pot = R.st ? e.w[1] : e.w[0];                       // fssh.jl:150-154
+        else pot = R.s.x[0] * e.w[0] + R.s.x[2] * e.w[1];                                     // ehrenfest.jl:85-95
+        if (obs & (1u << NQCB200_OBS_KINETIC)) em.emit(NQCB200_OBS_KINETIC, 0, kin);
+        if (obs & (1u << NQCB200_OBS_POTENTIAL)) em.emit(NQCB200_OBS_POTENTIAL, 0, pot);
+        if (obs & (1u << NQCB200_OBS_TOTAL_ENERGY)) em.emit(NQCB200_OBS_TOTAL_ENERGY, 0, kin + pot);
+    }
+    if (obs & ((1u << NQCB200_OBS_POSITION) | (1u << NQCB200_OBS_VELOCITY))) {
+        for (int dof = 0; dof < p.D; ++dof) {
+            if (obs & (1u << NQCB200_OBS_POSITION)) em.emit(NQCB200_OBS_POSITION, dof, M.rs[(size_t)dof * kSbThreads + tid]);
+            if (obs & (1u << NQCB200_OBS_VELOCITY)) em.emit(NQCB200_OBS_VELOCITY, dof, M.vs[(size_t)dof * kSbThreads + tid]);
+        }
+    }
+    if (obs & (1u << NQCB200_OBS_DISCRETE_STATE)) em.emit(NQCB200_OBS_DISCRETE_STATE, 0, (double)(R.st + 1));
+    const bool last = (em.isave == p.nsave - 1);
+    if (obs & ((1u << NQCB200_OBS_SCATTERING) | (1u << NQCB200_OBS_SCATTERING_DIABATIC))) {
+        const bool trans = M.rs[tid] > 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            if (obs & (1u << NQCB200_OBS_SCATTERING)) {
+                em.emit(NQCB200_OBS_SCATTERING, i, (last && !trans) ? adi[i] : 0.0);
+                em.emit(NQCB200_OBS_SCATTERING, N + i, (last && trans) ? adi[i] : 0.0);
+            }
+            if (obs & (1u << NQCB200_OBS_SCATTERING_DIABATIC)) {
+                em.emit(NQCB200_OBS_SCATTERING_DIABATIC, i, (last && !trans) ? dia[i] : 0.0);
+                em.emit(NQCB200_OBS_SCATTERING_DIABATIC, N + i, (last && trans) ? dia[i] : 0.0);
+            }
+        }
+    }
+    if (obs & (1u << NQCB200_OBS_SIGMA)) {
+#pragma unroll
+        for (int k = 0; k < N; ++k)
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                em.emit(NQCB200_OBS_SIGMA, j + N * k, R.s.X(j, k));
+                em.emit(NQCB200_OBS_SIGMA, N * N + j + N * k, R.s.Y(j, k));
+            }
+    }
+}
+
+template <int METHOD>
+__global__ void __launch_bounds__(kSbThreads, 1) spinboson_step_kernel(const __grid_constant__ KParams p) {
+    constexpr int N = 2;
+    extern __shared__ __align__(16) double sb_sm[];
+    SbSmem M;
+    M.carve(sb_sm, p.D);
+    const int tid = threadIdx.x, D = p.D;
+    int64_t traj = (int64_t)blockIdx.x * kSbThreads + tid;
+    const bool valid = traj < p.ntraj;
+    if (!valid) traj = p.ntraj - 1;
+    const int64_t T = p.ntraj;
+    const double dt = p.dt, hdt = 0.5 * p.dt;
+
+    // per-mode constants and sums over the bath
+    double C2 = 0.0, Cc = 0.0;      // sum c^2/m, sum c^2
+    for (int j = tid; j < D; j += kSbThreads) {
+        const double w = p.bath_a[j], c = p.bath_b[j], im = 1.0 / p.masses[j];
+        M.cst[j] = make_double4(w * w, c, im, c * im);
+    }
+    for (int j = 0; j < D; ++j) {
+        M.rs[(size_t)j * kSbThreads + tid] = p.r[(int64_t)j * T + traj];
+        M.vs[(size_t)j * kSbThreads + tid] = p.v[(int64_t)j * T + traj];
+    }
+    __syncthreads();
+    for (int j = 0; j < D; ++j) { const double4 k = M.cst[j]; C2 = fma(k.y, k.w, C2); Cc = fma(k.y, k.y, Cc); }
+
+    SbTraj R;
+    R.s.x[0] = p.sig_re[(int64_t)0 * T + traj]; R.s.x[1] = p.sig_re[(int64_t)2 * T + traj]; R.s.x[2] = p.sig_re[(int64_t)3 * T + traj];
+    R.s.y[0] = p.sig_im[(int64_t)2 * T + traj];
+    R.st = p.state ? p.state[traj] : 0;
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+#pragma unroll
+        for (int k = 0; k < N; ++k) R.Zref[j][k] = p.Zprev[(int64_t)(j + N * k) * T + traj];
+    R.cur.E[0] = p.ecur[(int64_t)0 * T + traj]; R.cur.E[1] = p.ecur[(int64_t)1 * T + traj];
+    R.cur.g[0] = p.ecur[(int64_t)(N + 0 + N * 1) * T + traj];
+    R.gm = 0.0; R.gd = 0.0;
+    Eig<N> e;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        e.w[i] = R.cur.E[i];
+#pragma unroll
+        for (int k = 0; k < N; ++k) e.Z[i][k] = R.Zref[i][k];
+    }
+    if (p.step0 == 0) {
+        // first step after set_state: no hop has happened, sigma is sigma(t0), Zref the eigenvectors at r0
+        double s00, s01, s11;
+        sb_sz(e, s00, s01, s11);
+        sb_force_scalars<METHOD>(R.s, R.st, s00, s01, s11, R.A, R.B);
+    } else {
+        R.A = p.sb_carry[traj]; R.B = p.sb_carry[T + traj];
+    }
+    unsigned long long nhops = 0, nfrus = 0;
+    bool first = true;
+
+#pragma unroll 1
+    for (int is = 0; is < p.nsteps; ++is) {
+        const int64_t step = p.step0 + is;
+        const double t = p.t0 + dt * (double)step;
+        const double tcur = (step == 0) ? 0.0 : t;   // Q1
+        double harm, lin, cvt, cwr, msv2;
+        sb_sweep<true>(M, D, tid, first, R.A, R.B, R.gm, R.gd, dt, hdt, harm, lin, cvt, cwr, msv2);
+        first = false; R.gm = 0.0; R.gd = 0.0;
+        // update_cache!: V -> eigen (gauge-fixed)
+        {
+            const double l = p.params[0] + lin;
+            double Vp[3] = {harm + l, p.params[1], harm - l};
+            sym_eigh<N>(Vp, e);
+            fix_gauge<N>(e, R.Zref);
+        }
+        double s00, s01, s11;
+        sb_sz(e, s00, s01, s11);
+        sb_force_scalars<METHOD>(R.s, R.st, s00, s01, s11, R.A, R.B);      // pre-hop state, sigma_prev
+        // sum_j c_j v_j after the second half kick: v_j = vt_j - hdt (w_j^2 r_j A + c_j B) / m_j
+        const double cv = cvt - hdt * (R.A * cwr + R.B * C2);
+        const double dfac = -s01 / (e.w[0] - e.w[1]);                       // d_j[0,1] = c_j dfac
+        ElecParams<N> nxt;
+        nxt.E[0] = e.w[0]; nxt.E[1] = e.w[1];
+        nxt.g[0] = dfac * cv;
+        propagate_density<N>(R.cur, tcur, nxt, t + dt, t, dt, R.s);
+
+        if (METHOD == NQCB200_METHOD_FSSH) {
+            const double xi = (p.rng == NQCB200_RNG_INJECTED)
+                                  ? p.draws[(step - p.draws_step0) * T + traj]
+                                  : philox_uniform(p.seed, (uint64_t)(p.traj_offset + traj), (uint64_t)step, 0u);
+            const int s0 = R.st, m = 1 - s0;
+            // fewest_switches_probability! fssh.jl:96-108 (Q4) + select_new_state :110-121 for two states
+            double g = 2.0 * (R.s.x[1] / (s0 ? R.s.x[2] : R.s.x[0])) * nxt.G(s0, m) * dt;
+            g = fmin(1.0, fmax(0.0, g));
+            if (g > xi) {
+                bool accept = true;
+                if (p.rescaling != NQCB200_RESCALE_OFF) {                   // surface_hopping.jl:64-99
+                    const double wn = m ? e.w[1] : e.w[0], wo = s0 ? e.w[1] : e.w[0];
+                    const double df = -s01 / (wn - wo);                     // d_j[new, old] = c_j df
+                    const double a = 0.5 * df * df * C2, b = df * cv, c = wn - wo;
+                    const double disc = b * b - 4.0 * a * c;
+                    if (disc < 0.0) {
+                        accept = false;
+                        nfrus += valid;
+                        if (p.rescaling == NQCB200_RESCALE_VINVERSION) {    // v -= 2 (v.dhat) dhat
+                            const double nrm = sqrt(df * df * Cc);
+                            const double gam = b / nrm;
+                            R.gd = 2.0 * gam * df / nrm;
+                        }
+                    } else {
+                        const double root = sqrt(disc);
+                        const double gam = (b < 0.0) ? (b + root) / (2.0 * a) : (b - root) / (2.0 * a);
+                        R.gm = gam * df;
+                    }
+                }
+                if (accept) { R.st = m; nhops += valid; }
+            }
+        }
+        R.cur = nxt;
+
+        if ((step + 1) % p.save_every == 0) {
+            const int64_t isave = (step + 1) / p.save_every;
+            if (isave < p.nsave) {
+                if (p.observables & ((1u << NQCB200_OBS_KINETIC) | (1u << NQCB200_OBS_TOTAL_ENERGY) | (1u << NQCB200_OBS_VELOCITY))) {
+                    // finish the pending kicks so that shared memory holds the true velocities
+                    double h2, l2, c2, w2;
+                    sb_sweep<false>(M, D, tid, false, R.A, R.B, R.gm, R.gd, dt, hdt, h2, l2, c2, w2, msv2);
+                    first = true; R.gm = 0.0; R.gd = 0.0;
+                }
+                Emitter em{p, traj, valid, (int)isave, M.red, 0};
+                sb_record_save<METHOD>(p, em, M, tid, R, e, msv2);
+            }
+        }
+    }
+
+    // launch exit: true velocities, state back to global memory
+    if (!first) {
+        double h2, l2, c2, w2, m2;
+        sb_sweep<false>(M, D, tid, false, R.A, R.B, R.gm, R.gd, dt, hdt, h2, l2, c2, w2, m2);
+    }
+    if (valid) {
+        for (int j = 0; j < D; ++j) {
+            p.r[(int64_t)j * T + traj] = M.rs[(size_t)j * kSbThreads + tid];
+            p.v[(int64_t)j * T + traj] = M.vs[(size_t)j * kSbThreads + tid];
+        }
+        p.sb_carry[traj] = R.A; p.sb_carry[T + traj] = R.B;
+#pragma unroll
+        for (int j = 0; j < N; ++j)
+#pragma unroll
+            for (int k = 0; k < N; ++k) {
+                p.sig_re[(int64_t)(j + N * k) * T + traj] = R.s.X(j, k);
+                p.sig_im[(int64_t)(j + N * k) * T + traj] = R.s.Y(j, k);
+                p.Zprev[(int64_t)(j + N * k) * T + traj] = R.Zref[j][k];
+            }
+        if (p.state) p.state[traj] = R.st;
+        p.ecur[(int64_t)0 * T + traj] = R.cur.E[0]; p.ecur[(int64_t)1 * T + traj] = R.cur.E[1];
+        p.ecur[(int64_t)(N + 0 + N * 1) * T + traj] = R.cur.g[0];
+        if (p.diagnostics) {
+            double s00, s01, s11;
+            sb_sz(e, s00, s01, s11);
+            const double dfac = -s01 / (e.w[0] - e.w[1]);
+#pragma unroll
+            for (int i = 0; i < N; ++i) p.diag_eig[(int64_t)i * T + traj] = e.w[i];
+#pragma unroll
+            for (int j = 0; j < N; ++j)
+#pragma unroll
+                for (int k = 0; k < N; ++k) p.diag_Z[(int64_t)(j + N * k) * T + traj] = e.Z[j][k];
+            for (int dof = 0; dof < D; ++dof) {
+                const double4 k = M.cst[dof];
+                const double r = M.rs[(size_t)dof * kSbThreads + tid];
+                p.acc[(int64_t)dof * T + traj] = -(k.x * r * R.A + k.y * R.B) * k.z;
+                p.diag_nac[((int64_t)dof * N * N + 0) * T + traj] = 0.0;
+                p.diag_nac[((int64_t)dof * N * N + 1) * T + traj] = -k.y * dfac;     // d[1,0]
+                p.diag_nac[((int64_t)dof * N * N + 2) * T + traj] = k.y * dfac;      // d[0,1]
+                p.diag_nac[((int64_t)dof * N * N + 3) * T + traj] = 0.0;
+            }
+        }
+    }
+    const unsigned long long wh = __reduce_add_sync(0xffffffffu, (unsigned)nhops);
+    const unsigned long long wf = __reduce_add_sync(0xffffffffu, (unsigned)nfrus);
+    if ((threadIdx.x & 31) == 0) {
+        if (wh) atomicAdd(&p.counters[0], wh);
+        if (wf) atomicAdd(&p.counters[1], wf);
+    }
+}
+
+#endif  // __CUDACC__
+
+}  // namespace nq

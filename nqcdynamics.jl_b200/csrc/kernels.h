@@ -17,6 +17,11 @@ struct KernelSet {
     int DPL = 1;            // nuclear dofs per lane
     int block = kBlockThreads;
     size_t dyn_smem = 0;
+    // launch shape of the STEP kernel when it differs from the init kernel's (0 = same as above)
+    int step_L = 0;
+    int step_block = 0;
+    size_t step_smem = 0;
+    bool needs_sb_carry = false;   // kernel_spinboson.cuh: two force scalars per trajectory carried between launches
     bool cta_per_trajectory = false;
     IeshLayout iesh = {};   // AdiabaticIESH tile / shared-memory plan (kernel_iesh.cuh)
     const char* name = "";

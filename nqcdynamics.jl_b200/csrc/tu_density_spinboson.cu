@@ -2,6 +2,7 @@
 #include <cstdlib>
 
 #include "kernel_density.cuh"
+#include "kernel_spinboson.cuh"
 
 namespace nq {
 namespace {
@@ -27,6 +28,18 @@ bool select_density_spinboson(const nqcb200_config& c, KernelSet& out, std::stri
     if (c.nbath != D) { why = "SpinBoson needs nbath == ndofs"; return false; }
     int lanes = 0;
     if (const char* env = getenv("NQCB200_SPINBOSON_LANES")) lanes = atoi(env);
+    // default: thread per trajectory with the bath resident in shared memory (kernel_spinboson.cuh); the lane-split
+    // generic kernels below remain for D beyond the shared-memory budget (and as an A/B switch through the env var)
+    if (lanes == 0 && D >= 2 && sb_smem_bytes(D) <= 220 * 1024 && (m == NQCB200_METHOD_FSSH || m == NQCB200_METHOD_EHRENFEST)) {
+        bool ok = (D <= 8) ? pick<8, 1>(m, out) : (D <= 104) ? pick<13, 8>(m, out) : pick<4, 32>(m, out);   // init kernel
+        if (!ok) return false;
+        out.step = (m == NQCB200_METHOD_FSSH) ? spinboson_step_kernel<NQCB200_METHOD_FSSH>
+                                              : spinboson_step_kernel<NQCB200_METHOD_EHRENFEST>;
+        out.step_L = 1; out.step_block = kSbThreads; out.step_smem = sb_smem_bytes(D);
+        out.needs_sb_carry = true;
+        out.name = (m == NQCB200_METHOD_FSSH) ? "spinboson_fssh_tpt" : "spinboson_ehrenfest_tpt";
+        return true;
+    }
     if (D <= 4 && (lanes == 0 || lanes == 1)) return pick<4, 1>(m, out);
     if (D <= 8 && (lanes == 0 || lanes == 1)) return pick<8, 1>(m, out);
     if (D <= 104 && (lanes == 0 || lanes == 8)) return pick<13, 8>(m, out);
