@@ -32,15 +32,15 @@ constexpr int kSbThreads = kBlockThreads;   // 128: the Emitter's block reductio
 struct SbSmem {
     double* rs;      // [D][TB]
     double* vs;      // [D][TB]  half-kicked velocity (true velocity before the first step of a launch)
-    double4* cst;    // [D] {w_j^2, c_j, 1/m_j, c_j/m_j}
+    double2 *k1, *k2, *k3;   // [D] {w^2/m, c/m}, {c, w^2/2}, {c w^2/m, m}
     double* red;     // emitter scratch
     NQ_D void carve(double* base, int D) {
         rs = base; vs = rs + (size_t)D * kSbThreads;
-        cst = reinterpret_cast<double4*>(vs + (size_t)D * kSbThreads);
-        red = reinterpret_cast<double*>(cst + D);
+        k1 = reinterpret_cast<double2*>(vs + (size_t)D * kSbThreads); k2 = k1 + D; k3 = k2 + D;
+        red = reinterpret_cast<double*>(k3 + D);
     }
 };
-NQ_HD size_t sb_smem_bytes(int D) { return ((size_t)2 * D * kSbThreads + 4 * (size_t)D + 2 * (kSbThreads / 32)) * sizeof(double); }
+NQ_HD size_t sb_smem_bytes(int D) { return ((size_t)2 * D * kSbThreads + 6 * (size_t)D + 2 * (kSbThreads / 32)) * sizeof(double); }
 
 // S = Z' sigma_z Z (symmetric 2x2): s00, s01, s11
 NQ_D void sb_sz(const Eig<2>& e, double& s00, double& s01, double& s11) {
@@ -65,35 +65,74 @@ struct SbTraj {
 };
 
 // One sweep over the modes.  first: vs holds the true velocity (launch entry) instead of the half-kicked one.
-// kick: perform the drift of a new step (false = only finish the pending kicks, used at save points / launch exit).
+// DRIFT: perform the drift of a new step (false = only finish the pending kicks, used at save points / launch exit).
 // Accumulates harm = sum w^2 r^2/2, lin = sum c r, cvt = sum c vt, cwr = sum c w^2 r / m (all at the new positions).
+// Per-mode constants: k1 = {w^2/m, c/m}, k2 = {c, w^2/2}, k3 = {c w^2/m, m}.  Four modes are advanced in lock step so that
+// their dependent FMA chains interleave (one warp per scheduler: instruction-level parallelism hides the latency).
 template <bool DRIFT>
 NQ_D void sb_sweep(const SbSmem& M, int D, int tid, bool first, double A, double B, double gm, double gd, double dt,
                    double hdt, double& harm, double& lin, double& cvt, double& cwr, double& msv2) {
-    harm = 0.0; lin = 0.0; cvt = 0.0; cwr = 0.0; msv2 = 0.0;
-#pragma unroll 4
-    for (int j = 0; j < D; ++j) {
-        const double4 k = M.cst[j];                         // broadcast
-        const double r = M.rs[(size_t)j * kSbThreads + tid];
-        double v = M.vs[(size_t)j * kSbThreads + tid];
-        const double acc = -(k.x * r * A + k.y * B) * k.z;
-        if (!first) v = fma(hdt, acc, v);                   // second half kick of the previous step   steps.jl:3-5
-        v -= k.y * fma(gm, k.z, gd);                        // pending hop rescaling / reflection
-        if (DRIFT) {
-            const double vt = fma(hdt, acc, v);             // first half kick of this step
-            const double rn = fma(dt, vt, r);               // step_A!  steps.jl:6-8
-            M.rs[(size_t)j * kSbThreads + tid] = rn;
-            M.vs[(size_t)j * kSbThreads + tid] = vt;
-            harm = fma(0.5 * k.x * rn, rn, harm);
-            lin = fma(k.y, rn, lin);
-            cvt = fma(k.y, vt, cvt);
-            cwr = fma(k.y * k.x * k.z, rn, cwr);
-        } else {
-            M.vs[(size_t)j * kSbThreads + tid] = v;         // true velocity
-            msv2 = fma(v / k.z, v, msv2);                   // sum m v^2
-            lin = fma(k.y, r, lin);
+    constexpr int W = 4;
+    double h4[W], l4[W], c4[W], w4[W], m4[W];
+#pragma unroll
+    for (int q = 0; q < W; ++q) { h4[q] = 0.0; l4[q] = 0.0; c4[q] = 0.0; w4[q] = 0.0; m4[q] = 0.0; }
+    const double nA = -A, nB = -B, kick2 = first ? 0.0 : hdt;
+    auto body = [&](const int (&jj)[W], const bool (&ok)[W]) {
+        double2 k1[W], k2[W], k3[W];
+        double r[W], v[W], acc[W];
+#pragma unroll
+        for (int q = 0; q < W; ++q) {
+            k1[q] = M.k1[jj[q]]; k2[q] = M.k2[jj[q]]; k3[q] = M.k3[jj[q]];
+            r[q] = M.rs[(size_t)jj[q] * kSbThreads + tid];
+            v[q] = M.vs[(size_t)jj[q] * kSbThreads + tid];
         }
+#pragma unroll
+        for (int q = 0; q < W; ++q) acc[q] = fma(nA * k1[q].x, r[q], nB * k1[q].y);     // -(w^2 r A + c B) / m
+#pragma unroll
+        for (int q = 0; q < W; ++q) v[q] = fma(kick2, acc[q], v[q]);                    // second half kick of the previous step
+#pragma unroll
+        for (int q = 0; q < W; ++q) v[q] = fma(-gm, k1[q].y, fma(-gd, k2[q].x, v[q]));  // pending hop rescaling / reflection
+        if (DRIFT) {
+            double vt[W], rn[W];
+#pragma unroll
+            for (int q = 0; q < W; ++q) vt[q] = fma(hdt, acc[q], v[q]);                 // first half kick of this step  steps.jl:3-5
+#pragma unroll
+            for (int q = 0; q < W; ++q) rn[q] = fma(dt, vt[q], r[q]);                   // step_A!  steps.jl:6-8
+#pragma unroll
+            for (int q = 0; q < W; ++q) {
+                if (ok[q]) {
+                    M.rs[(size_t)jj[q] * kSbThreads + tid] = rn[q];
+                    M.vs[(size_t)jj[q] * kSbThreads + tid] = vt[q];
+                    h4[q] = fma(k2[q].y * rn[q], rn[q], h4[q]);
+                    l4[q] = fma(k2[q].x, rn[q], l4[q]);
+                    c4[q] = fma(k2[q].x, vt[q], c4[q]);
+                    w4[q] = fma(k3[q].x, rn[q], w4[q]);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < W; ++q) {
+                if (ok[q]) {
+                    M.vs[(size_t)jj[q] * kSbThreads + tid] = v[q];                       // true velocity
+                    m4[q] = fma(k3[q].y * v[q], v[q], m4[q]);                           // sum m v^2
+                }
+            }
+        }
+    };
+    int j = 0;
+    for (; j + W <= D; j += W) {
+        const int jj[W] = {j, j + 1, j + 2, j + 3};
+        const bool ok[W] = {true, true, true, true};
+        body(jj, ok);
     }
+    if (j < D) {
+        const int jj[W] = {j, min(j + 1, D - 1), min(j + 2, D - 1), min(j + 3, D - 1)};
+        const bool ok[W] = {true, j + 1 < D, j + 2 < D, j + 3 < D};
+        body(jj, ok);
+    }
+    harm = (h4[0] + h4[1]) + (h4[2] + h4[3]); lin = (l4[0] + l4[1]) + (l4[2] + l4[3]);
+    cvt = (c4[0] + c4[1]) + (c4[2] + c4[3]); cwr = (w4[0] + w4[1]) + (w4[2] + w4[3]);
+    msv2 = (m4[0] + m4[1]) + (m4[2] + m4[3]);
 }
 
 template <int METHOD>
@@ -196,15 +235,15 @@ __global__ void __launch_bounds__(kSbThreads, 1) spinboson_step_kernel(const __g
     // per-mode constants and sums over the bath
     double C2 = 0.0, Cc = 0.0;      // sum c^2/m, sum c^2
     for (int j = tid; j < D; j += kSbThreads) {
-        const double w = p.bath_a[j], c = p.bath_b[j], im = 1.0 / p.masses[j];
-        M.cst[j] = make_double4(w * w, c, im, c * im);
+        const double w = p.bath_a[j], c = p.bath_b[j], m = p.masses[j];
+        M.k1[j] = make_double2(w * w / m, c / m); M.k2[j] = make_double2(c, 0.5 * w * w); M.k3[j] = make_double2(c * w * w / m, m);
     }
     for (int j = 0; j < D; ++j) {
         M.rs[(size_t)j * kSbThreads + tid] = p.r[(int64_t)j * T + traj];
         M.vs[(size_t)j * kSbThreads + tid] = p.v[(int64_t)j * T + traj];
     }
     __syncthreads();
-    for (int j = 0; j < D; ++j) { const double4 k = M.cst[j]; C2 = fma(k.y, k.w, C2); Cc = fma(k.y, k.y, Cc); }
+    for (int j = 0; j < D; ++j) { const double c = M.k2[j].x; C2 = fma(c, M.k1[j].y, C2); Cc = fma(c, c, Cc); }
 
     SbTraj R;
     R.s.x[0] = p.sig_re[(int64_t)0 * T + traj]; R.s.x[1] = p.sig_re[(int64_t)2 * T + traj]; R.s.x[2] = p.sig_re[(int64_t)3 * T + traj];
@@ -343,12 +382,13 @@ __global__ void __launch_bounds__(kSbThreads, 1) spinboson_step_kernel(const __g
 #pragma unroll
                 for (int k = 0; k < N; ++k) p.diag_Z[(int64_t)(j + N * k) * T + traj] = e.Z[j][k];
             for (int dof = 0; dof < D; ++dof) {
-                const double4 k = M.cst[dof];
+                const double2 k1 = M.k1[dof];
+                const double c = M.k2[dof].x;
                 const double r = M.rs[(size_t)dof * kSbThreads + tid];
-                p.acc[(int64_t)dof * T + traj] = -(k.x * r * R.A + k.y * R.B) * k.z;
+                p.acc[(int64_t)dof * T + traj] = fma(-R.A * k1.x, r, -R.B * k1.y);
                 p.diag_nac[((int64_t)dof * N * N + 0) * T + traj] = 0.0;
-                p.diag_nac[((int64_t)dof * N * N + 1) * T + traj] = -k.y * dfac;     // d[1,0]
-                p.diag_nac[((int64_t)dof * N * N + 2) * T + traj] = k.y * dfac;      // d[0,1]
+                p.diag_nac[((int64_t)dof * N * N + 1) * T + traj] = -c * dfac;       // d[1,0]
+                p.diag_nac[((int64_t)dof * N * N + 2) * T + traj] = c * dfac;        // d[0,1]
                 p.diag_nac[((int64_t)dof * N * N + 3) * T + traj] = 0.0;
             }
         }
