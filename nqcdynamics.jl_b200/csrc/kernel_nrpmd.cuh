@@ -83,8 +83,6 @@ template <class M, int NB>
 __global__ void __launch_bounds__(kBlockThreads) nrpmd_step_kernel(const __grid_constant__ KParams p) {
     constexpr int N = M::NS;
     __shared__ double smem[2 * (kBlockThreads / 32)];
-    __shared__ double s_to[NB * NB], s_from[NB * NB];
-    load_nm_tables<NB>(p, s_to, s_from);
     const int64_t gthread = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t traj = gthread / NB;
     const int lane = (int)(gthread % NB);
@@ -100,16 +98,15 @@ __global__ void __launch_bounds__(kBlockThreads) nrpmd_step_kernel(const __grid_
         q[j] = p.qmap[((int64_t)lane * N + j) * T + traj];
         pm[j] = p.pmap[((int64_t)lane * N + j) * T + traj];
     }
-    double cay[4];   // half-step Cayley
-#pragma unroll
-    for (int i = 0; i < 4; ++i) cay[i] = p.cayley[4 * lane + i];
+    FreeRingPolymer<NB> frp;   // half-step Cayley (the engine uploads sqrt(M) for NRPMD)
+    frp.init(p, lane, group_base);
     const double dt = p.dt;
     double Vp[sym_size(N)];
 
 #pragma unroll 1
     for (int is = 0; is < p.nsteps; ++is) {
         const int64_t step = p.step0 + is;
-        free_ring_polymer_step<NB>(s_to, s_from, cay, lane, group_base, r, v);
+        frp.step(r, v);
         nrpmd_potential<M>(p, r, Vp);
         Eig<N> e;
         sym_eigh<N>(Vp, e);
@@ -163,7 +160,7 @@ __global__ void __launch_bounds__(kBlockThreads) nrpmd_step_kernel(const __grid_
         }
         v -= force / mass;
         v -= dbar / mass * dt;
-        free_ring_polymer_step<NB>(s_to, s_from, cay, lane, group_base, r, v);
+        frp.step(r, v);
 
         if ((step + 1) % p.save_every == 0) {
             const int64_t isave = (step + 1) / p.save_every;

@@ -23,43 +23,81 @@ namespace nq {
 
 #if defined(__CUDACC__)
 
-// x_k = sum_j U[j,k] x_j ("to") or x_j = sum_k U[j,k] x_k ("from"); tab[i*NB + lane] holds the
-// coefficient this lane needs at iteration i, so shared-memory reads are conflict-free.
+// Free ring-polymer step (to-normal-modes -> Cayley 2x2 per mode -> back, steps.jl:10-17) as ONE
+// complex FFT over the lanes of a bead group instead of four dense NB x NB mat-vecs.
+//
+// With z_j = r_j + i v_j and Z_k = sum_j z_j e^{-2 pi i jk/NB}: the transforms of the two real
+// sequences are R_k = (Z_k + W_k)/2, V_k = (Z_k - W_k)/(2i), W_k = conj(Z_{NB-k}); the real normal
+// modes k and NB-k (cos / sin pair, same frequency, same Cayley matrix [[a,b],[c,d]]) are the real and
+// imaginary parts of R_k, so the propagated spectrum is
+//     Z'_k = R'_k + i V'_k = alpha_k Z_k + beta_k W_k,
+//     alpha = ((a+d) + i(c-b))/2,  beta = ((a-d) + i(c+b))/2,
+// and r', v' are the real / imaginary parts of the inverse FFT (1/NB folded into alpha, beta; the
+// orthogonal-U normalisation cancels).  Forward = radix-2 DIF (natural in, bit-reversed out), inverse =
+// radix-2 DIT (bit-reversed in, natural out), so no reordering: 2 log2(NB) + 1 shuffle rounds of one
+// complex number instead of 4 NB shuffles + 4 NB shared-memory loads (the dense version was 99.8 %
+// LSU-bound, profiles/r01).  Agrees with the dense U'..U product to rounding (1e-14).
 template <int NB>
-NQ_D double nm_apply(const double* tab, double x, int lane, int group_base) {
-    double out = 0.0;
+struct FreeRingPolymer {
+    static constexpr int LOG = (NB >= 32) ? 5 : (NB >= 16) ? 4 : (NB >= 8) ? 3 : (NB >= 4) ? 2 : (NB >= 2) ? 1 : 0;
+    static constexpr int NS = LOG > 0 ? LOG : 1;
+    double twr[NS], twi[NS];   // stage twiddle W_{2h}^{lane mod h} on the upper lanes, 1 on the lower ones
+    double sg[NS];             // -1 on the upper lanes of a stage, +1 on the lower ones
+    double ar, ai, br, bi;     // alpha, beta of the mode this lane holds after the forward pass
+    int partner;               // warp lane holding mode NB - k
+
+    NQ_D void init(const KParams& p, int lane, int group_base) {
+        int k = 0;
 #pragma unroll
-    for (int i = 0; i < NB; ++i) {
-        const double xi = __shfl_sync(0xffffffffu, x, group_base + i);
-        out = fma(tab[i * NB + lane], xi, out);
+        for (int b = 0; b < LOG; ++b) k |= ((lane >> b) & 1) << (LOG - 1 - b);
+        const int kc = (NB - k) % NB;
+        int lp = 0;
+#pragma unroll
+        for (int b = 0; b < LOG; ++b) lp |= ((kc >> b) & 1) << (LOG - 1 - b);
+        partner = group_base + lp;
+#pragma unroll
+        for (int s = 0; s < LOG; ++s) {
+            const int h = NB >> (s + 1);
+            const bool upper = (lane & h) != 0;
+            double si = 0.0, co = 1.0;
+            if (upper) sincospi(-(double)(lane & (h - 1)) / (double)h, &si, &co);
+            twr[s] = co; twi[s] = si; sg[s] = upper ? -1.0 : 1.0;
+        }
+        const double a = p.cayley[4 * k + 0], b = p.cayley[4 * k + 1], c = p.cayley[4 * k + 2], d = p.cayley[4 * k + 3];
+        if (NB == 1) { ar = a; ai = b; br = c; bi = d; return; }
+        const double inv = 0.5 / NB;
+        ar = (a + d) * inv; ai = (c - b) * inv; br = (a - d) * inv; bi = (c + b) * inv;
     }
-    return out;
-}
 
-template <int NB>
-NQ_D void free_ring_polymer_step(const double* tab_to, const double* tab_from, const double (&cay)[4], int lane,
-                                 int group_base, double& r, double& v) {
-    if (NB == 1) {
-        const double rt = cay[0] * r + cay[1] * v, vt = cay[2] * r + cay[3] * v;
-        r = rt; v = vt;
-        return;
+    NQ_D void step(double& r, double& v) const {
+        if (NB == 1) {
+            const double rt = ar * r + ai * v, vt = br * r + bi * v;
+            r = rt; v = vt;
+            return;
+        }
+        double zr = r, zi = v;
+#pragma unroll
+        for (int s = 0; s < LOG; ++s) {
+            const int h = NB >> (s + 1);
+            const double yr = __shfl_xor_sync(0xffffffffu, zr, h), yi = __shfl_xor_sync(0xffffffffu, zi, h);
+            const double tr = fma(sg[s], zr, yr), ti = fma(sg[s], zi, yi);   // lower: z + y, upper: y - z
+            if (h > 1) { zr = fma(tr, twr[s], -ti * twi[s]); zi = fma(tr, twi[s], ti * twr[s]); }
+            else { zr = tr; zi = ti; }
+        }
+        const double wr = __shfl_sync(0xffffffffu, zr, partner), wi = -__shfl_sync(0xffffffffu, zi, partner);
+        double nr = fma(ar, zr, fma(-ai, zi, fma(br, wr, -bi * wi)));
+        double ni = fma(ar, zi, fma(ai, zr, fma(br, wi, bi * wr)));
+#pragma unroll
+        for (int s = LOG - 1; s >= 0; --s) {
+            const int h = NB >> (s + 1);
+            double xr = nr, xi = ni;
+            if (h > 1) { xr = fma(nr, twr[s], ni * twi[s]); xi = fma(ni, twr[s], -nr * twi[s]); }   // conj(twiddle)
+            const double yr = __shfl_xor_sync(0xffffffffu, xr, h), yi = __shfl_xor_sync(0xffffffffu, xi, h);
+            nr = fma(sg[s], xr, yr); ni = fma(sg[s], xi, yi);                   // lower: x + y, upper: y - x
+        }
+        r = nr; v = ni;
     }
-    double rn = nm_apply<NB>(tab_to, r, lane, group_base);
-    double vn = nm_apply<NB>(tab_to, v, lane, group_base);
-    const double rt = cay[0] * rn + cay[1] * vn;     // step_C!
-    const double vt = cay[2] * rn + cay[3] * vn;
-    r = nm_apply<NB>(tab_from, rt, lane, group_base);
-    v = nm_apply<NB>(tab_from, vt, lane, group_base);
-}
-
-template <int NB>
-NQ_D void load_nm_tables(const KParams& p, double* s_to, double* s_from) {
-    for (int i = threadIdx.x; i < NB * NB; i += blockDim.x) {
-        s_to[i] = p.nm_to[i];
-        s_from[i] = p.nm_from[i];
-    }
-    __syncthreads();
-}
+};
 
 template <int NB>
 NQ_D double spring_energy(double r, double mass, double omega_n, int lane, int group_base) {
@@ -246,8 +284,6 @@ template <class M, int NB, int METHOD>
 __global__ void __launch_bounds__(kBlockThreads) ring_step_kernel(const __grid_constant__ KParams p) {
     constexpr int N = M::NS;
     __shared__ double smem[2 * (kBlockThreads / 32)];
-    __shared__ double s_to[NB * NB], s_from[NB * NB];
-    load_nm_tables<NB>(p, s_to, s_from);
     const int64_t gthread = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t traj = gthread / NB;
     const int lane = (int)(gthread % NB);
@@ -259,9 +295,8 @@ __global__ void __launch_bounds__(kBlockThreads) ring_step_kernel(const __grid_c
 
     RingRegs<N, NB> R;
     ring_load<N, NB>(p, traj, lane, R, true);
-    double cay[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) cay[i] = p.cayley[4 * lane + i];
+    FreeRingPolymer<NB> frp;
+    frp.init(p, lane, group_base);
     Eig<N> eb, ec;
     double Ab[sym_size(N)], Ac[sym_size(N)];
     unsigned long long nhops = 0, nfrus = 0;
@@ -274,7 +309,7 @@ __global__ void __launch_bounds__(kBlockThreads) ring_step_kernel(const __grid_c
         const double tcur = (step == 0) ? 0.0 : t;   // Q1
         double vt = fma(hdt, R.acc, R.v);
         double rt = R.r;
-        free_ring_polymer_step<NB>(s_to, s_from, cay, lane, group_base, rt, vt);
+        frp.step(rt, vt);
         // update_cache!: every bead and the centroid (bcb_electronics.jl:73)
         eval_point<M>(p, rt, R.Zb, eb, Ab);
         const double rcent = lane_sum<NB>(rt) / NB;
@@ -464,8 +499,6 @@ NQ_D void classical_record_save(const KParams& p, Emitter& em, int lane, int gro
 template <class M, int NB>
 __global__ void __launch_bounds__(kBlockThreads) classical_ring_step_kernel(const __grid_constant__ KParams p) {
     __shared__ double smem[2 * (kBlockThreads / 32)];
-    __shared__ double s_to[NB * NB], s_from[NB * NB];
-    load_nm_tables<NB>(p, s_to, s_from);
     const int64_t gthread = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t traj = gthread / NB;
     const int lane = (int)(gthread % NB);
@@ -475,9 +508,8 @@ __global__ void __launch_bounds__(kBlockThreads) classical_ring_step_kernel(cons
     const int64_t T = p.ntraj;
     double r = p.r[(int64_t)lane * T + traj], v = p.v[(int64_t)lane * T + traj], acc = p.acc[(int64_t)lane * T + traj];
     const double mass = p.masses[0];
-    double cay[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) cay[i] = p.cayley[4 * lane + i];
+    FreeRingPolymer<NB> frp;
+    frp.init(p, lane, group_base);
     const double dt = p.dt, hdt = 0.5 * p.dt;
 #pragma unroll 1
     for (int is = 0; is < p.nsteps; ++is) {
@@ -490,7 +522,7 @@ __global__ void __launch_bounds__(kBlockThreads) classical_ring_step_kernel(cons
             v = v + dt * (0.5 * a_old + 0.5 * acc);
         } else {
             double vt = fma(hdt, acc, v);
-            free_ring_polymer_step<NB>(s_to, s_from, cay, lane, group_base, r, vt);
+            frp.step(r, vt);
             acc = -M::gradient_dof(p.params, r) / mass;     // classical.jl:63-67
             v = fma(hdt, acc, vt);
         }
