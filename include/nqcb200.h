@@ -245,6 +245,18 @@ int nqcb200_set_draws(nqcb200_handle* h, const double* xi, int64_t nsteps);
  * reference: perform_step! -> hop callback -> save.                              */
 int nqcb200_run(nqcb200_handle* h, int64_t nsteps);
 
+/* One batch of the ensemble in one call: nqcb200_set_state (diabatic == 0: sigma / state in the adiabatic basis) or
+ * nqcb200_set_state_diabatic (diabatic != 0) followed by nqcb200_run(nsteps) -- what EnsembleB200's __solve does per
+ * batch with the arrays prob_func produced (selections.jl:38-101 -> solve, run_dynamics.jl:91-97).  For kernel
+ * families with a launch-fused initialisation (SpinBoson FSSH / Ehrenfest) the step kernel itself reads r and v in
+ * the caller's trajectory-major layout: from PINNED (cudaHostAlloc / cudaHostRegister) memory in place over PCIe,
+ * block by block, overlapping the dynamics of the blocks already loaded; pageable memory is staged with one
+ * cudaMemcpy.  Blocking; r and v must stay valid until it returns.  Other kernel families: identical to the two
+ * separate calls.                                                                                */
+int nqcb200_run_from_host(nqcb200_handle* h, const double* r, const double* v, const double* rho_re,
+                          const double* rho_im, const int32_t* state, const double* state_draw, int diabatic,
+                          int64_t nsteps);
+
 /* Download the current DynamicsVariables (any pointer may be NULL to skip that field). */
 int nqcb200_get_state(nqcb200_handle* h, double* r, double* v,
                       double* sig_re, double* sig_im, int32_t* state);

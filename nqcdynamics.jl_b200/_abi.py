@@ -91,6 +91,7 @@ def bind(lib: C.CDLL, prefix: str) -> None:
     f("set_gauge_reference", [H, _dp, C.c_int64])
     f("set_draws", [H, _dp, C.c_int64])
     f("run", [H, C.c_int64])
+    f("run_from_host", [H, _dp, _dp, _dp, _dp, _ip, _dp, C.c_int, C.c_int64], required=False)
     f("get_state", [H, _dp, _dp, _dp, _dp, _ip])
     f("get_mapping", [H, _dp, _dp])
     f("get_observable_sum", [H, C.c_int, _dp, C.c_int64])
@@ -107,7 +108,7 @@ def bind(lib: C.CDLL, prefix: str) -> None:
 
 HEADER_SYMBOLS = [
     "version", "device_count", "create", "destroy", "last_error", "observable_width", "set_state",
-    "set_state_diabatic", "set_mapping", "set_gauge_reference", "set_draws", "run", "get_state", "get_mapping",
+    "set_state_diabatic", "set_mapping", "set_gauge_reference", "set_draws", "run", "run_from_host", "get_state", "get_mapping",
     "get_observable_sum", "observable_sum_device", "observable_offset", "get_observable_per_trajectory",
     "get_diagnostics", "get_counters", "get_iesh_stats", "get_progress", "get_last_run_timing", "measure_fp64_peak",
 ]
@@ -213,6 +214,20 @@ class CHandle:
 
     def run(self, nsteps: int):
         self._call("run", C.c_int64(int(nsteps)))
+
+    def run_from_host(self, r, v, rho_re=None, rho_im=None, state=None, state_draw=None, diabatic=True, nsteps=0):
+        """set_state[_diabatic] + run in one call (nqcb200_run_from_host): pinned r / v are read in place by the kernel."""
+        r_, v_, sre_, sim_, st_ = self._state_args(r, v, rho_re, rho_im, state)
+        dr_ = _as_f64(state_draw, self.T) if state_draw is not None else None
+        if not hasattr(self._lib, self._p + "run_from_host"):      # the CPU oracle mirrors the two separate calls
+            if diabatic:
+                self._call("set_state_diabatic", _ptr(r_), _ptr(v_), _ptr(sre_), _ptr(sim_), _ptr(st_, _ip), _ptr(dr_))
+            else:
+                self._call("set_state", _ptr(r_), _ptr(v_), _ptr(sre_), _ptr(sim_), _ptr(st_, _ip))
+            self._call("run", C.c_int64(int(nsteps)))
+            return
+        self._call("run_from_host", _ptr(r_), _ptr(v_), _ptr(sre_), _ptr(sim_), _ptr(st_, _ip), _ptr(dr_),
+                   C.c_int(1 if diabatic else 0), C.c_int64(int(nsteps)))
 
     def get_state(self):
         T, B, D, n = self.T, self.B, self.D, self.n

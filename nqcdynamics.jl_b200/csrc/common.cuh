@@ -83,6 +83,12 @@ struct KParams {
     double* qmap;   // [B*n][T]
     double* pmap;
     double* sb_carry; // [2][T]  SpinBoson thread-per-trajectory kernel: force scalars (A, B) carried between launches
+    // launch-fused initialisation (nqcb200_run_from_host, kernels with KernelSet::fused_init): trajectory-major
+    // [T][B*D] sources read by the step kernel itself at step0 == 0 (device staging or pinned host memory)
+    const double* r_aos;
+    const double* v_aos;
+    int32_t init_basis, init_sample_state;
+    const double* init_state_draw;
     // AdiabaticIESH: psi / occupations are TRAJECTORY-major ([T][n*ne], [T][ne]); see kernel_iesh.cuh
     IeshLayout iesh;
     double* iesh_lam;   // [T][n]   adiabatic energies of the last step (warm start of the root finder)

@@ -123,4 +123,55 @@ NQ_HD void propagate_density(const ElecParams<N>& cur, double tcur, const ElecPa
 }
 #undef NQ_FOR_HERM
 
+// Two-state specialisation (every BASELINE config except ThreeStateMorse / IESH): G = g [[0,1],[-1,0]], so
+//     dx00 = -2 g x01 = -dx11 ,   dx01 = dE y01 + g (x00 - x11) ,   dy01 = -dE x01 ,
+// 10 FP64 instructions per RHS instead of the generic commutator's ~40, and the x11 stage sums are the negated
+// x00 ones (bit-identical to carrying them separately).  Same Tsit5 staging as the generic version above.
+template <>
+NQ_HD void propagate_density<2>(const ElecParams<2>& cur, double tcur, const ElecParams<2>& nxt, double tnext,
+                                double t, double dt, Herm<2>& s) {
+    using namespace tsit5;
+    const double h = dt / 5.0;
+    const double inv_span = 1.0 / (tnext - tcur);
+    const bool flat = !(fabs(inv_span) <= 1.0e300);   // zero span: the reference's isnan(loc) -> 0 branch
+    const double dEc = cur.E[0] - cur.E[1], dEd = (nxt.E[0] - nxt.E[1]) - dEc;
+    const double gc = cur.g[0], gd = nxt.g[0] - gc;
+    struct K { double a, b, c; };   // d x00 (= -d x11), d x01, d y01
+    double x00 = s.x[0], x01 = s.x[1], x11 = s.x[2], y01 = s.y[0];
+    auto rhs = [&](double tau, double u00, double u01, double u11, double w01, K& k) {
+        const double l = flat ? 0.0 : (tau - tcur) * inv_span;
+        const double dE = fma(dEd, l, dEc), g = fma(gd, l, gc);
+        k.a = -((g + g) * u01);
+        k.b = fma(dE, w01, g * (u00 - u11));
+        k.c = -(dE * u01);
+    };
+    K k1, k2, k3, k4, k5, k6;
+    double ts = t;
+    rhs(ts, x00, x01, x11, y01, k1);
+#pragma unroll 1
+    for (int sub = 0; sub < 5; ++sub) {
+        const double hh = (sub == 4) ? (t + dt) - ts : h;   // tstop snapping of the last sub-step
+#define NQ_STAGE2(SA, SB, SC, TAU, KOUT)                                                                       \
+        { const double sa_ = (SA), sb_ = (SB), sc_ = (SC);                                                      \
+          rhs((TAU), fma(hh, sa_, x00), fma(hh, sb_, x01), fma(-hh, sa_, x11), fma(hh, sc_, y01), KOUT); }
+        NQ_STAGE2(a21 * k1.a, a21 * k1.b, a21 * k1.c, ts + c1 * hh, k2)
+        NQ_STAGE2(a31 * k1.a + a32 * k2.a, a31 * k1.b + a32 * k2.b, a31 * k1.c + a32 * k2.c, ts + c2 * hh, k3)
+        NQ_STAGE2(a41 * k1.a + a42 * k2.a + a43 * k3.a, a41 * k1.b + a42 * k2.b + a43 * k3.b,
+                  a41 * k1.c + a42 * k2.c + a43 * k3.c, ts + c3 * hh, k4)
+        NQ_STAGE2(a51 * k1.a + a52 * k2.a + a53 * k3.a + a54 * k4.a, a51 * k1.b + a52 * k2.b + a53 * k3.b + a54 * k4.b,
+                  a51 * k1.c + a52 * k2.c + a53 * k3.c + a54 * k4.c, ts + c4 * hh, k5)
+        NQ_STAGE2(a61 * k1.a + a62 * k2.a + a63 * k3.a + a64 * k4.a + a65 * k5.a,
+                  a61 * k1.b + a62 * k2.b + a63 * k3.b + a64 * k4.b + a65 * k5.b,
+                  a61 * k1.c + a62 * k2.c + a63 * k3.c + a64 * k4.c + a65 * k5.c, ts + hh, k6)
+#undef NQ_STAGE2
+        const double sa = a71 * k1.a + a72 * k2.a + a73 * k3.a + a74 * k4.a + a75 * k5.a + a76 * k6.a;
+        const double sb = a71 * k1.b + a72 * k2.b + a73 * k3.b + a74 * k4.b + a75 * k5.b + a76 * k6.b;
+        const double sc = a71 * k1.c + a72 * k2.c + a73 * k3.c + a74 * k4.c + a75 * k5.c + a76 * k6.c;
+        x00 = fma(hh, sa, x00); x11 = fma(-hh, sa, x11); x01 = fma(hh, sb, x01); y01 = fma(hh, sc, y01);
+        ts = (sub == 4) ? (t + dt) : ts + hh;
+        if (sub < 4) rhs(ts, x00, x01, x11, y01, k1);   // FSAL
+    }
+    s.x[0] = x00; s.x[1] = x01; s.x[2] = x11; s.y[0] = y01;
+}
+
 }  // namespace nq

@@ -140,6 +140,7 @@ struct nqcb200_handle {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<void*> allocs;
     double* staging = nullptr;      // trajectory-major staging for uploads / downloads
+    double* aos_stage[2] = {nullptr, nullptr};   // run_from_host: trajectory-major r, v when the caller's memory is pageable
     size_t staging_doubles = 0;
     double* obs_folded = nullptr;
     double* d_draws = nullptr;
@@ -220,8 +221,9 @@ int launch_init(nqcb200_handle* h, int basis, int sample_state, const double* st
     return NQCB200_OK;
 }
 
+// fused: r / v are NOT uploaded and no init kernel runs -- the next step launch reads them itself (KParams.r_aos)
 int set_state_impl(nqcb200_handle* h, const double* r, const double* v, const double* sre, const double* sim,
-                   const int32_t* state, int basis, const double* state_draw) {
+                   const int32_t* state, int basis, const double* state_draw, bool fused = false) {
     if (!h) return NQCB200_ERR_INVALID;
     if (!r || !v) { h->err = "r and v are required"; return NQCB200_ERR_INVALID; }
     const nqcb200_config& c = h->cfg;
@@ -234,8 +236,10 @@ int set_state_impl(nqcb200_handle* h, const double* r, const double* v, const do
     NQ_CUDA(h, cudaSetDevice(c.device));
     int rc;
     const int BD = c.nbeads * c.ndofs;
-    if ((rc = upload_field(h, r, h->kp.r, BD)) != 0) return rc;
-    if ((rc = upload_field(h, v, h->kp.v, BD)) != 0) return rc;
+    if (!fused) {
+        if ((rc = upload_field(h, r, h->kp.r, BD)) != 0) return rc;
+        if ((rc = upload_field(h, v, h->kp.v, BD)) != 0) return rc;
+    }
     if (density) {
         if ((rc = upload_field(h, sre, h->kp.sig_re, h->nsig)) != 0) return rc;
         if (sim) { if ((rc = upload_field(h, sim, h->kp.sig_im, h->nsig)) != 0) return rc; }
@@ -276,12 +280,15 @@ int set_state_impl(nqcb200_handle* h, const double* r, const double* v, const do
     h->step_count = 0;
     h->kp.step0 = 0;
     h->kp.nsteps = 0;
-    if (T > 0 && c.method != NQCB200_METHOD_NRPMD) {   // NRPMD: save point 0 is recorded by set_mapping
+    h->kp.init_basis = basis;
+    h->kp.init_sample_state = sample_state;
+    h->kp.init_state_draw = (sample_state && state_draw) ? h->d_state_draw : nullptr;
+    if (T > 0 && c.method != NQCB200_METHOD_NRPMD && !fused) {   // NRPMD: save point 0 is recorded by set_mapping
         if (iesh) rc = launch_init(h, h->user_gauge ? 1 : 0, 0, nullptr);
         else rc = launch_init(h, basis, sample_state, (sample_state && state_draw) ? h->d_state_draw : nullptr);
         if (rc) return rc;
     }
-    NQ_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (!fused) NQ_CUDA(h, cudaStreamSynchronize(h->stream));
     h->nsave_done = (c.method == NQCB200_METHOD_NRPMD) ? 0 : 1;
     h->has_state = (c.method != NQCB200_METHOD_NRPMD);
     h->has_nuclei = true;
@@ -609,6 +616,44 @@ int nqcb200_run(nqcb200_handle* h, int64_t nsteps) {
     h->step_count += nsteps;
     h->nsave_done = std::min<int64_t>(c.nsave, h->step_count / c.save_every + 1);
     return NQCB200_OK;
+}
+
+int nqcb200_run_from_host(nqcb200_handle* h, const double* r, const double* v, const double* rho_re, const double* rho_im,
+                          const int32_t* state, const double* state_draw, int diabatic, int64_t nsteps) {
+    if (!h || nsteps < 0) return NQCB200_ERR_INVALID;
+    const nqcb200_config& c = h->cfg;
+    const bool density = (c.method == NQCB200_METHOD_FSSH || c.method == NQCB200_METHOD_EHRENFEST);
+    if (!diabatic && c.method == NQCB200_METHOD_FSSH && !state) { h->err = "FSSH needs the active state (or a diabatic rho)"; return NQCB200_ERR_INVALID; }
+    int rc;
+    if (!h->ks.fused_init || !density || c.ntraj == 0 || nsteps == 0 || h->user_gauge) {
+        // no launch-fused initialisation for this kernel family: plain upload, then run
+        if ((rc = set_state_impl(h, r, v, rho_re, rho_im, state, diabatic ? 1 : 0, diabatic ? state_draw : nullptr)) != 0) return rc;
+        return nqcb200_run(h, nsteps);
+    }
+    NQ_CUDA(h, cudaSetDevice(c.device));
+    if ((rc = set_state_impl(h, r, v, rho_re, rho_im, state, diabatic ? 1 : 0, diabatic ? state_draw : nullptr, true)) != 0) return rc;
+    // r, v: pinned (or registered) host memory is read in place by the step kernel over PCIe, so the upload of later
+    // blocks overlaps the dynamics of earlier ones; pageable memory goes through a trajectory-major device staging copy
+    const size_t count = (size_t)c.ntraj * c.nbeads * c.ndofs;
+    const double* src[2] = {r, v};
+    const double* dev[2] = {nullptr, nullptr};
+    for (int i = 0; i < 2; ++i) {
+        cudaPointerAttributes at;
+        bool mapped = false;
+        if (cudaPointerGetAttributes(&at, src[i]) == cudaSuccess) {
+            if (at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged) { dev[i] = (const double*)at.devicePointer; mapped = dev[i] != nullptr; }
+            else if (at.type == cudaMemoryTypeDevice) { dev[i] = src[i]; mapped = true; }
+        } else cudaGetLastError();
+        if (!mapped) {
+            if (!h->aos_stage[i]) { if ((rc = dev_alloc(h, &h->aos_stage[i], count)) != 0) return rc; }
+            NQ_CUDA(h, cudaMemcpyAsync(h->aos_stage[i], src[i], sizeof(double) * count, cudaMemcpyHostToDevice, h->stream));
+            dev[i] = h->aos_stage[i];
+        }
+    }
+    h->kp.r_aos = dev[0]; h->kp.v_aos = dev[1];
+    rc = nqcb200_run(h, nsteps);
+    h->kp.r_aos = nullptr; h->kp.v_aos = nullptr;
+    return rc;
 }
 
 int nqcb200_get_state(nqcb200_handle* h, double* r, double* v, double* sig_re, double* sig_im, int32_t* state) {

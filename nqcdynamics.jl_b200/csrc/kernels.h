@@ -22,6 +22,7 @@ struct KernelSet {
     int step_block = 0;
     size_t step_smem = 0;
     bool needs_sb_carry = false;   // kernel_spinboson.cuh: two force scalars per trajectory carried between launches
+    bool fused_init = false;       // the step kernel can initialise from KParams.r_aos / v_aos (see common.cuh)
     bool cta_per_trajectory = false;
     IeshLayout iesh = {};   // AdiabaticIESH tile / shared-memory plan (kernel_iesh.cuh)
     const char* name = "";

@@ -33,9 +33,15 @@ bool select_density_spinboson(const nqcb200_config& c, KernelSet& out, std::stri
     if (lanes == 0 && D >= 2 && sb_smem_bytes(D) <= 220 * 1024 && (m == NQCB200_METHOD_FSSH || m == NQCB200_METHOD_EHRENFEST)) {
         bool ok = (D <= 8) ? pick<8, 1>(m, out) : (D <= 104) ? pick<13, 8>(m, out) : pick<4, 32>(m, out);   // init kernel
         if (!ok) return false;
-        out.step = (m == NQCB200_METHOD_FSSH) ? spinboson_step_kernel<NQCB200_METHOD_FSSH>
-                                              : spinboson_step_kernel<NQCB200_METHOD_EHRENFEST>;
-        out.step_L = 1; out.step_block = kSbThreads; out.step_smem = sb_smem_bytes(D);
+        // two lanes per trajectory (two warps per scheduler) once the sweep is long enough to split
+        int lpt = (D >= 16) ? 2 : 1;
+        if (const char* env = getenv("NQCB200_SPINBOSON_LPT")) { const int v = atoi(env); if (v == 1 || v == 2) lpt = v; }
+        if (lpt == 2) out.step = (m == NQCB200_METHOD_FSSH) ? spinboson_step_kernel<NQCB200_METHOD_FSSH, 2>
+                                                            : spinboson_step_kernel<NQCB200_METHOD_EHRENFEST, 2>;
+        else out.step = (m == NQCB200_METHOD_FSSH) ? spinboson_step_kernel<NQCB200_METHOD_FSSH, 1>
+                                                   : spinboson_step_kernel<NQCB200_METHOD_EHRENFEST, 1>;
+        out.step_L = lpt; out.step_block = kSbTraj * lpt; out.step_smem = sb_smem_bytes(D);
+        out.fused_init = true;
         out.needs_sb_carry = true;
         out.name = (m == NQCB200_METHOD_FSSH) ? "spinboson_fssh_tpt" : "spinboson_ehrenfest_tpt";
         return true;

@@ -183,6 +183,50 @@ def test_spin_boson_parity(method, nmodes):
 
 
 @pytest.mark.parametrize("method", [A.METHOD_FSSH, A.METHOD_EHRENFEST])
+@pytest.mark.parametrize("nmodes,pinned", [(3, False), (37, True), (100, True), (100, False)])
+def test_spin_boson_run_from_host(method, nmodes, pinned):
+    """nqcb200_run_from_host: launch-fused initialisation straight from the caller's trajectory-major arrays
+    (pinned: read in place over PCIe; pageable: staged) == set_state_diabatic + run == the oracle.  Population
+    observables only (the kernel then skips the harmonic shift of the eigenvalues), ragged last block."""
+    T, nsteps = 300, 45
+    rng = np.random.default_rng(17)
+    model = nq.SpinBoson(nq.DebyeSpectralDensity(0.25, 0.5), nmodes, 0.1, 1.0)
+    obs = (1 << A.OBS_POPCORR_DIABATIC) | (1 << A.OBS_ADIABATIC_POP) | (1 << A.OBS_DIABATIC_POP) | (1 << A.OBS_SIGMA)
+    kw = model_config(model, method=method, masses=np.ones(nmodes), ntraj=T, dt=0.1, rng=A.RNG_INJECTED,
+                      save_every=3, nsave=nsteps // 3 + 1, observables=obs, per_trajectory=1)
+    mk = engine_factory()
+    cfgs = [A.make_config(**kw) for _ in range(3)]
+    fused, plain = mk(*cfgs[0]), mk(*cfgs[1])
+    o = oracle_factory()(*cfgs[2])
+    w = model.bath_a
+    sr = np.sqrt(1.0 / (2 * w * np.tanh(2.5 * w))); sv = np.sqrt(w / (2 * np.tanh(2.5 * w)))
+    r = rng.standard_normal((T, nmodes)) * sr
+    v = rng.standard_normal((T, nmodes)) * sv
+    if pinned:
+        import torch
+        r_h = torch.from_numpy(r.copy()).pin_memory().numpy()
+        v_h = torch.from_numpy(v.copy()).pin_memory().numpy()
+    else:
+        r_h, v_h = r, v
+    rho = _pure_state(T, 2, 0)
+    draws = rng.random((nsteps, T)); sdraw = rng.random(T)
+    fused.set_draws(draws)
+    fused.run_from_host(r_h, v_h, rho, None, None, sdraw, diabatic=True, nsteps=30)
+    fused.run(nsteps - 30)
+    for h in (plain, o):
+        h.set_state_diabatic(r, v, rho, None, None, sdraw)
+        h.set_draws(draws)
+        h.run(nsteps)
+    _compare_state(fused, o, 1e-9, "fused vs oracle")
+    _compare_state(fused, plain, 1e-12, "fused vs two-call")
+    _compare_observables(fused, o, obs, 1e-9, T)
+    for oid in (A.OBS_DIABATIC_POP, A.OBS_SIGMA):
+        assert np.max(np.abs(fused.observable_per_trajectory(oid) - o.observable_per_trajectory(oid))) < 1e-9
+    assert fused.counters()["hops"] == o.counters()["hops"]
+    assert fused.counters()["frustrated"] == o.counters()["frustrated"]
+
+
+@pytest.mark.parametrize("method", [A.METHOD_FSSH, A.METHOD_EHRENFEST])
 @pytest.mark.parametrize("nbeads", [4, 16, 32])
 @pytest.mark.parametrize("name,model,mass,r0,v0,temp", [
     ("tully1", nq.TullyModelOne(), 2000.0, -4.0, 10.0 / 2000, 1e-3),
