@@ -112,7 +112,8 @@ def run_cpu_oracle(wl, seconds, seed=1):
     import oracle
     import nqcdynamics_jl_b200 as nq
     A = nq._abi
-    cores = oracle.set_num_threads(0)
+    # all host cores the process may use (torchrun exports OMP_NUM_THREADS=1, which is not what is measured here)
+    cores = oracle.set_num_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     rng = np.random.default_rng(seed)
 
     # the large-bath IESH oracle takes ~0.1-10 s per trajectory-step: bound the sample by shortening the run

@@ -72,6 +72,21 @@ constexpr double a71 = 0.09646076681806523, a72 = 0.01, a73 = 0.4798896504144996
                  a75 = -3.290069515436081, a76 = 2.324710524099774;
 }  // namespace tsit5
 
+// The same coefficients in the constant bank: an FP64 immediate cannot be encoded in a DFMA, so compile-time
+// constants cost a UMOV pair per use (9 % of the issued instructions of the SpinBoson kernel, profiles/r01); a
+// constant-bank operand is free.
+#if defined(__CUDACC__)
+namespace tsit5 {
+enum { I_c1, I_c2, I_c3, I_c4, I_a21, I_a31, I_a32, I_a41, I_a42, I_a43, I_a51, I_a52, I_a53, I_a54, I_a61, I_a62, I_a63, I_a64, I_a65, I_a71, I_a72, I_a73, I_a74, I_a75, I_a76, I_COUNT };
+}
+static __constant__ double kTsit5Dev[tsit5::I_COUNT] = {tsit5::c1, tsit5::c2, tsit5::c3, tsit5::c4, tsit5::a21, tsit5::a31, tsit5::a32, tsit5::a41, tsit5::a42, tsit5::a43, tsit5::a51, tsit5::a52, tsit5::a53, tsit5::a54, tsit5::a61, tsit5::a62, tsit5::a63, tsit5::a64, tsit5::a65, tsit5::a71, tsit5::a72, tsit5::a73, tsit5::a74, tsit5::a75, tsit5::a76};
+#endif
+#if defined(__CUDA_ARCH__)
+#define NQ_TS(name) kTsit5Dev[tsit5::I_##name]
+#else
+#define NQ_TS(name) tsit5::name
+#endif
+
 #define NQ_FOR_HERM(expr)                                              \
     _Pragma("unroll") for (int i_ = 0; i_ < sym_size(N); ++i_) { auto& o = tmp.x[i_]; const int i = i_; const bool isx = true; expr; } \
     _Pragma("unroll") for (int i_ = 0; i_ < asym_size(N); ++i_) { auto& o = tmp.y[i_]; const int i = i_; const bool isx = false; expr; }
@@ -98,24 +113,24 @@ NQ_HD void propagate_density(const ElecParams<N>& cur, double tcur, const ElecPa
 #define NQ_STAGE(EXPRX, EXPRY)                                                              \
         _Pragma("unroll") for (int i = 0; i < sym_size(N); ++i) tmp.x[i] = s.x[i] + hh * (EXPRX);  \
         _Pragma("unroll") for (int i = 0; i < asym_size(N); ++i) tmp.y[i] = s.y[i] + hh * (EXPRY);
-        NQ_STAGE(a21 * k1.x[i], a21 * k1.y[i])
-        density_rhs<N>(cur, nxt, loc_of(ts + c1 * hh), tmp, k2);
-        NQ_STAGE(a31 * k1.x[i] + a32 * k2.x[i], a31 * k1.y[i] + a32 * k2.y[i])
-        density_rhs<N>(cur, nxt, loc_of(ts + c2 * hh), tmp, k3);
-        NQ_STAGE(a41 * k1.x[i] + a42 * k2.x[i] + a43 * k3.x[i], a41 * k1.y[i] + a42 * k2.y[i] + a43 * k3.y[i])
-        density_rhs<N>(cur, nxt, loc_of(ts + c3 * hh), tmp, k4);
-        NQ_STAGE(a51 * k1.x[i] + a52 * k2.x[i] + a53 * k3.x[i] + a54 * k4.x[i],
-                 a51 * k1.y[i] + a52 * k2.y[i] + a53 * k3.y[i] + a54 * k4.y[i])
-        density_rhs<N>(cur, nxt, loc_of(ts + c4 * hh), tmp, k5);
-        NQ_STAGE(a61 * k1.x[i] + a62 * k2.x[i] + a63 * k3.x[i] + a64 * k4.x[i] + a65 * k5.x[i],
-                 a61 * k1.y[i] + a62 * k2.y[i] + a63 * k3.y[i] + a64 * k4.y[i] + a65 * k5.y[i])
+        NQ_STAGE(NQ_TS(a21) * k1.x[i], NQ_TS(a21) * k1.y[i])
+        density_rhs<N>(cur, nxt, loc_of(ts + NQ_TS(c1) * hh), tmp, k2);
+        NQ_STAGE(NQ_TS(a31) * k1.x[i] + NQ_TS(a32) * k2.x[i], NQ_TS(a31) * k1.y[i] + NQ_TS(a32) * k2.y[i])
+        density_rhs<N>(cur, nxt, loc_of(ts + NQ_TS(c2) * hh), tmp, k3);
+        NQ_STAGE(NQ_TS(a41) * k1.x[i] + NQ_TS(a42) * k2.x[i] + NQ_TS(a43) * k3.x[i], NQ_TS(a41) * k1.y[i] + NQ_TS(a42) * k2.y[i] + NQ_TS(a43) * k3.y[i])
+        density_rhs<N>(cur, nxt, loc_of(ts + NQ_TS(c3) * hh), tmp, k4);
+        NQ_STAGE(NQ_TS(a51) * k1.x[i] + NQ_TS(a52) * k2.x[i] + NQ_TS(a53) * k3.x[i] + NQ_TS(a54) * k4.x[i],
+                 NQ_TS(a51) * k1.y[i] + NQ_TS(a52) * k2.y[i] + NQ_TS(a53) * k3.y[i] + NQ_TS(a54) * k4.y[i])
+        density_rhs<N>(cur, nxt, loc_of(ts + NQ_TS(c4) * hh), tmp, k5);
+        NQ_STAGE(NQ_TS(a61) * k1.x[i] + NQ_TS(a62) * k2.x[i] + NQ_TS(a63) * k3.x[i] + NQ_TS(a64) * k4.x[i] + NQ_TS(a65) * k5.x[i],
+                 NQ_TS(a61) * k1.y[i] + NQ_TS(a62) * k2.y[i] + NQ_TS(a63) * k3.y[i] + NQ_TS(a64) * k4.y[i] + NQ_TS(a65) * k5.y[i])
         density_rhs<N>(cur, nxt, loc_of(ts + hh), tmp, k6);
 #pragma unroll
         for (int i = 0; i < sym_size(N); ++i)
-            s.x[i] = s.x[i] + hh * (a71 * k1.x[i] + a72 * k2.x[i] + a73 * k3.x[i] + a74 * k4.x[i] + a75 * k5.x[i] + a76 * k6.x[i]);
+            s.x[i] = s.x[i] + hh * (NQ_TS(a71) * k1.x[i] + NQ_TS(a72) * k2.x[i] + NQ_TS(a73) * k3.x[i] + NQ_TS(a74) * k4.x[i] + NQ_TS(a75) * k5.x[i] + NQ_TS(a76) * k6.x[i]);
 #pragma unroll
         for (int i = 0; i < asym_size(N); ++i)
-            s.y[i] = s.y[i] + hh * (a71 * k1.y[i] + a72 * k2.y[i] + a73 * k3.y[i] + a74 * k4.y[i] + a75 * k5.y[i] + a76 * k6.y[i]);
+            s.y[i] = s.y[i] + hh * (NQ_TS(a71) * k1.y[i] + NQ_TS(a72) * k2.y[i] + NQ_TS(a73) * k3.y[i] + NQ_TS(a74) * k4.y[i] + NQ_TS(a75) * k5.y[i] + NQ_TS(a76) * k6.y[i]);
 #undef NQ_STAGE
         ts = (sub == 4) ? (t + dt) : ts + hh;
         if (sub < 4) density_rhs<N>(cur, nxt, loc_of(ts), s, k1);  // FSAL: k7 of this sub-step = k1 of the next
@@ -154,19 +169,19 @@ NQ_HD void propagate_density<2>(const ElecParams<2>& cur, double tcur, const Ele
 #define NQ_STAGE2(SA, SB, SC, TAU, KOUT)                                                                       \
         { const double sa_ = (SA), sb_ = (SB), sc_ = (SC);                                                      \
           rhs((TAU), fma(hh, sa_, x00), fma(hh, sb_, x01), fma(-hh, sa_, x11), fma(hh, sc_, y01), KOUT); }
-        NQ_STAGE2(a21 * k1.a, a21 * k1.b, a21 * k1.c, ts + c1 * hh, k2)
-        NQ_STAGE2(a31 * k1.a + a32 * k2.a, a31 * k1.b + a32 * k2.b, a31 * k1.c + a32 * k2.c, ts + c2 * hh, k3)
-        NQ_STAGE2(a41 * k1.a + a42 * k2.a + a43 * k3.a, a41 * k1.b + a42 * k2.b + a43 * k3.b,
-                  a41 * k1.c + a42 * k2.c + a43 * k3.c, ts + c3 * hh, k4)
-        NQ_STAGE2(a51 * k1.a + a52 * k2.a + a53 * k3.a + a54 * k4.a, a51 * k1.b + a52 * k2.b + a53 * k3.b + a54 * k4.b,
-                  a51 * k1.c + a52 * k2.c + a53 * k3.c + a54 * k4.c, ts + c4 * hh, k5)
-        NQ_STAGE2(a61 * k1.a + a62 * k2.a + a63 * k3.a + a64 * k4.a + a65 * k5.a,
-                  a61 * k1.b + a62 * k2.b + a63 * k3.b + a64 * k4.b + a65 * k5.b,
-                  a61 * k1.c + a62 * k2.c + a63 * k3.c + a64 * k4.c + a65 * k5.c, ts + hh, k6)
+        NQ_STAGE2(NQ_TS(a21) * k1.a, NQ_TS(a21) * k1.b, NQ_TS(a21) * k1.c, ts + NQ_TS(c1) * hh, k2)
+        NQ_STAGE2(NQ_TS(a31) * k1.a + NQ_TS(a32) * k2.a, NQ_TS(a31) * k1.b + NQ_TS(a32) * k2.b, NQ_TS(a31) * k1.c + NQ_TS(a32) * k2.c, ts + NQ_TS(c2) * hh, k3)
+        NQ_STAGE2(NQ_TS(a41) * k1.a + NQ_TS(a42) * k2.a + NQ_TS(a43) * k3.a, NQ_TS(a41) * k1.b + NQ_TS(a42) * k2.b + NQ_TS(a43) * k3.b,
+                  NQ_TS(a41) * k1.c + NQ_TS(a42) * k2.c + NQ_TS(a43) * k3.c, ts + NQ_TS(c3) * hh, k4)
+        NQ_STAGE2(NQ_TS(a51) * k1.a + NQ_TS(a52) * k2.a + NQ_TS(a53) * k3.a + NQ_TS(a54) * k4.a, NQ_TS(a51) * k1.b + NQ_TS(a52) * k2.b + NQ_TS(a53) * k3.b + NQ_TS(a54) * k4.b,
+                  NQ_TS(a51) * k1.c + NQ_TS(a52) * k2.c + NQ_TS(a53) * k3.c + NQ_TS(a54) * k4.c, ts + NQ_TS(c4) * hh, k5)
+        NQ_STAGE2(NQ_TS(a61) * k1.a + NQ_TS(a62) * k2.a + NQ_TS(a63) * k3.a + NQ_TS(a64) * k4.a + NQ_TS(a65) * k5.a,
+                  NQ_TS(a61) * k1.b + NQ_TS(a62) * k2.b + NQ_TS(a63) * k3.b + NQ_TS(a64) * k4.b + NQ_TS(a65) * k5.b,
+                  NQ_TS(a61) * k1.c + NQ_TS(a62) * k2.c + NQ_TS(a63) * k3.c + NQ_TS(a64) * k4.c + NQ_TS(a65) * k5.c, ts + hh, k6)
 #undef NQ_STAGE2
-        const double sa = a71 * k1.a + a72 * k2.a + a73 * k3.a + a74 * k4.a + a75 * k5.a + a76 * k6.a;
-        const double sb = a71 * k1.b + a72 * k2.b + a73 * k3.b + a74 * k4.b + a75 * k5.b + a76 * k6.b;
-        const double sc = a71 * k1.c + a72 * k2.c + a73 * k3.c + a74 * k4.c + a75 * k5.c + a76 * k6.c;
+        const double sa = NQ_TS(a71) * k1.a + NQ_TS(a72) * k2.a + NQ_TS(a73) * k3.a + NQ_TS(a74) * k4.a + NQ_TS(a75) * k5.a + NQ_TS(a76) * k6.a;
+        const double sb = NQ_TS(a71) * k1.b + NQ_TS(a72) * k2.b + NQ_TS(a73) * k3.b + NQ_TS(a74) * k4.b + NQ_TS(a75) * k5.b + NQ_TS(a76) * k6.b;
+        const double sc = NQ_TS(a71) * k1.c + NQ_TS(a72) * k2.c + NQ_TS(a73) * k3.c + NQ_TS(a74) * k4.c + NQ_TS(a75) * k5.c + NQ_TS(a76) * k6.c;
         x00 = fma(hh, sa, x00); x11 = fma(-hh, sa, x11); x01 = fma(hh, sb, x01); y01 = fma(hh, sc, y01);
         ts = (sub == 4) ? (t + dt) : ts + hh;
         if (sub < 4) rhs(ts, x00, x01, x11, y01, k1);   // FSAL

@@ -437,7 +437,7 @@ __global__ void __launch_bounds__(kSbTraj * LPT, 1) spinboson_step_kernel(const 
                                   : philox_uniform(p.seed, (uint64_t)(p.traj_offset + traj), (uint64_t)step, 0u);
             const int s0 = R.st, m = 1 - s0;
             // fewest_switches_probability! fssh.jl:96-108 (Q4) + select_new_state :110-121 for two states
-            double g = 2.0 * (R.s.x[1] / (s0 ? R.s.x[2] : R.s.x[0])) * nxt.G(s0, m) * dt;
+            double g = 2.0 * (R.s.x[1] / (s0 ? R.s.x[2] : R.s.x[0])) * (s0 ? -nxt.g[0] : nxt.g[0]) * dt;   // G(s0, m)
             g = fmin(1.0, fmax(0.0, g));
             if (g > xi) {
                 bool accept = true;
