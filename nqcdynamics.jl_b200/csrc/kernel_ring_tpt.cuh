@@ -1,0 +1,452 @@
+// kernel_ring_tpt.cuh -- RPSH / RP-Ehrenfest with ONE THREAD per trajectory.
+//
+// Same reference path as kernel_ring.cuh (BCBwithTsit5, bcb_electronics.jl:53-97; centroid hopping,
+// SurfaceHoppingMethods.jl:85-103, rpsh.jl:30-64; ehrenfest_rpmd.jl:23-51), different decomposition.  With the
+// beads on lanes, the centroid eigenproblem and the 31-RHS Tsit5 electronic propagation -- 3/4 of the work for
+// ThreeStateMorse -- were replicated on all NB lanes of a trajectory (ncu, profiles/r01: 125 k FP64 instructions
+// per trajectory-step, of which ~95 k redundant).  Here a thread owns the whole ring polymer:
+//   * bead coordinates, velocities and accelerations live in shared memory, [field][bead][thread]
+//     (conflict-free), and are visited bead by bead (model, NxN Jacobi, force);
+//   * the free ring-polymer step is an in-register radix-2 FFT of z_b = r_b + i v_b (same algebra as
+//     FreeRingPolymer in kernel_ring.cuh, coefficient tables in shared memory);
+//   * the centroid eigenproblem, NAC, Tsit5, hop and rescaling are done once per trajectory in registers.
+// FSSH needs no per-bead eigenvector gauge (the bead force is the diagonal element of Z' dV Z, which does not
+// depend on the column signs); RP-Ehrenfest uses off-diagonal elements, so its per-bead gauge references are
+// carried in shared memory as well.
+#pragma once
+#include "kernel_ring.cuh"
+
+namespace nq {
+
+#if defined(__CUDACC__)
+
+constexpr int kRtThreads = kBlockThreads;   // 128 (the Emitter's block reduction is sized for it)
+
+template <int N, int NB, int METHOD>
+NQ_HD constexpr size_t ring_tpt_smem_bytes() {
+    return ((size_t)(3 + (METHOD == NQCB200_METHOD_EHRENFEST ? N * N : 0)) * NB * kRtThreads + 6 * NB) * sizeof(double);
+}
+
+template <int NB>
+struct RtTables {      // per block, thread-uniform
+    const double* twr;  // [NB/2]  Re W^j, W = exp(-2 pi i / NB)
+    const double* twi;  // [NB/2]
+    const double* al;   // [2 NB]  alpha_k (re, im) with 1/NB folded in
+    const double* be;   // [2 NB]  beta_k
+};
+
+template <int NB>
+NQ_D constexpr int rt_log2() { return (NB >= 32) ? 5 : (NB >= 16) ? 4 : (NB >= 8) ? 3 : (NB >= 4) ? 2 : (NB >= 2) ? 1 : 0; }
+template <int NB>
+NQ_D constexpr int rt_bitrev(int x) {
+    int r = 0;
+    for (int b = 0; b < rt_log2<NB>(); ++b) r |= ((x >> b) & 1) << (rt_log2<NB>() - 1 - b);
+    return r;
+}
+
+// to-normal-modes -> Cayley -> back for one ring polymer held in registers (see FreeRingPolymer for the algebra)
+template <int NB>
+NQ_D void rt_free_step(const RtTables<NB>& tb, double (&zr)[NB], double (&zi)[NB]) {
+    constexpr int LOG = rt_log2<NB>();
+#pragma unroll
+    for (int s = 0; s < LOG; ++s) {          // DIF: natural in, bit-reversed out
+        const int h = NB >> (s + 1);
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+            if ((i & h) == 0) {
+                const int j = i & (h - 1), tw = j * (NB / (2 * h));
+                const double ur = zr[i], ui = zi[i], tr = zr[i + h], ti = zi[i + h];
+                zr[i] = ur + tr; zi[i] = ui + ti;
+                const double dr = ur - tr, di = ui - ti;
+                if (tw == 0) { zr[i + h] = dr; zi[i + h] = di; }
+                else {
+                    const double wr = tb.twr[tw], wi = tb.twi[tw];
+                    zr[i + h] = fma(dr, wr, -di * wi); zi[i + h] = fma(dr, wi, di * wr);
+                }
+            }
+        }
+    }
+    double nr[NB], ni[NB];
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {           // Z'_k = alpha_k Z_k + beta_k conj(Z_{NB-k})
+        const int k = rt_bitrev<NB>(i), ip = rt_bitrev<NB>((NB - k) % NB);
+        const double ar = tb.al[2 * k], ai = tb.al[2 * k + 1], br = tb.be[2 * k], bi = tb.be[2 * k + 1];
+        const double wr = zr[ip], wi = -zi[ip];
+        nr[i] = fma(ar, zr[i], fma(-ai, zi[i], fma(br, wr, -bi * wi)));
+        ni[i] = fma(ar, zi[i], fma(ai, zr[i], fma(br, wi, bi * wr)));
+    }
+#pragma unroll
+    for (int s = LOG - 1; s >= 0; --s) {     // DIT: bit-reversed in, natural out
+        const int h = NB >> (s + 1);
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+            if ((i & h) == 0) {
+                const int j = i & (h - 1), tw = j * (NB / (2 * h));
+                double tr = nr[i + h], ti = ni[i + h];
+                if (tw != 0) {
+                    const double wr = tb.twr[tw], wi = tb.twi[tw];
+                    const double xr = fma(tr, wr, ti * wi), xi = fma(ti, wr, -tr * wi);   // conj(twiddle)
+                    tr = xr; ti = xi;
+                }
+                const double ur = nr[i], ui = ni[i];
+                nr[i] = ur + tr; ni[i] = ui + ti;
+                nr[i + h] = ur - tr; ni[i + h] = ui - ti;
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NB; ++i) { zr[i] = nr[i]; zi[i] = ni[i]; }
+}
+
+template <int N, int NB, int METHOD>
+NQ_D void rt_record_save(const KParams& p, Emitter& em, const double* s_r, const double* s_v, int tid, const Herm<N>& s,
+                         int st, const Eig<N>& ec, double pot, double mass) {
+    const uint32_t obs = p.observables;
+    const int64_t T = p.ntraj;
+    double adi[N], dia[N];
+    adiabatic_population<N, METHOD>(s, st, adi);
+    diabatic_population<N, METHOD>(s, st, ec, dia);   // centroid transformation (density_matrix_dynamics.jl:83-87)
+    if (em.isave == 0 && em.active && (obs & ((1u << NQCB200_OBS_POPCORR_DIABATIC) | (1u << NQCB200_OBS_POPCORR_ADIABATIC)))) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) { p.pop0[(int64_t)i * T + em.traj] = dia[i]; p.pop0[(int64_t)(N + i) * T + em.traj] = adi[i]; }
+    }
+    if (obs & (1u << NQCB200_OBS_ADIABATIC_POP)) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) em.emit(NQCB200_OBS_ADIABATIC_POP, i, adi[i]);
+    }
+    if (obs & (1u << NQCB200_OBS_DIABATIC_POP)) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) em.emit(NQCB200_OBS_DIABATIC_POP, i, dia[i]);
+    }
+    if (obs & (1u << NQCB200_OBS_POPCORR_DIABATIC)) {
+        double p0[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) p0[i] = (em.isave == 0) ? dia[i] : p.pop0[(int64_t)i * T + em.traj];
+#pragma unroll
+        for (int j = 0; j < N; ++j)
+#pragma unroll
+            for (int i = 0; i < N; ++i) em.emit(NQCB200_OBS_POPCORR_DIABATIC, i + N * j, p0[i] * dia[j]);
+    }
+    if (obs & (1u << NQCB200_OBS_POPCORR_ADIABATIC)) {
+        double p0[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) p0[i] = (em.isave == 0) ? adi[i] : p.pop0[(int64_t)(N + i) * T + em.traj];
+#pragma unroll
+        for (int j = 0; j < N; ++j)
+#pragma unroll
+            for (int i = 0; i < N; ++i) em.emit(NQCB200_OBS_POPCORR_ADIABATIC, i + N * j, p0[i] * adi[j]);
+    }
+    double rsum = 0.0, vsum = 0.0, mv2 = 0.0, spr = 0.0;
+    {
+        double rprev = s_r[(NB - 1) * kRtThreads + tid];
+        for (int b = 0; b < NB; ++b) {
+            const double rb = s_r[b * kRtThreads + tid], vb = s_v[b * kRtThreads + tid];
+            rsum += rb; vsum += vb;
+            mv2 = fma(mass * vb, vb, mv2);
+            const double d = rprev - rb;       // every neighbouring pair once (ring_polymer.jl:89-107)
+            spr = fma(mass * d, d, spr);
+            rprev = rb;
+        }
+    }
+    if (obs & ((1u << NQCB200_OBS_KINETIC) | (1u << NQCB200_OBS_POTENTIAL) | (1u << NQCB200_OBS_TOTAL_ENERGY))) {
+        const double kin = 0.5 * mv2;
+        if (obs & (1u << NQCB200_OBS_KINETIC)) em.emit(NQCB200_OBS_KINETIC, 0, kin);
+        if (obs & (1u << NQCB200_OBS_POTENTIAL)) em.emit(NQCB200_OBS_POTENTIAL, 0, pot);
+        if (obs & (1u << NQCB200_OBS_TOTAL_ENERGY))
+            em.emit(NQCB200_OBS_TOTAL_ENERGY, 0, kin + pot + ((NB == 1) ? 0.0 : 0.5 * p.omega_n * p.omega_n * spr));
+    }
+    if (obs & (1u << NQCB200_OBS_POSITION)) em.emit(NQCB200_OBS_POSITION, 0, rsum / NB);
+    if (obs & (1u << NQCB200_OBS_VELOCITY)) em.emit(NQCB200_OBS_VELOCITY, 0, vsum / NB);
+    if (obs & (1u << NQCB200_OBS_DISCRETE_STATE)) em.emit(NQCB200_OBS_DISCRETE_STATE, 0, (double)(st + 1));
+    const bool last = (em.isave == p.nsave - 1);
+    if (obs & ((1u << NQCB200_OBS_SCATTERING) | (1u << NQCB200_OBS_SCATTERING_DIABATIC))) {
+        const bool trans = s_r[tid] > 0.0;   // get_positions(final)[1]: first dof of the first bead (DynamicsOutputs.jl:332)
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            if (obs & (1u << NQCB200_OBS_SCATTERING)) {
+                em.emit(NQCB200_OBS_SCATTERING, i, (last && !trans) ? adi[i] : 0.0);
+                em.emit(NQCB200_OBS_SCATTERING, N + i, (last && trans) ? adi[i] : 0.0);
+            }
+            if (obs & (1u << NQCB200_OBS_SCATTERING_DIABATIC)) {
+                em.emit(NQCB200_OBS_SCATTERING_DIABATIC, i, (last && !trans) ? dia[i] : 0.0);
+                em.emit(NQCB200_OBS_SCATTERING_DIABATIC, N + i, (last && trans) ? dia[i] : 0.0);
+            }
+        }
+    }
+    if (obs & (1u << NQCB200_OBS_SIGMA)) {
+#pragma unroll
+        for (int k = 0; k < N; ++k)
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                em.emit(NQCB200_OBS_SIGMA, j + N * k, s.X(j, k));
+                em.emit(NQCB200_OBS_SIGMA, N * N + j + N * k, s.Y(j, k));
+            }
+    }
+}
+
+template <class M, int NB, int METHOD>
+__global__ void __launch_bounds__(kRtThreads) ring_tpt_step_kernel(const __grid_constant__ KParams p) {
+    constexpr int N = M::NS;
+    constexpr bool EHR = (METHOD == NQCB200_METHOD_EHRENFEST);
+    static_assert(NB >= 2 && (NB & (NB - 1)) == 0, "ring polymer FFT: nbeads must be a power of two");
+    extern __shared__ __align__(16) double rt_sm[];
+    __shared__ double red[2 * (kRtThreads / 32)];
+    double* s_r = rt_sm;
+    double* s_v = s_r + NB * kRtThreads;
+    double* s_a = s_v + NB * kRtThreads;
+    double* s_Z = s_a + NB * kRtThreads;                       // EHR only: [bead][N*N][thread]
+    double* s_tab = s_Z + (EHR ? N * N * NB * kRtThreads : 0);  // twr[NB/2] twi[NB/2] al[2NB] be[2NB]
+    const int tid = threadIdx.x;
+    int64_t traj = (int64_t)blockIdx.x * kRtThreads + tid;
+    const bool valid = traj < p.ntraj;
+    if (!valid) traj = p.ntraj - 1;
+    const int64_t T = p.ntraj;
+
+    // coefficient tables (thread-uniform)
+    for (int j = tid; j < NB; j += kRtThreads) {
+        if (j < NB / 2) {
+            double si, co;
+            sincospi(-2.0 * (double)j / (double)NB, &si, &co);
+            s_tab[j] = co; s_tab[NB / 2 + j] = si;
+        }
+        const double a = p.cayley[4 * j + 0], b = p.cayley[4 * j + 1], c = p.cayley[4 * j + 2], d = p.cayley[4 * j + 3];
+        const double inv = 0.5 / NB;
+        s_tab[NB + 2 * j] = (a + d) * inv; s_tab[NB + 2 * j + 1] = (c - b) * inv;
+        s_tab[3 * NB + 2 * j] = (a - d) * inv; s_tab[3 * NB + 2 * j + 1] = (c + b) * inv;
+    }
+    RtTables<NB> tb{s_tab, s_tab + NB / 2, s_tab + NB, s_tab + 3 * NB};
+
+    for (int b = 0; b < NB; ++b) {
+        s_r[b * kRtThreads + tid] = p.r[(int64_t)b * T + traj];
+        s_v[b * kRtThreads + tid] = p.v[(int64_t)b * T + traj];
+        s_a[b * kRtThreads + tid] = p.acc[(int64_t)b * T + traj];
+        if (EHR) {
+            for (int jk = 0; jk < N * N; ++jk)
+                s_Z[(b * N * N + jk) * kRtThreads + tid] = p.Zprev[((int64_t)b * N * N + jk) * T + traj];
+        }
+    }
+    __syncthreads();
+
+    const double mass = p.masses[0];
+    Herm<N> s;
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+#pragma unroll
+        for (int k = j; k < N; ++k) {
+            s.x[sidx(N, j, k)] = p.sig_re[(int64_t)(j + N * k) * T + traj];
+            if (k > j) s.y[aidx(N, j, k)] = p.sig_im[(int64_t)(j + N * k) * T + traj];
+        }
+    int st = p.state ? p.state[traj] : 0;
+    double Zc[N][N];
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+#pragma unroll
+        for (int k = 0; k < N; ++k) Zc[j][k] = p.Zprev[((int64_t)NB * N * N + j + N * k) * T + traj];
+    ElecParams<N> cur;
+#pragma unroll
+    for (int i = 0; i < N; ++i) cur.E[i] = p.ecur[(int64_t)i * T + traj];
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+#pragma unroll
+        for (int k = j + 1; k < N; ++k) cur.g[aidx(N, j, k)] = p.ecur[(int64_t)(N + j + N * k) * T + traj];
+
+    Eig<N> ec;
+    double Ac[sym_size(N)];
+    unsigned long long nhops = 0, nfrus = 0;
+    const double dt = p.dt, hdt = 0.5 * p.dt;
+
+#pragma unroll 1
+    for (int is = 0; is < p.nsteps; ++is) {
+        const int64_t step = p.step0 + is;
+        const double t = p.t0 + dt * (double)step;
+        const double tcur = (step == 0) ? 0.0 : t;   // Q1
+        // B (half kick) + C (free ring polymer)  bcb_electronics.jl:62-71
+        {
+            double zr[NB], zi[NB];
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+                zr[b] = s_r[b * kRtThreads + tid];
+                zi[b] = fma(hdt, s_a[b * kRtThreads + tid], s_v[b * kRtThreads + tid]);
+            }
+            rt_free_step<NB>(tb, zr, zi);
+#pragma unroll
+            for (int b = 0; b < NB; ++b) { s_r[b * kRtThreads + tid] = zr[b]; s_v[b * kRtThreads + tid] = zi[b]; }
+        }
+        // update_cache! on every bead (bcb_electronics.jl:73), force, second half kick
+        double rsum = 0.0, vsum = 0.0;
+        double wsum[N];      // sum over beads of the adiabatic energies (potential outputs use the post-hop state)
+#pragma unroll
+        for (int i = 0; i < N; ++i) wsum[i] = 0.0;
+#pragma unroll 1
+        for (int b = 0; b < NB; ++b) {
+            const double q = s_r[b * kRtThreads + tid];
+            const double rr[1] = {q}, zz[1] = {0.0};
+            double Vp[sym_size(N)], dVp[sym_size(N)];
+            Eig<N> eb;
+            M::template potential_partial<1>(p.params, rr, zz, zz, true, Vp);
+            sym_eigh<N>(Vp, eb);
+            M::derivative_dof(p.params, q, 0.0, 0.0, dVp);
+            double f;
+            if (EHR) {
+                double Zb[N][N];
+#pragma unroll
+                for (int j = 0; j < N; ++j)
+#pragma unroll
+                    for (int k = 0; k < N; ++k) Zb[j][k] = s_Z[(b * N * N + j + N * k) * kRtThreads + tid];
+                fix_gauge<N>(eb, Zb);
+#pragma unroll
+                for (int j = 0; j < N; ++j)
+#pragma unroll
+                    for (int k = 0; k < N; ++k) s_Z[(b * N * N + j + N * k) * kRtThreads + tid] = Zb[j][k];
+                double Ab[sym_size(N)];
+                similarity<N>(dVp, eb.Z, Ab);
+                f = force_from_adiab<N, METHOD>(Ab, st, s);
+            } else {
+                // -(Z' dV Z)[st, st]: only the eigenvector of the occupied state is needed (fssh.jl:67-74)
+                double z[N];
+#pragma unroll
+                for (int a = 0; a < N; ++a) z[a] = select<N>(eb.Z[a], st);
+                double acc2 = 0.0;
+#pragma unroll
+                for (int a = 0; a < N; ++a) {
+                    double row = 0.0;
+#pragma unroll
+                    for (int c = 0; c < N; ++c) row += dVp[(a <= c) ? sidx(N, a, c) : sidx(N, c, a)] * z[c];
+                    acc2 += z[a] * row;
+                }
+                f = -acc2;
+            }
+#pragma unroll
+            for (int i = 0; i < N; ++i) wsum[i] += eb.w[i];
+            const double acc = f / mass;
+            const double vb = fma(hdt, acc, s_v[b * kRtThreads + tid]);
+            s_a[b * kRtThreads + tid] = acc;
+            s_v[b * kRtThreads + tid] = vb;
+            rsum += q; vsum += vb;
+        }
+        const double rcent = rsum / NB, vcent = vsum / NB;
+        eval_point<M>(p, rcent, Zc, ec, Ac);
+        ElecParams<N> nxt;
+#pragma unroll
+        for (int i = 0; i < N; ++i) nxt.E[i] = ec.w[i];
+#pragma unroll
+        for (int j = 0; j < N; ++j)
+#pragma unroll
+            for (int k = j + 1; k < N; ++k) nxt.g[aidx(N, j, k)] = (-Ac[sidx(N, j, k)] / (ec.w[j] - ec.w[k])) * vcent;
+        propagate_density<N>(cur, tcur, nxt, t + dt, t, dt, s);
+
+        if (METHOD == NQCB200_METHOD_FSSH) {
+            const double xi = (p.rng == NQCB200_RNG_INJECTED)
+                                  ? p.draws[(step - p.draws_step0) * T + traj]
+                                  : philox_uniform(p.seed, (uint64_t)(p.traj_offset + traj), (uint64_t)step, 0u);
+            const int s0 = st;
+            const double inv_ss = 1.0 / s.X(s0, s0);
+            double cum = 0.0;
+            int new_state = s0;
+#pragma unroll
+            for (int m = 0; m < N; ++m) {
+                double g = 0.0;
+                if (m != s0) g = 2.0 * (s.X(m, s0) * inv_ss) * nxt.G(s0, m) * dt;
+                g = fmin(1.0, fmax(0.0, g));
+                cum += g;
+                if (new_state == s0 && m != s0 && cum > xi) new_state = m;
+            }
+            if (new_state != s0) {
+                bool accept = true;
+                double dv = 0.0;     // the same velocity change on every bead (rpsh.jl:30-50)
+                if (p.rescaling != NQCB200_RESCALE_OFF) {
+                    const double wn = select<N>(ec.w, new_state), wo = select<N>(ec.w, s0);
+                    double ano = 0.0;
+#pragma unroll
+                    for (int j = 0; j < N; ++j)
+#pragma unroll
+                        for (int k = j + 1; k < N; ++k)
+                            ano = ((j == new_state && k == s0) || (k == new_state && j == s0)) ? Ac[sidx(N, j, k)] : ano;
+                    const double d = -ano / (wn - wo);
+                    const double a = 0.5 * d * d / mass, b = d * vcent, c = wn - wo;
+                    const double disc = b * b - 4.0 * a * c;
+                    if (disc < 0.0) {
+                        accept = false;
+                        nfrus += valid;
+                        if (p.rescaling == NQCB200_RESCALE_VINVERSION) {
+                            const double dn = d / fabs(d);
+                            dv = -2.0 * (vcent * dn) * dn;
+                        }
+                    } else {
+                        const double root = sqrt(disc);
+                        const double gam = (b < 0.0) ? (b + root) / (2.0 * a) : (b - root) / (2.0 * a);
+                        dv = -(gam * d / mass);
+                    }
+                }
+                if (dv != 0.0) {
+                    for (int b = 0; b < NB; ++b) s_v[b * kRtThreads + tid] += dv;
+                }
+                if (accept) { st = new_state; nhops += valid; }
+            }
+        }
+        cur = nxt;
+
+        if ((step + 1) % p.save_every == 0) {
+            const int64_t isave = (step + 1) / p.save_every;
+            if (isave < p.nsave) {
+                double pot = 0.0;     // rpsh.jl:52-64, ehrenfest_rpmd.jl:45-51
+                if (EHR) {
+#pragma unroll
+                    for (int i = 0; i < N; ++i) pot += s.x[sidx(N, i, i)] * wsum[i];
+                } else pot = select<N>(wsum, st);
+                Emitter em{p, traj, valid, (int)isave, red, 0};
+                rt_record_save<N, NB, METHOD>(p, em, s_r, s_v, tid, s, st, ec, pot, mass);
+            }
+        }
+    }
+
+    if (valid) {
+        for (int b = 0; b < NB; ++b) {
+            p.r[(int64_t)b * T + traj] = s_r[b * kRtThreads + tid];
+            p.v[(int64_t)b * T + traj] = s_v[b * kRtThreads + tid];
+            p.acc[(int64_t)b * T + traj] = s_a[b * kRtThreads + tid];
+            if (EHR) {
+                for (int jk = 0; jk < N * N; ++jk)
+                    p.Zprev[((int64_t)b * N * N + jk) * T + traj] = s_Z[(b * N * N + jk) * kRtThreads + tid];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < N; ++j)
+#pragma unroll
+            for (int k = 0; k < N; ++k) {
+                p.sig_re[(int64_t)(j + N * k) * T + traj] = s.X(j, k);
+                p.sig_im[(int64_t)(j + N * k) * T + traj] = s.Y(j, k);
+                p.Zprev[((int64_t)NB * N * N + j + N * k) * T + traj] = Zc[j][k];
+            }
+        if (p.state) p.state[traj] = st;
+#pragma unroll
+        for (int i = 0; i < N; ++i) p.ecur[(int64_t)i * T + traj] = cur.E[i];
+#pragma unroll
+        for (int j = 0; j < N; ++j)
+#pragma unroll
+            for (int k = j + 1; k < N; ++k) p.ecur[(int64_t)(N + j + N * k) * T + traj] = cur.g[aidx(N, j, k)];
+        if (p.diagnostics) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) p.diag_eig[(int64_t)i * T + traj] = ec.w[i];
+#pragma unroll
+            for (int j = 0; j < N; ++j)
+#pragma unroll
+                for (int k = 0; k < N; ++k) {
+                    p.diag_Z[(int64_t)(j + N * k) * T + traj] = ec.Z[j][k];
+                    double d = 0.0;
+                    if (j != k) d = -((j < k) ? Ac[sidx(N, j, k)] : Ac[sidx(N, k, j)]) / (ec.w[j] - ec.w[k]);
+                    p.diag_nac[(int64_t)(j + N * k) * T + traj] = d;
+                }
+        }
+    }
+    const unsigned long long wh = __reduce_add_sync(0xffffffffu, (unsigned)nhops);
+    const unsigned long long wf = __reduce_add_sync(0xffffffffu, (unsigned)nfrus);
+    if ((threadIdx.x & 31) == 0) {
+        if (wh) atomicAdd(&p.counters[0], wh);
+        if (wf) atomicAdd(&p.counters[1], wf);
+    }
+}
+
+#endif  // __CUDACC__
+
+}  // namespace nq

@@ -1,5 +1,8 @@
 // tu_ring.cu -- RPSH / RP-Ehrenfest kernels (beads on lanes).
+#include <cstdlib>
+
 #include "kernel_ring.cuh"
+#include "kernel_ring_tpt.cuh"
 
 namespace nq {
 namespace {
@@ -13,6 +16,17 @@ bool pick(int method, KernelSet& out, const char* name) {
         out.init = ring_init_kernel<M, NB, NQCB200_METHOD_EHRENFEST>;
     } else return false;
     out.L = NB; out.DPL = 1; out.name = name;
+    // step kernel: one thread per trajectory with the beads in shared memory (kernel_ring_tpt.cuh) when they fit;
+    // the beads-on-lanes kernel stays as the fallback (and as an A/B switch: NQCB200_RING_TPT=0)
+    const char* env = getenv("NQCB200_RING_TPT");
+    const bool want = !(env && atoi(env) == 0);
+    if (want && method == NQCB200_METHOD_FSSH && ring_tpt_smem_bytes<M::NS, NB, NQCB200_METHOD_FSSH>() <= 200 * 1024) {
+        out.step = ring_tpt_step_kernel<M, NB, NQCB200_METHOD_FSSH>;
+        out.step_L = 1; out.step_block = kRtThreads; out.step_smem = ring_tpt_smem_bytes<M::NS, NB, NQCB200_METHOD_FSSH>();
+    } else if (want && method == NQCB200_METHOD_EHRENFEST && ring_tpt_smem_bytes<M::NS, NB, NQCB200_METHOD_EHRENFEST>() <= 200 * 1024) {
+        out.step = ring_tpt_step_kernel<M, NB, NQCB200_METHOD_EHRENFEST>;
+        out.step_L = 1; out.step_block = kRtThreads; out.step_smem = ring_tpt_smem_bytes<M::NS, NB, NQCB200_METHOD_EHRENFEST>();
+    }
     return true;
 }
 template <class M>
