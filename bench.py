@@ -217,7 +217,7 @@ def main():
         ic["psi"], ic["state"] = wl.iesh_ground_state(T)
 
     def upload(h, r, v, psi=None):
-        return wl.upload(h, {"r": r, "v": v, "psi": ic.get("psi") if psi is None else psi, "state": ic.get("state")}, rho)
+        return wl.upload(h, {**ic, "r": r, "v": v, "psi": ic.get("psi") if psi is None else psi}, rho)
 
     upload(eng, ic["r"], ic["v"])
     peak = __import__("ctypes").c_double()

@@ -271,12 +271,10 @@ NQ_D void ring_store(const KParams& p, int64_t traj, int lane, const RingRegs<N,
 template <class M>
 NQ_D void eval_point(const KParams& p, double q, double (&Zref)[M::NS][M::NS], Eig<M::NS>& e, double (&Ap)[sym_size(M::NS)]) {
     constexpr int N = M::NS;
-    const double rr[1] = {q}, zz[1] = {0.0};
     double Vp[sym_size(N)], dVp[sym_size(N)];
-    M::template potential_partial<1>(p.params, rr, zz, zz, true, Vp);
+    model_value_and_derivative<M>(p.params, q, Vp, dVp);
     sym_eigh<N>(Vp, e);
     fix_gauge<N>(e, Zref);
-    M::derivative_dof(p.params, q, 0.0, 0.0, dVp);
     similarity<N>(dVp, e.Z, Ap);
 }
 

@@ -22,9 +22,9 @@ namespace nq {
 
 constexpr int kRtThreads = kBlockThreads;   // 128 (the Emitter's block reduction is sized for it)
 
-template <int N, int NB, int METHOD>
-NQ_HD constexpr size_t ring_tpt_smem_bytes() {
-    return ((size_t)(3 + (METHOD == NQCB200_METHOD_EHRENFEST ? N * N : 0)) * NB * kRtThreads + 6 * NB) * sizeof(double);
+// fft: nbeads is a power of two (compile-time NBT); otherwise the dense normal-mode product through two scratch rows
+NQ_HD constexpr size_t ring_tpt_smem_bytes(int N, int NB, bool ehrenfest, bool fft) {
+    return ((size_t)(3 + (ehrenfest ? N * N : 0) + (fft ? 0 : 2)) * NB * kRtThreads + (fft ? 6 * NB : NB * NB + 4 * NB)) * sizeof(double);
 }
 
 template <int NB>
@@ -98,9 +98,10 @@ NQ_D void rt_free_step(const RtTables<NB>& tb, double (&zr)[NB], double (&zi)[NB
     for (int i = 0; i < NB; ++i) { zr[i] = nr[i]; zi[i] = ni[i]; }
 }
 
-template <int N, int NB, int METHOD>
-NQ_D void rt_record_save(const KParams& p, Emitter& em, const double* s_r, const double* s_v, int tid, const Herm<N>& s,
-                         int st, const Eig<N>& ec, double pot, double mass) {
+// r_b = s_r[b * stride + idx] (shared memory: stride 128, idx = thread; global memory: stride T, idx = trajectory)
+template <int N, int METHOD>
+NQ_D void rt_record_save(const KParams& p, Emitter& em, int NB, const double* s_r, const double* s_v, int64_t stride,
+                         int64_t idx, const Herm<N>& s, int st, const Eig<N>& ec, double pot, double mass) {
     const uint32_t obs = p.observables;
     const int64_t T = p.ntraj;
     double adi[N], dia[N];
@@ -138,9 +139,9 @@ NQ_D void rt_record_save(const KParams& p, Emitter& em, const double* s_r, const
     }
     double rsum = 0.0, vsum = 0.0, mv2 = 0.0, spr = 0.0;
     {
-        double rprev = s_r[(NB - 1) * kRtThreads + tid];
+        double rprev = s_r[(NB - 1) * stride + idx];
         for (int b = 0; b < NB; ++b) {
-            const double rb = s_r[b * kRtThreads + tid], vb = s_v[b * kRtThreads + tid];
+            const double rb = s_r[b * stride + idx], vb = s_v[b * stride + idx];
             rsum += rb; vsum += vb;
             mv2 = fma(mass * vb, vb, mv2);
             const double d = rprev - rb;       // every neighbouring pair once (ring_polymer.jl:89-107)
@@ -153,14 +154,14 @@ NQ_D void rt_record_save(const KParams& p, Emitter& em, const double* s_r, const
         if (obs & (1u << NQCB200_OBS_KINETIC)) em.emit(NQCB200_OBS_KINETIC, 0, kin);
         if (obs & (1u << NQCB200_OBS_POTENTIAL)) em.emit(NQCB200_OBS_POTENTIAL, 0, pot);
         if (obs & (1u << NQCB200_OBS_TOTAL_ENERGY))
-            em.emit(NQCB200_OBS_TOTAL_ENERGY, 0, kin + pot + ((NB == 1) ? 0.0 : 0.5 * p.omega_n * p.omega_n * spr));
+            em.emit(NQCB200_OBS_TOTAL_ENERGY, 0, kin + pot + 0.5 * p.omega_n * p.omega_n * spr);
     }
     if (obs & (1u << NQCB200_OBS_POSITION)) em.emit(NQCB200_OBS_POSITION, 0, rsum / NB);
     if (obs & (1u << NQCB200_OBS_VELOCITY)) em.emit(NQCB200_OBS_VELOCITY, 0, vsum / NB);
     if (obs & (1u << NQCB200_OBS_DISCRETE_STATE)) em.emit(NQCB200_OBS_DISCRETE_STATE, 0, (double)(st + 1));
     const bool last = (em.isave == p.nsave - 1);
     if (obs & ((1u << NQCB200_OBS_SCATTERING) | (1u << NQCB200_OBS_SCATTERING_DIABATIC))) {
-        const bool trans = s_r[tid] > 0.0;   // get_positions(final)[1]: first dof of the first bead (DynamicsOutputs.jl:332)
+        const bool trans = s_r[idx] > 0.0;   // get_positions(final)[1]: first dof of the first bead (DynamicsOutputs.jl:332)
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             if (obs & (1u << NQCB200_OBS_SCATTERING)) {
@@ -184,18 +185,23 @@ NQ_D void rt_record_save(const KParams& p, Emitter& em, const double* s_r, const
     }
 }
 
-template <class M, int NB, int METHOD>
+// NBT > 0: nbeads = NBT, a power of two (FFT in registers).  NBT == 0: any nbeads (p.B), dense normal-mode product.
+template <class M, int NBT, int METHOD>
 __global__ void __launch_bounds__(kRtThreads) ring_tpt_step_kernel(const __grid_constant__ KParams p) {
     constexpr int N = M::NS;
     constexpr bool EHR = (METHOD == NQCB200_METHOD_EHRENFEST);
-    static_assert(NB >= 2 && (NB & (NB - 1)) == 0, "ring polymer FFT: nbeads must be a power of two");
+    constexpr bool FFT = NBT > 0;
+    static_assert(NBT == 0 || (NBT >= 2 && (NBT & (NBT - 1)) == 0), "ring polymer FFT: nbeads must be a power of two");
+    constexpr int NBF = FFT ? NBT : 2;      // array extent of the FFT path (unused when dense)
+    const int NB = FFT ? NBT : p.B;
     extern __shared__ __align__(16) double rt_sm[];
     __shared__ double red[2 * (kRtThreads / 32)];
     double* s_r = rt_sm;
     double* s_v = s_r + NB * kRtThreads;
     double* s_a = s_v + NB * kRtThreads;
     double* s_Z = s_a + NB * kRtThreads;                       // EHR only: [bead][N*N][thread]
-    double* s_tab = s_Z + (EHR ? N * N * NB * kRtThreads : 0);  // twr[NB/2] twi[NB/2] al[2NB] be[2NB]
+    double* s_t = s_Z + (EHR ? N * N * NB * kRtThreads : 0);    // dense only: two scratch rows [2][bead][thread]
+    double* s_tab = s_t + (FFT ? 0 : 2 * NB * kRtThreads);      // FFT: twr[NB/2] twi[NB/2] al[2NB] be[2NB]; dense: U[NB*NB] cay[4NB]
     const int tid = threadIdx.x;
     int64_t traj = (int64_t)blockIdx.x * kRtThreads + tid;
     const bool valid = traj < p.ntraj;
@@ -203,7 +209,11 @@ __global__ void __launch_bounds__(kRtThreads) ring_tpt_step_kernel(const __grid_
     const int64_t T = p.ntraj;
 
     // coefficient tables (thread-uniform)
-    for (int j = tid; j < NB; j += kRtThreads) {
+    if (!FFT) {
+        for (int i = tid; i < NB * NB; i += kRtThreads) s_tab[i] = p.nm_to[i];            // U[j,k] at j*NB + k
+        for (int i = tid; i < 4 * NB; i += kRtThreads) s_tab[NB * NB + i] = p.cayley[i];
+    }
+    for (int j = tid; FFT && j < NB; j += kRtThreads) {
         if (j < NB / 2) {
             double si, co;
             sincospi(-2.0 * (double)j / (double)NB, &si, &co);
@@ -214,7 +224,7 @@ __global__ void __launch_bounds__(kRtThreads) ring_tpt_step_kernel(const __grid_
         s_tab[NB + 2 * j] = (a + d) * inv; s_tab[NB + 2 * j + 1] = (c - b) * inv;
         s_tab[3 * NB + 2 * j] = (a - d) * inv; s_tab[3 * NB + 2 * j + 1] = (c + b) * inv;
     }
-    RtTables<NB> tb{s_tab, s_tab + NB / 2, s_tab + NB, s_tab + 3 * NB};
+    RtTables<NBF> tb{s_tab, s_tab + NB / 2, s_tab + NB, s_tab + 3 * NB};
 
     for (int b = 0; b < NB; ++b) {
         s_r[b * kRtThreads + tid] = p.r[(int64_t)b * T + traj];
@@ -261,16 +271,41 @@ __global__ void __launch_bounds__(kRtThreads) ring_tpt_step_kernel(const __grid_
         const double t = p.t0 + dt * (double)step;
         const double tcur = (step == 0) ? 0.0 : t;   // Q1
         // B (half kick) + C (free ring polymer)  bcb_electronics.jl:62-71
-        {
-            double zr[NB], zi[NB];
+        if constexpr (FFT) {
+            double zr[NBF], zi[NBF];
 #pragma unroll
-            for (int b = 0; b < NB; ++b) {
+            for (int b = 0; b < NBF; ++b) {
                 zr[b] = s_r[b * kRtThreads + tid];
                 zi[b] = fma(hdt, s_a[b * kRtThreads + tid], s_v[b * kRtThreads + tid]);
             }
-            rt_free_step<NB>(tb, zr, zi);
+            rt_free_step<NBF>(tb, zr, zi);
 #pragma unroll
-            for (int b = 0; b < NB; ++b) { s_r[b * kRtThreads + tid] = zr[b]; s_v[b * kRtThreads + tid] = zi[b]; }
+            for (int b = 0; b < NBF; ++b) { s_r[b * kRtThreads + tid] = zr[b]; s_v[b * kRtThreads + tid] = zi[b]; }
+        } else {
+            // dense U' .. Cayley .. U (RingPolymerArrays transform!, steps.jl:10-17)
+            const double* U = s_tab;
+            const double* cay = s_tab + NB * NB;
+            for (int b = 0; b < NB; ++b) s_v[b * kRtThreads + tid] = fma(hdt, s_a[b * kRtThreads + tid], s_v[b * kRtThreads + tid]);
+            for (int k = 0; k < NB; ++k) {
+                double a = 0.0, c = 0.0;
+                for (int j = 0; j < NB; ++j) {
+                    const double u = U[j * NB + k];
+                    a = fma(u, s_r[j * kRtThreads + tid], a);
+                    c = fma(u, s_v[j * kRtThreads + tid], c);
+                }
+                s_t[k * kRtThreads + tid] = cay[4 * k + 0] * a + cay[4 * k + 1] * c;
+                s_t[(NB + k) * kRtThreads + tid] = cay[4 * k + 2] * a + cay[4 * k + 3] * c;
+            }
+            for (int j = 0; j < NB; ++j) {
+                double a = 0.0, c = 0.0;
+                for (int k = 0; k < NB; ++k) {
+                    const double u = U[j * NB + k];
+                    a = fma(u, s_t[k * kRtThreads + tid], a);
+                    c = fma(u, s_t[(NB + k) * kRtThreads + tid], c);
+                }
+                s_r[j * kRtThreads + tid] = a;
+                s_v[j * kRtThreads + tid] = c;
+            }
         }
         // update_cache! on every bead (bcb_electronics.jl:73), force, second half kick
         double rsum = 0.0, vsum = 0.0;
@@ -280,12 +315,10 @@ __global__ void __launch_bounds__(kRtThreads) ring_tpt_step_kernel(const __grid_
 #pragma unroll 1
         for (int b = 0; b < NB; ++b) {
             const double q = s_r[b * kRtThreads + tid];
-            const double rr[1] = {q}, zz[1] = {0.0};
             double Vp[sym_size(N)], dVp[sym_size(N)];
             Eig<N> eb;
-            M::template potential_partial<1>(p.params, rr, zz, zz, true, Vp);
+            model_value_and_derivative<M>(p.params, q, Vp, dVp);
             sym_eigh<N>(Vp, eb);
-            M::derivative_dof(p.params, q, 0.0, 0.0, dVp);
             double f;
             if (EHR) {
                 double Zb[N][N];
@@ -395,7 +428,7 @@ __global__ void __launch_bounds__(kRtThreads) ring_tpt_step_kernel(const __grid_
                     for (int i = 0; i < N; ++i) pot += s.x[sidx(N, i, i)] * wsum[i];
                 } else pot = select<N>(wsum, st);
                 Emitter em{p, traj, valid, (int)isave, red, 0};
-                rt_record_save<N, NB, METHOD>(p, em, s_r, s_v, tid, s, st, ec, pot, mass);
+                rt_record_save<N, METHOD>(p, em, NB, s_r, s_v, kRtThreads, tid, s, st, ec, pot, mass);
             }
         }
     }
@@ -445,6 +478,224 @@ __global__ void __launch_bounds__(kRtThreads) ring_tpt_step_kernel(const __grid_
         if (wh) atomicAdd(&p.counters[0], wh);
         if (wf) atomicAdd(&p.counters[1], wf);
     }
+}
+
+
+template <class M>
+NQ_D void classical_tpt_record_save(const KParams& p, Emitter& em, int NB, const double* s_r, const double* s_v,
+                                    int64_t stride, int64_t idx, double mass) {
+    const uint32_t obs = p.observables;
+    double rsum = 0.0, vsum = 0.0, mv2 = 0.0, spr = 0.0, pot = 0.0;
+    double rprev = s_r[(NB - 1) * stride + idx];
+    for (int b = 0; b < NB; ++b) {
+        const double rb = s_r[b * stride + idx], vb = s_v[b * stride + idx];
+        rsum += rb; vsum += vb;
+        mv2 = fma(mass * vb, vb, mv2);
+        pot += M::potential_dof(p.params, rb);
+        const double d = rprev - rb;
+        spr = fma(mass * d, d, spr);
+        rprev = rb;
+    }
+    if (NB == 1) spr = 0.0;
+    const double kin = 0.5 * mv2;
+    if (obs & (1u << NQCB200_OBS_KINETIC)) em.emit(NQCB200_OBS_KINETIC, 0, kin);
+    if (obs & (1u << NQCB200_OBS_POTENTIAL)) em.emit(NQCB200_OBS_POTENTIAL, 0, pot);
+    if (obs & (1u << NQCB200_OBS_TOTAL_ENERGY)) em.emit(NQCB200_OBS_TOTAL_ENERGY, 0, kin + pot + 0.5 * p.omega_n * p.omega_n * spr);
+    if (obs & (1u << NQCB200_OBS_POSITION)) em.emit(NQCB200_OBS_POSITION, 0, rsum / NB);
+    if (obs & (1u << NQCB200_OBS_VELOCITY)) em.emit(NQCB200_OBS_VELOCITY, 0, vsum / NB);
+}
+
+// DynamicsVariables at t0 for any nbeads, one thread per trajectory: same steps as ring_init_kernel (kernel_ring.cuh).
+template <class M, int METHOD>
+__global__ void __launch_bounds__(kRtThreads) ring_tpt_init_kernel(const __grid_constant__ KParams p, int basis,
+                                                                   int sample_state, const double* state_draw) {
+    constexpr int N = M::NS;
+    __shared__ double red[2 * (kRtThreads / 32)];
+    const int NB = p.B;
+    int64_t traj = (int64_t)blockIdx.x * kRtThreads + threadIdx.x;
+    const bool valid = traj < p.ntraj;
+    if (!valid) traj = p.ntraj - 1;
+    const int64_t T = p.ntraj;
+    const double mass = p.masses[0];
+    Herm<N> s;
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+#pragma unroll
+        for (int k = j; k < N; ++k) {
+            s.x[sidx(N, j, k)] = p.sig_re[(int64_t)(j + N * k) * T + traj];
+            if (k > j) s.y[aidx(N, j, k)] = p.sig_im[(int64_t)(j + N * k) * T + traj];
+        }
+    int st = p.state ? p.state[traj] : 0;
+    double Zc[N][N];
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+#pragma unroll
+        for (int k = 0; k < N; ++k) Zc[j][k] = p.Zprev[((int64_t)NB * N * N + j + N * k) * T + traj];
+    double rsum = 0.0;
+    for (int b = 0; b < NB; ++b) rsum += p.r[(int64_t)b * T + traj];
+    Eig<N> ec;
+    double Ac[sym_size(N)];
+    eval_point<M>(p, rsum / NB, Zc, ec, Ac);
+    if (basis == 1) {   // centroid transformation (density_matrix_dynamics.jl:83-87)
+        Herm<N> o;
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+#pragma unroll
+            for (int j = i; j < N; ++j) {
+                double sx = 0.0, sy = 0.0;
+#pragma unroll
+                for (int a = 0; a < N; ++a)
+#pragma unroll
+                    for (int b = 0; b < N; ++b) {
+                        sx += ec.Z[a][i] * s.X(a, b) * ec.Z[b][j];
+                        sy += ec.Z[a][i] * s.Y(a, b) * ec.Z[b][j];
+                    }
+                o.x[sidx(N, i, j)] = sx;
+                if (j > i) o.y[aidx(N, i, j)] = sy;
+            }
+        s = o;
+    }
+    if (METHOD == NQCB200_METHOD_FSSH && sample_state) {
+        const double xi = state_draw ? state_draw[traj] : philox_uniform(p.seed, (uint64_t)(p.traj_offset + traj), 0ull, 1u);
+        double tot = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) tot += s.x[sidx(N, i, i)];
+        const double target = xi * tot;
+        double cw = s.x[sidx(N, 0, 0)];
+        st = 0;
+#pragma unroll
+        for (int i = 1; i < N; ++i) {
+            if (cw < target && st == i - 1) { st = i; cw += s.x[sidx(N, i, i)]; }
+        }
+    }
+    double wsum[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) wsum[i] = 0.0;
+    for (int b = 0; b < NB; ++b) {
+        double Zb[N][N], Ab[sym_size(N)];
+#pragma unroll
+        for (int j = 0; j < N; ++j)
+#pragma unroll
+            for (int k = 0; k < N; ++k) Zb[j][k] = p.Zprev[((int64_t)b * N * N + j + N * k) * T + traj];
+        Eig<N> eb;
+        eval_point<M>(p, p.r[(int64_t)b * T + traj], Zb, eb, Ab);
+        const double acc = force_from_adiab<N, METHOD>(Ab, st, s) / mass;
+#pragma unroll
+        for (int i = 0; i < N; ++i) wsum[i] += eb.w[i];
+        if (valid) {
+            p.acc[(int64_t)b * T + traj] = acc;
+#pragma unroll
+            for (int j = 0; j < N; ++j)
+#pragma unroll
+                for (int k = 0; k < N; ++k) p.Zprev[((int64_t)b * N * N + j + N * k) * T + traj] = Zb[j][k];
+        }
+    }
+    {
+        double pot = 0.0;
+        if (METHOD == NQCB200_METHOD_EHRENFEST) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) pot += s.x[sidx(N, i, i)] * wsum[i];
+        } else pot = select<N>(wsum, st);
+        Emitter em{p, traj, valid, 0, red, 0};
+        rt_record_save<N, METHOD>(p, em, NB, p.r, p.v, T, traj, s, st, ec, pot, mass);
+    }
+    if (valid) {
+#pragma unroll
+        for (int j = 0; j < N; ++j)
+#pragma unroll
+            for (int k = 0; k < N; ++k) {
+                p.sig_re[(int64_t)(j + N * k) * T + traj] = s.X(j, k);
+                p.sig_im[(int64_t)(j + N * k) * T + traj] = s.Y(j, k);
+                p.Zprev[((int64_t)NB * N * N + j + N * k) * T + traj] = Zc[j][k];
+            }
+        if (p.state) p.state[traj] = st;
+#pragma unroll
+        for (int i = 0; i < N + N * N; ++i) p.ecur[(int64_t)i * T + traj] = 0.0;   // Q1
+    }
+}
+
+// Classical RPMD (BCB, bcb.jl:81-116) for any nbeads: one thread per trajectory, dense normal-mode product.
+template <class M>
+__global__ void __launch_bounds__(kRtThreads) classical_tpt_step_kernel(const __grid_constant__ KParams p) {
+    extern __shared__ __align__(16) double rt_sm[];
+    __shared__ double red[2 * (kRtThreads / 32)];
+    const int NB = p.B, tid = threadIdx.x;
+    double* s_r = rt_sm;
+    double* s_v = s_r + NB * kRtThreads;
+    double* s_a = s_v + NB * kRtThreads;
+    double* s_t = s_a + NB * kRtThreads;
+    double* U = s_t + 2 * NB * kRtThreads;
+    double* cay = U + NB * NB;
+    int64_t traj = (int64_t)blockIdx.x * kRtThreads + tid;
+    const bool valid = traj < p.ntraj;
+    if (!valid) traj = p.ntraj - 1;
+    const int64_t T = p.ntraj;
+    for (int i = tid; i < NB * NB; i += kRtThreads) U[i] = p.nm_to[i];
+    for (int i = tid; i < 4 * NB; i += kRtThreads) cay[i] = p.cayley[i];
+    for (int b = 0; b < NB; ++b) {
+        s_r[b * kRtThreads + tid] = p.r[(int64_t)b * T + traj];
+        s_v[b * kRtThreads + tid] = p.v[(int64_t)b * T + traj];
+        s_a[b * kRtThreads + tid] = p.acc[(int64_t)b * T + traj];
+    }
+    __syncthreads();
+    const double mass = p.masses[0], dt = p.dt, hdt = 0.5 * p.dt;
+#pragma unroll 1
+    for (int is = 0; is < p.nsteps; ++is) {
+        const int64_t step = p.step0 + is;
+        for (int b = 0; b < NB; ++b) s_v[b * kRtThreads + tid] = fma(hdt, s_a[b * kRtThreads + tid], s_v[b * kRtThreads + tid]);
+        for (int k = 0; k < NB; ++k) {
+            double a = 0.0, c = 0.0;
+            for (int j = 0; j < NB; ++j) {
+                const double u = U[j * NB + k];
+                a = fma(u, s_r[j * kRtThreads + tid], a);
+                c = fma(u, s_v[j * kRtThreads + tid], c);
+            }
+            s_t[k * kRtThreads + tid] = cay[4 * k + 0] * a + cay[4 * k + 1] * c;
+            s_t[(NB + k) * kRtThreads + tid] = cay[4 * k + 2] * a + cay[4 * k + 3] * c;
+        }
+        for (int j = 0; j < NB; ++j) {
+            double a = 0.0, c = 0.0;
+            for (int k = 0; k < NB; ++k) {
+                const double u = U[j * NB + k];
+                a = fma(u, s_t[k * kRtThreads + tid], a);
+                c = fma(u, s_t[(NB + k) * kRtThreads + tid], c);
+            }
+            const double acc = -M::gradient_dof(p.params, a) / mass;     // classical.jl:63-67
+            s_r[j * kRtThreads + tid] = a;
+            s_a[j * kRtThreads + tid] = acc;
+            s_v[j * kRtThreads + tid] = fma(hdt, acc, c);
+        }
+        if ((step + 1) % p.save_every == 0) {
+            const int64_t isave = (step + 1) / p.save_every;
+            if (isave < p.nsave) {
+                Emitter em{p, traj, valid, (int)isave, red, 0};
+                classical_tpt_record_save<M>(p, em, NB, s_r, s_v, kRtThreads, tid, mass);
+            }
+        }
+    }
+    if (valid) {
+        for (int b = 0; b < NB; ++b) {
+            p.r[(int64_t)b * T + traj] = s_r[b * kRtThreads + tid];
+            p.v[(int64_t)b * T + traj] = s_v[b * kRtThreads + tid];
+            p.acc[(int64_t)b * T + traj] = s_a[b * kRtThreads + tid];
+        }
+    }
+}
+
+template <class M>
+__global__ void __launch_bounds__(kRtThreads) classical_tpt_init_kernel(const __grid_constant__ KParams p, int, int,
+                                                                        const double*) {
+    __shared__ double red[2 * (kRtThreads / 32)];
+    const int NB = p.B;
+    int64_t traj = (int64_t)blockIdx.x * kRtThreads + threadIdx.x;
+    const bool valid = traj < p.ntraj;
+    if (!valid) traj = p.ntraj - 1;
+    const int64_t T = p.ntraj;
+    const double mass = p.masses[0];
+    if (valid)
+        for (int b = 0; b < NB; ++b) p.acc[(int64_t)b * T + traj] = -M::gradient_dof(p.params, p.r[(int64_t)b * T + traj]) / mass;
+    Emitter em{p, traj, valid, 0, red, 0};
+    classical_tpt_record_save<M>(p, em, NB, p.r, p.v, T, traj, mass);
 }
 
 #endif  // __CUDACC__

@@ -1,5 +1,6 @@
 // tu_classical_nrpmd.cu -- classical MD / RPMD and NRPMD kernels (beads on lanes).
 #include "kernel_nrpmd.cuh"
+#include "kernel_ring_tpt.cuh"
 
 namespace nq {
 namespace {
@@ -8,6 +9,13 @@ void set_classical(KernelSet& k, const char* name) {
     k.step = classical_ring_step_kernel<M, NB>;
     k.init = classical_ring_init_kernel<M, NB>;
     k.L = NB; k.DPL = 1; k.name = name;
+}
+template <class M>
+void k_generic(KernelSet& k, const char* name, size_t bytes) {
+    k.step = classical_tpt_step_kernel<M>;
+    k.init = classical_tpt_init_kernel<M>;
+    k.L = 1; k.DPL = 1; k.name = name;
+    k.step_L = 1; k.step_block = kRtThreads; k.step_smem = bytes;
 }
 template <class M>
 bool pick_classical(int B, KernelSet& out, const char* name) {
@@ -19,7 +27,11 @@ bool pick_classical(int B, KernelSet& out, const char* name) {
         case 16: set_classical<M, 16>(out, name); return true;
         case 32: set_classical<M, 32>(out, name); return true;
     }
-    return false;
+    // any other nbeads: thread per trajectory, dense normal-mode product (kernel_ring_tpt.cuh)
+    const size_t bytes = ((size_t)5 * B * kRtThreads + (size_t)B * B + 4 * B) * sizeof(double);
+    if (B < 2 || bytes > 200 * 1024) return false;
+    k_generic<M>(out, name, bytes);
+    return true;
 }
 template <class M, int NB>
 void set_nrpmd(KernelSet& k, const char* name) {
@@ -46,7 +58,7 @@ bool select_classical(const nqcb200_config& c, KernelSet& out, std::string& why)
     bool ok = false;
     if (c.model == NQCB200_MODEL_HARMONIC) ok = pick_classical<ModelT<NQCB200_MODEL_HARMONIC>>(c.nbeads, out, "rpmd_harmonic");
     else if (c.model == NQCB200_MODEL_FREE) ok = pick_classical<ModelT<NQCB200_MODEL_FREE>>(c.nbeads, out, "rpmd_free");
-    if (!ok) why = "classical method needs a classical model and nbeads in {1,2,4,8,16,32}";
+    if (!ok) why = "classical method needs a classical model (and beads that fit in shared memory)";
     return ok;
 }
 

@@ -20,13 +20,26 @@ bool pick(int method, KernelSet& out, const char* name) {
     // the beads-on-lanes kernel stays as the fallback (and as an A/B switch: NQCB200_RING_TPT=0)
     const char* env = getenv("NQCB200_RING_TPT");
     const bool want = !(env && atoi(env) == 0);
-    if (want && method == NQCB200_METHOD_FSSH && ring_tpt_smem_bytes<M::NS, NB, NQCB200_METHOD_FSSH>() <= 200 * 1024) {
-        out.step = ring_tpt_step_kernel<M, NB, NQCB200_METHOD_FSSH>;
-        out.step_L = 1; out.step_block = kRtThreads; out.step_smem = ring_tpt_smem_bytes<M::NS, NB, NQCB200_METHOD_FSSH>();
-    } else if (want && method == NQCB200_METHOD_EHRENFEST && ring_tpt_smem_bytes<M::NS, NB, NQCB200_METHOD_EHRENFEST>() <= 200 * 1024) {
-        out.step = ring_tpt_step_kernel<M, NB, NQCB200_METHOD_EHRENFEST>;
-        out.step_L = 1; out.step_block = kRtThreads; out.step_smem = ring_tpt_smem_bytes<M::NS, NB, NQCB200_METHOD_EHRENFEST>();
+    const bool ehr = (method == NQCB200_METHOD_EHRENFEST);
+    const size_t bytes = ring_tpt_smem_bytes(M::NS, NB, ehr, true);
+    if (want && bytes <= 200 * 1024) {
+        if (ehr) out.step = ring_tpt_step_kernel<M, NB, NQCB200_METHOD_EHRENFEST>;
+        else out.step = ring_tpt_step_kernel<M, NB, NQCB200_METHOD_FSSH>;
+        out.step_L = 1; out.step_block = kRtThreads; out.step_smem = bytes;
     }
+    return true;
+}
+// any other nbeads: thread-per-trajectory init + step with the dense normal-mode product
+template <class M>
+bool pick_generic(int method, int B, KernelSet& out, const char* name) {
+    const bool ehr = (method == NQCB200_METHOD_EHRENFEST);
+    if (method != NQCB200_METHOD_FSSH && !ehr) return false;
+    const size_t bytes = ring_tpt_smem_bytes(M::NS, B, ehr, false);
+    if (B < 2 || bytes > 200 * 1024) return false;
+    if (ehr) { out.step = ring_tpt_step_kernel<M, 0, NQCB200_METHOD_EHRENFEST>; out.init = ring_tpt_init_kernel<M, NQCB200_METHOD_EHRENFEST>; }
+    else { out.step = ring_tpt_step_kernel<M, 0, NQCB200_METHOD_FSSH>; out.init = ring_tpt_init_kernel<M, NQCB200_METHOD_FSSH>; }
+    out.L = 1; out.DPL = 1; out.name = name;
+    out.step_L = 1; out.step_block = kRtThreads; out.step_smem = bytes;
     return true;
 }
 template <class M>
@@ -38,7 +51,7 @@ bool pick_beads(int method, int B, KernelSet& out, const char* name) {
         case 16: return pick<M, 16>(method, out, name);
         case 32: return pick<M, 32>(method, out, name);
     }
-    return false;
+    return pick_generic<M>(method, B, out, name);
 }
 }  // namespace
 
@@ -52,7 +65,7 @@ bool select_ring_density(const nqcb200_config& c, KernelSet& out, std::string& w
         case NQCB200_MODEL_THREE_STATE_MORSE: ok = pick_beads<ModelT<NQCB200_MODEL_THREE_STATE_MORSE>>(c.method, c.nbeads, out, "rp_morse3"); break;
         default: break;
     }
-    if (!ok) why = "ring-polymer kernel: unsupported model or nbeads not in {2,4,8,16,32}";
+    if (!ok) why = "ring-polymer kernel: unsupported model, or the beads do not fit in shared memory";
     return ok;
 }
 }  // namespace nq

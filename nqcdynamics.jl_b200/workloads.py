@@ -98,6 +98,9 @@ class Workload:
             h.set_state(ic["r"], ic["v"], psi, None, state)
             return ic["r"].nbytes + ic["v"].nbytes + psi.nbytes + state.nbytes
         h.set_state(ic["r"], ic["v"])
+        if self.method == A.METHOD_NRPMD:
+            h.set_mapping(ic["qmap"], ic["pmap"])
+            return ic["r"].nbytes + ic["v"].nbytes + ic["qmap"].nbytes + ic["pmap"].nbytes
         return ic["r"].nbytes + ic["v"].nbytes
 
     def iesh_ground_state(self, ntraj: int):
@@ -183,6 +186,30 @@ def _rpsh_morse() -> Workload:
                     rpsh_flops(3, 1, B, 60.0), sample, nbeads=B, temperature=kT)
 
 
+def nrpmd_flops(n: int, D: int, B: int, f_model: float) -> float:
+    """16 B^2 D + B [F_model + E(n) + 4n^3 D + 4n^3 + 2n^2 + 8n^2 + D (8n^3 + 2n^2 + 6n^2)]."""
+    E = 40.0 if n == 2 else 9.0 * n ** 3
+    return 16 * B * B * D + B * (f_model + E + 4 * n ** 3 * D + 4 * n ** 3 + 10 * n * n + D * (8 * n ** 3 + 8 * n * n))
+
+
+def _nrpmd_morse() -> Workload:
+    # C5 (second half): RingPolymerSimulation{NRPMD}(Atoms(20000), ThreeStateMorse(), 16; T = 300 K), gamma = 0.5;
+    # mapping variables on the focused-sampling circles of nrpmd.jl:47-65 (state 1 occupied), uniform angles
+    B, m, n, gamma = 16, 20000.0, 3, 0.5
+    kT = 300.0 * 3.166811563e-6
+    radius = np.full(n, np.sqrt(2 * gamma)); radius[0] = np.sqrt(2 + 2 * gamma)
+
+    def sample(rng, T):
+        th = rng.random((T, B, n)) * 2 * np.pi
+        return {"r": rng.normal(2.1, 1.0 / np.sqrt(m * 0.005), (T, B, 1)),
+                "v": rng.standard_normal((T, B, 1)) * np.sqrt(kT * B / m),
+                "qmap": radius * np.cos(th), "pmap": radius * np.sin(th)}
+    obs = (1 << A.OBS_POPCORR_DIABATIC)
+    return Workload("nrpmd_morse3_16", "C5 NRPMD 16 beads, ThreeStateMorse, mass 20000, 300 K, gamma=0.5, dt=1, tspan (0,3000), saveat 50",
+                    models.ThreeStateMorse(), A.METHOD_NRPMD, np.array([m]), 1.0, 3000, 50, obs, 100_000,
+                    nrpmd_flops(n, 1, B, 60.0), sample, nbeads=B, temperature=kT)
+
+
 def _iesh(M: int, nsteps: int, ntraj: int) -> Workload:
     # C4: Simulation{AdiabaticIESH}(Atoms(2000), AndersonHolstein(MiaoSubotnik(G = 6.4e-3), TrapezoidalRule(M, -W, W))),
     # W = 6G/2 (test/Dynamics/iesh.jl:17-25), kT = 9.5e-4, dt = 1 (iesh.jl:158); thermal sample in the U1 well.
@@ -212,6 +239,7 @@ def get(name: str) -> Workload:
         "spinboson_debye100_ehrenfest": lambda: _spinboson(A.METHOD_EHRENFEST, "spinboson_debye100_ehrenfest"),
         "rpmd_harmonic32": _rpmd_harmonic,
         "rpsh_morse3_16": _rpsh_morse,
+        "nrpmd_morse3_16": _nrpmd_morse,
     }
     if name not in table:
         raise KeyError(f"unknown workload {name!r}; available: {sorted(table)}")
@@ -219,4 +247,5 @@ def get(name: str) -> Workload:
 
 
 NAMES = ["tully1_fssh", "spinboson_debye100_fssh", "spinboson_debye100_ehrenfest", "rpmd_harmonic32", "rpsh_morse3_16",
+         "nrpmd_morse3_16",
          "iesh_anderson_holstein_m100", "iesh_anderson_holstein_m200", "iesh_anderson_holstein_m30"]

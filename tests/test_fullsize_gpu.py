@@ -1,0 +1,85 @@
+"""GPU: BASELINE.json's FULL sizes, checked through size-independent properties of the path (the oracle cannot run
+10^6 trajectories in seconds): probability conservation of every estimator, reflection + transmission = 1,
+shard additivity of the observable accumulators (the multi-GPU reduction), hop counters, bounded energy drift."""
+import numpy as np
+import pytest
+
+import nqcdynamics_jl_b200 as nq
+from nqcdynamics_jl_b200 import workloads
+from helpers import A, engine_factory
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(wl, T, nsteps, *, lo=0, n=None, seed=5, fused=False, ic=None):
+    n = T if n is None else n
+    kw = wl.config_kwargs(n, seed=seed, traj_offset=lo)
+    cfg, keep = A.make_config(**kw)
+    e = engine_factory()(cfg, keep)
+    sub = {k: v[lo:lo + n] for k, v in ic.items()}
+    if fused:
+        e.run_from_host(sub["r"], sub["v"], wl.initial_density(n), diabatic=True, nsteps=nsteps)
+    else:
+        wl.upload(e, sub)
+        e.run(nsteps)
+    return e
+
+
+@pytest.mark.parametrize("name", ["spinboson_debye100_fssh", "spinboson_debye100_ehrenfest"])
+def test_spinboson_million_trajectories(name):
+    """configs[1]: 10^6 trajectories x 200 steps.  sum_ij C_ij(t) = sum_i P_i(0) sum_j P_j(t) = 1 per trajectory."""
+    wl = workloads.get(name)
+    T = 1_000_000
+    ic = wl.sample(np.random.default_rng(1), T)
+    e = _run(wl, T, wl.nsteps, ic=ic, fused=True)
+    C = e.observable_sum(A.OBS_POPCORR_DIABATIC).reshape(wl.nsave, 2, 2)
+    assert np.max(np.abs(C.sum(axis=(1, 2)) - T)) < 1e-6 * T
+    if wl.method == A.METHOD_EHRENFEST:      # (the FSSH estimator mixes the active state with coherences: fssh.jl:132-142)
+        assert np.all(C > -1e-6 * T)                                       # populations stay in [0, 1]
+        assert abs(C[0, 0, 0] - T) < 1e-6 * T                              # PureState(1): P(0) = (1, 0)
+    c = e.counters()
+    assert c["steps"] == T * wl.nsteps and c["nonfinite"] == 0
+    if wl.method == A.METHOD_FSSH:
+        assert 0 < c["hops"] < c["steps"] and 0 <= c["frustrated"] < c["steps"]
+    # shard additivity: the two halves (keyed by the global trajectory index) add up to the whole
+    a = _run(wl, T, wl.nsteps, lo=0, n=T // 2, ic=ic, fused=True)
+    b = _run(wl, T, wl.nsteps, lo=T // 2, n=T // 2, ic=ic, fused=False)    # also: fused and two-call paths agree
+    Cab = (a.observable_sum(A.OBS_POPCORR_DIABATIC) + b.observable_sum(A.OBS_POPCORR_DIABATIC)).reshape(wl.nsave, 2, 2)
+    assert np.max(np.abs(Cab - C)) < 1e-7 * T
+    if wl.method == A.METHOD_FSSH:
+        assert a.counters()["hops"] + b.counters()["hops"] == c["hops"]
+
+
+def test_tully_scattering_full_size():
+    """configs[0] at 2^20 trajectories: every trajectory ends reflected or transmitted on exactly one surface."""
+    wl = workloads.get("tully1_fssh")
+    T = 1 << 20
+    ic = wl.sample(np.random.default_rng(2), T)
+    e = _run(wl, T, wl.nsteps, ic=ic)
+    scat = e.observable_sum(A.OBS_SCATTERING)
+    assert np.all(scat[:-1] == 0.0) and abs(scat[-1].sum() - T) < 1e-9 * T
+    pop = e.observable_sum(A.OBS_DIABATIC_POP)
+    assert np.max(np.abs(pop.sum(axis=1) - T)) < 1e-8 * T
+    assert scat[-1, 2:].sum() > 0.99 * T                                   # k = 10 a.u.: transmission
+
+
+def test_rpmd_energy_conservation_full_size():
+    """configs[2]: 32-bead RPMD on the harmonic model, 2^17 trajectories: the ring-polymer Hamiltonian is conserved."""
+    wl = workloads.get("rpmd_harmonic32")
+    T = 1 << 17
+    ic = wl.sample(np.random.default_rng(3), T)
+    e = _run(wl, T, 2000, ic=ic)
+    E = e.observable_sum(A.OBS_TOTAL_ENERGY)[: 2000 // wl.save_every + 1, 0]
+    assert np.max(np.abs(E - E[0])) < 1e-6 * abs(E[0])
+
+
+def test_rpsh_population_conservation_full_size():
+    """configs[4]: RPSH, 16 beads, ThreeStateMorse, 10^5 trajectories."""
+    wl = workloads.get("rpsh_morse3_16")
+    T = 100_000
+    ic = wl.sample(np.random.default_rng(4), T)
+    e = _run(wl, T, 1000, ic=ic)
+    ns = 1000 // wl.save_every + 1
+    C = e.observable_sum(A.OBS_POPCORR_DIABATIC)[:ns].reshape(ns, 3, 3)
+    assert np.max(np.abs(C.sum(axis=(1, 2)) - T)) < 1e-6 * T
+    assert e.counters()["nonfinite"] == 0

@@ -227,7 +227,7 @@ def test_spin_boson_run_from_host(method, nmodes, pinned):
 
 
 @pytest.mark.parametrize("method", [A.METHOD_FSSH, A.METHOD_EHRENFEST])
-@pytest.mark.parametrize("nbeads", [4, 16, 32])
+@pytest.mark.parametrize("nbeads", [3, 4, 10, 16, 32])      # 10 beads: test/Dynamics/bcbwithtsit5.jl:10-37
 @pytest.mark.parametrize("name,model,mass,r0,v0,temp", [
     ("tully1", nq.TullyModelOne(), 2000.0, -4.0, 10.0 / 2000, 1e-3),
     ("morse3", nq.ThreeStateMorse(), 20000.0, 2.1, 0.0, 9.5e-4),
@@ -256,7 +256,7 @@ def test_ring_polymer_parity(method, nbeads, name, model, mass, r0, v0, temp):
     _compare_observables(e, o, ALL_POP_OBS, 1e-9, T)
 
 
-@pytest.mark.parametrize("nbeads", [1, 2, 8, 32])
+@pytest.mark.parametrize("nbeads", [1, 2, 5, 8, 10, 32])
 def test_rpmd_parity(nbeads):
     """BASELINE config 3: RPMD on Harmonic, normal-mode Cayley propagation."""
     T, nsteps = 64, 200
