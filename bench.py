@@ -33,6 +33,15 @@ sys.path.insert(0, ROOT)
 
 DEFAULT_WORKLOAD = "spinboson_debye100_fssh"   # BASELINE.json configs[1]
 
+# dram__bytes_read.sum + dram__bytes_write.sum of the step kernel per TRAJECTORY per launch, from the `ncu --set full`
+# captures committed under profiles/r01/ (prof_r01_<tag>_raw.csv; bytes / trajectories of the capture).  The kernels
+# touch HBM only at launch entry / exit (state in, state out) and at save points, so the traffic of a launch scales
+# with the number of trajectories, not with the number of steps.
+NCU_DRAM_BYTES_PER_TRAJ = {
+    "spinboson_debye100_fssh": (2697.0, "sb_v4"), "spinboson_debye100_ehrenfest": (2697.0, "sb_v4"),
+    "tully1_fssh": (236.0, "tully1_v2"), "rpmd_harmonic32": (1356.0, "rpmd_fft"), "rpsh_morse3_16": (694.0, "rpsh_tpt"),
+}
+
 
 def parse_args():
     ap = argparse.ArgumentParser()
@@ -341,7 +350,11 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": float(peak.value), "unit": "TFLOP/s",
-                         "frac": achieved / float(peak.value) if peak.value else None, "traffic": None,
+                         "frac": achieved / float(peak.value) if peak.value else None,
+                         "traffic": (NCU_DRAM_BYTES_PER_TRAJ[wl.name][0] * T if wl.name in NCU_DRAM_BYTES_PER_TRAJ else None),
+                         "traffic_source": (f"profiles/r01/prof_r01_{NCU_DRAM_BYTES_PER_TRAJ[wl.name][1]}_raw.csv: DRAM read + write "
+                                            f"bytes per trajectory of that capture x {T} trajectories (bytes per launch)"
+                                            if wl.name in NCU_DRAM_BYTES_PER_TRAJ else None),
                          "flops_per_trajectory_step_algorithmic": flops_step,
                          "peak_source": "DFMA microbenchmark measured in this run (nqcb200_measure_fp64_peak); "
                                         "MEASURED_PEAKS.json has no FP64 entry",
