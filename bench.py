@@ -5,12 +5,15 @@
 
 A "step" is one whole ensemble job of the named workload: every trajectory advanced over the config's full
 tspan (e.g. 200 nuclear steps of dt = 0.1 for the spin-boson config) with its observables accumulated on the
-device at every save point.  Successive steps continue the same trajectories (work per step is identical).
+device at every save point.  Every step is the same job on a fresh batch: the initial conditions are re-drawn on the
+device from the resident distribution parameters (nqcb200_sample_state) before each run; only AdiabaticIESH / NRPMD
+(no device sampler) continue the same trajectories across steps.
 
   value     trajectory-steps/s with the trajectory state resident in HBM (device time, CUDA events on the
             engine's launch stream, max over ranks).
-  e2e       the same metric through the public C-ABI call sequence with HOST buffers: every step uploads fresh
-            initial conditions from pinned host memory (set_state), runs, and reads the reduced observable back.
+  e2e       the same metric through the public C-ABI call sequence with HOST buffers: every step hands over fresh
+            initial conditions in pinned host memory (nqcb200_run_from_host / set_state), runs, and reads the reduced
+            observable back.
   roofline  FP64: algorithmic flops per trajectory-step x trajectory-steps per launch / kernel
             time, against the DFMA peak measured in this run (MEASURED_PEAKS.json has no FP64 entry).
   cpu_baseline  the CPU oracle (a C++ restatement of the reference algorithm, NOT Julia) on the host cores,
@@ -212,8 +215,11 @@ def main():
     T = args.trajectories or wl.ntraj_default
     K, W = args.steps, args.warmup
     density = wl.method in (A.METHOD_FSSH, A.METHOD_EHRENFEST)
-    # one handle, trajectories keep running across the K+W steps; save capacity covers all of them
-    nsave_total = (W + K) * wl.nsteps // wl.save_every + 1
+    # one handle.  Every step is the SAME job: where the device-side sampler covers the workload's distribution, each
+    # step re-draws the batch from the resident distribution parameters (nqcb200_sample_state) and runs the config's
+    # full tspan; otherwise (AdiabaticIESH, NRPMD) the trajectories keep running and the save capacity covers all steps.
+    resample = wl.device_spec is not None
+    nsave_total = wl.nsave if resample else (W + K) * wl.nsteps // wl.save_every + 1
     kw = wl.config_kwargs(T, seed=20261017, device=local_rank, traj_offset=rank * T)
     kw["nsave"] = nsave_total
     cfg, keep = A.make_config(**kw)
@@ -245,7 +251,17 @@ def main():
             dist.all_reduce(t)
             torch.cuda.synchronize()
 
+    rho1 = None
+    if resample and density:
+        rho1 = np.zeros((wl.model.nstates, wl.model.nstates))
+        rho1[wl.initial_diabatic_state, wl.initial_diabatic_state] = 1.0
+
+    def fresh_batch():
+        if resample:
+            eng.sample_state(wl.device_spec[0], wl.device_spec[1], rho1, diabatic=True, state=0, normal_modes=wl.device_spec[2])
+
     for _ in range(W):
+        fresh_batch()
         eng.run(wl.nsteps)
     allreduce_observables(eng)
     barrier()
@@ -254,6 +270,7 @@ def main():
     kernel_ms, launches = 0.0, 0
     t0 = time.perf_counter()
     for _ in range(K):
+        fresh_batch()                           # inputs resident in HBM: only the distribution parameters are re-read
         eng.run(wl.nsteps)                      # blocking; device time from CUDA events on the launch stream
         ms, nl = eng.last_run_timing()
         kernel_ms += ms; launches += nl
@@ -326,6 +343,28 @@ def main():
         e2e = {"value": float(T) * world * wl.nsteps * ke / e2e_s, "unit": "trajectory-steps/s",
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": ke,
                "path": ("nqcb200_run_from_host (pinned host r, v read in place by the step kernel; rho uploaded)" if density else "nqcb200_set_state (pinned host r, v, psi) -> nqcb200_run") + " -> nqcb200_get_observable_sum"}
+        # informational: the same job with DEVICE-side initial conditions (nqcb200_sample_state: only the
+        # distribution parameters cross PCIe) -- not the contract's e2e, which keeps host buffers
+        if wl.device_spec is not None:
+            rs, vs, nm = wl.device_spec
+            rho1 = None
+            if density:
+                rho1 = np.zeros((wl.model.nstates, wl.model.nstates))
+                rho1[wl.initial_diabatic_state, wl.initial_diabatic_state] = 1.0
+            def job_dev(h):
+                h.sample_state(rs, vs, rho1, diabatic=True, state=0, normal_modes=nm)
+                h.run(wl.nsteps)
+            job_dev(eng2)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(ke):
+                job_dev(eng2)
+                allreduce_observables(eng2)
+                eng2.observable_sum(first_obs)
+            dev_s2 = time.perf_counter() - t0
+            barrier()
+            e2e["device_sampled_ic"] = {"value": float(T) * world * wl.nsteps * ke / dev_s2, "unit": "trajectory-steps/s",
+                                        "path": "nqcb200_sample_state -> nqcb200_run -> nqcb200_get_observable_sum (max over ranks not taken)"}
         eng2.close()
 
     cpu = None
@@ -342,6 +381,8 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": wl.name, "description": wl.description, "trajectories_per_gpu": T,
                        "nuclear_steps_per_step": wl.nsteps, "save_every": wl.save_every,
+                       "batch": ("every step re-draws the batch on the device (nqcb200_sample_state) and runs the full tspan"
+                                 if resample else "trajectories continue across steps"),
                        "observables_on_device": [o for o in range(A.OBS_COUNT) if (wl.observables >> o) & 1],
                        "l2": "trajectory state larger than L2" if T * 8 * 3 * len(wl.masses) * wl.nbeads > 126e6
                              else "state register-resident for the whole launch; no reuse of cached inputs between steps",

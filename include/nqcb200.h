@@ -257,6 +257,27 @@ int nqcb200_run_from_host(nqcb200_handle* h, const double* r, const double* v, c
                           const double* rho_im, const int32_t* state, const double* state_draw, int diabatic,
                           int64_t nsteps);
 
+/* Device-side initial conditions: sample_distribution (selections.jl:51-101) for the
+ * distributions the ensemble configs use -- every nuclear component either fixed or Normal(mean, sd), which covers
+ * DynamicalDistribution(v, r, size) of numbers / Normal / VelocityBoltzmann / harmonic Wigner -- times
+ * PureState(i) in either basis.  Nothing but the specification crosses PCIe.
+ *   r_dist, v_dist: nbeads*ndofs entries, [bead][dof]; kind 0: value a; kind 1: a + b * z, z ~ N(0, 1).
+ *   normal_modes != 0: the entries describe ring-polymer NORMAL-MODE coordinates (the exact thermal sample of a
+ *                      free / harmonic ring polymer); the engine transforms to beads with U (x_j = sum_k U[j,k] y_k).
+ *   rho_re, rho_im:  ONE n x n column-major matrix shared by all trajectories (NULL for methods without sigma);
+ *                    diabatic != 0 as in nqcb200_set_state_diabatic.
+ *   state:           1-based active state, or 0 to sample it from diag(sigma) (FSSH, fssh.jl:53-54; Philox purpose 1).
+ * The normals come from Philox4x32-10 keyed by (seed; global trajectory id, component, purpose 2) through Box-Muller
+ * (first normal -> position, second -> velocity), so the sample does not depend on the sharding; the CPU oracle
+ * implements the same stream.  Not available for AdiabaticIESH (NQCB200_ERR_UNSUPPORTED).                          */
+typedef struct nqcb200_dist {
+    int32_t kind;       /* 0 = fixed value a, 1 = Normal(mean a, standard deviation b) */
+    int32_t reserved;
+    double  a, b;
+} nqcb200_dist;
+int nqcb200_sample_state(nqcb200_handle* h, const nqcb200_dist* r_dist, const nqcb200_dist* v_dist, int normal_modes,
+                         const double* rho_re, const double* rho_im, int diabatic, int32_t state);
+
 /* Download the current DynamicsVariables (any pointer may be NULL to skip that field). */
 int nqcb200_get_state(nqcb200_handle* h, double* r, double* v,
                       double* sig_re, double* sig_im, int32_t* state);

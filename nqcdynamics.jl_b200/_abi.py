@@ -66,6 +66,14 @@ def _ptr(a: Optional[np.ndarray], typ=_dp):
     return a.ctypes.data_as(typ) if a is not None else None
 
 
+class Dist(C.Structure):
+    """``nqcb200_dist``: kind 0 = fixed value a, kind 1 = Normal(mean a, sd b)."""
+    _fields_ = [("kind", C.c_int32), ("reserved", C.c_int32), ("a", C.c_double), ("b", C.c_double)]
+
+
+DIST_FIXED, DIST_NORMAL = 0, 1
+
+
 def bind(lib: C.CDLL, prefix: str) -> None:
     """Declare argument/return types for every entry point of the header on ``lib``."""
     H = C.c_void_p
@@ -92,6 +100,7 @@ def bind(lib: C.CDLL, prefix: str) -> None:
     f("set_draws", [H, _dp, C.c_int64])
     f("run", [H, C.c_int64])
     f("run_from_host", [H, _dp, _dp, _dp, _dp, _ip, _dp, C.c_int, C.c_int64], required=False)
+    f("sample_state", [H, C.POINTER(Dist), C.POINTER(Dist), C.c_int, _dp, _dp, C.c_int, C.c_int32])
     f("get_state", [H, _dp, _dp, _dp, _dp, _ip])
     f("get_mapping", [H, _dp, _dp])
     f("get_observable_sum", [H, C.c_int, _dp, C.c_int64])
@@ -108,7 +117,7 @@ def bind(lib: C.CDLL, prefix: str) -> None:
 
 HEADER_SYMBOLS = [
     "version", "device_count", "create", "destroy", "last_error", "observable_width", "set_state",
-    "set_state_diabatic", "set_mapping", "set_gauge_reference", "set_draws", "run", "run_from_host", "get_state", "get_mapping",
+    "set_state_diabatic", "set_mapping", "set_gauge_reference", "set_draws", "run", "run_from_host", "sample_state", "get_state", "get_mapping",
     "get_observable_sum", "observable_sum_device", "observable_offset", "get_observable_per_trajectory",
     "get_diagnostics", "get_counters", "get_iesh_stats", "get_progress", "get_last_run_timing", "measure_fp64_peak",
 ]
@@ -228,6 +237,29 @@ class CHandle:
             return
         self._call("run_from_host", _ptr(r_), _ptr(v_), _ptr(sre_), _ptr(sim_), _ptr(st_, _ip), _ptr(dr_),
                    C.c_int(1 if diabatic else 0), C.c_int64(int(nsteps)))
+
+    def sample_state(self, r_spec, v_spec, rho=None, diabatic=True, state=0, normal_modes=False):
+        """Device-side initial conditions (nqcb200_sample_state).  r_spec / v_spec: nbeads*ndofs entries, each a number
+        (fixed) or a (mean, sd) pair (Normal); rho: ONE n x n matrix (numpy [row, col]) shared by all trajectories."""
+        def pack(spec):
+            spec = list(spec)
+            if len(spec) != self.B * self.D:
+                raise ValueError(f"expected {self.B * self.D} component specifications")
+            arr = (Dist * len(spec))()
+            for i, x in enumerate(spec):
+                if isinstance(x, (tuple, list)):
+                    arr[i].kind, arr[i].a, arr[i].b = DIST_NORMAL, float(x[0]), float(x[1])
+                else:
+                    arr[i].kind, arr[i].a, arr[i].b = DIST_FIXED, float(x), 0.0
+            return arr
+        rd, vd = pack(r_spec), pack(v_spec)
+        re = im = None
+        if rho is not None:
+            m = np.asarray(rho, dtype=np.complex128).reshape(self.n, self.n)
+            re = np.ascontiguousarray(m.real.T).reshape(-1)      # column-major
+            im = np.ascontiguousarray(m.imag.T).reshape(-1)
+        self._call("sample_state", rd, vd, C.c_int(1 if normal_modes else 0), _ptr(re), _ptr(im),
+                   C.c_int(1 if diabatic else 0), C.c_int32(int(state)))
 
     def get_state(self):
         T, B, D, n = self.T, self.B, self.D, self.n

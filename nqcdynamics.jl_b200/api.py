@@ -247,6 +247,28 @@ class DynamicalDistribution:
     def sample(self, rng, T, selection=None):
         return self._draw(self.position, rng, T, selection), self._draw(self.velocity, rng, T, selection)
 
+    def _component_spec(self, spec):
+        """Per-component (fixed | Normal) description of one entry for nqcb200_sample_state, or None if the entry is
+        not of that form (a vector of configurations, an arbitrary sampler)."""
+        D = int(np.prod(self.size[:2]))
+        B = self.size[2] if len(self.size) > 2 else 1
+        if isinstance(spec, Normal):
+            return [(spec.μ, spec.σ)] * (B * D)
+        if isinstance(spec, VelocityBoltzmann):
+            sd = np.sqrt(spec.temperature / np.repeat(np.asarray(spec.masses, dtype=float), spec.dims[0]))
+            return [(0.0, float(x)) for x in np.broadcast_to(sd, (B, D)).reshape(-1)]
+        if hasattr(spec, "sample") or (isinstance(spec, (list, tuple)) and len(spec) and np.ndim(spec[0]) >= 1):
+            return None
+        arr = np.asarray(spec, dtype=np.float64)
+        if arr.ndim == 0:
+            return [float(arr)] * (B * D)
+        return [float(x) for x in np.broadcast_to(self._to_flat(arr), (B, D)).reshape(-1)]
+
+    def device_spec(self):
+        """(r_spec, v_spec) for the device-side sampler, or None when host sampling is needed."""
+        r, v = self._component_spec(self.position), self._component_spec(self.velocity)
+        return None if r is None or v is None else (r, v)
+
 
 @dataclass
 class ProductDistribution:
@@ -307,8 +329,12 @@ class MeanReduction:
 
 @dataclass
 class EnsembleB200:
-    """``ensemble_algorithm=EnsembleB200(ngpus)``: shard trajectories over ``ngpus`` B200s of this node."""
+    """``ensemble_algorithm=EnsembleB200(ngpus)``: shard trajectories over ``ngpus`` B200s of this node.
+    ``device_sampling=True``: initial conditions of the form (number | Normal | VelocityBoltzmann) x PureState are
+    drawn on the device (nqcb200_sample_state; Philox stream keyed by the global trajectory index) instead of by
+    numpy on the host -- nothing but the specification is uploaded."""
     ngpus: int = 1
+    device_sampling: bool = False
 
 
 # ---- run_dynamics ----------------------------------------------------------------------------------
@@ -385,8 +411,16 @@ def run_dynamics(sim: Simulation, tspan, distribution, *, output, selection: Opt
         nuclear, electronic = distribution.nuclear, distribution.electronic
     else:
         nuclear, electronic = distribution, None
-    r, v = nuclear.sample(rng, T, selection)
     density = method.method_id in (A.METHOD_FSSH, A.METHOD_EHRENFEST)
+    dev_spec = None
+    if getattr(alg, "device_sampling", False):
+        dev_spec = nuclear.device_spec() if selection is None else None
+        if dev_spec is None or method.method_id in (A.METHOD_IESH, A.METHOD_NRPMD):
+            raise ValueError("device_sampling needs number / Normal / VelocityBoltzmann entries, no selection, and a method "
+                             "other than AdiabaticIESH / NRPMD")
+        r = v = None
+    else:
+        r, v = nuclear.sample(rng, T, selection)
     if density and electronic is None:
         raise ValueError("FSSH / Ehrenfest need an electronic distribution: nuclear * PureState(i)")
     iesh = method.method_id == A.METHOD_IESH
@@ -432,8 +466,21 @@ def run_dynamics(sim: Simulation, tspan, distribution, *, output, selection: Opt
                 t0=t0, temperature=sim.temperature, nrpmd_gamma=getattr(method, "γ", 0.5),
                 edc_C=getattr(method, "decoherence_C", 0.0))
             with Engine(cfg, keep) as eng:
-                rg, vg = r[lo:hi], v[lo:hi]
-                if density:
+                if dev_spec is not None:
+                    rho1 = None
+                    adiabatic = True
+                    if density:
+                        n = model.nstates
+                        rho1 = np.zeros((n, n)); rho1[electronic.state - 1, electronic.state - 1] = 1.0
+                        adiabatic = isinstance(electronic.statetype, Adiabatic) or electronic.statetype is Adiabatic
+                    st = electronic.state if (adiabatic and method.method_id == A.METHOD_FSSH) else 0
+                    eng.sample_state(dev_spec[0], dev_spec[1], rho1, diabatic=not adiabatic, state=st)
+                    rg = vg = None
+                else:
+                    rg, vg = r[lo:hi], v[lo:hi]
+                if dev_spec is not None:
+                    pass
+                elif density:
                     n = model.nstates
                     rho = np.zeros((Tg, n, n))
                     rho[:, electronic.state - 1, electronic.state - 1] = 1.0

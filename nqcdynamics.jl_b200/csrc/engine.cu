@@ -16,6 +16,7 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include "philox.cuh"
 
 using namespace nq;
 
@@ -99,6 +100,41 @@ __global__ void count_nonfinite(const double* r, const double* v, int64_t T, int
     if (bad) atomicAdd(out, 1ull);
 }
 
+// nqcb200_sample_state: r, v of every trajectory from per-component (fixed | Normal) specifications, SoA out
+__global__ void sample_rv_kernel(const nqcb200_dist* __restrict__ rd, const nqcb200_dist* __restrict__ vd, double* r, double* v,
+                                 int64_t T, int C, uint64_t seed, int64_t traj_offset) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    for (int c = 0; c < C; ++c) {
+        double z0 = 0.0, z1 = 0.0;
+        if (rd[c].kind == 1 || vd[c].kind == 1) philox_normal2(seed, (uint64_t)(traj_offset + t), (uint64_t)c, z0, z1);
+        r[(int64_t)c * T + t] = (rd[c].kind == 1) ? fma(rd[c].b, z0, rd[c].a) : rd[c].a;
+        v[(int64_t)c * T + t] = (vd[c].kind == 1) ? fma(vd[c].b, z1, vd[c].a) : vd[c].a;
+    }
+}
+// normal modes -> beads along the bead index for every dof: x_j = sum_k U[j,k] y_k  (U at nm_to[j*B + k]); tmp: [B*D][T]
+__global__ void from_normal_modes_kernel(const double* __restrict__ U, double* x, double* tmp, int64_t T, int B, int D) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    for (int d = 0; d < D; ++d) {
+        for (int j = 0; j < B; ++j) {
+            double s = 0.0;
+            for (int k = 0; k < B; ++k) s = fma(U[j * B + k], x[((int64_t)k * D + d) * T + t], s);
+            tmp[((int64_t)j * D + d) * T + t] = s;
+        }
+        for (int j = 0; j < B; ++j) x[((int64_t)j * D + d) * T + t] = tmp[((int64_t)j * D + d) * T + t];
+    }
+}
+__global__ void broadcast_matrix_kernel(const double* __restrict__ m, double* out, int64_t T, int C) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    for (int c = 0; c < C; ++c) out[(int64_t)c * T + t] = m[c];
+}
+__global__ void fill_i32_kernel(int32_t* out, int64_t count, int32_t value) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) out[i] = value;
+}
+
 // FP64 roofline denominator: MEASURED_PEAKS.json carries only HBM and bf16 numbers, so the DFMA
 // peak is measured in-run: 16 independent FMA chains per thread, every SM saturated.
 __global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, double seed) {
@@ -140,6 +176,7 @@ struct nqcb200_handle {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<void*> allocs;
     double* staging = nullptr;      // trajectory-major staging for uploads / downloads
+    nqcb200_dist* d_dist = nullptr;   // sample_state: [2][B*D] component specifications
     double* aos_stage[2] = {nullptr, nullptr};   // run_from_host: trajectory-major r, v when the caller's memory is pageable
     size_t staging_doubles = 0;
     double* obs_folded = nullptr;
@@ -221,6 +258,38 @@ int launch_init(nqcb200_handle* h, int basis, int sample_state, const double* st
     return NQCB200_OK;
 }
 
+// common tail of set_state / sample_state: gauge reference, accumulators, counters, init kernel (save point 0)
+int finish_set_state(nqcb200_handle* h, int basis, int sample_state, const double* state_draw, bool fused) {
+    const nqcb200_config& c = h->cfg;
+    const int64_t T = c.ntraj;
+    const bool iesh = (c.method == NQCB200_METHOD_IESH);
+    int rc;
+    if (!iesh && !h->user_gauge && c.nstates > 1 && h->kp.Zprev) {
+        fill_identity<<<(unsigned)((T + 255) / 256), 256, 0, h->stream>>>(h->kp.Zprev, T, c.nstates, h->zcopies);
+        NQ_CUDA(h, cudaGetLastError());
+    }
+    NQ_CUDA(h, cudaMemsetAsync(h->kp.obs_sum, 0, sizeof(double) * std::max<int64_t>(1, h->kp.layout.total) * kObsReplicas, h->stream));
+    if (h->kp.obs_traj) NQ_CUDA(h, cudaMemsetAsync(h->kp.obs_traj, 0, sizeof(double) * h->kp.layout.total * T, h->stream));
+    NQ_CUDA(h, cudaMemsetAsync(h->kp.counters, 0, sizeof(unsigned long long) * 8, h->stream));
+    h->step_count = 0;
+    h->kp.step0 = 0;
+    h->kp.nsteps = 0;
+    h->kp.init_basis = basis;
+    h->kp.init_sample_state = sample_state;
+    h->kp.init_state_draw = (sample_state && state_draw) ? h->d_state_draw : nullptr;
+    if (T > 0 && c.method != NQCB200_METHOD_NRPMD && !fused) {   // NRPMD: save point 0 is recorded by set_mapping
+        if (iesh) rc = launch_init(h, h->user_gauge ? 1 : 0, 0, nullptr);
+        else rc = launch_init(h, basis, sample_state, (sample_state && state_draw) ? h->d_state_draw : nullptr);
+        if (rc) return rc;
+    }
+    if (!fused) NQ_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->nsave_done = (c.method == NQCB200_METHOD_NRPMD) ? 0 : 1;
+    h->has_state = (c.method != NQCB200_METHOD_NRPMD);
+    h->has_nuclei = true;
+    h->user_gauge = false;   // a gauge reference applies to the next set_state only
+    return NQCB200_OK;
+}
+
 // fused: r / v are NOT uploaded and no init kernel runs -- the next step launch reads them itself (KParams.r_aos)
 int set_state_impl(nqcb200_handle* h, const double* r, const double* v, const double* sre, const double* sim,
                    const int32_t* state, int basis, const double* state_draw, bool fused = false) {
@@ -270,30 +339,7 @@ int set_state_impl(nqcb200_handle* h, const double* r, const double* v, const do
             if (state_draw) NQ_CUDA(h, cudaMemcpyAsync(h->d_state_draw, state_draw, sizeof(double) * T, cudaMemcpyHostToDevice, h->stream));
         }
     }
-    if (!iesh && !h->user_gauge && c.nstates > 1 && h->kp.Zprev) {
-        fill_identity<<<(unsigned)((T + 255) / 256), 256, 0, h->stream>>>(h->kp.Zprev, T, c.nstates, h->zcopies);
-        NQ_CUDA(h, cudaGetLastError());
-    }
-    NQ_CUDA(h, cudaMemsetAsync(h->kp.obs_sum, 0, sizeof(double) * std::max<int64_t>(1, h->kp.layout.total) * kObsReplicas, h->stream));
-    if (h->kp.obs_traj) NQ_CUDA(h, cudaMemsetAsync(h->kp.obs_traj, 0, sizeof(double) * h->kp.layout.total * T, h->stream));
-    NQ_CUDA(h, cudaMemsetAsync(h->kp.counters, 0, sizeof(unsigned long long) * 8, h->stream));
-    h->step_count = 0;
-    h->kp.step0 = 0;
-    h->kp.nsteps = 0;
-    h->kp.init_basis = basis;
-    h->kp.init_sample_state = sample_state;
-    h->kp.init_state_draw = (sample_state && state_draw) ? h->d_state_draw : nullptr;
-    if (T > 0 && c.method != NQCB200_METHOD_NRPMD && !fused) {   // NRPMD: save point 0 is recorded by set_mapping
-        if (iesh) rc = launch_init(h, h->user_gauge ? 1 : 0, 0, nullptr);
-        else rc = launch_init(h, basis, sample_state, (sample_state && state_draw) ? h->d_state_draw : nullptr);
-        if (rc) return rc;
-    }
-    if (!fused) NQ_CUDA(h, cudaStreamSynchronize(h->stream));
-    h->nsave_done = (c.method == NQCB200_METHOD_NRPMD) ? 0 : 1;
-    h->has_state = (c.method != NQCB200_METHOD_NRPMD);
-    h->has_nuclei = true;
-    h->user_gauge = false;   // a gauge reference applies to the next set_state only
-    return NQCB200_OK;
+    return finish_set_state(h, basis, sample_state, state_draw, fused);
 }
 
 }  // namespace
@@ -654,6 +700,55 @@ int nqcb200_run_from_host(nqcb200_handle* h, const double* r, const double* v, c
     rc = nqcb200_run(h, nsteps);
     h->kp.r_aos = nullptr; h->kp.v_aos = nullptr;
     return rc;
+}
+
+int nqcb200_sample_state(nqcb200_handle* h, const nqcb200_dist* r_dist, const nqcb200_dist* v_dist, int normal_modes,
+                         const double* rho_re, const double* rho_im, int diabatic, int32_t state) {
+    if (!h || !r_dist || !v_dist) return NQCB200_ERR_INVALID;
+    const nqcb200_config& c = h->cfg;
+    const int64_t T = c.ntraj;
+    const bool density = (c.method == NQCB200_METHOD_FSSH || c.method == NQCB200_METHOD_EHRENFEST);
+    if (c.method == NQCB200_METHOD_IESH) { h->err = "device-side sampling is not available for AdiabaticIESH"; return NQCB200_ERR_UNSUPPORTED; }
+    if (density && !rho_re) { h->err = "the density matrix is required for FSSH / Ehrenfest"; return NQCB200_ERR_INVALID; }
+    if (state < 0 || state > c.nstates) { h->err = "state out of range"; return NQCB200_ERR_INVALID; }
+    if (c.method == NQCB200_METHOD_FSSH && !diabatic && state == 0) { h->err = "FSSH needs the active state (or a diabatic rho)"; return NQCB200_ERR_INVALID; }
+    NQ_CUDA(h, cudaSetDevice(c.device));
+    const int BD = c.nbeads * c.ndofs;
+    for (int i = 0; i < BD; ++i)
+        if ((r_dist[i].kind != 0 && r_dist[i].kind != 1) || (v_dist[i].kind != 0 && v_dist[i].kind != 1)) { h->err = "unknown distribution kind"; return NQCB200_ERR_INVALID; }
+    int rc;
+    if (!h->d_dist) { if ((rc = dev_alloc(h, &h->d_dist, (size_t)2 * BD)) != 0) return rc; }
+    NQ_CUDA(h, cudaMemcpyAsync(h->d_dist, r_dist, sizeof(nqcb200_dist) * BD, cudaMemcpyHostToDevice, h->stream));
+    NQ_CUDA(h, cudaMemcpyAsync(h->d_dist + BD, v_dist, sizeof(nqcb200_dist) * BD, cudaMemcpyHostToDevice, h->stream));
+    int sample_st = 0;
+    if (T > 0) {
+        const unsigned grid = (unsigned)((T + 127) / 128);
+        sample_rv_kernel<<<grid, 128, 0, h->stream>>>(h->d_dist, h->d_dist + BD, h->kp.r, h->kp.v, T, BD, c.seed, c.traj_offset);
+        NQ_CUDA(h, cudaGetLastError());
+        if (normal_modes && c.nbeads > 1) {
+            from_normal_modes_kernel<<<grid, 128, 0, h->stream>>>(h->kp.nm_to, h->kp.r, h->kp.acc, T, c.nbeads, c.ndofs);
+            from_normal_modes_kernel<<<grid, 128, 0, h->stream>>>(h->kp.nm_to, h->kp.v, h->kp.acc, T, c.nbeads, c.ndofs);
+            NQ_CUDA(h, cudaGetLastError());
+        }
+        if (density) {
+            // one n x n matrix for everybody: stage it at the head of the staging buffer, broadcast into the SoA fields
+            const int nn = h->nsig;
+            std::vector<double> m(2 * (size_t)nn, 0.0);
+            for (int i = 0; i < nn; ++i) { m[i] = rho_re[i]; m[nn + i] = rho_im ? rho_im[i] : 0.0; }
+            NQ_CUDA(h, cudaMemcpyAsync(h->staging, m.data(), sizeof(double) * 2 * nn, cudaMemcpyHostToDevice, h->stream));
+            NQ_CUDA(h, cudaStreamSynchronize(h->stream));   // m goes out of scope
+            broadcast_matrix_kernel<<<grid, 128, 0, h->stream>>>(h->staging, h->kp.sig_re, T, nn);
+            broadcast_matrix_kernel<<<grid, 128, 0, h->stream>>>(h->staging + nn, h->kp.sig_im, T, nn);
+            NQ_CUDA(h, cudaGetLastError());
+        }
+        if (c.method == NQCB200_METHOD_FSSH) {
+            if (state > 0) {
+                fill_i32_kernel<<<grid, 128, 0, h->stream>>>(h->kp.state, T, state - 1);
+                NQ_CUDA(h, cudaGetLastError());
+            } else sample_st = 1;
+        }
+    }
+    return finish_set_state(h, diabatic ? 1 : 0, sample_st, nullptr, false);
 }
 
 int nqcb200_get_state(nqcb200_handle* h, double* r, double* v, double* sig_re, double* sig_im, int32_t* state) {

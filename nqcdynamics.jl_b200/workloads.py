@@ -69,6 +69,8 @@ class Workload:
     temperature: float = 0.0
     initial_diabatic_state: int = 0      # 0-based PureState index (diabatic basis)
     rescaling: int = A.RESCALE_STANDARD
+    # the same initial-condition distribution as `sample`, as (r_spec, v_spec, normal_modes) for nqcb200_sample_state
+    device_spec: Optional[tuple] = None
 
     @property
     def nsave(self) -> int:
@@ -124,7 +126,8 @@ def _tully1_fssh() -> Workload:
     obs = (1 << A.OBS_DIABATIC_POP) | (1 << A.OBS_SCATTERING)
     return Workload("tully1_fssh", "C1 TullyModelOne FSSH, n=2, D=1, mass 2000, k0=10, dt=1, tspan (0,3000), saveat 10",
                     models.TullyModelOne(), A.METHOD_FSSH, np.array([2000.0]), 1.0, 3000, 10, obs, 1 << 22,
-                    fssh_flops(2, 1, 30.0), sample, initial_diabatic_state=1)
+                    fssh_flops(2, 1, 30.0), sample, initial_diabatic_state=1,
+                    device_spec=([(-8.0, 1.0)], [10.0 / 2000.0], False))
 
 
 def _spinboson(method: int, name: str) -> Workload:
@@ -142,7 +145,8 @@ def _spinboson(method: int, name: str) -> Workload:
     obs = (1 << A.OBS_POPCORR_DIABATIC)
     flops = fssh_flops(2, N, 6.0 * N) if method == A.METHOD_FSSH else ehrenfest_flops(2, N, 6.0 * N)
     return Workload(name, "C2 SpinBoson (Debye bath, 100 modes), n=2, D=100, beta=5, dt=0.1, tspan (0,20), saveat 0.1",
-                    model, method, np.ones(N), 0.1, 200, 1, obs, 1_000_000, flops, sample)
+                    model, method, np.ones(N), 0.1, 200, 1, obs, 1_000_000, flops, sample,
+                    device_spec=([(0.0, float(x)) for x in sr], [(0.0, float(x)) for x in sv], False))
 
 
 def _rpmd_harmonic() -> Workload:
@@ -169,7 +173,8 @@ def _rpmd_harmonic() -> Workload:
     obs = (1 << A.OBS_POSITION) | (1 << A.OBS_KINETIC) | (1 << A.OBS_TOTAL_ENERGY)
     return Workload("rpmd_harmonic32", "C3 RPMD 32 beads, Harmonic(m_H, w=0.005), 300 K thermal sample, dt=2.5, 10^4 steps, saveat 100",
                     models.Harmonic(m=m, ω=w), A.METHOD_CLASSICAL, np.array([m]), 2.5, 10000, 100, obs, 1 << 18,
-                    rpmd_flops(B, 1, 3.0), sample, nbeads=B, temperature=kT)
+                    rpmd_flops(B, 1, 3.0), sample, nbeads=B, temperature=kT,
+                    device_spec=([(0.0, float(x)) for x in sr], [(0.0, float(sv))] * B, True))
 
 
 def _rpsh_morse() -> Workload:
@@ -183,7 +188,8 @@ def _rpsh_morse() -> Workload:
     obs = (1 << A.OBS_POPCORR_DIABATIC)
     return Workload("rpsh_morse3_16", "C5 RPSH 16 beads, ThreeStateMorse, mass 20000, 300 K, dt=1, tspan (0,3000), saveat 50",
                     models.ThreeStateMorse(), A.METHOD_FSSH, np.array([m]), 1.0, 3000, 50, obs, 100_000,
-                    rpsh_flops(3, 1, B, 60.0), sample, nbeads=B, temperature=kT)
+                    rpsh_flops(3, 1, B, 60.0), sample, nbeads=B, temperature=kT,
+                    device_spec=([(2.1, 1.0 / np.sqrt(m * 0.005))] * B, [(0.0, float(np.sqrt(kT * B / m)))] * B, False))
 
 
 def nrpmd_flops(n: int, D: int, B: int, f_model: float) -> float:

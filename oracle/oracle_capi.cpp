@@ -37,6 +37,17 @@ inline double philox_uniform(uint64_t seed, uint64_t gid, uint64_t step, uint32_
     return (double)(bits >> 11) * (1.0 / 9007199254740992.0);
 }
 
+// Two standard normals per Philox block (Box-Muller): the stream of nqcb200_sample_state (include/nqcb200.h),
+// counter = (global trajectory id, component, purpose 2); first normal -> position, second -> velocity.
+inline void philox_normal2(uint64_t seed, uint64_t gid, uint64_t comp, double& z0, double& z1) {
+    uint32_t c[4] = {(uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)comp, ((uint32_t)(comp >> 32) & 0x00FFFFFFu) | (2u << 24)};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    const double u1 = (double)(((((uint64_t)c[0] << 32) | c[1]) >> 11) + 1ull) * (1.0 / 9007199254740992.0);
+    const double u2 = (double)((((uint64_t)c[2] << 32) | c[3]) >> 11) * (1.0 / 9007199254740992.0);
+    const double rad = std::sqrt(-2.0 * std::log(u1)), ang = 6.283185307179586476925286766559 * u2;
+    z0 = rad * std::cos(ang); z1 = rad * std::sin(ang);
+}
+
 struct ObsLayout {
     int width[NQCB200_OBS_COUNT];
     int64_t offset[NQCB200_OBS_COUNT];
@@ -313,6 +324,52 @@ int nqco_set_state(nqco_handle* h, const double* r, const double* v, const doubl
 int nqco_set_state_diabatic(nqco_handle* h, const double* r, const double* v, const double* rho_re,
                             const double* rho_im, const int32_t* state, const double* state_draw) {
     return set_state_impl(h, r, v, rho_re, rho_im, state, 1, state_draw);
+}
+
+// CPU restatement of nqcb200_sample_state: same Philox / Box-Muller stream, then the ordinary set_state path.
+int nqco_sample_state(nqco_handle* h, const nqcb200_dist* r_dist, const nqcb200_dist* v_dist, int normal_modes,
+                      const double* rho_re, const double* rho_im, int diabatic, int32_t state) {
+    if (!h || !r_dist || !v_dist) return NQCB200_ERR_INVALID;
+    const Setup& S = h->S;
+    const int n = S.n, D = S.D, B = S.B;
+    const int method = S.cfg.method;
+    if (method == NQCB200_METHOD_IESH) { h->err = "device-side sampling is not available for AdiabaticIESH"; return NQCB200_ERR_UNSUPPORTED; }
+    const bool density = (method == NQCB200_METHOD_FSSH || method == NQCB200_METHOD_EHRENFEST);
+    if (density && !rho_re) return NQCB200_ERR_INVALID;
+    const int64_t T = (int64_t)h->traj.size();
+    const int C = B * D;
+    std::vector<double> r((size_t)T * C), v((size_t)T * C);
+    const vec U = normal_mode_matrix(B);    // U[j + B*k]
+    for (int64_t t = 0; t < T; ++t) {
+        for (int c = 0; c < C; ++c) {
+            double z0 = 0.0, z1 = 0.0;
+            if (r_dist[c].kind == 1 || v_dist[c].kind == 1) philox_normal2(S.cfg.seed, (uint64_t)(S.cfg.traj_offset + t), (uint64_t)c, z0, z1);
+            r[(size_t)t * C + c] = r_dist[c].kind == 1 ? std::fma(r_dist[c].b, z0, r_dist[c].a) : r_dist[c].a;
+            v[(size_t)t * C + c] = v_dist[c].kind == 1 ? std::fma(v_dist[c].b, z1, v_dist[c].a) : v_dist[c].a;
+        }
+        if (normal_modes && B > 1) {
+            for (std::vector<double>* x : {&r, &v}) {
+                std::vector<double> tmp(C);
+                for (int d = 0; d < D; ++d)
+                    for (int j = 0; j < B; ++j) {
+                        double s = 0.0;
+                        for (int k = 0; k < B; ++k) s = std::fma(U[j + (size_t)B * k], (*x)[(size_t)t * C + (size_t)k * D + d], s);
+                        tmp[(size_t)j * D + d] = s;
+                    }
+                std::copy(tmp.begin(), tmp.end(), x->begin() + (size_t)t * C);
+            }
+        }
+    }
+    std::vector<double> sre, sim;
+    std::vector<int32_t> st;
+    if (density) {
+        sre.resize((size_t)T * n * n); sim.assign((size_t)T * n * n, 0.0);
+        for (int64_t t = 0; t < T; ++t)
+            for (int i = 0; i < n * n; ++i) { sre[(size_t)t * n * n + i] = rho_re[i]; if (rho_im) sim[(size_t)t * n * n + i] = rho_im[i]; }
+        if (method == NQCB200_METHOD_FSSH && state > 0) st.assign((size_t)T, state);
+    }
+    return set_state_impl(h, r.data(), v.data(), density ? sre.data() : nullptr, density ? sim.data() : nullptr,
+                          st.empty() ? nullptr : st.data(), diabatic ? 1 : 0, nullptr);
 }
 
 int nqco_set_mapping(nqco_handle* h, const double* qmap, const double* pmap) {
