@@ -42,7 +42,7 @@ constexpr int kSbTraj = 128;   // trajectories per block (the bath of 128 trajec
 struct SbSmem {
     double* rs;      // [D][kSbTraj]
     double* vs;      // [D][kSbTraj]  half-kicked velocity (true velocity before the first step of a launch)
-    double2 *k1, *k2, *k3;   // [D] {w^2/m, c/m}, {c, w^2/2}, {c w^2/m, m}
+    double2 *k1, *k2, *k3;   // [D] {w^2/m, c/m}, {c, c w^2/m}, {w^2/2, m}  (k3 only for energies / kinetic sums)
     NQ_D void carve(double* base, int D) {
         rs = base; vs = rs + (size_t)D * kSbTraj;
         k1 = reinterpret_cast<double2*>(vs + (size_t)D * kSbTraj); k2 = k1 + D; k3 = k2 + D;
@@ -125,7 +125,7 @@ NQ_D void sb_sweep(const SbSmem& M, int D, int slot, int part, bool first, bool 
 #pragma unroll
         for (int q = 0; q < W; ++q) {
             k1[q] = M.k1[jj[q]]; k2[q] = M.k2[jj[q]];
-            k3[q] = M.k3[jj[q]];
+            if (HARM || !DRIFT) k3[q] = M.k3[jj[q]];
             r[q] = M.rs[(size_t)jj[q] * kSbTraj + slot];
             v[q] = M.vs[(size_t)jj[q] * kSbTraj + slot];
         }
@@ -149,10 +149,10 @@ NQ_D void sb_sweep(const SbSmem& M, int D, int slot, int part, bool first, bool 
                 if (ok[q]) {
                     M.rs[(size_t)jj[q] * kSbTraj + slot] = rn[q];
                     M.vs[(size_t)jj[q] * kSbTraj + slot] = vt[q];
-                    if (HARM) h4[q] = fma(k2[q].y * rn[q], rn[q], h4[q]);
+                    if (HARM) h4[q] = fma(k3[q].x * rn[q], rn[q], h4[q]);
                     l4[q] = fma(k2[q].x, rn[q], l4[q]);
                     c4[q] = fma(k2[q].x, vt[q], c4[q]);
-                    w4[q] = fma(k3[q].x, rn[q], w4[q]);
+                    w4[q] = fma(k2[q].y, rn[q], w4[q]);
                 }
             }
         } else {
@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(kSbTraj * LPT, 1) spinboson_step_kernel(const 
     // per-mode constants
     for (int j = tid; j < D; j += blockDim.x) {
         const double w = p.bath_a[j], c = p.bath_b[j], m = p.masses[j];
-        M.k1[j] = make_double2(w * w / m, c / m); M.k2[j] = make_double2(c, 0.5 * w * w); M.k3[j] = make_double2(c * w * w / m, m);
+        M.k1[j] = make_double2(w * w / m, c / m); M.k2[j] = make_double2(c, c * w * w / m); M.k3[j] = make_double2(0.5 * w * w, m);
     }
     if (fused) {
         // this block's [128][D] tile of the caller's trajectory-major r, v (device staging or pinned host memory)
@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(kSbTraj * LPT, 1) spinboson_step_kernel(const 
         for (int j = part; j < D; j += LPT) {
             const double r = M.rs[(size_t)j * kSbTraj + slot], v = M.vs[(size_t)j * kSbTraj + slot];
             lin = fma(M.k2[j].x, r, lin);
-            harm = fma(M.k2[j].y * r, r, harm);
+            harm = fma(M.k3[j].x * r, r, harm);
             msv2 = fma(M.k3[j].y * v, v, msv2);
         }
         lin = SbMap<LPT>::sum(lin); harm = need_harm ? SbMap<LPT>::sum(harm) : 0.0; msv2 = SbMap<LPT>::sum(msv2);

@@ -22,9 +22,17 @@ template <int N>
 NQ_HD void jacobi_rotate(double (&A)[N][N], double (&Z)[N][N], int p, int q) {
     const double apq = A[p][q];
     if (apq == 0.0) return;
-    const double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
-    const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-    const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+    // t = sgn(theta) / (|theta| + sqrt(theta^2 + 1)), theta = a / b, written without forming theta:
+    // one sqrt, one division and one reciprocal square root instead of three divisions and two square roots
+    const double a = A[q][q] - A[p][p], b = 2.0 * apq;
+    const double hyp = sqrt(fma(a, a, b * b));
+    const double t = b / (a + (a >= 0.0 ? hyp : -hyp));
+#if defined(__CUDA_ARCH__)
+    const double c = rsqrt(fma(t, t, 1.0));
+#else
+    const double c = 1.0 / sqrt(fma(t, t, 1.0));
+#endif
+    const double s = t * c;
 #pragma unroll
     for (int k = 0; k < N; ++k) {
         if (k != p && k != q) {
