@@ -268,6 +268,7 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     kernel_ms, launches = 0.0, 0
+    launches_before = eng.launch_count()
     t0 = time.perf_counter()
     for _ in range(K):
         fresh_batch()                           # inputs resident in HBM: only the distribution parameters are re-read
@@ -276,6 +277,7 @@ def main():
         kernel_ms += ms; launches += nl
     allreduce_observables(eng)                  # the job's only exchange: one all-reduce of the accumulators
     wall = time.perf_counter() - t0
+    launches_all = eng.launch_count() - launches_before      # sampling / init / step / fold kernels of the timed region
     clocks = sampler.stop()
     barrier()
     # device-timed value: max over ranks of the summed kernel time (+ the measured wall for the collective)
@@ -388,7 +390,7 @@ def main():
                              else "state register-resident for the whole launch; no reuse of cached inputs between steps",
                        "parallelism": f"trajectories sharded over {world} GPU(s), one NCCL all-reduce of observables"},
             "e2e": e2e,
-            "gpu_launches": int(launches),
+            "gpu_launches": int(launches_all), "gpu_step_kernel_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": float(peak.value), "unit": "TFLOP/s",
                          "frac": achieved / float(peak.value) if peak.value else None,

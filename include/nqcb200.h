@@ -321,6 +321,8 @@ int nqcb200_get_iesh_stats(nqcb200_handle* h, int64_t* hop_searches, int64_t* de
  * spent in step kernels by the last nqcb200_run, with the number of kernel launches it made.   */
 int nqcb200_get_progress(nqcb200_handle* h, int64_t* nsave_done, int64_t* step_count);
 int nqcb200_get_last_run_timing(nqcb200_handle* h, double* kernel_ms, int64_t* launches);
+/* Every kernel this handle has launched since nqcb200_create (uploads, sampling, init, step, fold, ...). */
+int nqcb200_get_launch_count(nqcb200_handle* h, int64_t* launches_total);
 
 /* Measured FP64 FMA peak of `device` in TFLOP/s (a DFMA-saturating microbenchmark; the roofline
  * denominator for this FP64 path -- MEASURED_PEAKS.json only carries HBM and bf16 numbers).      */

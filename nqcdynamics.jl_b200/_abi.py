@@ -112,6 +112,7 @@ def bind(lib: C.CDLL, prefix: str) -> None:
     f("get_iesh_stats", [H, _lp, _lp, _lp, _lp])
     f("get_progress", [H, _lp, _lp])
     f("get_last_run_timing", [H, _dp, _lp], required=False)
+    f("get_launch_count", [H, _lp], required=False)
     f("measure_fp64_peak", [C.c_int, _dp], required=False)
 
 
@@ -119,7 +120,7 @@ HEADER_SYMBOLS = [
     "version", "device_count", "create", "destroy", "last_error", "observable_width", "set_state",
     "set_state_diabatic", "set_mapping", "set_gauge_reference", "set_draws", "run", "run_from_host", "sample_state", "get_state", "get_mapping",
     "get_observable_sum", "observable_sum_device", "observable_offset", "get_observable_per_trajectory",
-    "get_diagnostics", "get_counters", "get_iesh_stats", "get_progress", "get_last_run_timing", "measure_fp64_peak",
+    "get_diagnostics", "get_counters", "get_iesh_stats", "get_progress", "get_last_run_timing", "get_launch_count", "measure_fp64_peak",
 ]
 
 _ENGINE_LIB: Optional[C.CDLL] = None
@@ -324,6 +325,11 @@ class CHandle:
         a, b = C.c_int64(), C.c_int64()
         self._call("get_progress", C.byref(a), C.byref(b))
         return int(a.value), int(b.value)
+
+    def launch_count(self) -> int:
+        n = C.c_int64()
+        self._call("get_launch_count", C.byref(n))
+        return int(n.value)
 
     def last_run_timing(self):
         ms, n = C.c_double(), C.c_int64()

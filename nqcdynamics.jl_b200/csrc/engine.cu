@@ -191,6 +191,7 @@ struct nqcb200_handle {
     int nsig = 0, nstate = 0;
     double last_ms = 0.0;
     int64_t last_launches = 0;
+    int64_t launches_total = 0;    // every kernel this handle has launched (any kind)
     int64_t persistent_ctas = 1;   // CTA-per-trajectory kernels: resident CTAs (one per SM)
     bool traj_major = false;       // AdiabaticIESH: psi / occupations / diagnostics stay trajectory-major on the device
     std::string err;
@@ -224,6 +225,7 @@ int upload_field(nqcb200_handle* h, const double* host, double* dst, int C) {
     NQ_CUDA(h, cudaMemcpyAsync(h->staging, host, sizeof(double) * T * C, cudaMemcpyHostToDevice, h->stream));
     dim3 grid((unsigned)((T + 31) / 32), (unsigned)((C + 31) / 32)), block(32, 8);
     aos_to_soa<double, double><<<grid, block, 0, h->stream>>>(h->staging, dst, T, C, 0.0);
+    ++h->launches_total;
     NQ_CUDA(h, cudaGetLastError());
     return NQCB200_OK;
 }
@@ -232,6 +234,7 @@ int download_field(nqcb200_handle* h, const double* src, double* host, int C) {
     if (T == 0 || C == 0) return NQCB200_OK;
     dim3 grid((unsigned)((T + 31) / 32), (unsigned)((C + 31) / 32)), block(32, 8);
     soa_to_aos<double, double><<<grid, block, 0, h->stream>>>(src, h->staging, T, C, 0.0);
+    ++h->launches_total;
     NQ_CUDA(h, cudaGetLastError());
     NQ_CUDA(h, cudaMemcpyAsync(host, h->staging, sizeof(double) * T * C, cudaMemcpyDeviceToHost, h->stream));
     NQ_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -248,12 +251,14 @@ int fold_observables(nqcb200_handle* h) {
     const int64_t total = h->kp.layout.total;
     if (total == 0) return NQCB200_OK;
     fold_replicas<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(h->kp.obs_sum, h->obs_folded, total, kObsReplicas);
+    ++h->launches_total;
     NQ_CUDA(h, cudaGetLastError());
     return NQCB200_OK;
 }
 
 int launch_init(nqcb200_handle* h, int basis, int sample_state, const double* state_draw) {
     h->ks.init<<<grid_for(h), h->ks.block, h->ks.dyn_smem, h->stream>>>(h->kp, basis, sample_state, state_draw);
+    ++h->launches_total;
     NQ_CUDA(h, cudaGetLastError());
     return NQCB200_OK;
 }
@@ -266,6 +271,7 @@ int finish_set_state(nqcb200_handle* h, int basis, int sample_state, const doubl
     int rc;
     if (!iesh && !h->user_gauge && c.nstates > 1 && h->kp.Zprev) {
         fill_identity<<<(unsigned)((T + 255) / 256), 256, 0, h->stream>>>(h->kp.Zprev, T, c.nstates, h->zcopies);
+        ++h->launches_total;
         NQ_CUDA(h, cudaGetLastError());
     }
     NQ_CUDA(h, cudaMemsetAsync(h->kp.obs_sum, 0, sizeof(double) * std::max<int64_t>(1, h->kp.layout.total) * kObsReplicas, h->stream));
@@ -324,6 +330,7 @@ int set_state_impl(nqcb200_handle* h, const double* r, const double* v, const do
         int32_t* stage_i = (int32_t*)h->staging;
         NQ_CUDA(h, cudaMemcpyAsync(stage_i, state, sizeof(int32_t) * cnt, cudaMemcpyHostToDevice, h->stream));
         add_offset_i32<<<(unsigned)((cnt + 255) / 256), 256, 0, h->stream>>>(stage_i, h->kp.state, cnt, -1);
+        ++h->launches_total;
         NQ_CUDA(h, cudaGetLastError());
     }
     int sample_state = 0;
@@ -333,6 +340,7 @@ int set_state_impl(nqcb200_handle* h, const double* r, const double* v, const do
             NQ_CUDA(h, cudaMemcpyAsync(stage_i, state, sizeof(int32_t) * T, cudaMemcpyHostToDevice, h->stream));
             dim3 grid((unsigned)((T + 31) / 32), 1), block(32, 8);
             aos_to_soa<int32_t, int32_t><<<grid, block, 0, h->stream>>>(stage_i, h->kp.state, T, 1, -1);
+            ++h->launches_total;
             NQ_CUDA(h, cudaGetLastError());
         } else {
             sample_state = 1;
@@ -649,7 +657,8 @@ int nqcb200_run(nqcb200_handle* h, int64_t nsteps) {
             const int64_t threads = h->cfg.ntraj * h->ks.step_L;
             const unsigned grid = (unsigned)std::max<int64_t>(1, (threads + h->ks.step_block - 1) / h->ks.step_block);
             h->ks.step<<<grid, h->ks.step_block, h->ks.step_smem, h->stream>>>(h->kp);
-        } else h->ks.step<<<grid_for(h), h->ks.block, h->ks.dyn_smem, h->stream>>>(h->kp);
+            ++h->launches_total;
+        } else { h->ks.step<<<grid_for(h), h->ks.block, h->ks.dyn_smem, h->stream>>>(h->kp); ++h->launches_total; }
         NQ_CUDA(h, cudaGetLastError());
         h->last_launches++;
         done += chunk;
@@ -724,10 +733,13 @@ int nqcb200_sample_state(nqcb200_handle* h, const nqcb200_dist* r_dist, const nq
     if (T > 0) {
         const unsigned grid = (unsigned)((T + 127) / 128);
         sample_rv_kernel<<<grid, 128, 0, h->stream>>>(h->d_dist, h->d_dist + BD, h->kp.r, h->kp.v, T, BD, c.seed, c.traj_offset);
+        ++h->launches_total;
         NQ_CUDA(h, cudaGetLastError());
         if (normal_modes && c.nbeads > 1) {
             from_normal_modes_kernel<<<grid, 128, 0, h->stream>>>(h->kp.nm_to, h->kp.r, h->kp.acc, T, c.nbeads, c.ndofs);
+            ++h->launches_total;
             from_normal_modes_kernel<<<grid, 128, 0, h->stream>>>(h->kp.nm_to, h->kp.v, h->kp.acc, T, c.nbeads, c.ndofs);
+            ++h->launches_total;
             NQ_CUDA(h, cudaGetLastError());
         }
         if (density) {
@@ -738,12 +750,15 @@ int nqcb200_sample_state(nqcb200_handle* h, const nqcb200_dist* r_dist, const nq
             NQ_CUDA(h, cudaMemcpyAsync(h->staging, m.data(), sizeof(double) * 2 * nn, cudaMemcpyHostToDevice, h->stream));
             NQ_CUDA(h, cudaStreamSynchronize(h->stream));   // m goes out of scope
             broadcast_matrix_kernel<<<grid, 128, 0, h->stream>>>(h->staging, h->kp.sig_re, T, nn);
+            ++h->launches_total;
             broadcast_matrix_kernel<<<grid, 128, 0, h->stream>>>(h->staging + nn, h->kp.sig_im, T, nn);
+            ++h->launches_total;
             NQ_CUDA(h, cudaGetLastError());
         }
         if (c.method == NQCB200_METHOD_FSSH) {
             if (state > 0) {
                 fill_i32_kernel<<<grid, 128, 0, h->stream>>>(h->kp.state, T, state - 1);
+                ++h->launches_total;
                 NQ_CUDA(h, cudaGetLastError());
             } else sample_st = 1;
         }
@@ -769,6 +784,7 @@ int nqcb200_get_state(nqcb200_handle* h, double* r, double* v, double* sig_re, d
                 const int64_t cnt = T * h->nstate;
                 int32_t* stage_i = (int32_t*)h->staging;
                 add_offset_i32<<<(unsigned)((cnt + 255) / 256), 256, 0, h->stream>>>(h->kp.state, stage_i, cnt, 1);
+                ++h->launches_total;
                 NQ_CUDA(h, cudaGetLastError());
                 NQ_CUDA(h, cudaMemcpyAsync(state, stage_i, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, h->stream));
             }
@@ -784,6 +800,7 @@ int nqcb200_get_state(nqcb200_handle* h, double* r, double* v, double* sig_re, d
         dim3 grid((unsigned)((T + 31) / 32), 1), block(32, 8);
         if (T > 0) {
             soa_to_aos<int32_t, int32_t><<<grid, block, 0, h->stream>>>(h->kp.state, stage_i, T, h->nstate, 1);
+            ++h->launches_total;
             NQ_CUDA(h, cudaGetLastError());
             NQ_CUDA(h, cudaMemcpyAsync(state, stage_i, sizeof(int32_t) * T * h->nstate, cudaMemcpyDeviceToHost, h->stream));
             NQ_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -861,6 +878,7 @@ int nqcb200_get_counters(nqcb200_handle* h, int64_t* steps, int64_t* hops, int64
     if (nonfinite && T > 0 && h->has_state) {
         NQ_CUDA(h, cudaMemsetAsync(h->kp.counters + 2, 0, sizeof(unsigned long long), h->stream));
         count_nonfinite<<<(unsigned)((T + 255) / 256), 256, 0, h->stream>>>(h->kp.r, h->kp.v, T, h->cfg.nbeads * h->cfg.ndofs, h->kp.counters + 2);
+        ++h->launches_total;
         NQ_CUDA(h, cudaGetLastError());
     }
     NQ_CUDA(h, cudaMemcpyAsync(host, h->kp.counters, sizeof(host), cudaMemcpyDeviceToHost, h->stream));
@@ -917,6 +935,12 @@ int nqcb200_measure_fp64_peak(int device, double* tflops) {
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
     if (cudaGetLastError() != cudaSuccess) return NQCB200_ERR_CUDA;
     *tflops = best;
+    return NQCB200_OK;
+}
+
+int nqcb200_get_launch_count(nqcb200_handle* h, int64_t* launches_total) {
+    if (!h || !launches_total) return NQCB200_ERR_INVALID;
+    *launches_total = h->launches_total;
     return NQCB200_OK;
 }
 
