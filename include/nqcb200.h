@@ -64,7 +64,11 @@ enum nqcb200_method {
     NQCB200_METHOD_EHRENFEST = 2,
     NQCB200_METHOD_IESH      = 3,
     NQCB200_METHOD_CLASSICAL = 4,
-    NQCB200_METHOD_NRPMD     = 5
+    NQCB200_METHOD_NRPMD     = 5,
+    /* Simulation{EhrenfestNA} + VerletwithElectronics (ehrenfest_na.jl:5-126, verlet_with_electronics.jl:76-79):
+     * the AdiabaticIESH state (psi: n x ne) without occupations or hops; mean-field force
+     * -sum_e <psi_e| Z' dV Z |psi_e>.  set_state: sigma = psi, state = NULL.                     */
+    NQCB200_METHOD_EHRENFEST_NA = 6
 };
 
 /* ---- analytic model Hamiltonians (NQCModels.jl, external to the reference tree) ------------ */

@@ -9,10 +9,13 @@ compute call raises.
 from . import _abi
 from ._abi import EngineError
 from .models import *  # noqa: F401,F403
-from .api import (Atoms, FSSH, Ehrenfest, Classical, AdiabaticIESH, NRPMD, Simulation, RingPolymerSimulation, Normal,
+from .api import (Atoms, FSSH, Ehrenfest, EhrenfestNA, Classical, AdiabaticIESH, NRPMD, Simulation, RingPolymerSimulation, Normal,
                   VelocityBoltzmann, Diabatic, Adiabatic, PureState, FermiDiracState, DynamicalDistribution, ProductDistribution,
                   OutputDiabaticPopulation, OutputAdiabaticPopulation, OutputKineticEnergy, OutputPotentialEnergy,
                   OutputTotalEnergy, OutputPosition, OutputVelocity, OutputCentroidPosition, OutputCentroidVelocity,
                   OutputDiscreteState, OutputQuantumSubsystem, OutputSurfaceHops, OutputStateResolvedScattering1D,
+                  OutputFinalKineticEnergy, OutputFirstPosition, OutputFirstVelocity, OutputFinalPosition,
+                  OutputFinalVelocity, OutputTotalDiabaticPopulation, OutputTotalAdiabaticPopulation, OutputSpringEnergy,
+                  OutputCentroidKineticEnergy, OutputFinalTime, OutputDynamicsVariables, OutputInitial, OutputFinal,
                   PopulationCorrelationFunction, SortByTrajectoryReduction, SortByOutputReduction, SumReduction,
                   MeanReduction, EnsembleB200, run_dynamics)

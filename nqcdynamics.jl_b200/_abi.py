@@ -16,7 +16,8 @@ ABI_VERSION = 1
 MAX_PARAMS = 32
 
 # enums (include/nqcb200.h)
-METHOD_FSSH, METHOD_EHRENFEST, METHOD_IESH, METHOD_CLASSICAL, METHOD_NRPMD = 1, 2, 3, 4, 5
+METHOD_FSSH, METHOD_EHRENFEST, METHOD_IESH, METHOD_CLASSICAL, METHOD_NRPMD, METHOD_EHRENFEST_NA = 1, 2, 3, 4, 5, 6
+IESH_FAMILY = (METHOD_IESH, METHOD_EHRENFEST_NA)      # psi: n x ne, trajectory-major
 (MODEL_TULLY_ONE, MODEL_TULLY_TWO, MODEL_TULLY_THREE, MODEL_DOUBLE_WELL, MODEL_SPIN_BOSON,
  MODEL_THREE_STATE_MORSE, MODEL_HARMONIC, MODEL_FREE, MODEL_ANDERSON_HOLSTEIN_MIAO_SUBOTNIK) = range(1, 10)
 RESCALE_STANDARD, RESCALE_VINVERSION, RESCALE_OFF = 0, 1, 2
@@ -160,7 +161,7 @@ class CHandle:
             raise EngineError(rc, (msg or b"").decode())
         self.n, self.D, self.B, self.ne = cfg.nstates, cfg.ndofs, cfg.nbeads, cfg.nelectrons
         self.T = int(cfg.ntraj)
-        self.nsig = self.n * (self.ne if cfg.method == METHOD_IESH else self.n)
+        self.nsig = self.n * (self.ne if cfg.method in IESH_FAMILY else self.n)
         self.nstate = self.ne if cfg.method == METHOD_IESH else 1
 
     # -- plumbing ------------------------------------------------------------------------------
@@ -265,9 +266,9 @@ class CHandle:
     def get_state(self):
         T, B, D, n = self.T, self.B, self.D, self.n
         r = np.empty((T, B, D)); v = np.empty((T, B, D))
-        has_sig = self.cfg.method in (METHOD_FSSH, METHOD_EHRENFEST, METHOD_IESH)
+        has_sig = self.cfg.method in (METHOD_FSSH, METHOD_EHRENFEST) + IESH_FAMILY
         has_state = self.cfg.method in (METHOD_FSSH, METHOD_IESH)
-        ncol = self.ne if self.cfg.method == METHOD_IESH else n
+        ncol = self.ne if self.cfg.method in IESH_FAMILY else n
         sre = np.empty((T, ncol, n)) if has_sig else None
         sim = np.empty((T, ncol, n)) if has_sig else None
         st = np.empty((T, self.nstate), dtype=np.int32) if has_state else None

@@ -75,6 +75,12 @@ class AdiabaticIESH:
 
 
 @dataclass
+class EhrenfestNA:
+    """``Simulation{EhrenfestNA}`` (ehrenfest_na.jl): independent-electron mean-field dynamics on the IESH state."""
+    method_id: int = A.METHOD_EHRENFEST_NA
+
+
+@dataclass
 class NRPMD:
     γ: float = 0.5                        # nrpmd.jl:43
     method_id: int = A.METHOD_NRPMD
@@ -281,7 +287,12 @@ class ProductDistribution:
 class _Output:
     name: str
     obs: int
-    kind: str = "series"      # series | final | hops | scatter
+    kind: str = "series"      # series | first | last | sum | hops | scatter | spring | centroid_ke | variables[_first|_last] | final_time
+    deps: Tuple[int, ...] = ()   # device observables this output is built from (default: just `obs`)
+
+    @property
+    def needs(self) -> Tuple[int, ...]:
+        return self.deps or (self.obs,)
 
 
 OutputDiabaticPopulation = _Output("OutputDiabaticPopulation", A.OBS_DIABATIC_POP)
@@ -296,6 +307,22 @@ OutputCentroidVelocity = _Output("OutputCentroidVelocity", A.OBS_VELOCITY)
 OutputDiscreteState = _Output("OutputDiscreteState", A.OBS_DISCRETE_STATE)
 OutputQuantumSubsystem = _Output("OutputQuantumSubsystem", A.OBS_SIGMA)
 OutputSurfaceHops = _Output("OutputSurfaceHops", A.OBS_DISCRETE_STATE, "hops")
+# outputs assembled on the host from the same device streams (DynamicsOutputs.jl:101-141,192-227,387-397)
+OutputFinalKineticEnergy = _Output("OutputFinalKineticEnergy", A.OBS_KINETIC, "last")
+OutputFirstPosition = _Output("OutputFirstPosition", A.OBS_POSITION, "first")
+OutputFirstVelocity = _Output("OutputFirstVelocity", A.OBS_VELOCITY, "first")
+OutputFinalPosition = _Output("OutputFinalPosition", A.OBS_POSITION, "last")
+OutputFinalVelocity = _Output("OutputFinalVelocity", A.OBS_VELOCITY, "last")
+OutputTotalDiabaticPopulation = _Output("OutputTotalDiabaticPopulation", A.OBS_DIABATIC_POP, "sum")
+OutputTotalAdiabaticPopulation = _Output("OutputTotalAdiabaticPopulation", A.OBS_ADIABATIC_POP, "sum")
+OutputSpringEnergy = _Output("OutputSpringEnergy", A.OBS_TOTAL_ENERGY, "spring",
+                             (A.OBS_TOTAL_ENERGY, A.OBS_KINETIC, A.OBS_POTENTIAL))
+OutputCentroidKineticEnergy = _Output("OutputCentroidKineticEnergy", A.OBS_VELOCITY, "centroid_ke")
+OutputFinalTime = _Output("OutputFinalTime", A.OBS_KINETIC, "final_time")
+_VARS = (A.OBS_POSITION, A.OBS_VELOCITY, A.OBS_SIGMA, A.OBS_DISCRETE_STATE)
+OutputDynamicsVariables = _Output("OutputDynamicsVariables", A.OBS_POSITION, "variables", _VARS)
+OutputInitial = _Output("OutputInitial", A.OBS_POSITION, "variables_first", _VARS)
+OutputFinal = _Output("OutputFinal", A.OBS_POSITION, "variables_last", _VARS)
 
 
 def OutputStateResolvedScattering1D(sim, type="adiabatic"):      # DynamicsOutputs.jl:313-338
@@ -344,7 +371,7 @@ def _shape_series(sim, out: _Output, arr: np.ndarray):
     if out.obs in (A.OBS_POPCORR_DIABATIC, A.OBS_POPCORR_ADIABATIC):
         return arr.reshape(-1, n, n).transpose(0, 2, 1)          # column-major (i, j) per frame
     if out.obs == A.OBS_SIGMA:
-        ncol = sim.model.nelectrons if sim.method.method_id == A.METHOD_IESH else n      # psi is (n, ne) for IESH
+        ncol = sim.model.nelectrons if sim.method.method_id in A.IESH_FAMILY else n      # psi is (n, ne) for IESH
         c = arr.reshape(-1, 2, ncol, n)
         return (c[:, 0] + 1j * c[:, 1]).transpose(0, 2, 1)
     if out.obs in (A.OBS_POSITION, A.OBS_VELOCITY):
@@ -354,8 +381,9 @@ def _shape_series(sim, out: _Output, arr: np.ndarray):
     return arr
 
 
-def _finalise(sim, out: _Output, arr: np.ndarray, per_trajectory: bool):
-    """Engine array -> reference output value.  arr: (nsave, width) (reduced) or that per trajectory."""
+def _finalise(sim, out: _Output, arrs: Dict[int, np.ndarray], per_trajectory: bool, t_final: float = 0.0):
+    """Engine arrays -> reference output value.  arrs[obs]: (nsave, width) (reduced) or that of one trajectory."""
+    arr = arrs[out.obs]
     if out.kind == "scatter":
         last = arr[-1]
         n = sim.model.nstates
@@ -367,9 +395,39 @@ def _finalise(sim, out: _Output, arr: np.ndarray, per_trajectory: bool):
         if sim.method.method_id == A.METHOD_IESH:
             st = np.sort(st, axis=1)        # the occupation vector is a set (an accepted hop is not re-sorted, iesh.jl:399-407)
         return int(np.count_nonzero(np.any(st[1:] != st[:-1], axis=1)))
+    if out.kind == "final_time":
+        return t_final
+    if out.kind == "spring":                # classical_hamiltonian = kinetic + potential + spring (DynamicsUtils.jl:108-151)
+        return (arrs[A.OBS_TOTAL_ENERGY] - arrs[A.OBS_KINETIC] - arrs[A.OBS_POTENTIAL])[:, 0]
+    if out.kind == "centroid_ke":           # DynamicsOutputs.jl:50-59: sum_i m_i v_centroid,i^2 / 2
+        return 0.5 * np.sum(sim.dof_masses * arr * arr, axis=1)
+    if out.kind.startswith("variables"):
+        if not per_trajectory:
+            raise ValueError(f"{out.name} is a per-trajectory output (use SortByTrajectoryReduction)")
+        if sim.beads > 1:
+            raise ValueError(f"{out.name}: bead-resolved frames are not streamed for ring polymers (centroids only)")
+        method = sim.method.method_id
+        r = _shape_series(sim, OutputPosition, arrs[A.OBS_POSITION])
+        v = _shape_series(sim, OutputVelocity, arrs[A.OBS_VELOCITY])
+        frames = []
+        for k in range(r.shape[0]):
+            u = {"v": v[k], "r": r[k]}
+            if method in (A.METHOD_FSSH, A.METHOD_EHRENFEST) + A.IESH_FAMILY:
+                sig = _shape_series(sim, OutputQuantumSubsystem, arrs[A.OBS_SIGMA][k:k + 1])[0]
+                u["σreal"], u["σimag"] = sig.real.copy(), sig.imag.copy()
+            if method in (A.METHOD_FSSH, A.METHOD_IESH):
+                u["state"] = np.rint(arrs[A.OBS_DISCRETE_STATE][k]).astype(np.int64)
+            frames.append(u)
+        return frames[0] if out.kind == "variables_first" else frames[-1] if out.kind == "variables_last" else frames
     val = _shape_series(sim, out, arr)
     if out.obs == A.OBS_DISCRETE_STATE:
         val = np.rint(val).astype(np.int64)
+    if out.kind == "first":
+        return val[0]
+    if out.kind == "last":
+        return val[-1]
+    if out.kind == "sum":
+        return val.sum(axis=1)
     return val
 
 
@@ -402,8 +460,15 @@ def run_dynamics(sim: Simulation, tspan, distribution, *, output, selection: Opt
     nsave = nsteps // save_every + 1
     per_traj = isinstance(reduction, (SortByTrajectoryReduction, SortByOutputReduction))
     obs_mask = 0
+    method_id = sim.method.method_id
     for o in outputs:
-        obs_mask |= 1 << o.obs
+        for d in o.needs:
+            if d == A.OBS_SIGMA and method_id not in (A.METHOD_FSSH, A.METHOD_EHRENFEST) + A.IESH_FAMILY:
+                continue
+            if d == A.OBS_DISCRETE_STATE and method_id not in (A.METHOD_FSSH, A.METHOD_IESH):
+                continue
+            obs_mask |= 1 << d
+    obs_ids = [d for d in range(A.OBS_COUNT) if (obs_mask >> d) & 1]
 
     method, model = sim.method, sim.model
     rng = np.random.default_rng(seed)
@@ -415,7 +480,7 @@ def run_dynamics(sim: Simulation, tspan, distribution, *, output, selection: Opt
     dev_spec = None
     if getattr(alg, "device_sampling", False):
         dev_spec = nuclear.device_spec() if selection is None else None
-        if dev_spec is None or method.method_id in (A.METHOD_IESH, A.METHOD_NRPMD):
+        if dev_spec is None or method.method_id in A.IESH_FAMILY + (A.METHOD_NRPMD,):
             raise ValueError("device_sampling needs number / Normal / VelocityBoltzmann entries, no selection, and a method "
                              "other than AdiabaticIESH / NRPMD")
         r = v = None
@@ -423,7 +488,8 @@ def run_dynamics(sim: Simulation, tspan, distribution, *, output, selection: Opt
         r, v = nuclear.sample(rng, T, selection)
     if density and electronic is None:
         raise ValueError("FSSH / Ehrenfest need an electronic distribution: nuclear * PureState(i)")
-    iesh = method.method_id == A.METHOD_IESH
+    iesh = method.method_id in A.IESH_FAMILY
+    mean_field = method.method_id == A.METHOD_EHRENFEST_NA
     psi0 = occ0 = None
     if iesh:
         # DynamicsVariables(sim, v, r) -> the ne lowest adiabatic orbitals (iesh.jl:89-97);
@@ -438,7 +504,7 @@ def run_dynamics(sim: Simulation, tspan, distribution, *, output, selection: Opt
             for t in range(T):
                 occ0[t] = electronic.sample_occupations(rng, model.adiabatic_energies(r[t].reshape(-1)), ne)
         else:
-            raise TypeError("AdiabaticIESH takes no electronic distribution (ground state) or a FermiDiracState")
+            raise TypeError("AdiabaticIESH / EhrenfestNA take no electronic distribution (ground state) or a FermiDiracState")
         psi0 = np.zeros((T, ne, n))
         psi0[np.arange(T)[:, None], np.arange(ne)[None, :], occ0 - 1] = 1.0
 
@@ -466,6 +532,7 @@ def run_dynamics(sim: Simulation, tspan, distribution, *, output, selection: Opt
                 t0=t0, temperature=sim.temperature, nrpmd_gamma=getattr(method, "γ", 0.5),
                 edc_C=getattr(method, "decoherence_C", 0.0))
             with Engine(cfg, keep) as eng:
+                ran = False
                 if dev_spec is not None:
                     rho1 = None
                     adiabatic = True
@@ -485,22 +552,25 @@ def run_dynamics(sim: Simulation, tspan, distribution, *, output, selection: Opt
                     rho = np.zeros((Tg, n, n))
                     rho[:, electronic.state - 1, electronic.state - 1] = 1.0
                     adiabatic = isinstance(electronic.statetype, Adiabatic) or electronic.statetype is Adiabatic
-                    if adiabatic:
-                        state = np.full(Tg, electronic.state, dtype=np.int32) if method.method_id == A.METHOD_FSSH else None
+                    state = np.full(Tg, electronic.state, dtype=np.int32) if (adiabatic and method.method_id == A.METHOD_FSSH) else None
+                    if draws is None:
+                        # one call per batch (nqcb200_run_from_host): kernels with a launch-fused initialisation read
+                        # r, v in place; everything else behaves like set_state[_diabatic] + run
+                        eng.run_from_host(rg, vg, rho, None, state, None, diabatic=not adiabatic, nsteps=nsteps)
+                        ran = True
+                    elif adiabatic:
                         eng.set_state(rg, vg, rho, None, state)
                     else:
                         eng.set_state_diabatic(rg, vg, rho)
                 elif iesh:
-                    eng.set_state(rg, vg, psi0[lo:hi], None, occ0[lo:hi])
+                    eng.set_state(rg, vg, psi0[lo:hi], None, None if mean_field else occ0[lo:hi])
                 else:
                     eng.set_state(rg, vg)
                 if draws is not None:
                     eng.set_draws(np.ascontiguousarray(draws[:, lo:hi]))
-                eng.run(nsteps)
-                res = {}
-                for o in outputs:
-                    res[o] = eng.observable_per_trajectory(o.obs) if per_traj else eng.observable_sum(o.obs)
-                results[g] = res
+                if not ran:
+                    eng.run(nsteps)
+                results[g] = {d: (eng.observable_per_trajectory(d) if per_traj else eng.observable_sum(d)) for d in obs_ids}
         except BaseException as exc:   # re-raised on the caller's thread
             errors.append(exc)
 
@@ -515,21 +585,22 @@ def run_dynamics(sim: Simulation, tspan, distribution, *, output, selection: Opt
 
     time = t0 + dt * save_every * np.arange(nsave)
     if per_traj:
-        per_out = {o: np.concatenate([res[o] for res in results], axis=0) for o in outputs}    # (T, nsave, w)
+        per_obs = {k: np.concatenate([res[k] for res in results], axis=0) for k in obs_ids}    # (T, nsave, w)
         trajs = []
         for i in range(T):
             d: Dict[str, Any] = {"Time": time.copy()} if savetime else {}
             for o in outputs:
-                d[o.name] = _finalise(sim, o, per_out[o][i], True)
+                d[o.name] = _finalise(sim, o, {k: per_obs[k][i] for k in obs_ids}, True, time[-1])
             trajs.append(d)
         if isinstance(reduction, SortByOutputReduction):
             keys = list(trajs[0].keys())
             return {k: [tr[k] for tr in trajs] for k in keys}
         return trajs[0] if T == 1 else trajs
-    summed = {o: sum(res[o] for res in results) for o in outputs}
     scale = 1.0 / T if isinstance(reduction, MeanReduction) else 1.0
+    summed = {k: sum(res[k] for res in results) * scale for k in obs_ids}
     d = {"Time": time * (T * scale)} if savetime else {}     # `:Time` is reduced too (test/Ensembles/ensembles.jl:21)
     for o in outputs:
-        val = _finalise(sim, o, summed[o] * scale, False)
-        d[o.name] = val
+        if o.kind == "centroid_ke":
+            raise ValueError("OutputCentroidKineticEnergy is not linear in the stream: use a per-trajectory reduction")
+        d[o.name] = _finalise(sim, o, summed, False, time[-1] * (T * scale))
     return d

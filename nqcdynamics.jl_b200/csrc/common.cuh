@@ -58,6 +58,7 @@ struct KParams {
     int32_t save_every, nsave;
     int32_t rescaling, rng, diagnostics, per_trajectory;
     int32_t estimate_probability, disable_hopping;
+    int32_t mean_field;   // EhrenfestNA on the IESH kernel: force and estimators from psi, no occupations
     uint32_t observables;
     uint64_t seed;
     double dt, t0, omega_n, nrpmd_gamma, edc_C;

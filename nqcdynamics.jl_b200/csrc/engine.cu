@@ -24,6 +24,9 @@ namespace {
 
 std::string g_create_error;
 
+// AdiabaticIESH and EhrenfestNA share the wavefunction layout (psi: n x ne, trajectory-major) and the kernel family
+inline bool iesh_family(int method) { return method == NQCB200_METHOD_IESH || method == NQCB200_METHOD_EHRENFEST_NA; }
+
 // Choose a kernel for (method, model, n, D, B); false => NQCB200_ERR_UNSUPPORTED (no fallback).
 bool select_kernels(const nqcb200_config& c, KernelSet& out, std::string& why) {
     switch (c.method) {
@@ -34,7 +37,8 @@ bool select_kernels(const nqcb200_config& c, KernelSet& out, std::string& why) {
             if (c.nbeads > 1) return select_ring_density(c, out, why);
             if (c.model == NQCB200_MODEL_SPIN_BOSON) return select_density_spinboson(c, out, why);
             return select_density_1d(c, out, why);
-        case NQCB200_METHOD_IESH: return select_iesh(c, out, why);
+        case NQCB200_METHOD_IESH:
+        case NQCB200_METHOD_EHRENFEST_NA: return select_iesh(c, out, why);
         default: break;
     }
     why = "unknown dynamics method";
@@ -77,6 +81,10 @@ __global__ void soa_to_aos(const Tin* __restrict__ in, Tout* __restrict__ out, i
 __global__ void add_offset_i32(const int32_t* __restrict__ in, int32_t* __restrict__ out, int64_t count, int32_t add) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < count) out[i] = in[i] + add;
+}
+__global__ void iota_mod_i32(int32_t* out, int64_t count, int mod) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) out[i] = (int32_t)(i % mod);
 }
 __global__ void fold_replicas(const double* __restrict__ rep, double* __restrict__ out, int64_t total, int nrep) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -159,9 +167,9 @@ int obs_width(const nqcb200_config& c, int id) {
         case NQCB200_OBS_POPCORR_DIABATIC: case NQCB200_OBS_POPCORR_ADIABATIC: return n * n;
         case NQCB200_OBS_KINETIC: case NQCB200_OBS_POTENTIAL: case NQCB200_OBS_TOTAL_ENERGY: return 1;
         case NQCB200_OBS_POSITION: case NQCB200_OBS_VELOCITY: return D;
-        case NQCB200_OBS_DISCRETE_STATE: return c.method == NQCB200_METHOD_IESH ? c.nelectrons : 1;
+        case NQCB200_OBS_DISCRETE_STATE: return iesh_family(c.method) ? c.nelectrons : 1;
         case NQCB200_OBS_SCATTERING: case NQCB200_OBS_SCATTERING_DIABATIC: return 2 * n;
-        case NQCB200_OBS_SIGMA: return c.method == NQCB200_METHOD_IESH ? 2 * n * c.nelectrons : 2 * n * n;
+        case NQCB200_OBS_SIGMA: return iesh_family(c.method) ? 2 * n * c.nelectrons : 2 * n * n;
     }
     return 0;
 }
@@ -267,7 +275,7 @@ int launch_init(nqcb200_handle* h, int basis, int sample_state, const double* st
 int finish_set_state(nqcb200_handle* h, int basis, int sample_state, const double* state_draw, bool fused) {
     const nqcb200_config& c = h->cfg;
     const int64_t T = c.ntraj;
-    const bool iesh = (c.method == NQCB200_METHOD_IESH);
+    const bool iesh = iesh_family(c.method);
     int rc;
     if (!iesh && !h->user_gauge && c.nstates > 1 && h->kp.Zprev) {
         fill_identity<<<(unsigned)((T + 255) / 256), 256, 0, h->stream>>>(h->kp.Zprev, T, c.nstates, h->zcopies);
@@ -304,9 +312,10 @@ int set_state_impl(nqcb200_handle* h, const double* r, const double* v, const do
     const nqcb200_config& c = h->cfg;
     const int64_t T = c.ntraj;
     const bool density = (c.method == NQCB200_METHOD_FSSH || c.method == NQCB200_METHOD_EHRENFEST);
-    const bool iesh = (c.method == NQCB200_METHOD_IESH);
+    const bool iesh = iesh_family(c.method);
     if (density && !sre) { h->err = "the density matrix is required for FSSH / Ehrenfest"; return NQCB200_ERR_INVALID; }
-    if (iesh && (!sre || !state)) { h->err = "AdiabaticIESH needs psi (n x ne) and the occupied states"; return NQCB200_ERR_INVALID; }
+    const bool mean_field = (c.method == NQCB200_METHOD_EHRENFEST_NA);
+    if (iesh && (!sre || (!state && !mean_field))) { h->err = "AdiabaticIESH needs psi (n x ne) and the occupied states"; return NQCB200_ERR_INVALID; }
     if (iesh && basis != 0) { h->err = "AdiabaticIESH: only adiabatic initial wavefunctions are supported"; return NQCB200_ERR_UNSUPPORTED; }
     NQ_CUDA(h, cudaSetDevice(c.device));
     int rc;
@@ -328,8 +337,12 @@ int set_state_impl(nqcb200_handle* h, const double* r, const double* v, const do
         else NQ_CUDA(h, cudaMemsetAsync(h->kp.sig_im, 0, bytes, h->stream));
         const int64_t cnt = T * h->nstate;
         int32_t* stage_i = (int32_t*)h->staging;
-        NQ_CUDA(h, cudaMemcpyAsync(stage_i, state, sizeof(int32_t) * cnt, cudaMemcpyHostToDevice, h->stream));
-        add_offset_i32<<<(unsigned)((cnt + 255) / 256), 256, 0, h->stream>>>(stage_i, h->kp.state, cnt, -1);
+        if (state) {
+            NQ_CUDA(h, cudaMemcpyAsync(stage_i, state, sizeof(int32_t) * cnt, cudaMemcpyHostToDevice, h->stream));
+            add_offset_i32<<<(unsigned)((cnt + 255) / 256), 256, 0, h->stream>>>(stage_i, h->kp.state, cnt, -1);
+        } else {   // EhrenfestNA: no occupations; the kernel's bookkeeping arrays get the first ne states
+            iota_mod_i32<<<(unsigned)((cnt + 255) / 256), 256, 0, h->stream>>>(h->kp.state, cnt, h->nstate);
+        }
         ++h->launches_total;
         NQ_CUDA(h, cudaGetLastError());
     }
@@ -385,7 +398,11 @@ int nqcb200_create(const nqcb200_config* cfg, nqcb200_handle** out) {
     KernelSet ks;
     std::string why;
     if (!select_kernels(*cfg, ks, why)) { g_create_error = why; return NQCB200_ERR_UNSUPPORTED; }
-    if (cfg->method == NQCB200_METHOD_IESH &&
+    if (cfg->method == NQCB200_METHOD_EHRENFEST_NA &&
+        (cfg->observables & ((1u << NQCB200_OBS_DIABATIC_POP) | (1u << NQCB200_OBS_SCATTERING_DIABATIC) | (1u << NQCB200_OBS_DISCRETE_STATE)))) {
+        g_create_error = "EhrenfestNA has no discrete state and no diabatic-population estimator"; return NQCB200_ERR_UNSUPPORTED;
+    }
+    if (iesh_family(cfg->method) &&
         (cfg->observables & ((1u << NQCB200_OBS_POPCORR_DIABATIC) | (1u << NQCB200_OBS_POPCORR_ADIABATIC)))) {
         g_create_error = "PopulationCorrelationFunction is not available for AdiabaticIESH"; return NQCB200_ERR_UNSUPPORTED;
     }
@@ -413,8 +430,10 @@ int nqcb200_create(const nqcb200_config* cfg, nqcb200_handle** out) {
     kp.save_every = c.save_every; kp.nsave = c.nsave; kp.rescaling = c.rescaling; kp.rng = c.rng;
     kp.diagnostics = c.diagnostics; kp.per_trajectory = c.per_trajectory;
     kp.estimate_probability = c.estimate_probability; kp.disable_hopping = c.disable_hopping;
+    kp.mean_field = (c.method == NQCB200_METHOD_EHRENFEST_NA) ? 1 : 0;
+    if (kp.mean_field) kp.disable_hopping = 1;
     kp.observables = c.observables; kp.seed = c.seed; kp.dt = c.dt; kp.t0 = c.t0;
-    kp.omega_n = B * c.temperature; kp.nrpmd_gamma = c.nrpmd_gamma; kp.edc_C = c.edc_C;
+    kp.omega_n = B * c.temperature; kp.nrpmd_gamma = c.nrpmd_gamma; kp.edc_C = kp.mean_field ? 0.0 : c.edc_C;
     std::memcpy(kp.params, c.params, sizeof(kp.params));
     // observable layout
     int64_t off = 0;
@@ -424,9 +443,9 @@ int nqcb200_create(const nqcb200_config* cfg, nqcb200_handle** out) {
         if (c.observables & (1u << id)) { kp.layout.offset[id] = off; off += (int64_t)c.nsave * kp.layout.width[id]; }
     }
     kp.layout.total = off;
-    const bool iesh = (c.method == NQCB200_METHOD_IESH);
+    const bool iesh = iesh_family(c.method);
     h->nsig = (c.method == NQCB200_METHOD_FSSH || c.method == NQCB200_METHOD_EHRENFEST) ? n * n : (iesh ? n * c.nelectrons : 0);
-    h->nstate = (c.method == NQCB200_METHOD_FSSH) ? 1 : (iesh ? c.nelectrons : 0);
+    h->nstate = (c.method == NQCB200_METHOD_FSSH) ? 1 : (iesh ? c.nelectrons : 0);   // EhrenfestNA: internal bookkeeping only
     h->zcopies = (B > 1) ? B + 1 : 1;
     h->traj_major = iesh;
     if (ks.cta_per_trajectory) {
@@ -717,7 +736,7 @@ int nqcb200_sample_state(nqcb200_handle* h, const nqcb200_dist* r_dist, const nq
     const nqcb200_config& c = h->cfg;
     const int64_t T = c.ntraj;
     const bool density = (c.method == NQCB200_METHOD_FSSH || c.method == NQCB200_METHOD_EHRENFEST);
-    if (c.method == NQCB200_METHOD_IESH) { h->err = "device-side sampling is not available for AdiabaticIESH"; return NQCB200_ERR_UNSUPPORTED; }
+    if (iesh_family(c.method)) { h->err = "device-side sampling is not available for AdiabaticIESH / EhrenfestNA"; return NQCB200_ERR_UNSUPPORTED; }
     if (density && !rho_re) { h->err = "the density matrix is required for FSSH / Ehrenfest"; return NQCB200_ERR_INVALID; }
     if (state < 0 || state > c.nstates) { h->err = "state out of range"; return NQCB200_ERR_INVALID; }
     if (c.method == NQCB200_METHOD_FSSH && !diabatic && state == 0) { h->err = "FSSH needs the active state (or a diabatic rho)"; return NQCB200_ERR_INVALID; }

@@ -242,6 +242,24 @@ NQ_D void iesh_refresh_unoccupied(const KParams& p, IeshSmem& S) {
     __syncthreads();
 }
 
+// EhrenfestNA force weight (ehrenfest_na.jl:72-90 with Z' dV Z = h' z0 z0'): sum_e |sum_n z0[n] psi[n,e]|^2.
+// Warps take electrons, lanes split the states; result on every thread.
+NQ_D double iesh_mean_field_weight(const KParams& p, const IeshSmem& S, const double* psi_re, const double* psi_im) {
+    const int n = p.n, ne = p.ne, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    double part = 0.0;
+    for (int e = warp; e < ne; e += nwarps) {
+        double cr = 0.0, ci = 0.0;
+        for (int i = lane; i < n; i += 32) {
+            cr = fma(S.z0[i], psi_re[(int64_t)n * e + i], cr);
+            ci = fma(S.z0[i], psi_im[(int64_t)n * e + i], ci);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { cr += __shfl_xor_sync(0xffffffffu, cr, o); ci += __shfl_xor_sync(0xffffffffu, ci, o); }
+        if (lane == 0) part += cr * cr + ci * ci;
+    }
+    return iesh_block_sum(part, S.red);
+}
+
 NQ_D void iesh_emit(const KParams& p, int64_t traj, int isave, int obs_id, int k, double val) {
     const int64_t off = p.layout.offset[obs_id] + (int64_t)isave * p.layout.width[obs_id] + k;
     if (p.obs_traj != nullptr) p.obs_traj[off * p.ntraj + traj] = val;
@@ -258,7 +276,14 @@ NQ_D void iesh_record_save(const KParams& p, IeshSmem& S, int64_t traj, int isav
     const bool trans = r > 0.0;
     if (obs & ((1u << NQCB200_OBS_ADIABATIC_POP) | (1u << NQCB200_OBS_SCATTERING))) {
         for (int i = tid; i < n; i += nt) {
-            const double a = (S.flag[i] >= 0) ? 1.0 : 0.0;                       // iesh.jl:371-375
+            double a = (S.flag[i] >= 0) ? 1.0 : 0.0;                             // iesh.jl:371-375
+            if (p.mean_field) {                                                   // ehrenfest_na.jl:116-125
+                a = 0.0;
+                for (int e = 0; e < ne; ++e) {
+                    const double x = psi_re[(int64_t)n * e + i], y = psi_im[(int64_t)n * e + i];
+                    a += x * x + y * y;
+                }
+            }
             if (obs & (1u << NQCB200_OBS_ADIABATIC_POP)) iesh_emit(p, traj, isave, NQCB200_OBS_ADIABATIC_POP, i, a);
             if (obs & (1u << NQCB200_OBS_SCATTERING)) {
                 iesh_emit(p, traj, isave, NQCB200_OBS_SCATTERING, i, (last && !trans) ? a : 0.0);
@@ -310,7 +335,14 @@ NQ_D void iesh_record_save(const KParams& p, IeshSmem& S, int64_t traj, int isav
             double h, dh, u0, du0;
             mdl.eval(r, h, dh, u0, du0);
             double pot = u0;                                                      // iesh.jl:380-388
-            for (int e = 0; e < ne; ++e) pot += S.lam[S.occ[e]];
+            if (p.mean_field) {                                                   // ehrenfest_na.jl:103-114
+                for (int e = 0; e < ne; ++e)
+                    for (int i = 0; i < n; ++i) {
+                        const double x = psi_re[(int64_t)n * e + i], y = psi_im[(int64_t)n * e + i];
+                        pot += S.lam[i] * (x * x + y * y);
+                    }
+            } else
+                for (int e = 0; e < ne; ++e) pot += S.lam[S.occ[e]];
             if (obs & (1u << NQCB200_OBS_KINETIC)) iesh_emit(p, traj, isave, NQCB200_OBS_KINETIC, 0, kin);
             if (obs & (1u << NQCB200_OBS_POTENTIAL)) iesh_emit(p, traj, isave, NQCB200_OBS_POTENTIAL, 0, pot);
             if (obs & (1u << NQCB200_OBS_TOTAL_ENERGY)) iesh_emit(p, traj, isave, NQCB200_OBS_TOTAL_ENERGY, 0, kin + pot);
@@ -665,7 +697,10 @@ __global__ void __launch_bounds__(384, 1) iesh_step_kernel(const __grid_constant
             double h, dh, u0, du0;
             mdl.eval(r, h, dh, u0, du0);
             iesh_eigen(p, S, h, vnorm, false);
-            {
+            if (p.mean_field) {
+                const double wsum = iesh_mean_field_weight(p, S, psi_re, psi_im);  // sigma_prev: psi before this step's propagation
+                acc = (-du0 - dh * wsum) / mdl.mass;
+            } else {
                 double part = 0.0;
                 for (int e = tid; e < ne; e += nt) { const double z = S.z0[S.occ[e]]; part += z * z; }
                 const double occsum = iesh_block_sum(part, S.red);
@@ -988,9 +1023,13 @@ __global__ void __launch_bounds__(384, 1) iesh_init_kernel(const __grid_constant
         __syncthreads();
         for (int i = tid; i < n; i += nt) { S.z0[i] *= S.sgn[i]; p.iesh_sgn[traj * n + i] = S.sgn[i]; p.iesh_lam[traj * n + i] = S.lam[i]; }
         __syncthreads();
-        double part = 0.0;
-        for (int e = tid; e < ne; e += nt) { const double z = S.z0[S.occ[e]]; part += z * z; }
-        const double occsum = iesh_block_sum(part, S.red);
+        double occsum;
+        if (p.mean_field) occsum = iesh_mean_field_weight(p, S, psi_re, psi_im);
+        else {
+            double part = 0.0;
+            for (int e = tid; e < ne; e += nt) { const double z = S.z0[S.occ[e]]; part += z * z; }
+            occsum = iesh_block_sum(part, S.red);
+        }
         if (tid == 0) p.acc[traj] = (-du0 - dh * occsum) / mdl.mass;
         iesh_record_save(p, S, traj, 0, r, v, mdl, psi_re, psi_im, S.work + p.iesh.off_b);
         {

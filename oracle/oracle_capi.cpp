@@ -18,6 +18,8 @@ using namespace nqco;
 
 namespace {
 
+inline bool iesh_family(int method) { return method == NQCB200_METHOD_IESH || method == NQCB200_METHOD_EHRENFEST_NA; }
+
 // Philox4x32-10 (Salmon et al. 2011).  key = seed, counter = (global trajectory id, step, purpose)
 inline void philox4x32_10(uint32_t ctr[4], uint32_t key0, uint32_t key1) {
     const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
@@ -81,9 +83,9 @@ static int obs_width(const nqcb200_config& c, int id) {
         case NQCB200_OBS_POPCORR_DIABATIC: case NQCB200_OBS_POPCORR_ADIABATIC: return n * n;
         case NQCB200_OBS_KINETIC: case NQCB200_OBS_POTENTIAL: case NQCB200_OBS_TOTAL_ENERGY: return 1;
         case NQCB200_OBS_POSITION: case NQCB200_OBS_VELOCITY: return D;
-        case NQCB200_OBS_DISCRETE_STATE: return c.method == NQCB200_METHOD_IESH ? c.nelectrons : 1;
+        case NQCB200_OBS_DISCRETE_STATE: return iesh_family(c.method) ? c.nelectrons : 1;
         case NQCB200_OBS_SCATTERING: case NQCB200_OBS_SCATTERING_DIABATIC: return 2 * n;
-        case NQCB200_OBS_SIGMA: return c.method == NQCB200_METHOD_IESH ? 2 * n * c.nelectrons : 2 * n * n;
+        case NQCB200_OBS_SIGMA: return iesh_family(c.method) ? 2 * n * c.nelectrons : 2 * n * n;
     }
     return 0;
 }
@@ -226,7 +228,7 @@ int nqco_create(const nqcb200_config* cfg, nqco_handle** out) {
         // (rpmdef.jl:30-57) which is out of scope; quantum method on a classical model is invalid
         g_err = "method/model combination unsupported"; delete h; return NQCB200_ERR_UNSUPPORTED;
     }
-    if (cfg->method == NQCB200_METHOD_IESH && (S.ne < 1 || S.ne >= S.n || S.B != 1)) {
+    if (iesh_family(cfg->method) && (S.ne < 1 || S.ne >= S.n || S.B != 1)) {
         g_err = "IESH needs 1 <= nelectrons < nstates and nbeads == 1"; delete h; return NQCB200_ERR_INVALID;
     }
     build_layout(h);
@@ -263,8 +265,8 @@ static int set_state_impl(nqco_handle* h, const double* r, const double* v, cons
     const int method = S.cfg.method;
     const int64_t T = (int64_t)h->traj.size();
     const bool density = (method == NQCB200_METHOD_FSSH || method == NQCB200_METHOD_EHRENFEST);
-    const size_t nsig = method == NQCB200_METHOD_IESH ? (size_t)n * ne : (size_t)n * n;
-    if ((density || method == NQCB200_METHOD_IESH) && !sre) { h->err = "sigma required"; return NQCB200_ERR_INVALID; }
+    const size_t nsig = iesh_family(method) ? (size_t)n * ne : (size_t)n * n;
+    if ((density || iesh_family(method)) && !sre) { h->err = "sigma required"; return NQCB200_ERR_INVALID; }
     if (method == NQCB200_METHOD_IESH && !state) { h->err = "state required"; return NQCB200_ERR_INVALID; }
     int rc = NQCB200_OK;
 #pragma omp parallel for schedule(static)
@@ -273,7 +275,7 @@ static int set_state_impl(nqco_handle* h, const double* r, const double* v, cons
         tr.r.assign(r + (size_t)t * B * D, r + (size_t)(t + 1) * B * D);
         tr.v.assign(v + (size_t)t * B * D, v + (size_t)(t + 1) * B * D);
         tr.sigma.assign(nsig, cd(0.0));
-        if (density || method == NQCB200_METHOD_IESH)
+        if (density || iesh_family(method))
             for (size_t i = 0; i < nsig; ++i) tr.sigma[i] = cd(sre[t * nsig + i], sim ? sim[t * nsig + i] : 0.0);
         tr.occ.clear();
         if (method == NQCB200_METHOD_IESH) for (int e = 0; e < ne; ++e) tr.occ.push_back(state[t * ne + e] - 1);
@@ -333,7 +335,7 @@ int nqco_sample_state(nqco_handle* h, const nqcb200_dist* r_dist, const nqcb200_
     const Setup& S = h->S;
     const int n = S.n, D = S.D, B = S.B;
     const int method = S.cfg.method;
-    if (method == NQCB200_METHOD_IESH) { h->err = "device-side sampling is not available for AdiabaticIESH"; return NQCB200_ERR_UNSUPPORTED; }
+    if (iesh_family(method)) { h->err = "device-side sampling is not available for AdiabaticIESH / EhrenfestNA"; return NQCB200_ERR_UNSUPPORTED; }
     const bool density = (method == NQCB200_METHOD_FSSH || method == NQCB200_METHOD_EHRENFEST);
     if (density && !rho_re) return NQCB200_ERR_INVALID;
     const int64_t T = (int64_t)h->traj.size();

@@ -115,6 +115,14 @@ inline void acceleration(const Setup& S, Trajectory& T, const vec& r, const cvec
                     f = -g0[I];
                     for (int kk : T.occ) f -= a[kk + (size_t)n * kk];
                 } break;
+                case NQCB200_METHOD_EHRENFEST_NA: {   // ehrenfest_na.jl:72-90 (psi = sigma_prev of the wavefunction integrator)
+                    if (I == 0) S.model.dU0(&r[(size_t)D * b], g0.data());
+                    f = -g0[I];
+                    for (int e = 0; e < S.ne; ++e)
+                        for (int m = 0; m < n; ++m)
+                            for (int nn = 0; nn < n; ++nn)
+                                f -= a[nn + (size_t)n * m] * (T.sigma[nn + (size_t)n * e] * std::conj(T.sigma[m + (size_t)n * e])).real();
+                } break;
                 case NQCB200_METHOD_CLASSICAL: f = -c.dV[I]; break;
                 default: throw std::runtime_error("acceleration: method");
             }
@@ -612,6 +620,7 @@ inline void step_iesh(const Setup& S, Trajectory& T, double xi) {  // verlet_wit
     acceleration(S, T, T.r, none);
     for (int i = 0; i < D; ++i) T.v[i] = std::fma(dt / 2, T.k[i], vtmp[i]);
     iesh_propagate_wavefunction(S, T);   // uses (vfinal, rfinal): Q5
+    if (S.cfg.method == NQCB200_METHOD_EHRENFEST_NA) return;   // no callback (ehrenfest_na.jl has none)
     iesh_hop(S, T, xi);
     if (S.cfg.edc_C > 0.0) iesh_edc(S, T);
 }
@@ -622,7 +631,8 @@ inline void step(const Setup& S, Trajectory& T, double xi) {
         case NQCB200_METHOD_EHRENFEST: step_density_method(S, T, xi); break;
         case NQCB200_METHOD_CLASSICAL: step_classical(S, T); break;
         case NQCB200_METHOD_NRPMD: step_nrpmd(S, T); break;
-        case NQCB200_METHOD_IESH: step_iesh(S, T, xi); break;
+        case NQCB200_METHOD_IESH:
+        case NQCB200_METHOD_EHRENFEST_NA: step_iesh(S, T, xi); break;
         default: throw std::runtime_error("step: method");
     }
     T.step++;
@@ -657,6 +667,10 @@ inline void adiabatic_population(const Setup& S, const Trajectory& T, double* po
         case NQCB200_METHOD_FSSH: pop[T.state] = 1.0; break;                                   // fssh.jl:144-148
         case NQCB200_METHOD_EHRENFEST: for (int i = 0; i < n; ++i) pop[i] = T.sigma[i + (size_t)n * i].real(); break;
         case NQCB200_METHOD_IESH: for (int kk : T.occ) pop[kk] = 1.0; break;                   // iesh.jl:371-375
+        case NQCB200_METHOD_EHRENFEST_NA:                                                      // ehrenfest_na.jl:116-125
+            for (int e = 0; e < S.ne; ++e)
+                for (int m = 0; m < n; ++m) pop[m] += std::norm(T.sigma[m + (size_t)n * e]);
+            break;
         default: break;
     }
 }
@@ -726,6 +740,11 @@ inline double potential_energy(const Setup& S, const Trajectory& T) {
         case NQCB200_METHOD_IESH:  // iesh.jl:380-388
             pot = S.model.U0(&T.r[0]);
             for (int kk : T.occ) pot += T.bead[0].w[kk];
+            break;
+        case NQCB200_METHOD_EHRENFEST_NA:  // ehrenfest_na.jl:103-114
+            pot = S.model.U0(&T.r[0]);
+            for (int e = 0; e < S.ne; ++e)
+                for (int i = 0; i < n; ++i) pot += T.bead[0].w[i] * std::norm(T.sigma[i + (size_t)n * e]);
             break;
         case NQCB200_METHOD_CLASSICAL:  // DynamicsUtils.jl:141-151
             for (int b = 0; b < S.B; ++b) pot += T.bead[b].V[0];

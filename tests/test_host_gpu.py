@@ -103,3 +103,55 @@ def test_run_dynamics_iesh_ground_state_and_fermi_dirac():
     assert mean["OutputAdiabaticPopulation"].shape == (5, n)
     assert np.allclose(mean["OutputAdiabaticPopulation"].sum(axis=1), ne)
     assert np.allclose(mean["OutputDiabaticPopulation"].sum(axis=1), ne, atol=1e-9)
+
+
+def test_derived_outputs():
+    """Outputs assembled on the host from the device streams (DynamicsOutputs.jl:101-141,192-227,387-397)."""
+    sim, dist = _tully()
+    out = (nq.OutputKineticEnergy, nq.OutputFinalKineticEnergy, nq.OutputPosition, nq.OutputFirstPosition,
+           nq.OutputFinalPosition, nq.OutputVelocity, nq.OutputFinalVelocity, nq.OutputDiabaticPopulation,
+           nq.OutputTotalDiabaticPopulation, nq.OutputTotalAdiabaticPopulation, nq.OutputFinalTime,
+           nq.OutputDynamicsVariables, nq.OutputInitial, nq.OutputFinal, nq.OutputDiscreteState,
+           nq.OutputQuantumSubsystem)
+    T = 6
+    res = nq.run_dynamics(sim, (0.0, 200.0), dist, output=out, trajectories=T, dt=1.0, saveat=20.0, seed=3)
+    for tr in res:
+        assert tr["OutputFinalKineticEnergy"] == tr["OutputKineticEnergy"][-1]
+        assert np.array_equal(tr["OutputFirstPosition"], tr["OutputPosition"][0])
+        assert np.array_equal(tr["OutputFinalPosition"], tr["OutputPosition"][-1])
+        assert np.array_equal(tr["OutputFinalVelocity"], tr["OutputVelocity"][-1])
+        assert np.allclose(tr["OutputTotalDiabaticPopulation"], 1.0) and np.allclose(tr["OutputTotalAdiabaticPopulation"], 1.0)
+        assert tr["OutputFinalTime"] == 200.0
+        frames = tr["OutputDynamicsVariables"]
+        assert len(frames) == 11 and set(frames[0]) == {"v", "r", "σreal", "σimag", "state"}
+        assert np.array_equal(frames[3]["r"], tr["OutputPosition"][3]) and frames[3]["σreal"].shape == (2, 2)
+        assert np.array_equal(frames[-1]["state"], np.atleast_1d(tr["OutputDiscreteState"][-1]))
+        assert np.array_equal(tr["OutputInitial"]["r"], frames[0]["r"]) and np.array_equal(tr["OutputFinal"]["v"], frames[-1]["v"])
+        assert np.allclose(frames[5]["σreal"] + 1j * frames[5]["σimag"], tr["OutputQuantumSubsystem"][5])
+    # ring polymer: spring energy and centroid kinetic energy
+    kT = 9.5e-4
+    rp = nq.RingPolymerSimulation[nq.Classical](nq.Atoms(1837.0), nq.Harmonic(m=1837.0, ω=0.005, r0=0.0), 8, temperature=kT)
+    d2 = nq.DynamicalDistribution(nq.Normal(0.0, 1e-3), nq.Normal(0.0, 0.2), rp.size)
+    o2 = (nq.OutputTotalEnergy, nq.OutputKineticEnergy, nq.OutputPotentialEnergy, nq.OutputSpringEnergy,
+          nq.OutputCentroidKineticEnergy, nq.OutputCentroidVelocity)
+    rr = nq.run_dynamics(rp, (0.0, 100.0), d2, output=o2, trajectories=4, dt=2.5, saveat=10.0, seed=5)
+    for tr in rr:
+        assert np.all(tr["OutputSpringEnergy"] > 0)
+        assert np.allclose(tr["OutputSpringEnergy"] + tr["OutputKineticEnergy"] + tr["OutputPotentialEnergy"], tr["OutputTotalEnergy"])
+        vc = np.asarray(tr["OutputCentroidVelocity"]).reshape(len(tr["OutputCentroidKineticEnergy"]), -1)
+        assert np.allclose(tr["OutputCentroidKineticEnergy"], 0.5 * 1837.0 * vc[:, 0] ** 2)
+
+
+def test_ehrenfest_na_through_run_dynamics():
+    """test/Dynamics/ehrenfest_na.jl:24-52 through the host API: energy conservation, conserved electron count."""
+    G = 6.4e-3
+    model = nq.AndersonHolstein(nq.MiaoSubotnik(Γ=G), nq.TrapezoidalRule(30, -3 * G, 3 * G))
+    sim = nq.Simulation[nq.EhrenfestNA](nq.Atoms(2000), model)
+    dist = nq.DynamicalDistribution(0.0, 21.0, sim.size)
+    out = (nq.OutputTotalEnergy, nq.OutputKineticEnergy, nq.OutputPotentialEnergy, nq.OutputPosition,
+           nq.OutputAdiabaticPopulation, nq.OutputQuantumSubsystem)
+    tr = nq.run_dynamics(sim, (0.0, 2000.0), dist, output=out, trajectories=1, dt=10.0, saveat=10.0)
+    assert np.var(tr["OutputTotalEnergy"]) < 1e-6
+    assert np.allclose(tr["OutputAdiabaticPopulation"].sum(axis=1), model.nelectrons)
+    assert tr["OutputQuantumSubsystem"].shape == (201, model.nstates, model.nelectrons)
+    assert abs(tr["OutputPosition"][-1].item() - 21.0) > 1e-3

@@ -469,3 +469,25 @@ def test_iesh_ground_state_overlap_and_pruning():
     assert n1 == 0 and n0 == nsteps * T and c1["hops"] == c0["hops"] == 0
     assert np.array_equal(s1["sigma"], s0["sigma"]) and np.array_equal(s1["r"], s0["r"])
     assert np.allclose(np.abs(np.linalg.det(s1["sigma"][:, :ne, :])), 1.0, atol=1e-6)     # still close to adiabatic
+
+
+def test_ehrenfest_na_conserves_energy_and_electrons():
+    """test/Dynamics/ehrenfest_na.jl:24-52: Simulation{EhrenfestNA} on AndersonHolstein(MiaoSubotnik, TrapezoidalRule(30)),
+    r = 21, v = 0, ground-state orbitals, dt = 10, tspan (0, 2000): var(total energy) < 1e-6; the electron count
+    sum_m adiabatic_population[m] = ne is conserved (unitary propagation)."""
+    from helpers import A
+    M, T, nsteps = 30, 2, 200
+    model, h = _iesh_oracle(M, T, 10.0, nsteps, method=A.METHOD_EHRENFEST_NA,
+                            observables=(1 << A.OBS_TOTAL_ENERGY) | (1 << A.OBS_KINETIC) | (1 << A.OBS_POTENTIAL) |
+                                        (1 << A.OBS_ADIABATIC_POP) | (1 << A.OBS_POSITION))
+    n, ne = model.nstates, model.nelectrons
+    psi = np.zeros((T, ne, n)); psi[:, np.arange(ne), np.arange(ne)] = 1.0
+    h.set_state(np.array([21.0, 18.0]), np.array([0.0, -1e-4]), psi, None, None)
+    h.run(nsteps)
+    E = h.observable_per_trajectory(A.OBS_TOTAL_ENERGY)[:, :, 0]
+    assert np.all(np.var(E, axis=1) < 1e-6)
+    assert np.max(np.abs(E - E[:, :1])) < 2e-5 * np.max(np.abs(E))
+    adi = h.observable_per_trajectory(A.OBS_ADIABATIC_POP)
+    assert np.allclose(adi.sum(axis=2), ne, atol=1e-9) and np.all(adi > -1e-12) and np.all(adi < 1 + 1e-9)
+    x = h.observable_per_trajectory(A.OBS_POSITION)[:, :, 0]
+    assert np.max(np.abs(x[0] - 21.0)) > 1e-3            # the trajectory does move on the mean-field surface

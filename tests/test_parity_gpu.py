@@ -468,3 +468,32 @@ def test_iesh_edc_and_philox_sharding():
             h.close()
         outs.append((np.concatenate([a[0]["sigma"] for a in acc]), np.concatenate([a[1] for a in acc])))
     assert np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][0], outs[1][0])
+
+
+NA_OBS = ((1 << A.OBS_ADIABATIC_POP) | (1 << A.OBS_KINETIC) | (1 << A.OBS_POTENTIAL) | (1 << A.OBS_TOTAL_ENERGY) |
+          (1 << A.OBS_POSITION) | (1 << A.OBS_VELOCITY) | (1 << A.OBS_SIGMA))
+
+
+@pytest.mark.parametrize("M,dt,nsteps", [(30, 10.0, 24), (100, 1.0, 8)])
+def test_ehrenfest_na_parity(M, dt, nsteps):
+    """Simulation{EhrenfestNA} (ehrenfest_na.jl) on the IESH kernel family: mean-field force from psi, no hops."""
+    T = 5
+    rng = np.random.default_rng(33)
+    model, (e, o) = _iesh_pair(M, T, dt, nsteps + 1, method=A.METHOD_EHRENFEST_NA, observables=NA_OBS)
+    n, ne = model.nstates, model.nelectrons
+    r = 21.0 * rng.random(T)
+    v = rng.standard_normal(T) * np.sqrt(9.5e-4 / 2000.0) * 3
+    re, im, _ = _iesh_random_state(rng, T, n, ne)
+    for h in (e, o):
+        h.set_state(r, v, re, im, None)
+    for chunk in range(nsteps // 4):
+        e.run(4); o.run(4)
+        se, so = e.get_state(), o.get_state()
+        assert rel_err(se["r"], so["r"]) < STEP_TOL and rel_err(se["v"], so["v"]) < STEP_TOL
+        assert np.max(np.abs(se["sigma"] - so["sigma"])) < STEP_TOL
+        de, do = e.diagnostics(), o.diagnostics()
+        assert rel_err(de["accel"], do["accel"]) < STEP_TOL and rel_err(de["eig"], do["eig"]) < STEP_TOL
+    _compare_observables(e, o, NA_OBS, 1e-9, T)
+    adi = e.observable_per_trajectory(A.OBS_ADIABATIC_POP)
+    assert np.allclose(adi.sum(axis=2), ne, atol=1e-9)
+    assert e.counters()["hops"] == 0
