@@ -57,6 +57,8 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target duration of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--stream", action="store_true",
+                    help="also measure the per-trajectory output-streaming path (SortByTrajectory / FileReduction)")
     return ap.parse_args()
 
 
@@ -369,6 +371,44 @@ def main():
                                         "path": "nqcb200_sample_state -> nqcb200_run -> nqcb200_get_observable_sum (max over ranks not taken)"}
         eng2.close()
 
+    # ---- output-streaming path: per-trajectory observables written at every save point, transposed to the
+    # reference's trajectory-major layout at HBM speed and copied to pinned host memory ---------------------
+    stream = None
+    if args.stream and rank == 0:
+        import torch as _t
+        obs_ids = [o for o in range(A.OBS_COUNT) if (wl.observables >> o) & 1]
+        probe = Engine(*A.make_config(**wl.config_kwargs(1, device=local_rank)))
+        widths = {o: probe.observable_width(o) for o in obs_ids}
+        probe.close()
+        per_traj_bytes = 8 * wl.nsave * sum(widths.values())
+        Ts = int(max(1024, min(T, (6 << 30) // max(1, per_traj_bytes))))        # <= 6 GiB of output
+        kw3 = wl.config_kwargs(Ts, seed=11, device=local_rank, per_trajectory=1)
+        es = Engine(*A.make_config(**kw3))
+        ics = {k: v[:Ts] for k, v in ic.items()} if Ts <= T else wl.sample(rng, Ts)
+        wl.upload(es, ics, rho[:Ts] if rho is not None else None)
+        es.run(wl.nsteps)
+        ms_stream, _ = es.last_run_timing()
+        tr_ms = cp_ms = 0.0
+        nbytes = 0
+        for o in obs_ids:
+            buf = _t.empty((Ts, wl.nsave, widths[o]), dtype=_t.float64).pin_memory().numpy()
+            es.observable_per_trajectory(o, out=buf)
+            tm = es.last_download_timing()
+            tr_ms += tm["transpose_ms"]; cp_ms += tm["copy_ms"]; nbytes += tm["bytes"]
+        es.close()
+        hbm_peak = None
+        try:
+            hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+        except Exception:
+            pass
+        tr_gbs = 2.0 * nbytes / (tr_ms * 1e-3) / 1e9 if tr_ms > 0 else None      # read + write
+        stream = {"trajectories": Ts, "output_bytes": nbytes,
+                  "step_kernel_traj_steps_per_s": float(Ts) * wl.nsteps / (ms_stream * 1e-3),
+                  "transpose": {"ms": tr_ms, "GB/s": tr_gbs, "hbm_peak_GB/s": hbm_peak,
+                                "frac": (tr_gbs / hbm_peak) if (tr_gbs and hbm_peak) else None,
+                                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if hbm_peak else "unavailable"},
+                  "d2h": {"ms": cp_ms, "GB/s": nbytes / (cp_ms * 1e-3) / 1e9 if cp_ms > 0 else None}}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         _, cpu, _, _ = run_cpu_oracle(wl, args.cpu_seconds)
@@ -403,7 +443,7 @@ def main():
                                         "MEASURED_PEAKS.json has no FP64 entry",
                          "note": "algorithmic = the reference's dense complex formulation (SURVEY.md 8d); the kernel "
                                  "executes fewer flops (Hermitian/antisymmetric structure), see DESIGN.md" + flops_note},
-            "cpu_baseline": cpu,
+            "cpu_baseline": cpu, "stream": stream,
             "counters": counters, "kernel_ms_total": kernel_ms, "wall_s_timed_region": wall,
             "observable_checksum": obs_check,
         }

@@ -325,6 +325,9 @@ int nqcb200_get_iesh_stats(nqcb200_handle* h, int64_t* hop_searches, int64_t* de
  * spent in step kernels by the last nqcb200_run, with the number of kernel launches it made.   */
 int nqcb200_get_progress(nqcb200_handle* h, int64_t* nsave_done, int64_t* step_count);
 int nqcb200_get_last_run_timing(nqcb200_handle* h, double* kernel_ms, int64_t* launches);
+/* The last per-trajectory download (get_state / get_observable_per_trajectory / ...): device time of the
+ * SoA -> trajectory-major transposition kernel (HBM-bound) and of the device-to-host copy, and the bytes moved. */
+int nqcb200_get_last_download_timing(nqcb200_handle* h, double* transpose_ms, double* copy_ms, int64_t* bytes);
 /* Every kernel this handle has launched since nqcb200_create (uploads, sampling, init, step, fold, ...). */
 int nqcb200_get_launch_count(nqcb200_handle* h, int64_t* launches_total);
 

@@ -114,6 +114,7 @@ def bind(lib: C.CDLL, prefix: str) -> None:
     f("get_progress", [H, _lp, _lp])
     f("get_last_run_timing", [H, _dp, _lp], required=False)
     f("get_launch_count", [H, _lp], required=False)
+    f("get_last_download_timing", [H, _dp, _dp, _lp], required=False)
     f("measure_fp64_peak", [C.c_int, _dp], required=False)
 
 
@@ -121,7 +122,7 @@ HEADER_SYMBOLS = [
     "version", "device_count", "create", "destroy", "last_error", "observable_width", "set_state",
     "set_state_diabatic", "set_mapping", "set_gauge_reference", "set_draws", "run", "run_from_host", "sample_state", "get_state", "get_mapping",
     "get_observable_sum", "observable_sum_device", "observable_offset", "get_observable_per_trajectory",
-    "get_diagnostics", "get_counters", "get_iesh_stats", "get_progress", "get_last_run_timing", "get_launch_count", "measure_fp64_peak",
+    "get_diagnostics", "get_counters", "get_iesh_stats", "get_progress", "get_last_run_timing", "get_launch_count", "get_last_download_timing", "measure_fp64_peak",
 ]
 
 _ENGINE_LIB: Optional[C.CDLL] = None
@@ -296,9 +297,13 @@ class CHandle:
         self._call("get_observable_sum", C.c_int(obs_id), _ptr(out), C.c_int64(out.size))
         return out
 
-    def observable_per_trajectory(self, obs_id: int) -> np.ndarray:
+    def observable_per_trajectory(self, obs_id: int, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """(ntraj, nsave, width); pass a pinned ``out`` of that shape to receive the copy at PCIe speed."""
         w = self.observable_width(obs_id)
-        out = np.empty((self.T, self.cfg.nsave, w))
+        if out is None:
+            out = np.empty((self.T, self.cfg.nsave, w))
+        elif out.shape != (self.T, self.cfg.nsave, w) or out.dtype != np.float64 or not out.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous float64 array of shape (ntraj, nsave, width)")
         self._call("get_observable_per_trajectory", C.c_int(obs_id), _ptr(out), C.c_int64(out.size))
         return out
 
@@ -326,6 +331,11 @@ class CHandle:
         a, b = C.c_int64(), C.c_int64()
         self._call("get_progress", C.byref(a), C.byref(b))
         return int(a.value), int(b.value)
+
+    def last_download_timing(self):
+        a, b, n = C.c_double(), C.c_double(), C.c_int64()
+        self._call("get_last_download_timing", C.byref(a), C.byref(b), C.byref(n))
+        return {"transpose_ms": a.value, "copy_ms": b.value, "bytes": int(n.value)}
 
     def launch_count(self) -> int:
         n = C.c_int64()

@@ -181,7 +181,9 @@ struct nqcb200_handle {
     KParams kp;
     KernelSet ks;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+    double last_transpose_ms = 0.0, last_copy_ms = 0.0;
+    int64_t last_download_bytes = 0;
     std::vector<void*> allocs;
     double* staging = nullptr;      // trajectory-major staging for uploads / downloads
     nqcb200_dist* d_dist = nullptr;   // sample_state: [2][B*D] component specifications
@@ -241,11 +243,19 @@ int download_field(nqcb200_handle* h, const double* src, double* host, int C) {
     const int64_t T = h->cfg.ntraj;
     if (T == 0 || C == 0) return NQCB200_OK;
     dim3 grid((unsigned)((T + 31) / 32), (unsigned)((C + 31) / 32)), block(32, 8);
+    // timed separately: the transposition runs at HBM speed, the copy at PCIe speed (nqcb200_get_last_download_timing)
+    NQ_CUDA(h, cudaEventRecord(h->ev0, h->stream));
     soa_to_aos<double, double><<<grid, block, 0, h->stream>>>(src, h->staging, T, C, 0.0);
     ++h->launches_total;
     NQ_CUDA(h, cudaGetLastError());
+    NQ_CUDA(h, cudaEventRecord(h->ev1, h->stream));
     NQ_CUDA(h, cudaMemcpyAsync(host, h->staging, sizeof(double) * T * C, cudaMemcpyDeviceToHost, h->stream));
+    NQ_CUDA(h, cudaEventRecord(h->ev2, h->stream));
     NQ_CUDA(h, cudaStreamSynchronize(h->stream));
+    float a = 0.f, b = 0.f;
+    NQ_CUDA(h, cudaEventElapsedTime(&a, h->ev0, h->ev1));
+    NQ_CUDA(h, cudaEventElapsedTime(&b, h->ev1, h->ev2));
+    h->last_transpose_ms = a; h->last_copy_ms = b; h->last_download_bytes = (int64_t)sizeof(double) * T * C;
     return NQCB200_OK;
 }
 
@@ -383,6 +393,7 @@ int nqcb200_destroy(nqcb200_handle* h) {
     for (void* p : h->allocs) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->ev2) cudaEventDestroy(h->ev2);
     if (h->stream) cudaStreamDestroy(h->stream);
     cudaGetLastError();
     delete h;
@@ -419,6 +430,7 @@ int nqcb200_create(const nqcb200_config* cfg, nqcb200_handle** out) {
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaEventCreate(&h->ev0);
         if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
+        if (e == cudaSuccess) e = cudaEventCreate(&h->ev2);
         if (e != cudaSuccess) { h->err = cudaGetErrorString(e); cudaGetLastError(); return fail(NQCB200_ERR_CUDA); }
     }
     const nqcb200_config& c = h->cfg;
@@ -954,6 +966,14 @@ int nqcb200_measure_fp64_peak(int device, double* tflops) {
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
     if (cudaGetLastError() != cudaSuccess) return NQCB200_ERR_CUDA;
     *tflops = best;
+    return NQCB200_OK;
+}
+
+int nqcb200_get_last_download_timing(nqcb200_handle* h, double* transpose_ms, double* copy_ms, int64_t* bytes) {
+    if (!h) return NQCB200_ERR_INVALID;
+    if (transpose_ms) *transpose_ms = h->last_transpose_ms;
+    if (copy_ms) *copy_ms = h->last_copy_ms;
+    if (bytes) *bytes = h->last_download_bytes;
     return NQCB200_OK;
 }
 
