@@ -13,6 +13,8 @@
 // (n = 2: 4 state variables x 6 stages).  This executes ~8x fewer flops than the reference's dense
 // complex commutator (16 n^3 + 10 n^2 per RHS) for the same result up to rounding.
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace nq {
@@ -142,51 +144,94 @@ NQ_HD void propagate_density(const ElecParams<N>& cur, double tcur, const ElecPa
 //     dx00 = -2 g x01 = -dx11 ,   dx01 = dE y01 + g (x00 - x11) ,   dy01 = -dE x01 ,
 // 10 FP64 instructions per RHS instead of the generic commutator's ~40, and the x11 stage sums are the negated
 // x00 ones (bit-identical to carrying them separately).  Same Tsit5 staging as the generic version above.
-template <>
-NQ_HD void propagate_density<2>(const ElecParams<2>& cur, double tcur, const ElecParams<2>& nxt, double tnext,
-                                double t, double dt, Herm<2>& s) {
+// `between(sub, std::integral_constant<int, stage>)` is called once per Tsit5 stage (6 per sub-step, 30 per nuclear
+// step) right after that stage's RHS has been issued: independent work placed there (the SpinBoson kernel runs the
+// next step's mode sweep in these slots) fills the fixed-latency bubbles of the serial stage chain.
+template <class Between>
+NQ_HD void propagate_density_2state(const ElecParams<2>& cur, double tcur, const ElecParams<2>& nxt, double tnext,
+                                    double t, double dt, Herm<2>& s, Between&& between) {
+    // Carried variables: z = x00 - x11 (the trace x00 + x11 is a constant of the motion), x01, y01:
+    //     dz = -4 g x01 ,   dx01 = dE y01 + g z ,   dy01 = -dE x01 .
+    // FP64 latency, not throughput, bounds the kernels that call this (one serial chain per thread, few warps per
+    // scheduler), so every stage is written with the NEWEST slope last: the partial sum over the older slopes is off
+    // the critical path and one FMA turns a fresh slope into the next stage's argument
+    // (3 dependent operations from d z to d x01 and 2 back, instead of 5 and 3).
     using namespace tsit5;
     const double h = dt / 5.0;
     const double inv_span = 1.0 / (tnext - tcur);
     const bool flat = !(fabs(inv_span) <= 1.0e300);   // zero span: the reference's isnan(loc) -> 0 branch
     const double dEc = cur.E[0] - cur.E[1], dEd = (nxt.E[0] - nxt.E[1]) - dEc;
     const double gc = cur.g[0], gd = nxt.g[0] - gc;
-    struct K { double a, b, c; };   // d x00 (= -d x11), d x01, d y01
-    double x00 = s.x[0], x01 = s.x[1], x11 = s.x[2], y01 = s.y[0];
-    auto rhs = [&](double tau, double u00, double u01, double u11, double w01, K& k) {
+    struct K { double a, b, c; };   // d z, d x01, d y01
+    const double tr = s.x[0] + s.x[2];
+    double z = s.x[0] - s.x[2], x01 = s.x[1], y01 = s.y[0];
+    auto rhs = [&](double tau, double uz, double u01, double w01, K& k) {
         const double l = flat ? 0.0 : (tau - tcur) * inv_span;
         const double dE = fma(dEd, l, dEc), g = fma(gd, l, gc);
-        k.a = -((g + g) * u01);
-        k.b = fma(dE, w01, g * (u00 - u11));
+        k.a = -((4.0 * g) * u01);
+        k.b = fma(dE, w01, g * uz);
         k.c = -(dE * u01);
     };
     K k1, k2, k3, k4, k5, k6;
     double ts = t;
-    rhs(ts, x00, x01, x11, y01, k1);
+    rhs(ts, z, x01, y01, k1);
 #pragma unroll 1
     for (int sub = 0; sub < 5; ++sub) {
         const double hh = (sub == 4) ? (t + dt) - ts : h;   // tstop snapping of the last sub-step
-#define NQ_STAGE2(SA, SB, SC, TAU, KOUT)                                                                       \
-        { const double sa_ = (SA), sb_ = (SB), sc_ = (SC);                                                      \
-          rhs((TAU), fma(hh, sa_, x00), fma(hh, sb_, x01), fma(-hh, sa_, x11), fma(hh, sc_, y01), KOUT); }
-        NQ_STAGE2(NQ_TS(a21) * k1.a, NQ_TS(a21) * k1.b, NQ_TS(a21) * k1.c, ts + NQ_TS(c1) * hh, k2)
-        NQ_STAGE2(NQ_TS(a31) * k1.a + NQ_TS(a32) * k2.a, NQ_TS(a31) * k1.b + NQ_TS(a32) * k2.b, NQ_TS(a31) * k1.c + NQ_TS(a32) * k2.c, ts + NQ_TS(c2) * hh, k3)
-        NQ_STAGE2(NQ_TS(a41) * k1.a + NQ_TS(a42) * k2.a + NQ_TS(a43) * k3.a, NQ_TS(a41) * k1.b + NQ_TS(a42) * k2.b + NQ_TS(a43) * k3.b,
-                  NQ_TS(a41) * k1.c + NQ_TS(a42) * k2.c + NQ_TS(a43) * k3.c, ts + NQ_TS(c3) * hh, k4)
-        NQ_STAGE2(NQ_TS(a51) * k1.a + NQ_TS(a52) * k2.a + NQ_TS(a53) * k3.a + NQ_TS(a54) * k4.a, NQ_TS(a51) * k1.b + NQ_TS(a52) * k2.b + NQ_TS(a53) * k3.b + NQ_TS(a54) * k4.b,
-                  NQ_TS(a51) * k1.c + NQ_TS(a52) * k2.c + NQ_TS(a53) * k3.c + NQ_TS(a54) * k4.c, ts + NQ_TS(c4) * hh, k5)
-        NQ_STAGE2(NQ_TS(a61) * k1.a + NQ_TS(a62) * k2.a + NQ_TS(a63) * k3.a + NQ_TS(a64) * k4.a + NQ_TS(a65) * k5.a,
-                  NQ_TS(a61) * k1.b + NQ_TS(a62) * k2.b + NQ_TS(a63) * k3.b + NQ_TS(a64) * k4.b + NQ_TS(a65) * k5.b,
-                  NQ_TS(a61) * k1.c + NQ_TS(a62) * k2.c + NQ_TS(a63) * k3.c + NQ_TS(a64) * k4.c + NQ_TS(a65) * k5.c, ts + hh, k6)
-#undef NQ_STAGE2
-        const double sa = NQ_TS(a71) * k1.a + NQ_TS(a72) * k2.a + NQ_TS(a73) * k3.a + NQ_TS(a74) * k4.a + NQ_TS(a75) * k5.a + NQ_TS(a76) * k6.a;
-        const double sb = NQ_TS(a71) * k1.b + NQ_TS(a72) * k2.b + NQ_TS(a73) * k3.b + NQ_TS(a74) * k4.b + NQ_TS(a75) * k5.b + NQ_TS(a76) * k6.b;
-        const double sc = NQ_TS(a71) * k1.c + NQ_TS(a72) * k2.c + NQ_TS(a73) * k3.c + NQ_TS(a74) * k4.c + NQ_TS(a75) * k5.c + NQ_TS(a76) * k6.c;
-        x00 = fma(hh, sa, x00); x11 = fma(-hh, sa, x11); x01 = fma(hh, sb, x01); y01 = fma(hh, sc, y01);
+        // stage i+1 argument = [x + hh sum_{j<i} a_{i+1,j} k_j] + (hh a_{i+1,i}) k_i
+#define NQ_ARG(P, C, KN) fma((C), (KN), (P))
+        {
+            const double c21 = hh * NQ_TS(a21);
+            rhs(ts + NQ_TS(c1) * hh, NQ_ARG(z, c21, k1.a), NQ_ARG(x01, c21, k1.b), NQ_ARG(y01, c21, k1.c), k2);
+        }
+        between(sub, std::integral_constant<int, 0>{});
+        {
+            const double c31 = hh * NQ_TS(a31), c32 = hh * NQ_TS(a32);
+            rhs(ts + NQ_TS(c2) * hh, NQ_ARG(fma(c31, k1.a, z), c32, k2.a), NQ_ARG(fma(c31, k1.b, x01), c32, k2.b),
+                NQ_ARG(fma(c31, k1.c, y01), c32, k2.c), k3);
+        }
+        between(sub, std::integral_constant<int, 1>{});
+        {
+            const double c41 = hh * NQ_TS(a41), c42 = hh * NQ_TS(a42), c43 = hh * NQ_TS(a43);
+            rhs(ts + NQ_TS(c3) * hh, NQ_ARG(fma(c42, k2.a, fma(c41, k1.a, z)), c43, k3.a),
+                NQ_ARG(fma(c42, k2.b, fma(c41, k1.b, x01)), c43, k3.b),
+                NQ_ARG(fma(c42, k2.c, fma(c41, k1.c, y01)), c43, k3.c), k4);
+        }
+        between(sub, std::integral_constant<int, 2>{});
+        {
+            const double c51 = hh * NQ_TS(a51), c52 = hh * NQ_TS(a52), c53 = hh * NQ_TS(a53), c54 = hh * NQ_TS(a54);
+            rhs(ts + NQ_TS(c4) * hh, NQ_ARG(fma(c53, k3.a, fma(c52, k2.a, fma(c51, k1.a, z))), c54, k4.a),
+                NQ_ARG(fma(c53, k3.b, fma(c52, k2.b, fma(c51, k1.b, x01))), c54, k4.b),
+                NQ_ARG(fma(c53, k3.c, fma(c52, k2.c, fma(c51, k1.c, y01))), c54, k4.c), k5);
+        }
+        between(sub, std::integral_constant<int, 3>{});
+        {
+            const double c61 = hh * NQ_TS(a61), c62 = hh * NQ_TS(a62), c63 = hh * NQ_TS(a63), c64 = hh * NQ_TS(a64),
+                         c65 = hh * NQ_TS(a65);
+            rhs(ts + hh, NQ_ARG(fma(c64, k4.a, fma(c63, k3.a, fma(c62, k2.a, fma(c61, k1.a, z)))), c65, k5.a),
+                NQ_ARG(fma(c64, k4.b, fma(c63, k3.b, fma(c62, k2.b, fma(c61, k1.b, x01)))), c65, k5.b),
+                NQ_ARG(fma(c64, k4.c, fma(c63, k3.c, fma(c62, k2.c, fma(c61, k1.c, y01)))), c65, k5.c), k6);
+        }
+        between(sub, std::integral_constant<int, 4>{});
+        {
+            const double c71 = hh * NQ_TS(a71), c72 = hh * NQ_TS(a72), c73 = hh * NQ_TS(a73), c74 = hh * NQ_TS(a74),
+                         c75 = hh * NQ_TS(a75), c76 = hh * NQ_TS(a76);
+            z = NQ_ARG(fma(c75, k5.a, fma(c74, k4.a, fma(c73, k3.a, fma(c72, k2.a, fma(c71, k1.a, z))))), c76, k6.a);
+            x01 = NQ_ARG(fma(c75, k5.b, fma(c74, k4.b, fma(c73, k3.b, fma(c72, k2.b, fma(c71, k1.b, x01))))), c76, k6.b);
+            y01 = NQ_ARG(fma(c75, k5.c, fma(c74, k4.c, fma(c73, k3.c, fma(c72, k2.c, fma(c71, k1.c, y01))))), c76, k6.c);
+        }
+#undef NQ_ARG
         ts = (sub == 4) ? (t + dt) : ts + hh;
-        if (sub < 4) rhs(ts, x00, x01, x11, y01, k1);   // FSAL
+        if (sub < 4) rhs(ts, z, x01, y01, k1);   // FSAL
+        between(sub, std::integral_constant<int, 5>{});
     }
-    s.x[0] = x00; s.x[1] = x01; s.x[2] = x11; s.y[0] = y01;
+    s.x[0] = 0.5 * (tr + z); s.x[1] = x01; s.x[2] = 0.5 * (tr - z); s.y[0] = y01;
+}
+
+template <>
+NQ_HD void propagate_density<2>(const ElecParams<2>& cur, double tcur, const ElecParams<2>& nxt, double tnext,
+                                double t, double dt, Herm<2>& s) {
+    propagate_density_2state(cur, tcur, nxt, tnext, t, dt, s, [](int, auto) {});
 }
 
 }  // namespace nq

@@ -42,7 +42,7 @@ constexpr int kSbTraj = 128;   // trajectories per block (the bath of 128 trajec
 struct SbSmem {
     double* rs;      // [D][kSbTraj]
     double* vs;      // [D][kSbTraj]  half-kicked velocity (true velocity before the first step of a launch)
-    double2 *k1, *k2, *k3;   // [D] {w^2/m, c/m}, {c, c w^2/m}, {w^2/2, m}  (k3 only for energies / kinetic sums)
+    double2 *k1, *k2, *k3;   // [D] {dt w^2/m, c/m}, {c, c w^2/m}, {w^2/2, m}  (k3 only for energies / kinetic sums)
     NQ_D void carve(double* base, int D) {
         rs = base; vs = rs + (size_t)D * kSbTraj;
         k1 = reinterpret_cast<double2*>(vs + (size_t)D * kSbTraj); k2 = k1 + D; k3 = k2 + D;
@@ -78,6 +78,31 @@ struct SbEmitter {
         if ((threadIdx.x & 31) == 0)
             atomicAdd(&p.obs_sum[(int64_t)((blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) % kObsReplicas) * p.layout.total + off], ws);
     }
+    // Four consecutive values (k0 .. k0+3) in one transposing reduction: after two exchange rounds each quarter of
+    // the warp owns one value, three more rounds finish it -- 6 double shuffles instead of 20, one atomic per value.
+    NQ_D void emit4(int obs_id, int k0, const double (&val)[4]) {
+        const int64_t off = p.layout.offset[obs_id] + (int64_t)isave * p.layout.width[obs_id] + k0;
+        if (p.obs_traj != nullptr && active) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) p.obs_traj[(off + q) * p.ntraj + traj] = val[q];
+        }
+        const int lane = threadIdx.x & 31;
+        const double v0 = active ? val[0] : 0.0, v1 = active ? val[1] : 0.0, v2 = active ? val[2] : 0.0, v3 = active ? val[3] : 0.0;
+        const bool hi = (lane & 16) != 0;
+        double a = hi ? v2 : v0, b = hi ? v3 : v1;
+        a += __shfl_xor_sync(0xffffffffu, hi ? v0 : v2, 16);
+        b += __shfl_xor_sync(0xffffffffu, hi ? v1 : v3, 16);
+        const bool mid = (lane & 8) != 0;
+        double c = mid ? b : a;
+        c += __shfl_xor_sync(0xffffffffu, mid ? a : b, 8);
+        c += __shfl_xor_sync(0xffffffffu, c, 4);
+        c += __shfl_xor_sync(0xffffffffu, c, 2);
+        c += __shfl_xor_sync(0xffffffffu, c, 1);
+        if ((lane & 7) == 0) {      // lanes 0, 8, 16, 24 hold the sums of values 0, 1, 2, 3
+            const int q = lane >> 3;
+            atomicAdd(&p.obs_sum[(int64_t)((blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) % kObsReplicas) * p.layout.total + off + q], c);
+        }
+    }
 };
 
 // S = Z' sigma_z Z (symmetric 2x2): s00, s01, s11
@@ -100,6 +125,7 @@ struct SbTraj {
     ElecParams<2> cur;
     double A, B;          // force scalars carried between steps (quirk Q2)
     double gm, gd;        // pending velocity change: v_j -= c_j (gm / m_j + gd)
+    double p0d[2], p0a[2];   // initial diabatic / adiabatic populations (correlation functions), cached from pop0
 };
 
 struct SbSums { double harm, lin, cvt, cwr, msv2; };
@@ -110,18 +136,21 @@ struct SbSums { double harm, lin, cvt, cwr, msv2; };
 // PEND (warp-uniform): some trajectory of the warp has a pending hop rescaling.  The sums are over ALL modes of the
 // trajectory (pair-summed), at the new positions.  Four modes are advanced in lock step so that their dependent FMA
 // chains interleave.
-template <int LPT, int METHOD, bool DRIFT, bool HARM>
+// LIN: accumulate sum c r at the new positions (otherwise the caller advances it: sum c r += dt sum c vt, exact in real
+// arithmetic because every mode drifts by dt vt).  k1.x carries dt w^2/m, so "dacc" below is dt times the acceleration
+// and the ordinary drift sweep (both half kicks, FSSH) turns v into vt with two FMAs.
+template <int LPT, int METHOD, bool DRIFT, bool HARM, bool LIN = true>
 NQ_D void sb_sweep(const SbSmem& M, int D, int slot, int part, bool first, bool pend, double A, double B, double gm,
                    double gd, double dt, double hdt, SbSums& S) {
     constexpr int W = 4;
     double h4[W], l4[W], c4[W], w4[W], m4[W];
 #pragma unroll
     for (int q = 0; q < W; ++q) { h4[q] = 0.0; l4[q] = 0.0; c4[q] = 0.0; w4[q] = 0.0; m4[q] = 0.0; }
-    const double nA = -A, nB = -B, kick2 = first ? 0.0 : hdt;
-    const double kboth = kick2 + hdt;   // second half kick of the previous step + first half kick of this one
+    // second half kick of the previous step (not on launch entry) + first half kick of this one, in units of dt
+    const double nA = -A, nBdt = -B * dt, kfac_2 = first ? 0.0 : 0.5, kfac_both = kfac_2 + 0.5;
     auto body = [&](const int (&jj)[W], const bool (&ok)[W]) {
         double2 k1[W], k2[W], k3[W];
-        double r[W], v[W], acc[W];
+        double r[W], v[W];
 #pragma unroll
         for (int q = 0; q < W; ++q) {
             k1[q] = M.k1[jj[q]]; k2[q] = M.k2[jj[q]];
@@ -129,19 +158,25 @@ NQ_D void sb_sweep(const SbSmem& M, int D, int slot, int part, bool first, bool 
             r[q] = M.rs[(size_t)jj[q] * kSbTraj + slot];
             v[q] = M.vs[(size_t)jj[q] * kSbTraj + slot];
         }
-#pragma unroll
-        for (int q = 0; q < W; ++q) {                                                  // -(w^2 r A + c B) / m
-            if (METHOD == NQCB200_METHOD_FSSH) acc[q] = fma(-k1[q].x, r[q], nB * k1[q].y);   // A = 1 (fssh.jl:67-74)
-            else acc[q] = fma(nA * k1[q].x, r[q], nB * k1[q].y);
-        }
         if (pend) {
 #pragma unroll
             for (int q = 0; q < W; ++q) v[q] = fma(-gm, k1[q].y, fma(-gd, k2[q].x, v[q]));   // hop rescaling / reflection
         }
-        if (DRIFT) {
-            double vt[W], rn[W];
+        double vt[W];
+        if (DRIFT && !first && METHOD == NQCB200_METHOD_FSSH) {
+            // vt = v + dt a,  dt a = -(dt w^2/m) r - dt B (c/m)   (A = 1, fssh.jl:67-74; step_B! twice, steps.jl:3-5)
 #pragma unroll
-            for (int q = 0; q < W; ++q) vt[q] = fma(kboth, acc[q], v[q]);               // step_B! twice  steps.jl:3-5
+            for (int q = 0; q < W; ++q) vt[q] = fma(nBdt, k1[q].y, fma(-k1[q].x, r[q], v[q]));
+        } else {
+#pragma unroll
+            for (int q = 0; q < W; ++q) {
+                const double dacc = (METHOD == NQCB200_METHOD_FSSH) ? fma(-k1[q].x, r[q], nBdt * k1[q].y)
+                                                                     : fma(nA * k1[q].x, r[q], nBdt * k1[q].y);
+                vt[q] = fma(DRIFT ? kfac_both : kfac_2, dacc, v[q]);
+            }
+        }
+        if (DRIFT) {
+            double rn[W];
 #pragma unroll
             for (int q = 0; q < W; ++q) rn[q] = fma(dt, vt[q], r[q]);                   // step_A!  steps.jl:6-8
 #pragma unroll
@@ -150,7 +185,7 @@ NQ_D void sb_sweep(const SbSmem& M, int D, int slot, int part, bool first, bool 
                     M.rs[(size_t)jj[q] * kSbTraj + slot] = rn[q];
                     M.vs[(size_t)jj[q] * kSbTraj + slot] = vt[q];
                     if (HARM) h4[q] = fma(k3[q].x * rn[q], rn[q], h4[q]);
-                    l4[q] = fma(k2[q].x, rn[q], l4[q]);
+                    if (LIN) l4[q] = fma(k2[q].x, rn[q], l4[q]);
                     c4[q] = fma(k2[q].x, vt[q], c4[q]);
                     w4[q] = fma(k2[q].y, rn[q], w4[q]);
                 }
@@ -159,9 +194,8 @@ NQ_D void sb_sweep(const SbSmem& M, int D, int slot, int part, bool first, bool 
 #pragma unroll
             for (int q = 0; q < W; ++q) {
                 if (ok[q]) {
-                    v[q] = fma(kick2, acc[q], v[q]);                                    // finish the previous step's kick
-                    M.vs[(size_t)jj[q] * kSbTraj + slot] = v[q];                        // true velocity
-                    m4[q] = fma(k3[q].y * v[q], v[q], m4[q]);                           // sum m v^2
+                    M.vs[(size_t)jj[q] * kSbTraj + slot] = vt[q];                       // true velocity (previous step's kick finished)
+                    m4[q] = fma(k3[q].y * vt[q], vt[q], m4[q]);                         // sum m v^2
                 }
             }
         }
@@ -187,7 +221,7 @@ NQ_D void sb_sweep(const SbSmem& M, int D, int slot, int part, bool first, bool 
 }
 
 template <int METHOD>
-NQ_D void sb_record_save(const KParams& p, SbEmitter& em, const SbSmem& M, int slot, const SbTraj& R, const Eig<2>& e,
+NQ_D void sb_record_save(const KParams& p, SbEmitter& em, const SbSmem& M, int slot, SbTraj& R, const Eig<2>& e,
                          double msv2) {
     constexpr int N = 2;
     const uint32_t obs = p.observables;
@@ -202,6 +236,10 @@ NQ_D void sb_record_save(const KParams& p, SbEmitter& em, const SbSmem& M, int s
 #pragma unroll
         for (int i = 0; i < N; ++i) { p.pop0[(int64_t)i * T + em.traj] = dia[i]; p.pop0[(int64_t)(N + i) * T + em.traj] = adi[i]; }
     }
+    if (em.isave == 0) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) { R.p0d[i] = dia[i]; R.p0a[i] = adi[i]; }
+    }
     if (obs & (1u << NQCB200_OBS_ADIABATIC_POP)) {
 #pragma unroll
         for (int i = 0; i < N; ++i) em.emit(NQCB200_OBS_ADIABATIC_POP, i, adi[i]);
@@ -213,20 +251,16 @@ NQ_D void sb_record_save(const KParams& p, SbEmitter& em, const SbSmem& M, int s
     if (obs & (1u << NQCB200_OBS_POPCORR_DIABATIC)) {
         double p0[N];
 #pragma unroll
-        for (int i = 0; i < N; ++i) p0[i] = (em.isave == 0) ? dia[i] : p.pop0[(int64_t)i * T + em.traj];
-#pragma unroll
-        for (int j = 0; j < N; ++j)
-#pragma unroll
-            for (int i = 0; i < N; ++i) em.emit(NQCB200_OBS_POPCORR_DIABATIC, i + N * j, p0[i] * dia[j]);
+        for (int i = 0; i < N; ++i) p0[i] = R.p0d[i];
+        const double c4[4] = {p0[0] * dia[0], p0[1] * dia[0], p0[0] * dia[1], p0[1] * dia[1]};   // i + N * j
+        em.emit4(NQCB200_OBS_POPCORR_DIABATIC, 0, c4);
     }
     if (obs & (1u << NQCB200_OBS_POPCORR_ADIABATIC)) {
         double p0[N];
 #pragma unroll
-        for (int i = 0; i < N; ++i) p0[i] = (em.isave == 0) ? adi[i] : p.pop0[(int64_t)(N + i) * T + em.traj];
-#pragma unroll
-        for (int j = 0; j < N; ++j)
-#pragma unroll
-            for (int i = 0; i < N; ++i) em.emit(NQCB200_OBS_POPCORR_ADIABATIC, i + N * j, p0[i] * adi[j]);
+        for (int i = 0; i < N; ++i) p0[i] = R.p0a[i];
+        const double c4[4] = {p0[0] * adi[0], p0[1] * adi[0], p0[0] * adi[1], p0[1] * adi[1]};
+        em.emit4(NQCB200_OBS_POPCORR_ADIABATIC, 0, c4);
     }
     if (obs & ((1u << NQCB200_OBS_KINETIC) | (1u << NQCB200_OBS_POTENTIAL) | (1u << NQCB200_OBS_TOTAL_ENERGY))) {
         const double kin = 0.5 * msv2;
@@ -292,7 +326,7 @@ __global__ void __launch_bounds__(kSbTraj * LPT, 1) spinboson_step_kernel(const 
     // per-mode constants
     for (int j = tid; j < D; j += blockDim.x) {
         const double w = p.bath_a[j], c = p.bath_b[j], m = p.masses[j];
-        M.k1[j] = make_double2(w * w / m, c / m); M.k2[j] = make_double2(c, c * w * w / m); M.k3[j] = make_double2(0.5 * w * w, m);
+        M.k1[j] = make_double2(dt * w * w / m, c / m); M.k2[j] = make_double2(c, c * w * w / m); M.k3[j] = make_double2(0.5 * w * w, m);
     }
     if (fused) {
         // this block's [128][D] tile of the caller's trajectory-major r, v (device staging or pinned host memory)
@@ -338,6 +372,14 @@ __global__ void __launch_bounds__(kSbTraj * LPT, 1) spinboson_step_kernel(const 
 #pragma unroll
         for (int k = 0; k < N; ++k) R.Zref[j][k] = p.Zprev[(int64_t)(j + N * k) * T + traj];
     R.gm = 0.0; R.gd = 0.0;
+    {
+        const bool corr = p.observables & ((1u << NQCB200_OBS_POPCORR_DIABATIC) | (1u << NQCB200_OBS_POPCORR_ADIABATIC));
+#pragma unroll
+        for (int i = 0; i < N; ++i) {      // written by save point 0 (init kernel / fused initialisation)
+            R.p0d[i] = (corr && !fused) ? p.pop0[(int64_t)i * T + traj] : 0.0;
+            R.p0a[i] = (corr && !fused) ? p.pop0[(int64_t)(N + i) * T + traj] : 0.0;
+        }
+    }
     Eig<N> e;
     if (fused) {
         // DynamicsVariables at t0 (fssh.jl:47-65, ehrenfest.jl:43-48): eigenproblem at r0, sigma = Z' rho Z, initial
@@ -402,6 +444,7 @@ __global__ void __launch_bounds__(kSbTraj * LPT, 1) spinboson_step_kernel(const 
     }
     unsigned long long nhops = 0, nfrus = 0;
     bool first = true;
+    double lin_run = 0.0;     // sum_j c_j r_j at the positions in shared memory (re-summed on every launch entry)
 
 #pragma unroll 1
     for (int is = 0; is < p.nsteps; ++is) {
@@ -411,7 +454,12 @@ __global__ void __launch_bounds__(kSbTraj * LPT, 1) spinboson_step_kernel(const 
         SbSums S;
         const bool pend = __any_sync(0xffffffffu, R.gm != 0.0 || R.gd != 0.0);
         if (need_harm) sb_sweep<LPT, METHOD, true, true>(M, D, slot, part, first, pend, R.A, R.B, R.gm, R.gd, dt, hdt, S);
-        else sb_sweep<LPT, METHOD, true, false>(M, D, slot, part, first, pend, R.A, R.B, R.gm, R.gd, dt, hdt, S);
+        else if (first) sb_sweep<LPT, METHOD, true, false>(M, D, slot, part, first, pend, R.A, R.B, R.gm, R.gd, dt, hdt, S);
+        else {
+            sb_sweep<LPT, METHOD, true, false, false>(M, D, slot, part, first, pend, R.A, R.B, R.gm, R.gd, dt, hdt, S);
+            S.lin = fma(dt, S.cvt, lin_run);      // sum c r advances by dt sum c vt
+        }
+        lin_run = S.lin;
         first = false; R.gm = 0.0; R.gd = 0.0;
         // update_cache!: V -> eigen (gauge-fixed)
         {
@@ -522,7 +570,7 @@ __global__ void __launch_bounds__(kSbTraj * LPT, 1) spinboson_step_kernel(const 
                 const double2 k1 = M.k1[dof];
                 const double c = M.k2[dof].x;
                 const double r = M.rs[(size_t)dof * kSbTraj + slot];
-                p.acc[(int64_t)dof * T + traj] = fma(-R.A * k1.x, r, -R.B * k1.y);
+                p.acc[(int64_t)dof * T + traj] = fma(-R.A * (k1.x / dt), r, -R.B * k1.y);
                 p.diag_nac[((int64_t)dof * N * N + 0) * T + traj] = 0.0;
                 p.diag_nac[((int64_t)dof * N * N + 1) * T + traj] = -c * dfac;       // d[1,0]
                 p.diag_nac[((int64_t)dof * N * N + 2) * T + traj] = c * dfac;        // d[0,1]
