@@ -62,6 +62,7 @@ struct KParams {
     uint32_t observables;
     uint64_t seed;
     double dt, t0, omega_n, nrpmd_gamma, edc_C;
+    double tsit5_ha[21];   // (dt/5) a_ij of Tsit5, row by row (a21; a31 a32; ...; a71..a76): constant-bank operands
     double params[NQCB200_MAX_PARAMS];
     // model / system arrays (device)
     const double* masses;   // [D]

@@ -98,7 +98,7 @@ static __constant__ double kTsit5Dev[tsit5::I_COUNT] = {tsit5::c1, tsit5::c2, ts
 // very first step of a trajectory).
 template <int N>
 NQ_HD void propagate_density(const ElecParams<N>& cur, double tcur, const ElecParams<N>& nxt, double tnext,
-                             double t, double dt, Herm<N>& s) {
+                             double t, double dt, Herm<N>& s, const double (&)[21]) {
     using namespace tsit5;
     const double h = dt / 5.0;
     const double inv_span = 1.0 / (tnext - tcur);
@@ -149,7 +149,7 @@ NQ_HD void propagate_density(const ElecParams<N>& cur, double tcur, const ElecPa
 // next step's mode sweep in these slots) fills the fixed-latency bubbles of the serial stage chain.
 template <class Between>
 NQ_HD void propagate_density_2state(const ElecParams<2>& cur, double tcur, const ElecParams<2>& nxt, double tnext,
-                                    double t, double dt, Herm<2>& s, Between&& between) {
+                                    double t, double dt, Herm<2>& s, const double (&ha)[21], Between&& between) {
     // Carried variables: z = x00 - x11 (the trace x00 + x11 is a constant of the motion), x01, y01:
     //     dz = -4 g x01 ,   dx01 = dE y01 + g z ,   dy01 = -dE x01 .
     // FP64 latency, not throughput, bounds the kernels that call this (one serial chain per thread, few warps per
@@ -178,44 +178,45 @@ NQ_HD void propagate_density_2state(const ElecParams<2>& cur, double tcur, const
 #pragma unroll 1
     for (int sub = 0; sub < 5; ++sub) {
         const double hh = (sub == 4) ? (t + dt) - ts : h;   // tstop snapping of the last sub-step
-        // stage i+1 argument = [x + hh sum_{j<i} a_{i+1,j} k_j] + (hh a_{i+1,i}) k_i
+        // stage i+1 argument = [x + h sum_{j<i} a_{i+1,j} k_j] + (h a_{i+1,i}) k_i with h a_ij = ha[] from the constant
+        // bank (the last sub-step's snapped length differs from h = dt/5 by rounding only: it enters the stage times)
 #define NQ_ARG(P, C, KN) fma((C), (KN), (P))
         {
-            const double c21 = hh * NQ_TS(a21);
+            const double c21 = ha[0];
             rhs(ts + NQ_TS(c1) * hh, NQ_ARG(z, c21, k1.a), NQ_ARG(x01, c21, k1.b), NQ_ARG(y01, c21, k1.c), k2);
         }
         between(sub, std::integral_constant<int, 0>{});
         {
-            const double c31 = hh * NQ_TS(a31), c32 = hh * NQ_TS(a32);
+            const double c31 = ha[1], c32 = ha[2];
             rhs(ts + NQ_TS(c2) * hh, NQ_ARG(fma(c31, k1.a, z), c32, k2.a), NQ_ARG(fma(c31, k1.b, x01), c32, k2.b),
                 NQ_ARG(fma(c31, k1.c, y01), c32, k2.c), k3);
         }
         between(sub, std::integral_constant<int, 1>{});
         {
-            const double c41 = hh * NQ_TS(a41), c42 = hh * NQ_TS(a42), c43 = hh * NQ_TS(a43);
+            const double c41 = ha[3], c42 = ha[4], c43 = ha[5];
             rhs(ts + NQ_TS(c3) * hh, NQ_ARG(fma(c42, k2.a, fma(c41, k1.a, z)), c43, k3.a),
                 NQ_ARG(fma(c42, k2.b, fma(c41, k1.b, x01)), c43, k3.b),
                 NQ_ARG(fma(c42, k2.c, fma(c41, k1.c, y01)), c43, k3.c), k4);
         }
         between(sub, std::integral_constant<int, 2>{});
         {
-            const double c51 = hh * NQ_TS(a51), c52 = hh * NQ_TS(a52), c53 = hh * NQ_TS(a53), c54 = hh * NQ_TS(a54);
+            const double c51 = ha[6], c52 = ha[7], c53 = ha[8], c54 = ha[9];
             rhs(ts + NQ_TS(c4) * hh, NQ_ARG(fma(c53, k3.a, fma(c52, k2.a, fma(c51, k1.a, z))), c54, k4.a),
                 NQ_ARG(fma(c53, k3.b, fma(c52, k2.b, fma(c51, k1.b, x01))), c54, k4.b),
                 NQ_ARG(fma(c53, k3.c, fma(c52, k2.c, fma(c51, k1.c, y01))), c54, k4.c), k5);
         }
         between(sub, std::integral_constant<int, 3>{});
         {
-            const double c61 = hh * NQ_TS(a61), c62 = hh * NQ_TS(a62), c63 = hh * NQ_TS(a63), c64 = hh * NQ_TS(a64),
-                         c65 = hh * NQ_TS(a65);
+            const double c61 = ha[10], c62 = ha[11], c63 = ha[12], c64 = ha[13],
+                         c65 = ha[14];
             rhs(ts + hh, NQ_ARG(fma(c64, k4.a, fma(c63, k3.a, fma(c62, k2.a, fma(c61, k1.a, z)))), c65, k5.a),
                 NQ_ARG(fma(c64, k4.b, fma(c63, k3.b, fma(c62, k2.b, fma(c61, k1.b, x01)))), c65, k5.b),
                 NQ_ARG(fma(c64, k4.c, fma(c63, k3.c, fma(c62, k2.c, fma(c61, k1.c, y01)))), c65, k5.c), k6);
         }
         between(sub, std::integral_constant<int, 4>{});
         {
-            const double c71 = hh * NQ_TS(a71), c72 = hh * NQ_TS(a72), c73 = hh * NQ_TS(a73), c74 = hh * NQ_TS(a74),
-                         c75 = hh * NQ_TS(a75), c76 = hh * NQ_TS(a76);
+            const double c71 = ha[15], c72 = ha[16], c73 = ha[17], c74 = ha[18],
+                         c75 = ha[19], c76 = ha[20];
             z = NQ_ARG(fma(c75, k5.a, fma(c74, k4.a, fma(c73, k3.a, fma(c72, k2.a, fma(c71, k1.a, z))))), c76, k6.a);
             x01 = NQ_ARG(fma(c75, k5.b, fma(c74, k4.b, fma(c73, k3.b, fma(c72, k2.b, fma(c71, k1.b, x01))))), c76, k6.b);
             y01 = NQ_ARG(fma(c75, k5.c, fma(c74, k4.c, fma(c73, k3.c, fma(c72, k2.c, fma(c71, k1.c, y01))))), c76, k6.c);
@@ -230,8 +231,8 @@ NQ_HD void propagate_density_2state(const ElecParams<2>& cur, double tcur, const
 
 template <>
 NQ_HD void propagate_density<2>(const ElecParams<2>& cur, double tcur, const ElecParams<2>& nxt, double tnext,
-                                double t, double dt, Herm<2>& s) {
-    propagate_density_2state(cur, tcur, nxt, tnext, t, dt, s, [](int, auto) {});
+                                double t, double dt, Herm<2>& s, const double (&ha)[21]) {
+    propagate_density_2state(cur, tcur, nxt, tnext, t, dt, s, ha, [](int, auto) {});
 }
 
 }  // namespace nq

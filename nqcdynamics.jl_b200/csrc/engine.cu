@@ -447,6 +447,15 @@ int nqcb200_create(const nqcb200_config* cfg, nqcb200_handle** out) {
     kp.observables = c.observables; kp.seed = c.seed; kp.dt = c.dt; kp.t0 = c.t0;
     kp.omega_n = B * c.temperature; kp.nrpmd_gamma = c.nrpmd_gamma; kp.edc_C = kp.mean_field ? 0.0 : c.edc_C;
     std::memcpy(kp.params, c.params, sizeof(kp.params));
+    {
+        static const double a[21] = {0.161,
+                                     -0.008480655492356989, 0.335480655492357,
+                                     2.8971530571054935, -6.359448489975075, 4.3622954328695815,
+                                     5.325864828439257, -11.748883564062828, 7.4955393428898365, -0.09249506636175525,
+                                     5.86145544294642, -12.92096931784711, 8.159367898576159, -0.071584973281401, -0.028269050394068383,
+                                     0.09646076681806523, 0.01, 0.4798896504144996, 1.379008574103742, -3.290069515436081, 2.324710524099774};
+        for (int i = 0; i < 21; ++i) kp.tsit5_ha[i] = (c.dt / 5.0) * a[i];
+    }
     // observable layout
     int64_t off = 0;
     for (int id = 0; id < NQCB200_OBS_COUNT; ++id) {

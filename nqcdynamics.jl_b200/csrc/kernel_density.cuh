@@ -389,7 +389,7 @@ __global__ void __launch_bounds__(kBlockThreads) density_step_kernel(const __gri
 #pragma unroll
             for (int i = 0; i < asym_size(N); ++i) nxt.g[i] = lane_sum<L>(nxt.g[i]);
         }
-        propagate_density<N>(R.cur, tcur, nxt, t + dt, t, dt, R.s);
+        propagate_density<N>(R.cur, tcur, nxt, t + dt, t, dt, R.s, p.tsit5_ha);
 
         if (METHOD == NQCB200_METHOD_FSSH) {
             const double xi = (p.rng == NQCB200_RNG_INJECTED)

@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(kBlockThreads) ring_step_kernel(const __grid_c
         for (int j = 0; j < N; ++j)
 #pragma unroll
             for (int k = j + 1; k < N; ++k) nxt.g[aidx(N, j, k)] = (-Ac[sidx(N, j, k)] / (ec.w[j] - ec.w[k])) * vcent;
-        propagate_density<N>(R.cur, tcur, nxt, t + dt, t, dt, R.s);
+        propagate_density<N>(R.cur, tcur, nxt, t + dt, t, dt, R.s, p.tsit5_ha);
 
         if (METHOD == NQCB200_METHOD_FSSH) {
             const double xi = (p.rng == NQCB200_RNG_INJECTED)

@@ -477,7 +477,7 @@ __global__ void __launch_bounds__(kSbTraj * LPT, 1) spinboson_step_kernel(const 
         ElecParams<N> nxt;
         nxt.E[0] = e.w[0]; nxt.E[1] = e.w[1];
         nxt.g[0] = dfac * cv;
-        propagate_density<N>(R.cur, tcur, nxt, t + dt, t, dt, R.s);
+        propagate_density<N>(R.cur, tcur, nxt, t + dt, t, dt, R.s, p.tsit5_ha);
 
         if (METHOD == NQCB200_METHOD_FSSH) {
             const double xi = (p.rng == NQCB200_RNG_INJECTED)
