@@ -22,17 +22,24 @@ template <int N>
 NQ_HD void jacobi_rotate(double (&A)[N][N], double (&Z)[N][N], int p, int q) {
     const double apq = A[p][q];
     if (apq == 0.0) return;
-    // t = sgn(theta) / (|theta| + sqrt(theta^2 + 1)), theta = a / b, written without forming theta:
-    // one sqrt, one division and one reciprocal square root instead of three divisions and two square roots
+    // Rotation angle |theta| <= pi/4 with tan 2 theta = b / a (a = A_qq - A_pp, b = 2 A_pq):
+    //     cos 2theta = |a| / hyp,  c = sqrt((1 + cos 2theta) / 2),  s = sgn(a) (b / hyp) / (2 c),  t = s / c.
+    // FP64 sqrt and division are ~90 / ~70-cycle dependent sequences on B200 (tools/micro/fp64_latency.cu) and the
+    // three rotations of a sweep are serial, so the rotation is written with two reciprocal square roots and no
+    // division: 1/hyp = rsqrt(a^2 + b^2), 1/c = rsqrt(c^2).
     const double a = A[q][q] - A[p][p], b = 2.0 * apq;
-    const double hyp = sqrt(fma(a, a, b * b));
-    const double t = b / (a + (a >= 0.0 ? hyp : -hyp));
 #if defined(__CUDA_ARCH__)
-    const double c = rsqrt(fma(t, t, 1.0));
+    const double ih = rsqrt(fma(a, a, b * b));
+    const double c2 = fma(0.5 * fabs(a), ih, 0.5);
+    const double rc = rsqrt(c2);
 #else
-    const double c = 1.0 / sqrt(fma(t, t, 1.0));
+    const double ih = 1.0 / sqrt(fma(a, a, b * b));
+    const double c2 = fma(0.5 * fabs(a), ih, 0.5);
+    const double rc = 1.0 / sqrt(c2);
 #endif
-    const double s = t * c;
+    const double c = c2 * rc;
+    const double s = (a >= 0.0 ? 0.5 : -0.5) * (b * ih) * rc;
+    const double t = s * rc;
 #pragma unroll
     for (int k = 0; k < N; ++k) {
         if (k != p && k != q) {
