@@ -41,8 +41,8 @@ DEFAULT_WORKLOAD = "spinboson_debye100_fssh"   # BASELINE.json configs[1]
 # touch HBM only at launch entry / exit (state in, state out) and at save points, so the traffic of a launch scales
 # with the number of trajectories, not with the number of steps.
 NCU_DRAM_BYTES_PER_TRAJ = {
-    "spinboson_debye100_fssh": (2697.0, "sb_v4"), "spinboson_debye100_ehrenfest": (2697.0, "sb_v4"),
-    "tully1_fssh": (236.0, "tully1_v2"), "rpmd_harmonic32": (1356.0, "rpmd_fft"), "rpsh_morse3_16": (694.0, "rpsh_tpt"),
+    "spinboson_debye100_fssh": (2696.0, "sb_v5"), "spinboson_debye100_ehrenfest": (2696.0, "sb_v5"),
+    "tully1_fssh": (236.0, "tully1_v3"), "rpmd_harmonic32": (1356.0, "rpmd_fft"), "rpsh_morse3_16": (664.0, "rpsh_tpt2"),
 }
 
 
