@@ -21,6 +21,9 @@ namespace nq {
 #if defined(__CUDACC__)
 
 constexpr int kRtThreads = kBlockThreads;   // 128 (the Emitter's block reduction is sized for it)
+#ifndef RT_MIN_BLOCKS
+#define RT_MIN_BLOCKS 3   // 168 registers: three blocks (12 warps) per SM hide the serial Jacobi chains better than 255 registers without spills (measured: 8.4e8 -> 9.0e8; four blocks: slower)
+#endif
 
 // fft: nbeads is a power of two (compile-time NBT); otherwise the dense normal-mode product through two scratch rows
 NQ_HD constexpr size_t ring_tpt_smem_bytes(int N, int NB, bool ehrenfest, bool fft) {
@@ -187,7 +190,7 @@ NQ_D void rt_record_save(const KParams& p, Emitter& em, int NB, const double* s_
 
 // NBT > 0: nbeads = NBT, a power of two (FFT in registers).  NBT == 0: any nbeads (p.B), dense normal-mode product.
 template <class M, int NBT, int METHOD>
-__global__ void __launch_bounds__(kRtThreads) ring_tpt_step_kernel(const __grid_constant__ KParams p) {
+__global__ void __launch_bounds__(kRtThreads, RT_MIN_BLOCKS) ring_tpt_step_kernel(const __grid_constant__ KParams p) {
     constexpr int N = M::NS;
     constexpr bool EHR = (METHOD == NQCB200_METHOD_EHRENFEST);
     constexpr bool FFT = NBT > 0;
