@@ -58,7 +58,12 @@ struct Emitter {
     int isave;
     double* smem;    // [2][kBlockThreads/32]
     int slot;
+    bool fresh = true;   // first emit of this save point
     NQ_D void emit(int obs_id, int k, double val) {
+        // The two scratch rows alternate, so an emit never overwrites the row thread 0 is still summing from the
+        // previous emit -- except across save points (every Emitter starts at row 0, and the previous save may have
+        // ended on row 0 after an odd number of emits): one barrier per save point closes that window (racecheck).
+        if (fresh) { __syncthreads(); fresh = false; }
         const int64_t off = p.layout.offset[obs_id] + (int64_t)isave * p.layout.width[obs_id] + k;
         if (p.obs_traj != nullptr && active) p.obs_traj[off * p.ntraj + traj] = val;
         const double ws = warp_sum(active ? val : 0.0);
