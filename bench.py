@@ -327,6 +327,7 @@ def main():
         eng.close()
         eng2 = Engine(cfg2, keep2)
         r_h, v_h = pin(ic["r"]), pin(ic["v"])
+        rho_h = pin(rho) if rho is not None else None
         psi_h = pin(ic["psi"]) if "psi" in ic else None
         first_obs = next(o for o in range(A.OBS_COUNT) if (wl.observables >> o) & 1)
         d2h = 0
@@ -334,8 +335,8 @@ def main():
         def job(h):
             """one ensemble batch through the public C-ABI calls with HOST buffers; returns the bytes handed over"""
             if density:     # set_state_diabatic + run in one call; the SpinBoson kernels read pinned r, v in place
-                h.run_from_host(r_h, v_h, rho, None, None, None, diabatic=True, nsteps=wl.nsteps)
-                return r_h.nbytes + v_h.nbytes + rho.nbytes
+                h.run_from_host(r_h, v_h, rho_h, None, None, None, diabatic=True, nsteps=wl.nsteps)
+                return r_h.nbytes + v_h.nbytes + rho_h.nbytes
             nbytes = upload(h, r_h, v_h, psi_h)
             h.run(wl.nsteps)
             return nbytes

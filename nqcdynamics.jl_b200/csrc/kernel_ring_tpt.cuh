@@ -69,14 +69,22 @@ NQ_D void rt_free_step(const RtTables<NB>& tb, double (&zr)[NB], double (&zi)[NB
             }
         }
     }
-    double nr[NB], ni[NB];
+    // Z'_k = alpha_k Z_k + beta_k conj(Z_{NB-k}), in place: the pair (k, NB-k) is updated together (k = 0 and NB/2
+    // pair with themselves), so no second copy of the spectrum is live
 #pragma unroll
-    for (int i = 0; i < NB; ++i) {           // Z'_k = alpha_k Z_k + beta_k conj(Z_{NB-k})
+    for (int i = 0; i < NB; ++i) {
         const int k = rt_bitrev<NB>(i), ip = rt_bitrev<NB>((NB - k) % NB);
+        if (ip < i) continue;                 // handled with its partner
         const double ar = tb.al[2 * k], ai = tb.al[2 * k + 1], br = tb.be[2 * k], bi = tb.be[2 * k + 1];
-        const double wr = zr[ip], wi = -zi[ip];
-        nr[i] = fma(ar, zr[i], fma(-ai, zi[i], fma(br, wr, -bi * wi)));
-        ni[i] = fma(ar, zi[i], fma(ai, zr[i], fma(br, wi, bi * wr)));
+        const double xr = zr[i], xi = zi[i], yr = zr[ip], yi = zi[ip];
+        zr[i] = fma(ar, xr, fma(-ai, xi, fma(br, yr, bi * yi)));          // W = conj(Z_partner) = (yr, -yi)
+        zi[i] = fma(ar, xi, fma(ai, xr, fma(-br, yi, bi * yr)));
+        if (ip != i) {
+            const int kp = (NB - k) % NB;
+            const double cr = tb.al[2 * kp], ci = tb.al[2 * kp + 1], dr = tb.be[2 * kp], di = tb.be[2 * kp + 1];
+            zr[ip] = fma(cr, yr, fma(-ci, yi, fma(dr, xr, di * xi)));
+            zi[ip] = fma(cr, yi, fma(ci, yr, fma(-dr, xi, di * xr)));
+        }
     }
 #pragma unroll
     for (int s = LOG - 1; s >= 0; --s) {     // DIT: bit-reversed in, natural out
@@ -85,20 +93,18 @@ NQ_D void rt_free_step(const RtTables<NB>& tb, double (&zr)[NB], double (&zi)[NB
         for (int i = 0; i < NB; ++i) {
             if ((i & h) == 0) {
                 const int j = i & (h - 1), tw = j * (NB / (2 * h));
-                double tr = nr[i + h], ti = ni[i + h];
+                double tr = zr[i + h], ti = zi[i + h];
                 if (tw != 0) {
                     const double wr = tb.twr[tw], wi = tb.twi[tw];
                     const double xr = fma(tr, wr, ti * wi), xi = fma(ti, wr, -tr * wi);   // conj(twiddle)
                     tr = xr; ti = xi;
                 }
-                const double ur = nr[i], ui = ni[i];
-                nr[i] = ur + tr; ni[i] = ui + ti;
-                nr[i + h] = ur - tr; ni[i + h] = ui - ti;
+                const double ur = zr[i], ui = zi[i];
+                zr[i] = ur + tr; zi[i] = ui + ti;
+                zr[i + h] = ur - tr; zi[i + h] = ui - ti;
             }
         }
     }
-#pragma unroll
-    for (int i = 0; i < NB; ++i) { zr[i] = nr[i]; zi[i] = ni[i]; }
 }
 
 // r_b = s_r[b * stride + idx] (shared memory: stride 128, idx = thread; global memory: stride T, idx = trajectory)
@@ -681,6 +687,78 @@ __global__ void __launch_bounds__(kRtThreads) classical_tpt_step_kernel(const __
             p.r[(int64_t)b * T + traj] = s_r[b * kRtThreads + tid];
             p.v[(int64_t)b * T + traj] = s_v[b * kRtThreads + tid];
             p.acc[(int64_t)b * T + traj] = s_a[b * kRtThreads + tid];
+        }
+    }
+}
+
+// Classical RPMD, power-of-two bead count, whole ring polymer in REGISTERS: one thread per trajectory, in-register FFT
+// for the free ring-polymer step, no shuffles and no shared-memory traffic in the step loop (the beads-on-lanes kernel
+// spends 69 % of the LSU wavefront budget on its 22 double shuffles per step).  The acceleration is not carried: a
+// single-surface model's force is a few flops, so it is re-evaluated at the start of the step.
+template <class M, int NB>
+__global__ void __launch_bounds__(kRtThreads, 2) classical_tpt_fft_kernel(const __grid_constant__ KParams p) {
+    static_assert(NB >= 2 && (NB & (NB - 1)) == 0, "power-of-two bead count");
+    __shared__ double red[2 * (kRtThreads / 32)];
+    __shared__ double s_tab[5 * NB];
+    const int tid = threadIdx.x;
+    int64_t traj = (int64_t)blockIdx.x * kRtThreads + tid;
+    const bool valid = traj < p.ntraj;
+    if (!valid) traj = p.ntraj - 1;
+    const int64_t T = p.ntraj;
+    for (int j = tid; j < NB; j += kRtThreads) {
+        if (j < NB / 2) {
+            double si, co;
+            sincospi(-2.0 * (double)j / (double)NB, &si, &co);
+            s_tab[j] = co; s_tab[NB / 2 + j] = si;
+        }
+        const double a = p.cayley[4 * j + 0], b = p.cayley[4 * j + 1], c = p.cayley[4 * j + 2], d = p.cayley[4 * j + 3];
+        const double inv = 0.5 / NB;
+        s_tab[NB + 2 * j] = (a + d) * inv; s_tab[NB + 2 * j + 1] = (c - b) * inv;
+        s_tab[3 * NB + 2 * j] = (a - d) * inv; s_tab[3 * NB + 2 * j + 1] = (c + b) * inv;
+    }
+    __syncthreads();
+    RtTables<NB> tb{s_tab, s_tab + NB / 2, s_tab + NB, s_tab + 3 * NB};
+    double r[NB], v[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) { r[b] = p.r[(int64_t)b * T + traj]; v[b] = p.v[(int64_t)b * T + traj]; }
+    const double mass = p.masses[0], hdt = 0.5 * p.dt, hm = hdt / mass;
+#pragma unroll 1
+    for (int is = 0; is < p.nsteps; ++is) {
+        const int64_t step = p.step0 + is;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) v[b] = fma(-hm, M::gradient_dof(p.params, r[b]), v[b]);     // B
+        rt_free_step<NB>(tb, r, v);                                                               // C
+#pragma unroll
+        for (int b = 0; b < NB; ++b) v[b] = fma(-hm, M::gradient_dof(p.params, r[b]), v[b]);     // B (classical.jl:63-67)
+        if ((step + 1) % p.save_every == 0) {
+            const int64_t isave = (step + 1) / p.save_every;
+            if (isave < p.nsave) {
+                const uint32_t obs = p.observables;
+                double rsum = 0.0, vsum = 0.0, mv2 = 0.0, spr = 0.0, pot = 0.0;
+#pragma unroll
+                for (int b = 0; b < NB; ++b) {
+                    rsum += r[b]; vsum += v[b];
+                    mv2 = fma(mass * v[b], v[b], mv2);
+                    pot += M::potential_dof(p.params, r[b]);
+                    const double d = r[(b + NB - 1) % NB] - r[b];
+                    spr = fma(mass * d, d, spr);
+                }
+                Emitter em{p, traj, valid, (int)isave, red, 0};
+                const double kin = 0.5 * mv2;
+                if (obs & (1u << NQCB200_OBS_KINETIC)) em.emit(NQCB200_OBS_KINETIC, 0, kin);
+                if (obs & (1u << NQCB200_OBS_POTENTIAL)) em.emit(NQCB200_OBS_POTENTIAL, 0, pot);
+                if (obs & (1u << NQCB200_OBS_TOTAL_ENERGY)) em.emit(NQCB200_OBS_TOTAL_ENERGY, 0, kin + pot + 0.5 * p.omega_n * p.omega_n * spr);
+                if (obs & (1u << NQCB200_OBS_POSITION)) em.emit(NQCB200_OBS_POSITION, 0, rsum / NB);
+                if (obs & (1u << NQCB200_OBS_VELOCITY)) em.emit(NQCB200_OBS_VELOCITY, 0, vsum / NB);
+            }
+        }
+    }
+    if (valid) {
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            p.r[(int64_t)b * T + traj] = r[b];
+            p.v[(int64_t)b * T + traj] = v[b];
+            p.acc[(int64_t)b * T + traj] = -M::gradient_dof(p.params, r[b]) / mass;
         }
     }
 }

@@ -1,4 +1,6 @@
 // tu_classical_nrpmd.cu -- classical MD / RPMD and NRPMD kernels (beads on lanes).
+#include <cstdlib>
+
 #include "kernel_nrpmd.cuh"
 #include "kernel_ring_tpt.cuh"
 
@@ -9,6 +11,15 @@ void set_classical(KernelSet& k, const char* name) {
     k.step = classical_ring_step_kernel<M, NB>;
     k.init = classical_ring_init_kernel<M, NB>;
     k.L = NB; k.DPL = 1; k.name = name;
+    if constexpr (NB >= 2) {
+        // step kernel: the whole ring polymer in one thread's registers (kernel_ring_tpt.cuh); NQCB200_RPMD_TPT=0
+        // keeps the beads-on-lanes kernel (A/B switch)
+        const char* env = getenv("NQCB200_RPMD_TPT");
+        if (!(env && atoi(env) == 0)) {
+            k.step = classical_tpt_fft_kernel<M, NB>;
+            k.step_L = 1; k.step_block = kRtThreads; k.step_smem = 0;
+        }
+    }
 }
 template <class M>
 void k_generic(KernelSet& k, const char* name, size_t bytes) {
