@@ -98,7 +98,7 @@ static __constant__ double kTsit5Dev[tsit5::I_COUNT] = {tsit5::c1, tsit5::c2, ts
 // very first step of a trajectory).
 template <int N>
 NQ_HD void propagate_density(const ElecParams<N>& cur, double tcur, const ElecParams<N>& nxt, double tnext,
-                             double t, double dt, Herm<N>& s, const double (&)[21]) {
+                             double t, double dt, Herm<N>& s, const double (&ha)[21]) {
     using namespace tsit5;
     const double h = dt / 5.0;
     const double inv_span = 1.0 / (tnext - tcur);
@@ -112,27 +112,31 @@ NQ_HD void propagate_density(const ElecParams<N>& cur, double tcur, const ElecPa
 #pragma unroll 1
     for (int sub = 0; sub < 5; ++sub) {
         const double hh = (sub == 4) ? (t + dt) - ts : h;   // tstop snapping of the last sub-step
+        // stage argument = s + sum_j (h a_ij) k_j with h a_ij = ha[] (kernel-parameter constant bank), FMAs only
 #define NQ_STAGE(EXPRX, EXPRY)                                                              \
-        _Pragma("unroll") for (int i = 0; i < sym_size(N); ++i) tmp.x[i] = s.x[i] + hh * (EXPRX);  \
-        _Pragma("unroll") for (int i = 0; i < asym_size(N); ++i) tmp.y[i] = s.y[i] + hh * (EXPRY);
-        NQ_STAGE(NQ_TS(a21) * k1.x[i], NQ_TS(a21) * k1.y[i])
+        _Pragma("unroll") for (int i = 0; i < sym_size(N); ++i) tmp.x[i] = (EXPRX);  \
+        _Pragma("unroll") for (int i = 0; i < asym_size(N); ++i) tmp.y[i] = (EXPRY);
+#define NQ_F1(A, K, REST) fma(ha[A], K, REST)
+        NQ_STAGE(NQ_F1(0, k1.x[i], s.x[i]), NQ_F1(0, k1.y[i], s.y[i]))
         density_rhs<N>(cur, nxt, loc_of(ts + NQ_TS(c1) * hh), tmp, k2);
-        NQ_STAGE(NQ_TS(a31) * k1.x[i] + NQ_TS(a32) * k2.x[i], NQ_TS(a31) * k1.y[i] + NQ_TS(a32) * k2.y[i])
+        NQ_STAGE(NQ_F1(2, k2.x[i], NQ_F1(1, k1.x[i], s.x[i])), NQ_F1(2, k2.y[i], NQ_F1(1, k1.y[i], s.y[i])))
         density_rhs<N>(cur, nxt, loc_of(ts + NQ_TS(c2) * hh), tmp, k3);
-        NQ_STAGE(NQ_TS(a41) * k1.x[i] + NQ_TS(a42) * k2.x[i] + NQ_TS(a43) * k3.x[i], NQ_TS(a41) * k1.y[i] + NQ_TS(a42) * k2.y[i] + NQ_TS(a43) * k3.y[i])
+        NQ_STAGE(NQ_F1(5, k3.x[i], NQ_F1(4, k2.x[i], NQ_F1(3, k1.x[i], s.x[i]))),
+                 NQ_F1(5, k3.y[i], NQ_F1(4, k2.y[i], NQ_F1(3, k1.y[i], s.y[i]))))
         density_rhs<N>(cur, nxt, loc_of(ts + NQ_TS(c3) * hh), tmp, k4);
-        NQ_STAGE(NQ_TS(a51) * k1.x[i] + NQ_TS(a52) * k2.x[i] + NQ_TS(a53) * k3.x[i] + NQ_TS(a54) * k4.x[i],
-                 NQ_TS(a51) * k1.y[i] + NQ_TS(a52) * k2.y[i] + NQ_TS(a53) * k3.y[i] + NQ_TS(a54) * k4.y[i])
+        NQ_STAGE(NQ_F1(9, k4.x[i], NQ_F1(8, k3.x[i], NQ_F1(7, k2.x[i], NQ_F1(6, k1.x[i], s.x[i])))),
+                 NQ_F1(9, k4.y[i], NQ_F1(8, k3.y[i], NQ_F1(7, k2.y[i], NQ_F1(6, k1.y[i], s.y[i])))))
         density_rhs<N>(cur, nxt, loc_of(ts + NQ_TS(c4) * hh), tmp, k5);
-        NQ_STAGE(NQ_TS(a61) * k1.x[i] + NQ_TS(a62) * k2.x[i] + NQ_TS(a63) * k3.x[i] + NQ_TS(a64) * k4.x[i] + NQ_TS(a65) * k5.x[i],
-                 NQ_TS(a61) * k1.y[i] + NQ_TS(a62) * k2.y[i] + NQ_TS(a63) * k3.y[i] + NQ_TS(a64) * k4.y[i] + NQ_TS(a65) * k5.y[i])
+        NQ_STAGE(NQ_F1(14, k5.x[i], NQ_F1(13, k4.x[i], NQ_F1(12, k3.x[i], NQ_F1(11, k2.x[i], NQ_F1(10, k1.x[i], s.x[i]))))),
+                 NQ_F1(14, k5.y[i], NQ_F1(13, k4.y[i], NQ_F1(12, k3.y[i], NQ_F1(11, k2.y[i], NQ_F1(10, k1.y[i], s.y[i]))))))
         density_rhs<N>(cur, nxt, loc_of(ts + hh), tmp, k6);
 #pragma unroll
         for (int i = 0; i < sym_size(N); ++i)
-            s.x[i] = s.x[i] + hh * (NQ_TS(a71) * k1.x[i] + NQ_TS(a72) * k2.x[i] + NQ_TS(a73) * k3.x[i] + NQ_TS(a74) * k4.x[i] + NQ_TS(a75) * k5.x[i] + NQ_TS(a76) * k6.x[i]);
+            s.x[i] = NQ_F1(20, k6.x[i], NQ_F1(19, k5.x[i], NQ_F1(18, k4.x[i], NQ_F1(17, k3.x[i], NQ_F1(16, k2.x[i], NQ_F1(15, k1.x[i], s.x[i]))))));
 #pragma unroll
         for (int i = 0; i < asym_size(N); ++i)
-            s.y[i] = s.y[i] + hh * (NQ_TS(a71) * k1.y[i] + NQ_TS(a72) * k2.y[i] + NQ_TS(a73) * k3.y[i] + NQ_TS(a74) * k4.y[i] + NQ_TS(a75) * k5.y[i] + NQ_TS(a76) * k6.y[i]);
+            s.y[i] = NQ_F1(20, k6.y[i], NQ_F1(19, k5.y[i], NQ_F1(18, k4.y[i], NQ_F1(17, k3.y[i], NQ_F1(16, k2.y[i], NQ_F1(15, k1.y[i], s.y[i]))))));
+#undef NQ_F1
 #undef NQ_STAGE
         ts = (sub == 4) ? (t + dt) : ts + hh;
         if (sub < 4) density_rhs<N>(cur, nxt, loc_of(ts), s, k1);  // FSAL: k7 of this sub-step = k1 of the next
