@@ -2,9 +2,13 @@
 //
 // NB beads of one trajectory occupy NB adjacent lanes of a warp (NB | 32, so 32/NB trajectories per
 // warp); every lane owns one bead's (r, v, acceleration, eigenvector gauge) in registers for the
-// whole launch.  The free ring-polymer step is: to-normal-modes -> Cayley 2x2 per mode -> back,
-// done as lane-dense NB x NB mat-vecs through warp shuffles with the (orthogonal) transformation
-// read conflict-free from shared memory.
+// whole launch.  The free ring-polymer step (to-normal-modes -> Cayley 2x2 per mode -> back) is ONE
+// complex FFT of r + i v over the lanes (FreeRingPolymer below).
+//
+// Role after round 1: these kernels initialise every power-of-two ring polymer (ring_init_kernel,
+// classical_ring_init_kernel), step classical MD (NB == 1) and NRPMD (kernel_nrpmd.cuh), and remain the A/B
+// fallback of the thread-per-trajectory step kernels of kernel_ring_tpt.cuh (RPSH / RP-Ehrenfest / RPMD), which
+// are 3-6x faster because they do not replicate the centroid electronic work / do not shuffle.
 //
 // Reference restated:
 //   BCB.perform_step!          src/DynamicsMethods/IntegrationAlgorithms/bcb.jl:81-116   (RPMD)

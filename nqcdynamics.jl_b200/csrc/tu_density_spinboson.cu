@@ -1,4 +1,5 @@
-// tu_density_spinboson.cu -- FSSH / Ehrenfest kernels for SpinBoson: L lanes per trajectory, modes over lanes.
+// tu_density_spinboson.cu -- FSSH / Ehrenfest kernels for SpinBoson: the shared-memory-resident kernel of
+// kernel_spinboson.cuh (default) and the generic lanes-over-modes kernels (init kernel, baths beyond the shared-memory budget).
 #include <cstdlib>
 
 #include "kernel_density.cuh"
