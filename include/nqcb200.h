@@ -68,7 +68,13 @@ enum nqcb200_method {
     /* Simulation{EhrenfestNA} + VerletwithElectronics (ehrenfest_na.jl:5-126, verlet_with_electronics.jl:76-79):
      * the AdiabaticIESH state (psi: n x ne) without occupations or hops; mean-field force
      * -sum_e <psi_e| Z' dV Z |psi_e>.  set_state: sigma = psi, state = NULL.                     */
-    NQCB200_METHOD_EHRENFEST_NA = 6
+    NQCB200_METHOD_EHRENFEST_NA = 6,
+    /* RingPolymerSimulation{ThermalLangevin} + BCOCB (langevin.jl:67-82, bcocb.jl:78-120, steps.jl:109-124): thermostatted
+     * ring-polymer dynamics, the sampler of the RPMD / RPSH thermal distributions.  PILE friction
+     * gamma_0 = cfg.nrpmd_gamma (the struct's one gamma field), gamma_k = 2 omega_k; O-step in normal modes between two
+     * half Cayley steps.  Classical (single-surface) models, nbeads a power of two >= 2.  Noise: Philox normals
+     * (purpose 3) keyed by (seed; trajectory, step, mode), or injected with nqcb200_set_noise.       */
+    NQCB200_METHOD_THERMAL_LANGEVIN = 7
 };
 
 /* ---- analytic model Hamiltonians (NQCModels.jl, external to the reference tree) ------------ */
@@ -244,6 +250,10 @@ int nqcb200_set_gauge_reference(nqcb200_handle* h, const double* Z, int64_t coun
 /* Parity mode (cfg.rng == INJECTED): xi[step*ntraj + traj], uniform [0,1) draws consumed one per
  * trajectory per step starting at the current step counter.                                    */
 int nqcb200_set_draws(nqcb200_handle* h, const double* xi, int64_t nsteps);
+
+/* ThermalLangevin parity mode (cfg.rng == INJECTED): standard normals xi[(step*ntraj + traj)*nbeads + mode], one per
+ * ring-polymer normal mode per step (W.dW / sqrt(dt) of steps.jl:116-119), starting at the current step counter.   */
+int nqcb200_set_noise(nqcb200_handle* h, const double* xi, int64_t nsteps);
 
 /* Advance every trajectory by nsteps of dt (blocking).  Order inside a step follows the
  * reference: perform_step! -> hop callback -> save.                              */

@@ -17,6 +17,7 @@ MAX_PARAMS = 32
 
 # enums (include/nqcb200.h)
 METHOD_FSSH, METHOD_EHRENFEST, METHOD_IESH, METHOD_CLASSICAL, METHOD_NRPMD, METHOD_EHRENFEST_NA = 1, 2, 3, 4, 5, 6
+METHOD_THERMAL_LANGEVIN = 7
 IESH_FAMILY = (METHOD_IESH, METHOD_EHRENFEST_NA)      # psi: n x ne, trajectory-major
 (MODEL_TULLY_ONE, MODEL_TULLY_TWO, MODEL_TULLY_THREE, MODEL_DOUBLE_WELL, MODEL_SPIN_BOSON,
  MODEL_THREE_STATE_MORSE, MODEL_HARMONIC, MODEL_FREE, MODEL_ANDERSON_HOLSTEIN_MIAO_SUBOTNIK) = range(1, 10)
@@ -99,6 +100,7 @@ def bind(lib: C.CDLL, prefix: str) -> None:
     f("set_mapping", [H, _dp, _dp])
     f("set_gauge_reference", [H, _dp, C.c_int64])
     f("set_draws", [H, _dp, C.c_int64])
+    f("set_noise", [H, _dp, C.c_int64])
     f("run", [H, C.c_int64])
     f("run_from_host", [H, _dp, _dp, _dp, _dp, _ip, _dp, C.c_int, C.c_int64], required=False)
     f("sample_state", [H, C.POINTER(Dist), C.POINTER(Dist), C.c_int, _dp, _dp, C.c_int, C.c_int32])
@@ -120,7 +122,7 @@ def bind(lib: C.CDLL, prefix: str) -> None:
 
 HEADER_SYMBOLS = [
     "version", "device_count", "create", "destroy", "last_error", "observable_width", "set_state",
-    "set_state_diabatic", "set_mapping", "set_gauge_reference", "set_draws", "run", "run_from_host", "sample_state", "get_state", "get_mapping",
+    "set_state_diabatic", "set_mapping", "set_gauge_reference", "set_draws", "set_noise", "run", "run_from_host", "sample_state", "get_state", "get_mapping",
     "get_observable_sum", "observable_sum_device", "observable_offset", "get_observable_per_trajectory",
     "get_diagnostics", "get_counters", "get_iesh_stats", "get_progress", "get_last_run_timing", "get_launch_count", "get_last_download_timing", "measure_fp64_peak",
 ]
@@ -223,6 +225,13 @@ class CHandle:
         if xi_.ndim != 2 or xi_.shape[1] != self.T:
             raise ValueError("draws must have shape (nsteps, ntraj)")
         self._call("set_draws", _ptr(xi_.reshape(-1)), C.c_int64(xi_.shape[0]))
+
+    def set_noise(self, xi):
+        """ThermalLangevin parity mode: standard normals of shape (nsteps, ntraj, nbeads), one per normal mode."""
+        xi_ = np.ascontiguousarray(xi, dtype=np.float64)
+        if xi_.ndim != 3 or xi_.shape[1] != self.T or xi_.shape[2] != self.B * self.D:
+            raise ValueError("noise must have shape (nsteps, ntraj, nbeads*ndofs)")
+        self._call("set_noise", _ptr(xi_.reshape(-1)), C.c_int64(xi_.shape[0]))
 
     def run(self, nsteps: int):
         self._call("run", C.c_int64(int(nsteps)))

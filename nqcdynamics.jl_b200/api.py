@@ -81,6 +81,13 @@ class EhrenfestNA:
 
 
 @dataclass
+class ThermalLangevin:
+    """``RingPolymerSimulation{ThermalLangevin}(atoms, model, n_beads; γ, temperature)`` (langevin.jl:67-82), BCOCB."""
+    γ: float = 1.0
+    method_id: int = A.METHOD_THERMAL_LANGEVIN
+
+
+@dataclass
 class NRPMD:
     γ: float = 0.5                        # nrpmd.jl:43
     method_id: int = A.METHOD_NRPMD

@@ -97,6 +97,10 @@ struct KParams {
     double* iesh_sgn;   // [T][n]   eigenvector column signs (gauge), constant along a trajectory
     double* iesh_orth;  // [T]      1.0 when the initial orbitals are orthonormal (determinant-free pruning bound)
     double* iesh_G;     // [grid][ldg*kb*nslab] v.d scratch when it does not fit in shared memory
+    // ThermalLangevin: friction gamma_0 and injected normals xi[((step - noise_step0) * T + traj) * B + mode]
+    double langevin_gamma;
+    const double* noise;
+    int64_t noise_step0;
     // draws (injected): xi[(step - draws_step0) * T + traj]
     const double* draws;
     int64_t draws_step0;

@@ -32,6 +32,7 @@ bool select_kernels(const nqcb200_config& c, KernelSet& out, std::string& why) {
     switch (c.method) {
         case NQCB200_METHOD_CLASSICAL: return select_classical(c, out, why);
         case NQCB200_METHOD_NRPMD: return select_nrpmd(c, out, why);
+        case NQCB200_METHOD_THERMAL_LANGEVIN: return select_langevin(c, out, why);
         case NQCB200_METHOD_FSSH:
         case NQCB200_METHOD_EHRENFEST:
             if (c.nbeads > 1) return select_ring_density(c, out, why);
@@ -194,6 +195,8 @@ struct nqcb200_handle {
     int64_t draws_cap = 0;
     int64_t draws_nsteps = 0;
     double* d_state_draw = nullptr;
+    double* d_noise = nullptr;      // ThermalLangevin injected normals
+    int64_t noise_cap = 0, noise_nsteps = 0;
     bool user_gauge = false;
     int zcopies = 1;
     int64_t step_count = 0, nsave_done = 0;
@@ -445,6 +448,7 @@ int nqcb200_create(const nqcb200_config* cfg, nqcb200_handle** out) {
     kp.mean_field = (c.method == NQCB200_METHOD_EHRENFEST_NA) ? 1 : 0;
     if (kp.mean_field) kp.disable_hopping = 1;
     kp.observables = c.observables; kp.seed = c.seed; kp.dt = c.dt; kp.t0 = c.t0;
+    kp.langevin_gamma = c.nrpmd_gamma;     // the config's one gamma field: NRPMD zero-point parameter / Langevin friction
     kp.omega_n = B * c.temperature; kp.nrpmd_gamma = c.nrpmd_gamma; kp.edc_C = kp.mean_field ? 0.0 : c.edc_C;
     std::memcpy(kp.params, c.params, sizeof(kp.params));
     {
@@ -513,8 +517,8 @@ int nqcb200_create(const nqcb200_config* cfg, nqcb200_handle** out) {
             const double a = 0.5 * wk * c.dt, den = 1.0 + a * a;
             cay[4 * k + 0] = (1.0 - a * a) / den; cay[4 * k + 1] = c.dt / den;
             cay[4 * k + 2] = -wk * wk * c.dt / den; cay[4 * k + 3] = (1.0 - a * a) / den;
-            if (c.method == NQCB200_METHOD_NRPMD) {
-                // RingPolymerMInt uses half = true (ringpolymer_mint.jl:22): principal square root of the
+            if (c.method == NQCB200_METHOD_NRPMD || c.method == NQCB200_METHOD_THERMAL_LANGEVIN) {
+                // RingPolymerMInt and BCOCB (bcocb.jl:30) use half = true (ringpolymer_mint.jl:22): principal square root of the
                 // unimodular 2x2, sqrt(M) = (M + I) / sqrt(tr M + 2)
                 const double sq = std::sqrt(cay[4 * k + 0] + cay[4 * k + 3] + 2.0);
                 cay[4 * k + 0] = (cay[4 * k + 0] + 1.0) / sq; cay[4 * k + 3] = (cay[4 * k + 3] + 1.0) / sq;
@@ -672,6 +676,26 @@ int nqcb200_set_draws(nqcb200_handle* h, const double* xi, int64_t nsteps) {
     return NQCB200_OK;
 }
 
+int nqcb200_set_noise(nqcb200_handle* h, const double* xi, int64_t nsteps) {
+    if (!h || !xi || nsteps < 0) return NQCB200_ERR_INVALID;
+    if (h->cfg.method != NQCB200_METHOD_THERMAL_LANGEVIN) { h->err = "injected noise exists only for ThermalLangevin"; return NQCB200_ERR_INVALID; }
+    NQ_CUDA(h, cudaSetDevice(h->cfg.device));
+    const int64_t need = nsteps * h->cfg.ntraj * h->cfg.nbeads;
+    if (need > h->noise_cap) {
+        void* p = nullptr;
+        NQ_CUDA(h, cudaMalloc(&p, sizeof(double) * std::max<int64_t>(need, 1)));
+        h->allocs.push_back(p);
+        h->d_noise = (double*)p;
+        h->noise_cap = need;
+    }
+    NQ_CUDA(h, cudaMemcpyAsync(h->d_noise, xi, sizeof(double) * need, cudaMemcpyHostToDevice, h->stream));
+    NQ_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->kp.noise = h->d_noise;
+    h->kp.noise_step0 = h->step_count;
+    h->noise_nsteps = nsteps;
+    return NQCB200_OK;
+}
+
 int nqcb200_run(nqcb200_handle* h, int64_t nsteps) {
     if (!h || nsteps < 0) return NQCB200_ERR_INVALID;
     if (!h->has_state) { h->err = "run before set_state"; return NQCB200_ERR_STATE; }
@@ -681,6 +705,11 @@ int nqcb200_run(nqcb200_handle* h, int64_t nsteps) {
         if (!h->kp.draws || h->step_count < h->kp.draws_step0 ||
             h->step_count + nsteps > h->kp.draws_step0 + h->draws_nsteps) {
             h->err = "not enough injected draws for this run"; return NQCB200_ERR_STATE;
+        }
+    }
+    if (c.method == NQCB200_METHOD_THERMAL_LANGEVIN && c.rng == NQCB200_RNG_INJECTED) {
+        if (!h->kp.noise || h->step_count < h->kp.noise_step0 || h->step_count + nsteps > h->kp.noise_step0 + h->noise_nsteps) {
+            h->err = "not enough injected noise for this run"; return NQCB200_ERR_STATE;
         }
     }
     h->last_launches = 0;

@@ -48,8 +48,9 @@ NQ_D constexpr int rt_bitrev(int x) {
 }
 
 // to-normal-modes -> Cayley -> back for one ring polymer held in registers (see FreeRingPolymer for the algebra)
-template <int NB>
-NQ_D void rt_free_step(const RtTables<NB>& tb, double (&zr)[NB], double (&zi)[NB]) {
+template <int NB, bool NOISE = false>
+NQ_D void rt_free_step(const RtTables<NB>& tb, double (&zr)[NB], double (&zi)[NB], const double* xi_ = nullptr,
+                       const double* bn = nullptr, const double* dn = nullptr) {
     constexpr int LOG = rt_log2<NB>();
 #pragma unroll
     for (int s = 0; s < LOG; ++s) {          // DIF: natural in, bit-reversed out
@@ -84,6 +85,19 @@ NQ_D void rt_free_step(const RtTables<NB>& tb, double (&zr)[NB], double (&zi)[NB
             const double cr = tb.al[2 * kp], ci = tb.al[2 * kp + 1], dr = tb.be[2 * kp], di = tb.be[2 * kp + 1];
             zr[ip] = fma(cr, yr, fma(-ci, yi, fma(dr, xr, di * xi)));
             zi[ip] = fma(cr, yi, fma(ci, yr, fma(-dr, xi, di * xr)));
+        }
+        if (NOISE) {      // Z'_k += (b_k + i d_k) N_k, N_k = n_lo + i n_hi for the pair (lo, NB - lo), real for k = 0, NB/2
+            const int lo = (k <= NB - k) ? k : NB - k;          // mode with the cosine: min(k, NB - k); k = 0 -> 0
+            const int hi = (NB - lo) % NB;
+            const double b0 = bn[lo], d0 = dn[lo];
+            if (ip == i) {
+                zr[i] = fma(b0, xi_[k], zr[i]); zi[i] = fma(d0, xi_[k], zi[i]);
+            } else {
+                const double nc = xi_[lo], ns = xi_[hi];
+                const double sgn = (k == lo) ? 1.0 : -1.0;      // position i holds mode lo (+) or NB - lo (conjugate)
+                zr[i] += b0 * nc - sgn * d0 * ns;  zi[i] += sgn * b0 * ns + d0 * nc;
+                zr[ip] += b0 * nc + sgn * d0 * ns; zi[ip] += -sgn * b0 * ns + d0 * nc;
+            }
         }
     }
 #pragma unroll
@@ -730,6 +744,103 @@ __global__ void __launch_bounds__(kRtThreads, 2) classical_tpt_fft_kernel(const 
         rt_free_step<NB>(tb, r, v);                                                               // C
 #pragma unroll
         for (int b = 0; b < NB; ++b) v[b] = fma(-hm, M::gradient_dof(p.params, r[b]), v[b]);     // B (classical.jl:63-67)
+        if ((step + 1) % p.save_every == 0) {
+            const int64_t isave = (step + 1) / p.save_every;
+            if (isave < p.nsave) {
+                const uint32_t obs = p.observables;
+                double rsum = 0.0, vsum = 0.0, mv2 = 0.0, spr = 0.0, pot = 0.0;
+#pragma unroll
+                for (int b = 0; b < NB; ++b) {
+                    rsum += r[b]; vsum += v[b];
+                    mv2 = fma(mass * v[b], v[b], mv2);
+                    pot += M::potential_dof(p.params, r[b]);
+                    const double d = r[(b + NB - 1) % NB] - r[b];
+                    spr = fma(mass * d, d, spr);
+                }
+                Emitter em{p, traj, valid, (int)isave, red, 0};
+                const double kin = 0.5 * mv2;
+                if (obs & (1u << NQCB200_OBS_KINETIC)) em.emit(NQCB200_OBS_KINETIC, 0, kin);
+                if (obs & (1u << NQCB200_OBS_POTENTIAL)) em.emit(NQCB200_OBS_POTENTIAL, 0, pot);
+                if (obs & (1u << NQCB200_OBS_TOTAL_ENERGY)) em.emit(NQCB200_OBS_TOTAL_ENERGY, 0, kin + pot + 0.5 * p.omega_n * p.omega_n * spr);
+                if (obs & (1u << NQCB200_OBS_POSITION)) em.emit(NQCB200_OBS_POSITION, 0, rsum / NB);
+                if (obs & (1u << NQCB200_OBS_VELOCITY)) em.emit(NQCB200_OBS_VELOCITY, 0, vsum / NB);
+            }
+        }
+    }
+    if (valid) {
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            p.r[(int64_t)b * T + traj] = r[b];
+            p.v[(int64_t)b * T + traj] = v[b];
+            p.acc[(int64_t)b * T + traj] = -M::gradient_dof(p.params, r[b]) / mass;
+        }
+    }
+}
+
+// RingPolymerSimulation{ThermalLangevin} + BCOCB (bcocb.jl:95-120): B, to normal modes, C(1/2), O, C(1/2), back, force, B,
+// on the register-resident ring polymer of classical_tpt_fft_kernel.  In the spectrum Z_k of z = r + i v (see
+// FreeRingPolymer) the deterministic part C(1/2) diag(1, c1_k) C(1/2) is again one real 2x2 matrix per frequency, i.e.
+// another (alpha_k, beta_k) pair, and the O-step noise n_k = c2_k sigma xi_k of the ORTHONORMAL real normal modes enters
+// as Z'_k += (b_k + i d_k) N_k with [[a,b],[c,d]] the half Cayley step and
+//     N_0 = sqrt(NB) n_0,  N_{NB/2} = sqrt(NB) n_{NB/2},  N_k = sqrt(NB/2) (n_k + i n_{NB-k}) = conj(N_{NB-k})  (0 < k < NB/2)
+// (R_k = sqrt(NB/2) (y_k + i y_{NB-k}) relates the DFT to the orthonormal cos / sin modes of RingPolymerArrays).
+// PILE friction (FrictionCache, bcocb.jl:78-87): gamma_0 = gamma, gamma_k = 2 omega_k, c1 = exp(-gamma_k dt),
+// c2 = sqrt(1 - c1^2), sigma = sqrt(NB kT / m) (steps.jl:109-124).
+template <class M, int NB>
+__global__ void __launch_bounds__(kRtThreads, 2) langevin_tpt_fft_kernel(const __grid_constant__ KParams p) {
+    static_assert(NB >= 2 && (NB & (NB - 1)) == 0, "power-of-two bead count");
+    __shared__ double red[2 * (kRtThreads / 32)];
+    __shared__ double s_tab[7 * NB];      // twr[NB/2] twi[NB/2] al[2NB] be[2NB] bn[NB] dn[NB]
+    const int tid = threadIdx.x;
+    int64_t traj = (int64_t)blockIdx.x * kRtThreads + tid;
+    const bool valid = traj < p.ntraj;
+    if (!valid) traj = p.ntraj - 1;
+    const int64_t T = p.ntraj;
+    const double mass = p.masses[0], hdt = 0.5 * p.dt, hm = hdt / mass;
+    const double sigma = sqrt(p.omega_n / mass);          // omega_n = NB kT: ring-polymer temperature
+    const double pi = 3.14159265358979323846;
+    for (int j = tid; j < NB; j += kRtThreads) {
+        if (j < NB / 2) {
+            double si, co;
+            sincospi(-2.0 * (double)j / (double)NB, &si, &co);
+            s_tab[j] = co; s_tab[NB / 2 + j] = si;
+        }
+        const double a = p.cayley[4 * j + 0], b = p.cayley[4 * j + 1], c = p.cayley[4 * j + 2], d = p.cayley[4 * j + 3];   // half step
+        const double wk = 2.0 * p.omega_n * sin(j * pi / NB);
+        const double gam = (j == 0) ? p.langevin_gamma : 2.0 * wk;
+        const double c1 = exp(-gam * p.dt), c2 = sqrt(1.0 - c1 * c1);
+        // S diag(1, c1) S
+        const double ma = a * a + b * c1 * c, mb = a * b + b * c1 * d, mc = c * a + d * c1 * c, md = c * b + d * c1 * d;
+        const double inv = 0.5 / NB;
+        s_tab[NB + 2 * j] = (ma + md) * inv; s_tab[NB + 2 * j + 1] = (mc - mb) * inv;
+        s_tab[3 * NB + 2 * j] = (ma - md) * inv; s_tab[3 * NB + 2 * j + 1] = (mc + mb) * inv;
+        const double scale = ((j == 0 || 2 * j == NB) ? sqrt((double)NB) : sqrt(0.5 * NB)) * c2 * sigma / NB;
+        s_tab[5 * NB + j] = b * scale; s_tab[6 * NB + j] = d * scale;
+    }
+    __syncthreads();
+    RtTables<NB> tb{s_tab, s_tab + NB / 2, s_tab + NB, s_tab + 3 * NB};
+    const double* bn = s_tab + 5 * NB;
+    const double* dn = s_tab + 6 * NB;
+    double r[NB], v[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) { r[b] = p.r[(int64_t)b * T + traj]; v[b] = p.v[(int64_t)b * T + traj]; }
+#pragma unroll 1
+    for (int is = 0; is < p.nsteps; ++is) {
+        const int64_t step = p.step0 + is;
+        double xi[NB];      // one standard normal per normal mode (mode index k)
+        if (p.rng == NQCB200_RNG_INJECTED) {
+#pragma unroll
+            for (int k = 0; k < NB; ++k) xi[k] = p.noise[((step - p.noise_step0) * T + traj) * NB + k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < NB; k += 2)
+                philox_normal2(p.seed, (uint64_t)(p.traj_offset + traj), (uint64_t)step * (NB / 2) + k / 2, xi[k], xi[k + 1], 3u);
+        }
+#pragma unroll
+        for (int b = 0; b < NB; ++b) v[b] = fma(-hm, M::gradient_dof(p.params, r[b]), v[b]);     // B
+        rt_free_step<NB, true>(tb, r, v, xi, bn, dn);                                             // C O C
+#pragma unroll
+        for (int b = 0; b < NB; ++b) v[b] = fma(-hm, M::gradient_dof(p.params, r[b]), v[b]);     // B
         if ((step + 1) % p.save_every == 0) {
             const int64_t isave = (step + 1) / p.save_every;
             if (isave < p.nsave) {

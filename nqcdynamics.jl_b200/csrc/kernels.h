@@ -35,6 +35,7 @@ bool select_density_spinboson(const nqcb200_config& c, KernelSet& out, std::stri
 bool select_ring_density(const nqcb200_config& c, KernelSet& out, std::string& why);
 bool select_classical(const nqcb200_config& c, KernelSet& out, std::string& why);
 bool select_nrpmd(const nqcb200_config& c, KernelSet& out, std::string& why);
+bool select_langevin(const nqcb200_config& c, KernelSet& out, std::string& why);
 bool select_iesh(const nqcb200_config& c, KernelSet& out, std::string& why);
 
 }  // namespace nq

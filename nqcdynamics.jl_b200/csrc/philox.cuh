@@ -40,9 +40,9 @@ NQ_HD double philox_uniform(uint64_t seed, uint64_t gid, uint64_t step, uint32_t
 
 // Two independent standard normals per block (Box-Muller), used by the device-side initial-condition sampler
 // (nqcb200_sample_state): counter = (global trajectory id, component, purpose 2).
-NQ_HD void philox_normal2(uint64_t seed, uint64_t gid, uint64_t comp, double& z0, double& z1) {
+NQ_HD void philox_normal2(uint64_t seed, uint64_t gid, uint64_t comp, double& z0, double& z1, uint32_t purpose = 2u) {
     uint32_t w[4];
-    philox4x32(seed, gid, comp, 2u, w);
+    philox4x32(seed, gid, comp, purpose, w);
     const double u1 = (double)(((((uint64_t)w[0] << 32) | w[1]) >> 11) + 1ull) * (1.0 / 9007199254740992.0);   // (0, 1]
     const double u2 = (double)((((uint64_t)w[2] << 32) | w[3]) >> 11) * (1.0 / 9007199254740992.0);           // [0, 1)
     const double rad = sqrt(-2.0 * log(u1));

@@ -73,6 +73,36 @@ bool select_classical(const nqcb200_config& c, KernelSet& out, std::string& why)
     return ok;
 }
 
+namespace {
+template <class M, int NB>
+void set_langevin(KernelSet& k, const char* name) {
+    k.step = langevin_tpt_fft_kernel<M, NB>;
+    k.init = classical_ring_init_kernel<M, NB>;
+    k.L = NB; k.DPL = 1; k.name = name;
+    k.step_L = 1; k.step_block = kRtThreads; k.step_smem = 0;
+}
+template <class M>
+bool pick_langevin(int B, KernelSet& out, const char* name) {
+    switch (B) {
+        case 2: set_langevin<M, 2>(out, name); return true;
+        case 4: set_langevin<M, 4>(out, name); return true;
+        case 8: set_langevin<M, 8>(out, name); return true;
+        case 16: set_langevin<M, 16>(out, name); return true;
+        case 32: set_langevin<M, 32>(out, name); return true;
+    }
+    return false;
+}
+}  // namespace
+
+bool select_langevin(const nqcb200_config& c, KernelSet& out, std::string& why) {
+    if (c.ndofs != 1) { why = "ThermalLangevin kernels are instantiated for ndofs == 1"; return false; }
+    bool ok = false;
+    if (c.model == NQCB200_MODEL_HARMONIC) ok = pick_langevin<ModelT<NQCB200_MODEL_HARMONIC>>(c.nbeads, out, "langevin_harmonic");
+    else if (c.model == NQCB200_MODEL_FREE) ok = pick_langevin<ModelT<NQCB200_MODEL_FREE>>(c.nbeads, out, "langevin_free");
+    if (!ok) why = "ThermalLangevin (BCOCB) needs a classical model and nbeads in {2,4,8,16,32}";
+    return ok;
+}
+
 bool select_nrpmd(const nqcb200_config& c, KernelSet& out, std::string& why) {
     if (c.ndofs != 1) { why = "NRPMD kernels are instantiated for ndofs == 1"; return false; }
     bool ok = false;

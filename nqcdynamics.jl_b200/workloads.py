@@ -83,6 +83,8 @@ class Workload:
                   bath_b=self.model.bath_b, save_every=self.save_every, nsave=self.nsave,
                   observables=self.observables, temperature=self.temperature, rescaling=self.rescaling,
                   nelectrons=self.model.nelectrons)
+        if hasattr(self, "gamma"):
+            kw["nrpmd_gamma"] = self.gamma
         kw.update(extra)
         return kw
 
@@ -177,6 +179,22 @@ def _rpmd_harmonic() -> Workload:
                     device_spec=([(0.0, float(x)) for x in sr], [(0.0, float(sv))] * B, True))
 
 
+def _langevin_harmonic() -> Workload:
+    # RingPolymerSimulation{ThermalLangevin}(Atoms(:H), Harmonic(m, w), 32; gamma, T = 300 K) -- the
+    # thermostatted run that GENERATES the C3 / C5 thermal distributions (BCOCB), started cold at the minimum
+    base = _rpmd_harmonic()
+    B = base.nbeads
+
+    def sample(rng, T):
+        return {"r": np.zeros((T, B, 1)), "v": np.zeros((T, B, 1))}
+    wl = Workload("langevin_harmonic32", "ThermalLangevin (BCOCB, PILE) 32 beads, Harmonic(m_H, w=0.005), 300 K, gamma=0.002, dt=2.5, 10^4 steps, saveat 100",
+                  base.model, A.METHOD_THERMAL_LANGEVIN, base.masses, 2.5, 10000, 100, base.observables, 1 << 18,
+                  base.flops_per_traj_step + 4 * B, sample, nbeads=B, temperature=base.temperature,
+                  device_spec=([0.0] * B, [0.0] * B, False))
+    wl.gamma = 0.002
+    return wl
+
+
 def _rpsh_morse() -> Workload:
     # C5: RingPolymerSimulation{FSSH}(Atoms(20000), ThreeStateMorse(), 16; T = 300 K)
     B, m = 16, 20000.0
@@ -246,6 +264,7 @@ def get(name: str) -> Workload:
         "rpmd_harmonic32": _rpmd_harmonic,
         "rpsh_morse3_16": _rpsh_morse,
         "nrpmd_morse3_16": _nrpmd_morse,
+        "langevin_harmonic32": _langevin_harmonic,
     }
     if name not in table:
         raise KeyError(f"unknown workload {name!r}; available: {sorted(table)}")
@@ -253,5 +272,5 @@ def get(name: str) -> Workload:
 
 
 NAMES = ["tully1_fssh", "spinboson_debye100_fssh", "spinboson_debye100_ehrenfest", "rpmd_harmonic32", "rpsh_morse3_16",
-         "nrpmd_morse3_16",
+         "nrpmd_morse3_16", "langevin_harmonic32",
          "iesh_anderson_holstein_m100", "iesh_anderson_holstein_m200", "iesh_anderson_holstein_m30"]

@@ -41,8 +41,8 @@ inline double philox_uniform(uint64_t seed, uint64_t gid, uint64_t step, uint32_
 
 // Two standard normals per Philox block (Box-Muller): the stream of nqcb200_sample_state (include/nqcb200.h),
 // counter = (global trajectory id, component, purpose 2); first normal -> position, second -> velocity.
-inline void philox_normal2(uint64_t seed, uint64_t gid, uint64_t comp, double& z0, double& z1) {
-    uint32_t c[4] = {(uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)comp, ((uint32_t)(comp >> 32) & 0x00FFFFFFu) | (2u << 24)};
+inline void philox_normal2(uint64_t seed, uint64_t gid, uint64_t comp, double& z0, double& z1, uint32_t purpose = 2u) {
+    uint32_t c[4] = {(uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)comp, ((uint32_t)(comp >> 32) & 0x00FFFFFFu) | (purpose << 24)};
     philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
     const double u1 = (double)(((((uint64_t)c[0] << 32) | c[1]) >> 11) + 1ull) * (1.0 / 9007199254740992.0);
     const double u2 = (double)((((uint64_t)c[2] << 32) | c[3]) >> 11) * (1.0 / 9007199254740992.0);
@@ -67,6 +67,8 @@ struct nqco_handle {
     vec obs_traj;                // per trajectory: [traj][obs-packed as obs_sum]
     vec draws;                   // injected: [step][traj]
     int64_t draws_first_step = 0, draws_nsteps = 0;
+    vec noise;                   // ThermalLangevin injected normals: [step][traj][B*D]
+    int64_t noise_first_step = 0, noise_nsteps = 0;
     vec Zref;                    // optional gauge reference
     int64_t zref_per_traj = 0;
     int64_t nsave_done = 0;
@@ -221,9 +223,10 @@ int nqco_create(const nqcb200_config* cfg, nqco_handle** out) {
     S.cfg.masses = nullptr; S.cfg.bath_a = nullptr; S.cfg.bath_b = nullptr;
     S.omega_n = S.B * cfg->temperature;
     S.U = normal_mode_matrix(S.B);
-    S.cayley = cayley_propagator(S.B, S.omega_n, cfg->dt, cfg->method == NQCB200_METHOD_NRPMD);
+    S.cayley = cayley_propagator(S.B, S.omega_n, cfg->dt,
+                                 cfg->method == NQCB200_METHOD_NRPMD || cfg->method == NQCB200_METHOD_THERMAL_LANGEVIN);
     bool quantum = !S.model.classical();
-    if ((cfg->method == NQCB200_METHOD_CLASSICAL) == quantum) {
+    if ((cfg->method == NQCB200_METHOD_CLASSICAL || cfg->method == NQCB200_METHOD_THERMAL_LANGEVIN) == quantum) {
         // classical method on a quantum model would route through the Fermi-weighted force
         // (rpmdef.jl:30-57) which is out of scope; quantum method on a classical model is invalid
         g_err = "method/model combination unsupported"; delete h; return NQCB200_ERR_UNSUPPORTED;
@@ -394,6 +397,15 @@ int nqco_set_draws(nqco_handle* h, const double* xi, int64_t nsteps) {
     return NQCB200_OK;
 }
 
+int nqco_set_noise(nqco_handle* h, const double* xi, int64_t nsteps) {
+    if (!h || !xi || nsteps < 0) return NQCB200_ERR_INVALID;
+    if (h->S.cfg.method != NQCB200_METHOD_THERMAL_LANGEVIN) return NQCB200_ERR_INVALID;
+    h->noise.assign(xi, xi + (size_t)nsteps * h->traj.size() * h->S.B * h->S.D);
+    h->noise_first_step = h->traj.empty() ? 0 : h->traj[0].step;
+    h->noise_nsteps = nsteps;
+    return NQCB200_OK;
+}
+
 int nqco_run(nqco_handle* h, int64_t nsteps) {
     if (!h) return NQCB200_ERR_INVALID;
     if (!h->has_state) { h->err = "run before set_state"; return NQCB200_ERR_STATE; }
@@ -425,6 +437,22 @@ int nqco_run(nqco_handle* h, int64_t nsteps) {
                             xi = h->draws[(size_t)(tr.step - h->draws_first_step) * T + t];
                         else
                             xi = philox_uniform(S.cfg.seed, S.cfg.traj_offset + t, (uint64_t)tr.step, 0);
+                    }
+                    if (S.cfg.method == NQCB200_METHOD_THERMAL_LANGEVIN) {
+                        const size_t nb = (size_t)S.B * S.D;
+                        tr.noise.resize(nb);
+                        if (S.cfg.rng == NQCB200_RNG_INJECTED) {
+                            if (tr.step < h->noise_first_step || tr.step >= h->noise_first_step + h->noise_nsteps)
+                                throw std::runtime_error("not enough injected noise");
+                            const double* src = &h->noise[((size_t)(tr.step - h->noise_first_step) * T + t) * nb];
+                            std::copy(src, src + nb, tr.noise.begin());
+                        } else {
+                            for (size_t k = 0; k < nb; k += 2) {     // same stream as the CUDA kernel (purpose 3)
+                                double z0, z1;
+                                philox_normal2(S.cfg.seed, (uint64_t)(S.cfg.traj_offset + t), (uint64_t)tr.step * (nb / 2) + k / 2, z0, z1, 3u);
+                                tr.noise[k] = z0; if (k + 1 < nb) tr.noise[k + 1] = z1;
+                            }
+                        }
                     }
                     step(S, tr, xi);
                 }

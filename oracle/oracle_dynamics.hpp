@@ -65,6 +65,7 @@ struct Trajectory {
     int64_t step = 0;
     Counters cnt;
     vec last_nac, last_eig, last_Z;
+    vec noise;            // ThermalLangevin: the B*D standard normals of the current step (W.dW / sqrt(dt))
 };
 
 inline void centroid_of(const Setup& S, const vec& x, double* out) {
@@ -123,7 +124,8 @@ inline void acceleration(const Setup& S, Trajectory& T, const vec& r, const cvec
                             for (int nn = 0; nn < n; ++nn)
                                 f -= a[nn + (size_t)n * m] * (T.sigma[nn + (size_t)n * e] * std::conj(T.sigma[m + (size_t)n * e])).real();
                 } break;
-                case NQCB200_METHOD_CLASSICAL: f = -c.dV[I]; break;
+                case NQCB200_METHOD_CLASSICAL:
+                case NQCB200_METHOD_THERMAL_LANGEVIN: f = -c.dV[I]; break;
                 default: throw std::runtime_error("acceleration: method");
             }
             T.k[I + (size_t)D * b] = f / S.masses[I];
@@ -341,6 +343,37 @@ inline void step_classical(const Setup& S, Trajectory& T) {
     vec vtmp(N), r(T.r);
     for (size_t i = 0; i < N; ++i) vtmp[i] = std::fma(dt / 2, T.k[i], T.v[i]);
     to_normal_modes(S, vtmp); to_normal_modes(S, r);
+    step_C(S, vtmp, r);
+    from_normal_modes(S, vtmp); from_normal_modes(S, r);
+    update_all_caches(S, T, r);
+    acceleration(S, T, r, none);
+    for (size_t i = 0; i < N; ++i) T.v[i] = std::fma(dt / 2, T.k[i], vtmp[i]);
+    T.r = r;
+}
+
+// ---- one step: RingPolymerSimulation{ThermalLangevin}, BCOCB  bcocb.jl:95-120 ---------------------
+// B, to normal modes, C(1/2), O, C(1/2), from normal modes, force, B.  FrictionCache bcocb.jl:78-87: gamma = [gamma_0,
+// 2 sqrt(2 springs_k)] = [gamma_0, 2 omega_k], c1 = exp(-dt gamma), c2 = sqrt(1 - c1^2); O-step steps.jl:109-124:
+// v_mode = c1 v_mode + c2 sqrt(T_rp / m) xi with T_rp = nbeads kT (get_ring_polymer_temperature, simulations.jl:104).
+inline void step_langevin_bcocb(const Setup& S, Trajectory& T) {
+    const double dt = S.cfg.dt;
+    const int B = S.B, D = S.D;
+    const size_t N = (size_t)B * D;
+    const double pi = 3.14159265358979323846;
+    cvec none;
+    vec vtmp(N), r(T.r);
+    for (size_t i = 0; i < N; ++i) vtmp[i] = std::fma(dt / 2, T.k[i], T.v[i]);
+    to_normal_modes(S, vtmp); to_normal_modes(S, r);
+    step_C(S, vtmp, r);                       // S.cayley holds the half step for this method
+    for (int b = 0; b < B; ++b) {
+        const double wk = 2.0 * S.omega_n * std::sin(b * pi / B);
+        const double gam = (b == 0) ? S.cfg.nrpmd_gamma : 2.0 * wk;
+        const double c1 = std::exp(-gam * dt), c2 = std::sqrt(1.0 - c1 * c1);
+        for (int d = 0; d < D; ++d) {
+            const double sigma = std::sqrt(S.omega_n / S.masses[d]);      // omega_n = nbeads kT
+            vtmp[d + (size_t)D * b] = c1 * vtmp[d + (size_t)D * b] + c2 * sigma * T.noise[d + (size_t)D * b];
+        }
+    }
     step_C(S, vtmp, r);
     from_normal_modes(S, vtmp); from_normal_modes(S, r);
     update_all_caches(S, T, r);
@@ -630,6 +663,7 @@ inline void step(const Setup& S, Trajectory& T, double xi) {
         case NQCB200_METHOD_FSSH:
         case NQCB200_METHOD_EHRENFEST: step_density_method(S, T, xi); break;
         case NQCB200_METHOD_CLASSICAL: step_classical(S, T); break;
+        case NQCB200_METHOD_THERMAL_LANGEVIN: step_langevin_bcocb(S, T); break;
         case NQCB200_METHOD_NRPMD: step_nrpmd(S, T); break;
         case NQCB200_METHOD_IESH:
         case NQCB200_METHOD_EHRENFEST_NA: step_iesh(S, T, xi); break;
@@ -746,6 +780,7 @@ inline double potential_energy(const Setup& S, const Trajectory& T) {
             for (int e = 0; e < S.ne; ++e)
                 for (int i = 0; i < n; ++i) pot += T.bead[0].w[i] * std::norm(T.sigma[i + (size_t)n * e]);
             break;
+        case NQCB200_METHOD_THERMAL_LANGEVIN:
         case NQCB200_METHOD_CLASSICAL:  // DynamicsUtils.jl:141-151
             for (int b = 0; b < S.B; ++b) pot += T.bead[b].V[0];
             break;
