@@ -10,7 +10,7 @@ from nqcdynamics_jl_b200.engine import Engine
 A = nq._abi
 rng = np.random.default_rng(0)
 for name, T, nsteps in [("spinboson_debye100_fssh", 300, 7), ("spinboson_debye100_ehrenfest", 131, 5), ("tully1_fssh", 333, 50),
-                        ("rpmd_harmonic32", 70, 20), ("rpsh_morse3_16", 150, 12), ("nrpmd_morse3_16", 40, 10)]:
+                        ("rpmd_harmonic32", 70, 20), ("rpsh_morse3_16", 150, 12), ("nrpmd_morse3_16", 40, 10), ("langevin_harmonic32", 90, 12)]:
     wl = workloads.get(name)
     obs = wl.observables | (1 << A.OBS_KINETIC) | (1 << A.OBS_TOTAL_ENERGY) if name.startswith("spinboson") else wl.observables
     for per_traj in (0, 1):
