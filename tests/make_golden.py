@@ -53,15 +53,34 @@ def cases():
                                        (1 << A.OBS_DISCRETE_STATE)), nsteps=40,
                            r=rng.normal(12.0, 4.0, (T, 1, 1)), v=-np.abs(rng.standard_normal((T, 1, 1))) * 8e-3, state0="iesh",
                            draw_scale=2e-4)
+    # SURVEY 8f additions (appended: the cases above keep their seeded inputs)
+    out["ehrenfest_na_m30"] = dict(model=ah, kw=dict(method=A.METHOD_EHRENFEST_NA, masses=[2000.0], dt=5.0, save_every=5, nsave=9,
+                                   observables=(1 << A.OBS_ADIABATIC_POP) | (1 << A.OBS_TOTAL_ENERGY) | (1 << A.OBS_POSITION)),
+                                   nsteps=40, r=rng.normal(12.0, 4.0, (T, 1, 1)), v=-np.abs(rng.standard_normal((T, 1, 1))) * 8e-3,
+                                   state0="na")
+    out["rpsh_morse3_10"] = dict(model=nq.ThreeStateMorse(), kw=dict(method=A.METHOD_FSSH, masses=[20000.0], dt=1.0, nbeads=10,
+                                 temperature=9.5e-4, save_every=20, nsave=11, observables=ALL_POP_OBS), nsteps=200,
+                                 r=rng.normal(2.1, 0.1, (T, 10, 1)), v=np.sqrt(9.5e-4 * 10 / 20000) * rng.standard_normal((T, 10, 1)),
+                                 state0=0)
+    out["langevin_harmonic8"] = dict(model=nq.Harmonic(m=1837.47, ω=0.005), kw=dict(method=A.METHOD_THERMAL_LANGEVIN, masses=[1837.47],
+                                     dt=2.5, nbeads=8, temperature=9.5e-4, nrpmd_gamma=2e-3, save_every=20, nsave=11,
+                                     observables=CLASSICAL_OBS), nsteps=200, r=0.2 * rng.standard_normal((T, 8, 1)),
+                                     v=np.sqrt(9.5e-4 * 8 / 1837.47) * rng.standard_normal((T, 8, 1)), state0=None, noise=True)
     return out, T, rng
 
 
-def run_case(make, case, T, draws, sdraw):
+def run_case(make, case, T, draws, sdraw, noise=None):
     kw = model_config(case["model"], ntraj=T, rng=A.RNG_INJECTED, **case["kw"])
     cfg, keep = A.make_config(**kw)
     h = make(cfg, keep)
     if case["state0"] is None:
         h.set_state(case["r"], case["v"])
+        if noise is not None:
+            h.set_noise(noise)
+    elif case["state0"] == "na":
+        n, ne = case["model"].nstates, case["model"].nelectrons
+        psi = np.zeros((T, ne, n)); psi[:, np.arange(ne), np.arange(ne)] = 1.0
+        h.set_state(case["r"], case["v"], psi, None, None)
     elif case["state0"] == "iesh":
         n, ne = case["model"].nstates, case["model"].nelectrons
         psi = np.zeros((T, ne, n)); psi[:, np.arange(ne), np.arange(ne)] = 1.0
@@ -87,9 +106,11 @@ if __name__ == "__main__":
     only = set(sys.argv[1:])
     for name, case in cs.items():
         draws = rng.random((case["nsteps"], T)) * case.get("draw_scale", 1.0); sdraw = rng.random(T)
+        noise = rng.standard_normal((case["nsteps"], T, case["kw"].get("nbeads", 1))) if case.get("noise") else None
         if only and name not in only:
             continue
-        res = run_case(lambda c, k: oracle.OracleEngine(c, k), case, T, draws, sdraw)
+        res = run_case(lambda c, k: oracle.OracleEngine(c, k), case, T, draws, sdraw, noise)
+        extra = {"noise": noise} if noise is not None else {}
         np.savez_compressed(os.path.join(HERE, "golden", f"engine_{name}.npz"), draws=draws, sdraw=sdraw,
-                            r0=case["r"], v0=case["v"], **res)
+                            r0=case["r"], v0=case["v"], **extra, **res)
         print(name, {k: v.shape for k, v in res.items()})
