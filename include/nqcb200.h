@@ -72,7 +72,7 @@ enum nqcb200_method {
     /* RingPolymerSimulation{ThermalLangevin} + BCOCB (langevin.jl:67-82, bcocb.jl:78-120, steps.jl:109-124): thermostatted
      * ring-polymer dynamics, the sampler of the RPMD / RPSH thermal distributions.  PILE friction
      * gamma_0 = cfg.nrpmd_gamma (the struct's one gamma field), gamma_k = 2 omega_k; O-step in normal modes between two
-     * half Cayley steps.  Classical (single-surface) models, nbeads a power of two >= 2.  Noise: Philox normals
+     * half Cayley steps.  Classical (single-surface) models, nbeads >= 2.  Noise: Philox normals
      * (purpose 3) keyed by (seed; trajectory, step, mode), or injected with nqcb200_set_noise.       */
     NQCB200_METHOD_THERMAL_LANGEVIN = 7
 };

@@ -638,7 +638,9 @@ __global__ void __launch_bounds__(kRtThreads) ring_tpt_init_kernel(const __grid_
 }
 
 // Classical RPMD (BCB, bcb.jl:81-116) for any nbeads: one thread per trajectory, dense normal-mode product.
-template <class M>
+// LANGEVIN: BCOCB (bcocb.jl:95-120) -- the Cayley table then holds the HALF step and the O-step of the PILE thermostat
+// acts on the normal-mode velocities between the two halves.
+template <class M, bool LANGEVIN = false>
 __global__ void __launch_bounds__(kRtThreads) classical_tpt_step_kernel(const __grid_constant__ KParams p) {
     extern __shared__ __align__(16) double rt_sm[];
     __shared__ double red[2 * (kRtThreads / 32)];
@@ -673,8 +675,26 @@ __global__ void __launch_bounds__(kRtThreads) classical_tpt_step_kernel(const __
                 a = fma(u, s_r[j * kRtThreads + tid], a);
                 c = fma(u, s_v[j * kRtThreads + tid], c);
             }
-            s_t[k * kRtThreads + tid] = cay[4 * k + 0] * a + cay[4 * k + 1] * c;
-            s_t[(NB + k) * kRtThreads + tid] = cay[4 * k + 2] * a + cay[4 * k + 3] * c;
+            double rn = cay[4 * k + 0] * a + cay[4 * k + 1] * c;
+            double vn = cay[4 * k + 2] * a + cay[4 * k + 3] * c;
+            if (LANGEVIN) {
+                const double wk = 2.0 * p.omega_n * sin(k * 3.14159265358979323846 / NB);
+                const double gam = (k == 0) ? p.langevin_gamma : 2.0 * wk;
+                const double c1 = exp(-gam * dt), c2 = sqrt(1.0 - c1 * c1);
+                double xi;
+                if (p.rng == NQCB200_RNG_INJECTED) xi = p.noise[((step - p.noise_step0) * T + traj) * NB + k];
+                else {
+                    double z0, z1;
+                    philox_normal2(p.seed, (uint64_t)(p.traj_offset + traj), (uint64_t)step * ((NB + 1) / 2) + k / 2, z0, z1, 3u);
+                    xi = (k & 1) ? z1 : z0;
+                }
+                vn = c1 * vn + c2 * sqrt(p.omega_n / mass) * xi;                     // step_O!  steps.jl:109-124
+                const double r2 = cay[4 * k + 0] * rn + cay[4 * k + 1] * vn;         // second half Cayley step
+                vn = cay[4 * k + 2] * rn + cay[4 * k + 3] * vn;
+                rn = r2;
+            }
+            s_t[k * kRtThreads + tid] = rn;
+            s_t[(NB + k) * kRtThreads + tid] = vn;
         }
         for (int j = 0; j < NB; ++j) {
             double a = 0.0, c = 0.0;

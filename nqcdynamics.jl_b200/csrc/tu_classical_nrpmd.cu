@@ -90,7 +90,14 @@ bool pick_langevin(int B, KernelSet& out, const char* name) {
         case 16: set_langevin<M, 16>(out, name); return true;
         case 32: set_langevin<M, 32>(out, name); return true;
     }
-    return false;
+    // any other bead count >= 2: thread per trajectory, dense normal-mode product
+    const size_t bytes = ((size_t)5 * B * kRtThreads + (size_t)B * B + 4 * B) * sizeof(double);
+    if (B < 2 || bytes > 200 * 1024) return false;
+    out.step = classical_tpt_step_kernel<M, true>;
+    out.init = classical_tpt_init_kernel<M>;
+    out.L = 1; out.DPL = 1; out.name = name;
+    out.step_L = 1; out.step_block = kRtThreads; out.step_smem = bytes;
+    return true;
 }
 }  // namespace
 
@@ -99,7 +106,7 @@ bool select_langevin(const nqcb200_config& c, KernelSet& out, std::string& why) 
     bool ok = false;
     if (c.model == NQCB200_MODEL_HARMONIC) ok = pick_langevin<ModelT<NQCB200_MODEL_HARMONIC>>(c.nbeads, out, "langevin_harmonic");
     else if (c.model == NQCB200_MODEL_FREE) ok = pick_langevin<ModelT<NQCB200_MODEL_FREE>>(c.nbeads, out, "langevin_free");
-    if (!ok) why = "ThermalLangevin (BCOCB) needs a classical model and nbeads in {2,4,8,16,32}";
+    if (!ok) why = "ThermalLangevin (BCOCB) needs a classical model and nbeads >= 2 (beads must fit in shared memory)";
     return ok;
 }
 

@@ -449,7 +449,7 @@ int nqco_run(nqco_handle* h, int64_t nsteps) {
                         } else {
                             for (size_t k = 0; k < nb; k += 2) {     // same stream as the CUDA kernel (purpose 3)
                                 double z0, z1;
-                                philox_normal2(S.cfg.seed, (uint64_t)(S.cfg.traj_offset + t), (uint64_t)tr.step * (nb / 2) + k / 2, z0, z1, 3u);
+                                philox_normal2(S.cfg.seed, (uint64_t)(S.cfg.traj_offset + t), (uint64_t)tr.step * ((nb + 1) / 2) + k / 2, z0, z1, 3u);
                                 tr.noise[k] = z0; if (k + 1 < nb) tr.noise[k + 1] = z1;
                             }
                         }

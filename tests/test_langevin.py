@@ -44,7 +44,7 @@ def test_oracle_bcocb_thermalises_harmonic_ring_polymer():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("B", [2, 8, 32])
+@pytest.mark.parametrize("B", [2, 5, 8, 10, 32])      # 5, 10: the dense any-bead-count kernel
 def test_engine_bcocb_matches_oracle_with_injected_noise(B):
     T, nsteps = 70, 40
     rng = np.random.default_rng(5)
@@ -76,14 +76,15 @@ def test_engine_bcocb_philox_stream_and_thermal_distribution():
     assert abs(np.mean(st["r"] ** 2) / r2 - 1.0) < 6.0 * np.sqrt(2.0 / (T * B)) + 0.02
     kin = e.observable_sum(A.OBS_KINETIC)[-40:, 0] / T
     assert abs(kin.mean() / ke - 1.0) < 0.02
-    # the production stream is the oracle's: a short run agrees trajectory by trajectory
-    kw2 = _cfg(64, B, 20, 5)
-    e2 = engine_factory()(*A.make_config(**kw2)); o2 = oracle_factory()(*A.make_config(**kw2))
-    for h in (e2, o2):
-        h.set_state(np.full((64, B, 1), 0.05), np.zeros((64, B, 1)))
-        h.run(20)
-    assert rel_err(e2.get_state()["r"], o2.get_state()["r"]) < 1e-10
-    assert rel_err(e2.get_state()["v"], o2.get_state()["v"]) < 1e-10
+    # the production stream is the oracle's: a short run agrees trajectory by trajectory (FFT kernel and dense kernel)
+    for B2 in (16, 5):
+        kw2 = _cfg(64, B2, 20, 5)
+        e2 = engine_factory()(*A.make_config(**kw2)); o2 = oracle_factory()(*A.make_config(**kw2))
+        for h in (e2, o2):
+            h.set_state(np.full((64, B2, 1), 0.05), np.zeros((64, B2, 1)))
+            h.run(20)
+        assert rel_err(e2.get_state()["r"], o2.get_state()["r"]) < 1e-10
+        assert rel_err(e2.get_state()["v"], o2.get_state()["v"]) < 1e-10
 
 
 @pytest.mark.gpu
