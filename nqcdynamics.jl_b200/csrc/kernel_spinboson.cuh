@@ -113,9 +113,9 @@ NQ_D void sb_sz(const Eig<2>& e, double& s00, double& s01, double& s11) {
 }
 // force scalars (A, B): acceleration of mode j = -(w_j^2 r_j A + c_j B) / m_j
 template <int METHOD>
-NQ_D void sb_force_scalars(const Herm<2>& s, int st, double s00, double s01, double s11, double& A, double& B) {
+NQ_D void sb_force_scalars(const Herm<2>& s, int st, double tr0, double s00, double s01, double s11, double& A, double& B) {
     if (METHOD == NQCB200_METHOD_FSSH) { A = 1.0; B = st ? s11 : s00; }                       // fssh.jl:67-74
-    else { A = s.x[0] + s.x[2]; B = s.x[0] * s00 + 2.0 * s.x[1] * s01 + s.x[2] * s11; }        // ehrenfest.jl:57-65
+    else { A = tr0; B = s.x[0] * s00 + 2.0 * s.x[1] * s01 + s.x[2] * s11; }                    // ehrenfest.jl:57-65 (tr sigma is conserved)
 }
 
 struct SbTraj {
@@ -148,6 +148,9 @@ NQ_D void sb_sweep(const SbSmem& M, int D, int slot, int part, bool first, bool 
     for (int q = 0; q < W; ++q) { h4[q] = 0.0; l4[q] = 0.0; c4[q] = 0.0; w4[q] = 0.0; m4[q] = 0.0; }
     // second half kick of the previous step (not on launch entry) + first half kick of this one, in units of dt
     const double nA = -A, nBdt = -B * dt, kfac_2 = first ? 0.0 : 0.5, kfac_both = kfac_2 + 0.5;
+    // Ehrenfest: A = tr sigma is a constant of the motion, 1 up to the rounding of Z' rho Z for a normalised initial
+    // state: within 4 ulp it is taken as exactly 1 (a relative change of the force below 1e-15) -> same fast path
+    const bool unitA = (METHOD == NQCB200_METHOD_FSSH) || __all_sync(0xffffffffu, fabs(A - 1.0) <= 1e-15);
     auto body = [&](const int (&jj)[W], const bool (&ok)[W]) {
         double2 k1[W], k2[W], k3[W];
         double r[W], v[W];
@@ -163,7 +166,7 @@ NQ_D void sb_sweep(const SbSmem& M, int D, int slot, int part, bool first, bool 
             for (int q = 0; q < W; ++q) v[q] = fma(-gm, k1[q].y, fma(-gd, k2[q].x, v[q]));   // hop rescaling / reflection
         }
         double vt[W];
-        if (DRIFT && !first && METHOD == NQCB200_METHOD_FSSH) {
+        if (DRIFT && !first && unitA) {
             // vt = v + dt a,  dt a = -(dt w^2/m) r - dt B (c/m)   (A = 1, fssh.jl:67-74; step_B! twice, steps.jl:3-5)
 #pragma unroll
             for (int q = 0; q < W; ++q) vt[q] = fma(nBdt, k1[q].y, fma(-k1[q].x, r[q], v[q]));
@@ -434,11 +437,12 @@ __global__ void __launch_bounds__(kSbTraj * LPT, 1) spinboson_step_kernel(const 
             for (int k = 0; k < N; ++k) e.Z[i][k] = R.Zref[i][k];
         }
     }
+    const double tr0 = R.s.x[0] + R.s.x[2];     // tr sigma: constant of the motion (the similarity transform keeps it too)
     if (p.step0 == 0) {
         // first step after set_state: no hop has happened, sigma is sigma(t0), Zref the eigenvectors at r0
         double s00, s01, s11;
         sb_sz(e, s00, s01, s11);
-        sb_force_scalars<METHOD>(R.s, R.st, s00, s01, s11, R.A, R.B);
+        sb_force_scalars<METHOD>(R.s, R.st, tr0, s00, s01, s11, R.A, R.B);
     } else {
         R.A = p.sb_carry[traj]; R.B = p.sb_carry[T + traj];
     }
@@ -470,7 +474,7 @@ __global__ void __launch_bounds__(kSbTraj * LPT, 1) spinboson_step_kernel(const 
         }
         double s00, s01, s11;
         sb_sz(e, s00, s01, s11);
-        sb_force_scalars<METHOD>(R.s, R.st, s00, s01, s11, R.A, R.B);      // pre-hop state, sigma_prev
+        sb_force_scalars<METHOD>(R.s, R.st, tr0, s00, s01, s11, R.A, R.B);      // pre-hop state, sigma_prev
         // sum_j c_j v_j after the second half kick: v_j = vt_j - hdt (w_j^2 r_j A + c_j B) / m_j
         const double cv = S.cvt - hdt * (R.A * S.cwr + R.B * C2);
         const double dfac = -s01 / (e.w[0] - e.w[1]);                       // d_j[0,1] = c_j dfac
