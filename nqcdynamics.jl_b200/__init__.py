@@ -18,4 +18,4 @@ from .api import (Atoms, FSSH, Ehrenfest, EhrenfestNA, ThermalLangevin, Classica
                   OutputFinalVelocity, OutputTotalDiabaticPopulation, OutputTotalAdiabaticPopulation, OutputSpringEnergy,
                   OutputCentroidKineticEnergy, OutputFinalTime, OutputDynamicsVariables, OutputInitial, OutputFinal,
                   PopulationCorrelationFunction, SortByTrajectoryReduction, SortByOutputReduction, SumReduction,
-                  MeanReduction, EnsembleB200, run_dynamics)
+                  MeanReduction, EnsembleB200, run_dynamics, TerminatingCallback, PositionOutside)

@@ -101,6 +101,8 @@ def bind(lib: C.CDLL, prefix: str) -> None:
     f("set_gauge_reference", [H, _dp, C.c_int64])
     f("set_draws", [H, _dp, C.c_int64])
     f("set_noise", [H, _dp, C.c_int64])
+    f("set_termination", [H, C.c_int, C.c_double, C.c_double])
+    f("get_termination", [H, _lp])
     f("run", [H, C.c_int64])
     f("run_from_host", [H, _dp, _dp, _dp, _dp, _ip, _dp, C.c_int, C.c_int64], required=False)
     f("sample_state", [H, C.POINTER(Dist), C.POINTER(Dist), C.c_int, _dp, _dp, C.c_int, C.c_int32])
@@ -122,7 +124,7 @@ def bind(lib: C.CDLL, prefix: str) -> None:
 
 HEADER_SYMBOLS = [
     "version", "device_count", "create", "destroy", "last_error", "observable_width", "set_state",
-    "set_state_diabatic", "set_mapping", "set_gauge_reference", "set_draws", "set_noise", "run", "run_from_host", "sample_state", "get_state", "get_mapping",
+    "set_state_diabatic", "set_mapping", "set_gauge_reference", "set_draws", "set_noise", "set_termination", "get_termination", "run", "run_from_host", "sample_state", "get_state", "get_mapping",
     "get_observable_sum", "observable_sum_device", "observable_offset", "get_observable_per_trajectory",
     "get_diagnostics", "get_counters", "get_iesh_stats", "get_progress", "get_last_run_timing", "get_launch_count", "get_last_download_timing", "measure_fp64_peak",
 ]
@@ -232,6 +234,16 @@ class CHandle:
         if xi_.ndim != 3 or xi_.shape[1] != self.T or xi_.shape[2] != self.B * self.D:
             raise ValueError("noise must have shape (nsteps, ntraj, nbeads*ndofs)")
         self._call("set_noise", _ptr(xi_.reshape(-1)), C.c_int64(xi_.shape[0]))
+
+    def set_termination(self, dof: int, lo: float, hi: float):
+        """TerminatingCallback(u -> r[dof] < lo || r[dof] > hi) (callbacks.jl:29); dof < 0 removes it."""
+        self._call("set_termination", C.c_int(int(dof)), C.c_double(float(lo)), C.c_double(float(hi)))
+
+    def termination(self) -> np.ndarray:
+        """Steps taken before terminate! fired, per trajectory (-1: still running)."""
+        out = np.full(max(self.T, 1), -1, dtype=np.int64)
+        self._call("get_termination", out.ctypes.data_as(_lp))
+        return out[:self.T]
 
     def run(self, nsteps: int):
         self._call("run", C.c_int64(int(nsteps)))

@@ -344,6 +344,28 @@ def PopulationCorrelationFunction(sim, statetype=None):          # TimeCorrelati
     return _Output("PopulationCorrelationFunction", A.OBS_POPCORR_ADIABATIC if adiabatic else A.OBS_POPCORR_DIABATIC)
 
 
+# ---- callbacks (src/DynamicsUtils/callbacks.jl) ------------------------------------------------------
+@dataclass(frozen=True)
+class PositionOutside:
+    """Termination predicate a device kernel can evaluate: ``(u, t, integrator) -> r[dof] < lo || r[dof] > hi`` with
+    ``r = get_positions(u)`` flattened column-major and ``dof`` 1-based (the scattering examples of the reference
+    documentation terminate when the particle has left the interaction region)."""
+    lo: float
+    hi: float
+    dof: int = 1
+
+
+class TerminatingCallback:
+    """``TerminatingCallback(func) = DiscreteCallback(func, terminate!)`` (callbacks.jl:29).  ``func`` must be a
+    :class:`PositionOutside` (arbitrary closures cannot run in the kernel).  Passed as ``callback=`` to
+    :func:`run_dynamics`, it is evaluated after every step, after the method's own hopping callback."""
+
+    def __init__(self, func):
+        if not isinstance(func, PositionOutside):
+            raise TypeError("EnsembleB200 evaluates the termination predicate in the step kernel: pass PositionOutside(lo, hi, dof)")
+        self.func = func
+
+
 # ---- reductions (src/Ensembles/reductions.jl) ------------------------------------------------------
 class SortByTrajectoryReduction:
     pass
@@ -441,13 +463,22 @@ def _finalise(sim, out: _Output, arrs: Dict[int, np.ndarray], per_trajectory: bo
 def run_dynamics(sim: Simulation, tspan, distribution, *, output, selection: Optional[Sequence[int]] = None,
                  reduction=None, ensemble_algorithm: Optional[EnsembleB200] = None, trajectories: int = 1,
                  dt: float = 1.0, saveat: Optional[float] = None, savetime: bool = True, seed: Optional[int] = None,
-                 draws: Optional[np.ndarray] = None, **kwargs):
+                 draws: Optional[np.ndarray] = None, callback: Optional[TerminatingCallback] = None, **kwargs):
     """Run ``trajectories`` trajectories over ``tspan`` sampling ``distribution`` (run_dynamics.jl:42-136).
 
     Keywords follow the reference; ``saveat`` must be a multiple of ``dt`` (the engine's integrators are
     fixed-step, like the reference's custom algorithms).  Extra: ``seed`` (Philox key / IC sampling) and
     ``draws`` (parity mode: uniform hop draws of shape (nsteps, trajectories)).  The reference's
-    ``precompile_dynamics`` pass is skipped (nothing to JIT)."""
+    ``precompile_dynamics`` pass is skipped (nothing to JIT).
+
+    ``callback=TerminatingCallback(PositionOutside(lo, hi, dof))``: a terminated trajectory's series end the way a
+    DiffEq solution does -- the saveat points up to the termination time, then the terminal state saved before and
+    after ``terminate!`` (``save_positions = (true, true)``, the DiscreteCallback default: the terminal time appears
+    twice, once if it coincides with a saveat point plus the post-affect copy).  That rule restates DiffEqBase's
+    ``apply_discrete_callback!`` (a dependency outside the reference tree; unpinned).  ``OutputFinal*``,
+    ``OutputStateResolvedScattering1D`` and ``OutputFinalTime`` see the terminal state / time.  Reduced (Sum / Mean)
+    series keep their fixed shape: a terminated trajectory contributes its terminal state to the later save points
+    (the reference cannot add ragged series at all)."""
     kwargs.pop("precompile_dynamics", None)
     if kwargs:
         raise TypeError(f"unsupported keyword(s) for the B200 ensemble path: {sorted(kwargs)}")
@@ -465,6 +496,13 @@ def run_dynamics(sim: Simulation, tspan, distribution, *, output, selection: Opt
     if save_every < 1 or (saveat is not None and abs(save_every * dt - float(saveat)) > 1e-9 * max(1.0, abs(float(saveat)))):
         raise ValueError("saveat must be a positive multiple of dt")
     nsave = nsteps // save_every + 1
+    if callback is not None:
+        if not isinstance(callback, TerminatingCallback):
+            raise TypeError("callback must be a TerminatingCallback(PositionOutside(...))")
+        if nsteps % save_every:
+            raise ValueError("with a TerminatingCallback the time span must be a whole number of saveat intervals")
+        if not 1 <= callback.func.dof <= sim.ndofs_total:
+            raise ValueError("PositionOutside.dof out of range")
     per_traj = isinstance(reduction, (SortByTrajectoryReduction, SortByOutputReduction))
     obs_mask = 0
     method_id = sim.method.method_id
@@ -540,6 +578,8 @@ def run_dynamics(sim: Simulation, tspan, distribution, *, output, selection: Opt
                 edc_C=getattr(method, "decoherence_C", 0.0))
             with Engine(cfg, keep) as eng:
                 ran = False
+                if callback is not None:
+                    eng.set_termination(callback.func.dof - 1, callback.func.lo, callback.func.hi)
                 if dev_spec is not None:
                     rho1 = None
                     adiabatic = True
@@ -578,6 +618,8 @@ def run_dynamics(sim: Simulation, tspan, distribution, *, output, selection: Opt
                 if not ran:
                     eng.run(nsteps)
                 results[g] = {d: (eng.observable_per_trajectory(d) if per_traj else eng.observable_sum(d)) for d in obs_ids}
+                if callback is not None:
+                    results[g]["term"] = eng.termination()
         except BaseException as exc:   # re-raised on the caller's thread
             errors.append(exc)
 
@@ -591,13 +633,23 @@ def run_dynamics(sim: Simulation, tspan, distribution, *, output, selection: Opt
         raise errors[0]
 
     time = t0 + dt * save_every * np.arange(nsave)
+    term = np.concatenate([res["term"] for res in results]) if callback is not None else np.full(T, -1, dtype=np.int64)
+    t_end = np.where(term >= 0, t0 + dt * term, time[-1])      # OutputFinalTime: last(sol.t)
     if per_traj:
         per_obs = {k: np.concatenate([res[k] for res in results], axis=0) for k in obs_ids}    # (T, nsave, w)
         trajs = []
         for i in range(T):
-            d: Dict[str, Any] = {"Time": time.copy()} if savetime else {}
+            ti, arrs = time, {k: per_obs[k][i] for k in obs_ids}
+            if term[i] >= 0:
+                # sol.t of a terminated trajectory: saveat points <= t_term, then the terminal state twice (see docstring);
+                # save index kf + 1 of the device stream holds the terminal state when t_term is not a saveat point
+                kf, rem = divmod(int(term[i]), save_every)
+                idx = list(range(kf + 1)) + ([kf + 1, kf + 1] if rem else [kf])
+                ti = np.concatenate([time[:kf + 1], np.full(len(idx) - kf - 1, t_end[i])])
+                arrs = {k: (a if k in (A.OBS_SCATTERING, A.OBS_SCATTERING_DIABATIC) else a[idx]) for k, a in arrs.items()}
+            d: Dict[str, Any] = {"Time": ti.copy()} if savetime else {}
             for o in outputs:
-                d[o.name] = _finalise(sim, o, {k: per_obs[k][i] for k in obs_ids}, True, time[-1])
+                d[o.name] = _finalise(sim, o, arrs, True, float(t_end[i]))
             trajs.append(d)
         if isinstance(reduction, SortByOutputReduction):
             keys = list(trajs[0].keys())
@@ -609,5 +661,5 @@ def run_dynamics(sim: Simulation, tspan, distribution, *, output, selection: Opt
     for o in outputs:
         if o.kind == "centroid_ke":
             raise ValueError("OutputCentroidKineticEnergy is not linear in the stream: use a per-trajectory reduction")
-        d[o.name] = _finalise(sim, o, summed, False, time[-1] * (T * scale))
+        d[o.name] = _finalise(sim, o, summed, False, float(t_end.sum()) * scale)
     return d

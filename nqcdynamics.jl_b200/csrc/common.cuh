@@ -101,6 +101,11 @@ struct KParams {
     double langevin_gamma;
     const double* noise;
     int64_t noise_step0;
+    // TerminatingCallback(u -> r[term_dof] < term_lo || r[term_dof] > term_hi) (callbacks.jl:29): step count at which
+    // terminate! fired per trajectory (-1 = running); only the kernels instantiated with TERM read these
+    int32_t term_dof;
+    double term_lo, term_hi;
+    long long* term_step;   // [T]
     // draws (injected): xi[(step - draws_step0) * T + traj]
     const double* draws;
     int64_t draws_step0;

@@ -298,6 +298,7 @@ int finish_set_state(nqcb200_handle* h, int basis, int sample_state, const doubl
     NQ_CUDA(h, cudaMemsetAsync(h->kp.obs_sum, 0, sizeof(double) * std::max<int64_t>(1, h->kp.layout.total) * kObsReplicas, h->stream));
     if (h->kp.obs_traj) NQ_CUDA(h, cudaMemsetAsync(h->kp.obs_traj, 0, sizeof(double) * h->kp.layout.total * T, h->stream));
     NQ_CUDA(h, cudaMemsetAsync(h->kp.counters, 0, sizeof(unsigned long long) * 8, h->stream));
+    if (h->kp.term_step) NQ_CUDA(h, cudaMemsetAsync(h->kp.term_step, 0xff, sizeof(long long) * std::max<int64_t>(T, 1), h->stream));   // -1: running
     h->step_count = 0;
     h->kp.step0 = 0;
     h->kp.nsteps = 0;
@@ -441,6 +442,7 @@ int nqcb200_create(const nqcb200_config* cfg, nqcb200_handle** out) {
     const int n = c.nstates, D = c.ndofs, B = c.nbeads;
     KParams& kp = h->kp;
     std::memset(&kp, 0, sizeof(kp));
+    kp.term_dof = -1;   // no TerminatingCallback until nqcb200_set_termination
     kp.ntraj = T; kp.traj_offset = c.traj_offset; kp.n = n; kp.D = D; kp.B = B; kp.ne = c.nelectrons;
     kp.save_every = c.save_every; kp.nsave = c.nsave; kp.rescaling = c.rescaling; kp.rng = c.rng;
     kp.diagnostics = c.diagnostics; kp.per_trajectory = c.per_trajectory;
@@ -722,7 +724,9 @@ int nqcb200_run(nqcb200_handle* h, int64_t nsteps) {
         const int64_t chunk = std::min(nsteps - done, max_per_launch);
         h->kp.step0 = h->step_count + done;
         h->kp.nsteps = (int32_t)chunk;
-        if (h->ks.step_block > 0) {
+        if (h->kp.term_dof >= 0) {   // TerminatingCallback instantiation (same launch shape as the init kernel's)
+            h->ks.step_term<<<grid_for(h), h->ks.block, h->ks.dyn_smem, h->stream>>>(h->kp); ++h->launches_total;
+        } else if (h->ks.step_block > 0) {
             const int64_t threads = h->cfg.ntraj * h->ks.step_L;
             const unsigned grid = (unsigned)std::max<int64_t>(1, (threads + h->ks.step_block - 1) / h->ks.step_block);
             h->ks.step<<<grid, h->ks.step_block, h->ks.step_smem, h->stream>>>(h->kp);
@@ -952,7 +956,14 @@ int nqcb200_get_counters(nqcb200_handle* h, int64_t* steps, int64_t* hops, int64
     }
     NQ_CUDA(h, cudaMemcpyAsync(host, h->kp.counters, sizeof(host), cudaMemcpyDeviceToHost, h->stream));
     NQ_CUDA(h, cudaStreamSynchronize(h->stream));
-    if (steps) *steps = h->step_count * T;
+    if (steps) {
+        *steps = h->step_count * T;
+        if (h->kp.term_dof >= 0 && h->kp.term_step && T > 0) {   // steps a terminated trajectory did not take
+            std::vector<long long> ts((size_t)T);
+            NQ_CUDA(h, cudaMemcpy(ts.data(), h->kp.term_step, sizeof(long long) * T, cudaMemcpyDeviceToHost));
+            for (long long x : ts) if (x >= 0) *steps -= h->step_count - x;
+        }
+    }
     if (hops) *hops = (int64_t)host[0];
     if (frustrated) *frustrated = (int64_t)host[1];
     if (nonfinite) *nonfinite = (int64_t)host[2];
@@ -970,6 +981,36 @@ int nqcb200_get_iesh_stats(nqcb200_handle* h, int64_t* hop_searches, int64_t* de
     if (determinants) *determinants = (int64_t)host[4];
     if (taylor_stages) *taylor_stages = (int64_t)host[5];
     if (gemm_stages) *gemm_stages = (int64_t)host[6];
+    return NQCB200_OK;
+}
+
+int nqcb200_set_termination(nqcb200_handle* h, int dof, double lo, double hi) {
+    if (!h) return NQCB200_ERR_INVALID;
+    if (dof < 0) { h->kp.term_dof = -1; return NQCB200_OK; }
+    if (!h->ks.step_term || h->cfg.nbeads != 1) {
+        h->err = "termination masks exist for the thread-per-trajectory FSSH / Ehrenfest kernels (1-D models, nbeads == 1)";
+        return NQCB200_ERR_UNSUPPORTED;
+    }
+    if (dof >= h->cfg.ndofs || !(lo <= hi)) { h->err = "termination: dof < ndofs and lo <= hi"; return NQCB200_ERR_INVALID; }
+    NQ_CUDA(h, cudaSetDevice(h->cfg.device));
+    if (!h->kp.term_step) {
+        int rc = dev_alloc(h, &h->kp.term_step, (size_t)h->cfg.ntraj);
+        if (rc) return rc;
+        NQ_CUDA(h, cudaMemsetAsync(h->kp.term_step, 0xff, sizeof(long long) * std::max<int64_t>(h->cfg.ntraj, 1), h->stream));
+        NQ_CUDA(h, cudaStreamSynchronize(h->stream));
+    }
+    h->kp.term_dof = dof; h->kp.term_lo = lo; h->kp.term_hi = hi;
+    return NQCB200_OK;
+}
+
+int nqcb200_get_termination(nqcb200_handle* h, int64_t* term_step) {
+    if (!h || !term_step) return NQCB200_ERR_INVALID;
+    const int64_t T = h->cfg.ntraj;
+    if (h->kp.term_dof < 0 || !h->kp.term_step) { for (int64_t t = 0; t < T; ++t) term_step[t] = -1; return NQCB200_OK; }
+    NQ_CUDA(h, cudaSetDevice(h->cfg.device));
+    static_assert(sizeof(long long) == sizeof(int64_t), "term_step layout");
+    NQ_CUDA(h, cudaMemcpyAsync(term_step, h->kp.term_step, sizeof(int64_t) * T, cudaMemcpyDeviceToHost, h->stream));
+    NQ_CUDA(h, cudaStreamSynchronize(h->stream));
     return NQCB200_OK;
 }
 

@@ -335,8 +335,12 @@ NQ_D double force_from_adiab(const double (&Ap)[sym_size(N)], int st, const Herm
     return f;
 }
 
-template <class M, int DPL, int L, int METHOD>
+// TERM: TerminatingCallback instantiation (thread-per-trajectory kernels only).  A terminated trajectory skips the
+// step body (its registers keep the final state) but still takes part in the block-collective save points, so the
+// fixed-shape outputs carry its final state from the termination on; term_step tells the host where the series ends.
+template <class M, int DPL, int L, int METHOD, bool TERM = false>
 __global__ void __launch_bounds__(kBlockThreads) density_step_kernel(const __grid_constant__ KParams p) {
+    static_assert(!TERM || L == 1, "termination masks exist for the thread-per-trajectory layout");
     constexpr int N = M::NS;
     __shared__ double smem[2 * (kBlockThreads / 32)];
     const int64_t gthread = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -358,10 +362,13 @@ __global__ void __launch_bounds__(kBlockThreads) density_step_kernel(const __gri
     }
     unsigned long long nhops = 0, nfrus = 0;
     const double dt = p.dt, hdt = 0.5 * p.dt;
+    long long term_step = -1;
+    if (TERM) term_step = p.term_step[traj];
 
 #pragma unroll 1
     for (int is = 0; is < p.nsteps; ++is) {
         const int64_t step = p.step0 + is;
+        if (!TERM || term_step < 0) {
         const double t = p.t0 + dt * (double)step;
         const double tcur = (step == 0) ? 0.0 : t;   // Q1: electronic buffer starts at t = 0, all zero
         double vt[DPL];
@@ -462,6 +469,13 @@ __global__ void __launch_bounds__(kBlockThreads) density_step_kernel(const __gri
             }
         }
         R.cur = nxt;
+        if (TERM) {   // DiscreteCallback(condition, terminate!) after the hopping callback, on the new u
+            double x = R.r[0];   // L == 1: DPL == D, every dof lives in this thread
+#pragma unroll
+            for (int jj = 1; jj < DPL; ++jj) x = (jj == p.term_dof) ? R.r[jj] : x;
+            if (x < p.term_lo || x > p.term_hi) term_step = step + 1;
+        }
+        }
 
         if ((step + 1) % p.save_every == 0) {
             const int64_t isave = (step + 1) / p.save_every;
@@ -474,6 +488,7 @@ __global__ void __launch_bounds__(kBlockThreads) density_step_kernel(const __gri
 
     if (valid) {
         store_regs<N, DPL, L>(p, traj, lane, R);
+        if (TERM) p.term_step[traj] = term_step;
         if (p.diagnostics) {
             if (lane0) {
 #pragma unroll

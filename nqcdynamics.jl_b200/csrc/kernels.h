@@ -13,6 +13,7 @@ using InitFn = void (*)(const KParams, int, int, const double*);
 struct KernelSet {
     StepFn step = nullptr;
     InitFn init = nullptr;
+    StepFn step_term = nullptr;   // TerminatingCallback instantiation of `step` (nqcb200_set_termination), if any
     int L = 1;              // lanes (threads) per trajectory
     int DPL = 1;            // nuclear dofs per lane
     int block = kBlockThreads;

@@ -7,9 +7,11 @@ template <class M>
 bool pick(int method, KernelSet& out, const char* name) {
     if (method == NQCB200_METHOD_FSSH) {
         out.step = density_step_kernel<M, 1, 1, NQCB200_METHOD_FSSH>;
+        out.step_term = density_step_kernel<M, 1, 1, NQCB200_METHOD_FSSH, true>;
         out.init = density_init_kernel<M, 1, 1, NQCB200_METHOD_FSSH>;
     } else if (method == NQCB200_METHOD_EHRENFEST) {
         out.step = density_step_kernel<M, 1, 1, NQCB200_METHOD_EHRENFEST>;
+        out.step_term = density_step_kernel<M, 1, 1, NQCB200_METHOD_EHRENFEST, true>;
         out.init = density_init_kernel<M, 1, 1, NQCB200_METHOD_EHRENFEST>;
     } else return false;
     out.L = 1; out.DPL = 1; out.name = name;

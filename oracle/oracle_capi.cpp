@@ -73,6 +73,9 @@ struct nqco_handle {
     int64_t zref_per_traj = 0;
     int64_t nsave_done = 0;
     bool has_state = false;
+    // TerminatingCallback(u -> r[dof] < lo || r[dof] > hi), callbacks.jl:29; dof < 0: none
+    int term_dof = -1;
+    double term_lo = 0.0, term_hi = 0.0;
     std::string err;
 };
 
@@ -432,6 +435,9 @@ int nqco_run(nqco_handle* h, int64_t nsteps) {
             try {
                 for (int64_t s = 0; s < chunk; ++s) {
                     double xi = 0.0;
+                    // terminate!(integrator): the trajectory is over; its frozen final state is what the later save
+                    // points of the fixed-shape output carry (the step counter still advances: it indexes the draws)
+                    if (tr.term_step >= 0) { tr.step++; continue; }
                     if (needs_draws) {
                         if (S.cfg.rng == NQCB200_RNG_INJECTED)
                             xi = h->draws[(size_t)(tr.step - h->draws_first_step) * T + t];
@@ -455,6 +461,12 @@ int nqco_run(nqco_handle* h, int64_t nsteps) {
                         }
                     }
                     step(S, tr, xi);
+                    // DiscreteCallback(condition, terminate!) runs after perform_step! and after the problem's own
+                    // hopping callback (CallbackSet(prob callbacks, solve callbacks)); condition on the new u
+                    if (h->term_dof >= 0) {
+                        const double x = tr.r[h->term_dof];
+                        if (x < h->term_lo || x > h->term_hi) tr.term_step = tr.step;
+                    }
                 }
             } catch (const std::exception& e) {
 #pragma omp critical
@@ -557,6 +569,19 @@ int nqco_get_iesh_stats(nqco_handle* h, int64_t* hop_searches, int64_t* determin
     if (determinants) *determinants = (h->S.cfg.method == NQCB200_METHOD_IESH && !h->S.cfg.disable_hopping) ? st : 0;
     if (taylor_stages) *taylor_stages = 0;   // the oracle follows the reference: dense Hermitian eigendecomposition
     if (gemm_stages) *gemm_stages = 0;
+    return NQCB200_OK;
+}
+
+/* TerminatingCallback with a position-window predicate (see nqcb200_set_termination). */
+int nqco_set_termination(nqco_handle* h, int dof, double lo, double hi) {
+    if (!h) return NQCB200_ERR_INVALID;
+    if (dof >= 0 && (h->S.B != 1 || dof >= h->S.D)) { h->err = "termination: plain Simulation (nbeads == 1), dof < D"; return NQCB200_ERR_INVALID; }
+    h->term_dof = dof; h->term_lo = lo; h->term_hi = hi;
+    return NQCB200_OK;
+}
+int nqco_get_termination(nqco_handle* h, int64_t* term_step) {
+    if (!h || !term_step) return NQCB200_ERR_INVALID;
+    for (size_t t = 0; t < h->traj.size(); ++t) term_step[t] = h->traj[t].term_step;
     return NQCB200_OK;
 }
 

@@ -63,6 +63,7 @@ struct Trajectory {
     ElectronicParameters cur, nxt;   // DoubleBuffer (current, next)
     vec pop0;             // initial population for the correlation function
     int64_t step = 0;
+    int64_t term_step = -1;   // TerminatingCallback (callbacks.jl:29): step count at which terminate! fired, -1 = running
     Counters cnt;
     vec last_nac, last_eig, last_Z;
     vec noise;            // ThermalLangevin: the B*D standard normals of the current step (W.dW / sqrt(dt))
@@ -681,6 +682,7 @@ inline void initialise(const Setup& S, Trajectory& T, const double* Zref) {
     if (B > 1) T.centroid.init(n, D, Zref ? Zref + (size_t)n * n * B : nullptr);
     T.k.assign((size_t)B * D, 0.0);
     T.step = 0;
+    T.term_step = -1;
     T.cnt = Counters();
     // Q1: both halves of the double buffer all-zero with t = 0.0 (tspan[1] of a (0, dt) problem)
     T.cur.vd.assign((size_t)n * n, cd(0.0)); T.cur.E.assign(n, cd(0.0)); T.cur.t = 0.0;
