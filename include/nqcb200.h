@@ -258,15 +258,18 @@ int nqcb200_set_noise(nqcb200_handle* h, const double* xi, int64_t nsteps);
 /* TerminatingCallback(func) = DiscreteCallback(func, terminate!) (src/DynamicsUtils/callbacks.jl:29, exported
  * DynamicsUtils.jl:156; the scattering examples pass it as `callback=` to run_dynamics) for the predicate family a
  * device kernel can evaluate: func(u, t, integrator) = r[dof] < lo || r[dof] > hi (0-based dof; "the particle has left
- * the interaction region").  Checked after every step, after the method's own hopping callback (DiffEq merges the
+ * the interaction region"); outgoing != 0 additionally asks for an outward velocity, (r < lo && v < 0) || (r > hi &&
+ * v > 0), the form of the IESH scattering example (docs/src/dynamicssimulations/dynamicsmethods/iesh.md:127-138:
+ * mean(r) > 5.5 A && mean(v) > 0), and `|| t > tcut` is its time clause (t = t0 + steps*dt; +INFINITY or NaN: none;
+ * lo = -INFINITY, hi = +INFINITY leaves only the time clause).  Checked after every step, after the method's own hopping callback (DiffEq merges the
  * callbacks as CallbackSet(problem callbacks, solve callbacks)).  A terminated trajectory stops stepping; its final
  * state is what nqcb200_get_state returns and what every later save point of the fixed-shape observable arrays
  * carries, so final-state outputs (OutputFinal, OutputStateResolvedScattering1D, DynamicsOutputs.jl:205-338) are the
  * reference's, and the host trims per-trajectory series with nqcb200_get_termination (OutputFinalTime :226-231 =
  * t0 + term_step*dt).  dof < 0 removes the callback.  Call before nqcb200_run; the flags are reset by set_state.
- * Available for the thread-per-trajectory FSSH / Ehrenfest kernels (1-D models, nbeads == 1), otherwise
- * NQCB200_ERR_UNSUPPORTED.                                                                          */
-int nqcb200_set_termination(nqcb200_handle* h, int dof, double lo, double hi);
+ * Available for the thread-per-trajectory FSSH / Ehrenfest kernels (1-D models, nbeads == 1) and for the
+ * AdiabaticIESH / EhrenfestNA kernel (whose CTA moves on to its next trajectory), otherwise NQCB200_ERR_UNSUPPORTED. */
+int nqcb200_set_termination(nqcb200_handle* h, int dof, double lo, double hi, int outgoing, double tcut);
 /* term_step[traj]: number of steps the trajectory took before terminate! fired, -1 while it is still running. */
 int nqcb200_get_termination(nqcb200_handle* h, int64_t* term_step);
 

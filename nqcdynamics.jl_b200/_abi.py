@@ -101,7 +101,7 @@ def bind(lib: C.CDLL, prefix: str) -> None:
     f("set_gauge_reference", [H, _dp, C.c_int64])
     f("set_draws", [H, _dp, C.c_int64])
     f("set_noise", [H, _dp, C.c_int64])
-    f("set_termination", [H, C.c_int, C.c_double, C.c_double])
+    f("set_termination", [H, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double])
     f("get_termination", [H, _lp])
     f("run", [H, C.c_int64])
     f("run_from_host", [H, _dp, _dp, _dp, _dp, _ip, _dp, C.c_int, C.c_int64], required=False)
@@ -235,9 +235,11 @@ class CHandle:
             raise ValueError("noise must have shape (nsteps, ntraj, nbeads*ndofs)")
         self._call("set_noise", _ptr(xi_.reshape(-1)), C.c_int64(xi_.shape[0]))
 
-    def set_termination(self, dof: int, lo: float, hi: float):
-        """TerminatingCallback(u -> r[dof] < lo || r[dof] > hi) (callbacks.jl:29); dof < 0 removes it."""
-        self._call("set_termination", C.c_int(int(dof)), C.c_double(float(lo)), C.c_double(float(hi)))
+    def set_termination(self, dof: int, lo: float, hi: float, outgoing: bool = False, tcut: float = float("inf")):
+        """TerminatingCallback(u -> r[dof] < lo || r[dof] > hi || t > tcut) (callbacks.jl:29); ``outgoing``: the position
+        clauses also ask for an outward velocity; dof < 0 removes it."""
+        self._call("set_termination", C.c_int(int(dof)), C.c_double(float(lo)), C.c_double(float(hi)), C.c_int(int(bool(outgoing))),
+                   C.c_double(float(tcut)))
 
     def termination(self) -> np.ndarray:
         """Steps taken before terminate! fired, per trajectory (-1: still running)."""

@@ -347,12 +347,14 @@ def PopulationCorrelationFunction(sim, statetype=None):          # TimeCorrelati
 # ---- callbacks (src/DynamicsUtils/callbacks.jl) ------------------------------------------------------
 @dataclass(frozen=True)
 class PositionOutside:
-    """Termination predicate a device kernel can evaluate: ``(u, t, integrator) -> r[dof] < lo || r[dof] > hi`` with
+    """Termination predicate a device kernel can evaluate: ``(u, t, integrator) -> r[dof] < lo || r[dof] > hi || t > tcut`` with
     ``r = get_positions(u)`` flattened column-major and ``dof`` 1-based (the scattering examples of the reference
     documentation terminate when the particle has left the interaction region)."""
     lo: float
     hi: float
     dof: int = 1
+    outgoing: bool = False          # ... && the velocity points outwards (iesh.md:127-138: mean(r) > x && mean(v) > 0)
+    tcut: float = float("inf")      # ... || t > tcut
 
 
 class TerminatingCallback:
@@ -579,7 +581,7 @@ def run_dynamics(sim: Simulation, tspan, distribution, *, output, selection: Opt
             with Engine(cfg, keep) as eng:
                 ran = False
                 if callback is not None:
-                    eng.set_termination(callback.func.dof - 1, callback.func.lo, callback.func.hi)
+                    eng.set_termination(callback.func.dof - 1, callback.func.lo, callback.func.hi, callback.func.outgoing, callback.func.tcut)
                 if dev_spec is not None:
                     rho1 = None
                     adiabatic = True

@@ -102,9 +102,11 @@ struct KParams {
     const double* noise;
     int64_t noise_step0;
     // TerminatingCallback(u -> r[term_dof] < term_lo || r[term_dof] > term_hi) (callbacks.jl:29): step count at which
-    // terminate! fired per trajectory (-1 = running); only the kernels instantiated with TERM read these
+    // terminate! fired per trajectory (-1 = running); read by the TERM instantiations and by the IESH kernel
     int32_t term_dof;
+    int32_t term_outgoing;   // != 0: the window test also asks for an outward velocity (v < 0 below lo, v > 0 above hi)
     double term_lo, term_hi;
+    double term_tcut;        // ... || t > term_tcut (+inf: no time clause)
     long long* term_step;   // [T]
     // draws (injected): xi[(step - draws_step0) * T + traj]
     const double* draws;

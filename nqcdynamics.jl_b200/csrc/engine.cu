@@ -724,7 +724,7 @@ int nqcb200_run(nqcb200_handle* h, int64_t nsteps) {
         const int64_t chunk = std::min(nsteps - done, max_per_launch);
         h->kp.step0 = h->step_count + done;
         h->kp.nsteps = (int32_t)chunk;
-        if (h->kp.term_dof >= 0) {   // TerminatingCallback instantiation (same launch shape as the init kernel's)
+        if (h->kp.term_dof >= 0 && h->ks.step_term) {   // TerminatingCallback instantiation (same launch shape as the init kernel's)
             h->ks.step_term<<<grid_for(h), h->ks.block, h->ks.dyn_smem, h->stream>>>(h->kp); ++h->launches_total;
         } else if (h->ks.step_block > 0) {
             const int64_t threads = h->cfg.ntraj * h->ks.step_L;
@@ -984,11 +984,11 @@ int nqcb200_get_iesh_stats(nqcb200_handle* h, int64_t* hop_searches, int64_t* de
     return NQCB200_OK;
 }
 
-int nqcb200_set_termination(nqcb200_handle* h, int dof, double lo, double hi) {
+int nqcb200_set_termination(nqcb200_handle* h, int dof, double lo, double hi, int outgoing, double tcut) {
     if (!h) return NQCB200_ERR_INVALID;
     if (dof < 0) { h->kp.term_dof = -1; return NQCB200_OK; }
-    if (!h->ks.step_term || h->cfg.nbeads != 1) {
-        h->err = "termination masks exist for the thread-per-trajectory FSSH / Ehrenfest kernels (1-D models, nbeads == 1)";
+    if ((!h->ks.step_term && !iesh_family(h->cfg.method)) || h->cfg.nbeads != 1) {
+        h->err = "termination masks exist for the thread-per-trajectory FSSH / Ehrenfest kernels (1-D models) and the AdiabaticIESH / EhrenfestNA kernel, nbeads == 1";
         return NQCB200_ERR_UNSUPPORTED;
     }
     if (dof >= h->cfg.ndofs || !(lo <= hi)) { h->err = "termination: dof < ndofs and lo <= hi"; return NQCB200_ERR_INVALID; }
@@ -999,7 +999,8 @@ int nqcb200_set_termination(nqcb200_handle* h, int dof, double lo, double hi) {
         NQ_CUDA(h, cudaMemsetAsync(h->kp.term_step, 0xff, sizeof(long long) * std::max<int64_t>(h->cfg.ntraj, 1), h->stream));
         NQ_CUDA(h, cudaStreamSynchronize(h->stream));
     }
-    h->kp.term_dof = dof; h->kp.term_lo = lo; h->kp.term_hi = hi;
+    h->kp.term_dof = dof; h->kp.term_lo = lo; h->kp.term_hi = hi; h->kp.term_outgoing = outgoing ? 1 : 0;
+    h->kp.term_tcut = (tcut == tcut) ? tcut : INFINITY;   // NaN: no time clause
     return NQCB200_OK;
 }
 

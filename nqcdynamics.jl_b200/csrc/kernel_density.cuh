@@ -470,10 +470,12 @@ __global__ void __launch_bounds__(kBlockThreads) density_step_kernel(const __gri
         }
         R.cur = nxt;
         if (TERM) {   // DiscreteCallback(condition, terminate!) after the hopping callback, on the new u
-            double x = R.r[0];   // L == 1: DPL == D, every dof lives in this thread
+            double x = R.r[0], vx = R.v[0];   // L == 1: DPL == D, every dof lives in this thread
 #pragma unroll
-            for (int jj = 1; jj < DPL; ++jj) x = (jj == p.term_dof) ? R.r[jj] : x;
-            if (x < p.term_lo || x > p.term_hi) term_step = step + 1;
+            for (int jj = 1; jj < DPL; ++jj) { x = (jj == p.term_dof) ? R.r[jj] : x; vx = (jj == p.term_dof) ? R.v[jj] : vx; }
+            const bool og = p.term_outgoing != 0;
+            if ((x < p.term_lo && (!og || vx < 0.0)) || (x > p.term_hi && (!og || vx > 0.0)) || p.t0 + dt * (double)(step + 1) > p.term_tcut)
+                term_step = step + 1;
         }
         }
 

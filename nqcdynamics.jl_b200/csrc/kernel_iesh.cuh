@@ -657,6 +657,20 @@ __device__ __noinline__ void iesh_det_lu(const KParams& p, const IeshSmem& S, co
     det_re = dr; det_im = di;
 }
 
+// TerminatingCallback predicate (nqcb200_set_termination): outside the position window [, moving outwards]
+// [, or t > tcut]; `steps_done` = steps the trajectory has completed, t = t0 + dt * steps_done
+NQ_D bool iesh_outside(const KParams& p, double r, double v, int64_t steps_done) {
+    return (r < p.term_lo && (!p.term_outgoing || v < 0.0)) || (r > p.term_hi && (!p.term_outgoing || v > 0.0)) ||
+           p.t0 + p.dt * (double)steps_done > p.term_tcut;
+}
+
+// Eigen-decomposition at the frozen position of a trajectory that terminated in an earlier launch (cold path).
+__device__ __noinline__ void iesh_eigen_frozen(const KParams& p, IeshSmem& S, const IeshModel& mdl, double r, double vnorm) {
+    double h, dh, u0, du0;
+    mdl.eval(r, h, dh, u0, du0);
+    iesh_eigen(p, S, h, vnorm, false);
+}
+
 // ---- the step kernel -----------------------------------------------------------------------------
 __global__ void __launch_bounds__(384, 1) iesh_step_kernel(const __grid_constant__ KParams p) {
     extern __shared__ __align__(16) double iesh_sm[];
@@ -691,6 +705,14 @@ __global__ void __launch_bounds__(384, 1) iesh_step_kernel(const __grid_constant
 #pragma unroll 1
         for (int is = 0; is < p.nsteps; ++is) {
             const int64_t step = p.step0 + is;
+            // TerminatingCallback mask (nqcb200_set_termination).  Stateless: a terminated trajectory is frozen, so the
+            // predicate that ended it still holds on its (r, v) (and t > tcut stays true); DiffEq does not test the condition at t0, hence
+            // step > 0.  r and v are uniform over the CTA, so the branch is too.
+            if (p.term_dof >= 0 && step > 0 && iesh_outside(p, r, v, step)) {
+                if (is == 0) iesh_eigen_frozen(p, S, mdl, r, vnorm);   // terminated in an earlier launch: eigenvectors for the saves
+                goto save_point;
+            }
+            {
             // ---- nuclei + eigen + force (verlet_with_electronics.jl:55-66) -------------------------
             const double vt = fma(hdt, acc, v);
             r = fma(dt, vt, r);
@@ -956,6 +978,11 @@ __global__ void __launch_bounds__(384, 1) iesh_step_kernel(const __grid_constant
                 }
                 __syncthreads();
             }
+
+            // ---- TerminatingCallback: after the hopping callback, on the new u (callbacks.jl:29) -------------
+            if (p.term_dof >= 0 && tid == 0 && iesh_outside(p, r, v, step + 1)) p.term_step[traj] = step + 1;
+            }
+        save_point:
 
             // ---- save (after the callback) ---------------------------------------------
             if ((step + 1) % p.save_every == 0) {

@@ -167,3 +167,99 @@ def test_run_dynamics_terminating_callback():
     assert np.max(np.abs(mean["OutputStateResolvedScattering1D"]["transmission"] - tsum)) < 1e-12
     with pytest.raises(TypeError):
         nq.TerminatingCallback(lambda u, t, integ: False)
+
+
+# ---- AdiabaticIESH: the CTA-per-trajectory kernel moves on to its next trajectory once terminate! has fired ---------
+def _iesh_case(T=16, nsteps=30, seed=22):
+    from test_parity_gpu import IESH_OBS, _iesh_model, _iesh_random_state
+    rng = np.random.default_rng(seed)
+    model = _iesh_model(30)
+    kw = model_config(model, method=A.METHOD_IESH, masses=[2000.0], ntraj=T, dt=5.0, rng=A.RNG_INJECTED, diagnostics=1,
+                      save_every=3, nsave=nsteps // 3 + 1, observables=IESH_OBS, per_trajectory=1)
+    r = 7.0 + 2.5 * rng.random(T)
+    v = -np.abs(rng.standard_normal(T)) * 6e-3 - 1e-3
+    re, im, state = _iesh_random_state(rng, T, model.nstates, model.nelectrons)
+    xi = rng.random((nsteps, T)) * 5e-4
+    return kw, (r, v, re, im, state), xi, IESH_OBS
+
+
+def _iesh_drive(h, st, xi, window, pieces):
+    if window is not None:
+        h.set_termination(0, *window)
+    h.set_state(*st)
+    h.set_draws(xi)
+    for n in pieces:
+        h.run(n)
+
+
+def test_oracle_iesh_termination_outgoing():
+    """Predicate of the IESH scattering example: beyond the window AND moving outwards; not tested at t0."""
+    kw, st, xi, _ = _iesh_case()
+    o = oracle_factory()(*A.make_config(**kw))
+    _iesh_drive(o, st, xi, (8.0, 1e9, True), (30,))
+    ts = o.termination()
+    r0, v0 = st[0], st[1]
+    assert np.all(ts[r0 + 5.0 * v0 < 7.9] == 1), "already beyond the window: ends after the FIRST step, not at t0"
+    assert (ts > 1).any() and (ts < 0).any()
+    inward = oracle_factory()(*A.make_config(**kw))
+    _iesh_drive(inward, st, xi, (-1e9, 4.0, True), (30,))          # above hi but moving inwards (v < 0): never fires
+    assert np.all(inward.termination() == -1)
+    plain = oracle_factory()(*A.make_config(**kw))
+    _iesh_drive(plain, st, xi, (-1e9, 4.0, False), (30,))           # without the velocity clause it fires at once
+    assert np.all(plain.termination() == 1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("pieces", [(30,), (4, 11, 15)])
+def test_iesh_termination_parity(pieces):
+    kw, st, xi, obs = _iesh_case()
+    e, o = make_pair(engine_factory(), oracle_factory(), **kw)
+    for h in (e, o):
+        _iesh_drive(h, st, xi, (8.0, 1e9, True), pieces)
+    te, to = e.termination(), o.termination()
+    assert (to == 1).any() and (to > 1).any() and (to < 0).any()
+    assert np.array_equal(te, to)
+    se_, so_ = e.get_state(), o.get_state()
+    for key in ("r", "v"):
+        assert rel_err(se_[key], so_[key]) < 1e-9
+    assert np.max(np.abs(se_["sigma"] - so_["sigma"])) < 1e-9
+    assert np.array_equal(se_["state"], so_["state"])
+    for oid in range(A.OBS_COUNT):
+        if obs & (1 << oid):
+            a, b = e.observable_per_trajectory(oid), o.observable_per_trajectory(oid)
+            assert np.max(np.abs(a - b)) <= 1e-8 * max(1.0, np.max(np.abs(b))), f"observable {oid}"
+    ce, co = e.counters(), o.counters()
+    assert (ce["steps"], ce["hops"], ce["frustrated"]) == (co["steps"], co["hops"], co["frustrated"])
+
+
+def test_oracle_time_clause():
+    """`|| t > tcut`: whoever is still running takes the first step that ends beyond tcut and stops there."""
+    T, nsteps = 12, 200
+    kw, r, v, rho, draws, sdraw = _scatter_setup(T, nsteps, save_every=5)
+    o = oracle_factory()(*A.make_config(**kw))
+    _drive(o, r, v, rho, draws, sdraw, (-np.inf, np.inf, False, 37.3), nsteps)
+    assert np.all(o.termination() == 38)
+    assert o.counters()["steps"] == 38 * T
+    o2 = oracle_factory()(*A.make_config(**kw))
+    _drive(o2, r, v, rho, draws, sdraw, None, 38)
+    assert np.array_equal(o.get_state()["r"], o2.get_state()["r"])
+
+
+@pytest.mark.gpu
+def test_time_clause_parity():
+    T, nsteps = 200, 1500
+    kw, r, v, rho, draws, sdraw = _scatter_setup(T, nsteps, seed=17)
+    e, o = make_pair(engine_factory(), oracle_factory(), **kw)
+    for h in (e, o):
+        _drive(h, r, v, rho, draws, sdraw, (-4.5, 4.0, True, 1203.5), nsteps, (600, 900))
+    te, to = e.termination(), o.termination()
+    assert np.array_equal(te, to) and to.max() == 1204 and (to < 1204).any() and (to >= 0).all()
+    assert rel_err(e.get_state()["r"], o.get_state()["r"]) < STEP_TOL
+    a, b = e.observable_per_trajectory(A.OBS_POSITION), o.observable_per_trajectory(A.OBS_POSITION)
+    assert np.max(np.abs(a - b)) < 1e-9
+    kw2, st, xi, obs = _iesh_case()
+    e2, o2 = make_pair(engine_factory(), oracle_factory(), **kw2)
+    for h in (e2, o2):
+        _iesh_drive(h, st, xi, (8.0, 1e9, True, 61.0), (7, 23))          # dt = 5: t > 61 first holds after 13 steps
+    assert np.array_equal(e2.termination(), o2.termination()) and o2.termination().max() == 13
+    assert np.max(np.abs(e2.observable_per_trajectory(A.OBS_DIABATIC_POP) - o2.observable_per_trajectory(A.OBS_DIABATIC_POP))) < 1e-8
