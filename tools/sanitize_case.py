@@ -52,3 +52,39 @@ for method, model, B in [(A.METHOD_FSSH, nq.ThreeStateMorse(), 10), (A.METHOD_EH
         e.set_state_diabatic(r, v, rho)
     e.run(10); e.get_state(); e.close()
     print("ok beads", B)
+# TerminatingCallback masks: TERM instantiation of the thread-per-trajectory kernel, and the IESH kernel's frozen path
+# (terminated trajectories re-entering a later launch rebuild their eigenvectors before the save points)
+T, nsteps = 333, 900
+model = nq.TullyModelOne()
+for method in (A.METHOD_FSSH, A.METHOD_EHRENFEST):
+    kw = dict(method=method, model=model.kind, nstates=2, ndofs=1, masses=[2000.0], ntraj=T, dt=1.0, params=model.params, save_every=7,
+              nsave=nsteps // 7 + 1, per_trajectory=1, seed=5,
+              observables=(1 << A.OBS_POSITION) | (1 << A.OBS_DIABATIC_POP) | (1 << A.OBS_SCATTERING) | (1 << A.OBS_TOTAL_ENERGY))
+    e = Engine(*A.make_config(**kw))
+    e.set_termination(0, -4.5, 1.0, True, 700.5)
+    rho = np.zeros((T, 2, 2)); rho[:, 0, 0] = 1.0
+    e.set_state_diabatic(-3.0 + 0.5 * rng.standard_normal(T), (8.0 + 14.0 * rng.random(T)) / 2000.0, rho)
+    for n in (3, 400, 497):
+        e.run(n)
+    ts = e.termination(); e.counters(); e.observable_per_trajectory(A.OBS_POSITION); e.close()
+    assert (ts >= 0).all() and ts.max() == 701 and (ts < 701).any()
+    print("ok termination", method)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+from test_termination import _iesh_case, _iesh_drive
+kw, st, xi, obs = _iesh_case()
+for method in (A.METHOD_IESH, A.METHOD_EHRENFEST_NA):
+    kw["method"] = method
+    if method == A.METHOD_EHRENFEST_NA:
+        kw["observables"] = (1 << A.OBS_KINETIC) | (1 << A.OBS_POSITION) | (1 << A.OBS_ADIABATIC_POP) | (1 << A.OBS_TOTAL_ENERGY)
+    e = Engine(*A.make_config(**kw))
+    if method == A.METHOD_EHRENFEST_NA:
+        e.set_termination(0, 8.0, 1e9, True, 61.0)
+        e.set_state(st[0], st[1], st[2], st[3], None)
+        for n in (7, 23):
+            e.run(n)
+    else:
+        _iesh_drive(e, st, xi, (8.0, 1e9, True, 61.0), (7, 23))
+    ts = e.termination(); e.observable_per_trajectory(A.OBS_ADIABATIC_POP); e.close()
+    assert ts.max() == 13 and (ts == 1).any()
+    print("ok iesh termination", method)
