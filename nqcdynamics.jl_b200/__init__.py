@@ -18,4 +18,5 @@ from .api import (Atoms, FSSH, Ehrenfest, EhrenfestNA, ThermalLangevin, Classica
                   OutputFinalVelocity, OutputTotalDiabaticPopulation, OutputTotalAdiabaticPopulation, OutputSpringEnergy,
                   OutputCentroidKineticEnergy, OutputFinalTime, OutputDynamicsVariables, OutputInitial, OutputFinal,
                   PopulationCorrelationFunction, SortByTrajectoryReduction, SortByOutputReduction, SumReduction,
-                  MeanReduction, EnsembleB200, run_dynamics, TerminatingCallback, PositionOutside)
+                  MeanReduction, EnsembleB200, run_dynamics, TerminatingCallback, PositionOutside,
+                  OutputSubsetKineticEnergy, OutputFinalSubsetKineticEnergy, OutputKineticTemperature)

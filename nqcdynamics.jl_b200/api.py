@@ -332,6 +332,36 @@ OutputInitial = _Output("OutputInitial", A.OBS_POSITION, "variables_first", _VAR
 OutputFinal = _Output("OutputFinal", A.OBS_POSITION, "variables_last", _VARS)
 
 
+def _atom_indices(indices, natoms):
+    """Julia-style atom selection: ``None`` / ``slice(None)`` = ``:``, otherwise 1-based indices."""
+    if indices is None or (isinstance(indices, slice) and indices == slice(None)):
+        return np.arange(natoms)
+    idx = np.atleast_1d(np.asarray(indices, dtype=np.int64)) - 1
+    if idx.min() < 0 or idx.max() >= natoms:
+        raise IndexError("atom index out of range (indices are 1-based)")
+    return idx
+
+
+@dataclass(frozen=True)
+class _SubsetOutput(_Output):
+    indices: Any = None
+
+
+def OutputSubsetKineticEnergy(indices):                           # DynamicsOutputs.jl:111-117
+    return _SubsetOutput("OutputSubsetKineticEnergy", A.OBS_VELOCITY, "subset_ke", (), indices)
+
+
+def OutputFinalSubsetKineticEnergy(indices):                      # DynamicsOutputs.jl:124-130
+    return _SubsetOutput("OutputFinalSubsetKineticEnergy", A.OBS_VELOCITY, "subset_ke_last", (), indices)
+
+
+def OutputKineticTemperature(indices=None):                       # DynamicsOutputs.jl:501-523 (kelvin)
+    return _SubsetOutput("OutputKineticTemperature", A.OBS_VELOCITY, "kinetic_temperature", (), indices)
+
+
+K_AU = 3.166811563455546e-06      # Boltzmann constant in hartree / K (UnitfulAtomic k_au)
+
+
 def OutputStateResolvedScattering1D(sim, type="adiabatic"):      # DynamicsOutputs.jl:313-338
     if type not in ("adiabatic", "diabatic"):
         raise ValueError(f"{type} not recognised. Only `:diabatic` or `:adiabatic` accepted.")
@@ -432,6 +462,21 @@ def _finalise(sim, out: _Output, arrs: Dict[int, np.ndarray], per_trajectory: bo
         return (arrs[A.OBS_TOTAL_ENERGY] - arrs[A.OBS_KINETIC] - arrs[A.OBS_POTENTIAL])[:, 0]
     if out.kind == "centroid_ke":           # DynamicsOutputs.jl:50-59: sum_i m_i v_centroid,i^2 / 2
         return 0.5 * np.sum(sim.dof_masses * arr * arr, axis=1)
+    if out.kind in ("subset_ke", "subset_ke_last", "kinetic_temperature"):
+        # classical_kinetic_energy(masses[indices], v[:, indices]) per saved frame (DynamicsUtils.jl:108-135)
+        if not per_trajectory:
+            raise ValueError(f"{out.name} is quadratic in the velocity stream: use a per-trajectory reduction")
+        if sim.beads > 1:
+            raise ValueError(f"{out.name}: bead-resolved velocities are not streamed for ring polymers")
+        natoms = len(sim.atoms)
+        idx = _atom_indices(out.indices, natoms)
+        v = _shape_series(sim, OutputVelocity, arr)[:, :, idx]                      # (nsave, ndofs, subset)
+        ke = 0.5 * np.einsum("a,kda->k", np.asarray(sim.atoms.masses, dtype=np.float64)[idx], v * v)
+        if out.kind == "subset_ke_last":
+            return float(ke[-1])
+        if out.kind == "kinetic_temperature":
+            return 2.0 * ke / K_AU / sim.size[0] / len(idx)
+        return ke
     if out.kind.startswith("variables"):
         if not per_trajectory:
             raise ValueError(f"{out.name} is a per-trajectory output (use SortByTrajectoryReduction)")
@@ -663,5 +708,7 @@ def run_dynamics(sim: Simulation, tspan, distribution, *, output, selection: Opt
     for o in outputs:
         if o.kind == "centroid_ke":
             raise ValueError("OutputCentroidKineticEnergy is not linear in the stream: use a per-trajectory reduction")
+        if o.kind in ("subset_ke", "subset_ke_last", "kinetic_temperature"):
+            raise ValueError(f"{o.name} is quadratic in the velocity stream: use a per-trajectory reduction")
         d[o.name] = _finalise(sim, o, summed, False, float(t_end.sum()) * scale)
     return d

@@ -139,3 +139,30 @@ def test_shard_bounds_cover_range():
             assert all(blocks[i][1] == blocks[i + 1][0] for i in range(W - 1))
             sizes = [b - a for a, b in blocks]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_subset_kinetic_outputs_host_logic():
+    """OutputSubsetKineticEnergy / OutputFinalSubsetKineticEnergy / OutputKineticTemperature (DynamicsOutputs.jl:111-130,
+    501-523) assembled from the velocity stream: classical_kinetic_energy(masses[idx], v[:, idx]) per frame."""
+    import numpy as np
+    import nqcdynamics_jl_b200 as nq
+    from nqcdynamics_jl_b200 import api
+    rng = np.random.default_rng(4)
+    masses = np.array([1.0, 3.0, 5.0, 7.0])
+    sim = nq.Simulation[nq.Ehrenfest](nq.Atoms(masses), nq.SpinBoson(nq.DebyeSpectralDensity(0.25, 0.5), 4, 0.0, 1.0))
+    nsave = 6
+    v = rng.standard_normal((nsave, 4))                       # (nsave, ndofs*natoms), ndofs = 1
+    arrs = {api.A.OBS_VELOCITY: v}
+    ke = api._finalise(sim, nq.OutputSubsetKineticEnergy([2, 4]), arrs, True)
+    want = 0.5 * (3.0 * v[:, 1] ** 2 + 7.0 * v[:, 3] ** 2)
+    assert np.allclose(ke, want, rtol=1e-14)
+    assert api._finalise(sim, nq.OutputFinalSubsetKineticEnergy([2, 4]), arrs, True) == pytest.approx(want[-1], rel=1e-14)
+    temp = api._finalise(sim, nq.OutputKineticTemperature(None), arrs, True)
+    full = 0.5 * (v ** 2 * masses).sum(axis=1)
+    assert np.allclose(temp, 2 * full / 3.166811563455546e-06 / 1 / 4, rtol=1e-13)
+    t2 = api._finalise(sim, nq.OutputKineticTemperature([1]), arrs, True)
+    assert np.allclose(t2, 2 * (0.5 * v[:, 0] ** 2) / 3.166811563455546e-06, rtol=1e-13)
+    with pytest.raises(ValueError):
+        api._finalise(sim, nq.OutputSubsetKineticEnergy([1]), arrs, False)
+    with pytest.raises(IndexError):
+        api._finalise(sim, nq.OutputSubsetKineticEnergy([5]), arrs, True)

@@ -155,3 +155,27 @@ def test_ehrenfest_na_through_run_dynamics():
     assert np.allclose(tr["OutputAdiabaticPopulation"].sum(axis=1), model.nelectrons)
     assert tr["OutputQuantumSubsystem"].shape == (201, model.nstates, model.nelectrons)
     assert abs(tr["OutputPosition"][-1].item() - 21.0) > 1e-3
+
+
+def test_subset_kinetic_outputs_through_host_api():
+    """OutputSubsetKineticEnergy / OutputFinalSubsetKineticEnergy / OutputKineticTemperature on a 100-atom bath:
+    the full-system subset reproduces the device's OutputKineticEnergy, subsets add up."""
+    sb = nq.SpinBoson(nq.DebyeSpectralDensity(0.25, 0.5), 100, 0.0, 1.0)
+    sim = nq.Simulation[nq.Ehrenfest](nq.Atoms(np.ones(100)), sb)
+    dist = nq.DynamicalDistribution(nq.Normal(0.0, 0.7), nq.Normal(0.0, 0.5), sim.size) * nq.PureState(1)
+    lo, hi = list(range(1, 41)), list(range(41, 101))
+    outs = (nq.OutputKineticEnergy, nq.OutputSubsetKineticEnergy(None), nq.OutputSubsetKineticEnergy(lo), nq.OutputKineticTemperature(hi),
+            nq.OutputFinalSubsetKineticEnergy(hi), nq.OutputVelocity)
+    res = nq.run_dynamics(sim, (0.0, 2.0), dist, output=outs, trajectories=5, dt=0.1, saveat=0.5, seed=9)
+    for tr in res:
+        ke = tr["OutputKineticEnergy"]
+        # one output name per functor type, as in the reference's Dictionary: the last OutputSubsetKineticEnergy wins
+        sub_lo = tr["OutputSubsetKineticEnergy"]
+        v = tr["OutputVelocity"].reshape(len(ke), 100)
+        assert np.allclose(sub_lo, 0.5 * (v[:, :40] ** 2).sum(axis=1), rtol=1e-13)
+        ke_hi = 0.5 * (v[:, 40:] ** 2).sum(axis=1)
+        assert np.allclose(sub_lo + ke_hi, ke, rtol=1e-12)
+        assert tr["OutputFinalSubsetKineticEnergy"] == pytest.approx(ke_hi[-1], rel=1e-13)
+        assert np.allclose(tr["OutputKineticTemperature"], 2 * ke_hi / 3.166811563455546e-06 / 60, rtol=1e-13)
+    with pytest.raises(ValueError):
+        nq.run_dynamics(sim, (0.0, 1.0), dist, output=nq.OutputKineticTemperature(None), trajectories=4, dt=0.1, reduction=nq.MeanReduction())
