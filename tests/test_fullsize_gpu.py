@@ -83,3 +83,27 @@ def test_rpsh_population_conservation_full_size():
     C = e.observable_sum(A.OBS_POPCORR_DIABATIC)[:ns].reshape(ns, 3, 3)
     assert np.max(np.abs(C.sum(axis=(1, 2)) - T)) < 1e-6 * T
     assert e.counters()["nonfinite"] == 0
+
+
+def test_tully_scattering_with_termination_full_size():
+    """configs[0] the way the reference's scattering scripts run it: TerminatingCallback once the particle has left the
+    interaction region.  The scattering probabilities are those of the run to the end of tspan (beyond r = 4 the
+    coupling is ~exp(-16): about one hop in 10^6 trajectories happens out there), in fewer steps."""
+    wl = workloads.get("tully1_fssh")
+    T = 1 << 20
+    ic = wl.sample(np.random.default_rng(2), T)
+    full = _run(wl, T, wl.nsteps, ic=ic)
+    cfg, keep = A.make_config(**wl.config_kwargs(T, seed=5))
+    term = engine_factory()(cfg, keep)
+    term.set_termination(0, -6.0, 4.0, True)
+    wl.upload(term, ic)
+    term.run(wl.nsteps)
+    ts = term.termination()
+    assert np.count_nonzero(ts < 0) < 0.01 * T, "all but the 3-sigma late starters leave the window within tspan"
+    a, b = full.observable_sum(A.OBS_SCATTERING)[-1], term.observable_sum(A.OBS_SCATTERING)[-1]
+    assert abs(b.sum() - T) < 1e-9 * T
+    assert np.max(np.abs(a - b)) <= 5.0, (a, b)
+    cf, ct = full.counters(), term.counters()
+    assert ct["steps"] == int(np.where(ts >= 0, ts, wl.nsteps).sum()) and ct["steps"] < 0.85 * cf["steps"]
+    assert abs(ct["hops"] - cf["hops"]) <= 5
+    print("masked / full kernel ms:", term.last_run_timing()[0], full.last_run_timing()[0])
