@@ -45,6 +45,12 @@ NCU_DRAM_BYTES_PER_TRAJ = {
     "spinboson_debye100_fssh": (2696.0, "sb_v5"), "spinboson_debye100_ehrenfest": (2696.0, "sb_v5"),
     "tully1_fssh": (236.0, "tully1_v3"), "rpmd_harmonic32": (1356.0, "rpmd_fft"), "rpsh_morse3_16": (664.0, "rpsh_tpt2"),
 }
+# FP64 flops the kernels EXECUTE per trajectory-step (DFMA = 2), from the committed instruction-mix passes
+# profiles/r01/instmix_r01_<tag>.csv (thread-level DFMA/DADD/DMUL counts / (T x steps)); see profiles/r01/SUMMARY.md
+NCU_EXECUTED_FLOPS_PER_TRAJ_STEP = {
+    "spinboson_debye100_fssh": (3630.0, "sb_v5"), "tully1_fssh": (1306.0, "tully1_v3"), "rpmd_harmonic32": (1940.0, "rpmd_tpt"),
+    "rpsh_morse3_16": (12700.0, "rpsh_tpt2"),
+}
 
 
 def parse_args():
@@ -449,6 +455,12 @@ def main():
                                             f"bytes per trajectory of that capture x {T} trajectories (bytes per launch)"
                                             if wl.name in NCU_DRAM_BYTES_PER_TRAJ else None),
                          "flops_per_trajectory_step_algorithmic": flops_step,
+                         "executed": ({"flops_per_trajectory_step": NCU_EXECUTED_FLOPS_PER_TRAJ_STEP[wl.name][0],
+                                       "achieved": NCU_EXECUTED_FLOPS_PER_TRAJ_STEP[wl.name][0] * per_launch_units / kernel_s_per_launch / 1e12,
+                                       "frac": (NCU_EXECUTED_FLOPS_PER_TRAJ_STEP[wl.name][0] * per_launch_units / kernel_s_per_launch / 1e12
+                                                / float(peak.value)) if peak.value else None,
+                                       "source": f"profiles/r01/instmix_r01_{NCU_EXECUTED_FLOPS_PER_TRAJ_STEP[wl.name][1]}.csv"}
+                                      if wl.name in NCU_EXECUTED_FLOPS_PER_TRAJ_STEP else None),
                          "peak_source": "DFMA microbenchmark measured in this run (nqcb200_measure_fp64_peak); "
                                         "MEASURED_PEAKS.json has no FP64 entry",
                          "note": "algorithmic = the reference's dense complex formulation (SURVEY.md 8d); the kernel "
