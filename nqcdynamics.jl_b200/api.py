@@ -217,6 +217,30 @@ class FermiDiracState:
                 state[k] = j
         return np.sort(np.asarray(state, dtype=np.int32)) + 1
 
+    def sample_diabatic(self, rng, H: np.ndarray, nelectrons: int):
+        """``DynamicsVariables(sim, v, r, ::FermiDiracState{Diabatic})`` (iesh.jl:138-184): Fermi-Dirac occupations of
+        the DIABATIC levels diag(H); electron i starts in its diabatic state d_i, i.e. with adiabatic coefficients
+        U[d_i, :] (up to the sign of U[d_i, 1], as the reference normalises by sqrt of the first population), and its
+        discrete adiabatic state is drawn with weights |U[d_i, :]|^2 without repetition.  U is taken in the engine's
+        default gauge (U[k, k] >= 0: column-sign continuity against the identity), so psi means the same thing on the
+        device.  Returns (psi (ne, n), sorted 1-based adiabatic occupations (ne,))."""
+        n = H.shape[0]
+        diab = self.sample_occupations(rng, np.diag(H).copy(), nelectrons) - 1
+        _, U = np.linalg.eigh(H)
+        U = U * np.where(np.diag(U) < 0.0, -1.0, 1.0)[None, :]
+        psi = np.zeros((nelectrons, n))
+        chosen: List[int] = []
+        for i, d in enumerate(diab):
+            row = U[d, :]
+            pop = row * row
+            while True:
+                s = int(rng.choice(n, p=pop / pop.sum()))
+                if s not in chosen:
+                    chosen.append(s)
+                    break
+            psi[i] = row * (row[0] / abs(row[0]))       # adiabatic_density[:, 1] ./ sqrt(adiabatic_population[1])
+        return psi, np.sort(np.asarray(chosen, dtype=np.int32)) + 1
+
 
 @dataclass
 class DynamicalDistribution:
@@ -593,12 +617,21 @@ def run_dynamics(sim: Simulation, tspan, distribution, *, output, selection: Opt
             if abs(electronic.fermi_level - getattr(model, "fermi_level", 0.0)) > 1e-12:
                 raise ValueError("Fermi level of model and distribution do not match")          # iesh.jl:105-112
             occ0 = np.empty((T, ne), dtype=np.int32)
+            diabatic_fd = isinstance(electronic.statetype, Diabatic) or electronic.statetype is Diabatic
+            if diabatic_fd:
+                if mean_field:
+                    raise TypeError("EhrenfestNA: FermiDiracState{Diabatic} is defined for AdiabaticIESH only (iesh.jl:138)")
+                psi0 = np.zeros((T, ne, n))
             for t in range(T):
-                occ0[t] = electronic.sample_occupations(rng, model.adiabatic_energies(r[t].reshape(-1)), ne)
+                if diabatic_fd:
+                    psi0[t], occ0[t] = electronic.sample_diabatic(rng, model.diabatic_hamiltonian(r[t].reshape(-1)), ne)
+                else:
+                    occ0[t] = electronic.sample_occupations(rng, model.adiabatic_energies(r[t].reshape(-1)), ne)
         else:
             raise TypeError("AdiabaticIESH / EhrenfestNA take no electronic distribution (ground state) or a FermiDiracState")
-        psi0 = np.zeros((T, ne, n))
-        psi0[np.arange(T)[:, None], np.arange(ne)[None, :], occ0 - 1] = 1.0
+        if psi0 is None:
+            psi0 = np.zeros((T, ne, n))
+            psi0[np.arange(T)[:, None], np.arange(ne)[None, :], occ0 - 1] = 1.0
 
     ngpus = max(1, int(alg.ngpus))
     if ngpus > device_count():

@@ -35,6 +35,13 @@ class Model:
         initial occupations (the reference does the same inside sample_distribution, iesh.jl:114-120)."""
         if self.kind != _abi.MODEL_ANDERSON_HOLSTEIN_MIAO_SUBOTNIK:
             raise NotImplementedError("adiabatic_energies: only needed for AndersonHolstein initial conditions")
+        return np.linalg.eigvalsh(self.diabatic_hamiltonian(r))
+
+    def diabatic_hamiltonian(self, r) -> np.ndarray:
+        """The n x n electronic Hamiltonian the IESH cache diagonalises (state-independent U0 removed): host-side, for
+        the Fermi-Dirac initial conditions only (iesh.jl:114-120, 153-160)."""
+        if self.kind != _abi.MODEL_ANDERSON_HOLSTEIN_MIAO_SUBOTNIK:
+            raise NotImplementedError("diabatic_hamiltonian: only needed for AndersonHolstein initial conditions")
         m, w, g, dG = self.params
         q = float(np.asarray(r).reshape(-1)[0])
         n = self.nstates
@@ -42,7 +49,7 @@ class Model:
         H[0, 0] = 0.5 * m * w * w * (q - g) ** 2 + dG - 0.5 * m * w * w * q * q
         H[np.arange(1, n), np.arange(1, n)] = self.bath_a
         H[0, 1:] = H[1:, 0] = self.bath_b
-        return np.linalg.eigvalsh(H)
+        return H
 
 
 def TullyModelOne(a=0.01, b=1.6, c=0.005, d=1.0) -> Model:

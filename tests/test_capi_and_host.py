@@ -166,3 +166,27 @@ def test_subset_kinetic_outputs_host_logic():
         api._finalise(sim, nq.OutputSubsetKineticEnergy([1]), arrs, False)
     with pytest.raises(IndexError):
         api._finalise(sim, nq.OutputSubsetKineticEnergy([5]), arrs, True)
+
+
+def test_fermi_dirac_diabatic_initial_conditions_host_logic():
+    """DynamicsVariables(sim, v, r, FermiDiracState{Diabatic}) (iesh.jl:138-184): every electron starts in ONE diabatic
+    level, drawn from the T = 0 Fermi-Dirac filling of diag(H); distinct sorted adiabatic occupations."""
+    import numpy as np
+    import nqcdynamics_jl_b200 as nq
+    model = nq.AndersonHolstein(nq.MiaoSubotnik(Γ=6.4e-3), nq.TrapezoidalRule(30, -0.0192, 0.0192))
+    n, ne = model.nstates, model.nelectrons
+    H = model.diabatic_hamiltonian([21.0])
+    fd = nq.FermiDiracState(0.0, 0.0, nq.Diabatic())
+    rng = np.random.default_rng(8)
+    psi, occ = fd.sample_diabatic(rng, H, ne)
+    assert psi.shape == (ne, n) and occ.shape == (ne,)
+    assert np.all(np.diff(occ) > 0) and occ.min() >= 1 and occ.max() <= n
+    assert np.allclose((psi ** 2).sum(axis=1), 1.0, atol=1e-13)
+    w, U = np.linalg.eigh(H)
+    U = U * np.where(np.diag(U) < 0, -1.0, 1.0)[None, :]
+    back = psi @ U.T                                   # diabatic coefficients of every electron: +-e_d
+    d = np.argmax(np.abs(back), axis=1)
+    assert np.allclose(np.abs(back[np.arange(ne), d]), 1.0, atol=1e-12)
+    lowest = np.sort(np.argsort(np.diag(H), kind="stable")[:ne])
+    assert np.array_equal(np.sort(d), lowest), "T = 0: the ne lowest diabatic levels are filled"
+    assert np.allclose(w, model.adiabatic_energies([21.0]))

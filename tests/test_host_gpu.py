@@ -178,3 +178,35 @@ def test_subset_kinetic_outputs_through_host_api():
         assert np.allclose(tr["OutputKineticTemperature"], 2 * ke_hi / 3.166811563455546e-06 / 60, rtol=1e-13)
     with pytest.raises(ValueError):
         nq.run_dynamics(sim, (0.0, 1.0), dist, output=nq.OutputKineticTemperature(None), trajectories=4, dt=0.1, reduction=nq.MeanReduction())
+
+
+def test_fermi_dirac_diabatic_state_matches_engine_gauge():
+    """FermiDiracState{Diabatic} (iesh.jl:138-184): psi is built on the host from eigenvectors in the engine's default
+    gauge, so Z_engine psi_e must be a single diabatic level; and the state runs through run_dynamics."""
+    from helpers import A, engine_factory, model_config
+    model = nq.AndersonHolstein(nq.MiaoSubotnik(Γ=6.4e-3), nq.TrapezoidalRule(30, -0.0192, 0.0192))
+    n, ne = model.nstates, model.nelectrons
+    T = 6
+    rng = np.random.default_rng(1)
+    r = 18.0 + 6.0 * rng.random(T)
+    fd = nq.FermiDiracState(0.0, 9.5e-4, nq.Diabatic())
+    psi = np.zeros((T, ne, n)); occ = np.zeros((T, ne), dtype=np.int32)
+    for t in range(T):
+        psi[t], occ[t] = fd.sample_diabatic(rng, model.diabatic_hamiltonian([r[t]]), ne)
+    kw = model_config(model, method=A.METHOD_IESH, masses=[2000.0], ntraj=T, dt=1.0, diagnostics=1, nsave=2,
+                      observables=1 << A.OBS_KINETIC)
+    e = engine_factory()(*A.make_config(**kw))
+    e.set_state(r, np.zeros(T), psi, None, occ)
+    Z = e.diagnostics()["Z"]                           # (T, n, n), Z[t][d, k] = <diabatic d | adiabatic k>
+    for t in range(T):
+        dia = psi[t] @ Z[t].T                          # <d | psi_e> = sum_k Z[d, k] psi_e[k]
+        d = np.argmax(np.abs(dia), axis=1)
+        assert np.allclose(np.abs(dia[np.arange(ne), d]), 1.0, atol=1e-9), "one diabatic level per electron"
+        assert len(set(d.tolist())) == ne
+    sim = nq.Simulation[nq.AdiabaticIESH](nq.Atoms(2000), model)
+    dist = nq.DynamicalDistribution(nq.Normal(0.0, 7e-4), nq.Normal(21.0, 1.0), (1, 1)) * fd
+    out = nq.run_dynamics(sim, (0.0, 10.0), dist, output=(nq.OutputDiscreteState, nq.OutputDiabaticPopulation), trajectories=4,
+                          dt=1.0, seed=4)
+    for tr in out:
+        assert tr["OutputDiscreteState"].shape == (11, ne)
+        assert np.allclose(tr["OutputDiabaticPopulation"].sum(axis=1), ne, atol=1e-8)
