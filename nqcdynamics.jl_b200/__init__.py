@@ -10,7 +10,7 @@ from . import _abi
 from ._abi import EngineError
 from .models import *  # noqa: F401,F403
 from .api import (Atoms, FSSH, Ehrenfest, EhrenfestNA, ThermalLangevin, Classical, AdiabaticIESH, NRPMD, Simulation, RingPolymerSimulation, Normal,
-                  VelocityBoltzmann, Diabatic, Adiabatic, PureState, FermiDiracState, DynamicalDistribution, ProductDistribution,
+                  VelocityBoltzmann, Diabatic, Adiabatic, PureState, MixedState, FermiDiracState, DynamicalDistribution, ProductDistribution,
                   OutputDiabaticPopulation, OutputAdiabaticPopulation, OutputKineticEnergy, OutputPotentialEnergy,
                   OutputTotalEnergy, OutputPosition, OutputVelocity, OutputCentroidPosition, OutputCentroidVelocity,
                   OutputDiscreteState, OutputQuantumSubsystem, OutputSurfaceHops, OutputStateResolvedScattering1D,

@@ -184,6 +184,35 @@ class PureState:
 
 
 @dataclass
+class MixedState:
+    """``MixedState(populations, statetype)`` (NQCDistributions; docs/src/NQCDistributions/overview.md:141-155): the
+    initial density matrix is ``Diagonal(populations)`` in the given basis (density_matrix_dynamics.jl:37-62); FSSH
+    draws the active state with weights Re diag(sigma) (fssh.jl:53-54)."""
+    populations: Sequence[float]
+    statetype: Any = field(default_factory=Diabatic)
+
+    def __mul__(self, other):
+        return ProductDistribution(other, self)
+
+    __rmul__ = __mul__
+
+
+def _electronic_density(electronic, n: int) -> np.ndarray:
+    """density_matrix(electronics, nstates) of NQCDistributions for PureState / MixedState (n x n, real diagonal)."""
+    rho = np.zeros((n, n))
+    if isinstance(electronic, MixedState):
+        pops = np.asarray(electronic.populations, dtype=np.float64)
+        if pops.shape != (n,):
+            raise ValueError(f"MixedState needs one population per state ({n})")
+        rho[np.arange(n), np.arange(n)] = pops
+    elif isinstance(electronic, PureState):
+        rho[electronic.state - 1, electronic.state - 1] = 1.0
+    else:
+        raise TypeError("FSSH / Ehrenfest take PureState or MixedState electronic distributions")
+    return rho
+
+
+@dataclass
 class FermiDiracState:
     """``FermiDiracState(fermi_level, temperature)`` in the adiabatic basis (NQCDistributions; used by AdiabaticIESH,
     iesh.jl:99-128): occupations drawn by the reference's Metropolis walk over orbital swaps
@@ -665,9 +694,9 @@ def run_dynamics(sim: Simulation, tspan, distribution, *, output, selection: Opt
                     adiabatic = True
                     if density:
                         n = model.nstates
-                        rho1 = np.zeros((n, n)); rho1[electronic.state - 1, electronic.state - 1] = 1.0
+                        rho1 = _electronic_density(electronic, n)
                         adiabatic = isinstance(electronic.statetype, Adiabatic) or electronic.statetype is Adiabatic
-                    st = electronic.state if (adiabatic and method.method_id == A.METHOD_FSSH) else 0
+                    st = electronic.state if (adiabatic and method.method_id == A.METHOD_FSSH and isinstance(electronic, PureState)) else 0
                     eng.sample_state(dev_spec[0], dev_spec[1], rho1, diabatic=not adiabatic, state=st)
                     rg = vg = None
                 else:
@@ -676,10 +705,15 @@ def run_dynamics(sim: Simulation, tspan, distribution, *, output, selection: Opt
                     pass
                 elif density:
                     n = model.nstates
-                    rho = np.zeros((Tg, n, n))
-                    rho[:, electronic.state - 1, electronic.state - 1] = 1.0
+                    rho = np.tile(_electronic_density(electronic, n), (Tg, 1, 1))
                     adiabatic = isinstance(electronic.statetype, Adiabatic) or electronic.statetype is Adiabatic
-                    state = np.full(Tg, electronic.state, dtype=np.int32) if (adiabatic and method.method_id == A.METHOD_FSSH) else None
+                    state = None
+                    if adiabatic and method.method_id == A.METHOD_FSSH:
+                        if isinstance(electronic, PureState):
+                            state = np.full(Tg, electronic.state, dtype=np.int32)
+                        else:     # sample(Weights(diag(sigma))) per trajectory (fssh.jl:53-54), keyed by the global index
+                            w = np.diag(rho[0]) / np.trace(rho[0])
+                            state = np.array([np.random.default_rng([engine_seed, lo + i]).choice(n, p=w) + 1 for i in range(Tg)], dtype=np.int32)
                     if draws is None:
                         # one call per batch (nqcb200_run_from_host): kernels with a launch-fused initialisation read
                         # r, v in place; everything else behaves like set_state[_diabatic] + run

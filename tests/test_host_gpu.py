@@ -210,3 +210,29 @@ def test_fermi_dirac_diabatic_state_matches_engine_gauge():
     for tr in out:
         assert tr["OutputDiscreteState"].shape == (11, ne)
         assert np.allclose(tr["OutputDiabaticPopulation"].sum(axis=1), ne, atol=1e-8)
+
+
+def test_mixed_state_distribution():
+    """MixedState(populations, basis): sigma(0) = Diagonal(populations) in that basis (density_matrix_dynamics.jl:37-62);
+    FSSH draws the active state with weights diag(sigma) (fssh.jl:53-54)."""
+    sim = nq.Simulation[nq.Ehrenfest](nq.Atoms(2000), nq.TullyModelTwo())
+    nuc = nq.DynamicalDistribution(16.0 / 2000, nq.Normal(-2.0, 0.3), (1, 1))
+    res = nq.run_dynamics(sim, (0.0, 50.0), nuc * nq.MixedState([0.3, 0.7], nq.Diabatic()), output=(nq.OutputDiabaticPopulation,
+                          nq.OutputAdiabaticPopulation), trajectories=16, dt=1.0, saveat=10.0, seed=6)
+    for tr in res:
+        assert np.allclose(tr["OutputDiabaticPopulation"][0], [0.3, 0.7], atol=1e-12)      # U (U' rho U) U' = rho
+        assert np.allclose(tr["OutputDiabaticPopulation"].sum(axis=1), 1.0, atol=1e-9)
+    res = nq.run_dynamics(sim, (0.0, 50.0), nuc * nq.MixedState([0.2, 0.8], nq.Adiabatic()), output=nq.OutputAdiabaticPopulation,
+                          trajectories=4, dt=1.0, saveat=10.0, seed=6)
+    for tr in res:
+        assert np.allclose(tr["OutputAdiabaticPopulation"][0], [0.2, 0.8], atol=1e-12)
+    fssh = nq.Simulation[nq.FSSH](nq.Atoms(2000), nq.TullyModelTwo())
+    T = 4000
+    for basis in (nq.Adiabatic(), nq.Diabatic()):
+        out = nq.run_dynamics(fssh, (0.0, 10.0), nq.DynamicalDistribution(16.0 / 2000, -9.0, (1, 1)) * nq.MixedState([1.0, 3.0], basis),
+                              output=nq.OutputDiscreteState, trajectories=T, dt=1.0, saveat=10.0, seed=7, reduction=nq.SortByOutputReduction())
+        first = np.array([s[0] for s in out["OutputDiscreteState"]])
+        frac2 = np.mean(first == 2)                        # at r = -9 the bases coincide: weights 1 : 3 either way
+        assert abs(frac2 - 0.75) < 5 * np.sqrt(0.75 * 0.25 / T), frac2
+    with pytest.raises(ValueError):
+        nq.run_dynamics(sim, (0.0, 5.0), nuc * nq.MixedState([1.0], nq.Diabatic()), output=nq.OutputDiabaticPopulation, trajectories=2)
