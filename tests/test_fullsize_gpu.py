@@ -107,3 +107,36 @@ def test_tully_scattering_with_termination_full_size():
     assert ct["steps"] == int(np.where(ts >= 0, ts, wl.nsteps).sum()) and ct["steps"] < 0.85 * cf["steps"]
     assert abs(ct["hops"] - cf["hops"]) <= 5
     print("masked / full kernel ms:", term.last_run_timing()[0], full.last_run_timing()[0])
+
+
+def test_iesh_termination_frees_the_cta():
+    """AdiabaticIESH scattering (iesh.md:127-138): one CTA per trajectory, so a terminated trajectory hands its CTA to the
+    next one -- the masked run takes the steps the oracle semantics say and correspondingly less device time."""
+    from test_parity_gpu import _iesh_model
+    from helpers import model_config
+    model = _iesh_model(30)
+    n, ne = model.nstates, model.nelectrons
+    T, nsteps = 148 * 16, 120
+    rng = np.random.default_rng(12)
+    r = 7.0 + 2.0 * rng.random(T)                     # half start beyond the window edge at 8 and leave after one step
+    v = -np.abs(rng.standard_normal(T)) * 2e-3 - 1e-4
+    psi = np.zeros((T, ne, n)); psi[:, np.arange(ne), np.arange(ne)] = 1.0
+    occ = np.tile(np.arange(1, ne + 1, dtype=np.int32), (T, 1))
+    kw = model_config(model, method=A.METHOD_IESH, masses=[2000.0], ntraj=T, dt=5.0, seed=3, save_every=10, nsave=nsteps // 10 + 1,
+                      observables=(1 << A.OBS_KINETIC) | (1 << A.OBS_POSITION) | (1 << A.OBS_ADIABATIC_POP))
+    runs = {}
+    for masked in (False, True):
+        e = engine_factory()(*A.make_config(**kw))
+        if masked:
+            e.set_termination(0, 8.0, 1e9, True)
+        e.set_state(r, v, psi, None, occ)
+        e.run(nsteps)
+        runs[masked] = (e.last_run_timing()[0], e.counters()["steps"], e.termination(), e.observable_sum(A.OBS_ADIABATIC_POP))
+    ms_full, steps_full, _, pop_full = runs[False]
+    ms_mask, steps_mask, ts, pop_mask = runs[True]
+    assert steps_full == T * nsteps
+    assert steps_mask == int(np.where(ts >= 0, ts, nsteps).sum()) and steps_mask < 0.7 * steps_full
+    assert np.count_nonzero(ts == 1) > 0.3 * T
+    assert np.allclose(pop_mask.sum(axis=1), T * ne, rtol=1e-12) and np.allclose(pop_full.sum(axis=1), T * ne, rtol=1e-12)
+    print("IESH masked / full kernel ms:", ms_mask, ms_full, "steps", steps_mask, steps_full)
+    assert ms_mask < 0.85 * ms_full
