@@ -66,6 +66,17 @@ def cases():
                                      dt=2.5, nbeads=8, temperature=9.5e-4, nrpmd_gamma=2e-3, save_every=20, nsave=11,
                                      observables=CLASSICAL_OBS), nsteps=200, r=0.2 * rng.standard_normal((T, 8, 1)),
                                      v=np.sqrt(9.5e-4 * 8 / 1837.47) * rng.standard_normal((T, 8, 1)), state0=None, noise=True)
+    # TerminatingCallback masks (callbacks.jl:29): scattering off TullyModelOne with the window / outward-velocity / tcut
+    # predicate, and the IESH scattering form of iesh.md:127-138
+    out["tully1_fssh_terminating"] = dict(model=nq.TullyModelOne(), kw=dict(method=A.METHOD_FSSH, masses=[2000.0], dt=1.0, save_every=20,
+                                          nsave=61, observables=ALL_POP_OBS | (1 << A.OBS_DISCRETE_STATE)), nsteps=1200,
+                                          r=rng.normal(-3.0, 0.5, (T, 1, 1)), v=(8.0 + 14.0 * rng.random((T, 1, 1))) / 2000, state0=1,
+                                          termination=(0, -4.5, 3.0, True, 1100.5))
+    out["iesh_m30_terminating"] = dict(model=ah, kw=dict(method=A.METHOD_IESH, masses=[2000.0], dt=5.0, save_every=5, nsave=9,
+                                       observables=(1 << A.OBS_ADIABATIC_POP) | (1 << A.OBS_DIABATIC_POP) | (1 << A.OBS_TOTAL_ENERGY) |
+                                                   (1 << A.OBS_POSITION)), nsteps=40,
+                                       r=7.0 + 2.5 * rng.random((T, 1, 1)), v=-np.abs(rng.standard_normal((T, 1, 1))) * 6e-3 - 1e-3,
+                                       state0="iesh", draw_scale=2e-4, termination=(0, 8.0, 1e9, True, 161.0))
     return out, T, rng
 
 
@@ -73,6 +84,8 @@ def run_case(make, case, T, draws, sdraw, noise=None):
     kw = model_config(case["model"], ntraj=T, rng=A.RNG_INJECTED, **case["kw"])
     cfg, keep = A.make_config(**kw)
     h = make(cfg, keep)
+    if "termination" in case:
+        h.set_termination(*case["termination"])
     if case["state0"] is None:
         h.set_state(case["r"], case["v"])
         if noise is not None:
@@ -98,6 +111,8 @@ def run_case(make, case, T, draws, sdraw, noise=None):
     for oid in range(A.OBS_COUNT):
         if case["kw"]["observables"] & (1 << oid):
             res[f"obs{oid}"] = h.observable_sum(oid)
+    if "termination" in case:
+        res["term_step"] = h.termination().astype(np.float64)
     return res
 
 

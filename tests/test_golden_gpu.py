@@ -13,7 +13,8 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 @pytest.mark.parametrize("name", ["tully1_fssh", "spinboson_fssh", "spinboson_ehrenfest", "rpmd_harmonic32", "rpsh_morse3_16",
-                                  "iesh_m30", "ehrenfest_na_m30", "rpsh_morse3_10", "langevin_harmonic8"])
+                                  "iesh_m30", "ehrenfest_na_m30", "rpsh_morse3_10", "langevin_harmonic8",
+                                  "tully1_fssh_terminating", "iesh_m30_terminating"])
 def test_engine_reproduces_golden(name):
     cs, T, _ = make_golden.cases()
     g = np.load(os.path.join(GOLDEN, f"engine_{name}.npz"))
