@@ -122,6 +122,9 @@ def test_termination_reset_and_unsupported():
     assert (first >= 0).any()
     _drive(e, r, v, rho, draws, sdraw, (-4.5, 4.0), nsteps)      # set_state resets the flags: same answer again
     assert np.array_equal(e.termination(), first)
+    for bad in ((3, -1.0, 1.0), (0, 2.0, 1.0), (0, float("nan"), 1.0)):     # dof out of range, empty window, NaN bound
+        with pytest.raises(nq.EngineError):
+            e.set_termination(*bad)
     e.set_termination(-1, 0.0, 0.0)                               # callback removed
     _drive(e, r, v, rho, draws, sdraw, None, nsteps)
     assert np.all(e.termination() == -1)
