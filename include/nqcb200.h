@@ -137,7 +137,9 @@ enum nqcb200_rng {
  *  SCATTERING      2n       OutputStateResolvedScattering1D(:adiabatic) :313-338 -- final state only:
  *                           [reflection(n), transmission(n)], transmission iff r[0] > 0
  *  SCATTERING_DIABATIC 2n   same with type=:diabatic
- *  SIGMA           2*n*n    OutputQuantumSubsystem :149 (re then im, column-major)                */
+ *  SIGMA           2*n*n    OutputQuantumSubsystem :149 (re then im, column-major)
+ *  MAPPING_Q       n*B      OutputMappingPosition :157 (NRPMD; (nstates, nbeads) column-major, as nqcb200_set_mapping)
+ *  MAPPING_P       n*B      OutputMappingMomentum :165                                             */
 enum nqcb200_observable {
     NQCB200_OBS_ADIABATIC_POP       = 0,
     NQCB200_OBS_DIABATIC_POP        = 1,
@@ -152,7 +154,9 @@ enum nqcb200_observable {
     NQCB200_OBS_SCATTERING          = 10,
     NQCB200_OBS_SCATTERING_DIABATIC = 11,
     NQCB200_OBS_SIGMA               = 12,
-    NQCB200_OBS_COUNT               = 13
+    NQCB200_OBS_MAPPING_Q           = 13,
+    NQCB200_OBS_MAPPING_P           = 14,
+    NQCB200_OBS_COUNT               = 15
 };
 
 #define NQCB200_MAX_PARAMS 32

@@ -19,4 +19,5 @@ from .api import (Atoms, FSSH, Ehrenfest, EhrenfestNA, ThermalLangevin, Classica
                   OutputCentroidKineticEnergy, OutputFinalTime, OutputDynamicsVariables, OutputInitial, OutputFinal,
                   PopulationCorrelationFunction, SortByTrajectoryReduction, SortByOutputReduction, SumReduction,
                   MeanReduction, EnsembleB200, run_dynamics, TerminatingCallback, PositionOutside,
-                  OutputSubsetKineticEnergy, OutputFinalSubsetKineticEnergy, OutputKineticTemperature)
+                  OutputSubsetKineticEnergy, OutputFinalSubsetKineticEnergy, OutputKineticTemperature,
+                  OutputMappingPosition, OutputMappingMomentum)

@@ -25,8 +25,8 @@ RESCALE_STANDARD, RESCALE_VINVERSION, RESCALE_OFF = 0, 1, 2
 RNG_PHILOX, RNG_INJECTED = 0, 1
 (OBS_ADIABATIC_POP, OBS_DIABATIC_POP, OBS_POPCORR_DIABATIC, OBS_POPCORR_ADIABATIC, OBS_KINETIC,
  OBS_POTENTIAL, OBS_TOTAL_ENERGY, OBS_POSITION, OBS_VELOCITY, OBS_DISCRETE_STATE, OBS_SCATTERING,
- OBS_SCATTERING_DIABATIC, OBS_SIGMA) = range(13)
-OBS_COUNT = 13
+ OBS_SCATTERING_DIABATIC, OBS_SIGMA, OBS_MAPPING_Q, OBS_MAPPING_P) = range(15)
+OBS_COUNT = 15
 
 ERRORS = {0: "ok", -1: "invalid argument", -2: "unsupported configuration (no kernel, no CPU fallback)",
           -3: "no CUDA device", -4: "CUDA error", -5: "call order violated", -6: "out of memory"}

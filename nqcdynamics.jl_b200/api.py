@@ -379,6 +379,8 @@ OutputSpringEnergy = _Output("OutputSpringEnergy", A.OBS_TOTAL_ENERGY, "spring",
                              (A.OBS_TOTAL_ENERGY, A.OBS_KINETIC, A.OBS_POTENTIAL))
 OutputCentroidKineticEnergy = _Output("OutputCentroidKineticEnergy", A.OBS_VELOCITY, "centroid_ke")
 OutputFinalTime = _Output("OutputFinalTime", A.OBS_KINETIC, "final_time")
+OutputMappingPosition = _Output("OutputMappingPosition", A.OBS_MAPPING_Q)      # DynamicsOutputs.jl:157 (NRPMD)
+OutputMappingMomentum = _Output("OutputMappingMomentum", A.OBS_MAPPING_P)      # DynamicsOutputs.jl:165
 _VARS = (A.OBS_POSITION, A.OBS_VELOCITY, A.OBS_SIGMA, A.OBS_DISCRETE_STATE)
 OutputDynamicsVariables = _Output("OutputDynamicsVariables", A.OBS_POSITION, "variables", _VARS)
 OutputInitial = _Output("OutputInitial", A.OBS_POSITION, "variables_first", _VARS)
@@ -488,6 +490,8 @@ def _shape_series(sim, out: _Output, arr: np.ndarray):
         ncol = sim.model.nelectrons if sim.method.method_id in A.IESH_FAMILY else n      # psi is (n, ne) for IESH
         c = arr.reshape(-1, 2, ncol, n)
         return (c[:, 0] + 1j * c[:, 1]).transpose(0, 2, 1)
+    if out.obs in (A.OBS_MAPPING_Q, A.OBS_MAPPING_P):
+        return arr.reshape(-1, sim.beads, n).transpose(0, 2, 1)                          # (nsave, nstates, nbeads) per frame
     if out.obs in (A.OBS_POSITION, A.OBS_VELOCITY):
         return arr.reshape((-1,) + tuple(reversed(sim.size[:2]))).transpose(0, 2, 1)   # (nsave, ndofs, natoms)
     if arr.shape[1] == 1:
@@ -662,6 +666,17 @@ def run_dynamics(sim: Simulation, tspan, distribution, *, output, selection: Opt
             psi0 = np.zeros((T, ne, n))
             psi0[np.arange(T)[:, None], np.arange(ne)[None, :], occ0 - 1] = 1.0
 
+    qmap0 = pmap0 = None
+    if method.method_id == A.METHOD_NRPMD:
+        # DynamicsVariables(sim::RingPolymerSimulation{<:NRPMD}, v, r, ::PureState{Diabatic}) (nrpmd.jl:47-65): one random
+        # angle per state and bead; radius sqrt(2 + 2 gamma) on the occupied state, sqrt(2 gamma) on the others
+        if not isinstance(electronic, PureState) or isinstance(electronic.statetype, Adiabatic) or electronic.statetype is Adiabatic:
+            raise TypeError("NRPMD takes nuclear * PureState(i, Diabatic())")
+        n, g = model.nstates, float(method.γ)
+        theta = rng.random((T, sim.beads, n)) * 2.0 * np.pi
+        radius = np.full(n, math.sqrt(2.0 * g)); radius[electronic.state - 1] = math.sqrt(2.0 + 2.0 * g)
+        qmap0, pmap0 = np.cos(theta) * radius, np.sin(theta) * radius
+
     ngpus = max(1, int(alg.ngpus))
     if ngpus > device_count():
         raise RuntimeError(f"EnsembleB200({ngpus}) but only {device_count()} CUDA device(s) visible")
@@ -725,6 +740,9 @@ def run_dynamics(sim: Simulation, tspan, distribution, *, output, selection: Opt
                         eng.set_state_diabatic(rg, vg, rho)
                 elif iesh:
                     eng.set_state(rg, vg, psi0[lo:hi], None, None if mean_field else occ0[lo:hi])
+                elif method.method_id == A.METHOD_NRPMD:
+                    eng.set_state(rg, vg)
+                    eng.set_mapping(qmap0[lo:hi], pmap0[lo:hi])
                 else:
                     eng.set_state(rg, vg)
                 if draws is not None:

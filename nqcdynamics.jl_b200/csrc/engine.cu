@@ -171,6 +171,7 @@ int obs_width(const nqcb200_config& c, int id) {
         case NQCB200_OBS_DISCRETE_STATE: return iesh_family(c.method) ? c.nelectrons : 1;
         case NQCB200_OBS_SCATTERING: case NQCB200_OBS_SCATTERING_DIABATIC: return 2 * n;
         case NQCB200_OBS_SIGMA: return iesh_family(c.method) ? 2 * n * c.nelectrons : 2 * n * n;
+        case NQCB200_OBS_MAPPING_Q: case NQCB200_OBS_MAPPING_P: return c.method == NQCB200_METHOD_NRPMD ? n * c.nbeads : 0;
     }
     return 0;
 }
@@ -416,6 +417,9 @@ int nqcb200_create(const nqcb200_config* cfg, nqcb200_handle** out) {
     if (cfg->method == NQCB200_METHOD_EHRENFEST_NA &&
         (cfg->observables & ((1u << NQCB200_OBS_DIABATIC_POP) | (1u << NQCB200_OBS_SCATTERING_DIABATIC) | (1u << NQCB200_OBS_DISCRETE_STATE)))) {
         g_create_error = "EhrenfestNA has no discrete state and no diabatic-population estimator"; return NQCB200_ERR_UNSUPPORTED;
+    }
+    if (cfg->method != NQCB200_METHOD_NRPMD && (cfg->observables & ((1u << NQCB200_OBS_MAPPING_Q) | (1u << NQCB200_OBS_MAPPING_P)))) {
+        g_create_error = "mapping variables exist for NRPMD only"; return NQCB200_ERR_UNSUPPORTED;
     }
     if (iesh_family(cfg->method) &&
         (cfg->observables & ((1u << NQCB200_OBS_POPCORR_DIABATIC) | (1u << NQCB200_OBS_POPCORR_ADIABATIC)))) {

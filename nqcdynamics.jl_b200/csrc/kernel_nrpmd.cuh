@@ -71,6 +71,20 @@ NQ_D void nrpmd_record_save(const KParams& p, Emitter& em, int lane, int group_b
         if (obs & (1u << NQCB200_OBS_POSITION)) em.emit(NQCB200_OBS_POSITION, 0, rc);
         if (obs & (1u << NQCB200_OBS_VELOCITY)) em.emit(NQCB200_OBS_VELOCITY, 0, vc);
     }
+    if (obs & ((1u << NQCB200_OBS_MAPPING_Q) | (1u << NQCB200_OBS_MAPPING_P))) {
+        // OutputMappingPosition / OutputMappingMomentum (DynamicsOutputs.jl:157,165): bead b's variables travel to the
+        // group's lane 0, which carries the trajectory's values into the stream ((nstates, nbeads) column-major)
+#pragma unroll 1
+        for (int b = 0; b < NB; ++b) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                const double qb = __shfl_sync(0xffffffffu, q[i], group_base + b);
+                const double pb = __shfl_sync(0xffffffffu, pm[i], group_base + b);
+                if (obs & (1u << NQCB200_OBS_MAPPING_Q)) em.emit(NQCB200_OBS_MAPPING_Q, i + N * b, qb);
+                if (obs & (1u << NQCB200_OBS_MAPPING_P)) em.emit(NQCB200_OBS_MAPPING_P, i + N * b, pb);
+            }
+        }
+    }
 }
 
 template <class M>

@@ -91,6 +91,7 @@ static int obs_width(const nqcb200_config& c, int id) {
         case NQCB200_OBS_DISCRETE_STATE: return iesh_family(c.method) ? c.nelectrons : 1;
         case NQCB200_OBS_SCATTERING: case NQCB200_OBS_SCATTERING_DIABATIC: return 2 * n;
         case NQCB200_OBS_SIGMA: return iesh_family(c.method) ? 2 * n * c.nelectrons : 2 * n * n;
+        case NQCB200_OBS_MAPPING_Q: case NQCB200_OBS_MAPPING_P: return c.method == NQCB200_METHOD_NRPMD ? n * c.nbeads : 0;
     }
     return 0;
 }
@@ -171,6 +172,11 @@ static void record_save(nqco_handle* h, int64_t isave) {
                 case NQCB200_OBS_SIGMA: {
                     int len = h->L.width[id] / 2;
                     for (int i = 0; i < len; ++i) { o[i] = tr.sigma[i].real(); o[len + i] = tr.sigma[i].imag(); }
+                } break;
+                case NQCB200_OBS_MAPPING_Q:      // OutputMappingPosition / Momentum, DynamicsOutputs.jl:157,165
+                case NQCB200_OBS_MAPPING_P: {
+                    const vec& m = (id == NQCB200_OBS_MAPPING_Q) ? tr.qmap : tr.pmap;
+                    for (int i = 0; i < h->L.width[id]; ++i) o[i] = m[i];
                 } break;
             }
             p += h->L.width[id];

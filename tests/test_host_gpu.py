@@ -236,3 +236,24 @@ def test_mixed_state_distribution():
         assert abs(frac2 - 0.75) < 5 * np.sqrt(0.75 * 0.25 / T), frac2
     with pytest.raises(ValueError):
         nq.run_dynamics(sim, (0.0, 5.0), nuc * nq.MixedState([1.0], nq.Diabatic()), output=nq.OutputDiabaticPopulation, trajectories=2)
+
+
+def test_nrpmd_through_host_api():
+    """RingPolymerSimulation{NRPMD} through run_dynamics (nrpmd.jl:47-65 initial mapping variables): populations start
+    on the PureState, the mapping-variable outputs have the reference's (nstates, nbeads) frames and radii."""
+    B, g = 4, 0.5
+    sim = nq.RingPolymerSimulation[nq.NRPMD](nq.Atoms(1.0), nq.DoubleWell(), B, γ=g, temperature=1.0)
+    dist = nq.DynamicalDistribution(nq.Normal(0.0, 0.5), nq.Normal(0.0, 0.3), sim.size) * nq.PureState(1, nq.Diabatic())
+    outs = (nq.OutputDiabaticPopulation, nq.OutputMappingPosition, nq.OutputMappingMomentum, nq.OutputTotalEnergy)
+    res = nq.run_dynamics(sim, (0.0, 1.0), dist, output=outs, trajectories=6, dt=0.01, saveat=0.1, seed=8)
+    for tr in res:
+        q, p = tr["OutputMappingPosition"], tr["OutputMappingMomentum"]
+        assert q.shape == (11, 2, B) and p.shape == (11, 2, B)
+        rad2 = q[0] ** 2 + p[0] ** 2
+        assert np.allclose(rad2[0], 2 + 2 * g) and np.allclose(rad2[1], 2 * g)
+        assert np.allclose(tr["OutputDiabaticPopulation"][0], [1.0, 0.0], atol=1e-12)       # (q^2 + p^2)/2 - gamma per bead
+        E = tr["OutputTotalEnergy"]
+        assert np.max(np.abs(E - E[0])) < 1e-3 * max(1.0, abs(E[0]))
+        assert not np.array_equal(q[0], q[-1])
+    with pytest.raises(TypeError):
+        nq.run_dynamics(sim, (0.0, 0.1), dist.nuclear * nq.PureState(1, nq.Adiabatic()), output=nq.OutputDiabaticPopulation, dt=0.01)

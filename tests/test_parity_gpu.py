@@ -289,7 +289,7 @@ def test_nrpmd_parity(nbeads, name, model, mass, r0, temp):
     n = model.nstates
     rng = np.random.default_rng(23)
     obs = ((1 << A.OBS_DIABATIC_POP) | (1 << A.OBS_POPCORR_DIABATIC) | (1 << A.OBS_KINETIC) | (1 << A.OBS_POTENTIAL) |
-           (1 << A.OBS_TOTAL_ENERGY) | (1 << A.OBS_POSITION) | (1 << A.OBS_VELOCITY))
+           (1 << A.OBS_TOTAL_ENERGY) | (1 << A.OBS_POSITION) | (1 << A.OBS_VELOCITY) | (1 << A.OBS_MAPPING_Q) | (1 << A.OBS_MAPPING_P))
     dt = 0.01 if mass < 100 else 1.0
     kw = model_config(model, method=A.METHOD_NRPMD, masses=[mass], ntraj=T, dt=dt, nbeads=nbeads, temperature=temp,
                       save_every=10, nsave=nsteps // 10 + 1, observables=obs, per_trajectory=1, nrpmd_gamma=0.5)
@@ -309,6 +309,12 @@ def test_nrpmd_parity(nbeads, name, model, mass, r0, temp):
         assert np.max(np.abs(qe - qo)) < 1e-10 and np.max(np.abs(pe - po)) < 1e-10
     _compare_observables(e, o, obs, 1e-9, T)
     assert np.max(np.abs(e.observable_per_trajectory(A.OBS_TOTAL_ENERGY) - o.observable_per_trajectory(A.OBS_TOTAL_ENERGY))) < 1e-9
+    # OutputMappingPosition / OutputMappingMomentum streams: frame 0 is what set_mapping uploaded, the last frame is get_mapping
+    for oid, first, last in ((A.OBS_MAPPING_Q, q, e.get_mapping()[0]), (A.OBS_MAPPING_P, p, e.get_mapping()[1])):
+        se_, so_ = e.observable_per_trajectory(oid), o.observable_per_trajectory(oid)
+        assert np.max(np.abs(se_ - so_)) < 1e-9
+        assert np.array_equal(se_[:, 0].reshape(T, nbeads, n), first)
+        assert np.array_equal(se_[:, -1].reshape(T, nbeads, n), np.asarray(last).reshape(T, nbeads, n))
 
 
 def test_unsupported_configuration_fails_loudly():
