@@ -212,7 +212,13 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     dist = None
     torch = None
+    stdout_fd = None
     if world > 1:
+        # stdout carries exactly one JSON line: whatever libraries write to fd 1 meanwhile (NCCL prints its
+        # "NCCL version ..." banner there when the communicator is created) is sent to stderr until the line is printed
+        sys.stdout.flush()
+        stdout_fd = os.dup(1)
+        os.dup2(2, 1)
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
@@ -470,6 +476,9 @@ def main():
             "batch_prepare_ms": 1e3 * prep / K,
             "observable_checksum": obs_check,
         }
+        if stdout_fd is not None:
+            sys.stdout.flush()
+            os.dup2(stdout_fd, 1)
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
