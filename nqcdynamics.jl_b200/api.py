@@ -481,6 +481,15 @@ class EnsembleB200:
 
 
 # ---- run_dynamics ----------------------------------------------------------------------------------
+def sample_nrpmd_mapping(rng, T: int, nbeads: int, nstates: int, state: int, γ: float):
+    """Initial NRPMD mapping variables (nrpmd.jl:47-65): theta ~ U[0, 2 pi) per state and bead, (q, p) = R (cos, sin) with
+    R = sqrt(2 + 2 gamma) on the occupied (1-based) state and sqrt(2 gamma) elsewhere.  Returns (T, nbeads, nstates) arrays."""
+    theta = rng.random((T, nbeads, nstates)) * 2.0 * np.pi
+    radius = np.full(nstates, math.sqrt(2.0 * γ))
+    radius[state - 1] = math.sqrt(2.0 + 2.0 * γ)
+    return np.cos(theta) * radius, np.sin(theta) * radius
+
+
 def _shape_series(sim, out: _Output, arr: np.ndarray):
     """arr: (nsave, width) -> the reference's per-frame value shape."""
     n = sim.model.nstates
@@ -672,10 +681,7 @@ def run_dynamics(sim: Simulation, tspan, distribution, *, output, selection: Opt
         # angle per state and bead; radius sqrt(2 + 2 gamma) on the occupied state, sqrt(2 gamma) on the others
         if not isinstance(electronic, PureState) or isinstance(electronic.statetype, Adiabatic) or electronic.statetype is Adiabatic:
             raise TypeError("NRPMD takes nuclear * PureState(i, Diabatic())")
-        n, g = model.nstates, float(method.γ)
-        theta = rng.random((T, sim.beads, n)) * 2.0 * np.pi
-        radius = np.full(n, math.sqrt(2.0 * g)); radius[electronic.state - 1] = math.sqrt(2.0 + 2.0 * g)
-        qmap0, pmap0 = np.cos(theta) * radius, np.sin(theta) * radius
+        qmap0, pmap0 = sample_nrpmd_mapping(rng, T, sim.beads, model.nstates, electronic.state, float(method.γ))
 
     ngpus = max(1, int(alg.ngpus))
     if ngpus > device_count():

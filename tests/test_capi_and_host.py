@@ -190,3 +190,19 @@ def test_fermi_dirac_diabatic_initial_conditions_host_logic():
     lowest = np.sort(np.argsort(np.diag(H), kind="stable")[:ne])
     assert np.array_equal(np.sort(d), lowest), "T = 0: the ne lowest diabatic levels are filled"
     assert np.allclose(w, model.adiabatic_energies([21.0]))
+
+
+def test_nrpmd_initial_mapping_kat():
+    """test/Dynamics/nrpmd.jl:27-40 ("Population correlation"): with DynamicsVariables(sim, v, r, PureState(1)) the
+    averaged K(0) K(0)' is [1 0; 0 0] (atol 0.1 there; exact here, because every sample has populations (1, 0))."""
+    import numpy as np
+    from nqcdynamics_jl_b200 import api
+    rng = np.random.default_rng(1)
+    q, p = api.sample_nrpmd_mapping(rng, 10_000, 10, 2, 1, 0.5)
+    pop = ((q ** 2 + p ** 2) / 2 - 0.5).mean(axis=1)               # Estimators.diabatic_population, nrpmd.jl:111-122
+    out = np.einsum("ti,tj->ij", pop, pop) / len(pop)
+    assert np.allclose(out, [[1, 0], [0, 0]], atol=1e-12)
+    th = np.arctan2(p, q) % (2 * np.pi)
+    assert abs(th.mean() - np.pi) < 0.02 and abs(th.var() - (2 * np.pi) ** 2 / 12) < 0.05      # uniform angles
+    q2, p2 = api.sample_nrpmd_mapping(rng, 4, 3, 3, 2, 0.0)         # gamma = 0: unoccupied states sit at the origin
+    assert np.all(q2[:, :, [0, 2]] == 0) and np.allclose(q2[:, :, 1] ** 2 + p2[:, :, 1] ** 2, 2.0)
