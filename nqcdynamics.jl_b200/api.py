@@ -481,6 +481,22 @@ class EnsembleB200:
 
 
 # ---- run_dynamics ----------------------------------------------------------------------------------
+def _trim_terminated(time: np.ndarray, arrs: Dict[int, np.ndarray], term_step: int, save_every: int, t_end: float):
+    """Fixed-shape device stream of one trajectory -> the frames a DiffEq solution holds after ``terminate!``.
+
+    sol.t of a terminated trajectory: the saveat points <= t_term, then the terminal state saved before and after the
+    affect (DiscreteCallback ``save_positions = (true, true)``; the pre-affect copy is skipped when t_term is itself a
+    saveat point).  The device stream carries the terminal state from save index ``term_step // save_every + 1`` on, so
+    that index provides the appended frames.  The scattering observables are final-frame quantities and stay whole."""
+    if term_step < 0:
+        return time, arrs
+    kf, rem = divmod(term_step, save_every)
+    idx = list(range(kf + 1)) + ([kf + 1, kf + 1] if rem else [kf])
+    ti = np.concatenate([time[:kf + 1], np.full(len(idx) - kf - 1, t_end)])
+    keep_whole = (A.OBS_SCATTERING, A.OBS_SCATTERING_DIABATIC)
+    return ti, {k: (a if k in keep_whole else a[idx]) for k, a in arrs.items()}
+
+
 def sample_nrpmd_mapping(rng, T: int, nbeads: int, nstates: int, state: int, γ: float):
     """Initial NRPMD mapping variables (nrpmd.jl:47-65): theta ~ U[0, 2 pi) per state and bead, (q, p) = R (cos, sin) with
     R = sqrt(2 + 2 gamma) on the occupied (1-based) state and sqrt(2 gamma) elsewhere.  Returns (T, nbeads, nstates) arrays."""
@@ -777,14 +793,7 @@ def run_dynamics(sim: Simulation, tspan, distribution, *, output, selection: Opt
         per_obs = {k: np.concatenate([res[k] for res in results], axis=0) for k in obs_ids}    # (T, nsave, w)
         trajs = []
         for i in range(T):
-            ti, arrs = time, {k: per_obs[k][i] for k in obs_ids}
-            if term[i] >= 0:
-                # sol.t of a terminated trajectory: saveat points <= t_term, then the terminal state twice (see docstring);
-                # save index kf + 1 of the device stream holds the terminal state when t_term is not a saveat point
-                kf, rem = divmod(int(term[i]), save_every)
-                idx = list(range(kf + 1)) + ([kf + 1, kf + 1] if rem else [kf])
-                ti = np.concatenate([time[:kf + 1], np.full(len(idx) - kf - 1, t_end[i])])
-                arrs = {k: (a if k in (A.OBS_SCATTERING, A.OBS_SCATTERING_DIABATIC) else a[idx]) for k, a in arrs.items()}
+            ti, arrs = _trim_terminated(time, {k: per_obs[k][i] for k in obs_ids}, int(term[i]), save_every, float(t_end[i]))
             d: Dict[str, Any] = {"Time": ti.copy()} if savetime else {}
             for o in outputs:
                 d[o.name] = _finalise(sim, o, arrs, True, float(t_end[i]))

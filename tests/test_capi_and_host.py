@@ -206,3 +206,31 @@ def test_nrpmd_initial_mapping_kat():
     assert abs(th.mean() - np.pi) < 0.02 and abs(th.var() - (2 * np.pi) ** 2 / 12) < 0.05      # uniform angles
     q2, p2 = api.sample_nrpmd_mapping(rng, 4, 3, 3, 2, 0.0)         # gamma = 0: unoccupied states sit at the origin
     assert np.all(q2[:, :, [0, 2]] == 0) and np.allclose(q2[:, :, 1] ** 2 + p2[:, :, 1] ** 2, 2.0)
+
+
+def test_terminated_series_trimming_host_logic():
+    """TerminatingCallback host side: sol.t / sol.u of a terminated trajectory from the fixed-shape device stream."""
+    import numpy as np
+    from nqcdynamics_jl_b200 import api
+    se, nsave = 5, 9
+    time = 2.0 + 0.5 * se * np.arange(nsave)                       # t0 = 2, dt = 0.5
+    stream = np.arange(nsave, dtype=float).reshape(nsave, 1) * 10   # frame k holds 10 k
+    scat = np.zeros((nsave, 4)); scat[-1] = [0, 0, 1, 0]
+    arrs = {api.A.OBS_POSITION: stream, api.A.OBS_SCATTERING: scat}
+    t, a = api._trim_terminated(time, arrs, -1, se, time[-1])
+    assert t is time and a is arrs                                   # still running: untouched
+    # terminated after 17 steps (between save 3 and save 4): 4 saveat frames, then the terminal frame twice
+    t, a = api._trim_terminated(time, arrs, 17, se, 2.0 + 0.5 * 17)
+    assert np.array_equal(t, [2.0, 4.5, 7.0, 9.5, 10.5, 10.5])
+    assert np.array_equal(a[api.A.OBS_POSITION][:, 0], [0, 10, 20, 30, 40, 40])
+    assert a[api.A.OBS_SCATTERING] is scat
+    # terminated exactly on a saveat point (step 20 = save 4): that frame once from saveat, once after the affect
+    t, a = api._trim_terminated(time, arrs, 20, se, 2.0 + 0.5 * 20)
+    assert np.array_equal(t, [2.0, 4.5, 7.0, 9.5, 12.0, 12.0])
+    assert np.array_equal(a[api.A.OBS_POSITION][:, 0], [0, 10, 20, 30, 40, 40])
+    # terminated at the very last step of the span
+    t, a = api._trim_terminated(time, arrs, 40, se, time[-1])
+    assert len(t) == nsave + 1 and t[-1] == t[-2] == time[-1]
+    # first step
+    t, a = api._trim_terminated(time, arrs, 1, se, 2.5)
+    assert np.array_equal(t, [2.0, 2.5, 2.5]) and np.array_equal(a[api.A.OBS_POSITION][:, 0], [0, 10, 10])
