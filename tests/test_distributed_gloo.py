@@ -30,9 +30,12 @@ def _worker(rank, world, port, T, nsteps, q):
     cfg, keep = A.make_config(**kw)
     h = oracle.OracleEngine(cfg, keep)
     rho = np.zeros((hi - lo, 2, 2)); rho[:, 0, 0] = 1
+    h.set_termination(0, -7.5, -3.5, True)          # TerminatingCallback mask: shard-independent like everything else
     h.set_state_diabatic(r[lo:hi], v[lo:hi], rho)
     h.run(nsteps)
-    acc = np.concatenate([h.observable_sum(A.OBS_DIABATIC_POP).ravel(), h.observable_sum(A.OBS_SCATTERING).ravel()])
+    ts = h.termination()
+    acc = np.concatenate([h.observable_sum(A.OBS_DIABATIC_POP).ravel(), h.observable_sum(A.OBS_SCATTERING).ravel(),
+                          [float(ts[ts >= 0].sum()), float(np.count_nonzero(ts >= 0)), float(h.counters()["steps"])]])
     allreduce_sum(acc)
     if rank == 0:
         q.put(acc)
@@ -62,7 +65,12 @@ def test_two_rank_sharding_matches_single_shard():
     cfg, keep = A.make_config(**kw)
     h = oracle.OracleEngine(cfg, keep)
     rho = np.zeros((T, 2, 2)); rho[:, 0, 0] = 1
+    h.set_termination(0, -7.5, -3.5, True)
     h.set_state_diabatic(r, v, rho)
     h.run(nsteps)
-    ref = np.concatenate([h.observable_sum(A.OBS_DIABATIC_POP).ravel(), h.observable_sum(A.OBS_SCATTERING).ravel()])
-    assert np.max(np.abs(acc - ref)) < 1e-10 * T
+    ts = h.termination()
+    assert 0 < np.count_nonzero(ts >= 0) < T, "the case mixes terminated and running trajectories"
+    ref = np.concatenate([h.observable_sum(A.OBS_DIABATIC_POP).ravel(), h.observable_sum(A.OBS_SCATTERING).ravel(),
+                          [float(ts[ts >= 0].sum()), float(np.count_nonzero(ts >= 0)), float(h.counters()["steps"])]])
+    assert np.max(np.abs(acc[:-3] - ref[:-3])) < 1e-10 * T
+    assert np.array_equal(acc[-3:], ref[-3:]), "termination steps and step counters are shard-independent"
