@@ -20,4 +20,4 @@ from .api import (Atoms, FSSH, Ehrenfest, EhrenfestNA, ThermalLangevin, Classica
                   PopulationCorrelationFunction, SortByTrajectoryReduction, SortByOutputReduction, SumReduction,
                   MeanReduction, EnsembleB200, run_dynamics, TerminatingCallback, PositionOutside,
                   OutputSubsetKineticEnergy, OutputFinalSubsetKineticEnergy, OutputKineticTemperature,
-                  OutputMappingPosition, OutputMappingMomentum)
+                  OutputMappingPosition, OutputMappingMomentum, OutputOccupations)

@@ -21,6 +21,7 @@ import numpy as np
 
 from . import _abi as A
 from . import models as _models
+from .distributed import shard_bounds
 from .engine import Engine, device_count
 
 # ---- atoms -------------------------------------------------------------------------------------
@@ -295,15 +296,18 @@ class DynamicalDistribution:
             return np.broadcast_to(x.T.reshape(1, D), (B, D))
         return np.broadcast_to(x.reshape(-1), (B, D)) if x.size == D else x.reshape(B, D)
 
-    def _draw(self, spec, rng, T, selection):
+    @staticmethod
+    def _is_configurations(spec):
+        return isinstance(spec, (list, tuple)) and len(spec) and np.ndim(spec[0]) >= 1
+
+    def _draw(self, spec, rng, T, idx):
         D = int(np.prod(self.size[:2]))
         B = self.size[2] if len(self.size) > 2 else 1
         shape = (T, B, D)
         if hasattr(spec, "sample"):
             return np.ascontiguousarray(spec.sample(rng, shape))
-        if isinstance(spec, (list, tuple)) and len(spec) and np.ndim(spec[0]) >= 1:
-            # a vector of configurations: OrderedSelection (selection given) or RandomSelection (selections.jl:24-36)
-            idx = [j - 1 for j in selection] if selection is not None else rng.integers(0, len(spec), T)
+        if self._is_configurations(spec):
+            # a vector of configurations, indexed by the ONE index drawn per trajectory (see sample)
             return np.ascontiguousarray(np.stack([self._to_flat(spec[i]) for i in idx]))
         arr = np.asarray(spec, dtype=np.float64)
         if arr.ndim == 0:
@@ -311,7 +315,17 @@ class DynamicalDistribution:
         return np.ascontiguousarray(np.broadcast_to(self._to_flat(arr), shape))
 
     def sample(self, rng, T, selection=None):
-        return self._draw(self.position, rng, T, selection), self._draw(self.velocity, rng, T, selection)
+        """``distribution[j]`` for the selected indices (OrderedSelection, selections.jl:38-42) or ``rand(distribution)``
+        (RandomSelection, :70-73).  Either way ONE index per trajectory picks the entry of every vector-of-configurations
+        field, so paired (r_i, v_i) samples -- e.g. the output of a previous Langevin run -- stay paired."""
+        lengths = {len(s) for s in (self.position, self.velocity) if self._is_configurations(s)}
+        if len(lengths) > 1:
+            raise ValueError("DynamicalDistribution: velocity and position sample vectors differ in length")
+        idx = None
+        if lengths:
+            n = lengths.pop()
+            idx = [j - 1 for j in selection] if selection is not None else rng.integers(0, n, T)
+        return self._draw(self.position, rng, T, idx), self._draw(self.velocity, rng, T, idx)
 
     def _component_spec(self, spec):
         """Per-component (fixed | Normal) description of one entry for nqcb200_sample_state, or None if the entry is
@@ -366,6 +380,9 @@ OutputCentroidPosition = _Output("OutputCentroidPosition", A.OBS_POSITION)
 OutputCentroidVelocity = _Output("OutputCentroidVelocity", A.OBS_VELOCITY)
 OutputDiscreteState = _Output("OutputDiscreteState", A.OBS_DISCRETE_STATE)
 OutputQuantumSubsystem = _Output("OutputQuantumSubsystem", A.OBS_SIGMA)
+# build-defined (not in DynamicsOutputs.jl): all ne occupied orbitals of an AdiabaticIESH trajectory per frame.  The
+# reference's OutputDiscreteState keeps only `first(u.state)` when the state is a vector (DynamicsOutputs.jl:178).
+OutputOccupations = _Output("OutputOccupations", A.OBS_DISCRETE_STATE, "occupations")
 OutputSurfaceHops = _Output("OutputSurfaceHops", A.OBS_DISCRETE_STATE, "hops")
 # outputs assembled on the host from the same device streams (DynamicsOutputs.jl:101-141,192-227,387-397)
 OutputFinalKineticEnergy = _Output("OutputFinalKineticEnergy", A.OBS_KINETIC, "last")
@@ -478,6 +495,7 @@ class EnsembleB200:
     numpy on the host -- nothing but the specification is uploaded."""
     ngpus: int = 1
     device_sampling: bool = False
+    device_ids: Optional[Sequence[int]] = None      # CUDA ordinal of each shard (default 0 .. ngpus-1; may repeat)
 
 
 # ---- run_dynamics ----------------------------------------------------------------------------------
@@ -578,8 +596,13 @@ def _finalise(sim, out: _Output, arrs: Dict[int, np.ndarray], per_trajectory: bo
             frames.append(u)
         return frames[0] if out.kind == "variables_first" else frames[-1] if out.kind == "variables_last" else frames
     val = _shape_series(sim, out, arr)
+    if out.kind == "occupations":
+        return np.rint(val).astype(np.int64).reshape(arr.shape[0], -1) if per_trajectory else val
     if out.obs == A.OBS_DISCRETE_STATE:
-        val = np.rint(val).astype(np.int64)
+        if val.ndim > 1:                     # IESH: `length(u.state) > 1 ? round(Int, first(u.state))` (DynamicsOutputs.jl:178)
+            val = val[:, 0]
+        if per_trajectory:                   # reduced (Sum / Mean) series stay real-valued
+            val = np.rint(val).astype(np.int64)
     if out.kind == "first":
         return val[0]
     if out.kind == "last":
@@ -657,6 +680,10 @@ def run_dynamics(sim: Simulation, tspan, distribution, *, output, selection: Opt
         if dev_spec is None or method.method_id in A.IESH_FAMILY + (A.METHOD_NRPMD,):
             raise ValueError("device_sampling needs number / Normal / VelocityBoltzmann entries, no selection, and a method "
                              "other than AdiabaticIESH / NRPMD")
+        if (density and method.method_id == A.METHOD_FSSH and isinstance(electronic, MixedState)
+                and (isinstance(electronic.statetype, Adiabatic) or electronic.statetype is Adiabatic)):
+            raise ValueError("device_sampling: an adiabatic MixedState needs the active state drawn per trajectory on the "
+                             "host (fssh.jl:53-54); use device_sampling=False or a diabatic MixedState")
         r = v = None
     else:
         r, v = nuclear.sample(rng, T, selection)
@@ -700,16 +727,19 @@ def run_dynamics(sim: Simulation, tspan, distribution, *, output, selection: Opt
         qmap0, pmap0 = sample_nrpmd_mapping(rng, T, sim.beads, model.nstates, electronic.state, float(method.γ))
 
     ngpus = max(1, int(alg.ngpus))
-    if ngpus > device_count():
-        raise RuntimeError(f"EnsembleB200({ngpus}) but only {device_count()} CUDA device(s) visible")
-    bounds = np.linspace(0, T, ngpus + 1).astype(np.int64)
+    device_ids = list(range(ngpus)) if alg.device_ids is None else [int(d) for d in alg.device_ids]
+    if len(device_ids) != ngpus:
+        raise ValueError("EnsembleB200: device_ids needs one CUDA ordinal per shard")
+    if max(device_ids) >= device_count() or min(device_ids) < 0:
+        raise RuntimeError(f"EnsembleB200(device_ids={device_ids}) but only {device_count()} CUDA device(s) visible")
+    bounds = [shard_bounds(T, ngpus, g) for g in range(ngpus)]      # the one sharding rule (distributed.py)
     engine_seed = int(rng.integers(0, 2 ** 63 - 1)) if seed is None else int(seed)
     results: List[Any] = [None] * ngpus
     errors: List[BaseException] = []
 
     def shard(g):
         try:
-            lo, hi = int(bounds[g]), int(bounds[g + 1])
+            lo, hi = bounds[g]
             Tg = hi - lo
             cfg, keep = A.make_config(
                 method=method.method_id, model=model.kind, nstates=model.nstates, ndofs=sim.ndofs_total,
@@ -718,7 +748,7 @@ def run_dynamics(sim: Simulation, tspan, distribution, *, output, selection: Opt
                 rescaling=_RESCALE[getattr(method, "rescaling", "standard")],
                 estimate_probability=int(getattr(method, "estimate_probability", True)),
                 disable_hopping=int(getattr(method, "disable_hopping", False)),
-                rng=A.RNG_INJECTED if draws is not None else A.RNG_PHILOX, device=g, save_every=save_every,
+                rng=A.RNG_INJECTED if draws is not None else A.RNG_PHILOX, device=device_ids[g], save_every=save_every,
                 nsave=nsave, per_trajectory=int(per_traj), observables=obs_mask, traj_offset=lo, seed=engine_seed,
                 t0=t0, temperature=sim.temperature, nrpmd_gamma=getattr(method, "γ", 0.5),
                 edc_C=getattr(method, "decoherence_C", 0.0))

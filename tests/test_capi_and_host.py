@@ -118,6 +118,24 @@ def test_distribution_layouts():
     assert list(r.ravel()) == [3.0, 1.0] and list(v.ravel()) == [0.3, 0.1]
 
 
+def test_paired_configurations_stay_paired():
+    """rand(distribution) draws ONE index for velocity and position (selections.jl:70-73 -> `u = rand(distribution)`;
+    `u.v`, `u.r`): correlated phase-space samples from a previous run must not be re-paired at random."""
+    sims = nq.Simulation[nq.FSSH](nq.Atoms(2000), nq.TullyModelOne())
+    n = 50
+    pos = [np.array([[float(i)]]) for i in range(n)]
+    vel = [np.array([[10.0 * i]]) for i in range(n)]
+    d = nq.DynamicalDistribution(vel, pos, sims.size)
+    r, v = d.sample(np.random.default_rng(4), 400)
+    assert np.array_equal(v.ravel(), 10.0 * r.ravel()) and len(set(r.ravel())) > 20
+    with pytest.raises(ValueError):
+        nq.DynamicalDistribution(vel[:3], pos, sims.size).sample(np.random.default_rng(0), 4)
+    # a vector of configurations next to a samplable entry: still one index for the vector
+    d2 = nq.DynamicalDistribution(nq.Normal(0.0, 1.0), pos, sims.size)
+    r, v = d2.sample(np.random.default_rng(5), 10)
+    assert r.shape == v.shape == (10, 1, 1)
+
+
 def test_run_dynamics_argument_checks():
     sim = nq.Simulation[nq.FSSH](nq.Atoms(2000), nq.TullyModelOne(), rescaling="vinversion")
     assert sim.method.rescaling == "vinversion"

@@ -86,17 +86,18 @@ def test_run_dynamics_iesh_ground_state_and_fermi_dirac():
     n, ne, T = model.nstates, model.nelectrons, 12
     dist = nq.DynamicalDistribution(nq.Normal(0.0, 7e-4), nq.Normal(21.0, 1.0), (1, 1))
     out = nq.run_dynamics(sim, (0.0, 50.0), dist, output=(nq.OutputQuantumSubsystem, nq.OutputDiscreteState,
-                                                          nq.OutputTotalEnergy, nq.OutputSurfaceHops),
+                                                          nq.OutputTotalEnergy, nq.OutputSurfaceHops, nq.OutputOccupations),
                           trajectories=T, dt=5.0, seed=3)
     assert len(out) == T and out[0]["OutputQuantumSubsystem"].shape == (11, n, ne)
-    assert np.array_equal(out[0]["OutputDiscreteState"][0], np.arange(1, ne + 1))
+    assert np.array_equal(out[0]["OutputOccupations"][0], np.arange(1, ne + 1))
+    assert out[0]["OutputDiscreteState"].shape == (11,) and out[0]["OutputDiscreteState"][0] == 1    # first(u.state), DynamicsOutputs.jl:178
     psi = out[3]["OutputQuantumSubsystem"][-1]
     assert np.allclose(np.sum(np.abs(psi) ** 2, axis=0), 1.0, atol=1e-12)
     E = np.array([tr["OutputTotalEnergy"] for tr in out])
     assert np.max(np.abs(E - E[:, :1])) < 1e-5           # no hops accepted without energy conservation
-    hot = nq.run_dynamics(sim, (0.0, 20.0), dist * nq.FermiDiracState(0.0, 9.5e-4), output=nq.OutputDiscreteState,
+    hot = nq.run_dynamics(sim, (0.0, 20.0), dist * nq.FermiDiracState(0.0, 9.5e-4), output=nq.OutputOccupations,
                           trajectories=T, dt=5.0, seed=4)
-    occ0 = np.array([tr["OutputDiscreteState"][0] for tr in hot])
+    occ0 = np.array([tr["OutputOccupations"][0] for tr in hot])
     assert occ0.shape == (T, ne) and np.all(np.diff(occ0, axis=1) > 0) and np.any(occ0 != np.arange(1, ne + 1))
     mean = nq.run_dynamics(sim, (0.0, 20.0), dist, output=(nq.OutputDiabaticPopulation, nq.OutputAdiabaticPopulation),
                            reduction=nq.MeanReduction(), trajectories=T, dt=5.0, seed=5)
@@ -205,10 +206,10 @@ def test_fermi_dirac_diabatic_state_matches_engine_gauge():
         assert len(set(d.tolist())) == ne
     sim = nq.Simulation[nq.AdiabaticIESH](nq.Atoms(2000), model)
     dist = nq.DynamicalDistribution(nq.Normal(0.0, 7e-4), nq.Normal(21.0, 1.0), (1, 1)) * fd
-    out = nq.run_dynamics(sim, (0.0, 10.0), dist, output=(nq.OutputDiscreteState, nq.OutputDiabaticPopulation), trajectories=4,
+    out = nq.run_dynamics(sim, (0.0, 10.0), dist, output=(nq.OutputOccupations, nq.OutputDiabaticPopulation), trajectories=4,
                           dt=1.0, seed=4)
     for tr in out:
-        assert tr["OutputDiscreteState"].shape == (11, ne)
+        assert tr["OutputOccupations"].shape == (11, ne)
         assert np.allclose(tr["OutputDiabaticPopulation"].sum(axis=1), ne, atol=1e-8)
 
 
