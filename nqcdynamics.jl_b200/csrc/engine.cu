@@ -556,6 +556,38 @@ int nqcb200_create(const nqcb200_config* cfg, nqcb200_handle** out) {
     }
     if (ks.needs_sb_carry) {
         if ((rc = dev_alloc(h, &kp.sb_carry, (size_t)2 * T)) != 0) return fail(rc);
+        // per-mode constants and lag tables of the epoch kernels (kernel_spinboson_epoch.cuh): the response
+        // of L = sum c r, C = sum c u, W = sum (c w^2/m) r to a unit impulse of shape c/m (s = 0) or c (s = 1), l steps on
+        std::vector<double> kc((size_t)4 * D), kap(2 * 3 * 32 + 2, 0.0);
+        for (int j = 0; j < D; ++j) {
+            const double w = c.bath_a[j], cj = c.bath_b[j], m = c.masses[j];
+            kc[4 * j + 0] = c.dt * w * w / m; kc[4 * j + 1] = cj / m; kc[4 * j + 2] = cj; kc[4 * j + 3] = cj * w * w / m;
+            kap[192] = std::fma(cj, cj / m, kap[192]); kap[193] = std::fma(cj, cj, kap[193]);
+            for (int s = 0; s < 2; ++s) {
+                double u = -(s == 0 ? kc[4 * j + 1] : kc[4 * j + 2]), r = c.dt * u;
+                for (int l = 0; l < 32; ++l) {
+                    kap[(s * 3 + 0) * 32 + l] = std::fma(kc[4 * j + 2], r, kap[(s * 3 + 0) * 32 + l]);
+                    kap[(s * 3 + 1) * 32 + l] = std::fma(kc[4 * j + 2], u, kap[(s * 3 + 1) * 32 + l]);
+                    kap[(s * 3 + 2) * 32 + l] = std::fma(kc[4 * j + 3], r, kap[(s * 3 + 2) * 32 + l]);
+                    const double vt = std::fma(-kc[4 * j + 0], r, u);
+                    r = std::fma(c.dt, vt, r); u = vt;
+                }
+            }
+        }
+        double *dkc = nullptr, *dkap = nullptr;
+        if ((rc = dev_alloc(h, &dkc, kc.size())) != 0) return fail(rc);
+        if ((rc = dev_alloc(h, &dkap, kap.size())) != 0) return fail(rc);
+        cudaMemcpyAsync(dkc, kc.data(), sizeof(double) * kc.size(), cudaMemcpyHostToDevice, h->stream);
+        cudaMemcpyAsync(dkap, kap.data(), sizeof(double) * kap.size(), cudaMemcpyHostToDevice, h->stream);
+        if (cudaStreamSynchronize(h->stream) != cudaSuccess) { h->err = "SpinBoson table upload"; cudaGetLastError(); return fail(NQCB200_ERR_CUDA); }
+        kp.sb_kc = dkc; kp.sb_kap = dkap;
+        if (ks.sb_epoch > 0) {
+            const int E = ks.sb_epoch;
+            if ((rc = dev_alloc(h, &kp.sb_sums, (size_t)3 * E * T)) != 0) return fail(rc);
+            if ((rc = dev_alloc(h, &kp.sb_f, (size_t)2 * (E + 1) * T)) != 0) return fail(rc);
+            if ((rc = dev_alloc(h, &kp.sb_aux, (size_t)T)) != 0) return fail(rc);
+            if ((rc = dev_alloc(h, &kp.sb_flag, (size_t)1)) != 0) return fail(rc);
+        }
     }
     if (ks.step_smem > 48 * 1024) {
         if (cudaFuncSetAttribute((const void*)ks.step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ks.step_smem) != cudaSuccess) {
@@ -724,6 +756,34 @@ int nqcb200_run(nqcb200_handle* h, int64_t nsteps) {
     const int64_t max_per_launch = 1 << 16;
     NQ_CUDA(h, cudaEventRecord(h->ev0, h->stream));
     int64_t done = 0;
+    if (h->ks.sb_epoch > 0) {
+        // kernel_spinboson_epoch.cuh: prep, then per epoch one bath pass (replay the previous epoch, free-evolve the next)
+        // and one electronic kernel, then the exit pass (replay + second half kick)
+        const unsigned grid = (unsigned)((c.ntraj + kBlockThreads - 1) / kBlockThreads);
+        KParams kp = h->kp;
+        kp.step0 = h->step_count; kp.nsteps = 0;
+        NQ_CUDA(h, cudaMemsetAsync(kp.sb_flag, 0, sizeof(int32_t), h->stream));
+        h->ks.sb_prep<<<grid, kBlockThreads, 0, h->stream>>>(kp); ++h->launches_total;
+        int32_t gen = 0;
+        NQ_CUDA(h, cudaMemcpyAsync(&gen, kp.sb_flag, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+        NQ_CUDA(h, cudaStreamSynchronize(h->stream));
+        kp.sb_gen = gen;
+        const int64_t E = gen ? 1 : h->ks.sb_epoch;      // tr sigma != 1 somewhere: the lag tables do not apply
+        int nrep = 0;
+        while (done < nsteps) {
+            const int kb = (int)std::min<int64_t>(E, nsteps - done);
+            kp.sb_entry = (done == 0); kp.sb_nrep = nrep; kp.sb_nfree = kb; kp.sb_exit = 0;
+            h->ks.sb_bath<<<grid, kBlockThreads, 0, h->stream>>>(kp); ++h->launches_total;
+            kp.step0 = h->step_count + done; kp.nsteps = kb;
+            h->ks.sb_elec<<<grid, kBlockThreads, 0, h->stream>>>(kp); ++h->launches_total;
+            h->last_launches += 2;
+            nrep = kb; done += kb;
+        }
+        kp.sb_entry = 0; kp.sb_nrep = nrep; kp.sb_nfree = 0; kp.sb_exit = 1;
+        h->ks.sb_bath<<<grid, kBlockThreads, 0, h->stream>>>(kp); ++h->launches_total;
+        h->last_launches += 2;
+        NQ_CUDA(h, cudaGetLastError());
+    }
     while (done < nsteps) {
         const int64_t chunk = std::min(nsteps - done, max_per_launch);
         h->kp.step0 = h->step_count + done;

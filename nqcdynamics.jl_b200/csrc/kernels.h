@@ -24,6 +24,9 @@ struct KernelSet {
     size_t step_smem = 0;
     bool needs_sb_carry = false;   // kernel_spinboson.cuh: two force scalars per trajectory carried between launches
     bool fused_init = false;       // the step kernel can initialise from KParams.r_aos / v_aos (see common.cuh)
+    // kernel_spinboson_epoch.cuh: E nuclear steps per (bath pass, electronic kernel) pair instead of one `step` kernel
+    int sb_epoch = 0;
+    StepFn sb_prep = nullptr, sb_bath = nullptr, sb_elec = nullptr;
     bool cta_per_trajectory = false;
     IeshLayout iesh = {};   // AdiabaticIESH tile / shared-memory plan (kernel_iesh.cuh)
     const char* name = "";

@@ -4,6 +4,7 @@
 
 #include "kernel_density.cuh"
 #include "kernel_spinboson.cuh"
+#include "kernel_spinboson_epoch.cuh"
 
 namespace nq {
 namespace {
@@ -45,6 +46,28 @@ bool select_density_spinboson(const nqcb200_config& c, KernelSet& out, std::stri
         out.fused_init = true;
         out.needs_sb_carry = true;
         out.name = (m == NQCB200_METHOD_FSSH) ? "spinboson_fssh_tpt" : "spinboson_ehrenfest_tpt";
+        // E steps per (bath pass, electronic kernel) pair (kernel_spinboson_epoch.cuh) when no output needs bath
+        // coordinates at the save points.  NQCB200_SPINBOSON_EPOCH=0 keeps the step-by-step kernel, =8 selects the
+        // shorter epoch (A/B switches, documented in DESIGN.md section 3).
+        const uint32_t electronic_only = (1u << NQCB200_OBS_ADIABATIC_POP) | (1u << NQCB200_OBS_DIABATIC_POP) |
+                                         (1u << NQCB200_OBS_POPCORR_DIABATIC) | (1u << NQCB200_OBS_POPCORR_ADIABATIC) |
+                                         (1u << NQCB200_OBS_DISCRETE_STATE) | (1u << NQCB200_OBS_SIGMA);
+        int epoch = 16;
+        if (const char* env = getenv("NQCB200_SPINBOSON_EPOCH")) epoch = atoi(env);
+        if (epoch != 0 && D >= 8 && !c.diagnostics && (c.observables & ~electronic_only) == 0) {
+            const bool f = (m == NQCB200_METHOD_FSSH);
+#define NQ_SB_EPOCH(E)                                                                                                   \
+            do {                                                                                                             \
+                out.sb_epoch = E;                                                                                            \
+                out.sb_prep = f ? sb_prep_kernel<NQCB200_METHOD_FSSH, E> : sb_prep_kernel<NQCB200_METHOD_EHRENFEST, E>;      \
+                out.sb_bath = sb_bath_kernel<E>;                                                                             \
+                out.sb_elec = f ? sb_elec_kernel<NQCB200_METHOD_FSSH, E> : sb_elec_kernel<NQCB200_METHOD_EHRENFEST, E>;      \
+            } while (0)
+            if (epoch == 8) NQ_SB_EPOCH(8); else NQ_SB_EPOCH(16);
+#undef NQ_SB_EPOCH
+            out.fused_init = false;
+            out.name = f ? "spinboson_fssh_epoch" : "spinboson_ehrenfest_epoch";
+        }
         return true;
     }
     if (D <= 4 && (lanes == 0 || lanes == 1)) return pick<4, 1>(m, out);

@@ -128,6 +128,8 @@ def compare(h, doc, tol=1e-10, stride=1):
             ref = _field(doc, key, where)
             if ref is None:
                 continue
+            if where == "t0" and key in ("w", "Z", "nac", "accel"):
+                continue        # the handles report the cache of the most recent STEP; the t0 Z went in as the gauge reference
             if key == "state":
                 if not np.array_equal(np.rint(mine), np.rint(ref)):
                     raise AssertionError(f"{doc['config']}: discrete state differs at {where}")

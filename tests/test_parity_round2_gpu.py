@@ -67,15 +67,22 @@ def test_fssh_frustrated_hop_policies(rescaling, name, model, mass, r0, v0, dt):
 
 @pytest.mark.parametrize("rescaling", POLICIES)
 @pytest.mark.parametrize("method", [A.METHOD_FSSH])
-@pytest.mark.parametrize("nmodes", [8, 100])
-def test_spin_boson_frustrated_hop_policies(rescaling, method, nmodes):
-    """spinboson_step_kernel (kernel_spinboson.cuh:496-504): a cold bath (beta = 200) makes most up-hops frustrated."""
-    T, nsteps = 64, 120
+@pytest.mark.parametrize("nmodes,kernel", [(8, "step"), (100, "step"), (8, "kblock"), (37, "kblock"), (100, "kblock")])
+def test_spin_boson_frustrated_hop_policies(rescaling, method, nmodes, kernel):
+    """A cold bath (beta = 200) makes most up-hops frustrated.  kernel = "step": spinboson_step_kernel
+    (kernel_spinboson.cuh, selected by energy outputs / diagnostics); "kblock": spinboson_kblock_kernel
+    (kernel_spinboson_kblock.cuh, electronic outputs only, K steps per pass over the bath, 70 trajectories = ragged
+    last block, 123 steps = ragged last K-block, two launches)."""
+    step_kernel = kernel == "step"
+    T, nsteps = (64, 120) if step_kernel else (70, 123)
     rng = np.random.default_rng(37)
     model = nq.SpinBoson(nq.DebyeSpectralDensity(0.25, 0.5), nmodes, 0.5, 1.0)
     obs = (1 << A.OBS_POPCORR_DIABATIC) | (1 << A.OBS_ADIABATIC_POP) | (1 << A.OBS_DIABATIC_POP) | (1 << A.OBS_SIGMA) | \
-          (1 << A.OBS_KINETIC) | (1 << A.OBS_TOTAL_ENERGY) | (1 << A.OBS_DISCRETE_STATE)
-    kw = model_config(model, method=method, masses=np.ones(nmodes), ntraj=T, dt=0.1, rng=A.RNG_INJECTED, diagnostics=1,
+          (1 << A.OBS_DISCRETE_STATE)
+    if step_kernel:
+        obs |= (1 << A.OBS_KINETIC) | (1 << A.OBS_TOTAL_ENERGY)
+    kw = model_config(model, method=method, masses=np.ones(nmodes) * (1.0 if step_kernel else 1.3), ntraj=T, dt=0.1,
+                      rng=A.RNG_INJECTED, diagnostics=int(step_kernel),
                       save_every=4, nsave=nsteps // 4 + 1, observables=obs, per_trajectory=1, rescaling=rescaling)
     e, o = make_pair(engine_factory(), oracle_factory(), **kw)
     w = model.bath_a
@@ -89,14 +96,46 @@ def test_spin_boson_frustrated_hop_policies(rescaling, method, nmodes):
     for h in (e, o):
         h.set_state_diabatic(r, v, rho, None, None, sdraw)
         h.set_draws(draws)
-    for chunk in range(nsteps // 20):
-        e.run(20); o.run(20)
-        _compare_state(e, o, 1e-9, f"chunk {chunk}")
-        de, do = e.diagnostics(), o.diagnostics()
-        assert rel_err(de["accel"], do["accel"]) < 1e-9
+    done = 0
+    for chunk in ([20] * (nsteps // 20) + ([nsteps % 20] if nsteps % 20 else [])):
+        e.run(chunk); o.run(chunk)
+        done += chunk
+        _compare_state(e, o, 1e-9, f"after {done} steps")
+        if step_kernel:
+            de, do = e.diagnostics(), o.diagnostics()
+            assert rel_err(de["accel"], do["accel"]) < 1e-9
     assert np.array_equal(e.observable_per_trajectory(A.OBS_DISCRETE_STATE), o.observable_per_trajectory(A.OBS_DISCRETE_STATE))
     _counters_match(e, o, need_frustrated=rescaling != A.RESCALE_OFF)
     _compare_observables(e, o, obs, 1e-9, T)
+
+
+@pytest.mark.parametrize("method", [A.METHOD_FSSH, A.METHOD_EHRENFEST])
+def test_spin_boson_kblock_long_run_and_unnormalised_sigma(method):
+    """spinboson_kblock_kernel over a whole BASELINE config-2 job (200 steps of dt = 0.1, 100 modes) against the oracle,
+    with Philox draws, plus an Ehrenfest density of trace 0.8 (force scalar A != 1: the K = 1 fallback of a block)."""
+    T, nsteps = 96, 200
+    rng = np.random.default_rng(53)
+    model = nq.SpinBoson(nq.DebyeSpectralDensity(0.25, 0.5), 100, 0.0, 1.0)
+    obs = (1 << A.OBS_POPCORR_DIABATIC) | (1 << A.OBS_ADIABATIC_POP) | (1 << A.OBS_DISCRETE_STATE) | (1 << A.OBS_SIGMA)
+    kw = model_config(model, method=method, masses=np.ones(100), ntraj=T, dt=0.1, rng=A.RNG_PHILOX, seed=4242, traj_offset=1000,
+                      save_every=1, nsave=nsteps + 1, observables=obs, per_trajectory=1)
+    w = model.bath_a
+    sr = np.sqrt(1.0 / (2 * w * np.tanh(2.5 * w))); sv = np.sqrt(w / (2 * np.tanh(2.5 * w)))
+    r = rng.standard_normal((T, 100)) * sr
+    v = rng.standard_normal((T, 100)) * sv
+    rho = _pure_state(T, 2, 0)
+    if method == A.METHOD_EHRENFEST:
+        rho[40:50] *= 0.8                      # unnormalised rows: one block of 32 trajectories takes the general-A path
+    e, o = make_pair(engine_factory(), oracle_factory(), **kw)
+    for h in (e, o):
+        h.set_state_diabatic(r, v, rho)
+        h.run(nsteps)
+    _compare_state(e, o, 1e-9, "final")
+    _compare_observables(e, o, obs, 1e-9, T)
+    assert np.max(np.abs(e.observable_per_trajectory(A.OBS_SIGMA) - o.observable_per_trajectory(A.OBS_SIGMA))) < 1e-9
+    if method == A.METHOD_FSSH:
+        assert np.array_equal(e.observable_per_trajectory(A.OBS_DISCRETE_STATE), o.observable_per_trajectory(A.OBS_DISCRETE_STATE))
+        assert e.counters()["hops"] == o.counters()["hops"] > 0
 
 
 @pytest.mark.parametrize("rescaling", POLICIES)
@@ -130,14 +169,23 @@ def test_rpsh_frustrated_hop_policies(rescaling, nbeads):
     _compare_observables(e, o, obs, 1e-9, T)
 
 
-@pytest.mark.parametrize("M,T,nsteps,dt,small_every", [(100, 8, 60, 1.0, 3), (100, 8, 50, 10.0, 4), (200, 4, 50, 1.0, 10),
-                                                       (200, 2, 50, 10.0, 10)])
+# The CPU oracle needs ~1 s per n = 201 base step and ~20 s per unpruned hop search (ne (n - ne) complex LUs), so the
+# full-depth n = 201 cases (4 x 50 and 2 x 50 steps; 250 s and 320 s on the GPU box's host, both green at this commit,
+# profiles/r02/SUMMARY.md) run only with NQCB200_SLOW_TESTS=1; the default suite keeps a 12-step n = 201 case.
+_SLOW = os.environ.get("NQCB200_SLOW_TESTS", "0") not in ("", "0")
+_DEPTH = [(100, 8, 60, 1.0, 3), (100, 8, 50, 10.0, 4), (200, 1, 12, 1.0, 6)]
+if _SLOW:
+    _DEPTH += [(200, 4, 50, 1.0, 10), (200, 2, 50, 10.0, 10)]
+
+
+@pytest.mark.parametrize("M,T,nsteps,dt,small_every", _DEPTH)
 def test_iesh_config4_depth(M, T, nsteps, dt, small_every):
     """BASELINE config 4 sizes over >= 50 steps and >= 4-8 trajectories from random orthonormal orbitals; the draws are
     small enough for the pruning estimate to fail on some steps, so the full hop search (one LU + determinant lemma on
     the device vs ne (n - ne) LUs in the oracle) is exercised at n = 101 / 201."""
     rng = np.random.default_rng(43 + M + int(dt))
-    model, (e, o) = _iesh_pair(M, T, dt, nsteps // 10 + 1, save_every=10)
+    chunk_len = 10 if nsteps % 10 == 0 else 6
+    model, (e, o) = _iesh_pair(M, T, dt, nsteps // chunk_len + 1, save_every=chunk_len)
     n, ne = model.nstates, model.nelectrons
     r = 6.0 + 12.0 * rng.random(T)
     v = -np.abs(rng.standard_normal(T)) * 4e-3
@@ -147,8 +195,8 @@ def test_iesh_config4_depth(M, T, nsteps, dt, small_every):
     for h in (e, o):
         h.set_state(r, v, re, im, state)
         h.set_draws(xi)
-    for chunk in range(nsteps // 10):
-        e.run(10); o.run(10)
+    for chunk in range(nsteps // chunk_len):
+        e.run(chunk_len); o.run(chunk_len)
         _iesh_compare(e, o, 1e-9, f"n={n} chunk {chunk}")
     assert e.hop_search_count() == o.hop_search_count() > 0
     ce, co = e.counters(), o.counters()
