@@ -35,6 +35,8 @@
 // Rounding: r, v follow the FMA sequence of kernel_spinboson.cuh; the bath sums are assembled in a different order
 // (free part + lag table), i.e. they differ in the last bits -- far inside the 1e-10 parity tolerance.
 #pragma once
+#include <cuda_pipeline.h>
+
 #include "kernel_spinboson.cuh"
 
 namespace nq {
@@ -43,6 +45,8 @@ namespace nq {
 
 constexpr int kSeLagStride = 32;   // KParams::sb_kap: [2 shapes][3 sums][32 lags], then sum c^2/m, sum c^2
 constexpr int kSeThreads = 128;
+constexpr int kSeGroup = 4;        // modes a thread advances in lock step (independent FMA chains)
+constexpr int kSeStages = 4;       // depth of the bath pass's cp.async ring
 
 // impulses of one epoch: sb_f[(s * (E + 1) + i) * T + traj], s = 0 (f1) | 1 (f2), i = 0 .. E (entry kb: the carry)
 template <int E>
@@ -90,47 +94,75 @@ __global__ void __launch_bounds__(kSeThreads) sb_prep_kernel(const __grid_consta
 //   sb_nrep  : replay steps (the previous epoch's, impulses f[0 .. nrep-1])
 //   sb_nfree : free-evolution steps of the new epoch; its first step carries the impulse f[nrep]
 //   sb_exit  : launch exit: after the replay, finish the last half kick and store TRUE velocities
-template <int E, bool VINV, bool GEN>
-NQ_D void se_bath_body(const KParams& p, int64_t traj) {
-    constexpr int W = 4;
+//   FULL     : nrep == nfree == E, no entry / exit work (every epoch of a long run but the first and the last): without
+//              the per-step conditions the E steps of a group form ONE basic block, which lets ptxas interleave the
+//              dependent accumulator FMAs of step k with the coordinate FMAs of step k + 1
+template <int E, bool VINV, bool GEN, bool FULL>
+NQ_D void se_bath_body(const KParams& p, int64_t traj, double* ring) {
+    constexpr int W = kSeGroup;
     const int64_t T = p.ntraj;
-    const int D = p.D, nrep = p.sb_nrep, nfree = p.sb_nfree;
+    const int D = p.D, nrep = FULL ? E : p.sb_nrep, nfree = FULL ? E : p.sb_nfree;
+    const bool entry = !FULL && p.sb_entry, exitk = !FULL && p.sb_exit;
     const double dt = p.dt;
     const double* __restrict__ kcg = p.sb_kc;
-    double aL[E], aC[E], aW[E];
+    // L before the first free step and after each of them (C follows from their differences: every mode drifts by
+    // dt vt, so sum c vt_k = (L_k - L_{k-1}) / dt exactly in real arithmetic), and W
+    double aL[E + 1], aW[E];
 #pragma unroll
-    for (int k = 0; k < E; ++k) { aL[k] = 0.0; aC[k] = 0.0; aW[k] = 0.0; }
+    for (int k = 0; k < E; ++k) { aL[k] = 0.0; aW[k] = 0.0; }
+    aL[E] = 0.0;
     double f1[E], f2[VINV ? E : 1];
 #pragma unroll
     for (int k = 0; k < E; ++k) {
-        f1[k] = (k < nrep) ? p.sb_f[se_f_index<E>(0, k, T, traj)] : 0.0;
-        if (VINV) f2[k] = (k < nrep) ? p.sb_f[se_f_index<E>(1, k, T, traj)] : 0.0;
+        f1[k] = (FULL || k < nrep) ? p.sb_f[se_f_index<E>(0, k, T, traj)] : 0.0;
+        if (VINV) f2[k] = (FULL || k < nrep) ? p.sb_f[se_f_index<E>(1, k, T, traj)] : 0.0;
     }
     const double f1c = p.sb_f[se_f_index<E>(0, nrep, T, traj)];                      // the next step's impulse
     const double f2c = VINV ? p.sb_f[se_f_index<E>(1, nrep, T, traj)] : 0.0;
     const double A = GEN ? p.sb_carry[traj] : 1.0;
-    const double xk = (p.sb_entry || p.sb_exit) ? p.sb_aux[traj] : 0.0;
-    for (int j0 = 0; j0 < D; j0 += W) {
+    const double xk = (entry || exitk) ? p.sb_aux[traj] : 0.0;
+    const bool store = FULL || nrep > 0 || entry || exitk;
+    // The coordinates of the next kSeStages - 1 groups of modes are in flight (cp.async into this thread's own slots of
+    // a shared-memory ring: no registers, no barriers) while this group's arithmetic runs -- two or three warps per
+    // scheduler do not hide an HBM round trip on their own.
+    const int ngroups = (D + W - 1) / W;
+    auto issue = [&](int g) {
+        if (g < ngroups) {
+            double* dst = ring + ((size_t)(g % kSeStages) * 2 * W) * kSeThreads + threadIdx.x;
+#pragma unroll
+            for (int q = 0; q < W; ++q) {
+                const int j = (g * W + q < D) ? g * W + q : g * W;
+                __pipeline_memcpy_async(dst + (size_t)q * kSeThreads, p.r + (int64_t)j * T + traj, sizeof(double));
+                __pipeline_memcpy_async(dst + (size_t)(W + q) * kSeThreads, p.v + (int64_t)j * T + traj, sizeof(double));
+            }
+        }
+        __pipeline_commit();
+    };
+#pragma unroll
+    for (int g = 0; g < kSeStages - 1; ++g) issue(g);
+    for (int j0 = 0, g = 0; j0 < D; j0 += W, ++g) {
         double r[W], u[W];
         double4 kc[W];
         bool ok[W];
+        issue(g + kSeStages - 1);
+        __pipeline_wait_prior(kSeStages - 1);
+        const double* src = ring + ((size_t)(g % kSeStages) * 2 * W) * kSeThreads + threadIdx.x;
 #pragma unroll
         for (int q = 0; q < W; ++q) {
             const int j = j0 + q;
             ok[q] = j < D;
-            const int jc = ok[q] ? j : j0;
-            r[q] = p.r[(int64_t)jc * T + traj]; u[q] = p.v[(int64_t)jc * T + traj];
-            kc[q] = se_ldkc(kcg, jc);
+            r[q] = src[(size_t)q * kSeThreads]; u[q] = src[(size_t)(W + q) * kSeThreads];
+            kc[q] = se_ldkc(kcg, ok[q] ? j : j0);
             if (!ok[q]) kc[q] = make_double4(0.0, 0.0, 0.0, 0.0);      // a tail mode contributes nothing (and is not stored)
             if (GEN) kc[q].x *= A;
         }
-        if (p.sb_entry) {
+        if (entry) {
 #pragma unroll
             for (int q = 0; q < W; ++q) u[q] = fma(xk, kc[q].y, fma(0.5 * kc[q].x, r[q], u[q]));
         }
 #pragma unroll
         for (int k = 0; k < E; ++k) {
-            if (k < nrep) {
+            if (FULL || k < nrep) {
 #pragma unroll
                 for (int q = 0; q < W; ++q) {
                     double v = u[q];
@@ -141,7 +173,7 @@ NQ_D void se_bath_body(const KParams& p, int64_t traj) {
                 }
             }
         }
-        if (p.sb_exit) {
+        if (exitk) {
             // true velocity: the second half kick of the last step and whatever its hop left pending
 #pragma unroll
             for (int q = 0; q < W; ++q) {
@@ -150,14 +182,18 @@ NQ_D void se_bath_body(const KParams& p, int64_t traj) {
                 u[q] = fma(-(f1c - xk), kc[q].y, fma(-0.5 * kc[q].x, r[q], v));           // f1c - xk = 1/2 dt B + gamma_m
             }
         }
-        if (nrep > 0 || p.sb_entry || p.sb_exit) {
+        if (store) {
 #pragma unroll
             for (int q = 0; q < W; ++q)
                 if (ok[q]) { p.r[(int64_t)(j0 + q) * T + traj] = r[q]; p.v[(int64_t)(j0 + q) * T + traj] = u[q]; }
         }
+        if (FULL || nfree > 0) {
+#pragma unroll
+            for (int q = 0; q < W; ++q) aL[0] = fma(kc[q].z, r[q], aL[0]);
+        }
 #pragma unroll
         for (int k = 0; k < E; ++k) {
-            if (k < nfree) {
+            if (FULL || k < nfree) {
 #pragma unroll
                 for (int q = 0; q < W; ++q) {
                     double v = u[q];
@@ -168,18 +204,18 @@ NQ_D void se_bath_body(const KParams& p, int64_t traj) {
                     const double vt = fma(-kc[q].x, r[q], v);
                     r[q] = fma(dt, vt, r[q]);
                     u[q] = vt;
-                    aL[k] = fma(kc[q].z, r[q], aL[k]);
-                    aC[k] = fma(kc[q].z, vt, aC[k]);
+                    aL[k + 1] = fma(kc[q].z, r[q], aL[k + 1]);
                     aW[k] = fma(kc[q].w, r[q], aW[k]);
                 }
             }
         }
     }
+    const double rdt = 1.0 / dt;
 #pragma unroll
     for (int k = 0; k < E; ++k) {
-        if (k < nfree) {
-            p.sb_sums[(int64_t)(3 * k + 0) * T + traj] = aL[k];
-            p.sb_sums[(int64_t)(3 * k + 1) * T + traj] = aC[k];
+        if (FULL || k < nfree) {
+            p.sb_sums[(int64_t)(3 * k + 0) * T + traj] = aL[k + 1];
+            p.sb_sums[(int64_t)(3 * k + 1) * T + traj] = (aL[k + 1] - aL[k]) * rdt;
             p.sb_sums[(int64_t)(3 * k + 2) * T + traj] = aW[k];
         }
     }
@@ -187,13 +223,17 @@ NQ_D void se_bath_body(const KParams& p, int64_t traj) {
 
 template <int E>
 __global__ void __launch_bounds__(kSeThreads, 2) sb_bath_kernel(const __grid_constant__ KParams p) {
-    const int64_t traj = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ double ring[kSeStages * 2 * kSeGroup * kSeThreads];
+    int64_t traj = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (traj >= p.ntraj) return;
     const bool vinv = p.rescaling == NQCB200_RESCALE_VINVERSION;
-    if (p.sb_gen) {
-        if (vinv) se_bath_body<E, true, true>(p, traj); else se_bath_body<E, false, true>(p, traj);
+    const bool full = p.sb_nrep == E && p.sb_nfree == E && !p.sb_entry && !p.sb_exit;
+    if (p.sb_gen) {        // epochs of one step
+        if (vinv) se_bath_body<E, true, true, false>(p, traj, ring); else se_bath_body<E, false, true, false>(p, traj, ring);
+    } else if (full) {
+        if (vinv) se_bath_body<E, true, false, true>(p, traj, ring); else se_bath_body<E, false, false, true>(p, traj, ring);
     } else {
-        if (vinv) se_bath_body<E, true, false>(p, traj); else se_bath_body<E, false, false>(p, traj);
+        if (vinv) se_bath_body<E, true, false, false>(p, traj, ring); else se_bath_body<E, false, false, false>(p, traj, ring);
     }
 }
 
