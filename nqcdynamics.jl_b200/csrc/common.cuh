@@ -87,15 +87,15 @@ struct KParams {
     double* sb_carry; // [2][T]  SpinBoson thread-per-trajectory kernel: force scalars (A, B) carried between launches
     // kernel_spinboson_epoch.cuh: per-mode constants {dt w^2/m, c/m, c, c w^2/m}[D] and the bath's lag tables
     // [2 shapes][3 sums][32 lags] followed by sum c^2/m and sum c^2 (host-built at create); bath sums of the current
-    // epoch [3E][T], impulses [2][E+1][T], entry / exit half kick [T], "some trajectory has tr sigma != 1" flag; and
+    // epoch [3E][T], impulses [2][E+1][T], entry / exit half kick [T]; sb_gen: some trajectory has tr sigma != 1; and
     // the shape of the bath pass being launched
     const double* sb_kc;
     const double* sb_kap;
     double* sb_sums;
     double* sb_f;
     double* sb_aux;
-    int32_t* sb_flag;
     int32_t sb_entry, sb_nrep, sb_nfree, sb_exit, sb_gen;
+    int64_t tlo, thi;        // trajectory range [tlo, thi) this launch works on (chunked nqcb200_run_from_host); 0, ntraj otherwise
     // launch-fused initialisation (nqcb200_run_from_host, kernels with KernelSet::fused_init): trajectory-major
     // [T][B*D] sources read by the step kernel itself at step0 == 0 (device staging or pinned host memory)
     const double* r_aos;

@@ -64,6 +64,21 @@ __global__ void aos_to_soa(const Tin* __restrict__ in, Tout* __restrict__ out, i
         if (t < T && c < C) out[(int64_t)c * T + t] = tile[threadIdx.x][i];
     }
 }
+// in: [n][C] (a chunk of trajectories, trajectory-major)  ->  out: [C][ldT] at trajectory offset lo
+__global__ void aos_to_soa_range(const double* __restrict__ in, double* __restrict__ out, int64_t n, int C, int64_t ldT, int64_t lo) {
+    __shared__ double tile[32][33];
+    const int64_t t0 = (int64_t)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int64_t t = t0 + i; const int c = c0 + threadIdx.x;
+        if (t < n && c < C) tile[i][threadIdx.x] = in[t * C + c];
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i; const int64_t t = t0 + threadIdx.x;
+        if (t < n && c < C) out[(int64_t)c * ldT + lo + t] = tile[threadIdx.x][i];
+    }
+}
 template <typename Tin, typename Tout>
 __global__ void soa_to_aos(const Tin* __restrict__ in, Tout* __restrict__ out, int64_t T, int C, Tout add) {
     __shared__ Tout tile[32][33];
@@ -208,6 +223,12 @@ struct nqcb200_handle {
     int64_t launches_total = 0;    // every kernel this handle has launched (any kind)
     int64_t persistent_ctas = 1;   // CTA-per-trajectory kernels: resident CTAs (one per SM)
     bool traj_major = false;       // AdiabaticIESH: psi / occupations / diagnostics stay trajectory-major on the device
+    // SpinBoson epoch kernels (kernel_spinboson_epoch.cuh)
+    bool sb_gen = false;           // some trajectory has tr sigma != 1 (Ehrenfest): epochs of one step
+    cudaStream_t copy_stream = nullptr;        // chunked nqcb200_run_from_host: H2D copies overlap the previous chunk's epochs
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+    double* chunk_stage[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [buffer][r | v], trajectory-major chunk
+    int64_t chunk_traj = 0;
     std::string err;
 };
 
@@ -279,6 +300,12 @@ int fold_observables(nqcb200_handle* h) {
 }
 
 int launch_init(nqcb200_handle* h, int basis, int sample_state, const double* state_draw) {
+    if (h->ks.sb_init) {      // thread per trajectory; basis / sample_state / state_draw travel in KParams (finish_set_state)
+        h->ks.sb_init<<<(unsigned)((h->cfg.ntraj + kBlockThreads - 1) / kBlockThreads), kBlockThreads, 0, h->stream>>>(h->kp);
+        ++h->launches_total;
+        NQ_CUDA(h, cudaGetLastError());
+        return NQCB200_OK;
+    }
     h->ks.init<<<grid_for(h), h->ks.block, h->ks.dyn_smem, h->stream>>>(h->kp, basis, sample_state, state_draw);
     ++h->launches_total;
     NQ_CUDA(h, cudaGetLastError());
@@ -340,6 +367,16 @@ int set_state_impl(nqcb200_handle* h, const double* r, const double* v, const do
         if ((rc = upload_field(h, v, h->kp.v, BD)) != 0) return rc;
     }
     if (density) {
+        h->sb_gen = false;
+        if (h->ks.sb_epoch > 0 && c.method == NQCB200_METHOD_EHRENFEST) {
+            // Ehrenfest force scalar A = tr sigma (basis independent): the epoch kernels' lag tables need A = 1
+            const int n = c.nstates;
+            for (int64_t t = 0; t < T && !h->sb_gen; ++t) {
+                double tr = 0.0;
+                for (int i = 0; i < n; ++i) tr += sre[(size_t)t * n * n + (size_t)i * n + i];
+                if (!(std::fabs(tr - 1.0) <= 4e-16)) h->sb_gen = true;
+            }
+        }
         if ((rc = upload_field(h, sre, h->kp.sig_re, h->nsig)) != 0) return rc;
         if (sim) { if ((rc = upload_field(h, sim, h->kp.sig_im, h->nsig)) != 0) return rc; }
         else NQ_CUDA(h, cudaMemsetAsync(h->kp.sig_im, 0, sizeof(double) * T * h->nsig, h->stream));
@@ -378,6 +415,36 @@ int set_state_impl(nqcb200_handle* h, const double* r, const double* v, const do
     return finish_set_state(h, basis, sample_state, state_draw, fused);
 }
 
+// kernel_spinboson_epoch.cuh for the trajectories [lo, hi): prep, then per epoch one bath pass (replay the previous
+// epoch, free-evolve the next) and one electronic kernel, then the exit pass (replay + second half kick).  Enqueued on
+// the handle's stream, no synchronisation.
+int sb_run_range(nqcb200_handle* h, int64_t lo, int64_t hi, int64_t nsteps) {
+    if (hi <= lo || nsteps <= 0) return NQCB200_OK;
+    const unsigned grid = (unsigned)((hi - lo + kBlockThreads - 1) / kBlockThreads);
+    KParams kp = h->kp;
+    kp.tlo = lo; kp.thi = hi;
+    kp.step0 = h->step_count; kp.nsteps = 0;
+    kp.sb_gen = h->sb_gen ? 1 : 0;
+    h->ks.sb_prep<<<grid, kBlockThreads, 0, h->stream>>>(kp); ++h->launches_total;
+    const int64_t E = h->sb_gen ? 1 : h->ks.sb_epoch;      // tr sigma != 1 somewhere: the lag tables do not apply
+    int nrep = 0;
+    int64_t done = 0;
+    while (done < nsteps) {
+        const int kb = (int)std::min<int64_t>(E, nsteps - done);
+        kp.sb_entry = (done == 0); kp.sb_nrep = nrep; kp.sb_nfree = kb; kp.sb_exit = 0;
+        h->ks.sb_bath<<<grid, kBlockThreads, 0, h->stream>>>(kp); ++h->launches_total;
+        kp.step0 = h->step_count + done; kp.nsteps = kb;
+        h->ks.sb_elec<<<grid, kBlockThreads, 0, h->stream>>>(kp); ++h->launches_total;
+        h->last_launches += 2;
+        nrep = kb; done += kb;
+    }
+    kp.sb_entry = 0; kp.sb_nrep = nrep; kp.sb_nfree = 0; kp.sb_exit = 1;
+    h->ks.sb_bath<<<grid, kBlockThreads, 0, h->stream>>>(kp); ++h->launches_total;
+    h->last_launches += 2;
+    NQ_CUDA(h, cudaGetLastError());
+    return NQCB200_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -400,6 +467,8 @@ int nqcb200_destroy(nqcb200_handle* h) {
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->ev2) cudaEventDestroy(h->ev2);
     if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    for (int i = 0; i < 2; ++i) { if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]); if (h->ev_free[i]) cudaEventDestroy(h->ev_free[i]); }
     cudaGetLastError();
     delete h;
     return NQCB200_OK;
@@ -447,6 +516,7 @@ int nqcb200_create(const nqcb200_config* cfg, nqcb200_handle** out) {
     KParams& kp = h->kp;
     std::memset(&kp, 0, sizeof(kp));
     kp.term_dof = -1;   // no TerminatingCallback until nqcb200_set_termination
+    kp.tlo = 0; kp.thi = T;
     kp.ntraj = T; kp.traj_offset = c.traj_offset; kp.n = n; kp.D = D; kp.B = B; kp.ne = c.nelectrons;
     kp.save_every = c.save_every; kp.nsave = c.nsave; kp.rescaling = c.rescaling; kp.rng = c.rng;
     kp.diagnostics = c.diagnostics; kp.per_trajectory = c.per_trajectory;
@@ -586,7 +656,6 @@ int nqcb200_create(const nqcb200_config* cfg, nqcb200_handle** out) {
             if ((rc = dev_alloc(h, &kp.sb_sums, (size_t)3 * E * T)) != 0) return fail(rc);
             if ((rc = dev_alloc(h, &kp.sb_f, (size_t)2 * (E + 1) * T)) != 0) return fail(rc);
             if ((rc = dev_alloc(h, &kp.sb_aux, (size_t)T)) != 0) return fail(rc);
-            if ((rc = dev_alloc(h, &kp.sb_flag, (size_t)1)) != 0) return fail(rc);
         }
     }
     if (ks.step_smem > 48 * 1024) {
@@ -752,37 +821,14 @@ int nqcb200_run(nqcb200_handle* h, int64_t nsteps) {
     }
     h->last_launches = 0;
     h->last_ms = 0.0;
+    int rc;
     if (c.ntraj == 0 || nsteps == 0) { h->step_count += nsteps; return NQCB200_OK; }
     const int64_t max_per_launch = 1 << 16;
     NQ_CUDA(h, cudaEventRecord(h->ev0, h->stream));
     int64_t done = 0;
     if (h->ks.sb_epoch > 0) {
-        // kernel_spinboson_epoch.cuh: prep, then per epoch one bath pass (replay the previous epoch, free-evolve the next)
-        // and one electronic kernel, then the exit pass (replay + second half kick)
-        const unsigned grid = (unsigned)((c.ntraj + kBlockThreads - 1) / kBlockThreads);
-        KParams kp = h->kp;
-        kp.step0 = h->step_count; kp.nsteps = 0;
-        NQ_CUDA(h, cudaMemsetAsync(kp.sb_flag, 0, sizeof(int32_t), h->stream));
-        h->ks.sb_prep<<<grid, kBlockThreads, 0, h->stream>>>(kp); ++h->launches_total;
-        int32_t gen = 0;
-        NQ_CUDA(h, cudaMemcpyAsync(&gen, kp.sb_flag, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
-        NQ_CUDA(h, cudaStreamSynchronize(h->stream));
-        kp.sb_gen = gen;
-        const int64_t E = gen ? 1 : h->ks.sb_epoch;      // tr sigma != 1 somewhere: the lag tables do not apply
-        int nrep = 0;
-        while (done < nsteps) {
-            const int kb = (int)std::min<int64_t>(E, nsteps - done);
-            kp.sb_entry = (done == 0); kp.sb_nrep = nrep; kp.sb_nfree = kb; kp.sb_exit = 0;
-            h->ks.sb_bath<<<grid, kBlockThreads, 0, h->stream>>>(kp); ++h->launches_total;
-            kp.step0 = h->step_count + done; kp.nsteps = kb;
-            h->ks.sb_elec<<<grid, kBlockThreads, 0, h->stream>>>(kp); ++h->launches_total;
-            h->last_launches += 2;
-            nrep = kb; done += kb;
-        }
-        kp.sb_entry = 0; kp.sb_nrep = nrep; kp.sb_nfree = 0; kp.sb_exit = 1;
-        h->ks.sb_bath<<<grid, kBlockThreads, 0, h->stream>>>(kp); ++h->launches_total;
-        h->last_launches += 2;
-        NQ_CUDA(h, cudaGetLastError());
+        if ((rc = sb_run_range(h, 0, c.ntraj, nsteps)) != 0) return rc;
+        done = nsteps;
     }
     while (done < nsteps) {
         const int64_t chunk = std::min(nsteps - done, max_per_launch);
@@ -824,6 +870,61 @@ int nqcb200_run_from_host(nqcb200_handle* h, const double* r, const double* v, c
     }
     NQ_CUDA(h, cudaSetDevice(c.device));
     if ((rc = set_state_impl(h, r, v, rho_re, rho_im, state, diabatic ? 1 : 0, diabatic ? state_draw : nullptr, true)) != 0) return rc;
+    if (h->ks.sb_epoch > 0) {
+        if (c.method == NQCB200_METHOD_FSSH && c.rng == NQCB200_RNG_INJECTED &&
+            (!h->kp.draws || h->step_count < h->kp.draws_step0 || h->step_count + nsteps > h->kp.draws_step0 + h->draws_nsteps)) {
+            h->err = "not enough injected draws for this run"; return NQCB200_ERR_STATE;
+        }
+        // Chunks of trajectories: the H2D copy of chunk c + 1 (copy stream, DMA engine) overlaps the transposition,
+        // initialisation and all epochs of chunk c (compute stream).  Every chunk runs the whole time span; trajectories
+        // are independent, and the observable accumulators are shared.
+        const int D = c.ndofs;
+        const int64_t T = c.ntraj;
+        if (!h->copy_stream) {
+            NQ_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+            for (int i = 0; i < 2; ++i) {
+                NQ_CUDA(h, cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming));
+                NQ_CUDA(h, cudaEventCreateWithFlags(&h->ev_free[i], cudaEventDisableTiming));
+            }
+            h->chunk_traj = std::min<int64_t>(T, 1 << 16);
+            for (int i = 0; i < 2; ++i)
+                for (int k = 0; k < 2; ++k)
+                    if ((rc = dev_alloc(h, &h->chunk_stage[i][k], (size_t)h->chunk_traj * D)) != 0) return rc;
+            NQ_CUDA(h, cudaStreamSynchronize(h->stream));      // the zero fill of the new buffers
+        }
+        h->last_launches = 0; h->last_ms = 0.0;
+        NQ_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+        NQ_CUDA(h, cudaEventRecord(h->ev2, h->stream));
+        NQ_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->ev2, 0));      // sigma / state uploads of set_state_impl are enqueued
+        const int64_t Tc = h->chunk_traj;
+        int ci = 0;
+        for (int64_t lo = 0; lo < T; lo += Tc, ++ci) {
+            const int64_t hi = std::min(T, lo + Tc), n = hi - lo;
+            const int b = ci & 1;
+            if (ci >= 2) NQ_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->ev_free[b], 0));
+            NQ_CUDA(h, cudaMemcpyAsync(h->chunk_stage[b][0], r + (size_t)lo * D, sizeof(double) * n * D, cudaMemcpyHostToDevice, h->copy_stream));
+            NQ_CUDA(h, cudaMemcpyAsync(h->chunk_stage[b][1], v + (size_t)lo * D, sizeof(double) * n * D, cudaMemcpyHostToDevice, h->copy_stream));
+            NQ_CUDA(h, cudaEventRecord(h->ev_h2d[b], h->copy_stream));
+            NQ_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_h2d[b], 0));
+            dim3 grid((unsigned)((n + 31) / 32), (unsigned)((D + 31) / 32)), block(32, 8);
+            aos_to_soa_range<<<grid, block, 0, h->stream>>>(h->chunk_stage[b][0], h->kp.r, n, D, T, lo);
+            aos_to_soa_range<<<grid, block, 0, h->stream>>>(h->chunk_stage[b][1], h->kp.v, n, D, T, lo);
+            h->launches_total += 2;
+            NQ_CUDA(h, cudaEventRecord(h->ev_free[b], h->stream));
+            KParams kp = h->kp;
+            kp.tlo = lo; kp.thi = hi;
+            h->ks.sb_init<<<(unsigned)((n + kBlockThreads - 1) / kBlockThreads), kBlockThreads, 0, h->stream>>>(kp); ++h->launches_total;
+            if ((rc = sb_run_range(h, lo, hi, nsteps)) != 0) return rc;
+        }
+        NQ_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+        NQ_CUDA(h, cudaStreamSynchronize(h->stream));
+        float ms = 0.f;
+        NQ_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        h->last_ms = ms;
+        h->step_count += nsteps;
+        h->nsave_done = std::min<int64_t>(c.nsave, h->step_count / c.save_every + 1);
+        return NQCB200_OK;
+    }
     // r, v: pinned (or registered) host memory is read in place by the step kernel over PCIe, so the upload of later
     // blocks overlaps the dynamics of earlier ones; pageable memory goes through a trajectory-major device staging copy
     const size_t count = (size_t)c.ntraj * c.nbeads * c.ndofs;
@@ -884,6 +985,11 @@ int nqcb200_sample_state(nqcb200_handle* h, const nqcb200_dist* r_dist, const nq
             const int nn = h->nsig;
             std::vector<double> m(2 * (size_t)nn, 0.0);
             for (int i = 0; i < nn; ++i) { m[i] = rho_re[i]; m[nn + i] = rho_im ? rho_im[i] : 0.0; }
+            {
+                double tr = 0.0;
+                for (int i = 0; i < c.nstates; ++i) tr += rho_re[(size_t)i * c.nstates + i];
+                h->sb_gen = h->ks.sb_epoch > 0 && c.method == NQCB200_METHOD_EHRENFEST && !(std::fabs(tr - 1.0) <= 4e-16);
+            }
             NQ_CUDA(h, cudaMemcpyAsync(h->staging, m.data(), sizeof(double) * 2 * nn, cudaMemcpyHostToDevice, h->stream));
             NQ_CUDA(h, cudaStreamSynchronize(h->stream));   // m goes out of scope
             broadcast_matrix_kernel<<<grid, 128, 0, h->stream>>>(h->staging, h->kp.sig_re, T, nn);

@@ -62,8 +62,8 @@ NQ_D double4 se_ldkc(const double* __restrict__ kc, int j) {      // uniform add
 template <int METHOD, int E>
 __global__ void __launch_bounds__(kSeThreads) sb_prep_kernel(const __grid_constant__ KParams p) {
     constexpr int N = 2;
-    const int64_t T = p.ntraj, traj = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (traj >= T) return;
+    const int64_t T = p.ntraj, traj = p.tlo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (traj >= p.thi) return;
     double A, B;
     if (p.step0 == 0) {
         // first step after set_state: no hop has happened, sigma is sigma(t0), Zprev the eigenvectors at r0
@@ -86,7 +86,73 @@ __global__ void __launch_bounds__(kSeThreads) sb_prep_kernel(const __grid_consta
     p.sb_aux[traj] = 0.5 * p.dt * B;                                   // xk: u = v + 1/2 (A a r + dt B c/m) on entry
     p.sb_f[se_f_index<E>(0, 0, T, traj)] = p.dt * B;                   // impulse of the first step
     p.sb_f[se_f_index<E>(1, 0, T, traj)] = 0.0;
-    if (METHOD != NQCB200_METHOD_FSSH && !(fabs(A - 1.0) <= 1e-15)) *p.sb_flag = 1;     // general-A path: epochs of one step
+}
+
+// ---- DynamicsVariables at t0 (fssh.jl:47-65, ehrenfest.jl:43-48): eigenproblem at r0, sigma = Z' rho Z, initial state
+// ~ diag(sigma), zeroed electronic buffer (quirk Q1), save point 0 -- thread per trajectory -------------------------------
+template <int METHOD>
+__global__ void __launch_bounds__(kSeThreads) sb_init_kernel(const __grid_constant__ KParams p) {
+    constexpr int N = 2;
+    const int64_t T = p.ntraj;
+    int64_t traj = p.tlo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = traj < p.thi;
+    if (!valid) traj = p.thi - 1;
+    double lin = 0.0;
+    for (int j = 0; j < p.D; ++j) lin = fma(se_ldkc(p.sb_kc, j).z, p.r[(int64_t)j * T + traj], lin);
+    SbTraj R;
+    R.s.x[0] = p.sig_re[(int64_t)0 * T + traj]; R.s.x[1] = p.sig_re[(int64_t)2 * T + traj]; R.s.x[2] = p.sig_re[(int64_t)3 * T + traj];
+    R.s.y[0] = p.sig_im[(int64_t)2 * T + traj];
+    R.st = p.state ? p.state[traj] : 0;
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+#pragma unroll
+        for (int k = 0; k < N; ++k) R.Zref[j][k] = p.Zprev[(int64_t)(j + N * k) * T + traj];
+    Eig<N> e;
+    const double l = p.params[0] + lin;
+    double Vp[3] = {l, p.params[1], -l};
+    sym_eigh<N>(Vp, e);
+    fix_gauge<N>(e, R.Zref);
+    if (p.init_basis == 1) {
+        Herm<N> o;
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+#pragma unroll
+            for (int j = i; j < N; ++j) {
+                double sx = 0.0, sy = 0.0;
+#pragma unroll
+                for (int a = 0; a < N; ++a)
+#pragma unroll
+                    for (int b = 0; b < N; ++b) {
+                        sx += e.Z[a][i] * R.s.X(a, b) * e.Z[b][j];
+                        sy += e.Z[a][i] * R.s.Y(a, b) * e.Z[b][j];
+                    }
+                o.x[sidx(N, i, j)] = sx;
+                if (j > i) o.y[aidx(N, i, j)] = sy;
+            }
+        R.s = o;
+    }
+    if (METHOD == NQCB200_METHOD_FSSH && p.init_sample_state) {
+        const double xi = p.init_state_draw ? p.init_state_draw[traj]
+                                            : philox_uniform(p.seed, (uint64_t)(p.traj_offset + traj), 0ull, 1u);
+        const double target = xi * (R.s.x[0] + R.s.x[2]);
+        R.st = (R.s.x[0] < target) ? 1 : 0;
+    }
+    SbSmem Mdummy; Mdummy.rs = nullptr; Mdummy.vs = nullptr; Mdummy.k1 = Mdummy.k2 = Mdummy.k3 = nullptr;
+    SbEmitter em{p, traj, valid, 0};
+    sb_record_save<METHOD>(p, em, Mdummy, 0, R, e, 0.0);      // also writes pop0 (correlation functions)
+    if (valid) {
+#pragma unroll
+        for (int j = 0; j < N; ++j)
+#pragma unroll
+            for (int k = 0; k < N; ++k) {
+                p.sig_re[(int64_t)(j + N * k) * T + traj] = R.s.X(j, k);
+                p.sig_im[(int64_t)(j + N * k) * T + traj] = R.s.Y(j, k);
+                p.Zprev[(int64_t)(j + N * k) * T + traj] = R.Zref[j][k];
+            }
+        if (p.state) p.state[traj] = R.st;
+        p.ecur[(int64_t)0 * T + traj] = 0.0; p.ecur[(int64_t)1 * T + traj] = 0.0;
+        p.ecur[(int64_t)(N + 0 + N * 1) * T + traj] = 0.0;
+    }
 }
 
 // ---- bath pass -------------------------------------------------------------------------------------------------------
@@ -224,8 +290,8 @@ NQ_D void se_bath_body(const KParams& p, int64_t traj, double* ring) {
 template <int E>
 __global__ void __launch_bounds__(kSeThreads, 2) sb_bath_kernel(const __grid_constant__ KParams p) {
     __shared__ double ring[kSeStages * 2 * kSeGroup * kSeThreads];
-    int64_t traj = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (traj >= p.ntraj) return;
+    const int64_t traj = p.tlo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (traj >= p.thi) return;
     const bool vinv = p.rescaling == NQCB200_RESCALE_VINVERSION;
     const bool full = p.sb_nrep == E && p.sb_nfree == E && !p.sb_entry && !p.sb_exit;
     if (p.sb_gen) {        // epochs of one step
@@ -244,9 +310,9 @@ __global__ void __launch_bounds__(kSeThreads, 4) sb_elec_kernel(const __grid_con
     __shared__ double fs[2][E + 1][kSeThreads];      // this epoch's impulses (f1, f2), per thread
     const int tid = threadIdx.x;
     const int64_t T = p.ntraj;
-    int64_t traj = (int64_t)blockIdx.x * blockDim.x + tid;
-    const bool valid = traj < T;
-    if (!valid) traj = T - 1;
+    int64_t traj = p.tlo + (int64_t)blockIdx.x * blockDim.x + tid;
+    const bool valid = traj < p.thi;
+    if (!valid) traj = p.thi - 1;
     const double dt = p.dt, hdt = 0.5 * p.dt;
     const bool vinv = p.rescaling == NQCB200_RESCALE_VINVERSION;
     const double* __restrict__ kap = p.sb_kap;

@@ -26,7 +26,7 @@ struct KernelSet {
     bool fused_init = false;       // the step kernel can initialise from KParams.r_aos / v_aos (see common.cuh)
     // kernel_spinboson_epoch.cuh: E nuclear steps per (bath pass, electronic kernel) pair instead of one `step` kernel
     int sb_epoch = 0;
-    StepFn sb_prep = nullptr, sb_bath = nullptr, sb_elec = nullptr;
+    StepFn sb_init = nullptr, sb_prep = nullptr, sb_bath = nullptr, sb_elec = nullptr;
     bool cta_per_trajectory = false;
     IeshLayout iesh = {};   // AdiabaticIESH tile / shared-memory plan (kernel_iesh.cuh)
     const char* name = "";

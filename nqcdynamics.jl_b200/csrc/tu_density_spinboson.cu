@@ -65,7 +65,8 @@ bool select_density_spinboson(const nqcb200_config& c, KernelSet& out, std::stri
             } while (0)
             if (epoch == 8) NQ_SB_EPOCH(8); else NQ_SB_EPOCH(16);
 #undef NQ_SB_EPOCH
-            out.fused_init = false;
+            out.sb_init = f ? sb_init_kernel<NQCB200_METHOD_FSSH> : sb_init_kernel<NQCB200_METHOD_EHRENFEST>;
+            out.fused_init = true;       // nqcb200_run_from_host: chunked upload overlapped with the epochs of the previous chunk
             out.name = f ? "spinboson_fssh_epoch" : "spinboson_ehrenfest_epoch";
         }
         return true;
