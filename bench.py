@@ -9,20 +9,24 @@ device at every save point.  Every step is the same job on a fresh batch: the in
 device from the resident distribution parameters (nqcb200_sample_state) before each run; only AdiabaticIESH / NRPMD
 (no device sampler) continue the same trajectories across steps.
 
-  value     trajectory-steps/s with the step's inputs resident in HBM: the K timed regions bracket the blocking,
-            stream-synchronised nqcb200_run of each step (max over ranks); the engine's CUDA-event time of the same
-            launches is kernel_ms_total and feeds the roofline.
-  e2e       the same metric through the public C-ABI call sequence with HOST buffers: every step hands over fresh
+  value     trajectory-steps/s with the step's inputs resident in HBM: the K timed regions bracket the device-side draw of a
+            fresh batch (nqcb200_sample_state: sampling, t0 eigenproblem, save point 0) and the blocking,
+            stream-synchronised nqcb200_run of each step (max over ranks); the engine's CUDA-event time of the step
+            kernels is kernel_ms_total and feeds the roofline.
+  e2e       the same metric through the public C-ABI call sequence with HOST buffers: each of the K steps hands over fresh
             initial conditions in pinned host memory (nqcb200_run_from_host / set_state), runs, and reads the reduced
             observable back.
-  roofline  FP64: algorithmic flops per trajectory-step x trajectory-steps per launch / kernel
-            time, against the DFMA peak measured in this run (MEASURED_PEAKS.json has no FP64 entry).
+  roofline  FP64: frac = the flops the kernels EXECUTE (committed ncu instruction mix x the live rate) over the DFMA peak
+            measured in this run (MEASURED_PEAKS.json has no FP64 entry); algorithmic_frac = the reference's dense
+            formulation, reported next to it because the kernels do not execute that work.
+  other_configs  short legs of the other BASELINE configs (C1, C3, C4, C5) measured by the same code in the same run.
   cpu_baseline  the CPU oracle (a C++ restatement of the reference algorithm, NOT Julia) on the host cores,
             on a bounded sample of the same workload.
 
 `--impl reference` times that CPU restatement alone (the Julia reference cannot run here: no julia binary).
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -37,20 +41,20 @@ sys.path.insert(0, ROOT)
 
 DEFAULT_WORKLOAD = "spinboson_debye100_fssh"   # BASELINE.json configs[1]
 
-# dram__bytes_read.sum + dram__bytes_write.sum of the step kernel per TRAJECTORY per launch, from the `ncu --set full`
-# captures committed under profiles/r01/ (prof_r01_<tag>_raw.csv; bytes / trajectories of the capture).  The kernels
-# touch HBM only at launch entry / exit (state in, state out) and at save points, so the traffic of a launch scales
-# with the number of trajectories, not with the number of steps.
-NCU_DRAM_BYTES_PER_TRAJ = {
-    "spinboson_debye100_fssh": (2696.0, "sb_v5"), "spinboson_debye100_ehrenfest": (2696.0, "sb_v5"),
-    "tully1_fssh": (236.0, "tully1_v3"), "rpmd_harmonic32": (1356.0, "rpmd_fft"), "rpsh_morse3_16": (664.0, "rpsh_tpt2"),
-}
-# FP64 flops the kernels EXECUTE per trajectory-step (DFMA = 2), from the committed instruction-mix passes
-# profiles/r01/instmix_r01_<tag>.csv (thread-level DFMA/DADD/DMUL counts / (T x steps)); see profiles/r01/SUMMARY.md
-NCU_EXECUTED_FLOPS_PER_TRAJ_STEP = {
-    "spinboson_debye100_fssh": (3630.0, "sb_v5"), "tully1_fssh": (1306.0, "tully1_v3"), "rpmd_harmonic32": (1940.0, "rpmd_tpt"),
-    "rpsh_morse3_16": (12700.0, "rpsh_tpt2"),
-}
+# Evidence tables, refreshed from the ncu passes committed under profiles/r02/ (tools/profile.sh; SUMMARY.md there):
+#   NCU_DRAM_BYTES_PER_TRAJ_STEP   dram__bytes_read.sum + dram__bytes_write.sum of the step kernel(s) per trajectory-step
+#   NCU_EXECUTED_FLOPS_PER_TRAJ_STEP  FP64 flops the kernels EXECUTE per trajectory-step (DFMA = 2, DADD = DMUL = 1; thread-level
+#                                  counts of the instruction-mix pass / (T x steps)), summed over the kernels of a step
+PROFILE_ROUND = "r02"
+NCU_DRAM_BYTES_PER_TRAJ_STEP = {}
+NCU_EXECUTED_FLOPS_PER_TRAJ_STEP = {}
+try:
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", PROFILE_ROUND, "executed_flops.json")) as _f:
+        _tab = json.load(_f)
+    NCU_EXECUTED_FLOPS_PER_TRAJ_STEP = {k: (v["flops_per_traj_step"], v["source"]) for k, v in _tab.items() if "flops_per_traj_step" in v}
+    NCU_DRAM_BYTES_PER_TRAJ_STEP = {k: (v["dram_bytes_per_traj_step"], v["source"]) for k, v in _tab.items() if "dram_bytes_per_traj_step" in v}
+except (OSError, ValueError):
+    pass
 
 
 def parse_args():
@@ -64,6 +68,8 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target duration of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true",
+                    help="skip the short legs of the other BASELINE configs appended under other_configs")
     ap.add_argument("--stream", action="store_true",
                     help="also measure the per-trajectory output-streaming path (SortByTrajectory / FileReduction)")
     return ap.parse_args()
@@ -82,7 +88,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -164,10 +170,24 @@ def run_cpu_oracle(wl, seconds, seed=1):
     return value, info, T2 * nsteps / wl.nsteps, dt2
 
 
+def workload_config(wl, T, world, resample, A):
+    """The `config` object of the JSON line: identical in the b200 arm and the reference arm (which times a bounded sample
+    of the SAME workload and says so under cpu_baseline.sample, not here)."""
+    return {"workload": wl.name, "description": wl.description, "trajectories_per_gpu": T,
+            "nuclear_steps_per_step": wl.nsteps, "save_every": wl.save_every,
+            "batch": ("every step draws a fresh batch from the config's initial-condition distribution and runs the full tspan"
+                      if resample else "trajectories continue across steps"),
+            "observables_on_device": [o for o in range(A.OBS_COUNT) if (wl.observables >> o) & 1],
+            "l2": "trajectory state larger than L2" if T * 8 * 3 * len(wl.masses) * wl.nbeads > 126e6
+                  else "state register-resident for the whole launch; no reuse of cached inputs between steps",
+            "parallelism": f"trajectories sharded over {world} GPU(s), one NCCL all-reduce of observables"}
+
+
 def reference_arm(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    import nqcdynamics_jl_b200 as nq
     per_step = max(2.0, min(args.cpu_seconds, 120.0 / max(1, args.steps + args.warmup)))
     times, units = [], []
     info = None
@@ -177,12 +197,12 @@ def reference_arm(args, wl):
             times.append(dt2); units.append(T2 * wl.nsteps)
     value = sum(units) / sum(times)
     info["value"] = value
+    T = args.trajectories or wl.ntraj_default
     line = {"impl": "reference", "metric": "trajectory-steps/sec (FP64)", "value": value, "unit": "trajectory-steps/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": wl.name, "description": wl.description,
-                       "note": "CPU restatement of the reference algorithm on the host cores; bounded sample per step"},
+            "config": workload_config(wl, T, max(1, args.gpus), wl.device_spec is not None, nq._abi),
             "cpu_baseline": info,
             "e2e": {"value": value, "unit": "trajectory-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -196,6 +216,225 @@ class _DevArray:
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
 
 
+class Bench:
+    """One process = one GPU.  measure() runs W + K jobs of one workload and returns the numbers of the JSON line."""
+
+    def __init__(self):
+        import nqcdynamics_jl_b200 as nq
+        from nqcdynamics_jl_b200 import workloads
+        self.nq, self.A, self.workloads = nq, nq._abi, workloads
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.dist = self.torch = None
+        self.stdout_fd = None
+        if self.world > 1:
+            # stdout carries exactly one JSON line: whatever libraries write to fd 1 meanwhile (NCCL prints its
+            # "NCCL version ..." banner there when the communicator is created) goes to stderr until the line is printed
+            sys.stdout.flush()
+            self.stdout_fd = os.dup(1)
+            os.dup2(2, 1)
+            import torch
+            import torch.distributed as dist
+            torch.cuda.set_device(self.local_rank)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+            self.dist, self.torch = dist, torch
+        self.lib = self.A.load_engine_library()
+        if self.lib.nqcb200_device_count() <= 0:
+            raise SystemExit("bench.py: no CUDA device visible -- the engine has no CPU path")
+        peak = ctypes.c_double()
+        self.lib.nqcb200_measure_fp64_peak(self.local_rank, ctypes.byref(peak))
+        self.peak = float(peak.value)
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+
+    def allreduce_observables(self, h):
+        if self.dist is None:
+            return
+        ptr, n = h.observable_sum_device()
+        if n:
+            t = self.torch.as_tensor(_DevArray(ptr, n), device=f"cuda:{self.local_rank}")
+            self.dist.all_reduce(t)
+            self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, *vals):
+        if self.dist is None:
+            return vals
+        tt = self.torch.tensor(list(vals), device=f"cuda:{self.local_rank}", dtype=self.torch.float64)
+        self.dist.all_reduce(tt, op=self.dist.ReduceOp.MAX)
+        return tuple(float(x) for x in tt)
+
+    def pin(self, a):
+        try:
+            import torch as _t
+            return _t.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+        except Exception:
+            return np.ascontiguousarray(a)
+
+    # ------------------------------------------------------------------------------------------
+    def measure(self, wl, T, K, W, e2e_steps, sample_clocks=True):
+        A, Engine = self.A, __import__("nqcdynamics_jl_b200.engine", fromlist=["Engine"]).Engine
+        world, rank, local_rank = self.world, self.rank, self.local_rank
+        density = wl.method in (A.METHOD_FSSH, A.METHOD_EHRENFEST)
+        # Every step is the SAME job.  Where the device-side sampler covers the workload's distribution, each step draws a
+        # fresh batch from the resident distribution parameters (nqcb200_sample_state) INSIDE the timed region and runs the
+        # config's full tspan; otherwise (AdiabaticIESH, NRPMD) the trajectories keep running across steps.
+        resample = wl.device_spec is not None
+        nsave_total = wl.nsave if resample else (W + K) * wl.nsteps // wl.save_every + 1
+        kw = wl.config_kwargs(T, seed=20261017, device=local_rank, traj_offset=rank * T)
+        kw["nsave"] = nsave_total
+        cfg, keep = A.make_config(**kw)
+        eng = Engine(cfg, keep)
+        rng = np.random.default_rng(1234 + rank)
+        ic = wl.sample(rng, T)
+        rho = wl.initial_density(T) if density else None
+        if wl.method == A.METHOD_IESH:
+            ic["psi"], ic["state"] = wl.iesh_ground_state(T)
+
+        def upload(h, r, v, psi=None):
+            return wl.upload(h, {**ic, "r": r, "v": v, "psi": ic.get("psi") if psi is None else psi}, rho)
+
+        upload(eng, ic["r"], ic["v"])
+        rho1 = None
+        if resample and density:
+            rho1 = np.zeros((wl.model.nstates, wl.model.nstates))
+            rho1[wl.initial_diabatic_state, wl.initial_diabatic_state] = 1.0
+
+        def fresh_batch(h):
+            if resample:
+                h.sample_state(wl.device_spec[0], wl.device_spec[1], rho1, diabatic=True, state=0, normal_modes=wl.device_spec[2])
+
+        for _ in range(W):
+            fresh_batch(eng)
+            eng.run(wl.nsteps)
+        self.allreduce_observables(eng)
+        self.barrier()
+        sampler = ClockSampler(local_rank) if sample_clocks else None
+        if sampler:
+            sampler.start()
+        kernel_ms, launches = 0.0, 0
+        launches_before = eng.launch_count()
+        wall, prep = 0.0, 0.0
+        for k in range(K):
+            # timed region of one step: barrier + fresh batch (device-side sampling, t0 eigenproblem, save point 0) +
+            # the (blocking) run [+ the job's only exchange after the last step]; the engine synchronises its stream
+            # before returning and times its step kernels with CUDA events on that stream
+            self.barrier()
+            t0 = time.perf_counter()
+            fresh_batch(eng)
+            t1 = time.perf_counter()
+            eng.run(wl.nsteps)
+            if k == K - 1:
+                self.allreduce_observables(eng)          # one all-reduce of the accumulators
+            wall += time.perf_counter() - t0
+            prep += t1 - t0
+            ms, nl = eng.last_run_timing()
+            kernel_ms += ms; launches += nl
+        launches_all = eng.launch_count() - launches_before      # sampling / init / step / fold kernels of the K steps
+        clocks = sampler.stop() if sampler else None
+        self.barrier()
+        dev_s, wall = self.max_over_ranks(kernel_ms * 1e-3, wall)
+        units = float(T) * world * wl.nsteps * K
+        value = units / wall
+        counters = eng.counters()
+        flops_alg = wl.flops_per_traj_step
+        flops_note = ""
+        executed = None
+        if wl.method == A.METHOD_IESH:
+            st = eng.iesh_stats()
+            counters.update(st)
+            frac = st["hop_searches"] / max(1, counters["steps"])
+            extra = self.workloads.iesh_hop_search_flops(wl.model.nstates, wl.model.nelectrons)
+            flops_alg = wl.flops_per_traj_step + frac * extra
+            flops_note = (f"; IESH: base step {wl.flops_per_traj_step:.4g} flops + unpruned hop search {extra:.4g} flops on "
+                          f"{frac:.4f} of the steps (measured), both counted in the reference's formulation")
+            # executed: the Horner GEMMs of the Taylor propagator on the DMMA pipe, 2 n^2 (2 ne) flops per stage, counted live
+            n, ne = wl.model.nstates, wl.model.nelectrons
+            executed = (2.0 * n * n * 2 * ne * st["gemm_stages"] / max(1, counters["steps"]),
+                        "live: nqcb200_get_iesh_stats gemm_stages x 2 n^2 (2 ne) DMMA flops (the vector-pipe work of the secular "
+                        "solver, norms and LU is not counted)")
+        elif wl.name in NCU_EXECUTED_FLOPS_PER_TRAJ_STEP:
+            executed = NCU_EXECUTED_FLOPS_PER_TRAJ_STEP[wl.name]
+        obs_check = (float(np.sum(eng.observable_sum(A.OBS_POPCORR_DIABATIC)[0]))
+                     if (wl.observables >> A.OBS_POPCORR_DIABATIC) & 1 else None)
+
+        # ---- end-to-end through the C ABI with HOST buffers: K' jobs, each handing over fresh pinned host arrays ----
+        e2e = None
+        if e2e_steps > 0:
+            kw2 = wl.config_kwargs(T, seed=7, device=local_rank, traj_offset=rank * T)
+            cfg2, keep2 = A.make_config(**kw2)
+            eng.close()
+            eng2 = Engine(cfg2, keep2)
+            r_h, v_h = self.pin(ic["r"]), self.pin(ic["v"])
+            rho_h = self.pin(rho) if rho is not None else None
+            psi_h = self.pin(ic["psi"]) if "psi" in ic else None
+            first_obs = next(o for o in range(A.OBS_COUNT) if (wl.observables >> o) & 1)
+            d2h = 0
+
+            def job(h):
+                """one ensemble batch through the public C-ABI calls with HOST buffers; returns the bytes handed over"""
+                if density:     # set_state_diabatic + run in one call (nqcb200_run_from_host)
+                    h.run_from_host(r_h, v_h, rho_h, None, None, None, diabatic=True, nsteps=wl.nsteps)
+                    return r_h.nbytes + v_h.nbytes + rho_h.nbytes
+                nbytes = upload(h, r_h, v_h, psi_h)
+                h.run(wl.nsteps)
+                return nbytes
+            h2d = job(eng2)                                                     # warm-up job
+            self.barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                job(eng2)
+                self.allreduce_observables(eng2)
+                out = eng2.observable_sum(first_obs)
+                d2h = out.nbytes
+            e2e_s = time.perf_counter() - t0
+            self.barrier()
+            (e2e_s,) = self.max_over_ranks(e2e_s)
+            e2e = {"value": float(T) * world * wl.nsteps * e2e_steps / e2e_s, "unit": "trajectory-steps/s",
+                   "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
+                   "h2d_GBps_per_rank": h2d * e2e_steps / e2e_s / 1e9,
+                   "path": ("nqcb200_run_from_host (pinned host r, v: chunked cudaMemcpyAsync on a copy stream under the "
+                            "previous chunk's kernels where the kernel family supports it; rho uploaded)" if density
+                            else "nqcb200_set_state (pinned host r, v, psi) -> nqcb200_run") + " -> nqcb200_get_observable_sum"}
+            eng2.close()
+        else:
+            eng.close()
+
+        per_launch_units = float(T) * wl.nsteps * K          # trajectory-steps behind kernel_ms_total (this rank)
+        kernel_s = max(kernel_ms * 1e-3, 1e-12)
+        alg_tf = flops_alg * per_launch_units / kernel_s / 1e12
+        roof = {"bound": "fp64", "peak": self.peak, "unit": "TFLOP/s",
+                "peak_source": "DFMA microbenchmark measured in this run (nqcb200_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
+                "algorithmic_achieved": alg_tf, "algorithmic_frac": alg_tf / self.peak if self.peak else None,
+                "flops_per_trajectory_step_algorithmic": flops_alg,
+                "note": "achieved / frac = FP64 flops the kernels EXECUTE (ncu instruction mix of the committed capture x the live "
+                        "rate) over the measured DFMA peak; algorithmic_* = the reference's dense complex formulation (SURVEY.md "
+                        "8d), which the kernels do not execute (Hermitian / antisymmetric / model structure), see DESIGN.md" + flops_note}
+        if executed is not None:
+            ex_tf = executed[0] * per_launch_units / kernel_s / 1e12
+            roof.update({"achieved": ex_tf, "frac": ex_tf / self.peak if self.peak else None,
+                         "flops_per_trajectory_step_executed": executed[0], "executed_source": executed[1]})
+        else:
+            roof.update({"achieved": None, "frac": None, "executed_source": "no instruction-mix capture committed for this workload"})
+        if wl.name in NCU_DRAM_BYTES_PER_TRAJ_STEP:
+            b, src = NCU_DRAM_BYTES_PER_TRAJ_STEP[wl.name]
+            roof.update({"traffic": b * float(T) * wl.nsteps, "traffic_source": f"{src}: DRAM read + write bytes per trajectory-step "
+                         f"of that capture x {T} trajectories x {wl.nsteps} steps (bytes per job)"})
+        else:
+            roof["traffic"] = None
+        return {"value": value, "ms_per_step": 1e3 * wall / K, "e2e": e2e, "gpu_launches": int(launches_all),
+                "gpu_step_kernel_launches": int(launches), "clocks": clocks, "roofline": roof, "counters": counters,
+                "kernel_ms_total": kernel_ms, "wall_s_timed_region": wall, "batch_prepare_ms": 1e3 * prep / K,
+                "observable_checksum": obs_check, "config": workload_config(wl, T, world, resample, A)}
+
+
+# short legs of the other BASELINE configs appended to the headline line (trajectories per GPU, steps, warm-up)
+OTHER_CONFIGS = [("tully1_fssh", 1 << 21, 2, 1), ("rpmd_harmonic32", 1 << 17, 2, 1), ("rpsh_morse3_16", 113664, 2, 1),
+                 ("iesh_anderson_holstein_m100", 2960, 2, 1)]
+
+
 def main():
     args = parse_args()
     import nqcdynamics_jl_b200 as nq
@@ -205,283 +444,89 @@ def main():
     if args.impl == "reference":
         reference_arm(args, wl)
         return
-
-    from nqcdynamics_jl_b200.engine import Engine
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    dist = None
-    torch = None
-    stdout_fd = None
-    if world > 1:
-        # stdout carries exactly one JSON line: whatever libraries write to fd 1 meanwhile (NCCL prints its
-        # "NCCL version ..." banner there when the communicator is created) is sent to stderr until the line is printed
-        sys.stdout.flush()
-        stdout_fd = os.dup(1)
-        os.dup2(2, 1)
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    lib = A.load_engine_library()
-    if lib.nqcb200_device_count() <= 0:
-        raise SystemExit("bench.py: no CUDA device visible -- the engine has no CPU path")
-
+    B = Bench()
     T = args.trajectories or wl.ntraj_default
     K, W = args.steps, args.warmup
-    density = wl.method in (A.METHOD_FSSH, A.METHOD_EHRENFEST)
-    # one handle.  Every step is the SAME job: where the device-side sampler covers the workload's distribution, each
-    # step re-draws the batch from the resident distribution parameters (nqcb200_sample_state) and runs the config's
-    # full tspan; otherwise (AdiabaticIESH, NRPMD) the trajectories keep running and the save capacity covers all steps.
-    resample = wl.device_spec is not None
-    nsave_total = wl.nsave if resample else (W + K) * wl.nsteps // wl.save_every + 1
-    kw = wl.config_kwargs(T, seed=20261017, device=local_rank, traj_offset=rank * T)
-    kw["nsave"] = nsave_total
-    cfg, keep = A.make_config(**kw)
-    eng = Engine(cfg, keep)
-    rng = np.random.default_rng(1234 + rank)
-    ic = wl.sample(rng, T)
-    rho = wl.initial_density(T) if density else None
+    res = B.measure(wl, T, K, W, 0 if args.no_e2e else K)
 
-    if wl.method == A.METHOD_IESH:
-        ic["psi"], ic["state"] = wl.iesh_ground_state(T)
-
-    def upload(h, r, v, psi=None):
-        return wl.upload(h, {**ic, "r": r, "v": v, "psi": ic.get("psi") if psi is None else psi}, rho)
-
-    upload(eng, ic["r"], ic["v"])
-    peak = __import__("ctypes").c_double()
-    lib.nqcb200_measure_fp64_peak(local_rank, __import__("ctypes").byref(peak))
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-
-    def allreduce_observables(h):
-        if dist is None:
-            return
-        ptr, n = h.observable_sum_device()
-        if n:
-            t = torch.as_tensor(_DevArray(ptr, n), device=f"cuda:{local_rank}")
-            dist.all_reduce(t)
-            torch.cuda.synchronize()
-
-    rho1 = None
-    if resample and density:
-        rho1 = np.zeros((wl.model.nstates, wl.model.nstates))
-        rho1[wl.initial_diabatic_state, wl.initial_diabatic_state] = 1.0
-
-    def fresh_batch():
-        if resample:
-            eng.sample_state(wl.device_spec[0], wl.device_spec[1], rho1, diabatic=True, state=0, normal_modes=wl.device_spec[2])
-
-    for _ in range(W):
-        fresh_batch()
-        eng.run(wl.nsteps)
-    allreduce_observables(eng)
-    barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    kernel_ms, launches = 0.0, 0
-    launches_before = eng.launch_count()
-    wall, prep = 0.0, 0.0
-    for k in range(K):
-        # the step's inputs are made resident first (untimed, reported as batch_prepare_ms): a fresh batch drawn on the
-        # device from the distribution parameters, gauge reference, t0 eigenproblem / save point 0
-        tp = time.perf_counter()
-        fresh_batch()
-        prep += time.perf_counter() - tp
-        # timed region of one step: barrier + (blocking) run [+ the job's only exchange after the last step] ; the engine
-        # synchronises its stream before returning, and times its kernels with CUDA events on that stream
-        barrier()
-        t0 = time.perf_counter()
-        eng.run(wl.nsteps)
-        if k == K - 1:
-            allreduce_observables(eng)          # one all-reduce of the accumulators
-        wall += time.perf_counter() - t0
-        ms, nl = eng.last_run_timing()
-        kernel_ms += ms; launches += nl
-    launches_all = eng.launch_count() - launches_before      # sampling / init / step / fold kernels of the K steps
-    clocks = sampler.stop()
-    barrier()
-    # value: the K timed regions (host clock around blocking, stream-synchronised calls), max over ranks; the CUDA-event
-    # kernel time of the same launches feeds the roofline
-    dev_s = kernel_ms * 1e-3
-    if dist is not None:
-        tt = torch.tensor([dev_s, wall], device=f"cuda:{local_rank}", dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dev_s, wall = float(tt[0]), float(tt[1])
-    region_s = wall
-    units = float(T) * world * wl.nsteps * K
-    value = units / region_s
-    counters = eng.counters()
-    flops_step = wl.flops_per_traj_step
-    flops_note = ""
-    if wl.method == A.METHOD_IESH:
-        counters.update(eng.iesh_stats())
-        frac = counters["hop_searches"] / max(1, counters["steps"])
-        extra = workloads.iesh_hop_search_flops(wl.model.nstates, wl.model.nelectrons)
-        flops_step = wl.flops_per_traj_step + frac * extra
-        flops_note = (f"; IESH: base step {wl.flops_per_traj_step:.4g} flops + unpruned hop search {extra:.4g} flops on "
-                      f"{frac:.4f} of the steps (measured), both counted in the reference's formulation")
-    obs_check = float(np.sum(eng.observable_sum(A.OBS_POPCORR_DIABATIC)[0])) if (wl.observables >> A.OBS_POPCORR_DIABATIC) & 1 else None
-
-    # ---- end-to-end through the C ABI with host buffers -------------------------------------------
-    e2e = None
-    if not args.no_e2e:
-        try:
-            import torch as _t
-            pin = lambda a: _t.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
-        except Exception:
-            pin = np.ascontiguousarray
-        kw2 = wl.config_kwargs(T, seed=7, device=local_rank, traj_offset=rank * T)
-        cfg2, keep2 = A.make_config(**kw2)
-        eng.close()
-        eng2 = Engine(cfg2, keep2)
-        r_h, v_h = pin(ic["r"]), pin(ic["v"])
-        rho_h = pin(rho) if rho is not None else None
-        psi_h = pin(ic["psi"]) if "psi" in ic else None
-        first_obs = next(o for o in range(A.OBS_COUNT) if (wl.observables >> o) & 1)
-        d2h = 0
-        ke = max(1, min(K, 3))
-        def job(h):
-            """one ensemble batch through the public C-ABI calls with HOST buffers; returns the bytes handed over"""
-            if density:     # set_state_diabatic + run in one call; the SpinBoson kernels read pinned r, v in place
-                h.run_from_host(r_h, v_h, rho_h, None, None, None, diabatic=True, nsteps=wl.nsteps)
-                return r_h.nbytes + v_h.nbytes + rho_h.nbytes
-            nbytes = upload(h, r_h, v_h, psi_h)
-            h.run(wl.nsteps)
-            return nbytes
-        h2d = job(eng2)                                                     # warm-up job
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(ke):
-            job(eng2)
-            allreduce_observables(eng2)
-            out = eng2.observable_sum(first_obs)
-            d2h = out.nbytes
-        e2e_s = time.perf_counter() - t0
-        barrier()
-        if dist is not None:
-            tt = torch.tensor([e2e_s], device=f"cuda:{local_rank}", dtype=torch.float64)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            e2e_s = float(tt[0])
-        e2e = {"value": float(T) * world * wl.nsteps * ke / e2e_s, "unit": "trajectory-steps/s",
-               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": ke,
-               "path": ("nqcb200_run_from_host (pinned host r, v read in place by the step kernel; rho uploaded)" if density else "nqcb200_set_state (pinned host r, v, psi) -> nqcb200_run") + " -> nqcb200_get_observable_sum"}
-        # informational: the same job with DEVICE-side initial conditions (nqcb200_sample_state: only the
-        # distribution parameters cross PCIe) -- not the contract's e2e, which keeps host buffers
-        if wl.device_spec is not None:
-            rs, vs, nm = wl.device_spec
-            rho1 = None
-            if density:
-                rho1 = np.zeros((wl.model.nstates, wl.model.nstates))
-                rho1[wl.initial_diabatic_state, wl.initial_diabatic_state] = 1.0
-            def job_dev(h):
-                h.sample_state(rs, vs, rho1, diabatic=True, state=0, normal_modes=nm)
-                h.run(wl.nsteps)
-            job_dev(eng2)
-            barrier()
-            t0 = time.perf_counter()
-            for _ in range(ke):
-                job_dev(eng2)
-                allreduce_observables(eng2)
-                eng2.observable_sum(first_obs)
-            dev_s2 = time.perf_counter() - t0
-            barrier()
-            e2e["device_sampled_ic"] = {"value": float(T) * world * wl.nsteps * ke / dev_s2, "unit": "trajectory-steps/s",
-                                        "path": "nqcb200_sample_state -> nqcb200_run -> nqcb200_get_observable_sum (max over ranks not taken)"}
-        eng2.close()
+    other = None
+    if not args.no_other_configs and args.workload == DEFAULT_WORKLOAD:
+        # the north_star's other targets (C1 >= 1e9 on 8 GPUs, C4 as a fraction of the FP64 peak, C3, C5), measured by the
+        # same code in the same run so that the driver sees them: short legs, no e2e / clocks
+        other = {}
+        for name, To, Ko, Wo in OTHER_CONFIGS:
+            try:
+                r = B.measure(workloads.get(name), To, Ko, Wo, 0, sample_clocks=False)
+                other[name] = {"value": r["value"], "unit": "trajectory-steps/s", "ms_per_step": r["ms_per_step"],
+                               "trajectories_per_gpu": To, "steps": Ko, "warmup": Wo,
+                               "roofline": {k: r["roofline"].get(k) for k in ("achieved", "frac", "algorithmic_frac", "peak",
+                                                                                 "flops_per_trajectory_step_executed", "executed_source")},
+                               "counters": r["counters"]}
+            except Exception as exc:      # a leg must never take the headline down
+                other[name] = {"error": str(exc)[:200]}
 
     # ---- output-streaming path: per-trajectory observables written at every save point, transposed to the
     # reference's trajectory-major layout at HBM speed and copied to pinned host memory ---------------------
     stream = None
-    if args.stream and rank == 0:
-        import torch as _t
-        obs_ids = [o for o in range(A.OBS_COUNT) if (wl.observables >> o) & 1]
-        probe = Engine(*A.make_config(**wl.config_kwargs(1, device=local_rank)))
-        widths = {o: probe.observable_width(o) for o in obs_ids}
-        probe.close()
-        per_traj_bytes = 8 * wl.nsave * sum(widths.values())
-        Ts = int(max(1024, min(T, (6 << 30) // max(1, per_traj_bytes))))        # <= 6 GiB of output
-        kw3 = wl.config_kwargs(Ts, seed=11, device=local_rank, per_trajectory=1)
-        es = Engine(*A.make_config(**kw3))
-        ics = {k: v[:Ts] for k, v in ic.items()} if Ts <= T else wl.sample(rng, Ts)
-        wl.upload(es, ics, rho[:Ts] if rho is not None else None)
-        es.run(wl.nsteps)
-        ms_stream, _ = es.last_run_timing()
-        tr_ms = cp_ms = 0.0
-        nbytes = 0
-        for o in obs_ids:
-            buf = _t.empty((Ts, wl.nsave, widths[o]), dtype=_t.float64).pin_memory().numpy()
-            es.observable_per_trajectory(o, out=buf)
-            tm = es.last_download_timing()
-            tr_ms += tm["transpose_ms"]; cp_ms += tm["copy_ms"]; nbytes += tm["bytes"]
-        es.close()
-        hbm_peak = None
-        try:
-            hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
-        except Exception:
-            pass
-        tr_gbs = 2.0 * nbytes / (tr_ms * 1e-3) / 1e9 if tr_ms > 0 else None      # read + write
-        stream = {"trajectories": Ts, "output_bytes": nbytes,
-                  "step_kernel_traj_steps_per_s": float(Ts) * wl.nsteps / (ms_stream * 1e-3),
-                  "transpose": {"ms": tr_ms, "GB/s": tr_gbs, "hbm_peak_GB/s": hbm_peak,
-                                "frac": (tr_gbs / hbm_peak) if (tr_gbs and hbm_peak) else None,
-                                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if hbm_peak else "unavailable"},
-                  "d2h": {"ms": cp_ms, "GB/s": nbytes / (cp_ms * 1e-3) / 1e9 if cp_ms > 0 else None}}
+    if args.stream and B.rank == 0:
+        stream = measure_stream(B, wl, T)
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if B.rank == 0 and B.world == 1 and not args.no_cpu_baseline:
         _, cpu, _, _ = run_cpu_oracle(wl, args.cpu_seconds)
 
-    if rank == 0:
-        per_launch_units = float(T) * wl.nsteps            # one run() = one launch (<= 65536 steps)
-        kernel_s_per_launch = (kernel_ms * 1e-3) / max(1, launches)
-        achieved = flops_step * per_launch_units / kernel_s_per_launch / 1e12
-        line = {
-            "metric": "trajectory-steps/sec (FP64)", "value": value, "unit": "trajectory-steps/s", "n_gpus": world,
-            "steps": K, "warmup": W, "ms_per_step": 1e3 * region_s / K, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": wl.name, "description": wl.description, "trajectories_per_gpu": T,
-                       "nuclear_steps_per_step": wl.nsteps, "save_every": wl.save_every,
-                       "batch": ("every step re-draws the batch on the device (nqcb200_sample_state) and runs the full tspan"
-                                 if resample else "trajectories continue across steps"),
-                       "observables_on_device": [o for o in range(A.OBS_COUNT) if (wl.observables >> o) & 1],
-                       "l2": "trajectory state larger than L2" if T * 8 * 3 * len(wl.masses) * wl.nbeads > 126e6
-                             else "state register-resident for the whole launch; no reuse of cached inputs between steps",
-                       "parallelism": f"trajectories sharded over {world} GPU(s), one NCCL all-reduce of observables"},
-            "e2e": e2e,
-            "gpu_launches": int(launches_all), "gpu_step_kernel_launches": int(launches),
-            "clocks": clocks,
-            "roofline": {"bound": "fp64", "achieved": achieved, "peak": float(peak.value), "unit": "TFLOP/s",
-                         "frac": achieved / float(peak.value) if peak.value else None,
-                         "traffic": (NCU_DRAM_BYTES_PER_TRAJ[wl.name][0] * T if wl.name in NCU_DRAM_BYTES_PER_TRAJ else None),
-                         "traffic_source": (f"profiles/r01/prof_r01_{NCU_DRAM_BYTES_PER_TRAJ[wl.name][1]}_raw.csv: DRAM read + write "
-                                            f"bytes per trajectory of that capture x {T} trajectories (bytes per launch)"
-                                            if wl.name in NCU_DRAM_BYTES_PER_TRAJ else None),
-                         "flops_per_trajectory_step_algorithmic": flops_step,
-                         "executed": ({"flops_per_trajectory_step": NCU_EXECUTED_FLOPS_PER_TRAJ_STEP[wl.name][0],
-                                       "achieved": NCU_EXECUTED_FLOPS_PER_TRAJ_STEP[wl.name][0] * per_launch_units / kernel_s_per_launch / 1e12,
-                                       "frac": (NCU_EXECUTED_FLOPS_PER_TRAJ_STEP[wl.name][0] * per_launch_units / kernel_s_per_launch / 1e12
-                                                / float(peak.value)) if peak.value else None,
-                                       "source": f"profiles/r01/instmix_r01_{NCU_EXECUTED_FLOPS_PER_TRAJ_STEP[wl.name][1]}.csv"}
-                                      if wl.name in NCU_EXECUTED_FLOPS_PER_TRAJ_STEP else None),
-                         "peak_source": "DFMA microbenchmark measured in this run (nqcb200_measure_fp64_peak); "
-                                        "MEASURED_PEAKS.json has no FP64 entry",
-                         "note": "algorithmic = the reference's dense complex formulation (SURVEY.md 8d); the kernel "
-                                 "executes fewer flops (Hermitian/antisymmetric structure), see DESIGN.md" + flops_note},
-            "cpu_baseline": cpu, "stream": stream,
-            "counters": counters, "kernel_ms_total": kernel_ms, "wall_s_timed_region": wall,
-            "batch_prepare_ms": 1e3 * prep / K,
-            "observable_checksum": obs_check,
-        }
-        if stdout_fd is not None:
+    if B.rank == 0:
+        line = {"metric": "trajectory-steps/sec (FP64)", "value": res["value"], "unit": "trajectory-steps/s", "n_gpus": B.world,
+                "steps": K, "warmup": W, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": res["config"], "e2e": res["e2e"],
+                "gpu_launches": res["gpu_launches"], "gpu_step_kernel_launches": res["gpu_step_kernel_launches"],
+                "clocks": res["clocks"], "roofline": res["roofline"], "cpu_baseline": cpu, "stream": stream,
+                "counters": res["counters"], "kernel_ms_total": res["kernel_ms_total"],
+                "wall_s_timed_region": res["wall_s_timed_region"], "batch_prepare_ms": res["batch_prepare_ms"],
+                "observable_checksum": res["observable_checksum"], "other_configs": other}
+        if B.stdout_fd is not None:
             sys.stdout.flush()
-            os.dup2(stdout_fd, 1)
+            os.dup2(B.stdout_fd, 1)
         print(json.dumps(line), flush=True)
-    if dist is not None:
-        dist.destroy_process_group()
+    if B.dist is not None:
+        B.dist.destroy_process_group()
+
+
+def measure_stream(B, wl, T):
+    import torch as _t
+    A, Engine = B.A, __import__("nqcdynamics_jl_b200.engine", fromlist=["Engine"]).Engine
+    obs_ids = [o for o in range(A.OBS_COUNT) if (wl.observables >> o) & 1]
+    probe = Engine(*A.make_config(**wl.config_kwargs(1, device=B.local_rank)))
+    widths = {o: probe.observable_width(o) for o in obs_ids}
+    probe.close()
+    per_traj_bytes = 8 * wl.nsave * sum(widths.values())
+    Ts = int(max(1024, min(T, (6 << 30) // max(1, per_traj_bytes))))        # <= 6 GiB of output
+    kw3 = wl.config_kwargs(Ts, seed=11, device=B.local_rank, per_trajectory=1)
+    es = Engine(*A.make_config(**kw3))
+    ics = wl.sample(np.random.default_rng(99), Ts)
+    wl.upload(es, ics, wl.initial_density(Ts) if wl.method in (A.METHOD_FSSH, A.METHOD_EHRENFEST) else None)
+    es.run(wl.nsteps)
+    ms_stream, _ = es.last_run_timing()
+    tr_ms = cp_ms = 0.0
+    nbytes = 0
+    for o in obs_ids:
+        buf = _t.empty((Ts, wl.nsave, widths[o]), dtype=_t.float64).pin_memory().numpy()
+        es.observable_per_trajectory(o, out=buf)
+        tm = es.last_download_timing()
+        tr_ms += tm["transpose_ms"]; cp_ms += tm["copy_ms"]; nbytes += tm["bytes"]
+    es.close()
+    hbm_peak = None
+    try:
+        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        pass
+    tr_gbs = 2.0 * nbytes / (tr_ms * 1e-3) / 1e9 if tr_ms > 0 else None      # read + write
+    return {"trajectories": Ts, "output_bytes": nbytes,
+            "step_kernel_traj_steps_per_s": float(Ts) * wl.nsteps / (ms_stream * 1e-3),
+            "transpose": {"ms": tr_ms, "GB/s": tr_gbs, "hbm_peak_GB/s": hbm_peak,
+                          "frac": (tr_gbs / hbm_peak) if (tr_gbs and hbm_peak) else None,
+                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if hbm_peak else "unavailable"},
+            "d2h": {"ms": cp_ms, "GB/s": nbytes / (cp_ms * 1e-3) / 1e9 if cp_ms > 0 else None}}
 
 
 if __name__ == "__main__":
