@@ -50,6 +50,18 @@ NQ_D void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
 NQ_D void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
+// 1/x to within one ulp: hardware seed (rcp.approx.ftz.f64, ~20 bits) and two Newton steps.  Used where the quotient
+// feeds an iteration or a 1e-10-tolerance quantity (secular sums, v.d); an IEEE division costs about twice as much
+// and the root finder / propagator are insensitive to the last bit.  |x| must be a normal number.
+NQ_D double iesh_rcp(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
+
 // block-wide sum / max, result broadcast to every thread (red: >= 34 doubles of shared memory)
 NQ_D double iesh_block_sum(double x, double* red) {
 #pragma unroll
@@ -104,7 +116,7 @@ NQ_D void iesh_secular(const double* eps, const double* V2, int M, int p, double
 #pragma unroll 4
     for (int k = sub; k < M; k += lr) {
         const double d = (eps[k] - ep) - mu;
-        const double inv = 1.0 / d;
+        const double inv = iesh_rcp(d);
         const double t = V2[k] * inv;
         const double u = t * inv;
         s1 += t;
@@ -267,9 +279,9 @@ NQ_D void iesh_emit(const KParams& p, int64_t traj, int isave, int obs_id, int k
 }
 
 // Estimators at a save point (iesh.jl:337-388).  Every thread of the CTA must call it.
-// zt: 16 * n doubles of scratch shared memory (the psi-chunk region is free at a save point)
-NQ_D void iesh_record_save(const KParams& p, IeshSmem& S, int64_t traj, int isave, double r, double v,
-                           const IeshModel& mdl, const double* psi_re, const double* psi_im, double* zt) {
+// zt: zt_cap doubles of scratch shared memory (the psi-chunk region is free at a save point), >= (warps + 9) * roundup(n, 4)
+__device__ __noinline__ void iesh_record_save(const KParams& p, IeshSmem& S, int64_t traj, int isave, double r, double v,
+                           const IeshModel& mdl, const double* psi_re, const double* psi_im, double* zt, int zt_cap) {
     const uint32_t obs = p.observables;
     const int n = p.n, ne = p.ne, tid = threadIdx.x, nt = blockDim.x;
     const bool last = (isave == p.nsave - 1);
@@ -293,30 +305,74 @@ NQ_D void iesh_record_save(const KParams& p, IeshSmem& S, int64_t traj, int isav
     }
     if (obs & ((1u << NQCB200_OBS_DIABATIC_POP) | (1u << NQCB200_OBS_SCATTERING_DIABATIC))) {
         // pop_i = sum_e [ (sum_a Z_ia x_ae)^2 - sum_a Z_ia^2 x_ae^2 + Z_{i,occ_e}^2 ],  x = Re psi  (iesh.jl:337-369)
-        // 16 diabatic rows of Z at a time are staged in shared memory (one division per Z entry per save point).
-        constexpr int TI = 16;
+        // One warp per diabatic row i: the lanes hold Z[i, a] for a = lane, lane + 32, ... (one division each), the row
+        // also sits in the warp's scratch row for Z[i, occ_e]; x[., e] is read coalesced; two warp sums per (i, e).
+        //   second term: sum_e sum_a Z_ia^2 x_ae^2 = sum_a Z_ia^2 s_a with s_a = sum_e x_ae^2 (O(n^2) instead of O(n^2 ne))
+        constexpr int QA = 8;                                   // n <= 256 states
+        constexpr int EB = 8;                                   // electrons per inner iteration (independent reduction chains)
+        const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+        const int n4 = (n + 3) & ~3;
+        double* zrow = zt + (size_t)warp * n4;
+        double* sa = zt + (size_t)nwarps * n4;                  // s_a
+        double* xs = sa + n4;                                   // Re psi of a chunk of electrons, [e][n4]
+        const int ecap = max(EB, ((zt_cap - (nwarps + 1) * n4) / n4) & ~(EB - 1));
         __syncthreads();
-        for (int i = tid; i < n; i += nt) S.pop[i] = 0.0;
-        for (int i0 = 0; i0 < n; i0 += TI) {
+        for (int i = tid; i < n; i += nt) {
+            S.pop[i] = 0.0;
+            double sq = 0.0;
+            for (int e = 0; e < ne; ++e) { const double x = psi_re[(int64_t)n * e + i]; sq = fma(x, x, sq); }
+            sa[i] = sq;
+        }
+        for (int ec0 = 0; ec0 < ne; ec0 += ecap) {
+            const int ecn = min(ecap, ne - ec0);
             __syncthreads();
-            for (int idx = tid; idx < TI * n; idx += nt) {
-                const int ii = idx / n, a = idx % n;
-                zt[idx] = (i0 + ii < n) ? iesh_Z(S, i0 + ii, a) : 0.0;
+            for (int idx = tid; idx < ecn * n; idx += nt) {
+                const int e = idx / n, a = idx - e * n;
+                xs[e * n4 + a] = psi_re[(int64_t)n * (ec0 + e) + a];
             }
             __syncthreads();
-            for (int idx = tid; idx < TI * ne; idx += nt) {
-                const int ii = idx % TI, e = idx / TI;
-                if (i0 + ii >= n) continue;
-                const double* zr = zt + ii * n;
-                const double* x = psi_re + (int64_t)n * e;
-                double y = 0.0, q = 0.0;
-#pragma unroll 4
-                for (int a = 0; a < n; ++a) {
-                    const double zx = zr[a] * x[a];
-                    y += zx; q = fma(zx, zx, q);
+            for (int i = warp; i < n; i += nwarps) {
+                double zr[QA];
+                double acc = 0.0;
+#pragma unroll
+                for (int qa = 0; qa < QA; ++qa) {
+                    const int a = lane + 32 * qa;
+                    zr[qa] = (a < n) ? iesh_Z(S, i, a) : 0.0;
+                    if (a < n) {
+                        zrow[a] = zr[qa];
+                        if (ec0 == 0) acc = fma(-zr[qa] * zr[qa], sa[a], acc);
+                    }
                 }
-                const double zo = zr[S.occ[e]];
-                atomicAdd(&S.pop[i0 + ii], y * y - q + zo * zo);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                for (int eb = 0; eb < ecn; eb += EB) {
+                    double y[EB];
+#pragma unroll
+                    for (int k = 0; k < EB; ++k) y[k] = 0.0;
+#pragma unroll
+                    for (int qa = 0; qa < QA; ++qa) {
+                        const int a = lane + 32 * qa;
+                        if (a < n) {
+#pragma unroll
+                            for (int k = 0; k < EB; ++k)
+                                if (eb + k < ecn) y[k] = fma(zr[qa], xs[(eb + k) * n4 + a], y[k]);
+                        }
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                        for (int k = 0; k < EB; ++k) y[k] += __shfl_xor_sync(0xffffffffu, y[k], o);
+                    }
+#pragma unroll
+                    for (int k = 0; k < EB; ++k) {
+                        if (eb + k < ecn) {
+                            const double zo = zrow[S.occ[ec0 + eb + k]];
+                            acc += y[k] * y[k] + zo * zo;
+                        }
+                    }
+                }
+                if (lane == 0) S.pop[i] += acc;
+                __syncwarp();
             }
         }
         __syncthreads();
@@ -423,21 +479,31 @@ __device__ __noinline__ double iesh_propagate(const KParams& p, const IeshSmem& 
             double q[R > 0 ? R : 1][NT][2], qx[NX][2];       // psi0 = e^{-i sigma dts} psi of the same elements
             double wr[R > 0 ? R : 1], wx[NX];                // w_i - sigma of the owned rows
             // f(row i, electron e, column tile t, y.re, y.im, psi0.re, psi0.im, ws) on every element pair this thread owns
+            // which of its element pairs this thread really owns (inside the matrix, inside the chunk): one bit each,
+            // evaluated once per chunk instead of three compares per element per stage
+            unsigned own[R > 0 ? R : 1], ownx = 0u;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                own[r] = 0u;
+                const int i = 8 * (warp + r * nwarps) + lq;
+#pragma unroll
+                for (int t = 0; t < NT; ++t)
+                    if (t < nt_act && i < n && e0 + 4 * t + lr4 < e1) own[r] |= 1u << t;
+            }
+#pragma unroll
+            for (int x = 0; x < NX; ++x)
+                if (xok[x] && 8 * xrow[x] + lq < n && e0 + 4 * xcol[x] + lr4 < e1) ownx |= 1u << x;
             auto for_own = [&](auto&& f) {
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     const int i = 8 * (warp + r * nwarps) + lq;
 #pragma unroll
-                    for (int t = 0; t < NT; ++t) {
-                        const int e = e0 + 4 * t + lr4;
-                        if (t < nt_act && i < n && e < e1) f(i, e, t, c[r][t][0], c[r][t][1], q[r][t][0], q[r][t][1], wr[r]);
-                    }
+                    for (int t = 0; t < NT; ++t)
+                        if ((own[r] >> t) & 1u) f(i, e0 + 4 * t + lr4, t, c[r][t][0], c[r][t][1], q[r][t][0], q[r][t][1], wr[r]);
                 }
 #pragma unroll
-                for (int x = 0; x < NX; ++x) {
-                    const int i = 8 * xrow[x] + lq, e = e0 + 4 * xcol[x] + lr4;
-                    if (xok[x] && i < n && e < e1) f(i, e, xcol[x], cx[x][0], cx[x][1], qx[x][0], qx[x][1], wx[x]);
-                }
+                for (int x = 0; x < NX; ++x)
+                    if ((ownx >> x) & 1u) f(8 * xrow[x] + lq, e0 + 4 * xcol[x] + lr4, xcol[x], cx[x][0], cx[x][1], qx[x][0], qx[x][1], wx[x]);
             };
             // accumulators <- psi0 + ck (ws Y, -ws X) of the current y
             auto diag_stage = [&](double ck) {
@@ -745,7 +811,7 @@ __global__ void __launch_bounds__(384, 1) iesh_step_kernel(const __grid_constant
                     for (int i = lane; i < n; i += 32) {
                         double g = 0.0;
                         if (i != j) {
-                            g = zj * S.z0[i] / ((S.eps[S.pole[i]] - ej) + (S.mu[i] - mj));
+                            g = zj * S.z0[i] * iesh_rcp((S.eps[S.pole[i]] - ej) + (S.mu[i] - mj));
                             if (occ_j && S.flag[i] < 0) sabs += fabs(g);         // |v_dot_d[m, e]|, iesh.jl:285-298
                         }
                         g2 = fma(g, g, g2);
@@ -987,7 +1053,7 @@ __global__ void __launch_bounds__(384, 1) iesh_step_kernel(const __grid_constant
             // ---- save (after the callback) ---------------------------------------------
             if ((step + 1) % p.save_every == 0) {
                 const int64_t isave = (step + 1) / p.save_every;
-                if (isave < p.nsave) iesh_record_save(p, S, traj, (int)isave, r, v, mdl, psi_re, psi_im, Bs);
+                if (isave < p.nsave) iesh_record_save(p, S, traj, (int)isave, r, v, mdl, psi_re, psi_im, Bs, L.work_doubles - L.off_b);
             }
         }
         __syncthreads();
@@ -1058,7 +1124,7 @@ __global__ void __launch_bounds__(384, 1) iesh_init_kernel(const __grid_constant
             occsum = iesh_block_sum(part, S.red);
         }
         if (tid == 0) p.acc[traj] = (-du0 - dh * occsum) / mdl.mass;
-        iesh_record_save(p, S, traj, 0, r, v, mdl, psi_re, psi_im, S.work + p.iesh.off_b);
+        iesh_record_save(p, S, traj, 0, r, v, mdl, psi_re, psi_im, S.work + p.iesh.off_b, p.iesh.work_doubles - p.iesh.off_b);
         {
             // are the orbitals orthonormal?  (enables the determinant-free pruning bound of the step kernel)
             double dev = 0.0;
