@@ -290,11 +290,11 @@ class Bench:
         rng = np.random.default_rng(1234 + rank)
         ic = wl.sample(rng, T)
         rho = wl.initial_density(T) if density else None
-        if wl.method == A.METHOD_IESH:
-            ic["psi"], ic["state"] = wl.iesh_ground_state(T)
+        if wl.method == A.METHOD_IESH:      # ground-state orbitals: psi is built on the device from the occupations
+            ic["state"] = wl.iesh_ground_state(T)[1]
 
         def upload(h, r, v, psi=None):
-            return wl.upload(h, {**ic, "r": r, "v": v, "psi": ic.get("psi") if psi is None else psi}, rho)
+            return wl.upload(h, {**ic, "r": r, "v": v}, rho)
 
         upload(eng, ic["r"], ic["v"])
         rho1 = None
@@ -369,7 +369,6 @@ class Bench:
             eng2 = Engine(cfg2, keep2)
             r_h, v_h = self.pin(ic["r"]), self.pin(ic["v"])
             rho_h = self.pin(rho) if rho is not None else None
-            psi_h = self.pin(ic["psi"]) if "psi" in ic else None
             first_obs = next(o for o in range(A.OBS_COUNT) if (wl.observables >> o) & 1)
             d2h = 0
 
@@ -378,7 +377,7 @@ class Bench:
                 if density:     # set_state_diabatic + run in one call (nqcb200_run_from_host)
                     h.run_from_host(r_h, v_h, rho_h, None, None, None, diabatic=True, nsteps=wl.nsteps)
                     return r_h.nbytes + v_h.nbytes + rho_h.nbytes
-                nbytes = upload(h, r_h, v_h, psi_h)
+                nbytes = upload(h, r_h, v_h)
                 h.run(wl.nsteps)
                 return nbytes
             h2d = job(eng2)                                                     # warm-up job

@@ -225,7 +225,10 @@ int nqcb200_observable_width(const nqcb200_handle* h, int obs_id);
  * electronic_dynamics.jl:118-127), eigenvector gauge reference, step counter = 0, observable
  * accumulators = 0, save point 0 recorded.
  *   sig_re/sig_im: density matrix (FSSH/Ehrenfest, n*n per trajectory) or psi (IESH, n*ne);
- *                  NULL for CLASSICAL/NRPMD.
+ *                  NULL for CLASSICAL/NRPMD.  AdiabaticIESH / EhrenfestNA with sig_re == NULL: electron e starts in the
+ *                  adiabatic orbital state[e] (psi[state[e], e] = 1; state == NULL: orbitals 1..ne), which is what
+ *                  DynamicsVariables(sim, v, r) and DynamicsVariables(sim, v, r, FermiDiracState{Adiabatic}) build
+ *                  (iesh.jl:89-128) -- psi is then filled on the device and only the occupations are uploaded.
  *   state: 1-based active state (FSSH: 1 per trajectory; IESH: ne sorted occupied states);
  *          NULL for methods without a discrete state.
  * Replaces: prob_func/sample_distribution output -> integrator init

@@ -17,7 +17,7 @@ from .api import (Atoms, FSSH, Ehrenfest, EhrenfestNA, ThermalLangevin, Classica
                   OutputFinalKineticEnergy, OutputFirstPosition, OutputFirstVelocity, OutputFinalPosition,
                   OutputFinalVelocity, OutputTotalDiabaticPopulation, OutputTotalAdiabaticPopulation, OutputSpringEnergy,
                   OutputCentroidKineticEnergy, OutputFinalTime, OutputDynamicsVariables, OutputInitial, OutputFinal,
-                  PopulationCorrelationFunction, SortByTrajectoryReduction, SortByOutputReduction, SumReduction,
+                  PopulationCorrelationFunction, SortByTrajectoryReduction, SortByOutputReduction, SumReduction, FileReduction,
                   MeanReduction, EnsembleB200, run_dynamics, TerminatingCallback, PositionOutside,
                   OutputSubsetKineticEnergy, OutputFinalSubsetKineticEnergy, OutputKineticTemperature,
                   OutputMappingPosition, OutputMappingMomentum, OutputOccupations)

@@ -167,7 +167,7 @@ class CHandle:
         self.n, self.D, self.B, self.ne = cfg.nstates, cfg.ndofs, cfg.nbeads, cfg.nelectrons
         self.T = int(cfg.ntraj)
         self.nsig = self.n * (self.ne if cfg.method in IESH_FAMILY else self.n)
-        self.nstate = self.ne if cfg.method == METHOD_IESH else 1
+        self.nstate = self.ne if cfg.method in IESH_FAMILY else 1
 
     # -- plumbing ------------------------------------------------------------------------------
     def _call(self, name, *args):

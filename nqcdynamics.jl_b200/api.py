@@ -13,6 +13,7 @@ Every trajectory is stepped on the GPU by ``libnqcb200.so``; there is no CPU pat
 from __future__ import annotations
 
 import math
+import os
 import threading
 from dataclasses import dataclass, field
 from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple, Union
@@ -487,6 +488,88 @@ class MeanReduction:
     pass
 
 
+class _NpzStore:
+    """Group / dataset container with the layout of the reference's HDF5 files, used when h5py is not importable: one
+    ``.npz`` archive whose member names are the HDF5 paths (``trajectory_<i>/<OutputName>``)."""
+
+    def __init__(self, path):
+        self.path, self.members = path, {}
+        if os.path.exists(path):
+            with np.load(path) as old:
+                self.members = {k: old[k] for k in old.files}
+
+    def create_dataset(self, group, name, value):
+        key = f"{group}/{name}"
+        if key in self.members:
+            raise ValueError(f"{key} already exists in {self.path}")      # HDF5 "cw" mode: create_group fails on duplicates
+        self.members[key] = np.asarray(value)
+
+    def close(self):
+        with open(self.path, "wb") as f:          # a file object keeps numpy from appending another extension
+            np.savez(f, **self.members)
+
+
+class _H5Store:
+    def __init__(self, path, h5py):
+        self.file = h5py.File(path, "a")
+
+    def create_dataset(self, group, name, value):
+        g = self.file.require_group(group)
+        g.create_dataset(name, data=np.asarray(value))
+
+    def close(self):
+        self.file.close()
+
+
+class FileReduction:
+    """``FileReduction(filename)`` (reductions.jl:57-91): every trajectory's outputs go to the group ``trajectory_<id>`` of one
+    file, one dataset per output (``Time`` included); the extension is forced to ``.h5`` unless it is ``.h5`` / ``.hdf5``.
+    Values follow the reference's conversion: numbers and numeric arrays as they are; a vector of arrays is stacked on a
+    NEW LAST axis (``reshape(reduce(hcat, value), size(value[1])..., :)``) -- numpy's leading frame axis is moved to the
+    end so that the on-disk dataset has the reference's shape.  ``run_dynamics`` then returns the reference's message.
+    Backend: h5py when importable (real HDF5); otherwise an ``.npz`` archive with the same group/dataset paths as member
+    names, written next to the requested name (``<name>.h5.npz``) -- the image this package is built in has no HDF5 library."""
+
+    def __init__(self, filename: str):
+        root, ext = os.path.splitext(filename)
+        self.filename = filename if ext in (".h5", ".hdf5") else root + ".h5"
+        try:
+            import h5py                      # noqa: F401
+            self.backend = "h5py"
+        except ImportError:
+            self.backend = "npz"
+        self.target = self.filename if self.backend == "h5py" else self.filename + ".npz"
+
+    def _open(self):
+        if self.backend == "h5py":
+            import h5py
+            return _H5Store(self.target, h5py)
+        return _NpzStore(self.target)
+
+    @staticmethod
+    def _convert(value):
+        if isinstance(value, dict):          # ComponentVector(reflection=..., transmission=...): flat vector, fields in order
+            return np.concatenate([np.ravel(np.asarray(v, dtype=np.float64)) for v in value.values()])
+        if isinstance(value, list):
+            if value and isinstance(value[0], dict):
+                raise TypeError("Cannot convert output type to HDF5 format")      # reductions.jl:82-84
+            value = np.asarray(value)
+        arr = np.asarray(value)
+        if arr.dtype == object:
+            raise TypeError("Cannot convert output type to HDF5 format")
+        return np.moveaxis(arr, 0, -1) if arr.ndim >= 2 else arr      # frames last, as the reference stacks them
+
+    def write(self, trajectories, first_id: int = 1):
+        store = self._open()
+        try:
+            for i, traj in enumerate(trajectories):
+                for key, value in traj.items():
+                    store.create_dataset(f"trajectory_{first_id + i}", str(key), self._convert(value))
+        finally:
+            store.close()
+        return f"Output written to {self.target}."
+
+
 @dataclass
 class EnsembleB200:
     """``ensemble_algorithm=EnsembleB200(ngpus)``: shard trajectories over ``ngpus`` B200s of this node.
@@ -655,7 +738,7 @@ def run_dynamics(sim: Simulation, tspan, distribution, *, output, selection: Opt
             raise ValueError("with a TerminatingCallback the time span must be a whole number of saveat intervals")
         if not 1 <= callback.func.dof <= sim.ndofs_total:
             raise ValueError("PositionOutside.dof out of range")
-    per_traj = isinstance(reduction, (SortByTrajectoryReduction, SortByOutputReduction))
+    per_traj = isinstance(reduction, (SortByTrajectoryReduction, SortByOutputReduction, FileReduction))
     obs_mask = 0
     method_id = sim.method.method_id
     for o in outputs:
@@ -714,9 +797,8 @@ def run_dynamics(sim: Simulation, tspan, distribution, *, output, selection: Opt
                     occ0[t] = electronic.sample_occupations(rng, model.adiabatic_energies(r[t].reshape(-1)), ne)
         else:
             raise TypeError("AdiabaticIESH / EhrenfestNA take no electronic distribution (ground state) or a FermiDiracState")
-        if psi0 is None:
-            psi0 = np.zeros((T, ne, n))
-            psi0[np.arange(T)[:, None], np.arange(ne)[None, :], occ0 - 1] = 1.0
+        # psi0 stays None for the adiabatic cases: electron e starts in orbital occ0[e], built on the device from the
+        # occupations alone (nqcb200_set_state with sig_re == NULL)
 
     qmap0 = pmap0 = None
     if method.method_id == A.METHOD_NRPMD:
@@ -791,7 +873,7 @@ def run_dynamics(sim: Simulation, tspan, distribution, *, output, selection: Opt
                     else:
                         eng.set_state_diabatic(rg, vg, rho)
                 elif iesh:
-                    eng.set_state(rg, vg, psi0[lo:hi], None, None if mean_field else occ0[lo:hi])
+                    eng.set_state(rg, vg, None if psi0 is None else psi0[lo:hi], None, None if (mean_field and psi0 is not None) else occ0[lo:hi])
                 elif method.method_id == A.METHOD_NRPMD:
                     eng.set_state(rg, vg)
                     eng.set_mapping(qmap0[lo:hi], pmap0[lo:hi])
@@ -828,6 +910,8 @@ def run_dynamics(sim: Simulation, tspan, distribution, *, output, selection: Opt
             for o in outputs:
                 d[o.name] = _finalise(sim, o, arrs, True, float(t_end[i]))
             trajs.append(d)
+        if isinstance(reduction, FileReduction):
+            return reduction.write(trajs)
         if isinstance(reduction, SortByOutputReduction):
             keys = list(trajs[0].keys())
             return {k: [tr[k] for tr in trajs] for k in keys}

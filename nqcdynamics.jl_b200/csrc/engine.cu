@@ -79,6 +79,11 @@ __global__ void aos_to_soa_range(const double* __restrict__ in, double* __restri
         if (t < n && c < C) out[(int64_t)c * ldT + lo + t] = tile[threadIdx.x][i];
     }
 }
+// AdiabaticIESH: psi[t][e][state[t][e]] = 1 (trajectory-major psi, 0-based occupations), everything else already zero
+__global__ void iesh_fill_psi(double* __restrict__ psi, const int32_t* __restrict__ state, int64_t cnt, int n, int ne) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // = t * ne + e
+    if (idx < cnt) psi[idx * n + state[idx]] = 1.0;
+}
 template <typename Tin, typename Tout>
 __global__ void soa_to_aos(const Tin* __restrict__ in, Tout* __restrict__ out, int64_t T, int C, Tout add) {
     __shared__ Tout tile[32][33];
@@ -357,7 +362,7 @@ int set_state_impl(nqcb200_handle* h, const double* r, const double* v, const do
     const bool iesh = iesh_family(c.method);
     if (density && !sre) { h->err = "the density matrix is required for FSSH / Ehrenfest"; return NQCB200_ERR_INVALID; }
     const bool mean_field = (c.method == NQCB200_METHOD_EHRENFEST_NA);
-    if (iesh && (!sre || (!state && !mean_field))) { h->err = "AdiabaticIESH needs psi (n x ne) and the occupied states"; return NQCB200_ERR_INVALID; }
+    if (iesh && sre && !state && !mean_field) { h->err = "AdiabaticIESH needs the occupied states next to psi (n x ne)"; return NQCB200_ERR_INVALID; }
     if (iesh && basis != 0) { h->err = "AdiabaticIESH: only adiabatic initial wavefunctions are supported"; return NQCB200_ERR_UNSUPPORTED; }
     NQ_CUDA(h, cudaSetDevice(c.device));
     int rc;
@@ -384,8 +389,9 @@ int set_state_impl(nqcb200_handle* h, const double* r, const double* v, const do
     if (iesh && T > 0) {
         // psi and the occupation vectors stay trajectory-major: one CTA owns one trajectory (kernel_iesh.cuh)
         const size_t bytes = sizeof(double) * (size_t)T * h->nsig;
-        NQ_CUDA(h, cudaMemcpyAsync(h->kp.sig_re, sre, bytes, cudaMemcpyHostToDevice, h->stream));
-        if (sim) NQ_CUDA(h, cudaMemcpyAsync(h->kp.sig_im, sim, bytes, cudaMemcpyHostToDevice, h->stream));
+        if (sre) NQ_CUDA(h, cudaMemcpyAsync(h->kp.sig_re, sre, bytes, cudaMemcpyHostToDevice, h->stream));
+        else NQ_CUDA(h, cudaMemsetAsync(h->kp.sig_re, 0, bytes, h->stream));      // filled from the occupations below
+        if (sim && sre) NQ_CUDA(h, cudaMemcpyAsync(h->kp.sig_im, sim, bytes, cudaMemcpyHostToDevice, h->stream));
         else NQ_CUDA(h, cudaMemsetAsync(h->kp.sig_im, 0, bytes, h->stream));
         const int64_t cnt = T * h->nstate;
         int32_t* stage_i = (int32_t*)h->staging;
@@ -396,6 +402,12 @@ int set_state_impl(nqcb200_handle* h, const double* r, const double* v, const do
             iota_mod_i32<<<(unsigned)((cnt + 255) / 256), 256, 0, h->stream>>>(h->kp.state, cnt, h->nstate);
         }
         ++h->launches_total;
+        if (!sre) {
+            // DynamicsVariables(sim, v, r[, FermiDiracState{Adiabatic}]) (iesh.jl:89-128): electron e starts in the adiabatic
+            // orbital state[e] -- psi[state[e], e] = 1 -- built on the device: only the occupations cross PCIe
+            iesh_fill_psi<<<(unsigned)((cnt + 255) / 256), 256, 0, h->stream>>>(h->kp.sig_re, h->kp.state, cnt, c.nstates, h->nstate);
+            ++h->launches_total;
+        }
         NQ_CUDA(h, cudaGetLastError());
     }
     int sample_state = 0;

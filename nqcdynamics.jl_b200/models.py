@@ -128,6 +128,29 @@ class TrapezoidalRule:
 
 
 @dataclass
+class ShenviGaussLegendre:
+    """Gauss-Legendre discretisation of Shenvi, Roy, Tully (2009) in two halves around the Fermi level
+    (docs/src/NQCModels/systembathmodels.md:236-262): with x_n, w_n the M/2-point Gauss-Legendre knots and weights,
+        eps_n = (eF - a)/2 x_n + (a + eF)/2 , w~_n = (eF - a)/2 w_n     (lower half)
+        eps_n = (b - eF)/2 x_n + (eF + b)/2 , w~_n = (b - eF)/2 w_n     (upper half)
+    and V_n = sqrt(w~_n) V(eps).  The reference's iesh.md:85-105 example uses it for AdiabaticIESH; the engine only ever
+    sees the resulting (eps_k, V_k)."""
+    M: int
+    bandmin: float
+    bandmax: float
+    fermi_level: float = 0.0
+
+    def discretize(self, coupling: float):
+        if self.M % 2:
+            raise ValueError("ShenviGaussLegendre needs an even number of states")
+        x, w = np.polynomial.legendre.leggauss(self.M // 2)
+        a, b, eF = self.bandmin, self.bandmax, self.fermi_level
+        eps = np.concatenate([0.5 * (eF - a) * x + 0.5 * (a + eF), 0.5 * (b - eF) * x + 0.5 * (eF + b)])
+        wt = np.concatenate([0.5 * (eF - a) * w, 0.5 * (b - eF) * w])
+        return eps, np.sqrt(wt) * coupling
+
+
+@dataclass
 class MiaoSubotnik:
     """U0 = 1/2 m w^2 x^2, U1 = 1/2 m w^2 (x-g)^2 + DeltaG, coupling sqrt(Gamma/2pi) (recalled)."""
     Γ: float = 6.4e-3
@@ -137,7 +160,8 @@ class MiaoSubotnik:
     ΔG: float = -3.8e-3
 
 
-def AndersonHolstein(impurity: MiaoSubotnik, bath: TrapezoidalRule, fermi_level: float = 0.0) -> Model:
+def AndersonHolstein(impurity: MiaoSubotnik, bath, fermi_level: float = 0.0) -> Model:
+    """``AndersonHolstein(impurity_model, bath; fermi_level)``: ``bath`` is a TrapezoidalRule or a ShenviGaussLegendre."""
     eps, V = bath.discretize(math.sqrt(impurity.Γ / (2.0 * math.pi)))
     ne = int(np.count_nonzero(eps <= fermi_level))
     return Model(_abi.MODEL_ANDERSON_HOLSTEIN_MIAO_SUBOTNIK, bath.M + 1,

@@ -97,8 +97,10 @@ class Workload:
             return ic["r"].nbytes + ic["v"].nbytes + rho.nbytes
         if self.method == A.METHOD_IESH:
             psi, state = ic.get("psi"), ic.get("state")
-            if psi is None:
-                psi, state = self.iesh_ground_state(T)
+            if psi is None:      # ground-state orbitals (iesh.jl:89-97) are built on the device from the occupations
+                state = np.tile(np.arange(1, self.model.nelectrons + 1, dtype=np.int32), (T, 1)) if state is None else state
+                h.set_state(ic["r"], ic["v"], None, None, state)
+                return ic["r"].nbytes + ic["v"].nbytes + state.nbytes
             h.set_state(ic["r"], ic["v"], psi, None, state)
             return ic["r"].nbytes + ic["v"].nbytes + psi.nbytes + state.nbytes
         h.set_state(ic["r"], ic["v"])

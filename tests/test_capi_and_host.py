@@ -118,6 +118,27 @@ def test_distribution_layouts():
     assert list(r.ravel()) == [3.0, 1.0] and list(v.ravel()) == [0.3, 0.1]
 
 
+def test_shenvi_gauss_legendre_bath():
+    """docs/src/NQCModels/systembathmodels.md:236-262: two Gauss-Legendre halves around the Fermi level; sum V_n^2 =
+    (band width) x coupling^2 (the weights integrate 1 over each half), knots denser towards the band centre, M/2
+    electrons at eF = 0; the model goes through the same AndersonHolstein table as TrapezoidalRule."""
+    M, W = 40, 0.9
+    bath = nq.ShenviGaussLegendre(M, -W, W)
+    eps, V = bath.discretize(0.3)
+    assert eps.shape == V.shape == (M,) and np.all(np.diff(eps) > 0)
+    assert abs(np.sum(V ** 2) - 2 * W * 0.3 ** 2) < 1e-13
+    assert np.allclose(eps, -eps[::-1]) and np.allclose(V, V[::-1])
+    x, w = np.polynomial.legendre.leggauss(M // 2)
+    assert np.allclose(eps[:M // 2], 0.5 * W * x - 0.5 * W) and np.allclose(V[M // 2:] ** 2, 0.5 * W * w * 0.09)
+    model = nq.AndersonHolstein(nq.MiaoSubotnik(Γ=6.4e-3), bath)
+    assert model.nstates == M + 1 and model.nelectrons == M // 2
+    assert np.array_equal(model.bath_a, eps) and np.allclose(model.bath_b, V / 0.3 * np.sqrt(6.4e-3 / (2 * np.pi)))
+    shifted = nq.ShenviGaussLegendre(M, -W, W, fermi_level=0.2).discretize(1.0)[0]
+    assert np.count_nonzero(shifted < 0.2) == M // 2
+    with pytest.raises(ValueError):
+        nq.ShenviGaussLegendre(7, -1.0, 1.0).discretize(1.0)
+
+
 def test_paired_configurations_stay_paired():
     """rand(distribution) draws ONE index for velocity and position (selections.jl:70-73 -> `u = rand(distribution)`;
     `u.v`, `u.r`): correlated phase-space samples from a previous run must not be re-paired at random."""
@@ -252,3 +273,36 @@ def test_terminated_series_trimming_host_logic():
     # first step
     t, a = api._trim_terminated(time, arrs, 1, se, 2.5)
     assert np.array_equal(t, [2.0, 2.5, 2.5]) and np.array_equal(a[api.A.OBS_POSITION][:, 0], [0, 10, 10])
+
+
+def test_file_reduction_layout(tmp_path):
+    """FileReduction (reductions.jl:57-91; test/Ensembles/reductions.jl:20-34): extension forced to .h5, one group per
+    trajectory, one dataset per output, a vector of (ndofs, natoms) frames becomes a 3-index array with the frames on the
+    LAST axis, a vector of numbers stays a vector.  Host logic only (the writer takes the per-trajectory dictionaries
+    run_dynamics builds)."""
+    red = nq.FileReduction(str(tmp_path / "test.out"))
+    assert red.filename.endswith("test.h5")
+    assert nq.FileReduction("a.hdf5").filename == "a.hdf5" and nq.FileReduction("b.h5").filename == "b.h5"
+    nsave = 11
+    trajs = [{"Time": np.linspace(0, 10, nsave), "OutputPosition": np.arange(nsave * 3 * 2, dtype=float).reshape(nsave, 3, 2) + t,
+              "OutputTotalEnergy": np.full(nsave, 0.5 + t),
+              "OutputStateResolvedScattering1D": {"reflection": np.array([1.0, 0.0]), "transmission": np.array([0.0, 0.0])},
+              "OutputSurfaceHops": 2} for t in range(3)]
+    msg = red.write(trajs)
+    assert msg == f"Output written to {red.target}."
+    if red.backend == "h5py":
+        import h5py
+        with h5py.File(red.target, "r") as f:
+            pos = f["trajectory_1"]["OutputPosition"][()]; ene = f["trajectory_3"]["OutputTotalEnergy"][()]
+            keys = sorted(f.keys())
+    else:
+        with np.load(red.target) as f:
+            pos = f["trajectory_1/OutputPosition"]; ene = f["trajectory_3/OutputTotalEnergy"]
+            keys = sorted({k.split("/")[0] for k in f.files})
+            assert f["trajectory_2/OutputStateResolvedScattering1D"].shape == (4,) and f["trajectory_2/OutputSurfaceHops"] == 2
+    assert keys == ["trajectory_1", "trajectory_2", "trajectory_3"]
+    assert pos.ndim == 3 and pos.shape == (3, 2, nsave) and ene.shape == (nsave,)      # Array{<:Real,3}, Vector{<:Real}
+    assert np.array_equal(pos[:, :, 4], trajs[0]["OutputPosition"][4]) and np.all(ene == 2.5)
+    with pytest.raises(Exception):       # the reference opens with "cw" and create_group fails on an existing group
+        red.write(trajs[:1])
+    assert red.write(trajs[:1], first_id=10).startswith("Output written")

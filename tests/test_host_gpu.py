@@ -258,3 +258,24 @@ def test_nrpmd_through_host_api():
         assert not np.array_equal(q[0], q[-1])
     with pytest.raises(TypeError):
         nq.run_dynamics(sim, (0.0, 0.1), dist.nuclear * nq.PureState(1, nq.Adiabatic()), output=nq.OutputDiabaticPopulation, dt=0.01)
+
+
+def test_run_dynamics_file_reduction(tmp_path):
+    """test/Ensembles/reductions.jl:20-34: run_dynamics(sim, (0, 10), u0; dt = 0.1, reduction = FileReduction("test.h5"),
+    output = (OutputPosition, OutputTotalEnergy)) on Simulation(Atoms(1), Harmonic()): trajectory_1/OutputPosition is a
+    3-index array, trajectory_1/OutputTotalEnergy a vector."""
+    sim = nq.Simulation[nq.Classical](nq.Atoms(1), nq.Harmonic())
+    dist = nq.DynamicalDistribution(nq.Normal(0.0, 1.0), nq.Normal(0.0, 1.0), sim.size)
+    red = nq.FileReduction(str(tmp_path / "test.h5"))
+    msg = nq.run_dynamics(sim, (0.0, 10.0), dist, dt=0.1, reduction=red, output=(nq.OutputPosition, nq.OutputTotalEnergy),
+                          trajectories=3, seed=1)
+    assert msg == f"Output written to {red.target}."
+    if red.backend == "h5py":
+        import h5py
+        with h5py.File(red.target, "r") as f:
+            pos, ene, t = f["trajectory_1/OutputPosition"][()], f["trajectory_1/OutputTotalEnergy"][()], f["trajectory_3/Time"][()]
+    else:
+        with np.load(red.target) as f:
+            pos, ene, t = f["trajectory_1/OutputPosition"], f["trajectory_1/OutputTotalEnergy"], f["trajectory_3/Time"]
+    assert pos.shape == (1, 1, 101) and ene.shape == (101,) and np.allclose(t, np.arange(101) * 0.1)
+    assert np.max(np.abs(ene - ene[0])) < 2e-2 * abs(ene[0]) + 1e-9      # velocity Verlet at omega dt = 0.1

@@ -275,3 +275,43 @@ def test_run_dynamics_two_shards_equal_one(case):
                          ensemble_algorithm=nq.EnsembleB200(3, device_ids=[0, 0, 0]), **{**kw, "output": kw["output"][0]})
     for k in m1:
         assert np.allclose(np.asarray(m1[k]), np.asarray(m2[k]), rtol=1e-12, atol=1e-13), (case, k)
+
+
+@pytest.mark.parametrize("method", [A.METHOD_IESH, A.METHOD_EHRENFEST_NA])
+def test_iesh_device_side_orbitals_and_gauss_legendre_bath(method):
+    """nqcb200_set_state with sig_re == NULL: psi[state[e], e] = 1 is built on the device (iesh.jl:89-128) -- bit-identical to
+    uploading the identity columns -- on an AndersonHolstein model discretised with ShenviGaussLegendre (iesh.md:98-105),
+    and the run agrees with the oracle."""
+    T, nsteps = 6, 20
+    rng = np.random.default_rng(61)
+    model = nq.AndersonHolstein(nq.MiaoSubotnik(Γ=6.4e-3), nq.ShenviGaussLegendre(30, -0.0192, 0.0192))
+    n, ne = model.nstates, model.nelectrons
+    obs = (1 << A.OBS_ADIABATIC_POP) | (1 << A.OBS_KINETIC) | (1 << A.OBS_SIGMA)
+    kw = model_config(model, method=method, masses=[2000.0], ntraj=T, dt=5.0, rng=A.RNG_INJECTED, diagnostics=1,
+                      save_every=5, nsave=nsteps // 5 + 1, observables=obs, per_trajectory=1)
+    r = 6.0 + 12.0 * rng.random(T)
+    v = -np.abs(rng.standard_normal(T)) * 3e-3
+    occ = np.stack([np.sort(rng.choice(n, ne, replace=False)) + 1 for _ in range(T)]).astype(np.int32)
+    psi = np.zeros((T, ne, n)); psi[np.arange(T)[:, None], np.arange(ne)[None, :], occ - 1] = 1.0
+    xi = rng.random((nsteps, T)) * 0.01
+    outs = []
+    for dev_psi in (True, False):
+        cfg, keep = A.make_config(**kw)
+        e = engine_factory()(cfg, keep)
+        e.set_state(r, v, None if dev_psi else psi, None, occ)
+        if method == A.METHOD_IESH:
+            e.set_draws(xi)
+        e.run(nsteps)
+        outs.append((e.get_state(), e.observable_per_trajectory(A.OBS_SIGMA)))
+    assert np.array_equal(outs[0][0]["sigma"], outs[1][0]["sigma"]) and np.array_equal(outs[0][1], outs[1][1])
+    assert np.array_equal(outs[0][0]["r"], outs[1][0]["r"])
+    cfg, keep = A.make_config(**kw)
+    o = oracle_factory()(cfg, keep)
+    o.set_state(r, v, psi, None, occ if method == A.METHOD_IESH else None)
+    if method == A.METHOD_IESH:
+        o.set_draws(xi)
+    o.run(nsteps)
+    so = o.get_state()
+    assert rel_err(outs[0][0]["r"], so["r"]) < 1e-9 and np.max(np.abs(outs[0][0]["sigma"] - so["sigma"])) < 1e-9
+    if method == A.METHOD_IESH:
+        assert np.array_equal(outs[0][0]["state"], so["state"])
