@@ -288,7 +288,7 @@ NQ_D void se_bath_body(const KParams& p, int64_t traj, double* ring) {
 }
 
 template <int E>
-__global__ void __launch_bounds__(kSeThreads, 2) sb_bath_kernel(const __grid_constant__ KParams p) {
+__global__ void __launch_bounds__(kSeThreads, 3) sb_bath_kernel(const __grid_constant__ KParams p) {
     __shared__ double ring[kSeStages * 2 * kSeGroup * kSeThreads];
     const int64_t traj = p.tlo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (traj >= p.thi) return;
