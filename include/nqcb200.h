@@ -92,7 +92,12 @@ enum nqcb200_method {
  *  FREE        {}                  classical, V = 0
  *  ANDERSON_HOLSTEIN_MIAO_SUBOTNIK {m,omega,g,DeltaG}; bath_a=eps_k[M], bath_b=V_k[M]
  *              U0 = 1/2 m w^2 q^2 (state independent), h = U1-U0, U1 = 1/2 m w^2 (q-g)^2 + DeltaG
- *              H[0,0]=h(q), H[k,k]=eps_k, H[0,k]=H[k,0]=V_k ; nstates = M+1   (iesh.md:71-76)      */
+ *              H[0,0]=h(q), H[k,k]=eps_k, H[0,k]=H[k,0]=V_k ; nstates = M+1   (iesh.md:71-76)
+ *  ANDERSON_HOLSTEIN_ERPENBECK_THOSS {De,a,x0,c, D1,D2,a1,x01,Vinf, q,atilde,xtilde}; bath_a=eps_k[M], bath_b=Vbar_k[M]
+ *              the impurity of the reference's own IESH tests and example (test/Dynamics/iesh.jl:23, iesh.md:85-105):
+ *              U0 = De (exp(-a (x-x0)) - 1)^2 + c,  U1 = D1 exp(-2 a1 (x-x01)) - D2 exp(-a1 (x-x01)) + Vinf,  h = U1-U0,
+ *              and a POSITION-DEPENDENT coupling H[0,k] = Vbar_k f(x), f = (1-q)/2 (1 - tanh((x-xtilde)/atilde)) + q
+ *              (NQCModels ErpenbeckThoss, external; formula and defaults recalled, carried as explicit params)      */
 enum nqcb200_model {
     NQCB200_MODEL_TULLY_ONE         = 1,
     NQCB200_MODEL_TULLY_TWO         = 2,
@@ -102,7 +107,8 @@ enum nqcb200_model {
     NQCB200_MODEL_THREE_STATE_MORSE = 6,
     NQCB200_MODEL_HARMONIC          = 7,
     NQCB200_MODEL_FREE              = 8,
-    NQCB200_MODEL_ANDERSON_HOLSTEIN_MIAO_SUBOTNIK = 9
+    NQCB200_MODEL_ANDERSON_HOLSTEIN_MIAO_SUBOTNIK = 9,
+    NQCB200_MODEL_ANDERSON_HOLSTEIN_ERPENBECK_THOSS = 10
 };
 
 /* frustrated-hop policy: surface_hopping.jl:65,79-91 */

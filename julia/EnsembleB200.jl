@@ -170,10 +170,11 @@ impurity_id(::NQCModels.MiaoSubotnik) = 9
 impurity_params(m::NQCModels.MiaoSubotnik) = (m.m, m.ω, m.g, m.ΔG)
 impurity_coupling(m::NQCModels.MiaoSubotnik) = sqrt(m.Γ / 2π)
 impurity_id(::NQCModels.ErpenbeckThoss) = 10
-# U0 = Morse(D_e, a, x0) + c ; U1 = D1 exp(-2a'(x-x0')) - 2 D1 exp(-a'(x-x0')) + V_inf ;
-# coupling V_k(x) = Vbar (1 - q tanh((x - xtilde)/atilde))/2 -- include/nqcb200.h, enum nqcb200_model
-impurity_params(m::NQCModels.ErpenbeckThoss) = (m.morse.Dₑ, m.morse.a, m.morse.x₀, m.c, m.D₁, m.D₂, m.x₀′, m.a′, m.V∞,
-                                                m.q, m.ã, m.x̃, m.V̄ₖ)
+# params order of include/nqcb200.h (ANDERSON_HOLSTEIN_ERPENBECK_THOSS): De, a, x0, c, D1, D2, a1, x01, Vinf, q, atilde, xtilde
+#   U0 = De (exp(-a (x - x0)) - 1)^2 + c ; U1 = D1 exp(-2 a1 (x - x01)) - D2 exp(-a1 (x - x01)) + Vinf ;
+#   V_k(x) = Vbar_k ((1 - q)/2 (1 - tanh((x - xtilde)/atilde)) + q)
+impurity_params(m::NQCModels.ErpenbeckThoss) = (m.morse.Dₑ, m.morse.a, m.morse.x₀, m.c, m.D₁, m.D₂, m.a′, m.x₀′, m.V∞,
+                                                m.q, m.ã, m.x̃)
 impurity_coupling(m::NQCModels.ErpenbeckThoss) = sqrt(m.Γ / 2π)
 impurity_id(m) = error("EnsembleB200: no device implementation of impurity model $(typeof(m))")
 

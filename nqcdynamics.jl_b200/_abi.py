@@ -20,7 +20,9 @@ METHOD_FSSH, METHOD_EHRENFEST, METHOD_IESH, METHOD_CLASSICAL, METHOD_NRPMD, METH
 METHOD_THERMAL_LANGEVIN = 7
 IESH_FAMILY = (METHOD_IESH, METHOD_EHRENFEST_NA)      # psi: n x ne, trajectory-major
 (MODEL_TULLY_ONE, MODEL_TULLY_TWO, MODEL_TULLY_THREE, MODEL_DOUBLE_WELL, MODEL_SPIN_BOSON,
- MODEL_THREE_STATE_MORSE, MODEL_HARMONIC, MODEL_FREE, MODEL_ANDERSON_HOLSTEIN_MIAO_SUBOTNIK) = range(1, 10)
+ MODEL_THREE_STATE_MORSE, MODEL_HARMONIC, MODEL_FREE, MODEL_ANDERSON_HOLSTEIN_MIAO_SUBOTNIK,
+ MODEL_ANDERSON_HOLSTEIN_ERPENBECK_THOSS) = range(1, 11)
+ANDERSON_HOLSTEIN_FAMILY = (MODEL_ANDERSON_HOLSTEIN_MIAO_SUBOTNIK, MODEL_ANDERSON_HOLSTEIN_ERPENBECK_THOSS)
 RESCALE_STANDARD, RESCALE_VINVERSION, RESCALE_OFF = 0, 1, 2
 RNG_PHILOX, RNG_INJECTED = 0, 1
 (OBS_ADIABATIC_POP, OBS_DIABATIC_POP, OBS_POPCORR_DIABATIC, OBS_POPCORR_ADIABATIC, OBS_KINETIC,

@@ -104,6 +104,7 @@ struct KParams {
     const double* init_state_draw;
     // AdiabaticIESH: psi / occupations are TRAJECTORY-major ([T][n*ne], [T][ne]); see kernel_iesh.cuh
     IeshLayout iesh;
+    int32_t iesh_impurity;   // 0: MiaoSubotnik (constant coupling), 1: ErpenbeckThoss (coupling scaled by f(x)), kernel_iesh.cuh
     double* iesh_lam;   // [T][n]   adiabatic energies of the last step (warm start of the root finder)
     double* iesh_sgn;   // [T][n]   eigenvector column signs (gauge), constant along a trajectory
     double* iesh_orth;  // [T]      1.0 when the initial orbitals are orthonormal (determinant-free pruning bound)

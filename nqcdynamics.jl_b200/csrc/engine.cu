@@ -571,6 +571,7 @@ int nqcb200_create(const nqcb200_config* cfg, nqcb200_handle** out) {
             h->err = "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)"; cudaGetLastError(); return fail(NQCB200_ERR_CUDA);
         }
         kp.iesh = ks.iesh;
+        kp.iesh_impurity = (c.model == NQCB200_MODEL_ANDERSON_HOLSTEIN_ERPENBECK_THOSS) ? 1 : 0;
     }
 
     int rc;

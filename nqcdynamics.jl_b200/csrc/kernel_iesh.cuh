@@ -89,13 +89,14 @@ NQ_D double iesh_block_max(double x, double* red) {
 // Shared-memory carve-up common to the step / init / diagnostics kernels.
 struct IeshSmem {
     double *eps, *V2, *Vb, *lam, *mu, *z0, *ws, *sgn, *red, *pop;
+    double* fsc;        // [0] coupling scale f(x) of the current geometry (1 for MiaoSubotnik), [1] h(x)
     int *pole, *occ, *un, *flag, *ctl;
     double* work;
     int np;
     NQ_D void carve(double* base, int n) {
         np = (n + 3) & ~3;
         eps = base; V2 = eps + np; Vb = V2 + np; lam = Vb + np; mu = lam + np; z0 = mu + np; ws = z0 + np;
-        sgn = ws + np; pop = sgn + np; red = pop + np;
+        sgn = ws + np; pop = sgn + np; red = pop + np; fsc = red + 56;
         pole = (int*)(red + 64); occ = pole + np; un = occ + np; flag = un + np; ctl = flag + np;
         work = (double*)(ctl + 16);
     }
@@ -109,7 +110,7 @@ NQ_HD int iesh_small_doubles(int n) {
 // Secular function at offset mu from pole p: f = (h - eps_p) - mu - sum_k V_k^2 / ((eps_k - eps_p) - mu),
 // fp = -f' = 1 + sum_k V_k^2 / (...)^2, s3 = sum_k V_k^2 / (...)^3 (so d fp / d mu = 2 s3).
 // The lr lanes of a group split the sum (xor butterfly: bit-identical result on all of them).
-NQ_D void iesh_secular(const double* eps, const double* V2, int M, int p, double hp, double mu, int sub, int lr,
+NQ_D void iesh_secular(const double* eps, const double* V2, double f2, int M, int p, double hp, double mu, int sub, int lr,
                        unsigned mask, double& f, double& fp, double& s3) {
     const double ep = eps[p];
     double s1 = 0.0, s2 = 0.0, s3l = 0.0;
@@ -117,7 +118,7 @@ NQ_D void iesh_secular(const double* eps, const double* V2, int M, int p, double
     for (int k = sub; k < M; k += lr) {
         const double d = (eps[k] - ep) - mu;
         const double inv = iesh_rcp(d);
-        const double t = V2[k] * inv;
+        const double t = (V2[k] * f2) * inv;
         const double u = t * inv;
         s1 += t;
         s2 += u;
@@ -139,7 +140,7 @@ NQ_D void iesh_secular(const double* eps, const double* V2, int M, int p, double
 // is then chosen by the sign of f at the interval midpoint).  Safeguarded Newton on phi(mu) = mu f(mu), which
 // removes the pole at mu = 0 and converges quadratically; the last step is accepted when it is below 3e-8 |mu|
 // (error after it ~ 1e-15 |mu|) and fp is corrected to first order with s3.
-NQ_D void iesh_root(const double* eps, const double* V2, int M, int i, double h, double vnorm, double lam_prev,
+NQ_D void iesh_root(const double* eps, const double* V2, double f2, int M, int i, double h, double vnorm, double lam_prev,
                     int sub, int lr, unsigned mask, int& p_out, double& mu_out, double& fp_out) {
     int p;
     double lo, hi;
@@ -157,7 +158,7 @@ NQ_D void iesh_root(const double* eps, const double* V2, int M, int i, double h,
         bool right;
         if (cold) {
             double f, fp, s3;
-            iesh_secular(eps, V2, M, i - 1, h - eps[i - 1], 0.5 * gap, sub, lr, mask, f, fp, s3);
+            iesh_secular(eps, V2, f2, M, i - 1, h - eps[i - 1], 0.5 * gap, sub, lr, mask, f, fp, s3);
             right = f > 0.0;                                  // f decreases: root right of the midpoint
         } else right = (eps[i] - lam_prev) < (lam_prev - eps[i - 1]);
         if (right) { p = i; lo = -gap; hi = 0.0; }
@@ -172,7 +173,7 @@ NQ_D void iesh_root(const double* eps, const double* V2, int M, int i, double h,
     double fpv = 1.0;
     for (int it = 0; it < 100; ++it) {
         double f, fp, s3;
-        iesh_secular(eps, V2, M, p, hp, mu, sub, lr, mask, f, fp, s3);
+        iesh_secular(eps, V2, f2, M, p, hp, mu, sub, lr, mask, f, fp, s3);
         fpv = fp;
         if (f == 0.0) break;
         if (f > 0.0) lo = mu; else hi = mu;
@@ -196,17 +197,45 @@ NQ_D double iesh_wdiff(const IeshSmem& S, int i, int j) {
 NQ_D double iesh_Z(const IeshSmem& S, int k, int i) {
     if (k == 0) return S.z0[i];
     const double d = (S.eps[S.pole[i]] - S.eps[k - 1]) + S.mu[i];   // lambda_i - eps_{k-1}
-    return S.z0[i] * S.Vb[k - 1] / d;
+    return S.z0[i] * (S.Vb[k - 1] * S.fsc[0]) / d;
 }
 
+// Impurity of the AndersonHolstein model: h = U1 - U0, the state-independent U0, and the common scale f(x) of the couplings
+// H[0,k] = Vbar_k f(x).  MiaoSubotnik: f = 1.  ErpenbeckThoss (NQCModels, external; the impurity of test/Dynamics/iesh.jl:23
+// and iesh.md:85-105): f = (1-q)/2 (1 - tanh((x - xt)/at)) + q > 0.  With a common scale the matrix stays an arrowhead and
+// dH/dx = h' e0 e0' + f' (e0 Vbar' + Vbar e0'); the eigen equation's first row gives Vbar . z_b = (w_i - h) z0_i / f, hence
+//     (Z' dH Z)_ij = z0_i z0_j [ h' + (f'/f) (w_i + w_j - 2h) ]
+// -- still an outer product with a two-term weight: force, NAC and v.d keep their O(n^2) forms.
 struct IeshModel {
-    double mw2, g, dG, mass;
-    NQ_D void eval(double q, double& h, double& dh, double& u0, double& du0) const {
-        u0 = 0.5 * mw2 * q * q;
-        const double u1 = 0.5 * mw2 * (q - g) * (q - g) + dG;
-        h = u1 - u0;
-        dh = mw2 * (q - g) - mw2 * q;
-        du0 = mw2 * q;
+    int erp;
+    double a[12], mass;
+    NQ_D void load(const KParams& p) {
+        erp = p.iesh_impurity;
+        for (int i = 0; i < 12; ++i) a[i] = p.params[i];
+        mass = p.masses[0];
+        if (!erp) a[0] = p.params[0] * p.params[1] * p.params[1];      // m w^2
+    }
+    NQ_D void eval(double q, double& h, double& dh, double& u0, double& du0, double& f, double& df) const {
+        if (!erp) {
+            const double mw2 = a[0], g = a[2], dG = a[3];
+            u0 = 0.5 * mw2 * q * q;
+            const double u1 = 0.5 * mw2 * (q - g) * (q - g) + dG;
+            h = u1 - u0;
+            dh = mw2 * (q - g) - mw2 * q;
+            du0 = mw2 * q;
+            f = 1.0; df = 0.0;
+        } else {
+            const double e0 = exp(-a[1] * (q - a[2]));
+            u0 = a[0] * (e0 - 1.0) * (e0 - 1.0) + a[3];
+            du0 = -2.0 * a[0] * a[1] * e0 * (e0 - 1.0);
+            const double e1 = exp(-a[6] * (q - a[7]));
+            const double u1 = a[4] * e1 * e1 - a[5] * e1 + a[8];
+            const double du1 = -2.0 * a[6] * a[4] * e1 * e1 + a[6] * a[5] * e1;
+            h = u1 - u0; dh = du1 - du0;
+            const double t = tanh((q - a[11]) / a[10]);
+            f = 0.5 * (1.0 - a[9]) * (1.0 - t) + a[9];
+            df = -0.5 * (1.0 - a[9]) * (1.0 - t * t) / a[10];
+        }
     }
 };
 
@@ -223,15 +252,17 @@ NQ_D double iesh_load_bath(const KParams& p, IeshSmem& S) {
 }
 
 // All roots for impurity level h; fills pole, mu, lam, z0 (signed with S.sgn).  Ends with a barrier.
-NQ_D void iesh_eigen(const KParams& p, IeshSmem& S, double h, double vnorm, bool cold) {
+NQ_D void iesh_eigen(const KParams& p, IeshSmem& S, double h, double f, double vnorm, bool cold) {
     const int n = p.n, M = n - 1, lr = p.iesh.lr;
     const int lane = threadIdx.x & 31;
     const int root = threadIdx.x / lr, sub = threadIdx.x % lr;
     const unsigned mask = (lr >= 32) ? 0xffffffffu : (((1u << lr) - 1u) << (lane & ~(lr - 1)));
+    if (threadIdx.x == 0) { S.fsc[0] = f; S.fsc[1] = h; }      // read after the closing barrier (iesh_Z, estimators)
+    vnorm *= fabs(f);
     if (root < n) {
         int pp; double mu, fp;
         const double guess = cold ? nan("") : S.lam[root];
-        iesh_root(S.eps, S.V2, M, root, h, vnorm, guess, sub, lr, mask, pp, mu, fp);
+        iesh_root(S.eps, S.V2, f * f, M, root, h, vnorm, guess, sub, lr, mask, pp, mu, fp);
         __syncwarp(mask);   // every lane of the group has read its warm start S.lam[root]
         if (sub == 0) {
             S.pole[root] = pp; S.mu[root] = mu; S.lam[root] = S.eps[pp] + mu;
@@ -256,19 +287,28 @@ NQ_D void iesh_refresh_unoccupied(const KParams& p, IeshSmem& S) {
 
 // EhrenfestNA force weight (ehrenfest_na.jl:72-90 with Z' dV Z = h' z0 z0'): sum_e |sum_n z0[n] psi[n,e]|^2.
 // Warps take electrons, lanes split the states; result on every thread.
-NQ_D double iesh_mean_field_weight(const KParams& p, const IeshSmem& S, const double* psi_re, const double* psi_im) {
+NQ_D double iesh_mean_field_weight(const KParams& p, const IeshSmem& S, const double* psi_re, const double* psi_im, int erp,
+                                   double h, double& weight2) {
+    // second weight (position-dependent coupling): sum_e Re conj(s_e) t_e, s_e = sum_i z0_i psi_ie, t_e = sum_i (w_i - h) z0_i psi_ie
     const int n = p.n, ne = p.ne, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    double part = 0.0;
+    double part = 0.0, part2 = 0.0;
     for (int e = warp; e < ne; e += nwarps) {
-        double cr = 0.0, ci = 0.0;
+        double cr = 0.0, ci = 0.0, tr = 0.0, ti = 0.0;
         for (int i = lane; i < n; i += 32) {
-            cr = fma(S.z0[i], psi_re[(int64_t)n * e + i], cr);
-            ci = fma(S.z0[i], psi_im[(int64_t)n * e + i], ci);
+            const double z = S.z0[i], xr = psi_re[(int64_t)n * e + i], xi = psi_im[(int64_t)n * e + i];
+            cr = fma(z, xr, cr);
+            ci = fma(z, xi, ci);
+            if (erp) { const double zw = z * (S.lam[i] - h); tr = fma(zw, xr, tr); ti = fma(zw, xi, ti); }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { cr += __shfl_xor_sync(0xffffffffu, cr, o); ci += __shfl_xor_sync(0xffffffffu, ci, o); }
-        if (lane == 0) part += cr * cr + ci * ci;
+        if (erp) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { tr += __shfl_xor_sync(0xffffffffu, tr, o); ti += __shfl_xor_sync(0xffffffffu, ti, o); }
+        }
+        if (lane == 0) { part += cr * cr + ci * ci; part2 += cr * tr + ci * ti; }
     }
+    weight2 = erp ? iesh_block_sum(part2, S.red) : 0.0;
     return iesh_block_sum(part, S.red);
 }
 
@@ -388,8 +428,8 @@ __device__ __noinline__ void iesh_record_save(const KParams& p, IeshSmem& S, int
     if (tid == 0) {
         if (obs & ((1u << NQCB200_OBS_KINETIC) | (1u << NQCB200_OBS_POTENTIAL) | (1u << NQCB200_OBS_TOTAL_ENERGY))) {
             const double kin = (mdl.mass * v * v) / 2.0;
-            double h, dh, u0, du0;
-            mdl.eval(r, h, dh, u0, du0);
+            double h, dh, u0, du0, fs, dfs;
+            mdl.eval(r, h, dh, u0, du0, fs, dfs);
             double pot = u0;                                                      // iesh.jl:380-388
             if (p.mean_field) {                                                   // ehrenfest_na.jl:103-114
                 for (int e = 0; e < ne; ++e)
@@ -732,9 +772,9 @@ NQ_D bool iesh_outside(const KParams& p, double r, double v, int64_t steps_done)
 
 // Eigen-decomposition at the frozen position of a trajectory that terminated in an earlier launch (cold path).
 __device__ __noinline__ void iesh_eigen_frozen(const KParams& p, IeshSmem& S, const IeshModel& mdl, double r, double vnorm) {
-    double h, dh, u0, du0;
-    mdl.eval(r, h, dh, u0, du0);
-    iesh_eigen(p, S, h, vnorm, false);
+    double h, dh, u0, du0, fs, dfs;
+    mdl.eval(r, h, dh, u0, du0, fs, dfs);
+    iesh_eigen(p, S, h, fs, vnorm, false);
 }
 
 // ---- the step kernel -----------------------------------------------------------------------------
@@ -748,7 +788,8 @@ __global__ void __launch_bounds__(384, 1) iesh_step_kernel(const __grid_constant
     const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
     const int n4 = (n + 3) & ~3;
     const double dt = p.dt, hdt = 0.5 * p.dt;
-    const IeshModel mdl{p.params[0] * p.params[1] * p.params[1], p.params[2], p.params[3], p.masses[0]};
+    IeshModel mdl;
+    mdl.load(p);
     const double vnorm = iesh_load_bath(p, S);
 
     double* Gs = S.work;                                   // resident: ldg x n4 ; streaming: 2 slabs of ldg x kb
@@ -782,17 +823,25 @@ __global__ void __launch_bounds__(384, 1) iesh_step_kernel(const __grid_constant
             // ---- nuclei + eigen + force (verlet_with_electronics.jl:55-66) -------------------------
             const double vt = fma(hdt, acc, v);
             r = fma(dt, vt, r);
-            double h, dh, u0, du0;
-            mdl.eval(r, h, dh, u0, du0);
-            iesh_eigen(p, S, h, vnorm, false);
+            double h, dh, u0, du0, fs, dfs;
+            mdl.eval(r, h, dh, u0, du0, fs, dfs);
+            iesh_eigen(p, S, h, fs, vnorm, false);
+            const double phi = dfs / fs;              // f'/f: (Z' dH Z)_ij = z0_i z0_j [h' + phi (w_i + w_j - 2h)]
             if (p.mean_field) {
-                const double wsum = iesh_mean_field_weight(p, S, psi_re, psi_im);  // sigma_prev: psi before this step's propagation
-                acc = (-du0 - dh * wsum) / mdl.mass;
+                double wsum2 = 0.0;
+                const double wsum = iesh_mean_field_weight(p, S, psi_re, psi_im, mdl.erp, h, wsum2);  // sigma_prev: psi before this step's propagation
+                acc = ((-du0 - dh * wsum) - 2.0 * phi * wsum2) / mdl.mass;
             } else {
-                double part = 0.0;
-                for (int e = tid; e < ne; e += nt) { const double z = S.z0[S.occ[e]]; part += z * z; }
+                double part = 0.0, part2 = 0.0;
+                for (int e = tid; e < ne; e += nt) {
+                    const int o = S.occ[e];
+                    const double z = S.z0[o];
+                    part += z * z;
+                    if (mdl.erp) part2 = fma(z * z, S.lam[o] - h, part2);
+                }
                 const double occsum = iesh_block_sum(part, S.red);
-                acc = (-du0 - dh * occsum) / mdl.mass;                            // iesh.jl:190-207
+                const double occsum2 = mdl.erp ? iesh_block_sum(part2, S.red) : 0.0;
+                acc = ((-du0 - dh * occsum) - 2.0 * phi * occsum2) / mdl.mass;      // iesh.jl:190-207
             }
             v = fma(hdt, acc, vt);
 
@@ -807,11 +856,13 @@ __global__ void __launch_bounds__(384, 1) iesh_step_kernel(const __grid_constant
                 // thread -> (row i fastest); one division per element, w_i - w_j from pole offsets
                 for (int j = warp; j < n; j += nwarps) {
                     const double zj = S.z0[j] * gpref, ej = S.eps[S.pole[j]], mj = S.mu[j];
+                    const double zje = -v * S.z0[j] * phi, wj = S.lam[j] - h;      // S.lam is final (barrier of iesh_eigen); S.ws is not yet
                     const bool occ_j = S.flag[j] >= 0;
                     for (int i = lane; i < n; i += 32) {
                         double g = 0.0;
                         if (i != j) {
-                            g = zj * S.z0[i] * iesh_rcp((S.eps[S.pole[i]] - ej) + (S.mu[i] - mj));
+                            const double num = mdl.erp ? fma(zje, (S.lam[i] - h) + wj, zj) : zj;
+                            g = num * S.z0[i] * iesh_rcp((S.eps[S.pole[i]] - ej) + (S.mu[i] - mj));
                             if (occ_j && S.flag[i] < 0) sabs += fabs(g);         // |v_dot_d[m, e]|, iesh.jl:285-298
                         }
                         g2 = fma(g, g, g2);
@@ -990,7 +1041,8 @@ __global__ void __launch_bounds__(384, 1) iesh_step_kernel(const __grid_constant
                         bool accept = true;
                         if (p.rescaling != NQCB200_RESCALE_OFF) {                 // surface_hopping.jl:64-99
                             const double wd = iesh_wdiff(S, hm, old_state);
-                            const double d = -dh * S.z0[hm] * S.z0[old_state] / wd;
+                            const double dhw = mdl.erp ? dh + phi * ((S.lam[hm] - h) + (S.lam[old_state] - h)) : dh;
+                            const double d = -dhw * S.z0[hm] * S.z0[old_state] / wd;
                             const double aa = (d * d / mdl.mass) / 2.0, bb = d * v, cc = wd;
                             const double disc = bb * bb - 4.0 * aa * cc;
                             if (disc < 0.0) {
@@ -1062,12 +1114,14 @@ __global__ void __launch_bounds__(384, 1) iesh_step_kernel(const __grid_constant
         if (tid == 0) { p.r[traj] = r; p.v[traj] = v; p.acc[traj] = acc; }
         if (p.diagnostics && p.diag_eig) {
             // eigenvalues, NAC d[j,i] (column-major j + n i), eigenvectors of the last evaluated geometry
-            double h, dh, u0, du0;
-            mdl.eval(r, h, dh, u0, du0);
+            double h, dh, u0, du0, fs, dfs;
+            mdl.eval(r, h, dh, u0, du0, fs, dfs);
+            const double phi = dfs / fs;
             for (int i = tid; i < n; i += nt) p.diag_eig[traj * n + i] = S.lam[i];
             for (int idx = tid; idx < n * n; idx += nt) {
                 const int j = idx % n, i = idx / n;
-                p.diag_nac[traj * (int64_t)n * n + idx] = (i == j) ? 0.0 : -dh * S.z0[j] * S.z0[i] / iesh_wdiff(S, j, i);
+                const double dhw = dh + phi * ((S.lam[i] - h) + (S.lam[j] - h));
+                p.diag_nac[traj * (int64_t)n * n + idx] = (i == j) ? 0.0 : -dhw * S.z0[j] * S.z0[i] / iesh_wdiff(S, j, i);
                 p.diag_Z[traj * (int64_t)n * n + idx] = iesh_Z(S, j, i);
             }
         }
@@ -1091,7 +1145,8 @@ __global__ void __launch_bounds__(384, 1) iesh_init_kernel(const __grid_constant
     IeshSmem S;
     S.carve(iesh_sm, p.n);
     const int n = p.n, ne = p.ne, tid = threadIdx.x, nt = blockDim.x;
-    const IeshModel mdl{p.params[0] * p.params[1] * p.params[1], p.params[2], p.params[3], p.masses[0]};
+    IeshModel mdl;
+    mdl.load(p);
     const double vnorm = iesh_load_bath(p, S);
     for (int64_t traj = blockIdx.x; traj < p.ntraj; traj += gridDim.x) {
         const double* psi_re = p.sig_re + traj * (int64_t)n * ne;
@@ -1101,9 +1156,10 @@ __global__ void __launch_bounds__(384, 1) iesh_init_kernel(const __grid_constant
         for (int e = tid; e < ne; e += nt) S.occ[e] = p.state[traj * ne + e];
         iesh_refresh_unoccupied(p, S);
         const double r = p.r[traj], v = p.v[traj];
-        double h, dh, u0, du0;
-        mdl.eval(r, h, dh, u0, du0);
-        iesh_eigen(p, S, h, vnorm, true);
+        double h, dh, u0, du0, fs, dfs;
+        mdl.eval(r, h, dh, u0, du0, fs, dfs);
+        const double phi = dfs / fs;
+        iesh_eigen(p, S, h, fs, vnorm, true);
         // gauge: flip column i when dot(Z_new[:,i], Z_ref[:,i]) < 0 ; identity reference -> sign of Z[i,i]
         for (int i = tid; i < n; i += nt) {
             double dot;
@@ -1116,14 +1172,20 @@ __global__ void __launch_bounds__(384, 1) iesh_init_kernel(const __grid_constant
         __syncthreads();
         for (int i = tid; i < n; i += nt) { S.z0[i] *= S.sgn[i]; p.iesh_sgn[traj * n + i] = S.sgn[i]; p.iesh_lam[traj * n + i] = S.lam[i]; }
         __syncthreads();
-        double occsum;
-        if (p.mean_field) occsum = iesh_mean_field_weight(p, S, psi_re, psi_im);
+        double occsum, occsum2 = 0.0;
+        if (p.mean_field) occsum = iesh_mean_field_weight(p, S, psi_re, psi_im, mdl.erp, h, occsum2);
         else {
-            double part = 0.0;
-            for (int e = tid; e < ne; e += nt) { const double z = S.z0[S.occ[e]]; part += z * z; }
+            double part = 0.0, part2 = 0.0;
+            for (int e = tid; e < ne; e += nt) {
+                const int o = S.occ[e];
+                const double z = S.z0[o];
+                part += z * z;
+                if (mdl.erp) part2 = fma(z * z, S.lam[o] - h, part2);
+            }
             occsum = iesh_block_sum(part, S.red);
+            if (mdl.erp) occsum2 = iesh_block_sum(part2, S.red);
         }
-        if (tid == 0) p.acc[traj] = (-du0 - dh * occsum) / mdl.mass;
+        if (tid == 0) p.acc[traj] = ((-du0 - dh * occsum) - 2.0 * phi * occsum2) / mdl.mass;
         iesh_record_save(p, S, traj, 0, r, v, mdl, psi_re, psi_im, S.work + p.iesh.off_b, p.iesh.work_doubles - p.iesh.off_b);
         {
             // are the orbitals orthonormal?  (enables the determinant-free pruning bound of the step kernel)
@@ -1146,7 +1208,8 @@ __global__ void __launch_bounds__(384, 1) iesh_init_kernel(const __grid_constant
             for (int i = tid; i < n; i += nt) p.diag_eig[traj * n + i] = S.lam[i];
             for (int idx = tid; idx < n * n; idx += nt) {
                 const int j = idx % n, i = idx / n;
-                p.diag_nac[traj * (int64_t)n * n + idx] = (i == j) ? 0.0 : -dh * S.z0[j] * S.z0[i] / iesh_wdiff(S, j, i);
+                const double dhw = dh + phi * ((S.lam[i] - h) + (S.lam[j] - h));
+                p.diag_nac[traj * (int64_t)n * n + idx] = (i == j) ? 0.0 : -dhw * S.z0[j] * S.z0[i] / iesh_wdiff(S, j, i);
                 p.diag_Z[traj * (int64_t)n * n + idx] = iesh_Z(S, j, i);
             }
         }

@@ -65,7 +65,7 @@ bool iesh_plan(int n, int ne, size_t smem_max, IeshLayout& L) {
 }  // namespace
 
 bool select_iesh(const nqcb200_config& c, KernelSet& out, std::string& why) {
-    if (c.model != NQCB200_MODEL_ANDERSON_HOLSTEIN_MIAO_SUBOTNIK) {
+    if (c.model != NQCB200_MODEL_ANDERSON_HOLSTEIN_MIAO_SUBOTNIK && c.model != NQCB200_MODEL_ANDERSON_HOLSTEIN_ERPENBECK_THOSS) {
         why = "AdiabaticIESH is built for the AndersonHolstein (Newns-Anderson) model"; return false;
     }
     if (c.ndofs != 1 || c.nbeads != 1) { why = "AdiabaticIESH kernel: ndofs == 1 and nbeads == 1"; return false; }

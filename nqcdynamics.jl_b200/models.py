@@ -33,22 +33,30 @@ class Model:
     def adiabatic_energies(self, r) -> np.ndarray:
         """Eigenvalues of the diabatic Hamiltonian at one configuration -- host-side, used ONLY to draw Fermi-Dirac
         initial occupations (the reference does the same inside sample_distribution, iesh.jl:114-120)."""
-        if self.kind != _abi.MODEL_ANDERSON_HOLSTEIN_MIAO_SUBOTNIK:
+        if self.kind not in _abi.ANDERSON_HOLSTEIN_FAMILY:
             raise NotImplementedError("adiabatic_energies: only needed for AndersonHolstein initial conditions")
         return np.linalg.eigvalsh(self.diabatic_hamiltonian(r))
 
     def diabatic_hamiltonian(self, r) -> np.ndarray:
         """The n x n electronic Hamiltonian the IESH cache diagonalises (state-independent U0 removed): host-side, for
         the Fermi-Dirac initial conditions only (iesh.jl:114-120, 153-160)."""
-        if self.kind != _abi.MODEL_ANDERSON_HOLSTEIN_MIAO_SUBOTNIK:
+        if self.kind not in _abi.ANDERSON_HOLSTEIN_FAMILY:
             raise NotImplementedError("diabatic_hamiltonian: only needed for AndersonHolstein initial conditions")
-        m, w, g, dG = self.params
         q = float(np.asarray(r).reshape(-1)[0])
         n = self.nstates
         H = np.zeros((n, n))
-        H[0, 0] = 0.5 * m * w * w * (q - g) ** 2 + dG - 0.5 * m * w * w * q * q
+        if self.kind == _abi.MODEL_ANDERSON_HOLSTEIN_MIAO_SUBOTNIK:
+            m, w, g, dG = self.params
+            H[0, 0] = 0.5 * m * w * w * (q - g) ** 2 + dG - 0.5 * m * w * w * q * q
+            f = 1.0
+        else:
+            De, a, x0, c, D1, D2, a1, x01, Vinf, qq, at, xt = self.params
+            u0 = De * (math.exp(-a * (q - x0)) - 1.0) ** 2 + c
+            e1 = math.exp(-a1 * (q - x01))
+            H[0, 0] = D1 * e1 * e1 - D2 * e1 + Vinf - u0
+            f = 0.5 * (1.0 - qq) * (1.0 - math.tanh((q - xt) / at)) + qq
         H[np.arange(1, n), np.arange(1, n)] = self.bath_a
-        H[0, 1:] = H[1:, 0] = self.bath_b
+        H[0, 1:] = H[1:, 0] = self.bath_b * f
         return H
 
 
@@ -160,10 +168,41 @@ class MiaoSubotnik:
     ΔG: float = -3.8e-3
 
 
-def AndersonHolstein(impurity: MiaoSubotnik, bath, fermi_level: float = 0.0) -> Model:
-    """``AndersonHolstein(impurity_model, bath; fermi_level)``: ``bath`` is a TrapezoidalRule or a ShenviGaussLegendre."""
+_EV = 1.0 / 27.211386245988          # hartree per eV
+_ANG = 1.0 / 0.529177210903         # bohr per angstrom
+
+
+@dataclass
+class ErpenbeckThoss:
+    """``ErpenbeckThoss(; Γ)`` (NQCModels, external; Erpenbeck & Thoss 2018): the impurity of the reference's own IESH tests
+    and example (test/Dynamics/iesh.jl:23, iesh.md:85-105).  U0 = Morse(De, a, x0) + c, U1 = D1 e^{-2a'(x-x0')} - D2 e^{-a'(x-x0')}
+    + V_inf, and a position-dependent coupling V_k(x) = Vbar_k [(1-q)/2 (1 - tanh((x - xt)/at)) + q], Vbar = sqrt(Γ/2π).
+    Formula and defaults are RECALLED from NQCModels (not in the reference tree); they travel as explicit parameters."""
+    Γ: float
+    Dₑ: float = 3.52 * _EV
+    a: float = 1.7361 / _ANG
+    x0: float = 1.78 * _ANG
+    c: float = -1.5 * _EV
+    D1: float = 4.52 * _EV
+    D2: float = 0.79 * _EV
+    a1: float = 1.379 / _ANG
+    x01: float = 1.78 * _ANG
+    Vinf: float = -1.5 * _EV
+    q: float = 0.05
+    at: float = 0.5 * _ANG
+    xt: float = 3.5 * _ANG
+
+
+def AndersonHolstein(impurity, bath, fermi_level: float = 0.0) -> Model:
+    """``AndersonHolstein(impurity_model, bath; fermi_level)``: ``impurity`` is a MiaoSubotnik or an ErpenbeckThoss, ``bath`` a
+    TrapezoidalRule or a ShenviGaussLegendre."""
     eps, V = bath.discretize(math.sqrt(impurity.Γ / (2.0 * math.pi)))
     ne = int(np.count_nonzero(eps <= fermi_level))
+    if isinstance(impurity, ErpenbeckThoss):
+        i = impurity
+        return Model(_abi.MODEL_ANDERSON_HOLSTEIN_ERPENBECK_THOSS, bath.M + 1,
+                     (i.Dₑ, i.a, i.x0, i.c, i.D1, i.D2, i.a1, i.x01, i.Vinf, i.q, i.at, i.xt), bath_a=eps, bath_b=V,
+                     nelectrons=ne, name="AndersonHolstein", fermi_level=fermi_level)
     return Model(_abi.MODEL_ANDERSON_HOLSTEIN_MIAO_SUBOTNIK, bath.M + 1,
                  (impurity.m, impurity.ω, impurity.g, impurity.ΔG), bath_a=eps, bath_b=V, nelectrons=ne,
                  name="AndersonHolstein", fermi_level=fermi_level)

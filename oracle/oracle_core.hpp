@@ -282,11 +282,28 @@ struct Model {
     // only AndersonHolstein carries one (U0); every other quantum model folds it into V.
     double U0(const double* r) const {
         if (kind == NQCB200_MODEL_ANDERSON_HOLSTEIN_MIAO_SUBOTNIK) return 0.5 * p[0] * p[1] * p[1] * r[0] * r[0];
+        if (kind == NQCB200_MODEL_ANDERSON_HOLSTEIN_ERPENBECK_THOSS) {
+            const double e = std::exp(-p[1] * (r[0] - p[2])) - 1.0;
+            return p[0] * e * e + p[3];
+        }
         return 0.0;
     }
     void dU0(const double* r, double* g) const {
         for (int i = 0; i < D; ++i) g[i] = 0.0;
         if (kind == NQCB200_MODEL_ANDERSON_HOLSTEIN_MIAO_SUBOTNIK) g[0] = p[0] * p[1] * p[1] * r[0];
+        if (kind == NQCB200_MODEL_ANDERSON_HOLSTEIN_ERPENBECK_THOSS) {
+            const double ex = std::exp(-p[1] * (r[0] - p[2]));
+            g[0] = -2.0 * p[0] * p[1] * ex * (ex - 1.0);
+        }
+    }
+    // ErpenbeckThoss: U1(x), U1'(x) and the coupling scale f(x), f'(x)
+    void erpenbeck(double x, double& u1, double& du1, double& f, double& df) const {
+        const double ex = std::exp(-p[6] * (x - p[7]));
+        u1 = p[4] * ex * ex - p[5] * ex + p[8];
+        du1 = -2.0 * p[6] * p[4] * ex * ex + p[6] * p[5] * ex;
+        const double t = std::tanh((x - p[11]) / p[10]);
+        f = 0.5 * (1.0 - p[9]) * (1.0 - t) + p[9];
+        df = -0.5 * (1.0 - p[9]) * (1.0 - t * t) / p[10];
     }
 
     void potential(const double* r, double* V) const {
@@ -344,6 +361,15 @@ struct Model {
                     V[0 + (size_t)n * k] = V[k] = bb[k - 1];
                 }
             } break;
+            case NQCB200_MODEL_ANDERSON_HOLSTEIN_ERPENBECK_THOSS: {
+                double u1, du1, f, df;
+                erpenbeck(q, u1, du1, f, df);
+                V[0] = u1 - U0(r);
+                for (int k = 1; k < n; ++k) {
+                    V[k + (size_t)n * k] = ba[k - 1];
+                    V[0 + (size_t)n * k] = V[k] = bb[k - 1] * f;
+                }
+            } break;
             default: throw std::runtime_error("oracle: unknown model");
         }
     }
@@ -397,6 +423,13 @@ struct Model {
             case NQCB200_MODEL_ANDERSON_HOLSTEIN_MIAO_SUBOTNIK: {
                 double m = p[0], om = p[1], g = p[2];
                 dV[0] = m * om * om * (q - g) - m * om * om * q;  // d(U1-U0)/dq
+            } break;
+            case NQCB200_MODEL_ANDERSON_HOLSTEIN_ERPENBECK_THOSS: {
+                double u1, du1, f, df, g0[8] = {0};
+                erpenbeck(q, u1, du1, f, df);
+                dU0(r, g0);
+                dV[0] = du1 - g0[0];
+                for (int k = 1; k < n; ++k) dV[0 + (size_t)n * k] = dV[k] = bb[k - 1] * df;
             } break;
             default: throw std::runtime_error("oracle: unknown model");
         }

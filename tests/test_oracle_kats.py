@@ -94,6 +94,9 @@ def test_bcb_second_order_on_harmonic_ring_polymer():
     (nq.TullyModelOne(), [-0.3]), (nq.TullyModelTwo(), [0.7]), (nq.TullyModelThree(), [-1.1]),
     (nq.DoubleWell(), [0.4]), (nq.ThreeStateMorse(), [3.4]),
     (nq.SpinBoson(nq.DebyeSpectralDensity(0.25, 0.5), 5, 0.1, 1.0), [0.3, -0.2, 0.5, 0.1, -0.7]),
+    (nq.AndersonHolstein(nq.MiaoSubotnik(Γ=6.4e-3), nq.TrapezoidalRule(8, -0.0192, 0.0192)), [11.0]),
+    (nq.AndersonHolstein(nq.ErpenbeckThoss(Γ=6.4e-3), nq.TrapezoidalRule(8, -0.0192, 0.0192)), [5.9]),     # test/Dynamics/iesh.jl:17-25
+    (nq.AndersonHolstein(nq.ErpenbeckThoss(Γ=0.2 / 27.2114), nq.ShenviGaussLegendre(8, -0.9, 0.9)), [3.1]),  # iesh.md:85-105
 ])
 def test_calculator_cache_identities(model, r):
     """test/Core/calculators.jl:99-108 (w = eigvals(V), |Z| = |eigvecs|, adiab = Z' dV Z) and

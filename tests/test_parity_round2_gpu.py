@@ -315,3 +315,64 @@ def test_iesh_device_side_orbitals_and_gauss_legendre_bath(method):
     assert rel_err(outs[0][0]["r"], so["r"]) < 1e-9 and np.max(np.abs(outs[0][0]["sigma"] - so["sigma"])) < 1e-9
     if method == A.METHOD_IESH:
         assert np.array_equal(outs[0][0]["state"], so["state"])
+
+
+@pytest.mark.parametrize("method", [A.METHOD_IESH, A.METHOD_EHRENFEST_NA])
+@pytest.mark.parametrize("bath", ["trapezoidal", "gauss_legendre"])
+def test_iesh_erpenbeck_thoss_parity(method, bath):
+    """AndersonHolstein(ErpenbeckThoss(; Γ), bath): the model of the reference's own IESH tests (test/Dynamics/iesh.jl:17-25:
+    Γ = 6.4e-3, M = 30, W = 3Γ, Atoms(2000)) and of its scattering example (iesh.md:85-105, ShenviGaussLegendre).  The
+    coupling depends on the position, so dH/dx is rank two; the arrowhead kernel uses
+    (Z' dH Z)_ij = z0_i z0_j [h' + (f'/f)(w_i + w_j - 2h)] and must reproduce the oracle's dense Z' dV Z path step by step."""
+    T, nsteps = 6, 24
+    rng = np.random.default_rng(71)
+    bath_obj = nq.TrapezoidalRule(30, -0.0192, 0.0192) if bath == "trapezoidal" else nq.ShenviGaussLegendre(30, -0.0192, 0.0192)
+    model = nq.AndersonHolstein(nq.ErpenbeckThoss(Γ=6.4e-3), bath_obj)
+    n, ne = model.nstates, model.nelectrons
+    obs = IESH_OBS if method == A.METHOD_IESH else (IESH_OBS & ~((1 << A.OBS_DIABATIC_POP) | (1 << A.OBS_DISCRETE_STATE)))
+    kw = model_config(model, method=method, masses=[2000.0], ntraj=T, dt=2.0, rng=A.RNG_INJECTED, diagnostics=1,
+                      save_every=4, nsave=nsteps // 4 + 1, observables=obs, per_trajectory=1)
+    e, o = make_pair(engine_factory(), oracle_factory(), **kw)
+    r = 3.0 + 5.0 * rng.random(T)                      # from the chemisorption well out to the coupling's switching region
+    v = rng.standard_normal(T) * 3e-3
+    re, im, state = _iesh_random_state(rng, T, n, ne)
+    xi = rng.random((nsteps, T)) * 0.05
+    for h in (e, o):
+        h.set_state(r, v, re, im, state if method == A.METHOD_IESH else None)
+        if method == A.METHOD_IESH:
+            h.set_draws(xi)
+    _iesh_compare(e, o, 1e-10, "t0") if method == A.METHOD_IESH else None
+    for chunk in range(nsteps // 4):
+        e.run(4); o.run(4)
+        se, so = e.get_state(), o.get_state()
+        assert rel_err(se["r"], so["r"]) < 1e-10 and rel_err(se["v"], so["v"]) < 1e-10, chunk
+        assert np.max(np.abs(se["sigma"] - so["sigma"])) < 1e-10, chunk
+        de, do = e.diagnostics(), o.diagnostics()
+        assert rel_err(de["eig"], do["eig"]) < 1e-10 and rel_err(de["accel"], do["accel"]) < 1e-10
+        assert np.max(np.abs(de["Z"] - do["Z"])) < 1e-10
+        assert np.max(np.abs(de["nac"] - do["nac"])) < 1e-10 * max(1.0, np.max(np.abs(do["nac"])))
+        if method == A.METHOD_IESH:
+            assert np.array_equal(se["state"], so["state"])
+    _compare_observables(e, o, obs, 1e-9, T)
+    if method == A.METHOD_IESH:
+        assert e.counters() == o.counters() or (e.counters()["hops"] == o.counters()["hops"])
+
+
+def test_iesh_erpenbeck_thoss_energy_conservation():
+    """test/Dynamics/iesh.jl:155-170 in spirit: a single AdiabaticIESH trajectory on the ErpenbeckThoss model conserves the
+    total energy between hops (no hops here: draws of 1) -- an independent check of the rank-two force."""
+    model = nq.AndersonHolstein(nq.ErpenbeckThoss(Γ=6.4e-3), nq.TrapezoidalRule(30, -0.0192, 0.0192))
+    n, ne, T, nsteps = model.nstates, model.nelectrons, 4, 400
+    kw = model_config(model, method=A.METHOD_IESH, masses=[2000.0], ntraj=T, dt=1.0, rng=A.RNG_INJECTED,
+                      save_every=10, nsave=nsteps // 10 + 1, observables=(1 << A.OBS_TOTAL_ENERGY) | (1 << A.OBS_POSITION), per_trajectory=1)
+    cfg, keep = A.make_config(**kw)
+    e = engine_factory()(cfg, keep)
+    r = np.array([3.2, 4.0, 5.0, 6.5]); v = np.array([2e-3, -3e-3, 1e-3, -4e-3])
+    e.set_state(r, v, None, None, np.tile(np.arange(1, ne + 1, dtype=np.int32), (T, 1)))
+    e.set_draws(np.ones((nsteps, T)))
+    e.run(nsteps)
+    E = e.observable_per_trajectory(A.OBS_TOTAL_ENERGY)[:, :, 0]
+    x = e.observable_per_trajectory(A.OBS_POSITION)[:, :, 0]
+    assert np.max(np.abs(x - x[:, :1])) > 0.5                       # the trajectories actually move
+    kin0 = 0.5 * 2000.0 * v * v
+    assert np.max(np.abs(E - E[:, :1])) < 5e-4 * np.max(kin0)       # velocity Verlet at dt = 1: 9e-7 on a kinetic energy of 0.009 (oracle: same)
