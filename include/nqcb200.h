@@ -323,6 +323,23 @@ typedef struct nqcb200_dist {
 int nqcb200_sample_state(nqcb200_handle* h, const nqcb200_dist* r_dist, const nqcb200_dist* v_dist, int normal_modes,
                          const double* rho_re, const double* rho_im, int diabatic, int32_t state);
 
+/* Device-side electronic initial conditions (second half).  Both are called AFTER the nuclei are in
+ * place (nqcb200_set_state / nqcb200_sample_state) and re-record save point 0; the CPU oracle implements the same streams.
+ *
+ * nqcb200_sample_occupations -- AdiabaticIESH with FermiDiracState{Adiabatic} (iesh.jl:99-128): the occupied adiabatic
+ *   orbitals of every trajectory are drawn by the reference's Metropolis walk over orbital swaps
+ *   (sample_fermi_dirac_distribution, DynamicsUtils.jl:194-208, Boltzmann-factor variant: nstates * nelectrons proposals
+ *   "occupied k <-> unoccupied u", accepted when exp(-beta (E_u - E_k)) > rand()) on the adiabatic energies at r0, then
+ *   sorted; psi[state[e], e] = 1.  beta = 1 / kT in atomic units (INFINITY: only downhill / level swaps are accepted).
+ *   Uniforms: Philox4x32-10 keyed by (seed; global trajectory id, 3 * proposal + {0, 1, 2}, purpose 5): index of the
+ *   occupied orbital, index in the CURRENT list of unoccupied orbitals (a swap exchanges the two list entries), acceptance.
+ *
+ * nqcb200_sample_mapping -- NRPMD with PureState{Diabatic}(state) (nrpmd.jl:47-65): theta ~ U[0, 2 pi) per (state, bead),
+ *   (q, p) = R (cos theta, sin theta), R = sqrt(2 + 2 gamma) on the occupied (1-based) state and sqrt(2 gamma) elsewhere.
+ *   Uniforms: Philox keyed by (seed; global trajectory id, state_index + nstates * bead, purpose 4).                       */
+int nqcb200_sample_occupations(nqcb200_handle* h, double beta);
+int nqcb200_sample_mapping(nqcb200_handle* h, int32_t state);
+
 /* Download the current DynamicsVariables (any pointer may be NULL to skip that field). */
 int nqcb200_get_state(nqcb200_handle* h, double* r, double* v,
                       double* sig_re, double* sig_im, int32_t* state);

@@ -108,6 +108,8 @@ def bind(lib: C.CDLL, prefix: str) -> None:
     f("run", [H, C.c_int64])
     f("run_from_host", [H, _dp, _dp, _dp, _dp, _ip, _dp, C.c_int, C.c_int64], required=False)
     f("sample_state", [H, C.POINTER(Dist), C.POINTER(Dist), C.c_int, _dp, _dp, C.c_int, C.c_int32])
+    f("sample_occupations", [H, C.c_double])
+    f("sample_mapping", [H, C.c_int32])
     f("get_state", [H, _dp, _dp, _dp, _dp, _ip])
     f("get_mapping", [H, _dp, _dp])
     f("get_observable_sum", [H, C.c_int, _dp, C.c_int64])
@@ -126,7 +128,7 @@ def bind(lib: C.CDLL, prefix: str) -> None:
 
 HEADER_SYMBOLS = [
     "version", "device_count", "create", "destroy", "last_error", "observable_width", "set_state",
-    "set_state_diabatic", "set_mapping", "set_gauge_reference", "set_draws", "set_noise", "set_termination", "get_termination", "run", "run_from_host", "sample_state", "get_state", "get_mapping",
+    "set_state_diabatic", "set_mapping", "set_gauge_reference", "set_draws", "set_noise", "set_termination", "get_termination", "run", "run_from_host", "sample_state", "sample_occupations", "sample_mapping", "get_state", "get_mapping",
     "get_observable_sum", "observable_sum_device", "observable_offset", "get_observable_per_trajectory",
     "get_diagnostics", "get_counters", "get_iesh_stats", "get_progress", "get_last_run_timing", "get_launch_count", "get_last_download_timing", "measure_fp64_peak",
 ]
@@ -288,6 +290,14 @@ class CHandle:
             im = np.ascontiguousarray(m.imag.T).reshape(-1)
         self._call("sample_state", rd, vd, C.c_int(1 if normal_modes else 0), _ptr(re), _ptr(im),
                    C.c_int(1 if diabatic else 0), C.c_int32(int(state)))
+
+    def sample_occupations(self, beta: float):
+        """AdiabaticIESH: FermiDiracState{Adiabatic} occupations drawn on the device (nqcb200_sample_occupations)."""
+        self._call("sample_occupations", C.c_double(float(beta)))
+
+    def sample_mapping(self, state: int):
+        """NRPMD: initial mapping variables for PureState{Diabatic}(state) drawn on the device (nqcb200_sample_mapping)."""
+        self._call("sample_mapping", C.c_int32(int(state)))
 
     def get_state(self):
         T, B, D, n = self.T, self.B, self.D, self.n

@@ -758,11 +758,12 @@ def run_dynamics(sim: Simulation, tspan, distribution, *, output, selection: Opt
         nuclear, electronic = distribution, None
     density = method.method_id in (A.METHOD_FSSH, A.METHOD_EHRENFEST)
     dev_spec = None
-    if getattr(alg, "device_sampling", False):
-        dev_spec = nuclear.device_spec() if selection is None else None
-        if dev_spec is None or method.method_id in A.IESH_FAMILY + (A.METHOD_NRPMD,):
-            raise ValueError("device_sampling needs number / Normal / VelocityBoltzmann entries, no selection, and a method "
-                             "other than AdiabaticIESH / NRPMD")
+    iesh_family = method.method_id in A.IESH_FAMILY
+    device_sampling = bool(getattr(alg, "device_sampling", False))
+    if device_sampling and not iesh_family:      # AdiabaticIESH: two nuclear numbers per trajectory stay on the host, the
+        dev_spec = nuclear.device_spec() if selection is None else None      # occupations are drawn on the device (below)
+        if dev_spec is None:
+            raise ValueError("device_sampling needs number / Normal / VelocityBoltzmann entries and no selection")
         if (density and method.method_id == A.METHOD_FSSH and isinstance(electronic, MixedState)
                 and (isinstance(electronic.statetype, Adiabatic) or electronic.statetype is Adiabatic)):
             raise ValueError("device_sampling: an adiabatic MixedState needs the active state drawn per trajectory on the "
@@ -786,6 +787,7 @@ def run_dynamics(sim: Simulation, tspan, distribution, *, output, selection: Opt
                 raise ValueError("Fermi level of model and distribution do not match")          # iesh.jl:105-112
             occ0 = np.empty((T, ne), dtype=np.int32)
             diabatic_fd = isinstance(electronic.statetype, Diabatic) or electronic.statetype is Diabatic
+            fd_on_device = device_sampling and not diabatic_fd and not mean_field
             if diabatic_fd:
                 if mean_field:
                     raise TypeError("EhrenfestNA: FermiDiracState{Diabatic} is defined for AdiabaticIESH only (iesh.jl:138)")
@@ -793,6 +795,8 @@ def run_dynamics(sim: Simulation, tspan, distribution, *, output, selection: Opt
             for t in range(T):
                 if diabatic_fd:
                     psi0[t], occ0[t] = electronic.sample_diabatic(rng, model.diabatic_hamiltonian(r[t].reshape(-1)), ne)
+                elif fd_on_device:       # nqcb200_sample_occupations draws them from the device's own eigenvalues at r0
+                    occ0[t] = np.arange(1, ne + 1)
                 else:
                     occ0[t] = electronic.sample_occupations(rng, model.adiabatic_energies(r[t].reshape(-1)), ne)
         else:
@@ -800,13 +804,18 @@ def run_dynamics(sim: Simulation, tspan, distribution, *, output, selection: Opt
         # psi0 stays None for the adiabatic cases: electron e starts in orbital occ0[e], built on the device from the
         # occupations alone (nqcb200_set_state with sig_re == NULL)
 
+    fd_beta = None
+    if iesh and isinstance(electronic, FermiDiracState) and device_sampling and not mean_field and not (
+            isinstance(electronic.statetype, Diabatic) or electronic.statetype is Diabatic):
+        fd_beta = electronic.β
     qmap0 = pmap0 = None
     if method.method_id == A.METHOD_NRPMD:
         # DynamicsVariables(sim::RingPolymerSimulation{<:NRPMD}, v, r, ::PureState{Diabatic}) (nrpmd.jl:47-65): one random
         # angle per state and bead; radius sqrt(2 + 2 gamma) on the occupied state, sqrt(2 gamma) on the others
         if not isinstance(electronic, PureState) or isinstance(electronic.statetype, Adiabatic) or electronic.statetype is Adiabatic:
             raise TypeError("NRPMD takes nuclear * PureState(i, Diabatic())")
-        qmap0, pmap0 = sample_nrpmd_mapping(rng, T, sim.beads, model.nstates, electronic.state, float(method.γ))
+        if not device_sampling:
+            qmap0, pmap0 = sample_nrpmd_mapping(rng, T, sim.beads, model.nstates, electronic.state, float(method.γ))
 
     ngpus = max(1, int(alg.ngpus))
     device_ids = list(range(ngpus)) if alg.device_ids is None else [int(d) for d in alg.device_ids]
@@ -847,6 +856,8 @@ def run_dynamics(sim: Simulation, tspan, distribution, *, output, selection: Opt
                         adiabatic = isinstance(electronic.statetype, Adiabatic) or electronic.statetype is Adiabatic
                     st = electronic.state if (adiabatic and method.method_id == A.METHOD_FSSH and isinstance(electronic, PureState)) else 0
                     eng.sample_state(dev_spec[0], dev_spec[1], rho1, diabatic=not adiabatic, state=st)
+                    if method.method_id == A.METHOD_NRPMD:
+                        eng.sample_mapping(electronic.state)
                     rg = vg = None
                 else:
                     rg, vg = r[lo:hi], v[lo:hi]
@@ -874,6 +885,8 @@ def run_dynamics(sim: Simulation, tspan, distribution, *, output, selection: Opt
                         eng.set_state_diabatic(rg, vg, rho)
                 elif iesh:
                     eng.set_state(rg, vg, None if psi0 is None else psi0[lo:hi], None, None if (mean_field and psi0 is not None) else occ0[lo:hi])
+                    if fd_beta is not None:
+                        eng.sample_occupations(fd_beta)
                 elif method.method_id == A.METHOD_NRPMD:
                     eng.set_state(rg, vg)
                     eng.set_mapping(qmap0[lo:hi], pmap0[lo:hi])

@@ -79,6 +79,47 @@ __global__ void aos_to_soa_range(const double* __restrict__ in, double* __restri
         if (t < n && c < C) out[(int64_t)c * ldT + lo + t] = tile[threadIdx.x][i];
     }
 }
+// FermiDiracState{Adiabatic} occupations (nqcb200_sample_occupations, DynamicsUtils.jl:194-208): one thread per trajectory,
+// the occupied / unoccupied lists live in global scratch ([T][n], first ne entries occupied); ascending result in state
+__global__ void iesh_sample_fd(const double* __restrict__ lam, int32_t* __restrict__ lists, int32_t* __restrict__ state, int64_t T,
+                               int n, int ne, double beta, uint64_t seed, int64_t traj_offset) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    int32_t* occ = lists + t * n;
+    int32_t* un = occ + ne;
+    const int nun = n - ne;
+    for (int i = 0; i < n; ++i) occ[i] = i;
+    const double* E = lam + t * n;
+    const uint64_t gid = (uint64_t)(traj_offset + t);
+    const bool cold = !(beta < 1e300);
+    for (int64_t it = 0; it < (int64_t)n * ne; ++it) {
+        const int k = min(ne - 1, (int)(nq::philox_uniform(seed, gid, 3 * it + 0, 5u) * ne));
+        const int u = min(nun - 1, (int)(nq::philox_uniform(seed, gid, 3 * it + 1, 5u) * nun));
+        const double de = E[un[u]] - E[occ[k]];
+        const double prob = cold ? (de <= 0.0 ? 1.0 : 0.0) : exp(fmin(700.0, -beta * de));
+        if (prob > nq::philox_uniform(seed, gid, 3 * it + 2, 5u)) { const int32_t tmp = occ[k]; occ[k] = un[u]; un[u] = tmp; }
+    }
+    for (int i = 1; i < ne; ++i) {        // insertion sort (sort!(state))
+        const int32_t x = occ[i];
+        int j = i - 1;
+        while (j >= 0 && occ[j] > x) { occ[j + 1] = occ[j]; --j; }
+        occ[j + 1] = x;
+    }
+    for (int e = 0; e < ne; ++e) state[t * ne + e] = occ[e];
+}
+// NRPMD initial mapping variables (nqcb200_sample_mapping, nrpmd.jl:47-65); qmap / pmap are SoA [bead * n + state][T]
+__global__ void nrpmd_sample_mapping(double* __restrict__ qmap, double* __restrict__ pmap, int64_t T, int n, int B, int occupied,
+                                     double gamma, uint64_t seed, int64_t traj_offset) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t t = idx % T;
+    const int comp = (int)(idx / T);
+    if (comp >= n * B) return;
+    const int s = comp % n;
+    const double theta = 6.283185307179586 * nq::philox_uniform(seed, (uint64_t)(traj_offset + t), (uint64_t)comp, 4u);
+    const double R = (s == occupied) ? sqrt(2.0 + 2.0 * gamma) : sqrt(2.0 * gamma);
+    qmap[(int64_t)comp * T + t] = R * cos(theta);
+    pmap[(int64_t)comp * T + t] = R * sin(theta);
+}
 // AdiabaticIESH: psi[t][e][state[t][e]] = 1 (trajectory-major psi, 0-based occupations), everything else already zero
 __global__ void iesh_fill_psi(double* __restrict__ psi, const int32_t* __restrict__ state, int64_t cnt, int n, int ne) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // = t * ne + e
@@ -745,6 +786,57 @@ int nqcb200_set_state(nqcb200_handle* h, const double* r, const double* v, const
 int nqcb200_set_state_diabatic(nqcb200_handle* h, const double* r, const double* v, const double* rho_re,
                                const double* rho_im, const int32_t* state, const double* state_draw) {
     return set_state_impl(h, r, v, rho_re, rho_im, state, 1, state_draw);
+}
+
+int nqcb200_sample_occupations(nqcb200_handle* h, double beta) {
+    if (!h) return NQCB200_ERR_INVALID;
+    const nqcb200_config& c = h->cfg;
+    if (c.method != NQCB200_METHOD_IESH) { h->err = "Fermi-Dirac occupations exist for AdiabaticIESH"; return NQCB200_ERR_INVALID; }
+    if (!h->has_state) { h->err = "sample_occupations before set_state"; return NQCB200_ERR_STATE; }
+    if (!(beta >= 0.0)) { h->err = "beta must be >= 0"; return NQCB200_ERR_INVALID; }
+    NQ_CUDA(h, cudaSetDevice(c.device));
+    const int64_t T = c.ntraj;
+    if (T == 0) return NQCB200_OK;
+    const int n = c.nstates, ne = c.nelectrons;
+    // the adiabatic energies at r0 are in iesh_lam (init kernel of the preceding set_state); staging holds the lists
+    int32_t* lists = (int32_t*)h->staging;
+    if ((size_t)T * n * sizeof(int32_t) > h->staging_doubles * sizeof(double)) { h->err = "staging too small"; return NQCB200_ERR_STATE; }
+    iesh_sample_fd<<<(unsigned)((T + 127) / 128), 128, 0, h->stream>>>(h->kp.iesh_lam, lists, h->kp.state, T, n, ne, beta, c.seed, c.traj_offset);
+    ++h->launches_total;
+    const size_t bytes = sizeof(double) * (size_t)T * h->nsig;
+    NQ_CUDA(h, cudaMemsetAsync(h->kp.sig_re, 0, bytes, h->stream));
+    NQ_CUDA(h, cudaMemsetAsync(h->kp.sig_im, 0, bytes, h->stream));
+    const int64_t cnt = T * ne;
+    iesh_fill_psi<<<(unsigned)((cnt + 255) / 256), 256, 0, h->stream>>>(h->kp.sig_re, h->kp.state, cnt, n, ne);
+    ++h->launches_total;
+    NQ_CUDA(h, cudaGetLastError());
+    // forces, orthonormality flag and save point 0 for the new orbitals (same tail as set_state)
+    return finish_set_state(h, 0, 0, nullptr, false);
+}
+
+int nqcb200_sample_mapping(nqcb200_handle* h, int32_t state) {
+    if (!h) return NQCB200_ERR_INVALID;
+    const nqcb200_config& c = h->cfg;
+    if (c.method != NQCB200_METHOD_NRPMD) { h->err = "mapping variables exist only for NRPMD"; return NQCB200_ERR_INVALID; }
+    if (!h->has_nuclei) { h->err = "sample_mapping before set_state"; return NQCB200_ERR_STATE; }
+    if (state < 1 || state > c.nstates) { h->err = "state out of range"; return NQCB200_ERR_INVALID; }
+    NQ_CUDA(h, cudaSetDevice(c.device));
+    const int64_t T = c.ntraj, total = T * c.nstates * c.nbeads;
+    if (T > 0) {
+        nrpmd_sample_mapping<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(h->kp.qmap, h->kp.pmap, T, c.nstates, c.nbeads, state - 1,
+                                                                                   c.nrpmd_gamma, c.seed, c.traj_offset);
+        ++h->launches_total;
+        NQ_CUDA(h, cudaGetLastError());
+    }
+    NQ_CUDA(h, cudaMemsetAsync(h->kp.obs_sum, 0, sizeof(double) * std::max<int64_t>(1, h->kp.layout.total) * kObsReplicas, h->stream));
+    if (T > 0) {
+        int rc2 = launch_init(h, 0, 0, nullptr);
+        if (rc2) return rc2;
+    }
+    NQ_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->nsave_done = 1;
+    h->has_state = true;
+    return NQCB200_OK;
 }
 
 int nqcb200_set_mapping(nqcb200_handle* h, const double* qmap, const double* pmap) {

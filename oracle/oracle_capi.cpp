@@ -278,8 +278,8 @@ static int set_state_impl(nqco_handle* h, const double* r, const double* v, cons
     const int64_t T = (int64_t)h->traj.size();
     const bool density = (method == NQCB200_METHOD_FSSH || method == NQCB200_METHOD_EHRENFEST);
     const size_t nsig = iesh_family(method) ? (size_t)n * ne : (size_t)n * n;
-    if ((density || iesh_family(method)) && !sre) { h->err = "sigma required"; return NQCB200_ERR_INVALID; }
-    if (method == NQCB200_METHOD_IESH && !state) { h->err = "state required"; return NQCB200_ERR_INVALID; }
+    if (density && !sre) { h->err = "sigma required"; return NQCB200_ERR_INVALID; }
+    if (method == NQCB200_METHOD_IESH && sre && !state) { h->err = "state required"; return NQCB200_ERR_INVALID; }
     int rc = NQCB200_OK;
 #pragma omp parallel for schedule(static)
     for (int64_t t = 0; t < T; ++t) {
@@ -287,10 +287,12 @@ static int set_state_impl(nqco_handle* h, const double* r, const double* v, cons
         tr.r.assign(r + (size_t)t * B * D, r + (size_t)(t + 1) * B * D);
         tr.v.assign(v + (size_t)t * B * D, v + (size_t)(t + 1) * B * D);
         tr.sigma.assign(nsig, cd(0.0));
-        if (density || iesh_family(method))
+        if ((density || iesh_family(method)) && sre)
             for (size_t i = 0; i < nsig; ++i) tr.sigma[i] = cd(sre[t * nsig + i], sim ? sim[t * nsig + i] : 0.0);
+        if (iesh_family(method) && !sre)      // iesh.jl:89-128: electron e starts in the adiabatic orbital state[e] (1..ne without state)
+            for (int e = 0; e < ne; ++e) tr.sigma[(size_t)(state ? state[t * ne + e] - 1 : e) + (size_t)n * e] = cd(1.0);
         tr.occ.clear();
-        if (method == NQCB200_METHOD_IESH) for (int e = 0; e < ne; ++e) tr.occ.push_back(state[t * ne + e] - 1);
+        if (method == NQCB200_METHOD_IESH) for (int e = 0; e < ne; ++e) tr.occ.push_back(state ? state[t * ne + e] - 1 : e);
         const double* zr = h->Zref.empty() ? nullptr : &h->Zref[(size_t)t * h->zref_per_traj * n * n];
         initialise(S, tr, zr);
         if (density && basis == 1) {
@@ -396,6 +398,57 @@ int nqco_set_mapping(nqco_handle* h, const double* qmap, const double* pmap) {
     std::fill(h->obs_sum.begin(), h->obs_sum.end(), 0.0);
     record_save(h, 0);
     return NQCB200_OK;
+}
+
+// CPU restatement of nqcb200_sample_occupations (same Philox stream and the same list bookkeeping as the device kernel):
+// sample_fermi_dirac_distribution, DynamicsUtils.jl:194-208 (Boltzmann-factor variant), on the adiabatic energies at r0.
+int nqco_sample_occupations(nqco_handle* h, double beta) {
+    if (!h || !h->has_state || h->S.cfg.method != NQCB200_METHOD_IESH || !(beta >= 0.0)) return NQCB200_ERR_INVALID;
+    Setup& S = h->S;
+    const int n = S.n, ne = S.ne, nun = n - ne, BD = S.B * S.D;
+    const int64_t T = (int64_t)h->traj.size();
+    std::vector<double> r((size_t)T * BD), v((size_t)T * BD);
+    std::vector<int32_t> state((size_t)T * ne);
+    const bool cold = !(beta < 1e300);
+    for (int64_t t = 0; t < T; ++t) {
+        const Trajectory& tr = h->traj[t];
+        std::copy(tr.r.begin(), tr.r.end(), r.begin() + t * BD);
+        std::copy(tr.v.begin(), tr.v.end(), v.begin() + t * BD);
+        const vec& E = hop_cache(S, tr).w;
+        std::vector<int> lst(n);
+        for (int i = 0; i < n; ++i) lst[i] = i;
+        int* occ = lst.data();
+        int* un = occ + ne;
+        const uint64_t gid = (uint64_t)(S.cfg.traj_offset + t);
+        for (int64_t it = 0; it < (int64_t)n * ne; ++it) {
+            const int k = std::min(ne - 1, (int)(philox_uniform(S.cfg.seed, gid, 3 * it + 0, 5u) * ne));
+            const int u = std::min(nun - 1, (int)(philox_uniform(S.cfg.seed, gid, 3 * it + 1, 5u) * nun));
+            const double de = E[un[u]] - E[occ[k]];
+            const double prob = cold ? (de <= 0.0 ? 1.0 : 0.0) : std::exp(std::min(700.0, -beta * de));
+            if (prob > philox_uniform(S.cfg.seed, gid, 3 * it + 2, 5u)) std::swap(occ[k], un[u]);
+        }
+        std::sort(occ, occ + ne);
+        for (int e = 0; e < ne; ++e) state[t * ne + e] = occ[e] + 1;
+    }
+    return set_state_impl(h, r.data(), v.data(), nullptr, nullptr, state.data(), 0, nullptr);
+}
+
+// CPU restatement of nqcb200_sample_mapping (nrpmd.jl:47-65), same Philox stream
+int nqco_sample_mapping(nqco_handle* h, int32_t state) {
+    if (!h || !h->has_state || h->S.cfg.method != NQCB200_METHOD_NRPMD || state < 1 || state > h->S.n) return NQCB200_ERR_INVALID;
+    const Setup& S = h->S;
+    const size_t per = (size_t)S.n * S.B;
+    const double g = S.cfg.nrpmd_gamma;
+    std::vector<double> q(per * h->traj.size()), p(per * h->traj.size());
+    for (size_t t = 0; t < h->traj.size(); ++t)
+        for (size_t comp = 0; comp < per; ++comp) {
+            const int s = (int)(comp % S.n);
+            const double theta = 6.283185307179586 * philox_uniform(S.cfg.seed, (uint64_t)(S.cfg.traj_offset + t), (uint64_t)comp, 4u);
+            const double R = (s == state - 1) ? std::sqrt(2.0 + 2.0 * g) : std::sqrt(2.0 * g);
+            q[t * per + comp] = R * std::cos(theta);
+            p[t * per + comp] = R * std::sin(theta);
+        }
+    return nqco_set_mapping(h, q.data(), p.data());
 }
 
 int nqco_set_draws(nqco_handle* h, const double* xi, int64_t nsteps) {
