@@ -169,43 +169,53 @@ NQ_HD void propagate_density_2state(const ElecParams<2>& cur, double tcur, const
     struct K { double a, b, c; };   // d z, d x01, d y01
     const double tr = s.x[0] + s.x[2];
     double z = s.x[0] - s.x[2], x01 = s.x[1], y01 = s.y[0];
-    auto rhs = [&](double tau, double uz, double u01, double w01, K& k) {
-        const double l = flat ? 0.0 : (tau - tcur) * inv_span;
-        const double dE = fma(dEd, l, dEc), g = fma(gd, l, gc);
+    // generator at stage time ts + c hh: loc = (ts - tcur) inv_span + c (hh inv_span), so dE and g are ONE FMA each from
+    // their values at ts (dE0, g0) and their increments over the sub-step (ddE, ddg) -- the same linear interpolation of
+    // electronic_dynamics.jl:55-79 with the division of labour moved out of the 31 RHS evaluations
+    double dE0, g0, ddE, ddg;
+    auto rhs = [&](double c, double uz, double u01, double w01, K& k) {
+        const double dE = fma(c, ddE, dE0), g = fma(c, ddg, g0);
         k.a = -((4.0 * g) * u01);
         k.b = fma(dE, w01, g * uz);
         k.c = -(dE * u01);
     };
+    auto at_substep = [&](double ts_, double hh_) {
+        const double l0 = flat ? 0.0 : (ts_ - tcur) * inv_span, dl = flat ? 0.0 : hh_ * inv_span;
+        dE0 = fma(dEd, l0, dEc); g0 = fma(gd, l0, gc);
+        ddE = dEd * dl; ddg = gd * dl;
+    };
     K k1, k2, k3, k4, k5, k6;
     double ts = t;
-    rhs(ts, z, x01, y01, k1);
+    at_substep(ts, h);
+    rhs(0.0, z, x01, y01, k1);
 #pragma unroll 1
     for (int sub = 0; sub < 5; ++sub) {
         const double hh = (sub == 4) ? (t + dt) - ts : h;   // tstop snapping of the last sub-step
+        at_substep(ts, hh);
         // stage i+1 argument = [x + h sum_{j<i} a_{i+1,j} k_j] + (h a_{i+1,i}) k_i with h a_ij = ha[] from the constant
         // bank (the last sub-step's snapped length differs from h = dt/5 by rounding only: it enters the stage times)
 #define NQ_ARG(P, C, KN) fma((C), (KN), (P))
         {
             const double c21 = ha[0];
-            rhs(ts + NQ_TS(c1) * hh, NQ_ARG(z, c21, k1.a), NQ_ARG(x01, c21, k1.b), NQ_ARG(y01, c21, k1.c), k2);
+            rhs(NQ_TS(c1), NQ_ARG(z, c21, k1.a), NQ_ARG(x01, c21, k1.b), NQ_ARG(y01, c21, k1.c), k2);
         }
         between(sub, std::integral_constant<int, 0>{});
         {
             const double c31 = ha[1], c32 = ha[2];
-            rhs(ts + NQ_TS(c2) * hh, NQ_ARG(fma(c31, k1.a, z), c32, k2.a), NQ_ARG(fma(c31, k1.b, x01), c32, k2.b),
+            rhs(NQ_TS(c2), NQ_ARG(fma(c31, k1.a, z), c32, k2.a), NQ_ARG(fma(c31, k1.b, x01), c32, k2.b),
                 NQ_ARG(fma(c31, k1.c, y01), c32, k2.c), k3);
         }
         between(sub, std::integral_constant<int, 1>{});
         {
             const double c41 = ha[3], c42 = ha[4], c43 = ha[5];
-            rhs(ts + NQ_TS(c3) * hh, NQ_ARG(fma(c42, k2.a, fma(c41, k1.a, z)), c43, k3.a),
+            rhs(NQ_TS(c3), NQ_ARG(fma(c42, k2.a, fma(c41, k1.a, z)), c43, k3.a),
                 NQ_ARG(fma(c42, k2.b, fma(c41, k1.b, x01)), c43, k3.b),
                 NQ_ARG(fma(c42, k2.c, fma(c41, k1.c, y01)), c43, k3.c), k4);
         }
         between(sub, std::integral_constant<int, 2>{});
         {
             const double c51 = ha[6], c52 = ha[7], c53 = ha[8], c54 = ha[9];
-            rhs(ts + NQ_TS(c4) * hh, NQ_ARG(fma(c53, k3.a, fma(c52, k2.a, fma(c51, k1.a, z))), c54, k4.a),
+            rhs(NQ_TS(c4), NQ_ARG(fma(c53, k3.a, fma(c52, k2.a, fma(c51, k1.a, z))), c54, k4.a),
                 NQ_ARG(fma(c53, k3.b, fma(c52, k2.b, fma(c51, k1.b, x01))), c54, k4.b),
                 NQ_ARG(fma(c53, k3.c, fma(c52, k2.c, fma(c51, k1.c, y01))), c54, k4.c), k5);
         }
@@ -213,7 +223,7 @@ NQ_HD void propagate_density_2state(const ElecParams<2>& cur, double tcur, const
         {
             const double c61 = ha[10], c62 = ha[11], c63 = ha[12], c64 = ha[13],
                          c65 = ha[14];
-            rhs(ts + hh, NQ_ARG(fma(c64, k4.a, fma(c63, k3.a, fma(c62, k2.a, fma(c61, k1.a, z)))), c65, k5.a),
+            rhs(1.0, NQ_ARG(fma(c64, k4.a, fma(c63, k3.a, fma(c62, k2.a, fma(c61, k1.a, z)))), c65, k5.a),
                 NQ_ARG(fma(c64, k4.b, fma(c63, k3.b, fma(c62, k2.b, fma(c61, k1.b, x01)))), c65, k5.b),
                 NQ_ARG(fma(c64, k4.c, fma(c63, k3.c, fma(c62, k2.c, fma(c61, k1.c, y01)))), c65, k5.c), k6);
         }
@@ -227,7 +237,7 @@ NQ_HD void propagate_density_2state(const ElecParams<2>& cur, double tcur, const
         }
 #undef NQ_ARG
         ts = (sub == 4) ? (t + dt) : ts + hh;
-        if (sub < 4) rhs(ts, z, x01, y01, k1);   // FSAL
+        if (sub < 4) rhs(1.0, z, x01, y01, k1);   // FSAL: the slope at the end of this sub-step = at the start of the next
         between(sub, std::integral_constant<int, 5>{});
     }
     s.x[0] = 0.5 * (tr + z); s.x[1] = x01; s.x[2] = 0.5 * (tr - z); s.y[0] = y01;

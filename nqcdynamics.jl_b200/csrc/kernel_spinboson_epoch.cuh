@@ -308,6 +308,7 @@ template <int METHOD, int E>
 __global__ void __launch_bounds__(kSeThreads, 4) sb_elec_kernel(const __grid_constant__ KParams p) {
     constexpr int N = 2;
     __shared__ double fs[2][E + 1][kSeThreads];      // this epoch's impulses (f1, f2), per thread
+    __shared__ double kaps[6][E];                    // lag tables: (c/m | c) x (L, C, W) x lag
     const int tid = threadIdx.x;
     const int64_t T = p.ntraj;
     int64_t traj = p.tlo + (int64_t)blockIdx.x * blockDim.x + tid;
@@ -318,6 +319,8 @@ __global__ void __launch_bounds__(kSeThreads, 4) sb_elec_kernel(const __grid_con
     const double* __restrict__ kap = p.sb_kap;
     const double C2 = kap[6 * kSeLagStride], Cc = kap[6 * kSeLagStride + 1];     // sum c^2/m, sum c^2
     const int kb = p.nsteps;
+    for (int idx = tid; idx < 6 * E; idx += kSeThreads) kaps[idx / E][idx % E] = kap[(idx / E) * kSeLagStride + idx % E];
+    __syncthreads();
 
     SbTraj R;
     Eig<N> e;
@@ -354,17 +357,28 @@ __global__ void __launch_bounds__(kSeThreads, 4) sb_elec_kernel(const __grid_con
         const double tcur = (step == 0) ? 0.0 : t;   // Q1
         double L = p.sb_sums[(int64_t)(3 * k + 0) * T + traj], Cv = p.sb_sums[(int64_t)(3 * k + 1) * T + traj],
                Wr = p.sb_sums[(int64_t)(3 * k + 2) * T + traj];
-        for (int i = 1; i <= k; ++i) {        // impulses of the epoch's later steps: lag tables
-            const double fi = fs[0][i][tid];
-            L = fma(fi, kap[(0 * 3 + 0) * kSeLagStride + (k - i)], L);
-            Cv = fma(fi, kap[(0 * 3 + 1) * kSeLagStride + (k - i)], Cv);
-            Wr = fma(fi, kap[(0 * 3 + 2) * kSeLagStride + (k - i)], Wr);
-            if (vinv) {
-                const double gi = fs[1][i][tid];
-                L = fma(gi, kap[(1 * 3 + 0) * kSeLagStride + (k - i)], L);
-                Cv = fma(gi, kap[(1 * 3 + 1) * kSeLagStride + (k - i)], Cv);
-                Wr = fma(gi, kap[(1 * 3 + 2) * kSeLagStride + (k - i)], Wr);
+        {
+            // impulses of the epoch's later steps through the lag tables (shared-memory copy); two interleaved partial
+            // sums per bath sum halve the dependent FMA chains
+            double L2 = 0.0, C2b = 0.0, W2 = 0.0;
+            int i = 1;
+            for (; i + 1 <= k; i += 2) {
+                const double fa = fs[0][i][tid], fb = fs[0][i + 1][tid];
+                L = fma(fa, kaps[0][k - i], L);          L2 = fma(fb, kaps[0][k - i - 1], L2);
+                Cv = fma(fa, kaps[1][k - i], Cv);        C2b = fma(fb, kaps[1][k - i - 1], C2b);
+                Wr = fma(fa, kaps[2][k - i], Wr);        W2 = fma(fb, kaps[2][k - i - 1], W2);
             }
+            if (i <= k) {
+                const double fa = fs[0][i][tid];
+                L = fma(fa, kaps[0][k - i], L); Cv = fma(fa, kaps[1][k - i], Cv); Wr = fma(fa, kaps[2][k - i], Wr);
+            }
+            if (vinv) {
+                for (int j = 1; j <= k; ++j) {
+                    const double gi = fs[1][j][tid];
+                    L2 = fma(gi, kaps[3][k - j], L2); C2b = fma(gi, kaps[4][k - j], C2b); W2 = fma(gi, kaps[5][k - j], W2);
+                }
+            }
+            L += L2; Cv += C2b; Wr += W2;
         }
         // update_cache!: V -> eigen (gauge-fixed); the harmonic shift is a multiple of the identity
         {
