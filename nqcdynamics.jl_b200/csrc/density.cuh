@@ -25,6 +25,17 @@ struct Herm {
     double y[asym_size(N) > 0 ? asym_size(N) : 1];  // Im sigma, packed strict upper
     NQ_HD double X(int j, int k) const { return (j <= k) ? x[sidx(N, j, k)] : x[sidx(N, k, j)]; }
     NQ_HD double Y(int j, int k) const { return (j == k) ? 0.0 : ((j < k) ? y[aidx(N, j, k)] : -y[aidx(N, k, j)]); }
+    // X(j, k) for RUN-TIME indices as a chain of selects over compile-time indices: a dynamically indexed x[] would
+    // push the whole density matrix into local memory (21 local loads + 17 stores per trajectory-step in the
+    // TullyModelOne kernel, profiles/r02/SUMMARY.md)
+    NQ_HD double Xsel(int j, int k) const {
+        double v = 0.0;
+#pragma unroll
+        for (int a = 0; a < N; ++a)
+#pragma unroll
+            for (int b = a; b < N; ++b) v = ((a == j && b == k) || (a == k && b == j)) ? x[sidx(N, a, b)] : v;
+        return v;
+    }
 };
 
 // One half of the reference's DoubleBuffer (electronic_dynamics.jl:15-36): eigenvalues and the
@@ -34,6 +45,14 @@ struct ElecParams {
     double E[N];
     double g[asym_size(N) > 0 ? asym_size(N) : 1];
     NQ_HD double G(int j, int k) const { return (j == k) ? 0.0 : ((j < k) ? g[aidx(N, j, k)] : -g[aidx(N, k, j)]); }
+    NQ_HD double Gsel(int j, int k) const {      // run-time indices, see Herm::Xsel
+        double v = 0.0;
+#pragma unroll
+        for (int a = 0; a < N; ++a)
+#pragma unroll
+            for (int b = a + 1; b < N; ++b) v = (a == j && b == k) ? g[aidx(N, a, b)] : ((a == k && b == j) ? -g[aidx(N, a, b)] : v);
+        return v;
+    }
 };
 
 template <int N>

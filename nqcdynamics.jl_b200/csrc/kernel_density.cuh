@@ -409,13 +409,13 @@ __global__ void __launch_bounds__(kBlockThreads) density_step_kernel(const __gri
                                   : philox_uniform(p.seed, (uint64_t)(p.traj_offset + traj), (uint64_t)step, 0u);
             // fewest_switches_probability! fssh.jl:96-108 (Q4) + select_new_state :110-121
             const int s0 = R.st;
-            const double inv_ss = 1.0 / R.s.X(s0, s0);
+            const double inv_ss = 1.0 / R.s.Xsel(s0, s0);
             double cum = 0.0;
             int new_state = s0;
 #pragma unroll
             for (int m = 0; m < N; ++m) {
                 double g = 0.0;
-                if (m != s0) g = 2.0 * (R.s.X(m, s0) * inv_ss) * nxt.G(s0, m) * dt;
+                if (m != s0) g = 2.0 * (R.s.Xsel(m, s0) * inv_ss) * nxt.Gsel(s0, m) * dt;
                 g = fmin(1.0, fmax(0.0, g));
                 cum += g;
                 if (new_state == s0 && m != s0 && cum > xi) new_state = m;
