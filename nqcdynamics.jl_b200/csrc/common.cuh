@@ -142,4 +142,41 @@ NQ_HD constexpr int sidx(int n, int j, int k) { return j * n - j * (j - 1) / 2 +
 // packed strict upper index for j < k
 NQ_HD constexpr int aidx(int n, int j, int k) { return j * n - j * (j + 1) / 2 + (k - j - 1); }
 
+#if defined(__CUDACC__)
+// exp(x) without a special-case path.  The library exp() ends its basic block with a range branch, so the six
+// exponentials of a ThreeStateMorse evaluation ran as six serial dependency chains (ncu, profiles/r02: 21 % of the RPSH
+// kernel's samples); this one is straight-line code and several of them overlap.  n = rint(x log2 e) by the 1.5 * 2^52 shift (the
+// exponent is clamped to the normal range: 2^-1022 instead of a subnormal or zero, 2^1023 x 1.. instead of +inf),
+// Cody-Waite reduction r = x - n ln2 with the fdlibm constants, Taylor polynomial of degree 13 on |r| <= ln2 / 2
+// (truncation 6e-18 relative), 2^n through the exponent field.  Within 1 ulp of the library function.
+NQ_D double exp_nb(double x) {
+    const double shift = 6755399441055744.0;
+    const double t = fma(x, 1.4426950408889634074, shift);
+    const int n = min(max(__double2loint(t), -1022), 1023);
+    const double fn = t - shift;
+    double r = fma(fn, -6.93147180369123816490e-01, x);
+    r = fma(fn, -1.90821492927058770002e-10, r);
+    double q = 1.0 / 6227020800.0;
+    q = fma(q, r, 1.0 / 479001600.0);
+    q = fma(q, r, 1.0 / 39916800.0);
+    q = fma(q, r, 1.0 / 3628800.0);
+    q = fma(q, r, 1.0 / 362880.0);
+    q = fma(q, r, 1.0 / 40320.0);
+    q = fma(q, r, 1.0 / 5040.0);
+    q = fma(q, r, 1.0 / 720.0);
+    q = fma(q, r, 1.0 / 120.0);
+    q = fma(q, r, 1.0 / 24.0);
+    q = fma(q, r, 1.0 / 6.0);
+    q = fma(q, r, 0.5);
+    q = fma(q, r, 1.0);
+    q = fma(q, r, 1.0);
+    return q * __hiloint2double((n + 1023) << 20, 0);
+}
+// a / b given rb = 1 / b: product + one residual correction (no slow-path branch)
+NQ_D double div_nb(double a, double b, double rb) {
+    const double q = a * rb;
+    return fma(fma(-q, b, a), rb, q);
+}
+#endif
+
 }  // namespace nq

@@ -59,6 +59,7 @@ struct Emitter {
     double* smem;    // [2][kBlockThreads/32]
     int slot;
     bool fresh = true;   // first emit of this save point
+    int nw = kBlockThreads / 32;   // warps per block
     NQ_D void emit(int obs_id, int k, double val) {
         // The two scratch rows alternate, so an emit never overwrites the row thread 0 is still summing from the
         // previous emit -- except across save points (every Emitter starts at row 0, and the previous save may have
@@ -68,12 +69,11 @@ struct Emitter {
         if (p.obs_traj != nullptr && active) p.obs_traj[off * p.ntraj + traj] = val;
         const double ws = warp_sum(active ? val : 0.0);
         const int warp = threadIdx.x >> 5;
-        if ((threadIdx.x & 31) == 0) smem[slot * (kBlockThreads / 32) + warp] = ws;
+        if ((threadIdx.x & 31) == 0) smem[slot * nw + warp] = ws;
         __syncthreads();
         if (threadIdx.x == 0) {
             double tot = 0.0;
-#pragma unroll
-            for (int w = 0; w < kBlockThreads / 32; ++w) tot += smem[slot * (kBlockThreads / 32) + w];
+            for (int w = 0; w < nw; ++w) tot += smem[slot * nw + w];
             atomicAdd(&p.obs_sum[(int64_t)(blockIdx.x % kObsReplicas) * p.layout.total + off], tot);
         }
         slot ^= 1;

@@ -121,7 +121,8 @@ __global__ void __launch_bounds__(kBlockThreads) nrpmd_step_kernel(const __grid_
     for (int is = 0; is < p.nsteps; ++is) {
         const int64_t step = p.step0 + is;
         frp.step(r, v);
-        nrpmd_potential<M>(p, r, Vp);
+        double dVp[sym_size(N)];
+        model_value_and_derivative<M>(p.params, r, Vp, dVp);    // V and dV/dr at the same r: shared transcendentals
         Eig<N> e;
         sym_eigh<N>(Vp, e);
         double vbar = 0.0;
@@ -150,8 +151,7 @@ __global__ void __launch_bounds__(kBlockThreads) nrpmd_step_kernel(const __grid_
             q[j] = sq; pm[j] = sp;
         }
         // nuclear kick: W = Z'(dV - Dbar I)Z ; Gamma, Xi (ringpolymer_mint.jl:107-121)
-        double dVp[sym_size(N)], Ap[sym_size(N)];
-        M::derivative_dof(p.params, r, 0.0, 0.0, dVp);
+        double Ap[sym_size(N)];
         double dbar = 0.0;
 #pragma unroll
         for (int i = 0; i < N; ++i) dbar += dVp[sidx(N, i, i)];

@@ -21,13 +21,29 @@ namespace nq {
 #if defined(__CUDACC__)
 
 constexpr int kRtThreads = kBlockThreads;   // 128 (the Emitter's block reduction is sized for it)
-#ifndef RT_MIN_BLOCKS
-#define RT_MIN_BLOCKS 3   // 168 registers: three blocks (12 warps) per SM hide the serial Jacobi chains better than 255 registers without spills (measured: 8.4e8 -> 9.0e8; four blocks: slower)
-#endif
+constexpr int kRpshMaxThreads = 384;   // ring_tpt_step_kernel: ONE block per SM, up to 12 warps at 168 registers
 
 // fft: nbeads is a power of two (compile-time NBT); otherwise the dense normal-mode product through two scratch rows
-NQ_HD constexpr size_t ring_tpt_smem_bytes(int N, int NB, bool ehrenfest, bool fft) {
-    return ((size_t)(3 + (ehrenfest ? N * N : 0) + (fft ? 0 : 2)) * NB * kRtThreads + (fft ? 6 * NB : NB * NB + 4 * NB)) * sizeof(double);
+NQ_HD constexpr size_t ring_tpt_smem_bytes(int N, int NB, bool ehrenfest, bool fft, int threads = kRtThreads) {
+    return ((size_t)(3 + (ehrenfest ? N * N : 0) + (fft ? 0 : 2)) * NB * threads + (fft ? 6 * NB : NB * NB + 4 * NB)) * sizeof(double);
+}
+
+// Block size of ring_tpt_step_kernel for a batch of ntraj trajectories on `sms` SMs: the kernel runs one block per SM and
+// a trajectory cannot be split, so the batch takes ceil(blocks / sms) waves whatever the block size -- pick the size
+// (a multiple of 32 up to kRpshMaxThreads and up to what shared memory holds) that minimises waves x time per wave, with
+// the time per wave of a block of w warps ~ (w + 4) (FP64 latency hiding saturates slowly: 8 warps 1.52e9, 12 warps
+// 1.50e9 trajectory-steps/s on whole waves).  BASELINE config 5, 10^5 trajectories on 148 SMs: 352 threads, 2 waves
+// (96 % full) instead of 3 waves of 256 (88 %).
+inline int ring_tpt_block_threads(int64_t ntraj, int sms, int max_threads) {
+    int best = 32;
+    double best_cost = 1e300;
+    for (int b = 32; b <= max_threads; b += 32) {
+        const int64_t blocks = (ntraj + b - 1) / b;
+        const int64_t waves = (blocks + sms - 1) / sms;
+        const double cost = (double)waves * (b / 32 + 4);
+        if (cost < best_cost - 1e-12) { best_cost = cost; best = b; }
+    }
+    return best;
 }
 
 template <int NB>
@@ -210,7 +226,7 @@ NQ_D void rt_record_save(const KParams& p, Emitter& em, int NB, const double* s_
 
 // NBT > 0: nbeads = NBT, a power of two (FFT in registers).  NBT == 0: any nbeads (p.B), dense normal-mode product.
 template <class M, int NBT, int METHOD>
-__global__ void __launch_bounds__(kRtThreads, RT_MIN_BLOCKS) ring_tpt_step_kernel(const __grid_constant__ KParams p) {
+__global__ void __launch_bounds__(kRpshMaxThreads, 1) ring_tpt_step_kernel(const __grid_constant__ KParams p) {
     constexpr int N = M::NS;
     constexpr bool EHR = (METHOD == NQCB200_METHOD_EHRENFEST);
     constexpr bool FFT = NBT > 0;
@@ -218,25 +234,26 @@ __global__ void __launch_bounds__(kRtThreads, RT_MIN_BLOCKS) ring_tpt_step_kerne
     constexpr int NBF = FFT ? NBT : 2;      // array extent of the FFT path (unused when dense)
     const int NB = FFT ? NBT : p.B;
     extern __shared__ __align__(16) double rt_sm[];
-    __shared__ double red[2 * (kRtThreads / 32)];
+    __shared__ double red[2 * (kRpshMaxThreads / 32)];
+    const int KT = blockDim.x;      // chosen on the host (ring_tpt_block_threads): whole waves, at most 12 warps
     double* s_r = rt_sm;
-    double* s_v = s_r + NB * kRtThreads;
-    double* s_a = s_v + NB * kRtThreads;
-    double* s_Z = s_a + NB * kRtThreads;                       // EHR only: [bead][N*N][thread]
-    double* s_t = s_Z + (EHR ? N * N * NB * kRtThreads : 0);    // dense only: two scratch rows [2][bead][thread]
-    double* s_tab = s_t + (FFT ? 0 : 2 * NB * kRtThreads);      // FFT: twr[NB/2] twi[NB/2] al[2NB] be[2NB]; dense: U[NB*NB] cay[4NB]
+    double* s_v = s_r + NB * KT;
+    double* s_a = s_v + NB * KT;
+    double* s_Z = s_a + NB * KT;                       // EHR only: [bead][N*N][thread]
+    double* s_t = s_Z + (EHR ? N * N * NB * KT : 0);    // dense only: two scratch rows [2][bead][thread]
+    double* s_tab = s_t + (FFT ? 0 : 2 * NB * KT);      // FFT: twr[NB/2] twi[NB/2] al[2NB] be[2NB]; dense: U[NB*NB] cay[4NB]
     const int tid = threadIdx.x;
-    int64_t traj = (int64_t)blockIdx.x * kRtThreads + tid;
+    int64_t traj = (int64_t)blockIdx.x * KT + tid;
     const bool valid = traj < p.ntraj;
     if (!valid) traj = p.ntraj - 1;
     const int64_t T = p.ntraj;
 
     // coefficient tables (thread-uniform)
     if (!FFT) {
-        for (int i = tid; i < NB * NB; i += kRtThreads) s_tab[i] = p.nm_to[i];            // U[j,k] at j*NB + k
-        for (int i = tid; i < 4 * NB; i += kRtThreads) s_tab[NB * NB + i] = p.cayley[i];
+        for (int i = tid; i < NB * NB; i += KT) s_tab[i] = p.nm_to[i];            // U[j,k] at j*NB + k
+        for (int i = tid; i < 4 * NB; i += KT) s_tab[NB * NB + i] = p.cayley[i];
     }
-    for (int j = tid; FFT && j < NB; j += kRtThreads) {
+    for (int j = tid; FFT && j < NB; j += KT) {
         if (j < NB / 2) {
             double si, co;
             sincospi(-2.0 * (double)j / (double)NB, &si, &co);
@@ -250,17 +267,17 @@ __global__ void __launch_bounds__(kRtThreads, RT_MIN_BLOCKS) ring_tpt_step_kerne
     RtTables<NBF> tb{s_tab, s_tab + NB / 2, s_tab + NB, s_tab + 3 * NB};
 
     for (int b = 0; b < NB; ++b) {
-        s_r[b * kRtThreads + tid] = p.r[(int64_t)b * T + traj];
-        s_v[b * kRtThreads + tid] = p.v[(int64_t)b * T + traj];
-        s_a[b * kRtThreads + tid] = p.acc[(int64_t)b * T + traj];
+        s_r[b * KT + tid] = p.r[(int64_t)b * T + traj];
+        s_v[b * KT + tid] = p.v[(int64_t)b * T + traj];
+        s_a[b * KT + tid] = p.acc[(int64_t)b * T + traj];
         if (EHR) {
             for (int jk = 0; jk < N * N; ++jk)
-                s_Z[(b * N * N + jk) * kRtThreads + tid] = p.Zprev[((int64_t)b * N * N + jk) * T + traj];
+                s_Z[(b * N * N + jk) * KT + tid] = p.Zprev[((int64_t)b * N * N + jk) * T + traj];
         }
     }
     __syncthreads();
 
-    const double mass = p.masses[0];
+    const double mass = p.masses[0], rmass = 1.0 / mass;
     Herm<N> s;
 #pragma unroll
     for (int j = 0; j < N; ++j)
@@ -293,41 +310,45 @@ __global__ void __launch_bounds__(kRtThreads, RT_MIN_BLOCKS) ring_tpt_step_kerne
         const int64_t step = p.step0 + is;
         const double t = p.t0 + dt * (double)step;
         const double tcur = (step == 0) ? 0.0 : t;   // Q1
+        // one barrier per step keeps the block's warps inside the same ~15 KB of code (the step loop is ~60 KB of SASS
+        // against a 32 KB instruction cache: ncu showed `no_instruction` as the largest stall, 25 % of all samples,
+        // spread evenly; with the barrier +13 %, profiles/r02/SUMMARY.md)
+        __syncthreads();
         // B (half kick) + C (free ring polymer)  bcb_electronics.jl:62-71
         if constexpr (FFT) {
             double zr[NBF], zi[NBF];
 #pragma unroll
             for (int b = 0; b < NBF; ++b) {
-                zr[b] = s_r[b * kRtThreads + tid];
-                zi[b] = fma(hdt, s_a[b * kRtThreads + tid], s_v[b * kRtThreads + tid]);
+                zr[b] = s_r[b * KT + tid];
+                zi[b] = fma(hdt, s_a[b * KT + tid], s_v[b * KT + tid]);
             }
             rt_free_step<NBF>(tb, zr, zi);
 #pragma unroll
-            for (int b = 0; b < NBF; ++b) { s_r[b * kRtThreads + tid] = zr[b]; s_v[b * kRtThreads + tid] = zi[b]; }
+            for (int b = 0; b < NBF; ++b) { s_r[b * KT + tid] = zr[b]; s_v[b * KT + tid] = zi[b]; }
         } else {
             // dense U' .. Cayley .. U (RingPolymerArrays transform!, steps.jl:10-17)
             const double* U = s_tab;
             const double* cay = s_tab + NB * NB;
-            for (int b = 0; b < NB; ++b) s_v[b * kRtThreads + tid] = fma(hdt, s_a[b * kRtThreads + tid], s_v[b * kRtThreads + tid]);
+            for (int b = 0; b < NB; ++b) s_v[b * KT + tid] = fma(hdt, s_a[b * KT + tid], s_v[b * KT + tid]);
             for (int k = 0; k < NB; ++k) {
                 double a = 0.0, c = 0.0;
                 for (int j = 0; j < NB; ++j) {
                     const double u = U[j * NB + k];
-                    a = fma(u, s_r[j * kRtThreads + tid], a);
-                    c = fma(u, s_v[j * kRtThreads + tid], c);
+                    a = fma(u, s_r[j * KT + tid], a);
+                    c = fma(u, s_v[j * KT + tid], c);
                 }
-                s_t[k * kRtThreads + tid] = cay[4 * k + 0] * a + cay[4 * k + 1] * c;
-                s_t[(NB + k) * kRtThreads + tid] = cay[4 * k + 2] * a + cay[4 * k + 3] * c;
+                s_t[k * KT + tid] = cay[4 * k + 0] * a + cay[4 * k + 1] * c;
+                s_t[(NB + k) * KT + tid] = cay[4 * k + 2] * a + cay[4 * k + 3] * c;
             }
             for (int j = 0; j < NB; ++j) {
                 double a = 0.0, c = 0.0;
                 for (int k = 0; k < NB; ++k) {
                     const double u = U[j * NB + k];
-                    a = fma(u, s_t[k * kRtThreads + tid], a);
-                    c = fma(u, s_t[(NB + k) * kRtThreads + tid], c);
+                    a = fma(u, s_t[k * KT + tid], a);
+                    c = fma(u, s_t[(NB + k) * KT + tid], c);
                 }
-                s_r[j * kRtThreads + tid] = a;
-                s_v[j * kRtThreads + tid] = c;
+                s_r[j * KT + tid] = a;
+                s_v[j * KT + tid] = c;
             }
         }
         // update_cache! on every bead (bcb_electronics.jl:73), force, second half kick
@@ -335,50 +356,96 @@ __global__ void __launch_bounds__(kRtThreads, RT_MIN_BLOCKS) ring_tpt_step_kerne
         double wsum[N];      // sum over beads of the adiabatic energies (potential outputs use the post-hop state)
 #pragma unroll
         for (int i = 0; i < N; ++i) wsum[i] = 0.0;
+        if constexpr (!EHR) {
+            // FSSH: the bead force is -(Z' dV Z)[st, st] (fssh.jl:67-74) -- one eigenvector column, no gauge -- so the beads
+            // are visited two at a time with their Jacobi chains in lock step and without sorting the eigenvectors
+            // (ncu, profiles/r02: the kernel waits on fixed-latency dependencies 39 % of its idle issue slots; the
+            // sorting network was 14 % of the executed instructions)
+            const bool saving = ((step + 1) % p.save_every == 0);
+#pragma unroll 1
+            for (int b = 0; b < NB; b += 2) {
+                const int b1 = FFT ? b + 1 : ((b + 1 < NB) ? b + 1 : b);     // odd bead counts (dense path): the last bead twice
+                const double q0 = s_r[b * KT + tid], q1 = s_r[b1 * KT + tid];
+                double V0[sym_size(N)], dV0[sym_size(N)], V1[sym_size(N)], dV1[sym_size(N)];
+                model_value_and_derivative<M>(p.params, q0, V0, dV0);
+                model_value_and_derivative<M>(p.params, q1, V1, dV1);
+                double w0[N], w1[N], Z0[N][N], Z1[N][N];
+                sym_eigh_pair_unsorted<N>(V0, V1, w0, Z0, w1, Z1);
+                int rk0[N], rk1[N];
+                eig_rank<N>(w0, rk0);
+                eig_rank<N>(w1, rk1);
+                double z0[N], z1[N];
+#pragma unroll
+                for (int a = 0; a < N; ++a) {
+                    z0[a] = 0.0; z1[a] = 0.0;
+#pragma unroll
+                    for (int i = 0; i < N; ++i) { z0[a] = (rk0[i] == st) ? Z0[a][i] : z0[a]; z1[a] = (rk1[i] == st) ? Z1[a][i] : z1[a]; }
+                }
+                double f0 = 0.0, f1 = 0.0;
+#pragma unroll
+                for (int a = 0; a < N; ++a) {
+                    double row0 = 0.0, row1 = 0.0;
+#pragma unroll
+                    for (int c = 0; c < N; ++c) {
+                        row0 += dV0[(a <= c) ? sidx(N, a, c) : sidx(N, c, a)] * z0[c];
+                        row1 += dV1[(a <= c) ? sidx(N, a, c) : sidx(N, c, a)] * z1[c];
+                    }
+                    f0 += z0[a] * row0; f1 += z1[a] * row1;
+                }
+                if (saving) {
+#pragma unroll
+                    for (int k = 0; k < N; ++k) {
+                        double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+                        for (int i = 0; i < N; ++i) { a0 = (rk0[i] == k) ? w0[i] : a0; a1 = (rk1[i] == k) ? w1[i] : a1; }
+                        wsum[k] += a0;
+                        if (FFT || b1 != b) wsum[k] += a1;
+                    }
+                }
+                {
+                    const double acc = div_nb(-f0, mass, rmass);
+                    const double vb = fma(hdt, acc, s_v[b * KT + tid]);
+                    s_a[b * KT + tid] = acc;
+                    s_v[b * KT + tid] = vb;
+                    rsum += q0; vsum += vb;
+                }
+                if (FFT || b1 != b) {
+                    const double acc = div_nb(-f1, mass, rmass);
+                    const double vb = fma(hdt, acc, s_v[b1 * KT + tid]);
+                    s_a[b1 * KT + tid] = acc;
+                    s_v[b1 * KT + tid] = vb;
+                    rsum += q1; vsum += vb;
+                }
+            }
+        } else {
 #pragma unroll 1
         for (int b = 0; b < NB; ++b) {
-            const double q = s_r[b * kRtThreads + tid];
+            const double q = s_r[b * KT + tid];
             double Vp[sym_size(N)], dVp[sym_size(N)];
             Eig<N> eb;
             model_value_and_derivative<M>(p.params, q, Vp, dVp);
             sym_eigh<N>(Vp, eb);
-            double f;
-            if (EHR) {
-                double Zb[N][N];
+            double Zb[N][N];
 #pragma unroll
-                for (int j = 0; j < N; ++j)
+            for (int j = 0; j < N; ++j)
 #pragma unroll
-                    for (int k = 0; k < N; ++k) Zb[j][k] = s_Z[(b * N * N + j + N * k) * kRtThreads + tid];
-                fix_gauge<N>(eb, Zb);
+                for (int k = 0; k < N; ++k) Zb[j][k] = s_Z[(b * N * N + j + N * k) * KT + tid];
+            fix_gauge<N>(eb, Zb);
 #pragma unroll
-                for (int j = 0; j < N; ++j)
+            for (int j = 0; j < N; ++j)
 #pragma unroll
-                    for (int k = 0; k < N; ++k) s_Z[(b * N * N + j + N * k) * kRtThreads + tid] = Zb[j][k];
-                double Ab[sym_size(N)];
-                similarity<N>(dVp, eb.Z, Ab);
-                f = force_from_adiab<N, METHOD>(Ab, st, s);
-            } else {
-                // -(Z' dV Z)[st, st]: only the eigenvector of the occupied state is needed (fssh.jl:67-74)
-                double z[N];
-#pragma unroll
-                for (int a = 0; a < N; ++a) z[a] = select<N>(eb.Z[a], st);
-                double acc2 = 0.0;
-#pragma unroll
-                for (int a = 0; a < N; ++a) {
-                    double row = 0.0;
-#pragma unroll
-                    for (int c = 0; c < N; ++c) row += dVp[(a <= c) ? sidx(N, a, c) : sidx(N, c, a)] * z[c];
-                    acc2 += z[a] * row;
-                }
-                f = -acc2;
-            }
+                for (int k = 0; k < N; ++k) s_Z[(b * N * N + j + N * k) * KT + tid] = Zb[j][k];
+            double Ab[sym_size(N)];
+            similarity<N>(dVp, eb.Z, Ab);
+            const double f = force_from_adiab<N, METHOD>(Ab, st, s);
 #pragma unroll
             for (int i = 0; i < N; ++i) wsum[i] += eb.w[i];
             const double acc = f / mass;
-            const double vb = fma(hdt, acc, s_v[b * kRtThreads + tid]);
-            s_a[b * kRtThreads + tid] = acc;
-            s_v[b * kRtThreads + tid] = vb;
+            const double vb = fma(hdt, acc, s_v[b * KT + tid]);
+            s_a[b * KT + tid] = acc;
+            s_v[b * KT + tid] = vb;
             rsum += q; vsum += vb;
+        }
         }
         const double rcent = rsum / NB, vcent = vsum / NB;
         eval_point<M>(p, rcent, Zc, ec, Ac);
@@ -435,7 +502,7 @@ __global__ void __launch_bounds__(kRtThreads, RT_MIN_BLOCKS) ring_tpt_step_kerne
                     }
                 }
                 if (dv != 0.0) {
-                    for (int b = 0; b < NB; ++b) s_v[b * kRtThreads + tid] += dv;
+                    for (int b = 0; b < NB; ++b) s_v[b * KT + tid] += dv;
                 }
                 if (accept) { st = new_state; nhops += valid; }
             }
@@ -450,20 +517,20 @@ __global__ void __launch_bounds__(kRtThreads, RT_MIN_BLOCKS) ring_tpt_step_kerne
 #pragma unroll
                     for (int i = 0; i < N; ++i) pot += s.x[sidx(N, i, i)] * wsum[i];
                 } else pot = select<N>(wsum, st);
-                Emitter em{p, traj, valid, (int)isave, red, 0};
-                rt_record_save<N, METHOD>(p, em, NB, s_r, s_v, kRtThreads, tid, s, st, ec, pot, mass);
+                Emitter em{p, traj, valid, (int)isave, red, 0, true, KT / 32};
+                rt_record_save<N, METHOD>(p, em, NB, s_r, s_v, KT, tid, s, st, ec, pot, mass);
             }
         }
     }
 
     if (valid) {
         for (int b = 0; b < NB; ++b) {
-            p.r[(int64_t)b * T + traj] = s_r[b * kRtThreads + tid];
-            p.v[(int64_t)b * T + traj] = s_v[b * kRtThreads + tid];
-            p.acc[(int64_t)b * T + traj] = s_a[b * kRtThreads + tid];
+            p.r[(int64_t)b * T + traj] = s_r[b * KT + tid];
+            p.v[(int64_t)b * T + traj] = s_v[b * KT + tid];
+            p.acc[(int64_t)b * T + traj] = s_a[b * KT + tid];
             if (EHR) {
                 for (int jk = 0; jk < N * N; ++jk)
-                    p.Zprev[((int64_t)b * N * N + jk) * T + traj] = s_Z[(b * N * N + jk) * kRtThreads + tid];
+                    p.Zprev[((int64_t)b * N * N + jk) * T + traj] = s_Z[(b * N * N + jk) * KT + tid];
             }
         }
 #pragma unroll

@@ -162,21 +162,28 @@ NQ_HD void model_value_and_derivative(const double* P, double q, double (&V)[sym
     M::template potential_partial<1>(P, rr, zz, zz, true, V);
     M::derivative_dof(P, q, 0.0, 0.0, dV);
 }
+#if defined(__CUDA_ARCH__)
+#define NQ_EXP exp_nb
+#else
+#define NQ_EXP exp
+#endif
 template <>
 NQ_HD void model_value_and_derivative<ModelT<NQCB200_MODEL_THREE_STATE_MORSE>>(const double* P, double q, double (&V)[6], double (&dV)[6]) {
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-        const double ex = exp(-P[3 + i] * (q - P[6 + i]));
+        const double ex = NQ_EXP(-P[3 + i] * (q - P[6 + i]));
         const double e = 1.0 - ex;
         V[sidx(3, i, i)] = 1.0 * (P[i] * e * e + P[9 + i]);
         dV[sidx(3, i, i)] = 2.0 * P[i] * P[3 + i] * ex * (1.0 - ex);
     }
     const double d01 = q - P[18], d02 = q - P[19], d12 = q - P[20];
-    const double g01 = exp(-P[15] * d01 * d01), g02 = exp(-P[16] * d02 * d02), g12 = exp(-P[17] * d12 * d12);
+    const double g01 = NQ_EXP(-P[15] * d01 * d01), g02 = NQ_EXP(-P[16] * d02 * d02), g12 = NQ_EXP(-P[17] * d12 * d12);
     V[sidx(3, 0, 1)] = 1.0 * P[12] * g01; V[sidx(3, 0, 2)] = 1.0 * P[13] * g02; V[sidx(3, 1, 2)] = 1.0 * P[14] * g12;
     dV[sidx(3, 0, 1)] = -2.0 * P[15] * d01 * P[12] * g01;
     dV[sidx(3, 0, 2)] = -2.0 * P[16] * d02 * P[13] * g02;
     dV[sidx(3, 1, 2)] = -2.0 * P[17] * d12 * P[14] * g12;
 }
+
+#undef NQ_EXP
 
 }  // namespace nq

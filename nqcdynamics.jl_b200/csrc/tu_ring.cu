@@ -6,8 +6,19 @@
 
 namespace nq {
 namespace {
+thread_local int t_device = 0;   // device of the handle being created (select_ring_density)
+// block size of ring_tpt_step_kernel (0: the beads of even one warp do not fit in shared memory)
+int tpt_threads(int N, int NB, bool ehr, bool fft, int64_t ntraj) {
+    int max_threads = 0;
+    for (int b = 32; b <= kRpshMaxThreads; b += 32)
+        if (ring_tpt_smem_bytes(N, NB, ehr, fft, b) <= 200 * 1024) max_threads = b;
+    if (max_threads == 0) return 0;
+    int sms = 148;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, t_device) != cudaSuccess || sms <= 0) sms = 148;
+    return ring_tpt_block_threads(ntraj > 0 ? ntraj : 1, sms, max_threads);
+}
 template <class M, int NB>
-bool pick(int method, KernelSet& out, const char* name) {
+bool pick(int method, int64_t ntraj, KernelSet& out, const char* name) {
     if (method == NQCB200_METHOD_FSSH) {
         out.step = ring_step_kernel<M, NB, NQCB200_METHOD_FSSH>;
         out.init = ring_init_kernel<M, NB, NQCB200_METHOD_FSSH>;
@@ -21,48 +32,49 @@ bool pick(int method, KernelSet& out, const char* name) {
     const char* env = getenv("NQCB200_RING_TPT");
     const bool want = !(env && atoi(env) == 0);
     const bool ehr = (method == NQCB200_METHOD_EHRENFEST);
-    const size_t bytes = ring_tpt_smem_bytes(M::NS, NB, ehr, true);
-    if (want && bytes <= 200 * 1024) {
+    const int threads = tpt_threads(M::NS, NB, ehr, true, ntraj);
+    if (want && threads > 0) {
         if (ehr) out.step = ring_tpt_step_kernel<M, NB, NQCB200_METHOD_EHRENFEST>;
         else out.step = ring_tpt_step_kernel<M, NB, NQCB200_METHOD_FSSH>;
-        out.step_L = 1; out.step_block = kRtThreads; out.step_smem = bytes;
+        out.step_L = 1; out.step_block = threads; out.step_smem = ring_tpt_smem_bytes(M::NS, NB, ehr, true, threads);
     }
     return true;
 }
 // any other nbeads: thread-per-trajectory init + step with the dense normal-mode product
 template <class M>
-bool pick_generic(int method, int B, KernelSet& out, const char* name) {
+bool pick_generic(int method, int B, int64_t ntraj, KernelSet& out, const char* name) {
     const bool ehr = (method == NQCB200_METHOD_EHRENFEST);
     if (method != NQCB200_METHOD_FSSH && !ehr) return false;
-    const size_t bytes = ring_tpt_smem_bytes(M::NS, B, ehr, false);
-    if (B < 2 || bytes > 200 * 1024) return false;
+    const int threads = tpt_threads(M::NS, B, ehr, false, ntraj);
+    if (B < 2 || threads == 0) return false;
     if (ehr) { out.step = ring_tpt_step_kernel<M, 0, NQCB200_METHOD_EHRENFEST>; out.init = ring_tpt_init_kernel<M, NQCB200_METHOD_EHRENFEST>; }
     else { out.step = ring_tpt_step_kernel<M, 0, NQCB200_METHOD_FSSH>; out.init = ring_tpt_init_kernel<M, NQCB200_METHOD_FSSH>; }
     out.L = 1; out.DPL = 1; out.name = name;
-    out.step_L = 1; out.step_block = kRtThreads; out.step_smem = bytes;
+    out.step_L = 1; out.step_block = threads; out.step_smem = ring_tpt_smem_bytes(M::NS, B, ehr, false, threads);
     return true;
 }
 template <class M>
-bool pick_beads(int method, int B, KernelSet& out, const char* name) {
+bool pick_beads(int method, int B, int64_t ntraj, KernelSet& out, const char* name) {
     switch (B) {
-        case 2: return pick<M, 2>(method, out, name);
-        case 4: return pick<M, 4>(method, out, name);
-        case 8: return pick<M, 8>(method, out, name);
-        case 16: return pick<M, 16>(method, out, name);
-        case 32: return pick<M, 32>(method, out, name);
+        case 2: return pick<M, 2>(method, ntraj, out, name);
+        case 4: return pick<M, 4>(method, ntraj, out, name);
+        case 8: return pick<M, 8>(method, ntraj, out, name);
+        case 16: return pick<M, 16>(method, ntraj, out, name);
+        case 32: return pick<M, 32>(method, ntraj, out, name);
     }
-    return pick_generic<M>(method, B, out, name);
+    return pick_generic<M>(method, B, ntraj, out, name);
 }
 }  // namespace
 
 bool select_ring_density(const nqcb200_config& c, KernelSet& out, std::string& why) {
     if (c.ndofs != 1) { why = "ring-polymer FSSH/Ehrenfest kernels are instantiated for ndofs == 1"; return false; }
+    t_device = c.device;
     bool ok = false;
     switch (c.model) {
-        case NQCB200_MODEL_TULLY_ONE: ok = pick_beads<ModelT<NQCB200_MODEL_TULLY_ONE>>(c.method, c.nbeads, out, "rp_tully1"); break;
-        case NQCB200_MODEL_TULLY_TWO: ok = pick_beads<ModelT<NQCB200_MODEL_TULLY_TWO>>(c.method, c.nbeads, out, "rp_tully2"); break;
-        case NQCB200_MODEL_DOUBLE_WELL: ok = pick_beads<ModelT<NQCB200_MODEL_DOUBLE_WELL>>(c.method, c.nbeads, out, "rp_doublewell"); break;
-        case NQCB200_MODEL_THREE_STATE_MORSE: ok = pick_beads<ModelT<NQCB200_MODEL_THREE_STATE_MORSE>>(c.method, c.nbeads, out, "rp_morse3"); break;
+        case NQCB200_MODEL_TULLY_ONE: ok = pick_beads<ModelT<NQCB200_MODEL_TULLY_ONE>>(c.method, c.nbeads, c.ntraj, out, "rp_tully1"); break;
+        case NQCB200_MODEL_TULLY_TWO: ok = pick_beads<ModelT<NQCB200_MODEL_TULLY_TWO>>(c.method, c.nbeads, c.ntraj, out, "rp_tully2"); break;
+        case NQCB200_MODEL_DOUBLE_WELL: ok = pick_beads<ModelT<NQCB200_MODEL_DOUBLE_WELL>>(c.method, c.nbeads, c.ntraj, out, "rp_doublewell"); break;
+        case NQCB200_MODEL_THREE_STATE_MORSE: ok = pick_beads<ModelT<NQCB200_MODEL_THREE_STATE_MORSE>>(c.method, c.nbeads, c.ntraj, out, "rp_morse3"); break;
         default: break;
     }
     if (!ok) why = "ring-polymer kernel: unsupported model, or the beads do not fit in shared memory";
