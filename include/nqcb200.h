@@ -56,6 +56,10 @@ extern "C" {
  * RingPolymerSimulation{FSSH}+BCBwithTsit5 rpsh.jl:8-10,  bcb_electronics.jl:53-97   (nbeads>1)
  * Simulation{Ehrenfest}                    ehrenfest.jl:27-41                        (+RP: nbeads>1)
  * Simulation{AdiabaticIESH}+VerletwithElectronics  iesh.jl:26-87, verlet_with_electronics.jl:42-69
+ * RingPolymerSimulation{AdiabaticIESH} / {EhrenfestNA} + BCBWavefunction  rpiesh.jl:3-52, rpehrenfest_na.jl:3-52,
+ *   bcb_wavefunction.jl:37-69  (METHOD_IESH / METHOD_EHRENFEST_NA with 2 <= nbeads <= 32, ndofs == 1: bead forces from one
+ *   eigenproblem per bead, psi propagated with the centroid eigenvalues / couplings / velocity of the previous geometry,
+ *   centroid hop test, rescaling on every bead; no EDC, no termination mask, no gauge reference)
  * RingPolymerSimulation{Classical}+BCB     classical.jl:40-86, bcb.jl:81-116         (RPMD)
  *   (nbeads==1: Simulation{Classical} + VelocityVerlet, classical.jl:86)
  * RingPolymerSimulation{NRPMD}+RingPolymerMInt  nrpmd.jl:34-45, ringpolymer_mint.jl:28-78     */

@@ -793,12 +793,14 @@ def run_dynamics(sim: Simulation, tspan, distribution, *, output, selection: Opt
                     raise TypeError("EhrenfestNA: FermiDiracState{Diabatic} is defined for AdiabaticIESH only (iesh.jl:138)")
                 psi0 = np.zeros((T, ne, n))
             for t in range(T):
+                # ring polymers: the centroid's eigenvalues / eigenvectors (get_centroid_eigen, test/Dynamics/rpiesh.jl:52)
+                r0 = r[t].reshape(sim.beads, -1).mean(axis=0) if r is not None else None
                 if diabatic_fd:
-                    psi0[t], occ0[t] = electronic.sample_diabatic(rng, model.diabatic_hamiltonian(r[t].reshape(-1)), ne)
+                    psi0[t], occ0[t] = electronic.sample_diabatic(rng, model.diabatic_hamiltonian(r0), ne)
                 elif fd_on_device:       # nqcb200_sample_occupations draws them from the device's own eigenvalues at r0
                     occ0[t] = np.arange(1, ne + 1)
                 else:
-                    occ0[t] = electronic.sample_occupations(rng, model.adiabatic_energies(r[t].reshape(-1)), ne)
+                    occ0[t] = electronic.sample_occupations(rng, model.adiabatic_energies(r0), ne)
         else:
             raise TypeError("AdiabaticIESH / EhrenfestNA take no electronic distribution (ground state) or a FermiDiracState")
         # psi0 stays None for the adiabatic cases: electron e starts in orbital occ0[e], built on the device from the

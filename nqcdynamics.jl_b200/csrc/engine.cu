@@ -764,6 +764,7 @@ int nqcb200_observable_width(const nqcb200_handle* h, int obs_id) {
 int nqcb200_set_gauge_reference(nqcb200_handle* h, const double* Z, int64_t count_per_traj) {
     if (!h || !Z) return NQCB200_ERR_INVALID;
     if (count_per_traj != h->zcopies || h->cfg.nstates < 2) { h->err = "gauge reference: expected nbeads(+1 centroid) matrices per trajectory"; return NQCB200_ERR_INVALID; }
+    if (h->traj_major && h->cfg.nbeads > 1) { h->err = "gauge reference: not available for ring-polymer AdiabaticIESH / EhrenfestNA (identity continuity is used)"; return NQCB200_ERR_UNSUPPORTED; }
     NQ_CUDA(h, cudaSetDevice(h->cfg.device));
     int rc;
     if (h->traj_major) {
@@ -1206,9 +1207,9 @@ int nqcb200_get_diagnostics(nqcb200_handle* h, double* eig, double* nac, double*
         const size_t T = (size_t)h->cfg.ntraj;
         if (eig) NQ_CUDA(h, cudaMemcpyAsync(eig, h->kp.diag_eig, sizeof(double) * T * n, cudaMemcpyDeviceToHost, h->stream));
         if (nac) NQ_CUDA(h, cudaMemcpyAsync(nac, h->kp.diag_nac, sizeof(double) * T * n * n, cudaMemcpyDeviceToHost, h->stream));
-        if (accel) NQ_CUDA(h, cudaMemcpyAsync(accel, h->kp.acc, sizeof(double) * T, cudaMemcpyDeviceToHost, h->stream));
         if (Z) NQ_CUDA(h, cudaMemcpyAsync(Z, h->kp.diag_Z, sizeof(double) * T * n * n, cudaMemcpyDeviceToHost, h->stream));
         NQ_CUDA(h, cudaStreamSynchronize(h->stream));
+        if (accel && (rc = download_field(h, h->kp.acc, accel, h->cfg.nbeads * D)) != 0) return rc;   // [bead][trajectory] like r, v
         return NQCB200_OK;
     }
     if (eig && (rc = download_field(h, h->kp.diag_eig, eig, n)) != 0) return rc;

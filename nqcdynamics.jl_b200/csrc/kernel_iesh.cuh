@@ -90,6 +90,7 @@ NQ_D double iesh_block_max(double x, double* red) {
 struct IeshSmem {
     double *eps, *V2, *Vb, *lam, *mu, *z0, *ws, *sgn, *red, *pop;
     double* fsc;        // [0] coupling scale f(x) of the current geometry (1 for MiaoSubotnik), [1] h(x)
+    double* rp;         // ring polymer (RPIESH / RP-EhrenfestNA): r[32] v[32] acc[32] + 64 doubles of normal-mode scratch
     int *pole, *occ, *un, *flag, *ctl;
     double* work;
     int np;
@@ -97,14 +98,15 @@ struct IeshSmem {
         np = (n + 3) & ~3;
         eps = base; V2 = eps + np; Vb = V2 + np; lam = Vb + np; mu = lam + np; z0 = mu + np; ws = z0 + np;
         sgn = ws + np; pop = sgn + np; red = pop + np; fsc = red + 56;
-        pole = (int*)(red + 64); occ = pole + np; un = occ + np; flag = un + np; ctl = flag + np;
+        rp = red + 64;
+        pole = (int*)(rp + 160); occ = pole + np; un = occ + np; flag = un + np; ctl = flag + np;
         work = (double*)(ctl + 16);
     }
 };
 // doubles needed in front of the work region (host mirror of carve)
 NQ_HD int iesh_small_doubles(int n) {
     const int np = (n + 3) & ~3;
-    return 9 * np + 64 + (4 * np + 16) / 2;
+    return 9 * np + 64 + 160 + (4 * np + 16) / 2;
 }
 
 // Secular function at offset mu from pole p: f = (h - eps_p) - mu - sum_k V_k^2 / ((eps_k - eps_p) - mu),
@@ -320,12 +322,16 @@ NQ_D void iesh_emit(const KParams& p, int64_t traj, int isave, int obs_id, int k
 
 // Estimators at a save point (iesh.jl:337-388).  Every thread of the CTA must call it.
 // zt: zt_cap doubles of scratch shared memory (the psi-chunk region is free at a save point), >= (warps + 9) * roundup(n, 4)
+// Ring polymers (rp_pot >= -inf passed with p.B > 1): r, v are the centroid, S holds the centroid eigenproblem (populations
+// use the centroid transformation like rt_record_save), the kinetic energy sums the beads in S.rp, rp_pot is the bead sum
+// of the potential (rpiesh.jl:38-52, rpehrenfest_na.jl:37-52) and the total adds the spring term (ring_polymer.jl:89-107).
 __device__ __noinline__ void iesh_record_save(const KParams& p, IeshSmem& S, int64_t traj, int isave, double r, double v,
-                           const IeshModel& mdl, const double* psi_re, const double* psi_im, double* zt, int zt_cap) {
+                           const IeshModel& mdl, const double* psi_re, const double* psi_im, double* zt, int zt_cap,
+                           double rp_pot = 0.0) {
     const uint32_t obs = p.observables;
     const int n = p.n, ne = p.ne, tid = threadIdx.x, nt = blockDim.x;
     const bool last = (isave == p.nsave - 1);
-    const bool trans = r > 0.0;
+    const bool trans = ((p.B > 1) ? S.rp[0] : r) > 0.0;      // get_positions(final)[1]: first dof of the first bead
     if (obs & ((1u << NQCB200_OBS_ADIABATIC_POP) | (1u << NQCB200_OBS_SCATTERING))) {
         for (int i = tid; i < n; i += nt) {
             double a = (S.flag[i] >= 0) ? 1.0 : 0.0;                             // iesh.jl:371-375
@@ -427,11 +433,22 @@ __device__ __noinline__ void iesh_record_save(const KParams& p, IeshSmem& S, int
     }
     if (tid == 0) {
         if (obs & ((1u << NQCB200_OBS_KINETIC) | (1u << NQCB200_OBS_POTENTIAL) | (1u << NQCB200_OBS_TOTAL_ENERGY))) {
-            const double kin = (mdl.mass * v * v) / 2.0;
+            double kin = (mdl.mass * v * v) / 2.0;
             double h, dh, u0, du0, fs, dfs;
             mdl.eval(r, h, dh, u0, du0, fs, dfs);
             double pot = u0;                                                      // iesh.jl:380-388
-            if (p.mean_field) {                                                   // ehrenfest_na.jl:103-114
+            double spring = 0.0;
+            if (p.B > 1) {
+                const double* rb = S.rp; const double* vb = S.rp + 32;
+                double mv2 = 0.0, spr = 0.0, rprev = rb[p.B - 1];
+                for (int b = 0; b < p.B; ++b) {
+                    mv2 = fma(mdl.mass * vb[b], vb[b], mv2);
+                    const double d = rprev - rb[b];
+                    spr = fma(mdl.mass * d, d, spr);
+                    rprev = rb[b];
+                }
+                kin = 0.5 * mv2; pot = rp_pot; spring = 0.5 * p.omega_n * p.omega_n * spr;
+            } else if (p.mean_field) {                                            // ehrenfest_na.jl:103-114
                 for (int e = 0; e < ne; ++e)
                     for (int i = 0; i < n; ++i) {
                         const double x = psi_re[(int64_t)n * e + i], y = psi_im[(int64_t)n * e + i];
@@ -441,7 +458,7 @@ __device__ __noinline__ void iesh_record_save(const KParams& p, IeshSmem& S, int
                 for (int e = 0; e < ne; ++e) pot += S.lam[S.occ[e]];
             if (obs & (1u << NQCB200_OBS_KINETIC)) iesh_emit(p, traj, isave, NQCB200_OBS_KINETIC, 0, kin);
             if (obs & (1u << NQCB200_OBS_POTENTIAL)) iesh_emit(p, traj, isave, NQCB200_OBS_POTENTIAL, 0, pot);
-            if (obs & (1u << NQCB200_OBS_TOTAL_ENERGY)) iesh_emit(p, traj, isave, NQCB200_OBS_TOTAL_ENERGY, 0, kin + pot);
+            if (obs & (1u << NQCB200_OBS_TOTAL_ENERGY)) iesh_emit(p, traj, isave, NQCB200_OBS_TOTAL_ENERGY, 0, kin + pot + spring);
         }
         if (obs & (1u << NQCB200_OBS_POSITION)) iesh_emit(p, traj, isave, NQCB200_OBS_POSITION, 0, r);
         if (obs & (1u << NQCB200_OBS_VELOCITY)) iesh_emit(p, traj, isave, NQCB200_OBS_VELOCITY, 0, v);
@@ -777,7 +794,141 @@ __device__ __noinline__ void iesh_eigen_frozen(const KParams& p, IeshSmem& S, co
     iesh_eigen(p, S, h, fs, vnorm, false);
 }
 
+// ---- ring polymers: RingPolymerSimulation{AdiabaticIESH} / {EhrenfestNA} with BCBWavefunction ---------------------
+// (rpiesh.jl:21-52, rpehrenfest_na.jl:13-52, bcb_wavefunction.jl:37-69).  The CTA still owns one trajectory; its beads
+// (positions, velocities, accelerations: CTA-uniform scalars) sit in S.rp.  Per step: half kick + free ring-polymer
+// step (dense normal-mode product on warp 0), one arrowhead eigenproblem per BEAD for the bead force, psi propagated
+// with the centroid generator of the PREVIOUS geometry and velocity (quirk Q5: propagate_wavefunction!(.., vprev, rprev, ..),
+// bcb_wavefunction.jl:67 -- the centroid eigenproblem and G = v.d built at the end of the previous step are exactly that
+// generator, so it is kept in S.ws / G across the bead solves), then the centroid eigenproblem at the new geometry for
+// the hop test (SurfaceHoppingMethods.jl:85-103: centroid eigenvalues, couplings and velocity; the rescaling moves
+// every bead by the same amount, rpsh.jl:30-50).  All geometries share the column signs S.sgn: for the arrowhead
+// matrix the sign that "continuity with the identity" picks is sign(V_{i-1}) whatever the impurity level.
+
+// acceleration of the geometry whose eigenproblem is in S (iesh.jl:190-207 / ehrenfest_na.jl:72-90); every thread
+NQ_D double iesh_acceleration(const KParams& p, const IeshSmem& S, const IeshModel& mdl, const double* psi_re,
+                              const double* psi_im, double h, double dh, double du0, double phi) {
+    double w1, w2 = 0.0;
+    if (p.mean_field) w1 = iesh_mean_field_weight(p, S, psi_re, psi_im, mdl.erp, h, w2);
+    else {
+        double part = 0.0, part2 = 0.0;
+        for (int e = threadIdx.x; e < p.ne; e += blockDim.x) {
+            const int o = S.occ[e];
+            const double z = S.z0[o];
+            part += z * z;
+            if (mdl.erp) part2 = fma(z * z, S.lam[o] - h, part2);
+        }
+        w1 = iesh_block_sum(part, S.red);
+        if (mdl.erp) w2 = iesh_block_sum(part2, S.red);
+    }
+    return ((-du0 - dh * w1) - 2.0 * phi * w2) / mdl.mass;
+}
+
+// G = v.d of the eigenproblem in S into Gdst (same element formula as the step kernel's build), shifted eigenvalues
+// into S.ws; returns the shift, the half spectral width, ||G||_F and sum |v.d[m, e]| (unoccupied m, occupied e)
+NQ_D void iesh_build_generator(const KParams& p, IeshSmem& S, const IeshModel& mdl, double* Gdst, double h, double dh,
+                               double phi, double v, double& sigma, double& wspan, double& gnorm, double& sabs_out) {
+    const int n = p.n, tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+    const int ldg = p.iesh.ldg;
+    const double wmin = S.lam[0], wmax = S.lam[n - 1];
+    sigma = 0.5 * (wmin + wmax);
+    wspan = 0.5 * (wmax - wmin);
+    __syncthreads();                 // the previous generator's S.ws / G have been consumed
+    for (int i = tid; i < n; i += nt) S.ws[i] = S.lam[i] - sigma;
+    const double gpref = -v * dh;
+    double g2 = 0.0, sabs = 0.0;
+    for (int j = warp; j < n; j += nwarps) {
+        const double zj = S.z0[j] * gpref, ej = S.eps[S.pole[j]], mj = S.mu[j];
+        const double zje = -v * S.z0[j] * phi, wj = S.lam[j] - h;
+        const bool occ_j = S.flag[j] >= 0;
+        for (int i = lane; i < n; i += 32) {
+            double g = 0.0;
+            if (i != j) {
+                const double num = mdl.erp ? fma(zje, (S.lam[i] - h) + wj, zj) : zj;
+                g = num * S.z0[i] * iesh_rcp((S.eps[S.pole[i]] - ej) + (S.mu[i] - mj));
+                if (occ_j && S.flag[i] < 0) sabs += fabs(g);
+            }
+            g2 = fma(g, g, g2);
+            Gdst[i + (int64_t)ldg * j] = g;
+        }
+    }
+    gnorm = sqrt(iesh_block_sum(g2, S.red));
+    sabs_out = iesh_block_sum(sabs, S.red);
+}
+
+// Taylor plan of the propagator (same rule as the step kernel): nsub sub-steps, K stages, the first Kg of them with G
+NQ_D void iesh_taylor_plan(double dt, double wspan, double gnorm, int& nsub, double& dts, int& K, int& Kg) {
+    const double rho_full = dt * (wspan + gnorm);
+    nsub = max(1, (int)ceil(rho_full / 4.0));
+    dts = dt / nsub;
+    const double rho = rho_full / nsub, rho_g = dts * gnorm;
+    K = 1; Kg = (rho_g >= 1e-18) ? 1 : 0;
+    double term = rho;
+    while (term > 1e-17 && K < 90) {
+        ++K;
+        if (rho_g * term / K >= 1e-18) Kg = K;
+        term *= rho / K;
+    }
+}
+
+// B (half kick) + C (free ring polymer) of BCBWavefunction on the beads in S.rp: dense U' . Cayley . U on warp 0
+// (RingPolymerArrays transform!, steps.jl:10-17; the engine's nm_to / cayley tables, full step).  Ends with a barrier.
+NQ_D void iesh_rp_free_step(const KParams& p, IeshSmem& S, double hdt) {
+    const int B = p.B, lane = threadIdx.x & 31;
+    double* rb = S.rp; double* vb = S.rp + 32; double* ab = S.rp + 64; double* tn = S.rp + 96;
+    if (threadIdx.x < 32) {
+        if (lane < B) vb[lane] = fma(hdt, ab[lane], vb[lane]);
+        __syncwarp();
+        if (lane < B) {
+            double a = 0.0, c = 0.0;
+            for (int j = 0; j < B; ++j) { const double u = p.nm_to[j * B + lane]; a = fma(u, rb[j], a); c = fma(u, vb[j], c); }
+            tn[lane] = p.cayley[4 * lane + 0] * a + p.cayley[4 * lane + 1] * c;
+            tn[32 + lane] = p.cayley[4 * lane + 2] * a + p.cayley[4 * lane + 3] * c;
+        }
+        __syncwarp();
+        if (lane < B) {
+            double a = 0.0, c = 0.0;
+            for (int k = 0; k < B; ++k) { const double u = p.nm_to[lane * B + k]; a = fma(u, tn[k], a); c = fma(u, tn[32 + k], c); }
+            rb[lane] = a; vb[lane] = c;
+        }
+    }
+    __syncthreads();
+}
+
+// bead sum of the potential (rpiesh.jl:38-52 / rpehrenfest_na.jl:37-52).  Overwrites S with the last bead's
+// eigenproblem: the caller re-solves the centroid afterwards.  Every thread gets the sum.
+NQ_D double iesh_rp_potential(const KParams& p, IeshSmem& S, const IeshModel& mdl, const double* psi_re,
+                              const double* psi_im, double vnorm) {
+    const int n = p.n, ne = p.ne, tid = threadIdx.x, nt = blockDim.x;
+    double pot = 0.0;
+    for (int b = 0; b < p.B; ++b) {
+        double h, dh, u0, du0, fs, dfs;
+        mdl.eval(S.rp[b], h, dh, u0, du0, fs, dfs);
+        iesh_eigen(p, S, h, fs, vnorm, false);
+        double part = 0.0;
+        if (p.mean_field) {
+            for (int idx = tid; idx < n * ne; idx += nt) {
+                const int i = idx % n;
+                part = fma(S.lam[i], psi_re[idx] * psi_re[idx] + psi_im[idx] * psi_im[idx], part);
+            }
+        } else
+            for (int e = tid; e < ne; e += nt) part += S.lam[S.occ[e]];
+        pot += u0 + iesh_block_sum(part, S.red);
+    }
+    return pot;
+}
+
+// centroid of the beads in S.rp (same summation order on every thread)
+NQ_D void iesh_rp_centroid(const KParams& p, const IeshSmem& S, double& r, double& v) {
+    double sr = 0.0, sv = 0.0;
+    for (int b = 0; b < p.B; ++b) { sr += S.rp[b]; sv += S.rp[32 + b]; }
+    r = sr / p.B; v = sv / p.B;
+}
+
 // ---- the step kernel -----------------------------------------------------------------------------
+// RP = false: Simulation{AdiabaticIESH / EhrenfestNA} (VerletwithElectronics); RP = true: the ring-polymer variants
+// (BCBWavefunction).  The RP = false instantiation contains none of the ring-polymer code.
+template <bool RP>
 __global__ void __launch_bounds__(384, 1) iesh_step_kernel(const __grid_constant__ KParams p) {
     extern __shared__ __align__(16) double iesh_sm[];
     IeshSmem S;
@@ -808,6 +959,21 @@ __global__ void __launch_bounds__(384, 1) iesh_step_kernel(const __grid_constant
         iesh_refresh_unoccupied(p, S);
         double r = p.r[traj], v = p.v[traj], acc = p.acc[traj];
         const bool orth_ok = p.iesh_orth[traj] != 0.0;
+        // RP: generator of the next propagation = centroid eigenproblem and G = v.d of the current geometry and velocity
+        double g_sigma = 0.0, g_wspan = 0.0, g_gnorm = 0.0, g_sabs = 0.0;
+        if constexpr (RP) {
+            if (tid < p.B) {
+                S.rp[tid] = p.r[(int64_t)tid * p.ntraj + traj];
+                S.rp[32 + tid] = p.v[(int64_t)tid * p.ntraj + traj];
+                S.rp[64 + tid] = p.acc[(int64_t)tid * p.ntraj + traj];
+            }
+            __syncthreads();
+            iesh_rp_centroid(p, S, r, v);
+            double h, dh, u0, du0, fs, dfs;
+            mdl.eval(r, h, dh, u0, du0, fs, dfs);
+            iesh_eigen(p, S, h, fs, vnorm, false);
+            iesh_build_generator(p, S, mdl, L.resident ? Gs : Gglob, h, dh, dfs / fs, v, g_sigma, g_wspan, g_gnorm, g_sabs);
+        }
 
 #pragma unroll 1
         for (int is = 0; is < p.nsteps; ++is) {
@@ -820,13 +986,15 @@ __global__ void __launch_bounds__(384, 1) iesh_step_kernel(const __grid_constant
                 goto save_point;
             }
             {
+            double h, dh, u0, du0, fs, dfs, phi, sabs, sigma, dts;
+            int nsub, K, Kg;
+            if constexpr (!RP) {
             // ---- nuclei + eigen + force (verlet_with_electronics.jl:55-66) -------------------------
             const double vt = fma(hdt, acc, v);
             r = fma(dt, vt, r);
-            double h, dh, u0, du0, fs, dfs;
             mdl.eval(r, h, dh, u0, du0, fs, dfs);
             iesh_eigen(p, S, h, fs, vnorm, false);
-            const double phi = dfs / fs;              // f'/f: (Z' dH Z)_ij = z0_i z0_j [h' + phi (w_i + w_j - 2h)]
+            phi = dfs / fs;              // f'/f: (Z' dH Z)_ij = z0_i z0_j [h' + phi (w_i + w_j - 2h)]
             if (p.mean_field) {
                 double wsum2 = 0.0;
                 const double wsum = iesh_mean_field_weight(p, S, psi_re, psi_im, mdl.erp, h, wsum2);  // sigma_prev: psi before this step's propagation
@@ -847,10 +1015,11 @@ __global__ void __launch_bounds__(384, 1) iesh_step_kernel(const __grid_constant
 
             // ---- G = v.d, shift, norms ------------------------------------------------------------
             const double wmin = S.lam[0], wmax = S.lam[n - 1];
-            const double sigma = 0.5 * (wmin + wmax);
+            sigma = 0.5 * (wmin + wmax);
             for (int i = tid; i < n; i += nt) S.ws[i] = S.lam[i] - sigma;
             const double gpref = -v * dh;
-            double g2 = 0.0, sabs = 0.0;
+            double g2 = 0.0;
+            sabs = 0.0;
             {
                 double* Gdst = L.resident ? Gs : Gglob;
                 // thread -> (row i fastest); one division per element, w_i - w_j from pole offsets
@@ -875,9 +1044,10 @@ __global__ void __launch_bounds__(384, 1) iesh_step_kernel(const __grid_constant
             const double wspan = 0.5 * (wmax - wmin);
             // Taylor plan: nsub sub-steps of dt/nsub; K stages (remainder < 1e-17), the first Kg of them with G
             const double rho_full = dt * (wspan + gnorm);
-            const int nsub = max(1, (int)ceil(rho_full / 4.0));
-            const double dts = dt / nsub, rho = rho_full / nsub, rho_g = dts * gnorm;
-            int K = 1, Kg = (rho_g >= 1e-18) ? 1 : 0;
+            nsub = max(1, (int)ceil(rho_full / 4.0));
+            dts = dt / nsub;
+            const double rho = rho_full / nsub, rho_g = dts * gnorm;
+            K = 1; Kg = (rho_g >= 1e-18) ? 1 : 0;
             {
                 double term = rho;                       // rho^K / K!
                 while (term > 1e-17 && K < 90) {
@@ -885,6 +1055,20 @@ __global__ void __launch_bounds__(384, 1) iesh_step_kernel(const __grid_constant
                     if (rho_g * term / K >= 1e-18) Kg = K;   // stage K contributes rho_g rho^(K-1) / K!
                     term *= rho / K;
                 }
+            }
+            } else {
+                // ---- BCBWavefunction (bcb_wavefunction.jl:49-66): B, C, update_cache! on every bead, acceleration!, B
+                iesh_rp_free_step(p, S, hdt);
+                for (int b = 0; b < p.B; ++b) {
+                    double hb, dhb, u0b, du0b, fsb, dfsb;
+                    mdl.eval(S.rp[b], hb, dhb, u0b, du0b, fsb, dfsb);
+                    iesh_eigen(p, S, hb, fsb, vnorm, false);
+                    const double ab = iesh_acceleration(p, S, mdl, psi_re, psi_im, hb, dhb, du0b, dfsb / fsb);   // psi: sigma_prev
+                    if (tid == 0) { S.rp[64 + b] = ab; S.rp[32 + b] = fma(hdt, ab, S.rp[32 + b]); }
+                }
+                // propagate_wavefunction!(.., vprev, rprev, ..): the generator left by the previous step (Q5)
+                sigma = g_sigma;
+                iesh_taylor_plan(dt, g_wspan, g_gnorm, nsub, dts, K, Kg);
             }
             nstages += (tid == 0) ? (unsigned long long)K * nsub : 0ull;
             ngemm += (tid == 0) ? (unsigned long long)Kg * nsub : 0ull;
@@ -895,6 +1079,16 @@ __global__ void __launch_bounds__(384, 1) iesh_step_kernel(const __grid_constant
             else if (L.rounds == 1) leak = iesh_propagate<1, 14, 2>(p, S, psi_re, psi_im, Gs, Bs, Gglob, sigma, dts, nsub, K, Kg);
             else leak = iesh_propagate<2, 8, 2>(p, S, psi_re, psi_im, Gs, Bs, Gglob, sigma, dts, nsub, K, Kg);
             __syncthreads();
+            if constexpr (RP) {
+                // hopping quantities of a ring polymer: centroid eigenvalues, couplings, velocity (SurfaceHoppingMethods.jl:85-103)
+                iesh_rp_centroid(p, S, r, v);
+                mdl.eval(r, h, dh, u0, du0, fs, dfs);
+                phi = dfs / fs;
+                iesh_eigen(p, S, h, fs, vnorm, false);
+                iesh_build_generator(p, S, mdl, L.resident ? Gs : Gglob, h, dh, phi, v, g_sigma, g_wspan, g_gnorm, g_sabs);
+                sabs = g_sabs;
+            }
+            const double v_before_hop = v;
 
             // ---- IESHCallback: hop test (iesh.jl:231-335,390-407) ----------------------------------
             if (!p.disable_hopping) {
@@ -1071,6 +1265,16 @@ __global__ void __launch_bounds__(384, 1) iesh_step_kernel(const __grid_constant
                 __syncthreads();
             }
 
+            if constexpr (RP) {
+                if (v != v_before_hop) {      // rescaling / velocity inversion: the same change on every bead (rpsh.jl:30-50)
+                    const double dv = v - v_before_hop;
+                    __syncthreads();
+                    if (tid < p.B) S.rp[32 + tid] += dv;
+                    __syncthreads();
+                    iesh_rp_centroid(p, S, r, v);
+                    iesh_build_generator(p, S, mdl, L.resident ? Gs : Gglob, h, dh, phi, v, g_sigma, g_wspan, g_gnorm, g_sabs);
+                }
+            }
             // ---- EDC decoherence (decoherence_corrections.jl:21-38) -----------------------------------
             if (p.edc_C > 0.0) {
                 const double Ekin = (mdl.mass * v * v) / 2.0;
@@ -1105,13 +1309,30 @@ __global__ void __launch_bounds__(384, 1) iesh_step_kernel(const __grid_constant
             // ---- save (after the callback) ---------------------------------------------
             if ((step + 1) % p.save_every == 0) {
                 const int64_t isave = (step + 1) / p.save_every;
-                if (isave < p.nsave) iesh_record_save(p, S, traj, (int)isave, r, v, mdl, psi_re, psi_im, Bs, L.work_doubles - L.off_b);
+                if (isave < p.nsave) {
+                    double rp_pot = 0.0;
+                    if constexpr (RP) {
+                        if (p.observables & ((1u << NQCB200_OBS_POTENTIAL) | (1u << NQCB200_OBS_TOTAL_ENERGY))) {
+                            rp_pot = iesh_rp_potential(p, S, mdl, psi_re, psi_im, vnorm);
+                            double h, dh, u0, du0, fs, dfs;
+                            mdl.eval(r, h, dh, u0, du0, fs, dfs);
+                            iesh_eigen(p, S, h, fs, vnorm, false);       // back to the centroid (estimators, next generator's roots)
+                        }
+                    }
+                    iesh_record_save(p, S, traj, (int)isave, r, v, mdl, psi_re, psi_im, Bs, L.work_doubles - L.off_b, rp_pot);
+                }
             }
         }
         __syncthreads();
         for (int i = tid; i < n; i += nt) p.iesh_lam[traj * n + i] = S.lam[i];
         for (int e = tid; e < ne; e += nt) p.state[traj * ne + e] = S.occ[e];
-        if (tid == 0) { p.r[traj] = r; p.v[traj] = v; p.acc[traj] = acc; }
+        if constexpr (RP) {
+            if (tid < p.B) {
+                p.r[(int64_t)tid * p.ntraj + traj] = S.rp[tid];
+                p.v[(int64_t)tid * p.ntraj + traj] = S.rp[32 + tid];
+                p.acc[(int64_t)tid * p.ntraj + traj] = S.rp[64 + tid];
+            }
+        } else if (tid == 0) { p.r[traj] = r; p.v[traj] = v; p.acc[traj] = acc; }
         if (p.diagnostics && p.diag_eig) {
             // eigenvalues, NAC d[j,i] (column-major j + n i), eigenvectors of the last evaluated geometry
             double h, dh, u0, du0, fs, dfs;
@@ -1139,6 +1360,7 @@ __global__ void __launch_bounds__(384, 1) iesh_step_kernel(const __grid_constant
 // Initialisation: update_cache!(r0) with a cold root search, gauge signs against the identity
 // (or a user reference Z through p.Zprev, [T][n*n] trajectory-major), initial acceleration
 // (verlet_with_electronics.jl:30-40), save point 0.
+template <bool RP>
 __global__ void __launch_bounds__(384, 1) iesh_init_kernel(const __grid_constant__ KParams p, int user_gauge, int,
                                                           const double*) {
     extern __shared__ __align__(16) double iesh_sm[];
@@ -1155,7 +1377,15 @@ __global__ void __launch_bounds__(384, 1) iesh_init_kernel(const __grid_constant
         for (int i = tid; i < n; i += nt) S.sgn[i] = 1.0;
         for (int e = tid; e < ne; e += nt) S.occ[e] = p.state[traj * ne + e];
         iesh_refresh_unoccupied(p, S);
-        const double r = p.r[traj], v = p.v[traj];
+        double r = p.r[traj], v = p.v[traj];
+        if constexpr (RP) {      // gauge, roots and estimators of a ring polymer: the centroid
+            if (tid < p.B) {
+                S.rp[tid] = p.r[(int64_t)tid * p.ntraj + traj];
+                S.rp[32 + tid] = p.v[(int64_t)tid * p.ntraj + traj];
+            }
+            __syncthreads();
+            iesh_rp_centroid(p, S, r, v);
+        }
         double h, dh, u0, du0, fs, dfs;
         mdl.eval(r, h, dh, u0, du0, fs, dfs);
         const double phi = dfs / fs;
@@ -1172,6 +1402,22 @@ __global__ void __launch_bounds__(384, 1) iesh_init_kernel(const __grid_constant
         __syncthreads();
         for (int i = tid; i < n; i += nt) { S.z0[i] *= S.sgn[i]; p.iesh_sgn[traj * n + i] = S.sgn[i]; p.iesh_lam[traj * n + i] = S.lam[i]; }
         __syncthreads();
+        double rp_pot = 0.0;
+        if constexpr (RP) {
+            // initial acceleration of every bead (bcb_wavefunction.jl:26-35) and the bead sum of the potential
+            for (int b = 0; b < p.B; ++b) {
+                double hb, dhb, u0b, du0b, fsb, dfsb;
+                mdl.eval(S.rp[b], hb, dhb, u0b, du0b, fsb, dfsb);
+                iesh_eigen(p, S, hb, fsb, vnorm, false);
+                const double ab = iesh_acceleration(p, S, mdl, psi_re, psi_im, hb, dhb, du0b, dfsb / fsb);
+                if (tid == 0) p.acc[(int64_t)b * p.ntraj + traj] = ab;
+            }
+            if (p.observables & ((1u << NQCB200_OBS_POTENTIAL) | (1u << NQCB200_OBS_TOTAL_ENERGY)))
+                rp_pot = iesh_rp_potential(p, S, mdl, psi_re, psi_im, vnorm);
+            iesh_eigen(p, S, h, fs, vnorm, false);      // back to the centroid
+            for (int i = tid; i < n; i += nt) p.iesh_lam[traj * n + i] = S.lam[i];
+            __syncthreads();
+        }
         double occsum, occsum2 = 0.0;
         if (p.mean_field) occsum = iesh_mean_field_weight(p, S, psi_re, psi_im, mdl.erp, h, occsum2);
         else {
@@ -1185,8 +1431,8 @@ __global__ void __launch_bounds__(384, 1) iesh_init_kernel(const __grid_constant
             occsum = iesh_block_sum(part, S.red);
             if (mdl.erp) occsum2 = iesh_block_sum(part2, S.red);
         }
-        if (tid == 0) p.acc[traj] = ((-du0 - dh * occsum) - 2.0 * phi * occsum2) / mdl.mass;
-        iesh_record_save(p, S, traj, 0, r, v, mdl, psi_re, psi_im, S.work + p.iesh.off_b, p.iesh.work_doubles - p.iesh.off_b);
+        if (!RP && tid == 0) p.acc[traj] = ((-du0 - dh * occsum) - 2.0 * phi * occsum2) / mdl.mass;
+        iesh_record_save(p, S, traj, 0, r, v, mdl, psi_re, psi_im, S.work + p.iesh.off_b, p.iesh.work_doubles - p.iesh.off_b, rp_pot);
         {
             // are the orbitals orthonormal?  (enables the determinant-free pruning bound of the step kernel)
             double dev = 0.0;

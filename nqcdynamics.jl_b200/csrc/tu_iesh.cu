@@ -68,7 +68,9 @@ bool select_iesh(const nqcb200_config& c, KernelSet& out, std::string& why) {
     if (c.model != NQCB200_MODEL_ANDERSON_HOLSTEIN_MIAO_SUBOTNIK && c.model != NQCB200_MODEL_ANDERSON_HOLSTEIN_ERPENBECK_THOSS) {
         why = "AdiabaticIESH is built for the AndersonHolstein (Newns-Anderson) model"; return false;
     }
-    if (c.ndofs != 1 || c.nbeads != 1) { why = "AdiabaticIESH kernel: ndofs == 1 and nbeads == 1"; return false; }
+    if (c.ndofs != 1) { why = "AdiabaticIESH kernel: ndofs == 1"; return false; }
+    if (c.nbeads < 1 || c.nbeads > 32) { why = "AdiabaticIESH / EhrenfestNA ring polymers: 1 <= nbeads <= 32"; return false; }
+    if (c.nbeads > 1 && c.edc_C > 0.0) { why = "EDC decoherence is built for nbeads == 1"; return false; }
     const int n = c.nstates, ne = c.nelectrons;
     if (ne > 112) { why = "AdiabaticIESH kernel: at most 112 electrons"; return false; }
     if (n < 3 || ne < 1 || ne >= n) { why = "AdiabaticIESH needs nstates >= 3 and 1 <= nelectrons < nstates"; return false; }
@@ -81,14 +83,14 @@ bool select_iesh(const nqcb200_config& c, KernelSet& out, std::string& why) {
     }
     IeshLayout L;
     if (!iesh_plan(n, ne, 227 * 1024, L)) { why = "AdiabaticIESH: system too large for one CTA's shared memory"; return false; }
-    out.step = iesh_step_kernel;
-    out.init = iesh_init_kernel;
+    if (c.nbeads > 1) { out.step = iesh_step_kernel<true>; out.init = iesh_init_kernel<true>; }       // RPIESH / RP-EhrenfestNA (BCBWavefunction)
+    else { out.step = iesh_step_kernel<false>; out.init = iesh_init_kernel<false>; }
     out.L = 1; out.DPL = 1;
     out.block = L.threads;
     out.dyn_smem = (size_t)L.smem_bytes;
     out.cta_per_trajectory = true;
     out.iesh = L;
-    out.name = "iesh_anderson_holstein";
+    out.name = (c.nbeads > 1) ? "rpiesh_anderson_holstein" : "iesh_anderson_holstein";
     return true;
 }
 }  // namespace nq

@@ -240,8 +240,8 @@ int nqco_create(const nqcb200_config* cfg, nqco_handle** out) {
         // (rpmdef.jl:30-57) which is out of scope; quantum method on a classical model is invalid
         g_err = "method/model combination unsupported"; delete h; return NQCB200_ERR_UNSUPPORTED;
     }
-    if (iesh_family(cfg->method) && (S.ne < 1 || S.ne >= S.n || S.B != 1)) {
-        g_err = "IESH needs 1 <= nelectrons < nstates and nbeads == 1"; delete h; return NQCB200_ERR_INVALID;
+    if (iesh_family(cfg->method) && (S.ne < 1 || S.ne >= S.n || (S.B > 1 && cfg->edc_C > 0.0))) {
+        g_err = "IESH needs 1 <= nelectrons < nstates (EDC: nbeads == 1)"; delete h; return NQCB200_ERR_INVALID;
     }
     build_layout(h);
     h->obs_sum.assign(h->L.total, 0.0);

@@ -497,13 +497,14 @@ inline void step_nrpmd(const Setup& S, Trajectory& T) {
 
 // ---- IESH -------------------------------------------------------------------------------------
 // get_quantum_propagator / propagate_wavefunction! wavefunction_dynamics.jl:15-58
-inline void iesh_propagate_wavefunction(const Setup& S, Trajectory& T) {
+// propagate_wavefunction!(sigma_final, sigma, v, r, sim, dt), wavefunction_dynamics.jl:15-58: c = the cache evaluated at r
+// (ring polymer: centroid), vh = get_hopping_velocity(sim, v)
+inline void iesh_propagate_wavefunction(const Setup& S, Trajectory& T, const Cache& c, const double* vh) {
     const int n = S.n, ne = S.ne;
-    const Cache& c = T.bead[0];
     cvec H((size_t)n * n, cd(0.0));
     for (int i = 0; i < n; ++i) H[i + (size_t)n * i] = c.w[i];
     for (int I = 0; I < S.D; ++I)
-        for (int J = 0; J < n * n; ++J) H[J] -= cd(0.0, 1.0) * c.nac[(size_t)I * n * n + J] * T.v[I];
+        for (int J = 0; J < n * n; ++J) H[J] -= cd(0.0, 1.0) * c.nac[(size_t)I * n * n + J] * vh[I];
     // tmp1 .= Hermitian(prop): upper triangle defines the matrix
     for (int j = 0; j < n; ++j)
         for (int i = j + 1; i < n; ++i) H[i + (size_t)n * j] = std::conj(H[j + (size_t)n * i]);
@@ -539,7 +540,9 @@ inline void iesh_unoccupied(int n, const std::vector<int>& occ, std::vector<int>
 inline void iesh_hop(const Setup& S, Trajectory& T, double xi) {
     if (S.cfg.disable_hopping) return;
     const int n = S.n, ne = S.ne, D = S.D;
-    const Cache& c = T.bead[0];
+    const Cache& c = hop_cache(S, T);          // ring polymer: centroid (SurfaceHoppingMethods.jl:85-103)
+    vec vh(D);
+    hop_velocity(S, T, vh.data());
     std::vector<int> un;
     iesh_unoccupied(n, T.occ, un);
     cvec Sm((size_t)ne * ne);
@@ -555,7 +558,7 @@ inline void iesh_hop(const Setup& S, Trajectory& T, double xi) {
     vec vdd((size_t)n * ne, 0.0);
     for (int I = 0; I < D; ++I)
         for (int e = 0; e < ne; ++e)
-            for (int m : un) vdd[m + (size_t)n * e] -= T.v[I] * c.nac[(size_t)I * n * n + m + (size_t)n * T.occ[e]];
+            for (int m : un) vdd[m + (size_t)n * e] -= vh[I] * c.nac[(size_t)I * n * n + m + (size_t)n * T.occ[e]];
     vec prob((size_t)n * ne, 0.0);
     bool pruned = false;
     if (S.cfg.estimate_probability) {
@@ -593,7 +596,7 @@ inline void iesh_hop(const Setup& S, Trajectory& T, double xi) {
         vec d(D);
         for (int I = 0; I < D; ++I) d[I] = c.nac[(size_t)I * n * n + new_state + (size_t)n * old_state];
         double a = 0.0, b = 0.0;
-        for (int I = 0; I < D; ++I) { a += d[I] * d[I] / S.masses[I]; b += d[I] * T.v[I]; }
+        for (int I = 0; I < D; ++I) { a += d[I] * d[I] / S.masses[I]; b += d[I] * vh[I]; }
         a /= 2.0;
         double cc = c.w[new_state] - c.w[old_state];
         double disc = b * b - 4.0 * a * cc;
@@ -605,13 +608,15 @@ inline void iesh_hop(const Setup& S, Trajectory& T, double xi) {
                 for (int I = 0; I < D; ++I) nrm += d[I] * d[I];
                 nrm = std::sqrt(nrm);
                 double gam = 0.0;
-                for (int I = 0; I < D; ++I) gam += T.v[I] * d[I] / nrm;
-                for (int I = 0; I < D; ++I) T.v[I] -= 2.0 * gam * d[I] / nrm;
+                for (int I = 0; I < D; ++I) gam += vh[I] * d[I] / nrm;
+                for (int b2 = 0; b2 < S.B; ++b2)      // every bead (rpsh.jl:39-50)
+                    for (int I = 0; I < D; ++I) T.v[I + (size_t)D * b2] -= 2.0 * gam * d[I] / nrm;
             }
         } else {
             double root = std::sqrt(disc);
             double gam = (b < 0.0) ? (b + root) / (2.0 * a) : (b - root) / (2.0 * a);
-            for (int I = 0; I < D; ++I) T.v[I] -= gam * d[I] / S.masses[I];
+            for (int b2 = 0; b2 < S.B; ++b2)          // rpsh.jl:30-37
+                for (int I = 0; I < D; ++I) T.v[I + (size_t)D * b2] -= gam * d[I] / S.masses[I];
         }
     }
     if (accept) {
@@ -653,10 +658,33 @@ inline void step_iesh(const Setup& S, Trajectory& T, double xi) {  // verlet_wit
     T.bead[0].update(S.model, T.r.data());
     acceleration(S, T, T.r, none);
     for (int i = 0; i < D; ++i) T.v[i] = std::fma(dt / 2, T.k[i], vtmp[i]);
-    iesh_propagate_wavefunction(S, T);   // uses (vfinal, rfinal): Q5
+    iesh_propagate_wavefunction(S, T, T.bead[0], T.v.data());   // uses (vfinal, rfinal): Q5
     if (S.cfg.method == NQCB200_METHOD_EHRENFEST_NA) return;   // no callback (ehrenfest_na.jl has none)
     iesh_hop(S, T, xi);
     if (S.cfg.edc_C > 0.0) iesh_edc(S, T);
+}
+
+// RingPolymerSimulation{AdiabaticIESH} / {EhrenfestNA}: BCBWavefunction perform_step!, bcb_wavefunction.jl:37-69.
+// Q5: psi is propagated with (vprev, rprev) -- get_hopping_eigenvalues / get_hopping_nonadiabatic_coupling evaluate the
+// centroid at the position they are handed (NQCCalculators' position-keyed getters, external) -- i.e. with the centroid
+// cache and centroid velocity from BEFORE this step's nuclear update; the hop callback then sees the new geometry.
+inline void step_rpiesh(const Setup& S, Trajectory& T, double xi) {
+    const double dt = S.cfg.dt;
+    const size_t nd = (size_t)S.B * S.D;
+    const Cache cprev = T.centroid;
+    vec vprev(S.D);
+    centroid_of(S, T.v, vprev.data());
+    vec vtmp(nd);
+    for (size_t i = 0; i < nd; ++i) vtmp[i] = std::fma(dt / 2, T.k[i], T.v[i]);     // step_B!
+    to_normal_modes(S, T.r); to_normal_modes(S, vtmp);
+    step_C(S, vtmp, T.r);
+    from_normal_modes(S, T.r); from_normal_modes(S, vtmp);
+    update_all_caches(S, T, T.r);
+    acceleration(S, T, T.r, T.sigma);                                                // sigma_prev / method.state
+    for (size_t i = 0; i < nd; ++i) T.v[i] = std::fma(dt / 2, T.k[i], vtmp[i]);
+    iesh_propagate_wavefunction(S, T, cprev, vprev.data());
+    if (S.cfg.method == NQCB200_METHOD_EHRENFEST_NA) return;
+    iesh_hop(S, T, xi);
 }
 
 inline void step(const Setup& S, Trajectory& T, double xi) {
@@ -667,7 +695,7 @@ inline void step(const Setup& S, Trajectory& T, double xi) {
         case NQCB200_METHOD_THERMAL_LANGEVIN: step_langevin_bcocb(S, T); break;
         case NQCB200_METHOD_NRPMD: step_nrpmd(S, T); break;
         case NQCB200_METHOD_IESH:
-        case NQCB200_METHOD_EHRENFEST_NA: step_iesh(S, T, xi); break;
+        case NQCB200_METHOD_EHRENFEST_NA: if (S.B > 1) step_rpiesh(S, T, xi); else step_iesh(S, T, xi); break;
         default: throw std::runtime_error("step: method");
     }
     T.step++;
@@ -773,14 +801,18 @@ inline double potential_energy(const Setup& S, const Trajectory& T) {
                 for (int i = 0; i < n; ++i) pot += T.sigma[i + (size_t)n * i].real() * T.bead[b].w[i];
             }
             break;
-        case NQCB200_METHOD_IESH:  // iesh.jl:380-388
-            pot = S.model.U0(&T.r[0]);
-            for (int kk : T.occ) pot += T.bead[0].w[kk];
+        case NQCB200_METHOD_IESH:  // iesh.jl:380-388, rpiesh.jl:38-52
+            for (int b = 0; b < S.B; ++b) {
+                pot += S.model.U0(&T.r[(size_t)S.D * b]);
+                for (int kk : T.occ) pot += T.bead[b].w[kk];
+            }
             break;
-        case NQCB200_METHOD_EHRENFEST_NA:  // ehrenfest_na.jl:103-114
-            pot = S.model.U0(&T.r[0]);
-            for (int e = 0; e < S.ne; ++e)
-                for (int i = 0; i < n; ++i) pot += T.bead[0].w[i] * std::norm(T.sigma[i + (size_t)n * e]);
+        case NQCB200_METHOD_EHRENFEST_NA:  // ehrenfest_na.jl:103-114, rpehrenfest_na.jl:37-52
+            for (int b = 0; b < S.B; ++b) {
+                pot += S.model.U0(&T.r[(size_t)S.D * b]);
+                for (int e = 0; e < S.ne; ++e)
+                    for (int i = 0; i < n; ++i) pot += T.bead[b].w[i] * std::norm(T.sigma[i + (size_t)n * e]);
+            }
             break;
         case NQCB200_METHOD_THERMAL_LANGEVIN:
         case NQCB200_METHOD_CLASSICAL:  // DynamicsUtils.jl:141-151

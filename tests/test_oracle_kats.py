@@ -494,3 +494,36 @@ def test_ehrenfest_na_conserves_energy_and_electrons():
     assert np.allclose(adi.sum(axis=2), ne, atol=1e-9) and np.all(adi > -1e-12) and np.all(adi < 1 + 1e-9)
     x = h.observable_per_trajectory(A.OBS_POSITION)[:, :, 0]
     assert np.max(np.abs(x[0] - 21.0)) > 1e-3            # the trajectory does move on the mean-field surface
+
+
+def test_rp_ehrenfest_na_and_rpiesh_conserve_energy():
+    """test/Dynamics/rp_ehrenfest_na.jl:10-41: RingPolymerSimulation{EhrenfestNA}(Atoms(2000), AndersonHolstein(MiaoSubotnik,
+    TrapezoidalRule(30); fermi_level = 0.001), 4 beads), v = 0, r = 21 + N(0, 1), dt = 10, tspan (0, 2000), BCBWavefunction:
+    var(total energy) < 1e-6 -- the reference's own assertion, on the oracle's step_rpiesh (bead forces, spring term, psi
+    propagated with the previous centroid generator).  RPIESH without hops (huge draws) on the same system likewise."""
+    import nqcdynamics_jl_b200 as nq
+    from helpers import A, model_config, oracle_factory
+    B, T, nsteps = 4, 2, 200
+    rng = np.random.default_rng(5)
+    model = nq.AndersonHolstein(nq.MiaoSubotnik(Γ=6.4e-3), nq.TrapezoidalRule(30, -0.0192, 0.0192), fermi_level=0.001)
+    n, ne = model.nstates, model.nelectrons
+    psi = np.zeros((T, ne, n)); psi[:, np.arange(ne), np.arange(ne)] = 1.0
+    r = 21.0 + rng.standard_normal((T, B))
+    obs = (1 << A.OBS_TOTAL_ENERGY) | (1 << A.OBS_ADIABATIC_POP) | (1 << A.OBS_POSITION)
+    for method in (A.METHOD_EHRENFEST_NA, A.METHOD_IESH):
+        kw = model_config(model, method=method, masses=[2000.0], ntraj=T, dt=10.0, nbeads=B, temperature=9.5e-4, rng=A.RNG_INJECTED,
+                          save_every=1, nsave=nsteps + 1, observables=obs, per_trajectory=1)
+        cfg, keep = A.make_config(**kw)
+        h = oracle_factory()(cfg, keep)
+        state = np.tile(np.arange(1, ne + 1, dtype=np.int32), (T, 1)) if method == A.METHOD_IESH else None
+        h.set_state(r, np.zeros((T, B)), psi, None, state)
+        if method == A.METHOD_IESH:
+            h.set_draws(np.full((nsteps, T), 0.999999))
+        h.run(nsteps)
+        E = h.observable_per_trajectory(A.OBS_TOTAL_ENERGY)[:, :, 0]
+        assert np.all(np.var(E, axis=1) < 1e-6), (method, np.var(E, axis=1))
+        adi = h.observable_per_trajectory(A.OBS_ADIABATIC_POP)
+        assert np.allclose(adi.sum(axis=2), ne, atol=1e-9)
+        x = h.observable_per_trajectory(A.OBS_POSITION)[:, :, 0]
+        assert np.max(np.abs(x[:, -1] - x[:, 0])) > 1e-3      # the centroid moves
+        h.close()
