@@ -284,8 +284,10 @@ int nqcb200_set_noise(nqcb200_handle* h, const double* xi, int64_t nsteps);
  * carries, so final-state outputs (OutputFinal, OutputStateResolvedScattering1D, DynamicsOutputs.jl:205-338) are the
  * reference's, and the host trims per-trajectory series with nqcb200_get_termination (OutputFinalTime :226-231 =
  * t0 + term_step*dt).  dof < 0 removes the callback.  Call before nqcb200_run; the flags are reset by set_state.
- * Available for the thread-per-trajectory FSSH / Ehrenfest kernels (1-D models, nbeads == 1) and for the
- * AdiabaticIESH / EhrenfestNA kernel (whose CTA moves on to its next trajectory), otherwise NQCB200_ERR_UNSUPPORTED. */
+ * Available for the thread-per-trajectory FSSH / Ehrenfest kernels (1-D models; ring polymers -- RPSH / RP-Ehrenfest --
+ * evaluate the predicate on the centroid of that dof and its centroid velocity) and for the AdiabaticIESH / EhrenfestNA
+ * kernel with nbeads == 1 (whose CTA moves on to its next trajectory), otherwise NQCB200_ERR_UNSUPPORTED (SpinBoson bath
+ * kernels, classical RPMD / NRPMD / Langevin, ring-polymer IESH). */
 int nqcb200_set_termination(nqcb200_handle* h, int dof, double lo, double hi, int outgoing, double tcut);
 /* term_step[traj]: number of steps the trajectory took before terminate! fired, -1 while it is still running. */
 int nqcb200_get_termination(nqcb200_handle* h, int64_t* term_step);

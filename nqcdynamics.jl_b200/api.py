@@ -452,7 +452,8 @@ def PopulationCorrelationFunction(sim, statetype=None):          # TimeCorrelati
 class PositionOutside:
     """Termination predicate a device kernel can evaluate: ``(u, t, integrator) -> r[dof] < lo || r[dof] > hi || t > tcut`` with
     ``r = get_positions(u)`` flattened column-major and ``dof`` 1-based (the scattering examples of the reference
-    documentation terminate when the particle has left the interaction region)."""
+    documentation terminate when the particle has left the interaction region).  Ring polymers: ``r`` and the velocity of
+    the ``outgoing`` clause are the CENTROID of that dof (a condition on ``get_centroid(get_positions(u))``)."""
     lo: float
     hi: float
     dof: int = 1

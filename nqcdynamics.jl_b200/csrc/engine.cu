@@ -940,12 +940,13 @@ int nqcb200_run(nqcb200_handle* h, int64_t nsteps) {
         const int64_t chunk = std::min(nsteps - done, max_per_launch);
         h->kp.step0 = h->step_count + done;
         h->kp.nsteps = (int32_t)chunk;
-        if (h->kp.term_dof >= 0 && h->ks.step_term) {   // TerminatingCallback instantiation (same launch shape as the init kernel's)
+        const bool term = h->kp.term_dof >= 0 && h->ks.step_term;
+        if (term && !h->ks.step_term_step_shape) {   // TerminatingCallback instantiation (same launch shape as the init kernel's)
             h->ks.step_term<<<grid_for(h), h->ks.block, h->ks.dyn_smem, h->stream>>>(h->kp); ++h->launches_total;
         } else if (h->ks.step_block > 0) {
             const int64_t threads = h->cfg.ntraj * h->ks.step_L;
             const unsigned grid = (unsigned)std::max<int64_t>(1, (threads + h->ks.step_block - 1) / h->ks.step_block);
-            h->ks.step<<<grid, h->ks.step_block, h->ks.step_smem, h->stream>>>(h->kp);
+            (term ? h->ks.step_term : h->ks.step)<<<grid, h->ks.step_block, h->ks.step_smem, h->stream>>>(h->kp);
             ++h->launches_total;
         } else { h->ks.step<<<grid_for(h), h->ks.block, h->ks.dyn_smem, h->stream>>>(h->kp); ++h->launches_total; }
         NQ_CUDA(h, cudaGetLastError());
@@ -1263,8 +1264,8 @@ int nqcb200_get_iesh_stats(nqcb200_handle* h, int64_t* hop_searches, int64_t* de
 int nqcb200_set_termination(nqcb200_handle* h, int dof, double lo, double hi, int outgoing, double tcut) {
     if (!h) return NQCB200_ERR_INVALID;
     if (dof < 0) { h->kp.term_dof = -1; return NQCB200_OK; }
-    if ((!h->ks.step_term && !iesh_family(h->cfg.method)) || h->cfg.nbeads != 1) {
-        h->err = "termination masks exist for the thread-per-trajectory FSSH / Ehrenfest kernels (1-D models) and the AdiabaticIESH / EhrenfestNA kernel, nbeads == 1";
+    if ((!h->ks.step_term && !iesh_family(h->cfg.method)) || (iesh_family(h->cfg.method) && h->cfg.nbeads != 1)) {
+        h->err = "termination masks exist for the thread-per-trajectory FSSH / Ehrenfest kernels (1-D models; ring polymers: predicate on the centroid) and the AdiabaticIESH / EhrenfestNA kernel with nbeads == 1";
         return NQCB200_ERR_UNSUPPORTED;
     }
     if (dof >= h->cfg.ndofs || !(lo <= hi)) { h->err = "termination: dof < ndofs and lo <= hi"; return NQCB200_ERR_INVALID; }

@@ -225,7 +225,10 @@ NQ_D void rt_record_save(const KParams& p, Emitter& em, int NB, const double* s_
 }
 
 // NBT > 0: nbeads = NBT, a power of two (FFT in registers).  NBT == 0: any nbeads (p.B), dense normal-mode product.
-template <class M, int NBT, int METHOD>
+// TERM: TerminatingCallback instantiation (nqcb200_set_termination): the position-window predicate on the CENTROID of the
+// chosen dof (and its centroid velocity for the `outgoing` clause), tested after the hopping callback on the new u
+// (callbacks.jl:29); a terminated trajectory skips the step body but keeps taking part in the barriers and save points.
+template <class M, int NBT, int METHOD, bool TERM = false>
 __global__ void __launch_bounds__(kRpshMaxThreads, 1) ring_tpt_step_kernel(const __grid_constant__ KParams p) {
     constexpr int N = M::NS;
     constexpr bool EHR = (METHOD == NQCB200_METHOD_EHRENFEST);
@@ -304,6 +307,26 @@ __global__ void __launch_bounds__(kRpshMaxThreads, 1) ring_tpt_step_kernel(const
     double Ac[sym_size(N)];
     unsigned long long nhops = 0, nfrus = 0;
     const double dt = p.dt, hdt = 0.5 * p.dt;
+    long long term_step = -1;
+    if (TERM) term_step = p.term_step[traj];
+    double wsum[N];      // sum over beads of the adiabatic energies (potential outputs use the post-hop state)
+    if (TERM && term_step >= 0) {
+        // terminated in an earlier launch: the estimators of its frozen state for this launch's save points
+#pragma unroll
+        for (int i = 0; i < N; ++i) { wsum[i] = 0.0; ec.w[i] = cur.E[i]; }
+#pragma unroll
+        for (int j = 0; j < N; ++j)
+#pragma unroll
+            for (int k2 = 0; k2 < N; ++k2) ec.Z[j][k2] = Zc[j][k2];
+        for (int b = 0; b < NB; ++b) {
+            double Vp[sym_size(N)], dVp[sym_size(N)];
+            Eig<N> eb;
+            model_value_and_derivative<M>(p.params, s_r[b * KT + tid], Vp, dVp);
+            sym_eigh<N>(Vp, eb);
+#pragma unroll
+            for (int i = 0; i < N; ++i) wsum[i] += eb.w[i];
+        }
+    }
 
 #pragma unroll 1
     for (int is = 0; is < p.nsteps; ++is) {
@@ -314,6 +337,7 @@ __global__ void __launch_bounds__(kRpshMaxThreads, 1) ring_tpt_step_kernel(const
         // against a 32 KB instruction cache: ncu showed `no_instruction` as the largest stall, 25 % of all samples,
         // spread evenly; with the barrier +13 %, profiles/r02/SUMMARY.md)
         __syncthreads();
+        if (!TERM || term_step < 0) {
         // B (half kick) + C (free ring polymer)  bcb_electronics.jl:62-71
         if constexpr (FFT) {
             double zr[NBF], zi[NBF];
@@ -353,7 +377,6 @@ __global__ void __launch_bounds__(kRpshMaxThreads, 1) ring_tpt_step_kernel(const
         }
         // update_cache! on every bead (bcb_electronics.jl:73), force, second half kick
         double rsum = 0.0, vsum = 0.0;
-        double wsum[N];      // sum over beads of the adiabatic energies (potential outputs use the post-hop state)
 #pragma unroll
         for (int i = 0; i < N; ++i) wsum[i] = 0.0;
         if constexpr (!EHR) {
@@ -361,7 +384,7 @@ __global__ void __launch_bounds__(kRpshMaxThreads, 1) ring_tpt_step_kernel(const
             // are visited two at a time with their Jacobi chains in lock step and without sorting the eigenvectors
             // (ncu, profiles/r02: the kernel waits on fixed-latency dependencies 39 % of its idle issue slots; the
             // sorting network was 14 % of the executed instructions)
-            const bool saving = ((step + 1) % p.save_every == 0);
+            const bool saving = TERM || ((step + 1) % p.save_every == 0);    // TERM: this step may be the trajectory's last
 #pragma unroll 1
             for (int b = 0; b < NB; b += 2) {
                 const int b1 = FFT ? b + 1 : ((b + 1 < NB) ? b + 1 : b);     // odd bead counts (dense path): the last bead twice
@@ -457,6 +480,7 @@ __global__ void __launch_bounds__(kRpshMaxThreads, 1) ring_tpt_step_kernel(const
 #pragma unroll
             for (int k = j + 1; k < N; ++k) nxt.g[aidx(N, j, k)] = (-Ac[sidx(N, j, k)] / (ec.w[j] - ec.w[k])) * vcent;
         propagate_density<N>(cur, tcur, nxt, t + dt, t, dt, s, p.tsit5_ha);
+        double dv_hop = 0.0;      // velocity change of the hop callback (every bead, hence the centroid)
 
         if (METHOD == NQCB200_METHOD_FSSH) {
             const double xi = (p.rng == NQCB200_RNG_INJECTED)
@@ -503,11 +527,19 @@ __global__ void __launch_bounds__(kRpshMaxThreads, 1) ring_tpt_step_kernel(const
                 }
                 if (dv != 0.0) {
                     for (int b = 0; b < NB; ++b) s_v[b * KT + tid] += dv;
+                    dv_hop = dv;
                 }
                 if (accept) { st = new_state; nhops += valid; }
             }
         }
         cur = nxt;
+        if (TERM) {
+            const double vx = vcent + dv_hop;
+            const bool og = p.term_outgoing != 0;
+            if ((rcent < p.term_lo && (!og || vx < 0.0)) || (rcent > p.term_hi && (!og || vx > 0.0)) || p.t0 + dt * (double)(step + 1) > p.term_tcut)
+                term_step = step + 1;
+        }
+        }
 
         if ((step + 1) % p.save_every == 0) {
             const int64_t isave = (step + 1) / p.save_every;
@@ -542,6 +574,7 @@ __global__ void __launch_bounds__(kRpshMaxThreads, 1) ring_tpt_step_kernel(const
                 p.Zprev[((int64_t)NB * N * N + j + N * k) * T + traj] = Zc[j][k];
             }
         if (p.state) p.state[traj] = st;
+        if (TERM) p.term_step[traj] = term_step;
 #pragma unroll
         for (int i = 0; i < N; ++i) p.ecur[(int64_t)i * T + traj] = cur.E[i];
 #pragma unroll

@@ -14,6 +14,7 @@ struct KernelSet {
     StepFn step = nullptr;
     InitFn init = nullptr;
     StepFn step_term = nullptr;   // TerminatingCallback instantiation of `step` (nqcb200_set_termination), if any
+    bool step_term_step_shape = false;   // step_term launches with the STEP kernel's shape (step_block / step_smem) instead of the init kernel's
     int L = 1;              // lanes (threads) per trajectory
     int DPL = 1;            // nuclear dofs per lane
     int block = kBlockThreads;

@@ -34,8 +34,9 @@ bool pick(int method, int64_t ntraj, KernelSet& out, const char* name) {
     const bool ehr = (method == NQCB200_METHOD_EHRENFEST);
     const int threads = tpt_threads(M::NS, NB, ehr, true, ntraj);
     if (want && threads > 0) {
-        if (ehr) out.step = ring_tpt_step_kernel<M, NB, NQCB200_METHOD_EHRENFEST>;
-        else out.step = ring_tpt_step_kernel<M, NB, NQCB200_METHOD_FSSH>;
+        if (ehr) { out.step = ring_tpt_step_kernel<M, NB, NQCB200_METHOD_EHRENFEST>; out.step_term = ring_tpt_step_kernel<M, NB, NQCB200_METHOD_EHRENFEST, true>; }
+        else { out.step = ring_tpt_step_kernel<M, NB, NQCB200_METHOD_FSSH>; out.step_term = ring_tpt_step_kernel<M, NB, NQCB200_METHOD_FSSH, true>; }
+        out.step_term_step_shape = true;
         out.step_L = 1; out.step_block = threads; out.step_smem = ring_tpt_smem_bytes(M::NS, NB, ehr, true, threads);
     }
     return true;
@@ -47,8 +48,9 @@ bool pick_generic(int method, int B, int64_t ntraj, KernelSet& out, const char* 
     if (method != NQCB200_METHOD_FSSH && !ehr) return false;
     const int threads = tpt_threads(M::NS, B, ehr, false, ntraj);
     if (B < 2 || threads == 0) return false;
-    if (ehr) { out.step = ring_tpt_step_kernel<M, 0, NQCB200_METHOD_EHRENFEST>; out.init = ring_tpt_init_kernel<M, NQCB200_METHOD_EHRENFEST>; }
-    else { out.step = ring_tpt_step_kernel<M, 0, NQCB200_METHOD_FSSH>; out.init = ring_tpt_init_kernel<M, NQCB200_METHOD_FSSH>; }
+    if (ehr) { out.step = ring_tpt_step_kernel<M, 0, NQCB200_METHOD_EHRENFEST>; out.step_term = ring_tpt_step_kernel<M, 0, NQCB200_METHOD_EHRENFEST, true>; out.init = ring_tpt_init_kernel<M, NQCB200_METHOD_EHRENFEST>; }
+    else { out.step = ring_tpt_step_kernel<M, 0, NQCB200_METHOD_FSSH>; out.step_term = ring_tpt_step_kernel<M, 0, NQCB200_METHOD_FSSH, true>; out.init = ring_tpt_init_kernel<M, NQCB200_METHOD_FSSH>; }
+    out.step_term_step_shape = true;
     out.L = 1; out.DPL = 1; out.name = name;
     out.step_L = 1; out.step_block = threads; out.step_smem = ring_tpt_smem_bytes(M::NS, B, ehr, false, threads);
     return true;

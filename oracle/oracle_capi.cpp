@@ -523,7 +523,12 @@ int nqco_run(nqco_handle* h, int64_t nsteps) {
                     // DiscreteCallback(condition, terminate!) runs after perform_step! and after the problem's own
                     // hopping callback (CallbackSet(prob callbacks, solve callbacks)); condition on the new u
                     if (h->term_dof >= 0) {
-                        const double x = tr.r[h->term_dof], vx = tr.v[h->term_dof];
+                        double x = tr.r[h->term_dof], vx = tr.v[h->term_dof];
+                        if (S.B > 1) {      // ring polymers: the predicate sees the centroid of that dof
+                            vec rc(S.D), vc(S.D);
+                            centroid_of(S, tr.r, rc.data()); centroid_of(S, tr.v, vc.data());
+                            x = rc[h->term_dof]; vx = vc[h->term_dof];
+                        }
                         const bool og = h->term_outgoing != 0;
                         if ((x < h->term_lo && (!og || vx < 0.0)) || (x > h->term_hi && (!og || vx > 0.0)) ||
                             S.cfg.t0 + S.cfg.dt * (double)tr.step > h->term_tcut) tr.term_step = tr.step;
@@ -636,7 +641,7 @@ int nqco_get_iesh_stats(nqco_handle* h, int64_t* hop_searches, int64_t* determin
 /* TerminatingCallback with a position-window predicate (see nqcb200_set_termination). */
 int nqco_set_termination(nqco_handle* h, int dof, double lo, double hi, int outgoing, double tcut) {
     if (!h) return NQCB200_ERR_INVALID;
-    if (dof >= 0 && (h->S.B != 1 || dof >= h->S.D)) { h->err = "termination: plain Simulation (nbeads == 1), dof < D"; return NQCB200_ERR_INVALID; }
+    if (dof >= 0 && dof >= h->S.D) { h->err = "termination: dof < D"; return NQCB200_ERR_INVALID; }
     h->term_dof = dof; h->term_lo = lo; h->term_hi = hi; h->term_outgoing = outgoing ? 1 : 0;
     h->term_tcut = (tcut == tcut) ? tcut : INFINITY;
     return NQCB200_OK;

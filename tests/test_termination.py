@@ -76,12 +76,61 @@ def test_oracle_termination_semantics():
     assert abs(sc[2:].sum() - np.count_nonzero(st_term["r"].reshape(T) > 0)) < 1e-12
 
 
-def test_oracle_termination_rejects_ring_polymers():
-    kw = model_config(nq.TullyModelOne(), method=A.METHOD_FSSH, masses=[2000.0], ntraj=2, dt=1.0, nbeads=4, temperature=1e-3,
-                      nsave=2, observables=1 << A.OBS_KINETIC)
+def _ring_scatter_setup(T, B, nsteps, method=A.METHOD_FSSH, save_every=5, seed=8):
+    rng = np.random.default_rng(seed)
+    model = nq.TullyModelOne()
+    temp = 1e-3
+    kw = model_config(model, method=method, masses=[2000.0], ntraj=T, dt=1.0, nbeads=B, temperature=temp, rng=A.RNG_INJECTED,
+                      save_every=save_every, nsave=nsteps // save_every + 1, observables=ALL_POP_OBS, per_trajectory=1)
+    r = -3.0 + 0.5 * rng.standard_normal((T, 1)) + 0.05 * rng.standard_normal((T, B))
+    v = (8.0 + 14.0 * rng.random((T, 1))) / 2000.0 + np.sqrt(temp * B / 2000.0) * 0.2 * rng.standard_normal((T, B))
+    rho = np.zeros((T, 2, 2)); rho[:, 0, 0] = 1.0
+    return kw, r, v, rho, rng.random((nsteps, T)), rng.random(T)
+
+
+def test_oracle_termination_ring_polymer_centroid():
+    """Ring polymers: the position-window predicate is evaluated on the centroid (a condition on
+    get_centroid(get_positions(u)), the form the reference's ring-polymer scattering scripts use)."""
+    T, B, nsteps, se = 12, 4, 1200, 5
+    kw, r, v, rho, draws, sdraw = _ring_scatter_setup(T, B, nsteps, save_every=se)
     o = oracle_factory()(*A.make_config(**kw))
-    with pytest.raises(nq.EngineError):
-        o.set_termination(0, -1.0, 1.0)
+    _drive(o, r, v, rho, draws, sdraw, (-4.5, 4.0), nsteps)
+    ts = o.termination()
+    assert (ts >= 0).any() and (ts < 0).any()
+    rc = o.get_state()["r"].reshape(T, B).mean(axis=1)
+    for t in range(T):
+        assert (ts[t] >= 0) == (rc[t] < -4.5 or rc[t] > 4.0)
+    pos = o.observable_per_trajectory(A.OBS_POSITION)[:, :, 0]
+    for t in np.nonzero(ts >= 0)[0]:
+        assert np.all(pos[t, ts[t] // se + 1:] == pos[t, -1]) and abs(pos[t, -1] - rc[t]) < 1e-12
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("method", [A.METHOD_FSSH, A.METHOD_EHRENFEST])
+@pytest.mark.parametrize("B,pieces", [(4, (None,)), (16, (7, 400, 293, 500)), (10, (600, 600))])
+def test_ring_polymer_termination_parity(method, B, pieces):
+    """TERM instantiation of ring_tpt_step_kernel (register FFT and dense normal-mode paths): identical termination steps,
+    hop sequences, frozen states and observables; terminated trajectories re-entering a later launch keep their estimators."""
+    T, nsteps, se = 200, 1200, 5
+    kw, r, v, rho, draws, sdraw = _ring_scatter_setup(T, B, nsteps, method=method, save_every=se, seed=12)
+    e, o = make_pair(engine_factory(), oracle_factory(), **kw)
+    for h in (e, o):
+        _drive(h, r, v, rho, draws, sdraw, (-4.5, 4.0), nsteps, pieces)
+    te, to = e.termination(), o.termination()
+    assert (to >= 0).any() and (to < 0).any()
+    assert np.array_equal(te, to), "identical termination steps"
+    se_, so_ = e.get_state(), o.get_state()
+    for key in ("r", "v"):
+        assert rel_err(se_[key], so_[key]) < 1e-9
+    assert np.max(np.abs(se_["sigma"] - so_["sigma"])) < 1e-9
+    if method == A.METHOD_FSSH:
+        assert np.array_equal(se_["state"], so_["state"])
+    for oid in range(A.OBS_COUNT):
+        if ALL_POP_OBS & (1 << oid):
+            a, b = e.observable_sum(oid), o.observable_sum(oid)
+            assert np.max(np.abs(a - b)) <= 1e-9 * max(1.0, np.max(np.abs(b))), f"observable {oid}"
+    ce, co = e.counters(), o.counters()
+    assert (ce["steps"], ce["hops"], ce["frustrated"]) == (co["steps"], co["hops"], co["frustrated"])
 
 
 @pytest.mark.gpu
