@@ -104,8 +104,10 @@ static __constant__ double kTsit5Dev[tsit5::I_COUNT] = {tsit5::c1, tsit5::c2, ts
 #endif
 #if defined(__CUDA_ARCH__)
 #define NQ_TS(name) kTsit5Dev[tsit5::I_##name]
+#define NQ_RCP(x) rcp_nb(x)      // one-ulp reciprocal without the IEEE slow path (common.cuh)
 #else
 #define NQ_TS(name) tsit5::name
+#define NQ_RCP(x) (1.0 / (x))
 #endif
 
 #define NQ_FOR_HERM(expr)                                              \
@@ -120,7 +122,7 @@ NQ_HD void propagate_density(const ElecParams<N>& cur, double tcur, const ElecPa
                              double t, double dt, Herm<N>& s, const double (&ha)[21]) {
     using namespace tsit5;
     const double h = dt / 5.0;
-    const double inv_span = 1.0 / (tnext - tcur);
+    const double inv_span = NQ_RCP(tnext - tcur);
     auto loc_of = [&](double tau) {
         double l = (tau - tcur) * inv_span;
         return (l != l) ? 0.0 : l;   // isnan -> 0 (electronic_dynamics.jl:62,75)
@@ -181,7 +183,7 @@ NQ_HD void propagate_density_2state(const ElecParams<2>& cur, double tcur, const
     // (3 dependent operations from d z to d x01 and 2 back, instead of 5 and 3).
     using namespace tsit5;
     const double h = dt / 5.0;
-    const double inv_span = 1.0 / (tnext - tcur);
+    const double inv_span = NQ_RCP(tnext - tcur);
     const bool flat = !(fabs(inv_span) <= 1.0e300);   // zero span: the reference's isnan(loc) -> 0 branch
     const double dEc = cur.E[0] - cur.E[1], dEd = (nxt.E[0] - nxt.E[1]) - dEc;
     const double gc = cur.g[0], gd = nxt.g[0] - gc;

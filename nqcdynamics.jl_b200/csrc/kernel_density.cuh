@@ -389,13 +389,13 @@ __global__ void __launch_bounds__(kBlockThreads) density_step_kernel(const __gri
             M::derivative_dof(p.params, R.r[jj], R.ba[jj], R.bb[jj], dVp);
             similarity<N>(dVp, e.Z, Ap);                                     // Z' dV Z
             const double f = force_from_adiab<N, METHOD>(Ap, R.st, R.s);     // pre-hop state / sigma_prev
-            R.acc[jj] = f / R.mass[jj];
+            R.acc[jj] = div_fast(f, R.mass[jj]);
             R.v[jj] = fma(hdt, R.acc[jj], vt[jj]);
 #pragma unroll
             for (int j = 0; j < N; ++j)
 #pragma unroll
                 for (int k = j + 1; k < N; ++k)   // d[j,k] = -adiab[j,k] / (w_j - w_k)
-                    nxt.g[aidx(N, j, k)] += (-Ap[sidx(N, j, k)] / (e.w[j] - e.w[k])) * R.v[jj];
+                    nxt.g[aidx(N, j, k)] += div_fast(-Ap[sidx(N, j, k)], e.w[j] - e.w[k]) * R.v[jj];
         }
         if (L > 1) {
 #pragma unroll
@@ -409,7 +409,7 @@ __global__ void __launch_bounds__(kBlockThreads) density_step_kernel(const __gri
                                   : philox_uniform(p.seed, (uint64_t)(p.traj_offset + traj), (uint64_t)step, 0u);
             // fewest_switches_probability! fssh.jl:96-108 (Q4) + select_new_state :110-121
             const int s0 = R.st;
-            const double inv_ss = 1.0 / R.s.Xsel(s0, s0);
+            const double inv_ss = rcp_nb(R.s.Xsel(s0, s0));
             double cum = 0.0;
             int new_state = s0;
 #pragma unroll

@@ -478,7 +478,7 @@ __global__ void __launch_bounds__(kRpshMaxThreads, 1) ring_tpt_step_kernel(const
 #pragma unroll
         for (int j = 0; j < N; ++j)
 #pragma unroll
-            for (int k = j + 1; k < N; ++k) nxt.g[aidx(N, j, k)] = (-Ac[sidx(N, j, k)] / (ec.w[j] - ec.w[k])) * vcent;
+            for (int k = j + 1; k < N; ++k) nxt.g[aidx(N, j, k)] = div_fast(-Ac[sidx(N, j, k)], ec.w[j] - ec.w[k]) * vcent;
         propagate_density<N>(cur, tcur, nxt, t + dt, t, dt, s, p.tsit5_ha);
         double dv_hop = 0.0;      // velocity change of the hop callback (every bead, hence the centroid)
 
@@ -487,7 +487,7 @@ __global__ void __launch_bounds__(kRpshMaxThreads, 1) ring_tpt_step_kernel(const
                                   ? p.draws[(step - p.draws_step0) * T + traj]
                                   : philox_uniform(p.seed, (uint64_t)(p.traj_offset + traj), (uint64_t)step, 0u);
             const int s0 = st;
-            const double inv_ss = 1.0 / s.Xsel(s0, s0);
+            const double inv_ss = rcp_nb(s.Xsel(s0, s0));
             double cum = 0.0;
             int new_state = s0;
 #pragma unroll

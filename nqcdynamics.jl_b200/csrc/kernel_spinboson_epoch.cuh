@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(kSeThreads, 4) sb_elec_kernel(const __grid_con
         sb_sz(e, s00, s01, s11);
         sb_force_scalars<METHOD>(R.s, R.st, tr0, s00, s01, s11, R.A, R.B);      // pre-hop state, sigma_prev
         const double cv = Cv - hdt * (R.A * Wr + R.B * C2);
-        const double dfac = -s01 / (e.w[0] - e.w[1]);
+        const double dfac = div_fast(-s01, e.w[0] - e.w[1]);
         ElecParams<N> nxt;
         nxt.E[0] = e.w[0]; nxt.E[1] = e.w[1];
         nxt.g[0] = dfac * cv;
@@ -402,7 +402,7 @@ __global__ void __launch_bounds__(kSeThreads, 4) sb_elec_kernel(const __grid_con
                                   ? p.draws[(step - p.draws_step0) * T + traj]
                                   : philox_uniform(p.seed, (uint64_t)(p.traj_offset + traj), (uint64_t)step, 0u);
             const int s0 = R.st, m = 1 - s0;
-            double g = 2.0 * (R.s.x[1] / (s0 ? R.s.x[2] : R.s.x[0])) * (s0 ? -nxt.g[0] : nxt.g[0]) * dt;   // fssh.jl:96-121 (Q4)
+            double g = 2.0 * div_fast(R.s.x[1], s0 ? R.s.x[2] : R.s.x[0]) * (s0 ? -nxt.g[0] : nxt.g[0]) * dt;   // fssh.jl:96-121 (Q4)
             g = fmin(1.0, fmax(0.0, g));
             if (g > xi) {
                 bool accept = true;

@@ -18,9 +18,59 @@ struct Eig {
     double Z[N][N];  // Z[row][col], column i = eigenvector i
 };
 
+#if defined(__CUDACC__)
+// 1 / sqrt(x) for a normal positive x: hardware seed (MUFU.RSQ64H) + one third-order correction
+// y (1 + e/2 + 3 e^2/8), e = 1 - x y^2 -- no special-case path, i.e. no branch: two of these can be in flight in one
+// basic block (the library rsqrt() carries a slow-path branch that ends the block).
+NQ_D double rsqrt_pos(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-x * y, y, 1.0);
+    return fma(y * e, fma(0.375, e, 0.5), y);
+}
+
+// jacobi_rotate without branches (same rotation, the zero-element case as selects)
+template <int N>
+NQ_D void jacobi_rotate_bf(double (&A)[N][N], double (&Z)[N][N], int p, int q) {
+    const double apq = A[p][q];
+    const double a = A[q][q] - A[p][p], b = 2.0 * apq;
+    const double x = fma(a, a, b * b);
+    const bool zero = (apq == 0.0) || !(x > 1.0e-280);
+    const double ih = rsqrt_pos(fmax(x, 1.0e-280));
+    const double c2 = fma(0.5 * fabs(a), ih, 0.5);
+    const double rc = rsqrt_pos(c2);
+    const double c = zero ? 1.0 : c2 * rc;
+    const double s = zero ? 0.0 : (a >= 0.0 ? 0.5 : -0.5) * (b * ih) * rc;
+    const double t = s * rc;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        if (k != p && k != q) {
+            const double akp = A[k][p], akq = A[k][q];
+            const double np_ = c * akp - s * akq, nq_ = s * akp + c * akq;
+            A[k][p] = np_; A[p][k] = np_;
+            A[k][q] = nq_; A[q][k] = nq_;
+        }
+    }
+    A[p][p] -= t * apq;
+    A[q][q] += t * apq;
+    A[p][q] = 0.0; A[q][p] = 0.0;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        const double zkp = Z[k][p], zkq = Z[k][q];
+        Z[k][p] = c * zkp - s * zkq;
+        Z[k][q] = s * zkp + c * zkq;
+    }
+}
+
+#endif
+
 template <int N>
 NQ_HD void jacobi_rotate(double (&A)[N][N], double (&Z)[N][N], int p, int q) {
     const double apq = A[p][q];
+    if (N > 2 && apq == 0.0) return;
+#if defined(__CUDA_ARCH__)
+    jacobi_rotate_bf<N>(A, Z, p, q);     // same rotation, straight-line code (two reciprocal square roots without slow paths)
+#else
     if (apq == 0.0) return;
     // Rotation angle |theta| <= pi/4 with tan 2 theta = b / a (a = A_qq - A_pp, b = 2 A_pq):
     //     cos 2theta = |a| / hyp,  c = sqrt((1 + cos 2theta) / 2),  s = sgn(a) (b / hyp) / (2 c),  t = s / c.
@@ -28,15 +78,9 @@ NQ_HD void jacobi_rotate(double (&A)[N][N], double (&Z)[N][N], int p, int q) {
     // three rotations of a sweep are serial, so the rotation is written with two reciprocal square roots and no
     // division: 1/hyp = rsqrt(a^2 + b^2), 1/c = rsqrt(c^2).
     const double a = A[q][q] - A[p][p], b = 2.0 * apq;
-#if defined(__CUDA_ARCH__)
-    const double ih = rsqrt(fma(a, a, b * b));
-    const double c2 = fma(0.5 * fabs(a), ih, 0.5);
-    const double rc = rsqrt(c2);
-#else
     const double ih = 1.0 / sqrt(fma(a, a, b * b));
     const double c2 = fma(0.5 * fabs(a), ih, 0.5);
     const double rc = 1.0 / sqrt(c2);
-#endif
     const double c = c2 * rc;
     const double s = (a >= 0.0 ? 0.5 : -0.5) * (b * ih) * rc;
     const double t = s * rc;
@@ -58,6 +102,7 @@ NQ_HD void jacobi_rotate(double (&A)[N][N], double (&Z)[N][N], int p, int q) {
         Z[k][p] = c * zkp - s * zkq;
         Z[k][q] = s * zkp + c * zkq;
     }
+#endif
 }
 
 // Vp: packed upper triangle (row-wise) of the symmetric matrix.
@@ -107,49 +152,6 @@ NQ_HD void sym_eigh(const double (&Vp)[sym_size(N)], Eig<N>& e) {
 }
 
 #if defined(__CUDACC__)
-// 1 / sqrt(x) for a normal positive x: hardware seed (MUFU.RSQ64H) + one third-order correction
-// y (1 + e/2 + 3 e^2/8), e = 1 - x y^2 -- no special-case path, i.e. no branch: two of these can be in flight in one
-// basic block (the library rsqrt() carries a slow-path branch that ends the block).
-NQ_D double rsqrt_pos(double x) {
-    double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    const double e = fma(-x * y, y, 1.0);
-    return fma(y * e, fma(0.375, e, 0.5), y);
-}
-
-// jacobi_rotate without branches (same rotation, the zero-element case as selects)
-template <int N>
-NQ_D void jacobi_rotate_bf(double (&A)[N][N], double (&Z)[N][N], int p, int q) {
-    const double apq = A[p][q];
-    const double a = A[q][q] - A[p][p], b = 2.0 * apq;
-    const double x = fma(a, a, b * b);
-    const bool zero = (apq == 0.0) || !(x > 1.0e-280);
-    const double ih = rsqrt_pos(fmax(x, 1.0e-280));
-    const double c2 = fma(0.5 * fabs(a), ih, 0.5);
-    const double rc = rsqrt_pos(c2);
-    const double c = zero ? 1.0 : c2 * rc;
-    const double s = zero ? 0.0 : (a >= 0.0 ? 0.5 : -0.5) * (b * ih) * rc;
-    const double t = s * rc;
-#pragma unroll
-    for (int k = 0; k < N; ++k) {
-        if (k != p && k != q) {
-            const double akp = A[k][p], akq = A[k][q];
-            const double np_ = c * akp - s * akq, nq_ = s * akp + c * akq;
-            A[k][p] = np_; A[p][k] = np_;
-            A[k][q] = nq_; A[q][k] = nq_;
-        }
-    }
-    A[p][p] -= t * apq;
-    A[q][q] += t * apq;
-    A[p][q] = 0.0; A[q][p] = 0.0;
-#pragma unroll
-    for (int k = 0; k < N; ++k) {
-        const double zkp = Z[k][p], zkq = Z[k][q];
-        Z[k][p] = c * zkp - s * zkq;
-        Z[k][q] = s * zkp + c * zkq;
-    }
-}
-
 // Two independent eigenproblems in lock step (instruction-level parallelism for the serial rotation chains: the
 // ring-polymer kernel visits its beads two at a time).  Eigenvalues / eigenvectors are left in Jacobi order --
 // `eig_rank` gives the ascending position of each column, so that a caller that needs one column (the occupied state's

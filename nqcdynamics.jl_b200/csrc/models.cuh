@@ -14,6 +14,13 @@
 
 namespace nq {
 
+// device: the branch-free exponential of common.cuh (several of them overlap in one basic block); host: libm
+#if defined(__CUDA_ARCH__)
+#define NQ_EXP exp_nb
+#else
+#define NQ_EXP exp
+#endif
+
 template <int KIND> struct ModelT;
 
 template <> struct ModelT<NQCB200_MODEL_TULLY_ONE> {
@@ -23,15 +30,15 @@ template <> struct ModelT<NQCB200_MODEL_TULLY_ONE> {
     NQ_HD static void potential_partial(const double* P, const double (&r)[DPL], const double (&)[DPL],
                                         const double (&)[DPL], bool lane0, double (&V)[3]) {
         const double q = r[0];
-        const double e = exp(-P[1] * fabs(q));
+        const double e = NQ_EXP(-P[1] * fabs(q));
         const double v11 = (q > 0.0) ? P[0] * (1.0 - e) : -P[0] * (1.0 - e);
         V[0] = lane0 ? v11 : 0.0; V[2] = -V[0];
-        V[1] = lane0 ? P[2] * exp(-P[3] * q * q) : 0.0;
+        V[1] = lane0 ? P[2] * NQ_EXP(-P[3] * q * q) : 0.0;
     }
     NQ_HD static void derivative_dof(const double* P, double q, double, double, double (&dV)[3]) {
-        const double d11 = P[0] * P[1] * exp(-P[1] * fabs(q));
+        const double d11 = P[0] * P[1] * NQ_EXP(-P[1] * fabs(q));
         dV[0] = d11; dV[2] = -d11;
-        dV[1] = -2.0 * P[2] * P[3] * q * exp(-P[3] * q * q);
+        dV[1] = -2.0 * P[2] * P[3] * q * NQ_EXP(-P[3] * q * q);
     }
 };
 
@@ -43,13 +50,13 @@ template <> struct ModelT<NQCB200_MODEL_TULLY_TWO> {
                                         const double (&)[DPL], bool lane0, double (&V)[3]) {
         const double q = r[0];
         V[0] = 0.0;
-        V[2] = lane0 ? -P[0] * exp(-P[1] * q * q) + P[4] : 0.0;
-        V[1] = lane0 ? P[2] * exp(-P[3] * q * q) : 0.0;
+        V[2] = lane0 ? -P[0] * NQ_EXP(-P[1] * q * q) + P[4] : 0.0;
+        V[1] = lane0 ? P[2] * NQ_EXP(-P[3] * q * q) : 0.0;
     }
     NQ_HD static void derivative_dof(const double* P, double q, double, double, double (&dV)[3]) {
         dV[0] = 0.0;
-        dV[2] = 2.0 * P[0] * P[1] * q * exp(-P[1] * q * q);
-        dV[1] = -2.0 * P[2] * P[3] * q * exp(-P[3] * q * q);
+        dV[2] = 2.0 * P[0] * P[1] * q * NQ_EXP(-P[1] * q * q);
+        dV[1] = -2.0 * P[2] * P[3] * q * NQ_EXP(-P[3] * q * q);
     }
 };
 
@@ -60,13 +67,13 @@ template <> struct ModelT<NQCB200_MODEL_TULLY_THREE> {
     NQ_HD static void potential_partial(const double* P, const double (&r)[DPL], const double (&)[DPL],
                                         const double (&)[DPL], bool lane0, double (&V)[3]) {
         const double q = r[0];
-        const double e = exp(-P[2] * fabs(q));
+        const double e = NQ_EXP(-P[2] * fabs(q));
         V[0] = lane0 ? P[0] : 0.0; V[2] = -V[0];
         V[1] = lane0 ? ((q < 0.0) ? P[1] * e : P[1] * (2.0 - e)) : 0.0;
     }
     NQ_HD static void derivative_dof(const double* P, double q, double, double, double (&dV)[3]) {
         dV[0] = 0.0; dV[2] = 0.0;
-        dV[1] = P[1] * P[2] * exp(-P[2] * fabs(q));
+        dV[1] = P[1] * P[2] * NQ_EXP(-P[2] * fabs(q));
     }
 };
 
@@ -119,24 +126,24 @@ template <> struct ModelT<NQCB200_MODEL_THREE_STATE_MORSE> {
         const double s = lane0 ? 1.0 : 0.0;
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-            const double e = 1.0 - exp(-P[3 + i] * (q - P[6 + i]));
+            const double e = 1.0 - NQ_EXP(-P[3 + i] * (q - P[6 + i]));
             V[sidx(3, i, i)] = s * (P[i] * e * e + P[9 + i]);
         }
         const double d01 = q - P[18], d02 = q - P[19], d12 = q - P[20];
-        V[sidx(3, 0, 1)] = s * P[12] * exp(-P[15] * d01 * d01);
-        V[sidx(3, 0, 2)] = s * P[13] * exp(-P[16] * d02 * d02);
-        V[sidx(3, 1, 2)] = s * P[14] * exp(-P[17] * d12 * d12);
+        V[sidx(3, 0, 1)] = s * P[12] * NQ_EXP(-P[15] * d01 * d01);
+        V[sidx(3, 0, 2)] = s * P[13] * NQ_EXP(-P[16] * d02 * d02);
+        V[sidx(3, 1, 2)] = s * P[14] * NQ_EXP(-P[17] * d12 * d12);
     }
     NQ_HD static void derivative_dof(const double* P, double q, double, double, double (&dV)[6]) {
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-            const double ex = exp(-P[3 + i] * (q - P[6 + i]));
+            const double ex = NQ_EXP(-P[3 + i] * (q - P[6 + i]));
             dV[sidx(3, i, i)] = 2.0 * P[i] * P[3 + i] * ex * (1.0 - ex);
         }
         const double d01 = q - P[18], d02 = q - P[19], d12 = q - P[20];
-        dV[sidx(3, 0, 1)] = -2.0 * P[15] * d01 * P[12] * exp(-P[15] * d01 * d01);
-        dV[sidx(3, 0, 2)] = -2.0 * P[16] * d02 * P[13] * exp(-P[16] * d02 * d02);
-        dV[sidx(3, 1, 2)] = -2.0 * P[17] * d12 * P[14] * exp(-P[17] * d12 * d12);
+        dV[sidx(3, 0, 1)] = -2.0 * P[15] * d01 * P[12] * NQ_EXP(-P[15] * d01 * d01);
+        dV[sidx(3, 0, 2)] = -2.0 * P[16] * d02 * P[13] * NQ_EXP(-P[16] * d02 * d02);
+        dV[sidx(3, 1, 2)] = -2.0 * P[17] * d12 * P[14] * NQ_EXP(-P[17] * d12 * d12);
     }
 };
 
@@ -162,11 +169,6 @@ NQ_HD void model_value_and_derivative(const double* P, double q, double (&V)[sym
     M::template potential_partial<1>(P, rr, zz, zz, true, V);
     M::derivative_dof(P, q, 0.0, 0.0, dV);
 }
-#if defined(__CUDA_ARCH__)
-#define NQ_EXP exp_nb
-#else
-#define NQ_EXP exp
-#endif
 template <>
 NQ_HD void model_value_and_derivative<ModelT<NQCB200_MODEL_THREE_STATE_MORSE>>(const double* P, double q, double (&V)[6], double (&dV)[6]) {
 #pragma unroll
