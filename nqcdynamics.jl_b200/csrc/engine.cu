@@ -993,7 +993,20 @@ int nqcb200_run_from_host(nqcb200_handle* h, const double* r, const double* v, c
                 NQ_CUDA(h, cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming));
                 NQ_CUDA(h, cudaEventCreateWithFlags(&h->ev_free[i], cudaEventDisableTiming));
             }
-            h->chunk_traj = std::min<int64_t>(T, 1 << 16);
+            // Chunk size = whole waves of BOTH epoch kernels: with 65 536 trajectories (512 blocks against 444 / 592
+            // resident ones) every kernel of a chunk ran a second, nearly empty wave and the chunked path was compute bound
+            // at 1.6x the unchunked kernel time (e2e 4.7e9 although PCIe alone allows 6.7e9 at the measured 55 GB/s).
+            {
+                int sms = 148, bb = 1, be = 1;
+                cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c.device);
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bb, (const void*)h->ks.sb_bath, kBlockThreads, 0);
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&be, (const void*)h->ks.sb_elec, kBlockThreads, 0);
+                bb = std::max(bb, 1); be = std::max(be, 1);
+                int64_t g = bb, l = be;
+                while (l) { const int64_t t = g % l; g = l; l = t; }          // gcd
+                const int64_t blocks = (int64_t)bb / g * be * sms;                // lcm(bb, be) x SMs
+                h->chunk_traj = std::min<int64_t>(T, std::min<int64_t>(blocks * kBlockThreads, 1 << 19));
+            }
             for (int i = 0; i < 2; ++i)
                 for (int k = 0; k < 2; ++k)
                     if ((rc = dev_alloc(h, &h->chunk_stage[i][k], (size_t)h->chunk_traj * D)) != 0) return rc;
