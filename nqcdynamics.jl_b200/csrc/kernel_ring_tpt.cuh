@@ -24,8 +24,9 @@ constexpr int kRtThreads = kBlockThreads;   // 128 (the Emitter's block reductio
 constexpr int kRpshMaxThreads = 384;   // ring_tpt_step_kernel: ONE block per SM, up to 12 warps at 168 registers
 
 // fft: nbeads is a power of two (compile-time NBT); otherwise the dense normal-mode product through two scratch rows
-NQ_HD constexpr size_t ring_tpt_smem_bytes(int N, int NB, bool ehrenfest, bool fft, int threads = kRtThreads) {
-    return ((size_t)(3 + (ehrenfest ? N * N : 0) + (fft ? 0 : 2)) * NB * threads + (fft ? 6 * NB : NB * NB + 4 * NB)) * sizeof(double);
+// threads = trajectory slots per block (block size / lanes per trajectory); lanes > 1 adds the [bead][N] energy scratch
+NQ_HD constexpr size_t ring_tpt_smem_bytes(int N, int NB, bool ehrenfest, bool fft, int threads = kRtThreads, bool lanes = false) {
+    return ((size_t)(3 + (ehrenfest ? N * N : 0) + (fft ? 0 : 2) + (lanes ? N : 0)) * NB * threads + (fft ? 6 * NB : NB * NB + 4 * NB)) * sizeof(double);
 }
 
 // Block size of ring_tpt_step_kernel for a batch of ntraj trajectories on `sms` SMs: the kernel runs one block per SM and
@@ -228,25 +229,37 @@ NQ_D void rt_record_save(const KParams& p, Emitter& em, int NB, const double* s_
 // TERM: TerminatingCallback instantiation (nqcb200_set_termination): the position-window predicate on the CENTROID of the
 // chosen dof (and its centroid velocity for the `outgoing` clause), tested after the hopping callback on the new u
 // (callbacks.jl:29); a terminated trajectory skips the step body but keeps taking part in the barriers and save points.
-template <class M, int NBT, int METHOD, bool TERM = false>
+// LPT > 1 (FSSH, register FFT, no TERM): LPT lanes share a trajectory -- each visits NBT / LPT beads (the bead loop is
+// ~55 % of a step) while the free ring-polymer step, the centroid eigenproblem, Tsit5 and the hop test run redundantly on
+// all of them (same inputs, same bits).  Selected by the host when a shard holds fewer trajectories than one wave of
+// threads (BASELINE config 5 on 8 GPUs: 12 500 trajectories per GPU), where a thread-per-trajectory launch leaves most
+// of every SM empty and runs at the latency of one dependent chain.  Bead sums are taken in bead order from shared
+// memory, so the result does not depend on LPT (sharding independence holds bit for bit).
+template <class M, int NBT, int METHOD, bool TERM = false, int LPT = 1>
 __global__ void __launch_bounds__(kRpshMaxThreads, 1) ring_tpt_step_kernel(const __grid_constant__ KParams p) {
     constexpr int N = M::NS;
     constexpr bool EHR = (METHOD == NQCB200_METHOD_EHRENFEST);
     constexpr bool FFT = NBT > 0;
     static_assert(NBT == 0 || (NBT >= 2 && (NBT & (NBT - 1)) == 0), "ring polymer FFT: nbeads must be a power of two");
     constexpr int NBF = FFT ? NBT : 2;      // array extent of the FFT path (unused when dense)
+    constexpr bool LANES = LPT > 1;
+    static_assert(!LANES || (FFT && !EHR && !TERM && NBT % (2 * LPT) == 0), "lanes per trajectory: FSSH, register FFT, whole bead pairs per lane");
     const int NB = FFT ? NBT : p.B;
     extern __shared__ __align__(16) double rt_sm[];
     __shared__ double red[2 * (kRpshMaxThreads / 32)];
     const int KT = blockDim.x;      // chosen on the host (ring_tpt_block_threads): whole waves, at most 12 warps
     double* s_r = rt_sm;
-    double* s_v = s_r + NB * KT;
-    double* s_a = s_v + NB * KT;
-    double* s_Z = s_a + NB * KT;                       // EHR only: [bead][N*N][thread]
-    double* s_t = s_Z + (EHR ? N * N * NB * KT : 0);    // dense only: two scratch rows [2][bead][thread]
-    double* s_tab = s_t + (FFT ? 0 : 2 * NB * KT);      // FFT: twr[NB/2] twi[NB/2] al[2NB] be[2NB]; dense: U[NB*NB] cay[4NB]
+    const int KSd = blockDim.x / LPT;
+    double* s_v = s_r + NB * KSd;
+    double* s_a = s_v + NB * KSd;
+    double* s_Z = s_a + NB * KSd;                      // EHR only: [bead][N*N][thread]
+    double* s_t = s_Z + (EHR ? N * N * NB * KSd : 0);   // dense only: two scratch rows [2][bead][thread]
+    double* s_w = s_t + (FFT ? 0 : 2 * NB * KSd);       // LANES only: per-bead adiabatic energies of a saving step [bead][N][slot]
+    double* s_tab = s_w + (LANES ? NB * N * KSd : 0);   // FFT: twr[NB/2] twi[NB/2] al[2NB] be[2NB]; dense: U[NB*NB] cay[4NB]
     const int tid = threadIdx.x;
-    int64_t traj = (int64_t)blockIdx.x * KT + tid;
+    const int KS = KT / LPT;                // trajectories per block
+    const int slot = tid / LPT, sub = tid % LPT;
+    int64_t traj = (int64_t)blockIdx.x * KS + slot;
     const bool valid = traj < p.ntraj;
     if (!valid) traj = p.ntraj - 1;
     const int64_t T = p.ntraj;
@@ -269,13 +282,13 @@ __global__ void __launch_bounds__(kRpshMaxThreads, 1) ring_tpt_step_kernel(const
     }
     RtTables<NBF> tb{s_tab, s_tab + NB / 2, s_tab + NB, s_tab + 3 * NB};
 
-    for (int b = 0; b < NB; ++b) {
-        s_r[b * KT + tid] = p.r[(int64_t)b * T + traj];
-        s_v[b * KT + tid] = p.v[(int64_t)b * T + traj];
-        s_a[b * KT + tid] = p.acc[(int64_t)b * T + traj];
+    for (int b = sub; b < NB; b += LPT) {
+        s_r[b * KS + slot] = p.r[(int64_t)b * T + traj];
+        s_v[b * KS + slot] = p.v[(int64_t)b * T + traj];
+        s_a[b * KS + slot] = p.acc[(int64_t)b * T + traj];
         if (EHR) {
             for (int jk = 0; jk < N * N; ++jk)
-                s_Z[(b * N * N + jk) * KT + tid] = p.Zprev[((int64_t)b * N * N + jk) * T + traj];
+                s_Z[(b * N * N + jk) * KS + slot] = p.Zprev[((int64_t)b * N * N + jk) * T + traj];
         }
     }
     __syncthreads();
@@ -321,7 +334,7 @@ __global__ void __launch_bounds__(kRpshMaxThreads, 1) ring_tpt_step_kernel(const
         for (int b = 0; b < NB; ++b) {
             double Vp[sym_size(N)], dVp[sym_size(N)];
             Eig<N> eb;
-            model_value_and_derivative<M>(p.params, s_r[b * KT + tid], Vp, dVp);
+            model_value_and_derivative<M>(p.params, s_r[b * KS + slot], Vp, dVp);
             sym_eigh<N>(Vp, eb);
 #pragma unroll
             for (int i = 0; i < N; ++i) wsum[i] += eb.w[i];
@@ -343,36 +356,39 @@ __global__ void __launch_bounds__(kRpshMaxThreads, 1) ring_tpt_step_kernel(const
             double zr[NBF], zi[NBF];
 #pragma unroll
             for (int b = 0; b < NBF; ++b) {
-                zr[b] = s_r[b * KT + tid];
-                zi[b] = fma(hdt, s_a[b * KT + tid], s_v[b * KT + tid]);
+                zr[b] = s_r[b * KS + slot];
+                zi[b] = fma(hdt, s_a[b * KS + slot], s_v[b * KS + slot]);
             }
+            if (LANES) __syncwarp();       // every lane of the trajectory has read the old beads
             rt_free_step<NBF>(tb, zr, zi);
 #pragma unroll
-            for (int b = 0; b < NBF; ++b) { s_r[b * KT + tid] = zr[b]; s_v[b * KT + tid] = zi[b]; }
+            for (int b = 0; b < NBF; ++b)
+                if (!LANES || b % LPT == sub) { s_r[b * KS + slot] = zr[b]; s_v[b * KS + slot] = zi[b]; }
+            if (LANES) __syncwarp();
         } else {
             // dense U' .. Cayley .. U (RingPolymerArrays transform!, steps.jl:10-17)
             const double* U = s_tab;
             const double* cay = s_tab + NB * NB;
-            for (int b = 0; b < NB; ++b) s_v[b * KT + tid] = fma(hdt, s_a[b * KT + tid], s_v[b * KT + tid]);
+            for (int b = 0; b < NB; ++b) s_v[b * KS + slot] = fma(hdt, s_a[b * KS + slot], s_v[b * KS + slot]);
             for (int k = 0; k < NB; ++k) {
                 double a = 0.0, c = 0.0;
                 for (int j = 0; j < NB; ++j) {
                     const double u = U[j * NB + k];
-                    a = fma(u, s_r[j * KT + tid], a);
-                    c = fma(u, s_v[j * KT + tid], c);
+                    a = fma(u, s_r[j * KS + slot], a);
+                    c = fma(u, s_v[j * KS + slot], c);
                 }
-                s_t[k * KT + tid] = cay[4 * k + 0] * a + cay[4 * k + 1] * c;
-                s_t[(NB + k) * KT + tid] = cay[4 * k + 2] * a + cay[4 * k + 3] * c;
+                s_t[k * KS + slot] = cay[4 * k + 0] * a + cay[4 * k + 1] * c;
+                s_t[(NB + k) * KS + slot] = cay[4 * k + 2] * a + cay[4 * k + 3] * c;
             }
             for (int j = 0; j < NB; ++j) {
                 double a = 0.0, c = 0.0;
                 for (int k = 0; k < NB; ++k) {
                     const double u = U[j * NB + k];
-                    a = fma(u, s_t[k * KT + tid], a);
-                    c = fma(u, s_t[(NB + k) * KT + tid], c);
+                    a = fma(u, s_t[k * KS + slot], a);
+                    c = fma(u, s_t[(NB + k) * KS + slot], c);
                 }
-                s_r[j * KT + tid] = a;
-                s_v[j * KT + tid] = c;
+                s_r[j * KS + slot] = a;
+                s_v[j * KS + slot] = c;
             }
         }
         // update_cache! on every bead (bcb_electronics.jl:73), force, second half kick
@@ -385,10 +401,12 @@ __global__ void __launch_bounds__(kRpshMaxThreads, 1) ring_tpt_step_kernel(const
             // (ncu, profiles/r02: the kernel waits on fixed-latency dependencies 39 % of its idle issue slots; the
             // sorting network was 14 % of the executed instructions)
             const bool saving = TERM || ((step + 1) % p.save_every == 0);    // TERM: this step may be the trajectory's last
+            const int nb_lane = NB / LPT, b_lo = sub * nb_lane;        // this lane's beads (all of them when LPT == 1)
 #pragma unroll 1
-            for (int b = 0; b < NB; b += 2) {
+            for (int bb = 0; bb < nb_lane; bb += 2) {
+                const int b = b_lo + bb;
                 const int b1 = FFT ? b + 1 : ((b + 1 < NB) ? b + 1 : b);     // odd bead counts (dense path): the last bead twice
-                const double q0 = s_r[b * KT + tid], q1 = s_r[b1 * KT + tid];
+                const double q0 = s_r[b * KS + slot], q1 = s_r[b1 * KS + slot];
                 double V0[sym_size(N)], dV0[sym_size(N)], V1[sym_size(N)], dV1[sym_size(N)];
                 model_value_and_derivative<M>(p.params, q0, V0, dV0);
                 model_value_and_derivative<M>(p.params, q1, V1, dV1);
@@ -421,29 +439,41 @@ __global__ void __launch_bounds__(kRpshMaxThreads, 1) ring_tpt_step_kernel(const
                         double a0 = 0.0, a1 = 0.0;
 #pragma unroll
                         for (int i = 0; i < N; ++i) { a0 = (rk0[i] == k) ? w0[i] : a0; a1 = (rk1[i] == k) ? w1[i] : a1; }
-                        wsum[k] += a0;
-                        if (FFT || b1 != b) wsum[k] += a1;
+                        if (LANES) { s_w[(b * N + k) * KS + slot] = a0; s_w[(b1 * N + k) * KS + slot] = a1; }
+                        else {
+                            wsum[k] += a0;
+                            if (FFT || b1 != b) wsum[k] += a1;
+                        }
                     }
                 }
                 {
                     const double acc = div_nb(-f0, mass, rmass);
-                    const double vb = fma(hdt, acc, s_v[b * KT + tid]);
-                    s_a[b * KT + tid] = acc;
-                    s_v[b * KT + tid] = vb;
-                    rsum += q0; vsum += vb;
+                    const double vb = fma(hdt, acc, s_v[b * KS + slot]);
+                    s_a[b * KS + slot] = acc;
+                    s_v[b * KS + slot] = vb;
+                    if (!LANES) { rsum += q0; vsum += vb; }
                 }
                 if (FFT || b1 != b) {
                     const double acc = div_nb(-f1, mass, rmass);
-                    const double vb = fma(hdt, acc, s_v[b1 * KT + tid]);
-                    s_a[b1 * KT + tid] = acc;
-                    s_v[b1 * KT + tid] = vb;
-                    rsum += q1; vsum += vb;
+                    const double vb = fma(hdt, acc, s_v[b1 * KS + slot]);
+                    s_a[b1 * KS + slot] = acc;
+                    s_v[b1 * KS + slot] = vb;
+                    if (!LANES) { rsum += q1; vsum += vb; }
+                }
+            }
+            if (LANES) {       // bead sums in bead order (the order of the single-lane kernel), from shared memory
+                __syncwarp();
+                for (int b = 0; b < NB; ++b) { rsum += s_r[b * KS + slot]; vsum += s_v[b * KS + slot]; }
+                if (saving) {
+                    for (int b = 0; b < NB; ++b)
+#pragma unroll
+                        for (int k = 0; k < N; ++k) wsum[k] += s_w[(b * N + k) * KS + slot];
                 }
             }
         } else {
 #pragma unroll 1
         for (int b = 0; b < NB; ++b) {
-            const double q = s_r[b * KT + tid];
+            const double q = s_r[b * KS + slot];
             double Vp[sym_size(N)], dVp[sym_size(N)];
             Eig<N> eb;
             model_value_and_derivative<M>(p.params, q, Vp, dVp);
@@ -452,21 +482,21 @@ __global__ void __launch_bounds__(kRpshMaxThreads, 1) ring_tpt_step_kernel(const
 #pragma unroll
             for (int j = 0; j < N; ++j)
 #pragma unroll
-                for (int k = 0; k < N; ++k) Zb[j][k] = s_Z[(b * N * N + j + N * k) * KT + tid];
+                for (int k = 0; k < N; ++k) Zb[j][k] = s_Z[(b * N * N + j + N * k) * KS + slot];
             fix_gauge<N>(eb, Zb);
 #pragma unroll
             for (int j = 0; j < N; ++j)
 #pragma unroll
-                for (int k = 0; k < N; ++k) s_Z[(b * N * N + j + N * k) * KT + tid] = Zb[j][k];
+                for (int k = 0; k < N; ++k) s_Z[(b * N * N + j + N * k) * KS + slot] = Zb[j][k];
             double Ab[sym_size(N)];
             similarity<N>(dVp, eb.Z, Ab);
             const double f = force_from_adiab<N, METHOD>(Ab, st, s);
 #pragma unroll
             for (int i = 0; i < N; ++i) wsum[i] += eb.w[i];
             const double acc = f / mass;
-            const double vb = fma(hdt, acc, s_v[b * KT + tid]);
-            s_a[b * KT + tid] = acc;
-            s_v[b * KT + tid] = vb;
+            const double vb = fma(hdt, acc, s_v[b * KS + slot]);
+            s_a[b * KS + slot] = acc;
+            s_v[b * KS + slot] = vb;
             rsum += q; vsum += vb;
         }
         }
@@ -514,7 +544,7 @@ __global__ void __launch_bounds__(kRpshMaxThreads, 1) ring_tpt_step_kernel(const
                     const double disc = b * b - 4.0 * a * c;
                     if (disc < 0.0) {
                         accept = false;
-                        nfrus += valid;
+                        nfrus += (valid && sub == 0);
                         if (p.rescaling == NQCB200_RESCALE_VINVERSION) {
                             const double dn = d / fabs(d);
                             dv = -2.0 * (vcent * dn) * dn;
@@ -526,10 +556,10 @@ __global__ void __launch_bounds__(kRpshMaxThreads, 1) ring_tpt_step_kernel(const
                     }
                 }
                 if (dv != 0.0) {
-                    for (int b = 0; b < NB; ++b) s_v[b * KT + tid] += dv;
+                    for (int b = sub; b < NB; b += LPT) s_v[b * KS + slot] += dv;
                     dv_hop = dv;
                 }
-                if (accept) { st = new_state; nhops += valid; }
+                if (accept) { st = new_state; nhops += (valid && sub == 0); }
             }
         }
         cur = nxt;
@@ -549,20 +579,22 @@ __global__ void __launch_bounds__(kRpshMaxThreads, 1) ring_tpt_step_kernel(const
 #pragma unroll
                     for (int i = 0; i < N; ++i) pot += s.x[sidx(N, i, i)] * wsum[i];
                 } else pot = select<N>(wsum, st);
-                Emitter em{p, traj, valid, (int)isave, red, 0, true, KT / 32};
-                rt_record_save<N, METHOD>(p, em, NB, s_r, s_v, KT, tid, s, st, ec, pot, mass);
+                if (LANES) __syncwarp();      // the hop's velocity change on the other lanes' beads
+                Emitter em{p, traj, valid && sub == 0, (int)isave, red, 0, true, KT / 32};
+                rt_record_save<N, METHOD>(p, em, NB, s_r, s_v, KS, slot, s, st, ec, pot, mass);
             }
         }
     }
 
+    if (LANES) __syncwarp();
     if (valid) {
-        for (int b = 0; b < NB; ++b) {
-            p.r[(int64_t)b * T + traj] = s_r[b * KT + tid];
-            p.v[(int64_t)b * T + traj] = s_v[b * KT + tid];
-            p.acc[(int64_t)b * T + traj] = s_a[b * KT + tid];
+        for (int b = sub; b < NB; b += LPT) {
+            p.r[(int64_t)b * T + traj] = s_r[b * KS + slot];
+            p.v[(int64_t)b * T + traj] = s_v[b * KS + slot];
+            p.acc[(int64_t)b * T + traj] = s_a[b * KS + slot];
             if (EHR) {
                 for (int jk = 0; jk < N * N; ++jk)
-                    p.Zprev[((int64_t)b * N * N + jk) * T + traj] = s_Z[(b * N * N + jk) * KT + tid];
+                    p.Zprev[((int64_t)b * N * N + jk) * T + traj] = s_Z[(b * N * N + jk) * KS + slot];
             }
         }
 #pragma unroll

@@ -1,4 +1,5 @@
 // tu_ring.cu -- RPSH / RP-Ehrenfest kernels (beads on lanes).
+#include <algorithm>
 #include <cstdlib>
 
 #include "kernel_ring.cuh"
@@ -32,6 +33,27 @@ bool pick(int method, int64_t ntraj, KernelSet& out, const char* name) {
     const char* env = getenv("NQCB200_RING_TPT");
     const bool want = !(env && atoi(env) == 0);
     const bool ehr = (method == NQCB200_METHOD_EHRENFEST);
+    // Lanes per trajectory (kernel_ring_tpt.cuh, LPT): built for shards smaller than one wave of threads (BASELINE config
+    // 5 on 8 GPUs is 12 500 trajectories per GPU) and MEASURED SLOWER there -- 12 500 trajectories x 3000 steps: 59 ms with
+    // one lane, 62 ms with two, 70 ms with four (profiles/r02/SUMMARY.md): the centroid chain / Tsit5 / hop test that every
+    // lane repeats costs more issue slots than the split bead loop saves.  Kept as a documented A/B switch
+    // (NQCB200_RING_LPT=2|4, parity-tested), never selected automatically.
+    if constexpr (NB >= 8) {
+        if (want && !ehr) {
+            int sms = 148;
+            if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, t_device) != cudaSuccess || sms <= 0) sms = 148;
+            const char* force = getenv("NQCB200_RING_LPT");
+            const int lpt = force ? atoi(force) : 1;
+            if (lpt == 4 || lpt == 2) {
+                const int block = ring_tpt_block_threads(std::max<int64_t>(ntraj, 1) * lpt, sms, kRpshMaxThreads);
+                if (lpt == 4) out.step = ring_tpt_step_kernel<M, NB, NQCB200_METHOD_FSSH, false, 4>;
+                else out.step = ring_tpt_step_kernel<M, NB, NQCB200_METHOD_FSSH, false, 2>;
+                out.step_L = lpt; out.step_block = block;
+                out.step_smem = ring_tpt_smem_bytes(M::NS, NB, false, true, block / lpt, true);
+                return true;        // no TERM instantiation with lanes: nqcb200_set_termination reports UNSUPPORTED
+            }
+        }
+    }
     const int threads = tpt_threads(M::NS, NB, ehr, true, ntraj);
     if (want && threads > 0) {
         if (ehr) { out.step = ring_tpt_step_kernel<M, NB, NQCB200_METHOD_EHRENFEST>; out.step_term = ring_tpt_step_kernel<M, NB, NQCB200_METHOD_EHRENFEST, true>; }
