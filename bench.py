@@ -233,7 +233,23 @@ class Bench:
         self.stdout_fd = None
         self.strong_total = None         # --scaling strong: total trajectories over all ranks, this rank's first global index
         self.strong_offset = 0
+        self.cpu_affinity = None
         if self.world > 1:
+            # pin this rank to the host cores next to ITS GPU before any pinned buffer is allocated (first touch decides the
+            # NUMA node of the 1.6 GB of host input the e2e leg streams per job; unbound ranks share one node's memory and
+            # its PCIe root).  Purely host-side; skipped when NVML or the affinity call is unavailable.
+            try:
+                import pynvml
+                pynvml.nvmlInit()
+                hdl = pynvml.nvmlDeviceGetHandleByIndex(self.local_rank)
+                ncpu = os.cpu_count() or 1
+                words = pynvml.nvmlDeviceGetCpuAffinity(hdl, (ncpu + 63) // 64)
+                cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1 and 64 * w + b < ncpu]
+                if cpus:
+                    os.sched_setaffinity(0, cpus)
+                    self.cpu_affinity = f"{len(cpus)} cores ({min(cpus)}-{max(cpus)})"
+            except Exception:
+                pass
             # stdout carries exactly one JSON line: whatever libraries write to fd 1 meanwhile (NCCL prints its
             # "NCCL version ..." banner there when the communicator is created) goes to stderr until the line is printed
             sys.stdout.flush()
@@ -400,7 +416,7 @@ class Bench:
             (e2e_s,) = self.max_over_ranks(e2e_s)
             e2e = {"value": ntot * wl.nsteps * e2e_steps / e2e_s, "unit": "trajectory-steps/s",
                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
-                   "h2d_GBps_per_rank": h2d * e2e_steps / e2e_s / 1e9,
+                   "h2d_GBps_per_rank": h2d * e2e_steps / e2e_s / 1e9, "host_affinity": self.cpu_affinity,
                    "path": ("nqcb200_run_from_host (pinned host r, v: chunked cudaMemcpyAsync on a copy stream under the "
                             "previous chunk's kernels where the kernel family supports it; rho uploaded)" if density
                             else "nqcb200_set_state (pinned host r, v, psi) -> nqcb200_run") + " -> nqcb200_get_observable_sum"}

@@ -14,10 +14,6 @@
 #pragma once
 #include "kernel_ring.cuh"
 
-#ifndef NRPMD_STEP_SYNC
-#define NRPMD_STEP_SYNC 0
-#endif
-
 namespace nq {
 
 #if defined(__CUDACC__)
@@ -124,9 +120,8 @@ __global__ void __launch_bounds__(kBlockThreads) nrpmd_step_kernel(const __grid_
 #pragma unroll 1
     for (int is = 0; is < p.nsteps; ++is) {
         const int64_t step = p.step0 + is;
-#if NRPMD_STEP_SYNC
-        __syncthreads();
-#endif
+        __syncthreads();      // keeps the block's warps in the same part of the step's code (instruction fetch: ncu showed 0.64
+                              // `no_instruction` stalls per issue; 8.20e8 -> 8.50e8 with the barrier, profiles/r02/SUMMARY.md)
         frp.step(r, v);
         double dVp[sym_size(N)];
         model_value_and_derivative<M>(p.params, r, Vp, dVp);    // V and dV/dr at the same r: shared transcendentals

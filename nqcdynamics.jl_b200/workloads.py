@@ -255,8 +255,40 @@ def _iesh(M: int, nsteps: int, ntraj: int) -> Workload:
                     model, A.METHOD_IESH, np.array([m]), 1.0, nsteps, 10, obs, ntraj, iesh_flops(n, ne), sample)
 
 
+def _iesh_scattering(M: int, nsteps: int, ntraj: int) -> Workload:
+    # The same model driven hard (not a BASELINE config; VERDICT r01: the thermal well is the propagator's best case):
+    # every trajectory starts at x = g moving towards the crossing with 0.05 hartree of kinetic energy (~50 kT), so v.d is
+    # large (more Horner stages with G), the orbitals leave the ground state and the unpruned hop search runs more often.
+    wl = _iesh(M, nsteps, ntraj)
+    imp = models.MiaoSubotnik(Γ=6.4e-3)
+    m, ke = 2000.0, 0.05
+    v0 = -np.sqrt(2.0 * ke / m)
+
+    def sample(rng, T):
+        return {"r": rng.normal(imp.g, 0.05, (T, 1, 1)), "v": np.full((T, 1, 1), v0) * (1.0 + 0.05 * rng.standard_normal((T, 1, 1)))}
+    return Workload(f"iesh_scattering_m{M}", wl.description.replace("kT=9.5e-4 thermal sample around x=g", "incident kinetic energy 0.05 Eh (~50 kT) from x=g towards the crossing"),
+                    wl.model, wl.method, wl.masses, wl.dt, nsteps, wl.save_every, wl.observables, ntraj, wl.flops_per_traj_step, sample)
+
+
+def _rpiesh(M: int, B: int, nsteps: int, ntraj: int) -> Workload:
+    # RingPolymerSimulation{AdiabaticIESH}(Atoms(2000), AndersonHolstein(MiaoSubotnik, TrapezoidalRule(M)), B beads) with
+    # BCBWavefunction (rpiesh.jl, test/Dynamics/rpiesh.jl:11-22), thermal ring polymers around x = g
+    wl = _iesh(M, nsteps, ntraj)
+    imp = models.MiaoSubotnik(Γ=6.4e-3)
+    kT, m = 9.5e-4, 2000.0
+    sr, sv = np.sqrt(kT / (m * imp.ω ** 2)), np.sqrt(kT * B / m)
+
+    def sample(rng, T):
+        return {"r": rng.normal(imp.g, sr, (T, 1, 1)) + 0.1 * sr * rng.standard_normal((T, B, 1)), "v": rng.normal(0.0, sv, (T, B, 1))}
+    return Workload(f"rpiesh_anderson_holstein_m{M}_b{B}", f"RPIESH (SURVEY 8f rank 3): {B}-bead ring polymer, " + wl.description,
+                    wl.model, wl.method, wl.masses, wl.dt, nsteps, wl.save_every, wl.observables, ntraj,
+                    wl.flops_per_traj_step * (1.0 + 0.15 * B), sample, nbeads=B, temperature=kT)
+
+
 def get(name: str) -> Workload:
     table = {
+        "iesh_scattering_m100": lambda: _iesh_scattering(100, 1000, 10_000),
+        "rpiesh_anderson_holstein_m100_b4": lambda: _rpiesh(100, 4, 1000, 10_000),
         "iesh_anderson_holstein_m100": lambda: _iesh(100, 1000, 10_000),
         "iesh_anderson_holstein_m200": lambda: _iesh(200, 200, 10_000),
         "iesh_anderson_holstein_m30": lambda: _iesh(30, 1000, 10_000),
@@ -275,4 +307,5 @@ def get(name: str) -> Workload:
 
 NAMES = ["tully1_fssh", "spinboson_debye100_fssh", "spinboson_debye100_ehrenfest", "rpmd_harmonic32", "rpsh_morse3_16",
          "nrpmd_morse3_16", "langevin_harmonic32",
-         "iesh_anderson_holstein_m100", "iesh_anderson_holstein_m200", "iesh_anderson_holstein_m30"]
+         "iesh_anderson_holstein_m100", "iesh_anderson_holstein_m200", "iesh_anderson_holstein_m30", "iesh_scattering_m100",
+         "rpiesh_anderson_holstein_m100_b4"]
