@@ -389,6 +389,7 @@ __device__ __noinline__ void iesh_record_save(const KParams& p, IeshSmem& S, int
                         if (ec0 == 0) acc = fma(-zr[qa] * zr[qa], sa[a], acc);
                     }
                 }
+                __syncwarp();      // zrow is read below by lanes that did not write the element (shuffles order execution, not memory)
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
                 for (int eb = 0; eb < ecn; eb += EB) {

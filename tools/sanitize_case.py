@@ -88,3 +88,38 @@ for method in (A.METHOD_IESH, A.METHOD_EHRENFEST_NA):
     ts = e.termination(); e.observable_per_trajectory(A.OBS_ADIABATIC_POP); e.close()
     assert ts.max() == 13 and (ts == 1).any()
     print("ok iesh termination", method)
+# round 2, last third: ring-polymer IESH / EhrenfestNA (bead arrays + kept generator in shared memory), TERM instantiation of
+# the ring-polymer kernel (register FFT and dense bead counts), lanes-per-trajectory variant (subprocess: the switch is
+# read at create)
+from test_parity_gpu import IESH_OBS, NA_OBS, _iesh_model, _iesh_random_state
+from helpers import model_config
+for method, obs_, M, B in ((A.METHOD_IESH, IESH_OBS, 30, 4), (A.METHOD_EHRENFEST_NA, NA_OBS, 30, 3), (A.METHOD_IESH, IESH_OBS, 100, 2)):
+    model = _iesh_model(M)
+    T, nsteps = 3, 6
+    kw = model_config(model, method=method, masses=[2000.0], ntraj=T, dt=5.0, nbeads=B, temperature=9.5e-4, seed=11, save_every=2,
+                      nsave=nsteps // 2 + 1, observables=obs_, per_trajectory=1, diagnostics=1)
+    e = Engine(*A.make_config(**kw))
+    re, im, state = _iesh_random_state(rng, T, model.nstates, model.nelectrons)
+    r = 10.0 + rng.standard_normal((T, B)); v = -3e-3 + 1e-4 * rng.standard_normal((T, B))
+    e.set_state(r, v, re, im, state if method == A.METHOD_IESH else None)
+    for n in (2, 4):
+        e.run(n)
+    e.get_state(); e.diagnostics(); e.observable_per_trajectory(A.OBS_TOTAL_ENERGY); e.close()
+    print("ok ring-polymer iesh", method, M, B)
+from test_termination import _ring_scatter_setup, _drive
+for B in (4, 10):
+    kw, r, v, rho, draws, sdraw = _ring_scatter_setup(70, B, 900, save_every=5)
+    e = Engine(*A.make_config(**kw))
+    _drive(e, r, v, rho, draws, sdraw, (-4.5, 4.0), 900, (300, 600))
+    assert (e.termination() >= 0).any()
+    e.observable_per_trajectory(A.OBS_POSITION); e.close()
+    print("ok ring termination", B)
+if os.environ.get("NQCB200_RING_LPT") is None:
+    import subprocess
+    env = dict(os.environ, NQCB200_RING_LPT="4", NQCB200_SANITIZE_LANES_ONLY="1")
+    code = ("import sys; sys.path[:0]=[%r, %r, %r]; import numpy as np; import nqcdynamics_jl_b200 as nq; from nqcdynamics_jl_b200 import workloads; "
+            "from nqcdynamics_jl_b200.engine import Engine; A=nq._abi; wl=workloads.get('rpsh_morse3_16'); T=150; "
+            "e=Engine(*A.make_config(**wl.config_kwargs(T, seed=3, nsave=12//wl.save_every+1, per_trajectory=1))); ic=wl.sample(np.random.default_rng(0),T); "
+            "e.run_from_host(ic['r'], ic['v'], wl.initial_density(T), diabatic=True, nsteps=6); e.run(6); e.get_state(); e.close(); print('ok lanes')"
+            % (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "oracle")))
+    subprocess.run([sys.executable, "-c", code], env=env, check=True)
