@@ -717,6 +717,14 @@ int nqcb200_create(const nqcb200_config* cfg, nqcb200_handle** out) {
             h->err = "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) for the step kernel"; cudaGetLastError(); return fail(NQCB200_ERR_CUDA);
         }
     }
+    {
+        // the TerminatingCallback instantiation launches with the step kernel's shape or with its own
+        const size_t term_smem = ks.term_block > 0 ? ks.term_smem : (ks.step_term_step_shape ? ks.step_smem : 0);
+        if (ks.step_term && term_smem > 48 * 1024 &&
+            cudaFuncSetAttribute((const void*)ks.step_term, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)term_smem) != cudaSuccess) {
+            h->err = "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) for the terminating step kernel"; cudaGetLastError(); return fail(NQCB200_ERR_CUDA);
+        }
+    }
     if (iesh) {
         if ((rc = dev_alloc(h, &kp.iesh_lam, (size_t)n * T)) != 0) return fail(rc);
         if ((rc = dev_alloc(h, &kp.iesh_sgn, (size_t)n * T)) != 0) return fail(rc);
@@ -944,9 +952,12 @@ int nqcb200_run(nqcb200_handle* h, int64_t nsteps) {
         if (term && !h->ks.step_term_step_shape) {   // TerminatingCallback instantiation (same launch shape as the init kernel's)
             h->ks.step_term<<<grid_for(h), h->ks.block, h->ks.dyn_smem, h->stream>>>(h->kp); ++h->launches_total;
         } else if (h->ks.step_block > 0) {
-            const int64_t threads = h->cfg.ntraj * h->ks.step_L;
-            const unsigned grid = (unsigned)std::max<int64_t>(1, (threads + h->ks.step_block - 1) / h->ks.step_block);
-            (term ? h->ks.step_term : h->ks.step)<<<grid, h->ks.step_block, h->ks.step_smem, h->stream>>>(h->kp);
+            const bool own = term && h->ks.term_block > 0;      // the TERM instantiation has its own launch shape
+            const int L = own ? h->ks.term_L : h->ks.step_L, blk = own ? h->ks.term_block : h->ks.step_block;
+            const size_t smem = own ? h->ks.term_smem : h->ks.step_smem;
+            const int64_t threads = h->cfg.ntraj * L;
+            const unsigned grid = (unsigned)std::max<int64_t>(1, (threads + blk - 1) / blk);
+            (term ? h->ks.step_term : h->ks.step)<<<grid, blk, smem, h->stream>>>(h->kp);
             ++h->launches_total;
         } else { h->ks.step<<<grid_for(h), h->ks.block, h->ks.dyn_smem, h->stream>>>(h->kp); ++h->launches_total; }
         NQ_CUDA(h, cudaGetLastError());

@@ -26,7 +26,8 @@ constexpr int kRpshMaxThreads = 384;   // ring_tpt_step_kernel: ONE block per SM
 // fft: nbeads is a power of two (compile-time NBT); otherwise the dense normal-mode product through two scratch rows
 // threads = trajectory slots per block (block size / lanes per trajectory); lanes > 1 adds the [bead][N] energy scratch
 NQ_HD constexpr size_t ring_tpt_smem_bytes(int N, int NB, bool ehrenfest, bool fft, int threads = kRtThreads, bool lanes = false) {
-    return ((size_t)(3 + (ehrenfest ? N * N : 0) + (fft ? 0 : 2) + (lanes ? N : 0)) * NB * threads + (fft ? 6 * NB : NB * NB + 4 * NB)) * sizeof(double);
+    return ((size_t)(3 + (ehrenfest ? N * N : 0) + (fft ? 0 : 2) + (lanes ? N : 0)) * NB * threads + (lanes ? threads : 0) +
+            (fft ? 6 * NB : NB * NB + 4 * NB)) * sizeof(double);
 }
 
 // Block size of ring_tpt_step_kernel for a batch of ntraj trajectories on `sms` SMs: the kernel runs one block per SM and
@@ -229,12 +230,15 @@ NQ_D void rt_record_save(const KParams& p, Emitter& em, int NB, const double* s_
 // TERM: TerminatingCallback instantiation (nqcb200_set_termination): the position-window predicate on the CENTROID of the
 // chosen dof (and its centroid velocity for the `outgoing` clause), tested after the hopping callback on the new u
 // (callbacks.jl:29); a terminated trajectory skips the step body but keeps taking part in the barriers and save points.
-// LPT > 1 (FSSH, register FFT, no TERM): LPT lanes share a trajectory -- each visits NBT / LPT beads (the bead loop is
-// ~55 % of a step) while the free ring-polymer step, the centroid eigenproblem, Tsit5 and the hop test run redundantly on
-// all of them (same inputs, same bits).  Selected by the host when a shard holds fewer trajectories than one wave of
-// threads (BASELINE config 5 on 8 GPUs: 12 500 trajectories per GPU), where a thread-per-trajectory launch leaves most
-// of every SM empty and runs at the latency of one dependent chain.  Bead sums are taken in bead order from shared
-// memory, so the result does not depend on LPT (sharding independence holds bit for bit).
+// LPT > 1 (FSSH, register FFT, no TERM): warp-specialised phases for shards smaller than one wave of threads (BASELINE
+// config 5 on 8 GPUs: 12 500 trajectories per GPU), where a thread-per-trajectory launch leaves most of every SM empty and
+// runs at the latency of one dependent chain.  The block holds KS = blockDim / LPT trajectories; thread t works for
+// trajectory t % KS as member t / KS of its group, so the OWNERS (member 0) fill the first KS / 32 warps.  Per step:
+// owners run the free ring-polymer step; barrier; ALL warps visit bead pairs (member g the beads [g NB/LPT, (g+1) NB/LPT),
+// the bead loop is ~55 % of a step); barrier; owners take the bead sums in bead order from shared memory and run the
+// centroid eigenproblem, Tsit5 and the hop test while the helper warps wait at the next barrier (whole warps: no issue
+// slots).  A first version with the LPT members on adjacent lanes repeating the owner's work was slower than one lane
+// (profiles/r02/SUMMARY.md).  Same bead pairs and the same summation order as LPT = 1: results do not depend on LPT.
 template <class M, int NBT, int METHOD, bool TERM = false, int LPT = 1>
 __global__ void __launch_bounds__(kRpshMaxThreads, 1) ring_tpt_step_kernel(const __grid_constant__ KParams p) {
     constexpr int N = M::NS;
@@ -255,10 +259,11 @@ __global__ void __launch_bounds__(kRpshMaxThreads, 1) ring_tpt_step_kernel(const
     double* s_Z = s_a + NB * KSd;                      // EHR only: [bead][N*N][thread]
     double* s_t = s_Z + (EHR ? N * N * NB * KSd : 0);   // dense only: two scratch rows [2][bead][thread]
     double* s_w = s_t + (FFT ? 0 : 2 * NB * KSd);       // LANES only: per-bead adiabatic energies of a saving step [bead][N][slot]
-    double* s_tab = s_w + (LANES ? NB * N * KSd : 0);   // FFT: twr[NB/2] twi[NB/2] al[2NB] be[2NB]; dense: U[NB*NB] cay[4NB]
+    int* s_st = reinterpret_cast<int*>(s_w + (LANES ? NB * N * KSd : 0));     // LANES only: occupied state per trajectory (owner -> helpers)
+    double* s_tab = s_w + (LANES ? NB * N * KSd + KSd : 0);   // FFT: twr[NB/2] twi[NB/2] al[2NB] be[2NB]; dense: U[NB*NB] cay[4NB]
     const int tid = threadIdx.x;
     const int KS = KT / LPT;                // trajectories per block
-    const int slot = tid / LPT, sub = tid % LPT;
+    const int slot = LANES ? tid % KS : tid, sub = LANES ? tid / KS : 0;
     int64_t traj = (int64_t)blockIdx.x * KS + slot;
     const bool valid = traj < p.ntraj;
     if (!valid) traj = p.ntraj - 1;
@@ -303,6 +308,7 @@ __global__ void __launch_bounds__(kRpshMaxThreads, 1) ring_tpt_step_kernel(const
             if (k > j) s.y[aidx(N, j, k)] = p.sig_im[(int64_t)(j + N * k) * T + traj];
         }
     int st = p.state ? p.state[traj] : 0;
+    if (LANES && sub == 0) s_st[slot] = st;
     double Zc[N][N];
 #pragma unroll
     for (int j = 0; j < N; ++j)
@@ -316,7 +322,7 @@ __global__ void __launch_bounds__(kRpshMaxThreads, 1) ring_tpt_step_kernel(const
 #pragma unroll
         for (int k = j + 1; k < N; ++k) cur.g[aidx(N, j, k)] = p.ecur[(int64_t)(N + j + N * k) * T + traj];
 
-    Eig<N> ec;
+    Eig<N> ec = {};
     double Ac[sym_size(N)];
     unsigned long long nhops = 0, nfrus = 0;
     const double dt = p.dt, hdt = 0.5 * p.dt;
@@ -352,20 +358,17 @@ __global__ void __launch_bounds__(kRpshMaxThreads, 1) ring_tpt_step_kernel(const
         __syncthreads();
         if (!TERM || term_step < 0) {
         // B (half kick) + C (free ring polymer)  bcb_electronics.jl:62-71
-        if constexpr (FFT) {
+        if (FFT && (!LANES || sub == 0)) {
             double zr[NBF], zi[NBF];
 #pragma unroll
             for (int b = 0; b < NBF; ++b) {
                 zr[b] = s_r[b * KS + slot];
                 zi[b] = fma(hdt, s_a[b * KS + slot], s_v[b * KS + slot]);
             }
-            if (LANES) __syncwarp();       // every lane of the trajectory has read the old beads
             rt_free_step<NBF>(tb, zr, zi);
 #pragma unroll
-            for (int b = 0; b < NBF; ++b)
-                if (!LANES || b % LPT == sub) { s_r[b * KS + slot] = zr[b]; s_v[b * KS + slot] = zi[b]; }
-            if (LANES) __syncwarp();
-        } else {
+            for (int b = 0; b < NBF; ++b) { s_r[b * KS + slot] = zr[b]; s_v[b * KS + slot] = zi[b]; }
+        } else if (!FFT) {
             // dense U' .. Cayley .. U (RingPolymerArrays transform!, steps.jl:10-17)
             const double* U = s_tab;
             const double* cay = s_tab + NB * NB;
@@ -391,6 +394,7 @@ __global__ void __launch_bounds__(kRpshMaxThreads, 1) ring_tpt_step_kernel(const
                 s_v[j * KS + slot] = c;
             }
         }
+        if (LANES) { __syncthreads(); st = s_st[slot]; }      // the owners' beads and occupied state for every member
         // update_cache! on every bead (bcb_electronics.jl:73), force, second half kick
         double rsum = 0.0, vsum = 0.0;
 #pragma unroll
@@ -462,7 +466,7 @@ __global__ void __launch_bounds__(kRpshMaxThreads, 1) ring_tpt_step_kernel(const
                 }
             }
             if (LANES) {       // bead sums in bead order (the order of the single-lane kernel), from shared memory
-                __syncwarp();
+                __syncthreads();
                 for (int b = 0; b < NB; ++b) { rsum += s_r[b * KS + slot]; vsum += s_v[b * KS + slot]; }
                 if (saving) {
                     for (int b = 0; b < NB; ++b)
@@ -500,6 +504,7 @@ __global__ void __launch_bounds__(kRpshMaxThreads, 1) ring_tpt_step_kernel(const
             rsum += q; vsum += vb;
         }
         }
+        if (!LANES || sub == 0) {          // LANES: the owner warps; the helper warps go on to the next barrier
         const double rcent = rsum / NB, vcent = vsum / NB;
         eval_point<M>(p, rcent, Zc, ec, Ac);
         ElecParams<N> nxt;
@@ -556,10 +561,10 @@ __global__ void __launch_bounds__(kRpshMaxThreads, 1) ring_tpt_step_kernel(const
                     }
                 }
                 if (dv != 0.0) {
-                    for (int b = sub; b < NB; b += LPT) s_v[b * KS + slot] += dv;
+                    for (int b = 0; b < NB; ++b) s_v[b * KS + slot] += dv;
                     dv_hop = dv;
                 }
-                if (accept) { st = new_state; nhops += (valid && sub == 0); }
+                if (accept) { st = new_state; nhops += (valid && sub == 0); if (LANES) s_st[slot] = st; }
             }
         }
         cur = nxt;
@@ -568,6 +573,7 @@ __global__ void __launch_bounds__(kRpshMaxThreads, 1) ring_tpt_step_kernel(const
             const bool og = p.term_outgoing != 0;
             if ((rcent < p.term_lo && (!og || vx < 0.0)) || (rcent > p.term_hi && (!og || vx > 0.0)) || p.t0 + dt * (double)(step + 1) > p.term_tcut)
                 term_step = step + 1;
+        }
         }
         }
 
@@ -579,16 +585,15 @@ __global__ void __launch_bounds__(kRpshMaxThreads, 1) ring_tpt_step_kernel(const
 #pragma unroll
                     for (int i = 0; i < N; ++i) pot += s.x[sidx(N, i, i)] * wsum[i];
                 } else pot = select<N>(wsum, st);
-                if (LANES) __syncwarp();      // the hop's velocity change on the other lanes' beads
                 Emitter em{p, traj, valid && sub == 0, (int)isave, red, 0, true, KT / 32};
                 rt_record_save<N, METHOD>(p, em, NB, s_r, s_v, KS, slot, s, st, ec, pot, mass);
             }
         }
     }
 
-    if (LANES) __syncwarp();
-    if (valid) {
-        for (int b = sub; b < NB; b += LPT) {
+    if (LANES) __syncthreads();
+    if (valid && sub == 0) {
+        for (int b = 0; b < NB; ++b) {
             p.r[(int64_t)b * T + traj] = s_r[b * KS + slot];
             p.v[(int64_t)b * T + traj] = s_v[b * KS + slot];
             p.acc[(int64_t)b * T + traj] = s_a[b * KS + slot];

@@ -15,6 +15,8 @@ struct KernelSet {
     InitFn init = nullptr;
     StepFn step_term = nullptr;   // TerminatingCallback instantiation of `step` (nqcb200_set_termination), if any
     bool step_term_step_shape = false;   // step_term launches with the STEP kernel's shape (step_block / step_smem) instead of the init kernel's
+    int term_L = 0, term_block = 0;       // ... or with its own shape when the step kernel's differs (warp-specialised ring-polymer variant)
+    size_t term_smem = 0;
     int L = 1;              // lanes (threads) per trajectory
     int DPL = 1;            // nuclear dofs per lane
     int block = kBlockThreads;

@@ -33,24 +33,29 @@ bool pick(int method, int64_t ntraj, KernelSet& out, const char* name) {
     const char* env = getenv("NQCB200_RING_TPT");
     const bool want = !(env && atoi(env) == 0);
     const bool ehr = (method == NQCB200_METHOD_EHRENFEST);
-    // Lanes per trajectory (kernel_ring_tpt.cuh, LPT): built for shards smaller than one wave of threads (BASELINE config
-    // 5 on 8 GPUs is 12 500 trajectories per GPU) and MEASURED SLOWER there -- 12 500 trajectories x 3000 steps: 59 ms with
-    // one lane, 62 ms with two, 70 ms with four (profiles/r02/SUMMARY.md): the centroid chain / Tsit5 / hop test that every
-    // lane repeats costs more issue slots than the split bead loop saves.  Kept as a documented A/B switch
-    // (NQCB200_RING_LPT=2|4, parity-tested), never selected automatically.
+    // Shards smaller than one wave of threads (strong scaling: BASELINE config 5 is 12 500 trajectories per GPU on 8 GPUs):
+    // warp-specialised phases, LPT members per trajectory (kernel_ring_tpt.cuh).  NQCB200_RING_LPT=1|2|4 overrides (A/B).
     if constexpr (NB >= 8) {
         if (want && !ehr) {
             int sms = 148;
             if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, t_device) != cudaSuccess || sms <= 0) sms = 148;
             const char* force = getenv("NQCB200_RING_LPT");
-            const int lpt = force ? atoi(force) : 1;
+            const int64_t per_sm = (std::max<int64_t>(ntraj, 1) + sms - 1) / sms;
+            const int lpt = force ? atoi(force) : (per_sm <= 96 ? 4 : (per_sm <= 192 ? 2 : 1));
             if (lpt == 4 || lpt == 2) {
-                const int block = ring_tpt_block_threads(std::max<int64_t>(ntraj, 1) * lpt, sms, kRpshMaxThreads);
+                const int ks = (int)std::min<int64_t>(kRpshMaxThreads / lpt, 32 * ((per_sm + 31) / 32));     // owners fill whole warps
                 if (lpt == 4) out.step = ring_tpt_step_kernel<M, NB, NQCB200_METHOD_FSSH, false, 4>;
                 else out.step = ring_tpt_step_kernel<M, NB, NQCB200_METHOD_FSSH, false, 2>;
-                out.step_L = lpt; out.step_block = block;
-                out.step_smem = ring_tpt_smem_bytes(M::NS, NB, false, true, block / lpt, true);
-                return true;        // no TERM instantiation with lanes: nqcb200_set_termination reports UNSUPPORTED
+                out.step_L = lpt; out.step_block = ks * lpt;
+                out.step_smem = ring_tpt_smem_bytes(M::NS, NB, false, true, ks, true);
+                // TerminatingCallback: the thread-per-trajectory TERM instantiation with its own launch shape
+                const int tthreads = tpt_threads(M::NS, NB, false, true, ntraj);
+                if (tthreads > 0) {
+                    out.step_term = ring_tpt_step_kernel<M, NB, NQCB200_METHOD_FSSH, true>;
+                    out.term_L = 1; out.term_block = tthreads; out.term_smem = ring_tpt_smem_bytes(M::NS, NB, false, true, tthreads);
+                    out.step_term_step_shape = true;
+                }
+                return true;
             }
         }
     }

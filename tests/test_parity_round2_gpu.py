@@ -376,3 +376,45 @@ def test_iesh_erpenbeck_thoss_energy_conservation():
     assert np.max(np.abs(x - x[:, :1])) > 0.5                       # the trajectories actually move
     kin0 = 0.5 * 2000.0 * v * v
     assert np.max(np.abs(E - E[:, :1])) < 5e-4 * np.max(kin0)       # velocity Verlet at dt = 1: 9e-7 on a kinetic energy of 0.009 (oracle: same)
+
+
+@pytest.mark.parametrize("nbeads", [8, 16])
+def test_rpsh_launch_shapes_agree_bit_for_bit(nbeads, monkeypatch):
+    """ring_tpt_step_kernel: thread per trajectory (LPT = 1) and the warp-specialised variants the engine selects for shards
+    smaller than one wave (LPT = 2, 4: owner warps + helper warps over the bead pairs) visit the same bead pairs and take the
+    bead sums in the same order -- identical results, so a run does not depend on how it was sharded; parity with the oracle
+    for every shape."""
+    from nqcdynamics_jl_b200.engine import Engine
+    import oracle
+    T, nsteps = 70, 600
+    rng = np.random.default_rng(41)
+    model = nq.TullyModelOne()          # scattering through the crossing: hops, frustrated hops, the rescaling on every bead
+    mass, temp = 2000.0, 1e-3
+    kw = model_config(model, method=A.METHOD_FSSH, masses=[mass], ntraj=T, dt=1.0, nbeads=nbeads, temperature=temp, rng=A.RNG_INJECTED,
+                      diagnostics=1, save_every=50, nsave=nsteps // 50 + 1, observables=ALL_POP_OBS, per_trajectory=1)
+    r = -3.0 + 0.5 * rng.standard_normal((T, 1)) + 0.05 * rng.standard_normal((T, nbeads))
+    v = (6.0 + 14.0 * rng.random((T, 1))) / mass + np.sqrt(temp * nbeads / mass) * 0.2 * rng.standard_normal((T, nbeads))
+    rho = np.zeros((T, 2, 2)); rho[:, 0, 0] = 1.0
+    draws = rng.random((nsteps, T)); sdraw = rng.random(T)
+    outs = {}
+    for lpt in ("1", "2", "4"):
+        monkeypatch.setenv("NQCB200_RING_LPT", lpt)
+        e = Engine(*A.make_config(**kw))
+        e.set_state_diabatic(r, v, rho, None, None, sdraw); e.set_draws(draws)
+        for n in (7, 593):
+            e.run(n)
+        outs[lpt] = (e.get_state(), e.observable_per_trajectory(A.OBS_TOTAL_ENERGY), e.observable_sum(A.OBS_POPCORR_DIABATIC), e.counters())
+        e.close()
+    monkeypatch.delenv("NQCB200_RING_LPT")
+    o = oracle.OracleEngine(*A.make_config(**kw))
+    o.set_state_diabatic(r, v, rho, None, None, sdraw); o.set_draws(draws)
+    o.run(nsteps)
+    so = o.get_state()
+    for lpt, (st, E, pc, cnt) in outs.items():
+        for key in ("r", "v", "sigma", "state"):
+            assert np.array_equal(st[key], outs["1"][0][key]), (lpt, key)
+        assert np.array_equal(E, outs["1"][1]) and cnt == outs["1"][3]
+        assert np.max(np.abs(pc - outs["1"][2])) < 1e-12 * T            # block sums in a different order
+        assert rel_err(st["r"], so["r"]) < 1e-9 and rel_err(st["v"], so["v"]) < 1e-9
+        assert np.array_equal(st["state"], so["state"])
+    assert outs["1"][3]["hops"] == o.counters()["hops"] > 0
