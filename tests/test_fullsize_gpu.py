@@ -85,6 +85,29 @@ def test_rpsh_population_conservation_full_size():
     assert e.counters()["nonfinite"] == 0
 
 
+def test_rpsh_one_eighth_shard_matches_thread_per_trajectory(monkeypatch):
+    """configs[4] as one of 8 GPUs sees it (12 500 trajectories, less than one wave of threads): the engine selects the
+    warp-specialised launch shape; hop counts and the correlation function equal those of the thread-per-trajectory shape."""
+    wl = workloads.get("rpsh_morse3_16")
+    T, nsteps = 12_500, 1500
+    ic = wl.sample(np.random.default_rng(6), T)
+    ns = nsteps // wl.save_every + 1
+    res = []
+    for lpt in (None, "1"):
+        if lpt is None:
+            monkeypatch.delenv("NQCB200_RING_LPT", raising=False)
+        else:
+            monkeypatch.setenv("NQCB200_RING_LPT", lpt)
+        e = _run(wl, T, nsteps, ic=ic)
+        res.append((e.observable_sum(A.OBS_POPCORR_DIABATIC)[:ns].copy(), e.counters(), e.get_state()))
+    (ca, na, sa), (cb, nb, sb) = res
+    assert na == nb and na["hops"] > 0 and na["nonfinite"] == 0
+    for key in ("r", "v", "sigma", "state"):
+        assert np.array_equal(sa[key], sb[key]), key
+    assert np.max(np.abs(ca - cb)) < 1e-9 * T
+    assert np.max(np.abs(ca.reshape(ns, 3, 3).sum(axis=(1, 2)) - T)) < 1e-6 * T
+
+
 def test_tully_scattering_with_termination_full_size():
     """configs[0] the way the reference's scattering scripts run it: TerminatingCallback once the particle has left the
     interaction region.  The scattering probabilities are those of the run to the end of tspan (beyond r = 4 the
