@@ -42,8 +42,13 @@ bool pick(int method, int64_t ntraj, KernelSet& out, const char* name) {
             const char* force = getenv("NQCB200_RING_LPT");
             const int64_t per_sm = (std::max<int64_t>(ntraj, 1) + sms - 1) / sms;
             const int lpt = force ? atoi(force) : (per_sm <= 96 ? 4 : (per_sm <= 192 ? 2 : 1));
+            int ks = 0;
             if (lpt == 4 || lpt == 2) {
-                const int ks = (int)std::min<int64_t>(kRpshMaxThreads / lpt, 32 * ((per_sm + 31) / 32));     // owners fill whole warps
+                ks = (int)std::min<int64_t>(kRpshMaxThreads / lpt, 32 * ((per_sm + 31) / 32));     // owners fill whole warps
+                while (ks > 32 && ring_tpt_smem_bytes(M::NS, NB, false, true, ks, true) > 200 * 1024) ks -= 32;   // 32 beads x 192 owners do not fit
+                if (ring_tpt_smem_bytes(M::NS, NB, false, true, ks, true) > 200 * 1024) ks = 0;
+            }
+            if (ks > 0) {
                 if (lpt == 4) out.step = ring_tpt_step_kernel<M, NB, NQCB200_METHOD_FSSH, false, 4>;
                 else out.step = ring_tpt_step_kernel<M, NB, NQCB200_METHOD_FSSH, false, 2>;
                 out.step_L = lpt; out.step_block = ks * lpt;

@@ -418,3 +418,33 @@ def test_rpsh_launch_shapes_agree_bit_for_bit(nbeads, monkeypatch):
         assert rel_err(st["r"], so["r"]) < 1e-9 and rel_err(st["v"], so["v"]) < 1e-9
         assert np.array_equal(st["state"], so["state"])
     assert outs["1"][3]["hops"] == o.counters()["hops"] > 0
+
+
+def test_rpsh_32_beads_mid_size_shard(monkeypatch):
+    """150 trajectories per SM with 32 beads: the two-member warp-specialised shape is selected and its owner count is cut
+    to what shared memory holds (128 owners x 32 beads x 6 arrays = 198 KB); same bits as thread per trajectory."""
+    from nqcdynamics_jl_b200.engine import Engine
+    T, nsteps, B = 148 * 150, 12, 32
+    rng = np.random.default_rng(43)
+    model = nq.TullyModelOne()
+    kw = model_config(model, method=A.METHOD_FSSH, masses=[2000.0], ntraj=T, dt=1.0, nbeads=B, temperature=1e-3, seed=17,
+                      save_every=4, nsave=nsteps // 4 + 1, observables=(1 << A.OBS_POPCORR_DIABATIC) | (1 << A.OBS_TOTAL_ENERGY))
+    r = -1.0 + 0.5 * rng.standard_normal((T, 1)) + 0.05 * rng.standard_normal((T, B))
+    v = 12.0 / 2000.0 + np.sqrt(1e-3 * B / 2000.0) * 0.2 * rng.standard_normal((T, B))
+    rho = np.zeros((T, 2, 2)); rho[:, 0, 0] = 1.0
+    outs = []
+    for lpt in (None, "1"):
+        if lpt is None:
+            monkeypatch.delenv("NQCB200_RING_LPT", raising=False)
+        else:
+            monkeypatch.setenv("NQCB200_RING_LPT", lpt)
+        e = Engine(*A.make_config(**kw))
+        e.set_state_diabatic(r, v, rho)
+        e.run(nsteps)
+        outs.append((e.get_state(), e.observable_sum(A.OBS_TOTAL_ENERGY), e.counters()))
+        e.close()
+    (sa, ea, ca), (sb, eb, cb) = outs
+    assert ca == cb and ca["nonfinite"] == 0
+    for key in ("r", "v", "sigma", "state"):
+        assert np.array_equal(sa[key], sb[key]), key
+    assert np.max(np.abs(ea - eb)) <= 1e-9 * np.max(np.abs(eb))
