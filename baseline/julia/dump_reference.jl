@@ -199,6 +199,27 @@ function main(outdir)
                          "nelectrons" => NQCModels.nelectrons(am)))
     end
 
+    # ---- RPIESH / RP-EhrenfestNA with BCBWavefunction (test/Dynamics/rpiesh.jl:11-22, rp_ehrenfest_na.jl:10-31) ------------
+    # These pin quirk Q5 (propagate_wavefunction!(.., vprev, rprev, ..), bcb_wavefunction.jl:67) and the bead-sum force.  The
+    # replay takes no gauge reference for them: tests/julia_golden.py moves the dump into the identity-continuity gauge.
+    # RP-EhrenfestNA contracts bead-basis derivatives with centroid-basis psi (rpehrenfest_na.jl:20-28), so its force depends
+    # on the column signs LAPACK gives each bead at t0; a disagreement there is that dependence, not a propagation error.
+    for (tag, Meth) in (("rpiesh", AdiabaticIESH), ("rp_ehrenfest_na", EhrenfestNA))
+        M, B, T = 30, 4, 9.5e-4
+        am = AndersonHolstein(MiaoSubotnik(; Γ), TrapezoidalRule(M, -3Γ, 3Γ))
+        sim = RingPolymerSimulation{Meth}(Atoms(2000), am, B; temperature = T)
+        u0s = [begin
+                   r = (8.0 + 10.0 * rand()) .+ 0.5 .* randn(1, 1, B); v = -abs(randn()) * 2e-3 .+ 1e-4 .* randn(1, 1, B)
+                   NQCCalculators.update_cache!(sim.cache, r)
+                   DynamicsVariables(sim, v, r)
+               end for _ in 1:4]
+        imp = am.impurity_model
+        dump(outdir, "RP_$(tag)_miao_subotnik_m$(M)_b$(B)", sim, (0.0, 200.0), 5.0, u0s;
+             meta = Dict("model_params" => Dict("m" => imp.m, "omega" => imp.ω, "g" => imp.g, "DeltaG" => imp.ΔG, "Gamma" => Γ,
+                                                "eps" => flat(am.bath.bathstates), "V" => flat(am.bath.bathcoupling) .* sqrt(Γ / 2π)),
+                         "nelectrons" => NQCModels.nelectrons(am), "nbeads" => B, "temperature" => T))
+    end
+
     # ---- C5: RPSH, 16 beads, ThreeStateMorse (docs/src/dynamicssimulations/dynamicsmethods/rpsh.md:40-68) -----------
     T = 9.5e-4
     tm = ThreeStateMorse()

@@ -67,6 +67,35 @@ def config_kwargs(doc, **extra):
     return kw
 
 
+def _ring_polymer_wavefunction(doc):
+    size = doc["size"]
+    return doc["method"] in ("AdiabaticIESH", "EhrenfestNA") and int(doc.get("nbeads", size[2] if len(size) > 2 else 1)) > 1
+
+
+def canonical_gauge(doc):
+    """Ring-polymer AdiabaticIESH / EhrenfestNA dumps: the engine takes no gauge reference there (its arrowhead solver uses
+    continuity with the identity for every geometry), so the DUMP is moved into that gauge instead -- column i of the
+    centroid eigenvectors is flipped when Z[i, i] < 0 at t0, together with row i of psi and row / column i of the couplings,
+    in every frame (both sides then follow sign continuity in time).  Returns a transformed copy."""
+    import copy
+    doc = copy.deepcopy(doc)
+    n = int(doc["nstates"])
+    for tr in doc["trajectories"]:
+        Z0 = np.asarray(tr["t0"]["Z"], dtype=np.float64).reshape(n, n)          # [col][row]
+        sgn = np.where(np.diagonal(Z0) < 0.0, -1.0, 1.0)
+        for snap in [tr["t0"]] + tr["steps"]:
+            if "Z" in snap:
+                snap["Z"] = (np.asarray(snap["Z"], dtype=np.float64).reshape(n, n) * sgn[:, None]).reshape(-1).tolist()
+            for key in ("sigma_re", "sigma_im"):
+                if key in snap:
+                    a = np.asarray(snap[key], dtype=np.float64).reshape(-1, n)         # [electron][row]
+                    snap[key] = (a * sgn[None, :]).reshape(-1).tolist()
+            if "nac" in snap:
+                d = np.asarray(snap["nac"], dtype=np.float64).reshape(-1, n, n)       # [dof][col][row]
+                snap["nac"] = (d * sgn[None, :, None] * sgn[None, None, :]).reshape(-1).tolist()
+    return doc
+
+
 def _field(doc, key, where):
     """Stack one SNAP field over trajectories: where = 't0' or a step index."""
     rows = []
@@ -82,7 +111,9 @@ def upload_initial_state(h, doc):
     """The dumped t0 frame -> nqcb200_set_gauge_reference + nqcb200_set_state (+ set_mapping, set_draws)."""
     T = len(doc["trajectories"])
     Zb, Z = _field(doc, "Z_beads", "t0"), _field(doc, "Z", "t0")
-    if Zb is not None and Z is not None:            # ring polymer: per bead, then the centroid
+    if _ring_polymer_wavefunction(doc):
+        pass                                        # identity continuity; the dump was moved into that gauge (canonical_gauge)
+    elif Zb is not None and Z is not None:          # ring polymer: per bead, then the centroid
         h.set_gauge_reference(np.concatenate([Zb, Z], axis=1), h.B + 1)
     elif Z is not None:
         h.set_gauge_reference(Z, 1)
@@ -119,6 +150,8 @@ def _snapshot(h, doc):
 
 def compare(h, doc, tol=1e-10, stride=1):
     """Step ``h`` through the dump and return the worst relative deviation per field; raises on a hop mismatch."""
+    if _ring_polymer_wavefunction(doc):
+        doc = canonical_gauge(doc)
     upload_initial_state(h, doc)
     worst = {}
 

@@ -96,3 +96,50 @@ def test_engine_replays_oracle_dump(tmp_path):
     path, _ = _selftest_dump(str(tmp_path), _tully_header(), 300, 6, 5, -1.5, 9.0 / 2000, 2)
     doc = jg.load(path)
     jg.compare(_handle(engine_factory(), doc), doc, TOL)
+
+
+# ---- ring-polymer AdiabaticIESH / EhrenfestNA dumps (BCBWavefunction): no gauge reference, the dump is canonicalised ----
+def _rpiesh_selftest(tmp_path, method, seed):
+    M, B, T, nsteps = 30, 4, 3, 24
+    model = nq.AndersonHolstein(nq.MiaoSubotnik(Γ=6.4e-3), nq.TrapezoidalRule(M, -0.0192, 0.0192))
+    n, ne = model.nstates, model.nelectrons
+    header = {"config": f"selftest_rp_{method}", "method": method, "model": "AndersonHolstein",
+              "model_params": {"m": 2000.0, "omega": 2e-4, "g": 20.6097, "DeltaG": -3.8e-3, "Gamma": 6.4e-3,
+                               "eps": np.asarray(model.bath_a).tolist(), "V": np.asarray(model.bath_b).tolist()},
+              "masses": [2000.0], "size": [1, 1, B], "nbeads": B, "temperature": 9.5e-4, "dt": 5.0, "t0": 0.0, "nstates": n,
+              "nelectrons": ne, "rescaling": "standard"}
+    imp = nq.MiaoSubotnik(Γ=6.4e-3)
+    header["model_params"].update(m=imp.m, omega=imp.ω, g=imp.g, DeltaG=imp.ΔG)
+    rng = np.random.default_rng(seed)
+    doc0 = dict(header, nsteps=nsteps, trajectories=[{}] * T)
+    h = _handle(oracle_factory(), doc0)
+    r = 10.0 + rng.standard_normal((T, B)); v = -3e-3 + 1e-4 * rng.standard_normal((T, B))
+    psi = np.zeros((T, ne, n)); psi[:, np.arange(ne), np.arange(ne)] = 1.0
+    state = np.tile(np.arange(1, ne + 1, dtype=np.int32), (T, 1)) if method == "AdiabaticIESH" else None
+    draws = rng.random((nsteps, T)) * 0.05 if method == "AdiabaticIESH" else None
+    path = os.path.join(tmp_path, f"dump_{method}.json")
+    jg.write_dump(path, h, header, r, v, psi, None, state, draws, nsteps)
+    doc = jg.load(path)
+    # what LAPACK may do: arbitrary column signs of the centroid eigenvectors at t0 (kept by continuity afterwards)
+    flip = np.where(rng.random(n) < 0.4, -1.0, 1.0)
+    for tr in doc["trajectories"]:
+        for snap in [tr["t0"]] + tr["steps"]:
+            snap["Z"] = (np.asarray(snap["Z"]).reshape(n, n) * flip[:, None]).reshape(-1).tolist()
+            for key in ("sigma_re", "sigma_im"):
+                snap[key] = (np.asarray(snap[key]).reshape(-1, n) * flip[None, :]).reshape(-1).tolist()
+            snap["nac"] = (np.asarray(snap["nac"]).reshape(-1, n, n) * flip[None, :, None] * flip[None, None, :]).reshape(-1).tolist()
+    return doc
+
+
+@pytest.mark.parametrize("method", ["AdiabaticIESH", "EhrenfestNA"])
+def test_harness_replays_ring_polymer_wavefunction_dump(tmp_path, method):
+    doc = _rpiesh_selftest(str(tmp_path), method, 7)
+    worst = jg.compare(_handle(oracle_factory(), doc), doc, TOL)
+    assert set(worst) >= {"r", "v", "sigma_re", "sigma_im", "w", "Z", "nac", "accel"} and max(worst.values()) < 1e-12
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("method", ["AdiabaticIESH", "EhrenfestNA"])
+def test_engine_replays_ring_polymer_wavefunction_dump(tmp_path, method):
+    doc = _rpiesh_selftest(str(tmp_path), method, 8)
+    jg.compare(_handle(engine_factory(), doc), doc, TOL)
