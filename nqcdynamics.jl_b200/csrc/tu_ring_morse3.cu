@@ -1,0 +1,9 @@
+// tu_ring_morse3.cu -- ring-polymer FSSH / Ehrenfest kernels for one model (see ring_select.cuh).
+#include "ring_select.cuh"
+
+namespace nq {
+bool select_ring_morse3(const nqcb200_config& c, KernelSet& out) {
+    t_device = c.device;
+    return pick_beads<ModelT<NQCB200_MODEL_THREE_STATE_MORSE>>(c.method, c.nbeads, c.ntraj, out, "rp_morse3");
+}
+}  // namespace nq
